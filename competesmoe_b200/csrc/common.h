@@ -1,0 +1,117 @@
+// Shared host-side helpers for the C-ABI translation units.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+
+#include "csmoe.h"
+
+namespace csmoe {
+
+void set_error(const char* fmt, ...);
+int num_sms();
+
+#define CSMOE_CHECK_ARG(cond, ...)       \
+  do {                                   \
+    if (!(cond)) {                       \
+      ::csmoe::set_error(__VA_ARGS__);   \
+      return CSMOE_ERR_ARG;              \
+    }                                    \
+  } while (0)
+
+#define CSMOE_CHECK_CUDA(expr)                                                               \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess) {                                                                 \
+      ::csmoe::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return CSMOE_ERR_CUDA;                                                                 \
+    }                                                                                        \
+  } while (0)
+
+#define CSMOE_CHECK_LAUNCH() CSMOE_CHECK_CUDA(cudaGetLastError())
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// ---- device helpers shared by the bandwidth-bound kernels
+template <typename T>
+struct Vec8;  // 8 elements = one 16-byte (bf16) or two 16-byte (fp32) accesses
+
+__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&f)[8]) {
+  uint4 u = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ void load8(const float* p, float (&f)[8]) {
+  float4 a = *reinterpret_cast<const float4*>(p);
+  float4 b = *reinterpret_cast<const float4*>(p + 4);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+  f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&f)[8]) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+__device__ __forceinline__ void store8(float* p, const float (&f)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(f[4], f[5], f[6], f[7]);
+}
+__device__ __forceinline__ float round_as(float x, const __nv_bfloat16*) { return bf16_round(x); }
+__device__ __forceinline__ float round_as(float x, const float*) { return x; }
+
+// ---- activations (fp32 math on values already rounded to the storage dtype, like the reference's eager ops)
+__device__ __forceinline__ float act_apply(float z, int act) {
+  switch (act) {
+    case CSMOE_ACT_RELU:
+      return z > 0.f ? z : 0.f;
+    case CSMOE_ACT_GELU:
+      return 0.5f * z * (1.f + erff(z * 0.70710678118654752440f));
+    case CSMOE_ACT_GELU_TANH: {
+      const float k0 = 0.79788456080286535588f, k1 = 0.044715f;
+      return 0.5f * z * (1.f + tanhf(k0 * (z + k1 * z * z * z)));
+    }
+    case CSMOE_ACT_SILU:
+      return z / (1.f + __expf(-z));
+    default:
+      return z;
+  }
+}
+__device__ __forceinline__ float act_grad(float z, int act) {
+  switch (act) {
+    case CSMOE_ACT_RELU:
+      return z > 0.f ? 1.f : 0.f;
+    case CSMOE_ACT_GELU: {
+      const float cdf = 0.5f * (1.f + erff(z * 0.70710678118654752440f));
+      const float pdf = 0.39894228040143267794f * __expf(-0.5f * z * z);
+      return cdf + z * pdf;
+    }
+    case CSMOE_ACT_GELU_TANH: {
+      const float k0 = 0.79788456080286535588f, k1 = 0.044715f;
+      const float u = k0 * (z + k1 * z * z * z);
+      const float t = tanhf(u);
+      const float du = k0 * (1.f + 3.f * k1 * z * z);
+      return 0.5f * (1.f + t) + 0.5f * z * (1.f - t * t) * du;
+    }
+    case CSMOE_ACT_SILU: {
+      const float s = 1.f / (1.f + __expf(-z));
+      return s * (1.f + z * (1.f - s));
+    }
+    default:
+      return 1.f;
+  }
+}
+
+}  // namespace csmoe

@@ -1,0 +1,503 @@
+// Grouped GEMM for the expert FFNs: persistent, warp-specialised, TMA -> shared memory (128B swizzle) -> tcgen05.mma
+// with fp32 accumulators in TMEM -> tcgen05.ld epilogue.  One CTA per SM, 192 threads:
+//   warp 0      TMA producer (one lane)
+//   warp 1      MMA issuer   (one lane)
+//   warps 2..5  epilogue (TMEM lane quadrant = warp % 4); warp 2 also owns the TMEM allocation
+// Two accumulator stages in TMEM (2 x BN columns) let the epilogue of tile i overlap the MMAs of tile i+1.
+//
+// Modes (see csmoe.h): ROWS  C[rows,n]  = A[rows,k] . B[e]      (A K-major; B K-major [n,k] or MN-major [k,n])
+//                      REDUCE C[e][m,n] = A[rows_e,m]^T . B[rows_e,n]   (both operands MN-major)
+// The functions replaced are cvmm_kernel / cvmm_backward_kernel3 (moe_pretrain_model/layers/cvmm.py:61-168,194-345) and
+// the per-expert nn.Linear calls of moe_model/model/moe/moe.py:196-204.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace csmoe {
+namespace {
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;
+constexpr int kThreads = 192;
+constexpr int kAccStages = 2;
+constexpr int kABytes = kBM * kBK * 2;  // 16 KiB
+constexpr int kSubTileBytes = 64 * kBK * 2;  // one 64(mn) x 64(k) MN-major box = 8 KiB
+
+struct KParams {
+  int n;              // valid output columns
+  int m_valid;        // REDUCE: valid output rows per expert
+  int num_kb;         // ROWS: K blocks per tile
+  int num_experts;
+  int num_m_blocks;
+  int num_n_blocks;
+  int dense;
+  int dense_mblocks;  // dense_rows / 128
+  int dense_kblocks;  // dense_rows / 64
+  int a_expert_rows;
+  int b_expert_rows;
+  int act;
+  int c_fp32;
+  int bias_fp32;
+  int accumulate;
+  int glu_f;          // SILU_GLU: F (n == 2F); 0 otherwise
+  const int* tile_expert;
+  const int* pad_offsets;
+  void* c;
+  void* preact;
+  const void* bias;
+  long long ldc;
+  long long ldpre;
+  long long c_expert_stride;
+  long long total_tiles;
+};
+
+struct Tile {
+  int e, mb, nb, a_row, b_row, nkb;
+  bool valid;
+};
+
+template <int MODE>
+__device__ __forceinline__ Tile decode_tile(const KParams& p, long long t) {
+  Tile ti;
+  if (MODE == CSMOE_GEMM_ROWS) {
+    ti.mb = static_cast<int>(t % p.num_m_blocks);
+    ti.nb = static_cast<int>(t / p.num_m_blocks);
+    if (p.dense) {
+      ti.e = ti.mb / p.dense_mblocks;
+      ti.a_row = (ti.mb % p.dense_mblocks) * kBM + ti.e * p.a_expert_rows;
+    } else {
+      ti.e = __ldg(p.tile_expert + ti.mb);
+      ti.a_row = ti.mb * kBM;
+    }
+    ti.b_row = 0;
+    ti.nkb = p.num_kb;
+    ti.valid = ti.e >= 0;
+  } else {
+    const long long per_e = static_cast<long long>(p.num_m_blocks) * p.num_n_blocks;
+    ti.e = static_cast<int>(t / per_e);
+    const int r = static_cast<int>(t % per_e);
+    ti.mb = r / p.num_n_blocks;
+    ti.nb = r % p.num_n_blocks;
+    if (p.dense) {
+      ti.a_row = ti.e * p.a_expert_rows;
+      ti.b_row = ti.e * p.b_expert_rows;
+      ti.nkb = p.dense_kblocks;
+    } else {
+      const int r0 = __ldg(p.pad_offsets + ti.e), r1 = __ldg(p.pad_offsets + ti.e + 1);
+      ti.a_row = r0;
+      ti.b_row = r0;
+      ti.nkb = (r1 - r0) / kBK;
+    }
+    ti.valid = true;
+  }
+  return ti;
+}
+
+template <typename OutT>
+__device__ __forceinline__ void epilogue_store8(const KParams& p, const float (&acc)[8], OutT* c_row, OutT* pre_row,
+                                                const void* bias_row, int col) {
+  float z[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) z[i] = acc[i];
+  if (bias_row != nullptr) {
+    float b[8];
+    if (p.bias_fp32)
+      load8(reinterpret_cast<const float*>(bias_row) + col, b);
+    else
+      load8(reinterpret_cast<const __nv_bfloat16*>(bias_row) + col, b);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) z[i] += b[i];
+  }
+  if (p.accumulate) {
+    float old[8];
+    load8(c_row + col, old);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) z[i] += old[i];
+  }
+  if (p.act != CSMOE_ACT_NONE || pre_row != nullptr) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) z[i] = round_as(z[i], static_cast<const OutT*>(nullptr));
+    if (pre_row != nullptr) store8(pre_row + col, z);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) z[i] = act_apply(z[i], p.act);
+  }
+  store8(c_row + col, z);
+}
+
+template <int MODE, bool B_MN, int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+grouped_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const KParams p) {
+  constexpr bool kAMn = (MODE == CSMOE_GEMM_REDUCE);
+  constexpr bool kBMn = kAMn || B_MN;
+  constexpr int kBBytes = BN * kBK * 2;
+  constexpr int kStageBytes = kABytes + kBBytes;
+  constexpr int kStages = (BN == 256) ? 4 : 6;
+  constexpr uint32_t kTmemCols = kAccStages * BN;
+  constexpr uint32_t kIdesc = ptx::make_idesc_bf16(kBM, BN, kAMn, kBMn);
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + kStages * kStageBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + kAccStages + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 2 * kAccStages);
+  // generic pointer to the TMEM-address slot (same location as tmem_slot)
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tma_a);
+    ptx::prefetch_tmap(&tma_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      ptx::mbar_init(full_bar(s), 1);
+      ptx::mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < kAccStages; ++a) {
+      ptx::mbar_init(tfull_bar(a), 1);
+      ptx::mbar_init(tempty_bar(a), 4);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(tmem_slot, kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const Tile ti = decode_tile<MODE>(p, t);
+        if (!ti.valid) continue;
+        for (int kb = 0; kb < ti.nkb; ++kb) {
+          ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t fb = full_bar(stage);
+          ptx::mbar_arrive_expect_tx(fb, kStageBytes);
+          const uint32_t sa = smem_base + stage * kStageBytes;
+          const uint32_t sb = sa + kABytes;
+          if (MODE == CSMOE_GEMM_ROWS) {
+            ptx::tma_load_2d(sa, &tma_a, fb, kb * kBK, ti.a_row);
+            if (!B_MN) {
+              ptx::tma_load_3d(sb, &tma_b, fb, kb * kBK, ti.nb * BN, ti.e);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BN / 64; ++j)
+                ptx::tma_load_3d(sb + j * kSubTileBytes, &tma_b, fb, ti.nb * BN + j * 64, kb * kBK, ti.e);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < kBM / 64; ++j)
+              ptx::tma_load_2d(sa + j * kSubTileBytes, &tma_a, fb, ti.mb * kBM + j * 64, ti.a_row + kb * kBK);
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              ptx::tma_load_2d(sb + j * kSubTileBytes, &tma_b, fb, ti.nb * BN + j * 64, ti.b_row + kb * kBK);
+          }
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const Tile ti = decode_tile<MODE>(p, t);
+        if (!ti.valid || ti.nkb == 0) continue;
+        ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < ti.nkb; ++kb) {
+          ptx::mbar_wait(full_bar(stage), phase);
+          ptx::tc_fence_after();
+          const uint32_t sa = smem_base + stage * kStageBytes;
+          const uint32_t sb = sa + kABytes;
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            // K-major: 16 k-elements = 32 bytes inside the 128B swizzle row; 8-row groups are 1024 B apart.
+            // MN-major: 16 k-rows = 2048 bytes; 64-wide mn blocks are kSubTileBytes apart, 8-k groups 1024 B apart.
+            const uint64_t adesc = kAMn ? ptx::make_smem_desc_sw128(sa + k * 2048, kSubTileBytes, 1024)
+                                        : ptx::make_smem_desc_sw128(sa + k * 32, 16, 1024);
+            const uint64_t bdesc = kBMn ? ptx::make_smem_desc_sw128(sb + k * 2048, kSubTileBytes, 1024)
+                                        : ptx::make_smem_desc_sw128(sb + k * 32, 16, 1024);
+            ptx::umma_f16(d_tmem, adesc, bdesc, kIdesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          ptx::umma_commit(empty_bar(stage));
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        ptx::umma_commit(tfull_bar(acc));
+        if (++acc == kAccStages) {
+          acc = 0;
+          acc_phase ^= 1u;
+        }
+      }
+    }
+  } else {
+    // ===================================================== epilogue (4 warps, 128 TMEM lanes)
+    const int quad = warp & 3;
+    const int row_in_tile = quad * 32 + lane;
+    uint32_t acc = 0, acc_phase = 0;
+    for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      const Tile ti = decode_tile<MODE>(p, t);
+      if (!ti.valid) continue;
+      const bool has_acc = ti.nkb > 0;
+      if (has_acc) {
+        ptx::mbar_wait(tfull_bar(acc), acc_phase);
+        ptx::tc_fence_after();
+      }
+      long long out_row;
+      bool row_ok;
+      long long c_off = 0;
+      if (MODE == CSMOE_GEMM_ROWS) {
+        out_row = static_cast<long long>(ti.mb) * kBM + row_in_tile;
+        row_ok = true;
+      } else {
+        out_row = static_cast<long long>(ti.mb) * kBM + row_in_tile;
+        row_ok = out_row < p.m_valid;
+        c_off = static_cast<long long>(ti.e) * p.c_expert_stride;
+      }
+      const void* bias_row = nullptr;
+      if (p.bias != nullptr) {
+        const long long boff = static_cast<long long>(ti.e) * p.n;
+        bias_row = p.bias_fp32 ? static_cast<const void*>(reinterpret_cast<const float*>(p.bias) + boff)
+                               : static_cast<const void*>(reinterpret_cast<const __nv_bfloat16*>(p.bias) + boff);
+      }
+      const uint32_t t_row = tmem_base + acc * BN + (static_cast<uint32_t>(quad * 32) << 16);
+#pragma unroll 1
+      for (int chunk = 0; chunk < BN / 32; ++chunk) {
+        uint32_t v[32];
+        if (has_acc) {
+          ptx::tmem_ld_32x32b_x32(t_row + chunk * 32, v);
+          ptx::tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = 0u;
+        }
+        const int col0 = ti.nb * BN + chunk * 32;
+        if (row_ok && col0 < p.n) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int col = col0 + g * 8;
+            if (col < p.n) {
+              float a8[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) a8[i] = __uint_as_float(v[g * 8 + i]);
+              if (p.c_fp32) {
+                float* c_row = reinterpret_cast<float*>(p.c) + c_off + out_row * p.ldc;
+                float* pre_row = p.preact ? reinterpret_cast<float*>(p.preact) + out_row * p.ldpre : nullptr;
+                epilogue_store8<float>(p, a8, c_row, pre_row, bias_row, col);
+              } else {
+                __nv_bfloat16* c_row = reinterpret_cast<__nv_bfloat16*>(p.c) + c_off + out_row * p.ldc;
+                __nv_bfloat16* pre_row =
+                    p.preact ? reinterpret_cast<__nv_bfloat16*>(p.preact) + out_row * p.ldpre : nullptr;
+                epilogue_store8<__nv_bfloat16>(p, a8, c_row, pre_row, bias_row, col);
+              }
+            }
+          }
+        }
+      }
+      if (has_acc) {
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
+        if (++acc == kAccStages) {
+          acc = 0;
+          acc_phase ^= 1u;
+        }
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                              const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeFn get_encode_fn() {
+  static EncodeFn fn = []() -> EncodeFn {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return reinterpret_cast<EncodeFn>(p);
+  }();
+  return fn;
+}
+
+int encode_bf16_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                    const cuuint32_t* box) {
+  EncodeFn fn = get_encode_fn();
+  if (fn == nullptr) {
+    set_error("cuTensorMapEncodeTiled is not available (no CUDA driver?)");
+    return CSMOE_ERR_DRIVER;
+  }
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base), dims,
+                  strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed: CUresult %d (rank %d dims %llu,%llu,%llu stride0 %llu box %u,%u)", (int)r,
+              rank, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)(rank > 2 ? dims[2] : 0),
+              (unsigned long long)strides_bytes[0], box[0], box[1]);
+    return CSMOE_ERR_DRIVER;
+  }
+  return CSMOE_OK;
+}
+
+template <int MODE, bool B_MN, int BN>
+int launch(const CUtensorMap& ma, const CUtensorMap& mb, const KParams& kp, int grid, cudaStream_t stream) {
+  constexpr int kStages = (BN == 256) ? 4 : 6;
+  constexpr int kSmem = kStages * (kABytes + BN * kBK * 2) + 1024 + 256;
+  auto kern = grouped_gemm_kernel<MODE, B_MN, BN>;
+  static bool configured = false;  // per instantiation; benign race (idempotent attribute set)
+  if (!configured) {
+    CSMOE_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    configured = true;
+  }
+  kern<<<grid, kThreads, kSmem, stream>>>(ma, mb, kp);
+  CSMOE_CHECK_LAUNCH();
+  return CSMOE_OK;
+}
+
+}  // namespace
+}  // namespace csmoe
+
+using namespace csmoe;
+
+extern "C" int csmoe_grouped_gemm(const csmoe_gemm_args* a, void* stream_) {
+  CSMOE_CHECK_ARG(a != nullptr, "csmoe_grouped_gemm: args is NULL");
+  CSMOE_CHECK_ARG(a->a && a->b && a->c, "csmoe_grouped_gemm: a/b/c must be non-NULL");
+  CSMOE_CHECK_ARG(a->mode == CSMOE_GEMM_ROWS || a->mode == CSMOE_GEMM_REDUCE, "csmoe_grouped_gemm: bad mode %d", a->mode);
+  CSMOE_CHECK_ARG(a->num_experts >= 1, "csmoe_grouped_gemm: num_experts must be >= 1");
+  CSMOE_CHECK_ARG(a->m > 0 && a->n > 0 && a->k > 0, "csmoe_grouped_gemm: m, n, k must be positive");
+  CSMOE_CHECK_ARG(a->n % 8 == 0, "csmoe_grouped_gemm: n (%lld) must be a multiple of 8", (long long)a->n);
+  CSMOE_CHECK_ARG(a->lda % 8 == 0 && a->ldb % 8 == 0, "csmoe_grouped_gemm: lda/ldb must be multiples of 8 elements");
+  CSMOE_CHECK_ARG(a->ldc % (a->c_dtype == CSMOE_F32 ? 4 : 8) == 0, "csmoe_grouped_gemm: ldc alignment");
+  CSMOE_CHECK_ARG((reinterpret_cast<uintptr_t>(a->a) | reinterpret_cast<uintptr_t>(a->b) |
+                   reinterpret_cast<uintptr_t>(a->c)) % 16 == 0,
+                  "csmoe_grouped_gemm: a/b/c must be 16-byte aligned");
+  CSMOE_CHECK_ARG(a->c_dtype == CSMOE_F32 || a->c_dtype == CSMOE_BF16, "csmoe_grouped_gemm: bad c_dtype");
+  CSMOE_CHECK_ARG(a->act != CSMOE_ACT_SILU_GLU, "csmoe_grouped_gemm: SILU_GLU is not fused here; use csmoe_act_fwd");
+  if (a->dense) {
+    CSMOE_CHECK_ARG(a->dense_rows > 0 && a->dense_rows % kBM == 0, "csmoe_grouped_gemm: dense_rows must be a multiple of 128");
+  } else if (a->mode == CSMOE_GEMM_ROWS) {
+    CSMOE_CHECK_ARG(a->tile_expert != nullptr, "csmoe_grouped_gemm: ROWS mode needs tile_expert");
+    CSMOE_CHECK_ARG(a->m % kBM == 0, "csmoe_grouped_gemm: ROWS mode m must be a multiple of 128");
+  } else {
+    CSMOE_CHECK_ARG(a->pad_offsets != nullptr, "csmoe_grouped_gemm: REDUCE mode needs pad_offsets");
+  }
+  if (a->accumulate) CSMOE_CHECK_ARG(a->c_dtype == CSMOE_F32, "csmoe_grouped_gemm: accumulate needs an fp32 C");
+
+  cudaStream_t stream = as_stream(stream_);
+  const int E = a->num_experts;
+  const bool big_n = a->n > 128;
+  const int BN = big_n ? 256 : 128;
+
+  KParams kp{};
+  kp.n = static_cast<int>(a->n);
+  kp.num_experts = E;
+  kp.dense = a->dense;
+  kp.dense_mblocks = a->dense ? static_cast<int>(a->dense_rows / kBM) : 0;
+  kp.dense_kblocks = a->dense ? static_cast<int>(a->dense_rows / kBK) : 0;
+  kp.a_expert_rows = static_cast<int>(a->a_expert_rows);
+  kp.act = a->act;
+  kp.c_fp32 = a->c_dtype == CSMOE_F32;
+  kp.bias_fp32 = a->bias_dtype == CSMOE_F32;
+  kp.accumulate = a->accumulate;
+  kp.tile_expert = a->tile_expert;
+  kp.pad_offsets = a->pad_offsets;
+  kp.c = a->c;
+  kp.preact = a->preact;
+  kp.bias = a->bias;
+  kp.ldc = a->ldc;
+  kp.ldpre = a->ldpre;
+  kp.c_expert_stride = a->c_expert_stride;
+  kp.num_n_blocks = static_cast<int>((a->n + BN - 1) / BN);
+
+  CUtensorMap ma, mb;
+  int rc;
+  if (a->mode == CSMOE_GEMM_ROWS) {
+    const long long a_rows = a->dense ? (a->a_expert_rows ? (long long)E * a->a_expert_rows : a->dense_rows) : a->m;
+    kp.num_m_blocks = a->dense ? E * kp.dense_mblocks : static_cast<int>(a->m / kBM);
+    kp.num_kb = static_cast<int>((a->k + kBK - 1) / kBK);
+    kp.total_tiles = static_cast<long long>(kp.num_m_blocks) * kp.num_n_blocks;
+    {
+      cuuint64_t dims[2] = {(cuuint64_t)a->k, (cuuint64_t)a_rows};
+      cuuint64_t str[1] = {(cuuint64_t)a->lda * 2};
+      cuuint32_t box[2] = {kBK, kBM};
+      if ((rc = encode_bf16_map(&ma, a->a, 2, dims, str, box)) != CSMOE_OK) return rc;
+    }
+    if (a->b_layout == 0) {
+      cuuint64_t dims[3] = {(cuuint64_t)a->k, (cuuint64_t)a->n, (cuuint64_t)E};
+      cuuint64_t str[2] = {(cuuint64_t)a->ldb * 2, (cuuint64_t)a->b_expert_stride * 2};
+      if (E == 1) str[1] = (cuuint64_t)a->ldb * 2 * a->n;
+      cuuint32_t box[3] = {kBK, (cuuint32_t)BN, 1};
+      if ((rc = encode_bf16_map(&mb, a->b, 3, dims, str, box)) != CSMOE_OK) return rc;
+    } else {
+      cuuint64_t dims[3] = {(cuuint64_t)a->n, (cuuint64_t)a->k, (cuuint64_t)E};
+      cuuint64_t str[2] = {(cuuint64_t)a->ldb * 2, (cuuint64_t)a->b_expert_stride * 2};
+      if (E == 1) str[1] = (cuuint64_t)a->ldb * 2 * a->k;
+      cuuint32_t box[3] = {64, kBK, 1};
+      if ((rc = encode_bf16_map(&mb, a->b, 3, dims, str, box)) != CSMOE_OK) return rc;
+    }
+  } else {
+    kp.m_valid = static_cast<int>(a->m);
+    kp.num_m_blocks = static_cast<int>((a->m + kBM - 1) / kBM);
+    kp.b_expert_rows = static_cast<int>(a->b_expert_stride);
+    kp.total_tiles = static_cast<long long>(E) * kp.num_m_blocks * kp.num_n_blocks;
+    const long long a_rows = a->dense ? (a->a_expert_rows ? (long long)E * a->a_expert_rows : a->dense_rows) : a->k;
+    const long long b_rows = a->dense ? (a->b_expert_stride ? (long long)E * a->b_expert_stride : a->dense_rows) : a->k;
+    {
+      cuuint64_t dims[2] = {(cuuint64_t)a->m, (cuuint64_t)a_rows};
+      cuuint64_t str[1] = {(cuuint64_t)a->lda * 2};
+      cuuint32_t box[2] = {64, kBK};
+      if ((rc = encode_bf16_map(&ma, a->a, 2, dims, str, box)) != CSMOE_OK) return rc;
+    }
+    {
+      cuuint64_t dims[2] = {(cuuint64_t)a->n, (cuuint64_t)b_rows};
+      cuuint64_t str[1] = {(cuuint64_t)a->ldb * 2};
+      cuuint32_t box[2] = {64, kBK};
+      if ((rc = encode_bf16_map(&mb, a->b, 2, dims, str, box)) != CSMOE_OK) return rc;
+    }
+  }
+  if (kp.total_tiles == 0) return CSMOE_OK;
+  int grid = num_sms();
+  if (grid <= 0) return CSMOE_ERR_CUDA;
+  if (a->max_ctas > 0 && a->max_ctas < grid) grid = a->max_ctas;
+  if (kp.total_tiles < grid) grid = static_cast<int>(kp.total_tiles);
+
+  if (a->mode == CSMOE_GEMM_ROWS) {
+    if (a->b_layout == 0)
+      return big_n ? launch<CSMOE_GEMM_ROWS, false, 256>(ma, mb, kp, grid, stream)
+                   : launch<CSMOE_GEMM_ROWS, false, 128>(ma, mb, kp, grid, stream);
+    return big_n ? launch<CSMOE_GEMM_ROWS, true, 256>(ma, mb, kp, grid, stream)
+                 : launch<CSMOE_GEMM_ROWS, true, 128>(ma, mb, kp, grid, stream);
+  }
+  return big_n ? launch<CSMOE_GEMM_REDUCE, true, 256>(ma, mb, kp, grid, stream)
+               : launch<CSMOE_GEMM_REDUCE, true, 128>(ma, mb, kp, grid, stream);
+}

@@ -1,0 +1,178 @@
+/* csmoe.h — C ABI of libcsmoe.so: the B200 (sm_100a) kernels behind CompeteSMoE's sparse-MoE layer.
+ *
+ * Every entry point takes raw device pointers, sizes and a cudaStream_t (passed as void*), returns 0 on success or a
+ * negative csmoe_status, never allocates device memory, never synchronises the host with the device and is therefore
+ * CUDA-graph capturable.  The caller (PyTorch on the host side) owns all buffers.
+ *
+ * The reference (Fsoft-AIC/CompeteSMoE) has no native interface; each entry point below names the Python code it
+ * replaces (paths relative to the reference root).  See INTEGRATION.md for the binding a maintainer would add.
+ */
+#ifndef CSMOE_H_
+#define CSMOE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CSMOE_ABI_VERSION 1
+
+typedef enum csmoe_status {
+  CSMOE_OK = 0,
+  CSMOE_ERR_ARG = -1,      /* bad argument (null pointer, unsupported size / alignment / dtype) */
+  CSMOE_ERR_CUDA = -2,     /* a CUDA runtime call failed; csmoe_last_error() has the text */
+  CSMOE_ERR_DRIVER = -3,   /* libcuda entry point (cuTensorMapEncodeTiled) unavailable or failed */
+  CSMOE_ERR_UNSUPPORTED = -4
+} csmoe_status;
+
+typedef enum csmoe_dtype { CSMOE_F32 = 0, CSMOE_BF16 = 1 } csmoe_dtype;
+
+typedef enum csmoe_act {
+  CSMOE_ACT_NONE = 0,
+  CSMOE_ACT_RELU = 1,
+  CSMOE_ACT_GELU = 2,      /* erf form, torch.nn.GELU() */
+  CSMOE_ACT_GELU_TANH = 3, /* transformers ACT2FN["gelu_pytorch_tanh"] (SigLIP MLP) */
+  CSMOE_ACT_SILU = 4,
+  CSMOE_ACT_SILU_GLU = 5   /* Phi3MLP: cols [0,F) = gate, [F,2F) = up; h = up * silu(gate) */
+} csmoe_act;
+
+/* Row tile of every grouped operand: expert segments in the permuted ("expert-major") row space start at multiples of
+ * this, so that one GEMM tile never straddles two experts. */
+#define CSMOE_ROW_TILE 128
+
+int csmoe_abi_version(void);
+/* Text of the last failure on the calling thread ("" if none). */
+const char* csmoe_last_error(void);
+/* 1 when the current device is compute capability 10.x, 0 otherwise, <0 on error. */
+int csmoe_device_supported(void);
+
+/* ------------------------------------------------------------------------------------------------ routing metadata
+ * Replaces cvmm_prepare_sel2 (moe_pretrain_model/layers/cvmm.py:580-592: flatten -> sort -> index maps) and the
+ * E x torch.where of MoeLayer.compute_moe (moe_model/model/moe/moe.py:189-191).
+ *
+ * In : sel[T*K] int32 expert id of slot j = t*K + k.
+ * Out: counts[E], offsets[E+1] (exclusive scan of counts = the reference's sorted segment boundaries),
+ *      pad_offsets[E+1] (segment starts rounded up to CSMOE_ROW_TILE),
+ *      sorted_sel[T*K], sort_index[T*K] (stable argsort of sel: the reference's ssel / out_index; in_index = /K),
+ *      slot_to_row[T*K] (row of slot j in the padded expert-major space), row_to_slot[row_cap] (-1 for padding rows),
+ *      tile_expert[row_cap/CSMOE_ROW_TILE] (expert owning each row tile, -1 past the end).
+ * row_cap must be >= csmoe_route_row_cap(T*K, E).  Any output pointer except counts/offsets/pad_offsets may be NULL.
+ * workspace: csmoe_route_workspace_bytes(T*K, E) bytes. */
+int64_t csmoe_route_row_cap(int64_t n_slots, int32_t num_experts);
+int64_t csmoe_route_workspace_bytes(int64_t n_slots, int32_t num_experts);
+int csmoe_route_build(const int32_t* sel, int64_t n_slots, int32_t num_experts, int64_t row_cap, int32_t* counts,
+                      int32_t* offsets, int32_t* pad_offsets, int32_t* sorted_sel, int64_t* sort_index,
+                      int32_t* slot_to_row, int32_t* row_to_slot, int32_t* tile_expert, void* workspace, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ router
+ * Replaces router_policy + topk_expert (moe_model/model/moe/competesmoe.py:301-320, moe.py:113-132;
+ * moe_pretrain_model/layers/moe/competesmoe.py:465-490): logits = x @ Wg^T (fp32 accumulate, rounded to `x_dtype`),
+ * p = softmax_fp32(logits), (w, idx) = topk(p, K) (descending, ties -> lowest index), w /= round_to_x_dtype(sum w).
+ * x[T,D] and wg[E,D] share x_dtype (bf16 or fp32).  Outputs: logits[T,E] (x_dtype), probs[T,E] fp32, topk_w[T,K] fp32,
+ * topk_idx[T,K] int32.  E <= 64, K <= 8. */
+int csmoe_router_fwd(const void* x, const void* wg, int32_t x_dtype, int64_t T, int32_t D, int32_t E, int32_t K,
+                     void* logits, float* probs, float* topk_w, int32_t* topk_idx, void* stream);
+
+/* Top-k over given fp32 scores[T,E] (competition step: affinity scores; moe_model/.../competesmoe.py:249-254).
+ * mode 0: w = topk values; mode 1: w = sigmoid(topk values) (norm_sigmoid).  Then w /= round_to(dtype)(sum w). */
+int csmoe_topk_renorm(const float* scores, int64_t T, int32_t E, int32_t K, int32_t mode, int32_t round_dtype,
+                      float* topk_w, int32_t* topk_idx, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ permutation
+ * Gather rows of src[T, D] into the padded expert-major space: dst[row] = scale(row) * src[row_to_slot[row] / K],
+ * zero for padding rows.  scale = slot_w[slot] when slot_w != NULL (combine backward), else 1.
+ * Replaces x[batch_idx, token_idx] (moe.py:199) and the gathered A loads of cvmm_kernel (cvmm.py:114-118). */
+int csmoe_gather_rows(const void* src, int32_t dtype, int64_t T, int32_t D, int32_t K, const int32_t* row_to_slot,
+                      int64_t row_cap, const float* slot_w, void* dst, void* stream);
+
+/* Combine: out[t] = sum_k w[t,k] * y[slot_to_row[t*K+k]]  in ascending-expert order (deterministic), replacing the
+ * in-place `results[b,t] += w * out` loop (moe.py:204) and the bmm reduce of CVMM.forward (cvmm.py:481-483).
+ * round_each != 0 reproduces the reference's rounding of the running sum to `dtype` after every expert (moe.py:204).
+ * sel[T*K] gives the expert of each slot (ordering key).  bias (may be NULL): o_bias[D] added at the end. */
+int csmoe_combine_fwd(const void* y, int32_t dtype, int64_t T, int32_t D, int32_t K, const int32_t* slot_to_row,
+                      const int32_t* sel, const float* w, int32_t round_each, void* out, void* stream);
+/* dw[t,k] = <dout[t], y[row(t,k)]> (fp32). */
+int csmoe_combine_bwd_w(const void* y, const void* dout, int32_t dtype, int64_t T, int32_t D, int32_t K,
+                        const int32_t* slot_to_row, float* dw, void* stream);
+/* Un-permute with reduction: dx[t] (+)= sum_k g[slot_to_row[t*K+k]]; accumulate != 0 adds to the existing dx. */
+int csmoe_scatter_reduce(const void* g, int32_t dtype, int64_t T, int32_t D, int32_t K, const int32_t* slot_to_row,
+                         int32_t accumulate, void* dx, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ grouped GEMM
+ * tcgen05/TMEM grouped GEMM fed by TMA; bf16 operands, fp32 accumulation.
+ * Replaces cvmm_kernel / cvmm_backward_kernel3 (moe_pretrain_model/layers/cvmm.py:61-168, 194-345) and the per-expert
+ * nn.Linear calls of compute_moe / competition_policy (moe_model/model/moe/moe.py:196-204, competesmoe.py:240-245).
+ *
+ * mode ROWS   : C[row, :] = A[row, :] . B[expert(row)]   for row tiles of the padded expert-major space
+ *               (forward and dgrad).  A is [m, k] row-major.  b_layout 0: B[e] is [n, k] row-major (nn.Linear weight,
+ *               forward); b_layout 1: B[e] is [k, n] row-major (sigma-MoE keys/values forward, nn.Linear dgrad).
+ * mode REDUCE : C[e] = A[rows of e, :]^T . B[rows of e, :]   (wgrad).  A is [rows, m], B is [rows, n] row-major,
+ *               C[e] is [m, n].
+ * dense != 0  : every expert processes the same dense_rows rows (competition step, all experts on all tokens):
+ *               ROWS: A row tile = tile % (dense_rows/128) (+ e*a_expert_rows), C row = e*dense_rows + ...;
+ *               REDUCE: A rows of e start at e*a_expert_rows, B rows at e*b_expert_rows (0 = shared operand).
+ * Epilogue    : + bias[e][n] (optional), activation (optional, ROWS only); when preact != NULL the pre-activation value
+ *               is also stored (same layout/dtype as C; for SILU_GLU preact is [m, 2F] and C is [m, F] with n = 2F).
+ * All leading dimensions are in elements and must make rows 16-byte aligned; n % 8 == 0. */
+typedef enum csmoe_gemm_mode { CSMOE_GEMM_ROWS = 0, CSMOE_GEMM_REDUCE = 1 } csmoe_gemm_mode;
+
+typedef struct csmoe_gemm_args {
+  int32_t mode;
+  int32_t b_layout;
+  int32_t num_experts;
+  int32_t dense;
+  int64_t m, n, k;
+  int64_t dense_rows;
+  const void* a;
+  int64_t lda;
+  int64_t a_expert_rows;
+  const void* b;
+  int64_t ldb;
+  int64_t b_expert_stride; /* ROWS: elements between consecutive experts' weights. REDUCE+dense: rows between experts */
+  void* c;
+  int64_t ldc;
+  int64_t c_expert_stride; /* REDUCE: elements between consecutive experts' outputs */
+  int32_t c_dtype;
+  int32_t act;
+  const void* bias;        /* [num_experts, n] or NULL */
+  int32_t bias_dtype;
+  int32_t accumulate;      /* REDUCE: C[e] += result (fp32 C only) */
+  void* preact;
+  int64_t ldpre;
+  const int32_t* tile_expert; /* ROWS, !dense: [m / 128] */
+  const int32_t* pad_offsets; /* REDUCE, !dense: [num_experts + 1] */
+  int32_t max_ctas;        /* 0 = one per SM */
+  int32_t reserved;
+} csmoe_gemm_args;
+
+int csmoe_grouped_gemm(const csmoe_gemm_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ activations
+ * Elementwise forward/backward used where the activation is not fused into a GEMM epilogue.
+ * fwd: h = act(z).  GLU: z is [rows, 2F], h is [rows, F].   bwd: dz = dh * act'(z). */
+int csmoe_act_fwd(const void* z, int32_t dtype, int64_t rows, int64_t cols, int64_t ldz, int32_t act, void* h,
+                  int64_t ldh, void* stream);
+int csmoe_act_bwd(const void* z, const void* dh, int32_t dtype, int64_t rows, int64_t cols, int64_t ldz, int64_t ldh,
+                  int32_t act, void* dz, void* stream);
+/* Column sums of g[rows of e, n] per expert -> dbias[e, n] (fp32 accumulate, written as `out_dtype`). */
+int csmoe_bias_grad(const void* g, int32_t dtype, int64_t ldg, int32_t n, int32_t num_experts,
+                    const int32_t* pad_offsets, int32_t dense, int64_t dense_rows, void* dbias, int32_t out_dtype,
+                    void* stream);
+/* dst = (bf16) src, n elements. */
+int csmoe_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ competition
+ * Neural-response score (moe_model/.../competesmoe.py:240-243; moe_pretrain_model/.../competesmoe.py:399-403):
+ * aff[t, e] = mean_d softplus(y[e, t, d]) over dense expert outputs y[E, t_pad, D] (the grouped GEMM's dense layout).
+ * Written as fp32 after rounding to `dtype` (the reference stores it in x.dtype). */
+int csmoe_affinity_fwd(const void* y, int32_t dtype, int32_t E, int64_t T, int64_t t_pad, int32_t D, float* aff,
+                       void* stream);
+/* dy[e,t,d] (+)= daff[t,e] * sigmoid(y[e,t,d]) / D. accumulate: add into an existing dy. */
+int csmoe_affinity_bwd(const void* y, const float* daff, int32_t dtype, int32_t E, int64_t T, int64_t t_pad, int32_t D,
+                       int32_t accumulate, void* dy, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CSMOE_H_ */
