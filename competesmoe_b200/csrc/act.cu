@@ -1,0 +1,218 @@
+// Elementwise expert-FFN pieces that are not (yet) fused into a GEMM epilogue: activation forward/backward
+// (ReLU / GELU / GELU-tanh / SiLU / SiLU-GLU), per-expert bias gradients and the fp32 -> bf16 parameter cast used under
+// autocast.  HBM-bound, 16-byte accesses.  Replaces the eager activation calls inside the reference's expert modules
+// (moe_model/model/multimodal_encoder/siglip_smoe.py:85-97, Phi3MLP; moe_pretrain_model/layers/moe/moe.py:405).
+#include "common.h"
+
+namespace csmoe {
+namespace {
+
+constexpr int kThreads = 256;
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+act_fwd_kernel(const T* __restrict__ z, long long rows, long long cols, long long ldz, int act, T* __restrict__ h,
+               long long ldh) {
+  const long long vec_per_row = cols / 8;
+  const long long total = rows * vec_per_row;
+  for (long long i = static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * kThreads) {
+    const long long r = i / vec_per_row, c = (i % vec_per_row) * 8;
+    float v[8], o[8];
+    if (act == CSMOE_ACT_SILU_GLU) {
+      float u[8];
+      load8(z + r * ldz + c, v);          // gate
+      load8(z + r * ldz + cols + c, u);   // up
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float s = round_as(act_apply(v[j], CSMOE_ACT_SILU), static_cast<const T*>(nullptr));
+        o[j] = u[j] * s;
+      }
+    } else {
+      load8(z + r * ldz + c, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = act_apply(v[j], act);
+    }
+    store8(h + r * ldh + c, o);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+act_bwd_kernel(const T* __restrict__ z, const T* __restrict__ dh, long long rows, long long cols, long long ldz,
+               long long ldh, int act, T* __restrict__ dz) {
+  const long long vec_per_row = cols / 8;
+  const long long total = rows * vec_per_row;
+  for (long long i = static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * kThreads) {
+    const long long r = i / vec_per_row, c = (i % vec_per_row) * 8;
+    float v[8], g[8], o[8];
+    load8(dh + r * ldh + c, g);
+    if (act == CSMOE_ACT_SILU_GLU) {
+      float u[8], du[8];
+      load8(z + r * ldz + c, v);
+      load8(z + r * ldz + cols + c, u);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float s = round_as(act_apply(v[j], CSMOE_ACT_SILU), static_cast<const T*>(nullptr));
+        du[j] = g[j] * s;
+        const float ds = round_as(g[j] * u[j], static_cast<const T*>(nullptr));
+        o[j] = ds * act_grad(v[j], CSMOE_ACT_SILU);
+      }
+      store8(dz + r * ldz + c, o);
+      store8(dz + r * ldz + cols + c, du);
+    } else {
+      load8(z + r * ldz + c, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = g[j] * act_grad(v[j], act);
+      store8(dz + r * ldz + c, o);
+    }
+  }
+}
+
+// dbias[e][n]: grid (ceil(n / 256), E); block = 32 column-vectors x 8 row lanes.
+template <typename T, typename OutT>
+__global__ void __launch_bounds__(256)
+bias_grad_kernel(const T* __restrict__ g, long long ldg, int n, const int32_t* __restrict__ pad_offsets, int dense,
+                 long long dense_rows, OutT* __restrict__ dbias) {
+  __shared__ float red[8][32][8];
+  const int e = blockIdx.y;
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int col = (blockIdx.x * 32 + cx) * 8;
+  long long r0, r1;
+  if (dense) {
+    r0 = e * dense_rows;
+    r1 = r0 + dense_rows;
+  } else {
+    r0 = pad_offsets[e];
+    r1 = pad_offsets[e + 1];
+  }
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (col < n) {
+    for (long long r = r0 + ry; r < r1; r += 8) {
+      float v[8];
+      load8(g + r * ldg + col, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += v[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[ry][cx][j] = acc[j];
+  __syncthreads();
+  if (ry == 0 && col < n) {
+    float s[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s[j] = 0.f;
+#pragma unroll
+      for (int y = 0; y < 8; ++y) s[j] += red[y][cx][j];
+    }
+    store8(dbias + static_cast<long long>(e) * n + col, s);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
+  const long long nv = n / 8;
+  for (long long i = static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x; i < nv;
+       i += static_cast<long long>(gridDim.x) * kThreads) {
+    float v[8];
+    load8(src + i * 8, v);
+    store8(dst + i * 8, v);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 7)) {
+    const long long i = nv * 8 + threadIdx.x;
+    dst[i] = __float2bfloat16_rn(src[i]);
+  }
+}
+
+inline unsigned flat_grid(long long work_items) {
+  const long long blocks = (work_items + kThreads - 1) / kThreads;
+  const long long cap = static_cast<long long>(num_sms() > 0 ? num_sms() : 148) * 8;
+  return static_cast<unsigned>(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
+}
+
+}  // namespace
+}  // namespace csmoe
+
+using namespace csmoe;
+
+extern "C" int csmoe_act_fwd(const void* z, int32_t dtype, int64_t rows, int64_t cols, int64_t ldz, int32_t act,
+                             void* h, int64_t ldh, void* stream_) {
+  CSMOE_CHECK_ARG(z && h, "csmoe_act_fwd: NULL pointer");
+  CSMOE_CHECK_ARG(cols > 0 && cols % 8 == 0 && ldz % 8 == 0 && ldh % 8 == 0, "csmoe_act_fwd: cols/ld must be multiples of 8");
+  CSMOE_CHECK_ARG(act >= CSMOE_ACT_NONE && act <= CSMOE_ACT_SILU_GLU, "csmoe_act_fwd: bad act %d", act);
+  if (rows == 0) return CSMOE_OK;
+  cudaStream_t stream = as_stream(stream_);
+  const unsigned grid = flat_grid(rows * (cols / 8));
+  if (dtype == CSMOE_BF16) {
+    act_fwd_kernel<__nv_bfloat16><<<grid, kThreads, 0, stream>>>(static_cast<const __nv_bfloat16*>(z), rows, cols, ldz,
+                                                                 act, static_cast<__nv_bfloat16*>(h), ldh);
+  } else if (dtype == CSMOE_F32) {
+    act_fwd_kernel<float><<<grid, kThreads, 0, stream>>>(static_cast<const float*>(z), rows, cols, ldz, act,
+                                                         static_cast<float*>(h), ldh);
+  } else {
+    CSMOE_CHECK_ARG(false, "csmoe_act_fwd: unsupported dtype %d", dtype);
+  }
+  CSMOE_CHECK_LAUNCH();
+  return CSMOE_OK;
+}
+
+extern "C" int csmoe_act_bwd(const void* z, const void* dh, int32_t dtype, int64_t rows, int64_t cols, int64_t ldz,
+                             int64_t ldh, int32_t act, void* dz, void* stream_) {
+  CSMOE_CHECK_ARG(z && dh && dz, "csmoe_act_bwd: NULL pointer");
+  CSMOE_CHECK_ARG(cols > 0 && cols % 8 == 0 && ldz % 8 == 0 && ldh % 8 == 0, "csmoe_act_bwd: cols/ld must be multiples of 8");
+  CSMOE_CHECK_ARG(act >= CSMOE_ACT_NONE && act <= CSMOE_ACT_SILU_GLU, "csmoe_act_bwd: bad act %d", act);
+  if (rows == 0) return CSMOE_OK;
+  cudaStream_t stream = as_stream(stream_);
+  const unsigned grid = flat_grid(rows * (cols / 8));
+  if (dtype == CSMOE_BF16) {
+    act_bwd_kernel<__nv_bfloat16><<<grid, kThreads, 0, stream>>>(static_cast<const __nv_bfloat16*>(z),
+                                                                 static_cast<const __nv_bfloat16*>(dh), rows, cols, ldz,
+                                                                 ldh, act, static_cast<__nv_bfloat16*>(dz));
+  } else if (dtype == CSMOE_F32) {
+    act_bwd_kernel<float><<<grid, kThreads, 0, stream>>>(static_cast<const float*>(z), static_cast<const float*>(dh),
+                                                         rows, cols, ldz, ldh, act, static_cast<float*>(dz));
+  } else {
+    CSMOE_CHECK_ARG(false, "csmoe_act_bwd: unsupported dtype %d", dtype);
+  }
+  CSMOE_CHECK_LAUNCH();
+  return CSMOE_OK;
+}
+
+extern "C" int csmoe_bias_grad(const void* g, int32_t dtype, int64_t ldg, int32_t n, int32_t num_experts,
+                               const int32_t* pad_offsets, int32_t dense, int64_t dense_rows, void* dbias,
+                               int32_t out_dtype, void* stream_) {
+  CSMOE_CHECK_ARG(g && dbias, "csmoe_bias_grad: NULL pointer");
+  CSMOE_CHECK_ARG(dense || pad_offsets, "csmoe_bias_grad: pad_offsets required unless dense");
+  CSMOE_CHECK_ARG(n > 0 && n % 8 == 0 && ldg % 8 == 0, "csmoe_bias_grad: n/ldg must be multiples of 8");
+  CSMOE_CHECK_ARG(num_experts >= 1 && num_experts <= 65535, "csmoe_bias_grad: bad num_experts");
+  cudaStream_t stream = as_stream(stream_);
+  dim3 grid((n + 255) / 256, num_experts);
+#define LAUNCH_BG(T, O)                                                                                             \
+  bias_grad_kernel<T, O><<<grid, 256, 0, stream>>>(static_cast<const T*>(g), ldg, n, pad_offsets, dense, dense_rows, \
+                                                   static_cast<O*>(dbias))
+  if (dtype == CSMOE_BF16 && out_dtype == CSMOE_BF16) {
+    LAUNCH_BG(__nv_bfloat16, __nv_bfloat16);
+  } else if (dtype == CSMOE_BF16 && out_dtype == CSMOE_F32) {
+    LAUNCH_BG(__nv_bfloat16, float);
+  } else if (dtype == CSMOE_F32 && out_dtype == CSMOE_F32) {
+    LAUNCH_BG(float, float);
+  } else {
+    CSMOE_CHECK_ARG(false, "csmoe_bias_grad: unsupported dtype combination %d -> %d", dtype, out_dtype);
+  }
+#undef LAUNCH_BG
+  CSMOE_CHECK_LAUNCH();
+  return CSMOE_OK;
+}
+
+extern "C" int csmoe_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream_) {
+  CSMOE_CHECK_ARG(src && dst, "csmoe_cast_f32_bf16: NULL pointer");
+  CSMOE_CHECK_ARG((reinterpret_cast<uintptr_t>(src) % 16 == 0) && (reinterpret_cast<uintptr_t>(dst) % 16 == 0),
+                  "csmoe_cast_f32_bf16: pointers must be 16-byte aligned");
+  if (n == 0) return CSMOE_OK;
+  cast_f32_bf16_kernel<<<flat_grid(n / 8 + 1), kThreads, 0, as_stream(stream_)>>>(
+      src, static_cast<__nv_bfloat16*>(dst), n);
+  CSMOE_CHECK_LAUNCH();
+  return CSMOE_OK;
+}

@@ -1,0 +1,329 @@
+"""Tensor-level wrappers over the C ABI (include/csmoe.h).
+
+Each function takes CUDA torch tensors, allocates outputs with torch (PyTorch owns device memory) and launches the
+corresponding libcsmoe kernel on the current stream.  No computation happens here and nothing falls back to PyTorch or
+the CPU: a non-CUDA tensor or a failing call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import (ACT_GELU, ACT_GELU_TANH, ACT_NONE, ACT_RELU, ACT_SILU, ACT_SILU_GLU, BF16, F32, GEMM_REDUCE,
+                   GEMM_ROWS, ROW_TILE, GemmArgs, check)
+
+__all__ = [
+    "Route", "route_build", "router_fwd", "topk_renorm", "gather_rows", "combine_fwd", "combine_bwd_w",
+    "scatter_reduce", "gemm_rows", "gemm_reduce", "act_fwd", "act_bwd", "bias_grad", "cast_bf16", "affinity_fwd",
+    "affinity_bwd", "ACT_NONE", "ACT_RELU", "ACT_GELU", "ACT_GELU_TANH", "ACT_SILU", "ACT_SILU_GLU",
+]
+
+launch_count = 0  # number of libcsmoe kernel-launching calls issued (bench.py reports it)
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.bfloat16:
+        return BF16
+    if t.dtype == torch.float32:
+        return F32
+    raise TypeError(f"libcsmoe supports bfloat16 and float32 tensors, got {t.dtype}")
+
+
+def _cuda(*ts: Optional[torch.Tensor]) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("libcsmoe kernels need CUDA tensors; there is no CPU path in this package")
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _call(name: str, *args) -> None:
+    global launch_count
+    launch_count += 1
+    check(getattr(_lib.load(), name)(*args), name)
+
+
+# ----------------------------------------------------------------------------------------------- routing metadata
+@dataclass
+class Route:
+    """Permutation maps between slot order (t*K + k) and the padded expert-major row space."""
+    num_experts: int
+    top_k: int
+    n_slots: int
+    row_cap: int
+    sel: torch.Tensor          # [n_slots] int32 expert of each slot
+    counts: torch.Tensor       # [E] int32
+    offsets: torch.Tensor      # [E+1] int32 (exclusive scan of counts)
+    pad_offsets: torch.Tensor  # [E+1] int32 (segment starts, multiples of ROW_TILE)
+    sorted_sel: torch.Tensor   # [n_slots] int32  (reference: ssel)
+    sort_index: torch.Tensor   # [n_slots] int64  (reference: out_index; in_index = sort_index // K)
+    slot_to_row: torch.Tensor  # [n_slots] int32
+    row_to_slot: torch.Tensor  # [row_cap] int32, -1 on padding rows
+    tile_expert: torch.Tensor  # [row_cap / ROW_TILE] int32, -1 past the end
+
+
+def route_row_cap(n_slots: int, num_experts: int) -> int:
+    return int(_lib.load().csmoe_route_row_cap(n_slots, num_experts))
+
+
+def route_build(sel: torch.Tensor, num_experts: int) -> Route:
+    """sel: [T, K] (or flat) integer expert ids on CUDA."""
+    _cuda(sel)
+    top_k = sel.shape[-1] if sel.dim() > 1 else 1
+    flat = sel.reshape(-1)
+    if flat.dtype != torch.int32:
+        flat = flat.to(torch.int32)
+    flat = flat.contiguous()
+    n = flat.numel()
+    dev = flat.device
+    lib = _lib.load()
+    row_cap = int(lib.csmoe_route_row_cap(n, num_experts))
+    ws = torch.empty(max(int(lib.csmoe_route_workspace_bytes(n, num_experts)) // 4, 1), dtype=torch.int32, device=dev)
+    i32 = dict(dtype=torch.int32, device=dev)
+    counts = torch.empty(num_experts, **i32)
+    offsets = torch.empty(num_experts + 1, **i32)
+    pad_offsets = torch.empty(num_experts + 1, **i32)
+    sorted_sel = torch.empty(n, **i32)
+    sort_index = torch.empty(n, dtype=torch.int64, device=dev)
+    slot_to_row = torch.empty(n, **i32)
+    row_to_slot = torch.empty(row_cap, **i32)
+    tile_expert = torch.empty(row_cap // ROW_TILE, **i32)
+    _call("csmoe_route_build", _p(flat), n, num_experts, row_cap, _p(counts), _p(offsets), _p(pad_offsets),
+          _p(sorted_sel), _p(sort_index), _p(slot_to_row), _p(row_to_slot), _p(tile_expert), _p(ws), _stream())
+    return Route(num_experts, top_k, n, row_cap, flat, counts, offsets, pad_offsets, sorted_sel, sort_index,
+                 slot_to_row, row_to_slot, tile_expert)
+
+
+# ----------------------------------------------------------------------------------------------- router
+def router_fwd(x: torch.Tensor, wg: torch.Tensor, top_k: int):
+    """x [T, D], wg [E, D] (same dtype) -> logits [T,E] (x dtype), probs [T,E] f32, topk_w [T,K] f32, topk_idx [T,K] i32."""
+    _cuda(x, wg)
+    assert x.dim() == 2 and wg.dim() == 2 and x.shape[1] == wg.shape[1] and x.dtype == wg.dtype
+    x, wg = x.contiguous(), wg.contiguous()
+    T, D = x.shape
+    E = wg.shape[0]
+    logits = torch.empty(T, E, dtype=x.dtype, device=x.device)
+    probs = torch.empty(T, E, dtype=torch.float32, device=x.device)
+    tw = torch.empty(T, top_k, dtype=torch.float32, device=x.device)
+    ti = torch.empty(T, top_k, dtype=torch.int32, device=x.device)
+    _call("csmoe_router_fwd", _p(x), _p(wg), _dt(x), T, D, E, top_k, _p(logits), _p(probs), _p(tw), _p(ti), _stream())
+    return logits, probs, tw, ti
+
+
+def topk_renorm(scores: torch.Tensor, top_k: int, sigmoid: bool = False, round_dtype: torch.dtype = torch.float32,
+                round_out: bool = False):
+    """scores [T, E] f32 -> (w [T,K] f32, idx [T,K] i32); w = topk / round(sum topk)."""
+    _cuda(scores)
+    scores = scores.contiguous()
+    assert scores.dtype == torch.float32 and scores.dim() == 2
+    T, E = scores.shape
+    tw = torch.empty(T, top_k, dtype=torch.float32, device=scores.device)
+    ti = torch.empty(T, top_k, dtype=torch.int32, device=scores.device)
+    mode = (1 if sigmoid else 0) | (2 if round_out else 0)
+    rd = BF16 if round_dtype == torch.bfloat16 else F32
+    _call("csmoe_topk_renorm", _p(scores), T, E, top_k, mode, rd, _p(tw), _p(ti), _stream())
+    return tw, ti
+
+
+# ----------------------------------------------------------------------------------------------- permutation
+def gather_rows(src: torch.Tensor, route: Route, slot_w: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """src [T, D] -> [row_cap, D] in the padded expert-major space (zeros on padding rows)."""
+    _cuda(src, slot_w)
+    src = src.contiguous()
+    T, D = src.shape
+    dst = torch.empty(route.row_cap, D, dtype=src.dtype, device=src.device)
+    if slot_w is not None:
+        slot_w = slot_w.reshape(-1).contiguous()
+        assert slot_w.dtype == torch.float32 and slot_w.numel() == route.n_slots
+    _call("csmoe_gather_rows", _p(src), _dt(src), T, D, route.top_k, _p(route.row_to_slot), route.row_cap, _p(slot_w),
+          _p(dst), _stream())
+    return dst
+
+
+def combine_fwd(y: torch.Tensor, slot_to_row: torch.Tensor, sel: torch.Tensor, w: torch.Tensor, T: int, top_k: int,
+                round_each: bool = False, round_w: bool = False) -> torch.Tensor:
+    _cuda(y, slot_to_row, sel, w)
+    D = y.shape[-1]
+    out = torch.empty(T, D, dtype=y.dtype, device=y.device)
+    w = w.reshape(-1).contiguous()
+    assert w.dtype == torch.float32 and slot_to_row.dtype == torch.int32 and sel.dtype == torch.int32
+    flags = (1 if round_each else 0) | (2 if round_w else 0)
+    _call("csmoe_combine_fwd", _p(y), _dt(y), T, D, top_k, _p(slot_to_row), _p(sel), _p(w), flags, _p(out), _stream())
+    return out
+
+
+def combine_bwd_w(y: torch.Tensor, dout: torch.Tensor, slot_to_row: torch.Tensor, T: int, top_k: int) -> torch.Tensor:
+    _cuda(y, dout, slot_to_row)
+    dout = dout.contiguous()
+    assert y.dtype == dout.dtype
+    D = y.shape[-1]
+    dw = torch.empty(T, top_k, dtype=torch.float32, device=y.device)
+    _call("csmoe_combine_bwd_w", _p(y), _p(dout), _dt(y), T, D, top_k, _p(slot_to_row), _p(dw), _stream())
+    return dw
+
+
+def scatter_reduce(g: torch.Tensor, slot_to_row: torch.Tensor, T: int, top_k: int,
+                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """dx[t] = sum_k g[row(t,k)]; adds into `out` when given."""
+    _cuda(g, slot_to_row, out)
+    D = g.shape[-1]
+    acc = out is not None
+    if out is None:
+        out = torch.empty(T, D, dtype=g.dtype, device=g.device)
+    _call("csmoe_scatter_reduce", _p(g), _dt(g), T, D, top_k, _p(slot_to_row), 1 if acc else 0, _p(out), _stream())
+    return out
+
+
+# ----------------------------------------------------------------------------------------------- grouped GEMM
+def _gemm(args: GemmArgs) -> None:
+    _call("csmoe_grouped_gemm", C.byref(args), _stream())
+
+
+def gemm_rows(a: torch.Tensor, w: torch.Tensor, *, w_is_kn: bool, route: Optional[Route] = None,
+              dense_rows: int = 0, a_expert_rows: int = 0, bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
+              want_preact: bool = False, out_dtype: Optional[torch.dtype] = None):
+    """C[row] = A[row] . W[expert(row)] (+bias, activation).
+
+    a: [rows, k] bf16.  w: [E, n, k] (w_is_kn=False, nn.Linear layout) or [E, k, n] (w_is_kn=True).
+    route given: rows are the padded expert-major space.  dense_rows > 0: every expert processes `dense_rows` rows of
+    `a` (shared when a_expert_rows == 0) and C is [E * dense_rows, n].
+    Returns C, or (C, preact) when want_preact.
+    """
+    _cuda(a, w, bias)
+    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16, "grouped GEMM operands must be bfloat16"
+    assert a.dim() == 2 and w.dim() == 3 and a.stride(1) == 1 and w.stride(2) == 1
+    E = w.shape[0]
+    k = a.shape[1]
+    n = w.shape[2] if w_is_kn else w.shape[1]
+    assert (w.shape[1] if w_is_kn else w.shape[2]) == k, f"contraction mismatch: a {tuple(a.shape)} w {tuple(w.shape)}"
+    out_dtype = out_dtype or a.dtype
+    g = GemmArgs()
+    g.mode, g.b_layout, g.num_experts = GEMM_ROWS, 1 if w_is_kn else 0, E
+    if dense_rows:
+        assert dense_rows % ROW_TILE == 0
+        m = E * dense_rows
+        g.dense, g.dense_rows, g.a_expert_rows = 1, dense_rows, a_expert_rows
+    else:
+        assert route is not None and a.shape[0] == route.row_cap
+        m = route.row_cap
+        g.tile_expert = _p(route.tile_expert)
+    g.m, g.n, g.k = m, n, k
+    g.a, g.lda = _p(a), a.stride(0)
+    g.b, g.ldb, g.b_expert_stride = _p(w), w.stride(1), w.stride(0)
+    c = torch.empty(m, n, dtype=out_dtype, device=a.device)
+    g.c, g.ldc, g.c_dtype = _p(c), n, _dt(c)
+    g.act = act
+    pre = None
+    if want_preact:
+        pre = torch.empty(m, n, dtype=out_dtype, device=a.device)
+        g.preact, g.ldpre = _p(pre), n
+    if bias is not None:
+        bias = bias.contiguous()
+        assert bias.shape == (E, n)
+        g.bias, g.bias_dtype = _p(bias), _dt(bias)
+    _gemm(g)
+    return (c, pre) if want_preact else c
+
+
+def gemm_reduce(a: torch.Tensor, b: torch.Tensor, num_experts: int, *, route: Optional[Route] = None,
+                dense_rows: int = 0, a_expert_rows: int = 0, b_expert_rows: int = 0,
+                out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
+    """C[e] = A[rows of e]^T . B[rows of e]  -> [E, a.shape[1], b.shape[1]] (wgrad)."""
+    _cuda(a, b)
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
+    assert a.dim() == 2 and b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1
+    m, n = a.shape[1], b.shape[1]
+    g = GemmArgs()
+    g.mode, g.num_experts = GEMM_REDUCE, num_experts
+    if dense_rows:
+        assert dense_rows % ROW_TILE == 0
+        g.dense, g.dense_rows, g.a_expert_rows, g.b_expert_stride = 1, dense_rows, a_expert_rows, b_expert_rows
+        g.k = dense_rows
+    else:
+        assert route is not None and a.shape[0] == route.row_cap and b.shape[0] == route.row_cap
+        g.pad_offsets = _p(route.pad_offsets)
+        g.k = route.row_cap
+    g.m, g.n = m, n
+    g.a, g.lda = _p(a), a.stride(0)
+    g.b, g.ldb = _p(b), b.stride(0)
+    c = torch.empty(num_experts, m, n, dtype=out_dtype, device=a.device)
+    g.c, g.ldc, g.c_expert_stride, g.c_dtype = _p(c), n, m * n, _dt(c)
+    _gemm(g)
+    return c
+
+
+# ----------------------------------------------------------------------------------------------- elementwise
+def act_fwd(z: torch.Tensor, act: int) -> torch.Tensor:
+    _cuda(z)
+    assert z.dim() == 2 and z.stride(1) == 1
+    rows = z.shape[0]
+    cols = z.shape[1] // 2 if act == ACT_SILU_GLU else z.shape[1]
+    h = torch.empty(rows, cols, dtype=z.dtype, device=z.device)
+    _call("csmoe_act_fwd", _p(z), _dt(z), rows, cols, z.stride(0), act, _p(h), cols, _stream())
+    return h
+
+
+def act_bwd(z: torch.Tensor, dh: torch.Tensor, act: int) -> torch.Tensor:
+    _cuda(z, dh)
+    dh = dh.contiguous()
+    rows = z.shape[0]
+    cols = z.shape[1] // 2 if act == ACT_SILU_GLU else z.shape[1]
+    assert dh.shape == (rows, cols) and dh.dtype == z.dtype
+    dz = torch.empty_like(z)
+    _call("csmoe_act_bwd", _p(z), _p(dh), _dt(z), rows, cols, z.stride(0), cols, act, _p(dz), _stream())
+    return dz
+
+
+def bias_grad(g: torch.Tensor, num_experts: int, *, route: Optional[Route] = None, dense_rows: int = 0,
+              out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    _cuda(g)
+    n = g.shape[1]
+    out_dtype = out_dtype or g.dtype
+    db = torch.empty(num_experts, n, dtype=out_dtype, device=g.device)
+    po = None if dense_rows else _p(route.pad_offsets)
+    _call("csmoe_bias_grad", _p(g), _dt(g), g.stride(0), n, num_experts, po, 1 if dense_rows else 0, dense_rows, _p(db),
+          _dt(db), _stream())
+    return db
+
+
+def cast_bf16(src: torch.Tensor) -> torch.Tensor:
+    """fp32 -> bf16 copy (parameters under autocast)."""
+    _cuda(src)
+    if src.dtype == torch.bfloat16:
+        return src
+    src = src.contiguous()
+    dst = torch.empty(src.shape, dtype=torch.bfloat16, device=src.device)
+    _call("csmoe_cast_f32_bf16", _p(src), _p(dst), src.numel(), _stream())
+    return dst
+
+
+# ----------------------------------------------------------------------------------------------- competition
+def affinity_fwd(y: torch.Tensor, num_experts: int, T: int, t_pad: int) -> torch.Tensor:
+    """y [E * t_pad, D] -> aff [T, E] f32 (values rounded to y.dtype)."""
+    _cuda(y)
+    D = y.shape[-1]
+    aff = torch.empty(T, num_experts, dtype=torch.float32, device=y.device)
+    _call("csmoe_affinity_fwd", _p(y), _dt(y), num_experts, T, t_pad, D, _p(aff), _stream())
+    return aff
+
+
+def affinity_bwd(y: torch.Tensor, daff: torch.Tensor, num_experts: int, T: int, t_pad: int,
+                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _cuda(y, daff, out)
+    D = y.shape[-1]
+    daff = daff.contiguous().float()
+    acc = out is not None
+    if out is None:
+        out = torch.zeros_like(y) if t_pad != T else torch.empty_like(y)
+    _call("csmoe_affinity_bwd", _p(y), _p(daff), _dt(y), num_experts, T, t_pad, D, 1 if acc else 0, _p(out), _stream())
+    return out

@@ -1,0 +1,373 @@
+"""Generate tests/golden/*.pt by running the UNMODIFIED reference modules (imported from /root/reference).
+
+Run in the build container only:   python -m oracle.gen_golden
+The GPU box has no /root/reference; tests read only the committed fixtures.  Each fixture stores seeded inputs, weights,
+the forced schedule branch, and the reference's outputs / losses / gradients.  While generating, the oracle restatement
+is replayed on the same data and must agree (this is the oracle's pin; tests/test_oracle_golden.py repeats it).
+
+Reference entry points exercised:
+  moe_model/model/moe/register.py:18 get_moe("competesmoe") -> competesmoe.py:9 CompeteSMoE (forward :337)
+  moe_pretrain_model/layers/moe/competesmoe.py:38 CompeteSMoE (forward :524), through the import shim of SURVEY.md B.1
+  moe_pretrain_model/layers/cvmm.py:460 CVMM autograd function run on the Triton interpreter
+"""
+from __future__ import annotations
+
+import contextlib
+import importlib
+import io
+import os
+import sys
+import types
+from pathlib import Path
+from types import SimpleNamespace
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+REF = Path("/root/reference")
+OUT = Path(__file__).resolve().parent.parent / "tests" / "golden"
+
+
+def quiet():
+    return contextlib.redirect_stdout(io.StringIO())
+
+
+# ------------------------------------------------------------------------------------------------ multimodal
+def mm_args(**kw):
+    base = dict(rate_flip=0.05, warm_up=0.0, max_compete_in_iter=3, hybrid=False, router_theta=1.0,
+                router_loss_coef=0.01, diversity_loss_coef=0.01, bal_comp_loss_coef=0.01, balance_loss_coef=0.01,
+                router_z_loss_coef=0.001, norm_sigmoid=False, init_weight=True, moe_name="competesmoe")
+    base.update(kw)
+    return SimpleNamespace(**base)
+
+
+class _TinyGLU(nn.Module):
+    """Same arithmetic and parameter names as transformers' Phi3MLP (gate_up_proj / down_proj, SiLU-GLU)."""
+
+    def __init__(self, d, f):
+        super().__init__()
+        self.gate_up_proj = nn.Linear(d, 2 * f, bias=False)
+        self.down_proj = nn.Linear(f, d, bias=False)
+        self.activation_fn = nn.SiLU()
+
+    def forward(self, x):
+        up = self.gate_up_proj(x)
+        gate, up = up.chunk(2, dim=-1)
+        return self.down_proj(up * self.activation_fn(gate))
+
+
+def build_expert(kind, d_in, d_out, f, ref_mods):
+    if kind == "siglip":
+        cfg = SimpleNamespace(hidden_act="gelu_pytorch_tanh", hidden_size=d_in, intermediate_size=f)
+        return ref_mods["siglip"].SiglipMLP(cfg)
+    if kind == "projector":
+        return nn.Sequential(nn.Linear(d_in, d_out), nn.GELU(), nn.Linear(d_out, d_out))
+    if kind == "glu":
+        try:
+            from transformers.models.phi3.modeling_phi3 import Phi3MLP
+            from transformers import Phi3Config
+            return Phi3MLP(Phi3Config(hidden_size=d_in, intermediate_size=f, hidden_act="silu"))
+        except Exception:
+            return _TinyGLU(d_in, f)
+    raise ValueError(kind)
+
+
+def expert_weights(kind, mod):
+    if kind == "siglip":
+        return {"kind": "mlp", "act": "gelu_tanh", "w1": mod.fc1.weight, "b1": mod.fc1.bias, "w2": mod.fc2.weight,
+                "b2": mod.fc2.bias}
+    if kind == "projector":
+        return {"kind": "mlp", "act": "gelu", "w1": mod[0].weight, "b1": mod[0].bias, "w2": mod[2].weight,
+                "b2": mod[2].bias}
+    return {"kind": "glu", "act": "silu", "w1": mod.gate_up_proj.weight, "w2": mod.down_proj.weight}
+
+
+def gen_multimodal(ref_mods, name, kind, d_in, d_out, f, E, K, B, N, competition, dtype=torch.float32, upcycled=False,
+                   seed=0, **argkw):
+    from oracle import multimodal as om
+
+    torch.manual_seed(seed)
+    args = mm_args(**argkw)
+    with quiet():
+        if upcycled:
+            expert = build_expert(kind, d_in, d_out, f, ref_mods)
+        else:
+            expert = nn.ModuleList([build_expert(kind, d_in, d_out, f, ref_mods) for _ in range(E)])
+        layer = ref_mods["get_moe"]("competesmoe")(in_embed_dim=d_in, out_embed_dim=d_out, num_of_experts=E,
+                                                  num_selected=K, expert=expert, args=args)
+        layer = layer.to(dtype)
+        layer.set_total_steps(4, id_layer=0, prob_flips_final={})
+    layer.prob_flips = torch.full((4,), bool(competition))
+    layer.set_current_steps(1)
+    g = torch.Generator().manual_seed(1234 + seed)
+    x = torch.randn(B, N, d_in, generator=g).to(dtype).requires_grad_(True)
+    dy = torch.randn(B, N, d_out, generator=g).to(dtype)
+    captured = {}
+    orig_compute_moe = layer.compute_moe
+
+    def spy(*a, **kw):  # record the routing decision the reference takes (moe.py:172 arguments)
+        captured["selected"] = kw["selected_experts"].detach().clone()
+        captured["weights"] = kw["weights"].detach().clone()
+        return orig_compute_moe(*a, **kw)
+
+    layer.compute_moe = spy
+    out, aux, _, info = layer(x)
+    loss = (out.float() * dy.float()).sum() + aux.float()
+    loss.backward()
+    fx = {
+        "meta": dict(name=name, kind=kind, d_in=d_in, d_out=d_out, f=f, E=E, K=K, B=B, N=N, competition=competition,
+                     dtype=str(dtype), upcycled=upcycled, args=vars(args)),
+        "x": x.detach().clone(), "dy": dy, "gate_w": layer.gate.weight.detach().clone(),
+        "experts": [{k: (v.detach().clone() if torch.is_tensor(v) else v)
+                     for k, v in expert_weights(kind, m).items()} for m in layer.experts],
+        "out": out.detach().clone(), "aux": aux.detach().clone(), "info": {k: v.clone() for k, v in info.items()},
+        "dx": x.grad.clone(), "dgate_w": None if layer.gate.weight.grad is None else layer.gate.weight.grad.clone(),
+        "dexperts": [{n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None} for m in layer.experts],
+    }
+    # ---- pin the oracle against the reference on this very case
+    x2 = fx["x"].clone().requires_grad_(True)
+    gw = fx["gate_w"].clone().requires_grad_(True)
+    exps = [{k: (v.clone().requires_grad_(True) if torch.is_tensor(v) else v) for k, v in e.items()}
+            for e in fx["experts"]]
+    o_out, o_aux, _, o_info, dbg = om.competesmoe_forward(x2, gw, exps, K, d_out, args, competition)
+    ((o_out.float() * dy.float()).sum() + o_aux.float()).backward()
+    tol = dict(rtol=1e-5, atol=1e-6) if dtype == torch.float32 else dict(rtol=2e-2, atol=2e-2)
+    # Routing: bit-exact except tokens whose k-th/(k+1)-th score margin is < 1e-3 (torch.topk's tie order is
+    # unspecified; bf16 affinity scores tie often).  Those tokens are counted and excluded from the value checks.
+    scores = dbg["affinity"] if competition else dbg["gate_softmax"]
+    margin = om.topk_margin(scores, K)
+    agree = (captured["selected"] == dbg["selected"]).all(-1)
+    assert bool((margin[~agree] < 1e-3).all()), "routing differs on a token with margin >= 1e-3"
+    n_exempt = int((~agree).sum())
+    if not upcycled:  # with identical experts every score ties and the reference's order is arbitrary
+        torch.testing.assert_close(o_out[agree], fx["out"][agree], **tol)
+        torch.testing.assert_close(x2.grad[agree], fx["dx"][agree], **tol)
+        torch.testing.assert_close(captured["weights"][agree].float(), dbg["weights"][agree].float(), **tol)
+    if n_exempt == 0:
+        torch.testing.assert_close(o_aux.float(), fx["aux"].float(), **tol)
+        for k_ in info:
+            torch.testing.assert_close(o_info[k_].float(), info[k_].float(), **tol)
+    fx["selected"] = captured["selected"]          # the reference's own decision
+    fx["weights"] = captured["weights"]
+    fx["selected_oracle"] = dbg["selected"].clone()
+    fx["n_exempt"] = n_exempt
+    torch.save(fx, OUT / f"{name}.pt")
+    print(f"  wrote {name}.pt  (oracle == reference, {n_exempt} low-margin tokens exempt)  aux={float(aux.detach()):.6f} "
+          f"info={ {k: round(float(v), 6) for k, v in info.items()} }")
+
+
+def load_multimodal_reference():
+    sys.path.insert(0, str(REF))
+    with quiet():
+        importlib.import_module("moe_model.model.moe")
+        reg = importlib.import_module("moe_model.model.moe.register")
+        siglip = importlib.import_module("moe_model.model.multimodal_encoder.siglip_smoe")
+    return {"get_moe": reg.get_moe, "siglip": siglip}
+
+
+# ------------------------------------------------------------------------------------------------ pretrain
+def load_pretrain_reference():
+    R = str(REF / "moe_pretrain_model")
+    sys.path.insert(0, R)
+
+    def stub(name, path):
+        m = types.ModuleType(name)
+        m.__path__ = [path]
+        sys.modules[name] = m
+        return m
+
+    L = stub("layers", R + "/layers")
+    LM = stub("layers.moe", R + "/layers/moe")
+    FW = stub("framework", R + "/framework")
+    with quiet():
+        cv = importlib.import_module("layers.cvmm")
+        L.cvmm, L.cvmm_prepare_sel = cv.cvmm, cv.cvmm_prepare_sel
+        FW.utils = importlib.import_module("framework.utils")
+        FW.layers = importlib.import_module("framework.layers")
+        base = importlib.import_module("layers.moe.moe")
+        LM.MoE = base.MoE
+        reg = importlib.import_module("layers.moe.register")
+        comp = importlib.import_module("layers.moe.competesmoe")
+    return {"cvmm": cv, "base": base, "get_moe": reg.get_moe, "comp": comp}
+
+
+def pt_args(**kw):
+    base = dict(warm_up=0.0, rate_flip=0.07, stop_after=8, max_compete_in_iter=3, is_cosine=False, is_norm_weight=False,
+                norm_sigmoid=False, scale_weight=1.0, hybrid=False, tribrid=False, in_topk=False,
+                balance_affinity=False, balance_loss_coef=0.01, balance_loss_coef_comp=0.01, router_loss_coef=0.01,
+                router_theta=1.0, test_only=False)
+    base.update(kw)
+    return SimpleNamespace(**base)
+
+
+def gen_pretrain(pm, name, D, E, H, K, B, N, competition, seed=0, **argkw):
+    """Reference layer with its `cvmm` name bound to the oracle's per-expert restatement (the Triton op needs a GPU);
+    the restatement itself is pinned by gen_cvmm_interpreter below."""
+    from oracle import pretrain as op
+
+    def cvmm_standin(x, sel, keys):
+        if not isinstance(sel, pm["cvmm"].CVMMSel):
+            sel = pm["cvmm"].cvmm_prepare_sel(sel, keys.shape[0])
+        s = op.Sel(sel.raw_sel, sel.sel, sel.sel_index, sel.out_index, sel.reduction_weight)
+        return op.cvmm(x, s, keys, torch.float32)
+
+    pm["base"].cvmm = cvmm_standin
+    pm["comp"].cvmm = cvmm_standin
+    args = pt_args(**argkw)
+    torch.manual_seed(seed)
+    cwd = os.getcwd()
+    os.chdir("/tmp")  # set_total_steps appends to ./file_path.txt (competesmoe.py:218-221)
+    try:
+        with quiet():
+            layer = pm["get_moe"]("competesmoe")(D, E, H, n_heads=K, args=args, activation=F.relu, selection_mode="gate",
+                                                 log_interval=None)
+            layer.train()
+            layer.regularization_present = True
+            layer.set_total_steps(id_layer=0)
+    finally:
+        os.chdir(cwd)
+    layer.prob_flips_final[0][:] = bool(competition)
+    layer.set_current_steps(1)
+    g = torch.Generator().manual_seed(1234 + seed)
+    x = torch.randn(B, N, D, generator=g).requires_grad_(True)
+    dy = torch.randn(B, N, D, generator=g)
+    out = layer(x, id_layer=0)
+    regs = layer.get_reg_loss()
+    loss = (out * dy).sum() + sum(regs.values())
+    loss.backward()
+    fx = {
+        "meta": dict(name=name, D=D, E=E, H=H, K=K, B=B, N=N, competition=competition, args=vars(args)),
+        "x": x.detach().clone(), "dy": dy, "w_gate": layer.w_gate.detach().clone(), "keys": layer.keys.detach().clone(),
+        "values": layer.values.detach().clone(), "out": out.detach().clone(),
+        "regs": {k: v.detach().clone() for k, v in regs.items()},
+        "dx": x.grad.clone(), "dw_gate": layer.w_gate.grad.clone(), "dkeys": layer.keys.grad.clone(),
+        "dvalues": layer.values.grad.clone(),
+    }
+    x2 = fx["x"].clone().requires_grad_(True)
+    wg, ks, vs = (fx[n].clone().requires_grad_(True) for n in ("w_gate", "keys", "values"))
+    o_out, o_regs, dbg = op.competesmoe_forward(x2, wg, ks, vs, K, args, competition)
+    ((o_out * dy).sum() + sum(o_regs.values())).backward()
+    tol = dict(rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(o_out, fx["out"], **tol)
+    assert set(o_regs) == set(regs), (set(o_regs), set(regs))
+    for k_ in regs:
+        torch.testing.assert_close(o_regs[k_], fx["regs"][k_], **tol)
+    torch.testing.assert_close(x2.grad, fx["dx"], **tol)
+    torch.testing.assert_close(wg.grad, fx["dw_gate"], **tol)
+    torch.testing.assert_close(ks.grad, fx["dkeys"], **tol)
+    torch.testing.assert_close(vs.grad, fx["dvalues"], **tol)
+    fx["selected"] = dbg["selected"].clone()
+    torch.save(fx, OUT / f"{name}.pt")
+    print(f"  wrote {name}.pt  (oracle == reference)  regs={ {k: round(float(v), 6) for k, v in regs.items()} }")
+
+
+def gen_cvmm_interpreter(name="cvmm_triton_interp"):
+    """Run the reference's own CVMM autograd function with its Triton kernels on the Triton interpreter (fixed tiles,
+    autotuner bypassed) and store inputs/outputs/gradients.  Must run in a fresh process with TRITON_INTERPRET=1."""
+    from oracle import pretrain as op
+
+    pm = load_pretrain_reference()
+    cv = pm["cvmm"]
+    import triton
+
+    def fwd_call(x, sel_index, sel, keys, out_dtype, out_index):
+        x = x.flatten(end_dim=-2)
+        sel_shape = sel.shape
+        sel = sel.flatten()
+        M = sel.shape[0]
+        O, K, N = keys.shape
+        out = torch.empty((M, N), dtype=out_dtype)
+        none = out_index.numel() == 1 and out_index == -1
+        BM = BN = BK = 32
+        grid = (triton.cdiv(M, BM) * triton.cdiv(N, BN),)
+        cv.cvmm_kernel.fn[grid](x, keys, out, sel_index, sel, out_index, M, N, K, x.stride(0), x.stride(1),
+                                keys.stride(0), keys.stride(1), keys.stride(2), out.stride(0), out.stride(1),
+                                sel_index.stride(0), sel.stride(0), 0 if none else out_index.stride(0),
+                                out_index_is_none=none, dtype_id=cv.dtype_to_type_id(out.dtype), allow_tf32=False,
+                                BLOCK_SIZE_M=BM, BLOCK_SIZE_N=BN, BLOCK_SIZE_K=BK, GROUP_SIZE_M=8)
+        return out.view(*sel_shape, N)
+
+    def bwd_call(x, sel_index, sel, grads, n_experts, key_dtype, op_dtype, out_index):
+        x = x.flatten(end_dim=-2).transpose(0, 1)
+        grads = grads.flatten(end_dim=-2)
+        sel = sel.flatten()
+        M, _ = x.shape
+        K, N = grads.shape
+        out = torch.zeros((n_experts, M, N), dtype=key_dtype)
+        none = out_index.numel() == 1 and out_index == -1
+        BM = BN = 32
+        BK, KB = 16, 4
+        grid = (triton.cdiv(M, BM) * triton.cdiv(N, BN), triton.cdiv(K, BK * KB))
+        cv.cvmm_backward_kernel3.fn[grid](x, grads, out, sel_index, sel, out_index, M, N, K, x.stride(0), x.stride(1),
+                                          grads.stride(0), grads.stride(1), out.stride(0), out.stride(1), out.stride(2),
+                                          sel_index.stride(0), sel.stride(0), 0 if none else out_index.stride(0),
+                                          out_index_is_none=none, out_dtype_id=cv.dtype_to_type_id(out.dtype),
+                                          dtype_id=cv.dtype_to_type_id(op_dtype), allow_tf32=False, BLOCK_SIZE_M=BM,
+                                          BLOCK_SIZE_N=BN, BLOCK_SIZE_K=BK, GROUP_SIZE_M=8, K_BLOCKS=KB)
+        return out
+
+    cv.cvmm_triton_call = fwd_call
+    cv.cvmm_triton_backward = bwd_call
+    torch.manual_seed(0)
+    B, N, D, H, E, K = 2, 12, 32, 32, 4, 2
+    x = torch.randn(B, N, D, requires_grad=True)
+    keys = (torch.randn(E, D, H) / D ** 0.5).requires_grad_(True)
+    values = (torch.randn(E, H, D) / H ** 0.5).requires_grad_(True)
+    selx = torch.stack([torch.randperm(E)[:K] for _ in range(B * N)]).view(B, N, K).int()
+    w = torch.rand(B, N, K).requires_grad_(True)
+    dy = torch.randn(B, N, D)
+    # reference: both call patterns of compute_moe_main (competesmoe.py:510-522); stable sort for the index maps
+    s = op.prepare_sel2(selx)
+    rs = cv.CVMMSel(s.raw_sel, s.sel, s.sel_index, s.out_index, None)
+    scores = cv.CVMM.apply(x, rs.sel_index, rs.sel, keys, rs.out_index, None)
+    act = F.relu(scores)
+    out = cv.CVMM.apply(act, rs.out_index, rs.sel, values, None, w)
+    (out * dy).sum().backward()
+    fx = {"x": x.detach().clone(), "keys": keys.detach().clone(), "values": values.detach().clone(), "sel": selx,
+          "w": w.detach().clone(), "dy": dy, "scores": scores.detach().clone(), "out": out.detach().clone(),
+          "dx": x.grad.clone(), "dkeys": keys.grad.clone(), "dvalues": values.grad.clone(), "dw": w.grad.clone()}
+    # oracle replay
+    x2, k2, v2, w2 = (fx[n].clone().requires_grad_(True) for n in ("x", "keys", "values", "w"))
+    o = op.compute_moe_main(x2, selx, w2, k2, v2, F.relu, torch.float32)
+    (o * dy).sum().backward()
+    tol = dict(rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(o, fx["out"], **tol)
+    torch.testing.assert_close(x2.grad, fx["dx"], **tol)
+    torch.testing.assert_close(k2.grad, fx["dkeys"], **tol)
+    torch.testing.assert_close(v2.grad, fx["dvalues"], **tol)
+    torch.testing.assert_close(w2.grad, fx["dw"], **tol)
+    torch.save(fx, OUT / f"{name}.pt")
+    print(f"  wrote {name}.pt  (oracle cvmm == reference Triton kernels on the interpreter)")
+
+
+def main():
+    OUT.mkdir(parents=True, exist_ok=True)
+    if os.environ.get("TRITON_INTERPRET") == "1":
+        gen_cvmm_interpreter()
+        return
+    print("multimodal reference (moe_model/model/moe):")
+    mm = load_multimodal_reference()
+    for comp in (False, True):
+        tag = "comp" if comp else "router"
+        gen_multimodal(mm, f"mm_siglip_{tag}_f32", "siglip", 64, 64, 128, 4, 2, 2, 24, comp)
+        gen_multimodal(mm, f"mm_projector_{tag}_f32", "projector", 48, 64, 64, 4, 2, 2, 16, comp, seed=1)
+        gen_multimodal(mm, f"mm_glu_{tag}_f32", "glu", 64, 64, 96, 4, 2, 2, 16, comp, seed=2)
+    gen_multimodal(mm, "mm_siglip_comp_hybrid_f32", "siglip", 64, 64, 128, 8, 2, 2, 16, True, seed=3, hybrid=True,
+                   router_theta=0.5)
+    gen_multimodal(mm, "mm_siglip_router_bf16", "siglip", 64, 64, 128, 4, 2, 2, 24, False, dtype=torch.bfloat16, seed=4)
+    gen_multimodal(mm, "mm_siglip_comp_bf16", "siglip", 64, 64, 128, 4, 2, 2, 24, True, dtype=torch.bfloat16, seed=4)
+    gen_multimodal(mm, "mm_siglip_comp_upcycled_f32", "siglip", 64, 64, 128, 4, 2, 2, 16, True, upcycled=True, seed=5)
+    print("pretrain reference (moe_pretrain_model/layers/moe):")
+    pm = load_pretrain_reference()
+    gen_pretrain(pm, "pt_router_f32", 64, 8, 32, 2, 2, 32, False)
+    gen_pretrain(pm, "pt_comp_f32", 64, 8, 32, 2, 2, 32, True, seed=1)
+    gen_pretrain(pm, "pt_comp_hybrid_bal_f32", 64, 16, 16, 4, 2, 16, True, seed=2, hybrid=True, balance_affinity=True,
+                 router_theta=0.5)
+    gen_pretrain(pm, "pt_comp_intopk_f32", 64, 8, 32, 2, 2, 16, True, seed=3, in_topk=True)
+    gen_pretrain(pm, "pt_comp_tribrid_f32", 64, 8, 32, 2, 2, 16, True, seed=4, tribrid=True)
+    print("done; now run:  TRITON_INTERPRET=1 python -m oracle.gen_golden")
+
+
+if __name__ == "__main__":
+    main()
