@@ -1,0 +1,253 @@
+"""Autograd functions that compose the libcsmoe kernels into the differentiable pieces of the MoE layer.
+
+  GateFn        router GEMM + softmax + top-k (csmoe_router_fwd)         reference: competesmoe.py:301-320
+  SparseFFNFn   permute -> grouped GEMMs -> combine, and its backward     reference: moe.py:172-213 / cvmm.py:460-551
+  DenseFFNFn    every expert on every token (competition step)           reference: competesmoe.py:240-245 / :399-403
+  AffinityFn    mean softplus score of each (token, expert)              reference: competesmoe.py:243 / :403
+  SelectCombineFn  gate-weighted sum of the selected dense outputs        reference: recomputed by compute_moe (:374)
+
+Stacked expert weights use one of two layouts: "nk" = [E, n, k] (nn.Linear.weight) or "kn" = [E, k, n] (sigma-MoE
+keys / values).  All GEMM operands are bfloat16; fp32 accumulation happens in TMEM.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import ops
+from ._lib import ROW_TILE
+
+
+@dataclass(frozen=True)
+class FFNSpec:
+    """Static description of the expert FFN."""
+    act: int                 # ops.ACT_*
+    kn_layout: bool = False  # False: w1 [E,F,D], w2 [E,Dout,F] (nn.Linear);  True: w1 [E,D,H], w2 [E,H,Dout] (sigma-MoE)
+    round_each: bool = True  # combine: round the running sum to the activation dtype after every expert (moe.py:204)
+    round_w: bool = False    # combine: round the routing weight to the activation dtype first (cvmm.py:483)
+
+    @property
+    def glu(self) -> bool:
+        return self.act == ops.ACT_SILU_GLU
+
+
+def _bf16(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    if t is None or t.dtype == torch.bfloat16:
+        return t
+    return ops.cast_bf16(t)
+
+
+def _pad_rows(x: torch.Tensor, rows: int) -> torch.Tensor:
+    if x.shape[0] == rows:
+        return x
+    pad = torch.zeros(rows - x.shape[0], x.shape[1], dtype=x.dtype, device=x.device)
+    return torch.cat([x, pad], dim=0)
+
+
+def _ffn_first(xp, w1, b1, spec: FFNSpec, **where):
+    """z (pre-activation, with bias) and h = act(z) for the first projection."""
+    if spec.glu:
+        z = ops.gemm_rows(xp, w1, w_is_kn=spec.kn_layout, bias=b1, **where)
+        return z, ops.act_fwd(z, spec.act)
+    if spec.act == ops.ACT_NONE:
+        z = ops.gemm_rows(xp, w1, w_is_kn=spec.kn_layout, bias=b1, **where)
+        return z, z
+    h, z = ops.gemm_rows(xp, w1, w_is_kn=spec.kn_layout, bias=b1, act=spec.act, want_preact=True, **where)
+    return z, h
+
+
+# ------------------------------------------------------------------------------------------------ router
+class GateFn(Function):
+    """(x [T,D], wg [E,D]) -> logits [T,E] (x dtype), probs [T,E] f32, topk_w [T,K] f32, topk_idx [T,K] i32."""
+
+    @staticmethod
+    def forward(ctx, x, wg, top_k: int):
+        logits, probs, tw, ti = ops.router_fwd(x, wg.to(x.dtype), top_k)
+        ctx.save_for_backward(x, wg, probs, tw, ti)
+        ctx.mark_non_differentiable(ti)
+        return logits, probs, tw, ti
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dlogits, dprobs, dtw, _):
+        x, wg, probs, tw, ti = ctx.saved_tensors
+        idx = ti.long()
+        dp = torch.zeros_like(probs) if dprobs is None else dprobs.float().clone()
+        if dtw is not None:
+            # w_k = p_k / s, s = sum_j p_j over the selected experts
+            s = torch.gather(probs, 1, idx).sum(-1, keepdim=True)
+            dsel = (dtw - (dtw * tw).sum(-1, keepdim=True)) / s
+            dp.scatter_add_(1, idx, dsel)
+        dl = probs * (dp - (dp * probs).sum(-1, keepdim=True))
+        if dlogits is not None:
+            dl = dl + dlogits.float()
+        dl = dl.to(x.dtype)
+        dx = dl @ wg.to(x.dtype) if ctx.needs_input_grad[0] else None
+        dwg = (dl.t() @ x).to(wg.dtype) if ctx.needs_input_grad[1] else None
+        return dx, dwg, None
+
+
+# ------------------------------------------------------------------------------------------------ sparse experts
+class SparseFFNFn(Function):
+    """out[t] = sum_k w[t,k] * FFN_{sel[t,k]}(x[t])   with x [T,D] bf16, w [T,K] f32, sel [T,K] i32."""
+
+    @staticmethod
+    def forward(ctx, x, w, sel, w1, b1, w2, b2, spec: FFNSpec):
+        T, K = sel.shape
+        E = w1.shape[0]
+        xb = _bf16(x)
+        w1b, w2b = _bf16(w1), _bf16(w2)
+        route = ops.route_build(sel, E)
+        xp = ops.gather_rows(xb, route)
+        z, h = _ffn_first(xp, w1b, b1, spec, route=route)
+        y = ops.gemm_rows(h, w2b, w_is_kn=spec.kn_layout, bias=b2, route=route)
+        out = ops.combine_fwd(y, route.slot_to_row, route.sel, w, T, K, round_each=spec.round_each, round_w=spec.round_w)
+        ctx.route, ctx.spec = route, spec
+        ctx.x_dtype = x.dtype
+        ctx.has_b = (b1 is not None, b2 is not None)
+        ctx.save_for_backward(xp, z, h, y, w, w1, w2)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        xp, z, h, y, w, w1, w2 = ctx.saved_tensors
+        route, spec = ctx.route, ctx.spec
+        T, K, E = route.n_slots // route.top_k, route.top_k, route.num_experts
+        w1b, w2b = _bf16(w1), _bf16(w2)
+        dout = _bf16(dout.contiguous())
+        need = ctx.needs_input_grad
+        dw = ops.combine_bwd_w(y, dout, route.slot_to_row, T, K) if need[1] else None
+        wu = w.to(torch.bfloat16).float() if spec.round_w else w
+        dyp = ops.gather_rows(dout, route, slot_w=wu)                          # w * dout in expert-major order
+        db2 = ops.bias_grad(dyp, E, route=route, out_dtype=w2.dtype) if ctx.has_b[1] else None
+        if spec.kn_layout:
+            dw2 = ops.gemm_reduce(h, dyp, E, route=route, out_dtype=w2.dtype)  # [E, H, Dout]
+        else:
+            dw2 = ops.gemm_reduce(dyp, h, E, route=route, out_dtype=w2.dtype)  # [E, Dout, F]
+        dh = ops.gemm_rows(dyp, w2b, w_is_kn=not spec.kn_layout, route=route)
+        dz = dh if spec.act == ops.ACT_NONE else ops.act_bwd(z, dh, spec.act)
+        db1 = ops.bias_grad(dz, E, route=route, out_dtype=w1.dtype) if ctx.has_b[0] else None
+        if spec.kn_layout:
+            dw1 = ops.gemm_reduce(xp, dz, E, route=route, out_dtype=w1.dtype)  # [E, D, H]
+        else:
+            dw1 = ops.gemm_reduce(dz, xp, E, route=route, out_dtype=w1.dtype)  # [E, F, D]
+        dx = None
+        if need[0]:
+            dxp = ops.gemm_rows(dz, w1b, w_is_kn=not spec.kn_layout, route=route)
+            dx = ops.scatter_reduce(dxp, route.slot_to_row, T, K).to(ctx.x_dtype)
+        return dx, dw, None, dw1, db1, dw2, db2, None
+
+
+# ------------------------------------------------------------------------------------------------ dense experts
+class DenseFFNFn(Function):
+    """y[e, t] = FFN_e(x[t]) for every expert and token -> [E * t_pad, Dout] (t_pad = T rounded up to the row tile)."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, spec: FFNSpec):
+        T = x.shape[0]
+        t_pad = (T + ROW_TILE - 1) // ROW_TILE * ROW_TILE
+        xb = _pad_rows(_bf16(x), t_pad)
+        w1b, w2b = _bf16(w1), _bf16(w2)
+        z, h = _ffn_first(xb, w1b, b1, spec, dense_rows=t_pad, a_expert_rows=0)
+        y = ops.gemm_rows(h, w2b, w_is_kn=spec.kn_layout, bias=b2, dense_rows=t_pad, a_expert_rows=t_pad)
+        ctx.spec, ctx.T, ctx.t_pad, ctx.x_dtype = spec, T, t_pad, x.dtype
+        ctx.has_b = (b1 is not None, b2 is not None)
+        ctx.save_for_backward(xb, z, h, w1, w2)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        xb, z, h, w1, w2 = ctx.saved_tensors
+        spec, T, t_pad = ctx.spec, ctx.T, ctx.t_pad
+        E = w1.shape[0]
+        w1b, w2b = _bf16(w1), _bf16(w2)
+        dy = _bf16(dy.contiguous())
+        db2 = ops.bias_grad(dy, E, dense_rows=t_pad, out_dtype=w2.dtype) if ctx.has_b[1] else None
+        if spec.kn_layout:
+            dw2 = ops.gemm_reduce(h, dy, E, dense_rows=t_pad, a_expert_rows=t_pad, b_expert_rows=t_pad, out_dtype=w2.dtype)
+        else:
+            dw2 = ops.gemm_reduce(dy, h, E, dense_rows=t_pad, a_expert_rows=t_pad, b_expert_rows=t_pad, out_dtype=w2.dtype)
+        dh = ops.gemm_rows(dy, w2b, w_is_kn=not spec.kn_layout, dense_rows=t_pad, a_expert_rows=t_pad)
+        dz = dh if spec.act == ops.ACT_NONE else ops.act_bwd(z, dh, spec.act)
+        db1 = ops.bias_grad(dz, E, dense_rows=t_pad, out_dtype=w1.dtype) if ctx.has_b[0] else None
+        if spec.kn_layout:
+            dw1 = ops.gemm_reduce(xb, dz, E, dense_rows=t_pad, a_expert_rows=0, b_expert_rows=t_pad, out_dtype=w1.dtype)
+        else:
+            dw1 = ops.gemm_reduce(dz, xb, E, dense_rows=t_pad, a_expert_rows=t_pad, b_expert_rows=0, out_dtype=w1.dtype)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dxe = ops.gemm_rows(dz, w1b, w_is_kn=not spec.kn_layout, dense_rows=t_pad, a_expert_rows=t_pad)
+            dx = dxe.view(E, t_pad, -1)[:, :T].float().sum(0).to(ctx.x_dtype)
+        return dx, dw1, db1, dw2, db2, None
+
+
+class AffinityFn(Function):
+    """aff[t, e] = mean_d softplus(y[e, t, d]) (fp32 tensor holding values rounded to y.dtype)."""
+
+    @staticmethod
+    def forward(ctx, y, num_experts: int, T: int, t_pad: int):
+        aff = ops.affinity_fwd(y, num_experts, T, t_pad)
+        ctx.save_for_backward(y)
+        ctx.dims = (num_experts, T, t_pad)
+        return aff
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, daff):
+        (y,) = ctx.saved_tensors
+        E, T, t_pad = ctx.dims
+        return ops.affinity_bwd(y, daff, E, T, t_pad), None, None, None
+
+
+class SelectCombineFn(Function):
+    """out[t] = sum_k w[t,k] * y[sel[t,k] * t_pad + t]  (ascending-expert order, rounded like compute_moe)."""
+
+    @staticmethod
+    def forward(ctx, y, w, sel, t_pad: int, spec: FFNSpec):
+        T, K = sel.shape
+        rows = (sel.long() * t_pad + torch.arange(T, device=sel.device).unsqueeze(1)).to(torch.int32).reshape(-1)
+        sel_flat = sel.reshape(-1).contiguous()
+        out = ops.combine_fwd(y, rows, sel_flat, w, T, K, round_each=spec.round_each, round_w=spec.round_w)
+        ctx.save_for_backward(y, w, rows)
+        ctx.dims = (T, K, spec)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        y, w, rows = ctx.saved_tensors
+        T, K, spec = ctx.dims
+        dout = dout.contiguous().to(y.dtype)
+        dw = ops.combine_bwd_w(y, dout, rows, T, K)
+        wu = w.to(torch.bfloat16).float() if spec.round_w else w
+        dy = torch.zeros_like(y)
+        # each (expert, token) row is selected at most once: plain indexed store of w * dout
+        contrib = (wu.reshape(T, K, 1) * dout.float().unsqueeze(1)).to(y.dtype).reshape(T * K, -1)
+        dy.index_copy_(0, rows.long(), contrib)
+        return dy, dw, None, None, None
+
+
+class GatherRowsFn(Function):
+    """topk_out[t, k] = y[sel[t,k] * t_pad + t]  -> [T, K, D]  (input of the diversity loss, competesmoe.py:255-258)."""
+
+    @staticmethod
+    def forward(ctx, y, sel, t_pad: int):
+        T, K = sel.shape
+        rows = (sel.long() * t_pad + torch.arange(T, device=sel.device).unsqueeze(1)).reshape(-1)
+        ctx.save_for_backward(rows)
+        ctx.shape = y.shape
+        return y.index_select(0, rows).view(T, K, -1)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        (rows,) = ctx.saved_tensors
+        dy = torch.zeros(ctx.shape, dtype=g.dtype, device=g.device)
+        dy.index_copy_(0, rows, g.reshape(rows.numel(), -1))
+        return dy, None, None

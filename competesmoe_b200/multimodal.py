@@ -1,0 +1,265 @@
+"""Drop-in for the multimodal MoE plugin (reference: moe_model/model/moe/{moe.py,competesmoe.py,register.py}).
+
+Same constructor, forward signature, return 4-tuple, `args` attribute names, schedule methods and checkpoint layout
+(`gate.weight`, `experts.{e}.<child>.{weight,bias}`, buffer `prob_flips`) as the reference; the arithmetic runs in the
+libcsmoe CUDA kernels (no eager expert loop, no host syncs per expert).  See INTEGRATION.md for how the class is
+registered under the reference's own `MOE_REGISTRY`.
+"""
+from __future__ import annotations
+
+import copy
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import experts as X
+from . import ops
+from .functional import AffinityFn, DenseFFNFn, FFNSpec, GateFn, GatherRowsFn, SelectCombineFn, SparseFFNFn
+from .schedule import make_layer_schedule
+
+MOE_REGISTRY: Dict[str, type] = {}
+
+
+def register_moe(*names):
+    """Same contract as moe_model/model/moe/register.py:5-16, except that the decorated class is returned."""
+    def decorate(cls):
+        for name in names:
+            if name in MOE_REGISTRY and MOE_REGISTRY[name] != cls:
+                raise AssertionError(f"Model named '{name}' conflicts with existing model! {cls} vs {MOE_REGISTRY[name]}")
+            MOE_REGISTRY[name] = cls
+        return cls
+    return decorate
+
+
+def get_moe(model_name):
+    try:
+        return MOE_REGISTRY[model_name]
+    except KeyError:
+        raise ValueError(f"Attempted to load moe method'{model_name}', but no model for this name found! "
+                         f"Supported model names: {', '.join(MOE_REGISTRY.keys())}")
+
+
+class TopkRenormFn(Function):
+    """(scores [T,E] f32) -> (w [T,K] f32, idx [T,K] i32): top-k of the affinity scores, renormalised
+    (competesmoe.py:249-254).  Differentiable w.r.t. the scores: the weights are *not* detached in the reference."""
+
+    @staticmethod
+    def forward(ctx, scores, k: int, sigmoid: bool, dtype: torch.dtype):
+        w, idx = ops.topk_renorm(scores, k, sigmoid=sigmoid, round_dtype=dtype, round_out=dtype == torch.bfloat16)
+        ctx.save_for_backward(scores, w, idx)
+        ctx.sigmoid = sigmoid
+        ctx.mark_non_differentiable(idx)
+        return w, idx
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dw, _):
+        scores, w, idx = ctx.saved_tensors
+        li = idx.long()
+        v = torch.gather(scores, 1, li)
+        if ctx.sigmoid:
+            v = torch.sigmoid(v)
+        s = v.sum(-1, keepdim=True)
+        dv = (dw - (dw * w).sum(-1, keepdim=True)) / s
+        if ctx.sigmoid:
+            dv = dv * v * (1 - v)
+        ds = torch.zeros_like(scores).scatter_add_(1, li, dv)
+        return ds, None, None, None
+
+
+class MoeLayer(nn.Module):
+    """Base layer: gate + experts + the loss helpers every router shares (reference: moe.py:8-132,214-226)."""
+
+    def __init__(self, in_embed_dim=768, out_embed_dim=768, num_of_experts=4, num_selected=2, expert=None, args=None):
+        super().__init__()
+        self.in_embed_dim = in_embed_dim
+        self.out_embed_dim = out_embed_dim
+        self.num_of_experts = num_of_experts
+        self.num_selected = num_selected
+        if expert is None:
+            self.experts = nn.ModuleList([
+                nn.Sequential(nn.Linear(in_embed_dim, out_embed_dim), nn.GELU(), nn.Linear(out_embed_dim, out_embed_dim))
+                for _ in range(num_of_experts)])
+        elif isinstance(expert, nn.ModuleList):
+            self.experts = expert
+        else:
+            self.experts = nn.ModuleList([copy.deepcopy(expert) for _ in range(num_of_experts)])
+        self.gate = nn.Linear(in_embed_dim, num_of_experts, bias=False)
+        self.args = args
+        self.is_vision = False
+        self.log_metrics = {}
+        self._layout: Optional[X.ExpertLayout] = None
+
+    # ---- initialisation (moe.py:50-70)
+    def init_gate_weights(self, std=0.02):
+        if getattr(self.args, "init_weight", True) is False:
+            return
+        device = self.gate.weight.device if self.gate.weight.device != torch.device("meta") else torch.device("cpu")
+        gen = torch.Generator(device=device)
+        gen.manual_seed(42)
+        nn.init.normal_(self.gate.weight, mean=0.0, std=std, generator=gen)
+
+    # ---- expert parameters as stacked tensors
+    def _expert_layout(self) -> X.ExpertLayout:
+        if self._layout is None:
+            layouts = [X.describe_expert(m) for m in self.experts]
+            if any(l != layouts[0] for l in layouts):
+                raise NotImplementedError("all experts of a layer must share one architecture")
+            self._layout = layouts[0]
+        return self._layout
+
+    def _stacked_weights(self):
+        lay = self._expert_layout()
+        lin1 = [m.get_submodule(lay.first) for m in self.experts]
+        lin2 = [m.get_submodule(lay.second) for m in self.experts]
+        groups = [[l.weight for l in lin1], [l.bias for l in lin1], [l.weight for l in lin2], [l.bias for l in lin2]]
+        for g in groups:
+            if g[0] is not None:
+                X.fuse_storage(g)
+        w1, b1, w2, b2 = (X.stack_params(g) for g in groups)
+        return lay, w1, b1, w2, b2
+
+    # ---- losses (moe.py:71-110); inputs are [B, N, E] / [B, N, K]
+    def zloss(self, gate_logits, gate_softmax=None):
+        return torch.square(torch.logsumexp(gate_logits.float(), dim=-1)).mean()
+
+    def balanceloss(self, selected_experts, gate_softmax):
+        proxy = gate_softmax.mean(dim=-2)
+        top1 = F.one_hot(selected_experts[..., 0].long(), self.num_of_experts).to(gate_softmax.dtype)
+        return (proxy * top1.mean(dim=-2)).mean() * float(self.num_of_experts ** 2)
+
+    def combine_loss(self, selected_experts, gate_softmax, gate_logits, acitve_zloss=True):
+        balance_loss = self.balanceloss(selected_experts=selected_experts, gate_softmax=gate_softmax)
+        router_z_loss = torch.zeros((), device=gate_softmax.device)
+        if acitve_zloss:
+            router_z_loss = self.zloss(gate_logits, gate_softmax)
+            aux = balance_loss * self.args.balance_loss_coef + router_z_loss * self.args.router_z_loss_coef
+        else:
+            aux = balance_loss * self.args.balance_loss_coef
+        return aux, balance_loss, router_z_loss
+
+    def experts_diversity_loss(self, expert_outputs):
+        """[B*N (or B, N), K, D] -> mean of the off-diagonal cosine similarities (competesmoe.py:180-218)."""
+        eo = expert_outputs.to(torch.float32)
+        K, D = eo.shape[-2:]
+        nrm = F.normalize(eo, p=2, dim=-1).reshape(-1, K, D)
+        sim = torch.bmm(nrm, nrm.transpose(1, 2))
+        sim = sim * (1 - torch.eye(K, device=eo.device))
+        return sim.mean()
+
+    def _spec(self, lay: X.ExpertLayout) -> FFNSpec:
+        return FFNSpec(act=lay.act, kn_layout=False, round_each=True, round_w=False)
+
+    def forward(self, x, return_id_experts=False):
+        """Plain sparse MoE (moe.py:228-246)."""
+        B, N, D = x.shape
+        x2 = x.reshape(B * N, D)
+        lay, w1, b1, w2, b2 = self._stacked_weights()
+        logits, probs, gw, gidx = GateFn.apply(x2, self.gate.weight, self.num_selected)
+        out = SparseFFNFn.apply(x2, gw, gidx, w1, b1, w2, b2, self._spec(lay)).view(B, N, self.out_embed_dim)
+        aux, balance_loss, router_z_loss = self.combine_loss(gidx.view(B, N, -1), probs.view(B, N, -1), logits.view(B, N, -1))
+        infor_aux = {"balance_loss": balance_loss.detach().clone(), "router_z_loss": router_z_loss.detach().clone()}
+        if return_id_experts:
+            return out, aux, probs.view(B, N, -1)
+        return out, aux, None, infor_aux
+
+
+@register_moe("competesmoe", "competesmoe_b200")
+class CompeteSMoE(MoeLayer):
+    """CompeteSMoE layer (reference: moe_model/model/moe/competesmoe.py:9-415)."""
+
+    def __init__(self, in_embed_dim=768, out_embed_dim=768, num_of_experts=4, num_selected=2, expert=None, args=None):
+        super().__init__(in_embed_dim, out_embed_dim, num_of_experts, num_selected, expert, args)
+        if args is None or not hasattr(args, "rate_flip"):
+            raise ValueError("The 'args' parameter must have the attribute 'rate_flip'.")
+        if not hasattr(args, "warm_up"):
+            raise ValueError("The 'args' parameter must include 'warm_up'.")
+        self.warm_up = args.warm_up
+        self.rate_flip = args.rate_flip
+        self.total_steps = None
+        self.current_steps = 0
+        self.step_warm = None
+        self.is_prob_flips = True
+        self.register_buffer("prob_flips", torch.zeros(15801))
+        self._flips_host = None
+        self._flips_key = None
+        self.last_routing = None   # (selected [B,N,K] i32, weights [B,N,K] f32) of the last forward, for tests / logging
+        self.init_gate_weights()
+
+    # ---- schedule (competesmoe.py:35-179)
+    def set_total_steps(self, total_steps, id_layer, prob_flips_final):
+        assert id_layer is not None, "You must setup id layer is not None"
+        assert prob_flips_final is not None, "You must setup prob_flips_final is not None"
+        self.total_steps = total_steps
+        self.step_warm, flags = make_layer_schedule(total_steps, self.warm_up, self.rate_flip,
+                                                    self.args.max_compete_in_iter, prob_flips_final)
+        self.flip_steps = total_steps - self.step_warm
+        prob_flips_final[id_layer] = flags
+        self.prob_flips = flags
+        self.is_prob_flips = False
+        return prob_flips_final
+
+    def set_current_steps(self, step):
+        self.current_steps = step
+
+    def _is_competition_step(self, x) -> bool:
+        """competesmoe.py:347, without a device->host sync per call: the flag vector is mirrored on the host and
+        refreshed only when the buffer object or its version changes (load_state_dict, set_total_steps)."""
+        if not x.requires_grad or self.step_warm is None or self.current_steps < self.step_warm:
+            return False
+        pf = self.prob_flips
+        key = (id(pf), pf._version, pf.data_ptr())
+        if key != self._flips_key:
+            self._flips_host = pf.detach().to("cpu").ne(0).tolist()
+            self._flips_key = key
+        return bool(self._flips_host[self.current_steps - self.step_warm])
+
+    # ---- policies
+    def router_policy(self, x2):
+        return GateFn.apply(x2, self.gate.weight, self.num_selected)
+
+    def router_loss(self, gate_softmax, affinity_softmax):
+        return F.mse_loss(gate_softmax, affinity_softmax)
+
+    def forward(self, x, return_id_experts=False, is_vision=False):
+        B, N, D = x.shape
+        T, E, K = B * N, self.num_of_experts, self.num_selected
+        x2 = x.reshape(T, D)
+        lay, w1, b1, w2, b2 = self._stacked_weights()
+        spec = self._spec(lay)
+        gate_logits, gate_softmax, gate_w, gate_idx = self.router_policy(x2)
+        auxiliary_loss = torch.tensor(0.0, device=x.device, dtype=x.dtype)
+        infor_aux = {}
+        if self._is_competition_step(x):
+            y_all = DenseFFNFn.apply(x2, w1, b1, w2, b2, spec)                       # [E * t_pad, Dout]
+            t_pad = y_all.shape[0] // E
+            aff = AffinityFn.apply(y_all, E, T, t_pad)                               # [T, E] f32 (x.dtype-rounded)
+            aff_softmax = F.softmax(aff, dim=-1, dtype=torch.float32)
+            aff_w, aff_idx = TopkRenormFn.apply(aff, K, bool(getattr(self.args, "norm_sigmoid", False)), x.dtype)
+            li = aff_idx.long()
+            if getattr(self.args, "hybrid", False):
+                routerloss = self.router_loss(gate_softmax, aff_softmax.detach()) + self.router_loss(
+                    torch.gather(gate_softmax, -1, li), torch.gather(aff_softmax, -1, li).detach()) * self.args.router_theta
+            else:
+                routerloss = self.router_loss(gate_softmax, aff_softmax.detach())
+            diversity_loss = self.experts_diversity_loss(GatherRowsFn.apply(y_all, aff_idx, t_pad))
+            balance_loss = self.balanceloss(aff_idx.view(B, N, K), aff_softmax.view(B, N, E))
+            auxiliary_loss = routerloss * self.args.router_loss_coef + diversity_loss * self.args.diversity_loss_coef + \
+                balance_loss * self.args.bal_comp_loss_coef
+            # the selected experts' outputs were already computed by the dense pass: reuse instead of recomputing
+            out = SelectCombineFn.apply(y_all, aff_w, aff_idx, t_pad, spec)
+            self.last_routing = (aff_idx.view(B, N, K), aff_w.detach().view(B, N, K))
+            infor_aux = {"balance_loss": balance_loss.detach().clone(), "diversity_loss": diversity_loss.detach().clone(),
+                         "routerloss": routerloss.detach().clone()}
+        else:
+            out = SparseFFNFn.apply(x2, gate_w, gate_idx, w1, b1, w2, b2, spec)
+            self.last_routing = (gate_idx.view(B, N, K), gate_w.detach().view(B, N, K))
+            if x.requires_grad or return_id_experts:
+                auxiliary_loss, balance_loss, router_z_loss = self.combine_loss(
+                    gate_idx.view(B, N, K), gate_softmax.view(B, N, E), gate_logits.view(B, N, E))
+                infor_aux = {"balance_loss": balance_loss.detach().clone(), "router_z_loss": router_z_loss.detach().clone()}
+        return out.view(B, N, self.out_embed_dim).to(x.dtype), auxiliary_loss, None, infor_aux

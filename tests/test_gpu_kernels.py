@@ -1,0 +1,265 @@
+"""GPU parity of the individual libcsmoe kernels (through the C ABI) against the CPU oracle / plain torch."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import multimodal as om
+from oracle import pretrain as op
+
+from helpers import assert_close_rms
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from competesmoe_b200 import ops as _ops
+    return _ops
+
+
+# ------------------------------------------------------------------------------------------------ routing metadata
+@pytest.mark.parametrize("T,K,E", [(1, 1, 1), (7, 2, 4), (4096, 2, 4), (4096, 2, 8), (3000, 8, 64), (65536, 8, 64),
+                                   (513, 3, 1000)])
+def test_route_build_bit_exact(ops, T, K, E):
+    g = torch.Generator().manual_seed(T + K + E)
+    sel = torch.stack([torch.randperm(E, generator=g)[:K] for _ in range(min(T, 512))])
+    sel = sel.repeat((T + sel.shape[0] - 1) // sel.shape[0], 1)[:T].int()
+    if E >= 4:
+        sel[sel == 1] = 0            # leave expert 1 empty, make expert 0 hot (duplicates within a token are fine here)
+    r = ops.route_build(sel.to(DEV), E)
+    ref = op.prepare_sel2(sel)       # stable argsort = the reference's maps after canonicalisation
+    flat = sel.flatten()
+    counts = torch.bincount(flat.long(), minlength=E)
+    assert torch.equal(r.counts.cpu().long(), counts)
+    assert torch.equal(r.offsets.cpu().long(), F.pad(counts.cumsum(0), (1, 0)))
+    assert torch.equal(r.sorted_sel.cpu(), ref.sel.flatten())
+    assert torch.equal(r.sort_index.cpu(), ref.out_index)
+    assert torch.equal(r.sort_index.cpu() // K, ref.sel_index)
+    pad = F.pad(((counts + 127) // 128 * 128).cumsum(0), (1, 0))
+    assert torch.equal(r.pad_offsets.cpu().long(), pad)
+    # slot <-> row maps are mutually inverse and expert-major
+    s2r, r2s = r.slot_to_row.cpu().long(), r.row_to_slot.cpu().long()
+    assert torch.equal(r2s[s2r], torch.arange(T * K))
+    assert int((r2s >= 0).sum()) == T * K
+    row_expert = torch.bucketize(s2r, pad[1:], right=True)
+    assert torch.equal(row_expert, flat.long())
+    te = r.tile_expert.cpu().long()
+    n_tiles = int(pad[-1]) // 128
+    assert torch.equal(te[:n_tiles], torch.bucketize(torch.arange(n_tiles) * 128, pad[1:], right=True))
+    assert bool((te[n_tiles:] == -1).all())
+
+
+def test_route_build_empty_input(ops):
+    r = ops.route_build(torch.zeros(0, 2, dtype=torch.int32, device=DEV), 4)
+    assert r.counts.tolist() == [0, 0, 0, 0] and r.pad_offsets.tolist() == [0] * 5
+    assert bool((r.tile_expert == -1).all())
+
+
+# ------------------------------------------------------------------------------------------------ router
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("T,D,E,K", [(257, 64, 4, 2), (1024, 1152, 4, 2), (512, 1024, 64, 8), (300, 512, 8, 2), (64, 3072, 4, 2)])
+def test_router_matches_oracle(ops, dtype, T, D, E, K):
+    g = torch.Generator().manual_seed(D + E)
+    x = torch.randn(1, T, D, generator=g).to(dtype)
+    wg = (torch.randn(E, D, generator=g) * 0.05).to(dtype)
+    w_ref, idx_ref, p_ref, l_ref = om.router_policy(x, wg, K)
+    logits, probs, tw, ti = ops.router_fwd(x[0].to(DEV), wg.to(DEV), K)
+    assert_close_rms(logits, l_ref[0], 2e-2 if dtype == torch.bfloat16 else 1e-4, "logits")
+    torch.testing.assert_close(probs.cpu(), p_ref[0], rtol=2e-2 if dtype == torch.bfloat16 else 1e-4, atol=1e-6)
+    # routing: bit-exact except tokens with margin < 1e-3 (computed on the oracle's probabilities)
+    margin = om.topk_margin(p_ref[0], K)
+    agree = (ti.cpu().long() == idx_ref[0]).all(-1)
+    assert bool((margin[~agree] < 1e-3).all()), "routing differs on a token with margin >= 1e-3"
+    torch.testing.assert_close(tw.cpu()[agree], w_ref[0][agree].float(), rtol=2e-2 if dtype == torch.bfloat16 else 1e-4, atol=1e-6)
+    print(f"router {dtype} T={T} E={E}: {int((~agree).sum())} low-margin tokens exempt")
+
+
+def test_router_tie_break_is_lowest_index(ops):
+    x = torch.zeros(8, 64, device=DEV, dtype=torch.bfloat16)      # all logits equal -> all probabilities tie
+    wg = torch.randn(8, 64, device=DEV, dtype=torch.bfloat16)
+    _, probs, tw, ti = ops.router_fwd(x, wg, 3)
+    assert ti.cpu().tolist() == [[0, 1, 2]] * 8
+    torch.testing.assert_close(tw.sum(-1).cpu(), torch.ones(8), rtol=1e-2, atol=1e-2)
+
+
+@pytest.mark.parametrize("E,K", [(4, 2), (64, 8), (33, 5)])
+def test_topk_renorm(ops, E, K):
+    g = torch.Generator().manual_seed(E)
+    s = torch.rand(500, E, generator=g)
+    w, idx = ops.topk_renorm(s.to(DEV), K)
+    wr, ir = om.stable_topk(s, K)
+    assert torch.equal(idx.cpu().long(), ir)
+    torch.testing.assert_close(w.cpu(), wr / wr.sum(-1, keepdim=True), rtol=1e-5, atol=1e-7)
+    w2, idx2 = ops.topk_renorm(s.to(DEV), K, sigmoid=True)
+    ws = torch.sigmoid(wr)
+    assert torch.equal(idx2.cpu().long(), ir)
+    torch.testing.assert_close(w2.cpu(), ws / ws.sum(-1, keepdim=True), rtol=1e-5, atol=1e-7)
+
+
+# ------------------------------------------------------------------------------------------------ permute / combine
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_gather_combine_scatter(ops, dtype):
+    T, K, E, D = 777, 2, 4, 256
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(T, D, generator=g).to(dtype)
+    sel = torch.stack([torch.randperm(E, generator=g)[:K] for _ in range(T)]).int()
+    w = torch.rand(T, K, generator=g)
+    r = ops.route_build(sel.to(DEV), E)
+    xp = ops.gather_rows(x.to(DEV), r)
+    r2s = r.row_to_slot.cpu().long()
+    ref = torch.zeros(r.row_cap, D, dtype=dtype)
+    ref[r2s >= 0] = x[r2s[r2s >= 0] // K]
+    assert torch.equal(xp.cpu(), ref)                                   # pure data movement: bit-exact, zero padding
+    # combine of the gathered rows with weights == sum_k w * x[t]
+    out = ops.combine_fwd(xp, r.slot_to_row, r.sel, w.to(DEV), T, K)
+    torch.testing.assert_close(out.cpu().float(), (w.sum(-1, keepdim=True) * x.float()), rtol=2e-2, atol=2e-2)
+    # scatter_reduce is the adjoint of gather
+    dx = ops.scatter_reduce(xp, r.slot_to_row, T, K)
+    torch.testing.assert_close(dx.cpu().float(), K * x.float(), rtol=1e-2, atol=1e-2)
+    dw = ops.combine_bwd_w(xp, x.to(DEV), r.slot_to_row, T, K)
+    torch.testing.assert_close(dw.cpu(), (x.float() ** 2).sum(-1, keepdim=True).expand(T, K), rtol=1e-2, atol=1e-2)
+    # weighted gather (combine backward)
+    gw = ops.gather_rows(x.to(DEV), r, slot_w=w.to(DEV))
+    refw = torch.zeros(r.row_cap, D)
+    refw[r2s >= 0] = x[r2s[r2s >= 0] // K].float() * w.flatten()[r2s[r2s >= 0]].unsqueeze(1)
+    torch.testing.assert_close(gw.cpu().float(), refw, rtol=1e-2, atol=1e-2)
+
+
+def test_combine_order_matches_reference_rounding(ops):
+    """moe.py:204: results accumulate in bf16, experts visited in ascending id."""
+    T, K, E, D = 64, 2, 4, 128
+    g = torch.Generator().manual_seed(9)
+    sel = torch.stack([torch.randperm(E, generator=g)[:K] for _ in range(T)]).int()
+    y = torch.randn(T * K, D, generator=g).bfloat16()       # row j = output for slot j
+    w = torch.rand(T, K, generator=g)
+    ref = torch.zeros(T, D, dtype=torch.bfloat16)
+    for e in range(E):
+        t_idx, k_idx = torch.where(sel == e)
+        ref[t_idx] += w[t_idx, k_idx].unsqueeze(0).T * y[t_idx * K + k_idx]
+    rows = torch.arange(T * K, dtype=torch.int32, device=DEV)
+    out = ops.combine_fwd(y.to(DEV), rows, sel.flatten().to(DEV), w.to(DEV), T, K, round_each=True)
+    assert torch.equal(out.cpu(), ref)
+
+
+# ------------------------------------------------------------------------------------------------ grouped GEMM
+def _route_for_counts(ops, counts):
+    sel = torch.cat([torch.full((c,), e, dtype=torch.int32) for e, c in enumerate(counts)])
+    return ops.route_build(sel.view(-1, 1).to(DEV), len(counts))
+
+
+@pytest.mark.parametrize("kn", [False, True])
+@pytest.mark.parametrize("counts,n,k", [([128], 256, 64), ([300, 0, 77, 513], 4304, 1152), ([300, 0, 77, 513], 1152, 4304),
+                                        ([100, 200, 300], 128, 512), ([5, 5, 5, 5, 5, 5, 5, 5], 64, 1024)])
+def test_gemm_rows(ops, kn, counts, n, k):
+    E = len(counts)
+    r = _route_for_counts(ops, counts)
+    g = torch.Generator().manual_seed(n + k)
+    a = torch.zeros(r.row_cap, k, dtype=torch.bfloat16)
+    pad = r.pad_offsets.cpu().tolist()
+    for e, c in enumerate(counts):
+        a[pad[e]:pad[e] + c] = torch.randn(c, k, generator=g).bfloat16()
+    w = (torch.randn(E, k, n, generator=g) / k ** 0.5).bfloat16() if kn else (torch.randn(E, n, k, generator=g) / k ** 0.5).bfloat16()
+    bias = torch.randn(E, n, generator=g).bfloat16()
+    c_, pre = ops.gemm_rows(a.to(DEV), w.to(DEV), w_is_kn=kn, route=r, bias=bias.to(DEV), act=ops.ACT_GELU_TANH, want_preact=True)
+    for e, cnt in enumerate(counts):
+        we = w[e].float() if kn else w[e].float().t()
+        z = (a[pad[e]:pad[e] + cnt].float() @ we + bias[e].float()).bfloat16()
+        assert_close_rms(pre[pad[e]:pad[e] + cnt], z, 2e-2, f"preact e={e}")
+        assert_close_rms(c_[pad[e]:pad[e] + cnt], F.gelu(z.float(), approximate="tanh"), 2e-2, f"act e={e}")
+
+
+@pytest.mark.parametrize("counts,m,n", [([128], 128, 256), ([300, 0, 77, 513], 4304, 1152), ([300, 0, 77, 513], 1152, 4304),
+                                        ([100, 200, 300], 512, 128)])
+def test_gemm_reduce(ops, counts, m, n):
+    E = len(counts)
+    r = _route_for_counts(ops, counts)
+    g = torch.Generator().manual_seed(m + n)
+    a = torch.zeros(r.row_cap, m, dtype=torch.bfloat16)
+    b = torch.zeros(r.row_cap, n, dtype=torch.bfloat16)
+    pad = r.pad_offsets.cpu().tolist()
+    for e, c in enumerate(counts):
+        a[pad[e]:pad[e] + c] = torch.randn(c, m, generator=g).bfloat16()
+        b[pad[e]:pad[e] + c] = torch.randn(c, n, generator=g).bfloat16()
+    out = ops.gemm_reduce(a.to(DEV), b.to(DEV), E, route=r, out_dtype=torch.float32)
+    for e, c in enumerate(counts):
+        ref = a[pad[e]:pad[e] + c].float().t() @ b[pad[e]:pad[e] + c].float()
+        assert_close_rms(out[e], ref, 1e-4, f"wgrad e={e}")
+
+
+def test_gemm_linearity_at_full_size(ops):
+    """Size-independent property at the bench shape (C2 rows x D x 2F): G(a1 + a2) == G(a1) + G(a2) up to rounding."""
+    counts = [2048] * 4
+    r = _route_for_counts(ops, counts)
+    D, N = 3072, 16384
+    g = torch.Generator(device=DEV).manual_seed(0)
+    a1 = torch.randn(r.row_cap, D, device=DEV, generator=g).bfloat16()
+    a2 = torch.randn(r.row_cap, D, device=DEV, generator=g).bfloat16()
+    w = (torch.randn(4, N, D, device=DEV, generator=g) * 0.02).bfloat16()
+    s = (a1.float() + a2.float()).bfloat16()
+    y1 = ops.gemm_rows(a1, w, w_is_kn=False, route=r, out_dtype=torch.float32)
+    y2 = ops.gemm_rows(a2, w, w_is_kn=False, route=r, out_dtype=torch.float32)
+    ys = ops.gemm_rows(s, w, w_is_kn=False, route=r, out_dtype=torch.float32)
+    assert_close_rms(ys, y1 + y2, 2e-2, "linearity")
+    # and a spot check of one row tile against torch
+    ref = a1[:128].float() @ w[0].float().t()
+    assert_close_rms(y1[:128], ref, 1e-3, "tile 0")
+
+
+# ------------------------------------------------------------------------------------------------ elementwise
+@pytest.mark.parametrize("act,fn", [("ACT_RELU", F.relu), ("ACT_GELU", F.gelu), ("ACT_GELU_TANH", lambda z: F.gelu(z, approximate="tanh")),
+                                    ("ACT_SILU", F.silu)])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_activation_fwd_bwd(ops, act, fn, dtype):
+    code = getattr(ops, act)
+    g = torch.Generator().manual_seed(1)
+    z = (torch.randn(300, 264, generator=g) * 2).to(dtype)
+    dh = torch.randn(300, 264, generator=g).to(dtype)
+    zr = z.float().requires_grad_(True)
+    fn(zr).backward(dh.float())
+    tol = 2e-2 if dtype == torch.bfloat16 else 1e-4
+    assert_close_rms(ops.act_fwd(z.to(DEV), code), fn(z.float()), tol, "fwd")
+    assert_close_rms(ops.act_bwd(z.to(DEV), dh.to(DEV), code), zr.grad, tol, "bwd")
+
+
+def test_glu_fwd_bwd(ops):
+    g = torch.Generator().manual_seed(2)
+    z = torch.randn(200, 512, generator=g).bfloat16()
+    dh = torch.randn(200, 256, generator=g).bfloat16()
+    zr = z.float().requires_grad_(True)
+    gate, up = zr.chunk(2, dim=-1)
+    (up * F.silu(gate)).backward(dh.float())
+    assert_close_rms(ops.act_fwd(z.to(DEV), ops.ACT_SILU_GLU), (z.float()[:, 256:] * F.silu(z.float()[:, :256])), 2e-2, "glu fwd")
+    assert_close_rms(ops.act_bwd(z.to(DEV), dh.to(DEV), ops.ACT_SILU_GLU), zr.grad, 2e-2, "glu bwd")
+
+
+def test_bias_grad_and_cast(ops):
+    counts = [300, 0, 77, 513]
+    r = _route_for_counts(ops, counts)
+    g = torch.Generator().manual_seed(3)
+    x = torch.zeros(r.row_cap, 4304)
+    pad = r.pad_offsets.cpu().tolist()
+    for e, c in enumerate(counts):
+        x[pad[e]:pad[e] + c] = torch.randn(c, 4304, generator=g)
+    db = ops.bias_grad(x.bfloat16().to(DEV), 4, route=r, out_dtype=torch.float32)
+    ref = torch.stack([x.bfloat16().float()[pad[e]:pad[e + 1]].sum(0) for e in range(4)])
+    assert_close_rms(db, ref, 1e-3, "bias grad")
+    src = torch.randn(1000003, generator=g)
+    assert torch.equal(ops.cast_bf16(src.to(DEV)).cpu(), src.bfloat16())
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_affinity_fwd_bwd(ops, dtype):
+    E, T, D = 4, 200, 1152
+    t_pad = 256
+    g = torch.Generator().manual_seed(4)
+    y = torch.randn(E, t_pad, D, generator=g).to(dtype)
+    daff = torch.randn(T, E, generator=g)
+    yr = y.float().requires_grad_(True)
+    aff_ref = F.softplus(yr[:, :T]).mean(-1).t()        # [T, E]
+    aff_ref.backward(daff)
+    aff = ops.affinity_fwd(y.view(E * t_pad, D).to(DEV), E, T, t_pad)
+    tol = 2e-2 if dtype == torch.bfloat16 else 1e-4
+    assert_close_rms(aff, aff_ref.detach(), tol, "affinity")
+    dy = ops.affinity_bwd(y.view(E * t_pad, D).to(DEV), daff.to(DEV), E, T, t_pad)
+    assert_close_rms(dy.view(E, t_pad, D), yr.grad, tol, "affinity bwd")

@@ -1,0 +1,147 @@
+"""GPU parity of the multimodal drop-in layer against the golden vectors (outputs of the unmodified reference) and, at
+other shapes, against the CPU oracle.  Tolerances: bf16 rtol 2e-2 (plus an atol scaled by the tensor RMS); routing
+indices bit-exact except tokens with a top-k margin below 1e-3, which are counted and reported."""
+from types import SimpleNamespace
+
+import pytest
+import torch
+
+from oracle import multimodal as om
+
+from conftest import load_golden
+from helpers import assert_close_rms, build_multimodal_layer, expert_linears
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+CASES = ["mm_siglip_router_bf16", "mm_siglip_comp_bf16", "mm_siglip_router_f32", "mm_projector_router_f32",
+         "mm_glu_router_f32", "mm_siglip_comp_f32", "mm_projector_comp_f32", "mm_glu_comp_f32",
+         "mm_siglip_comp_hybrid_f32"]
+
+
+def run_layer(layer, fx, dtype):
+    x = fx["x"].to(DEV, dtype).requires_grad_(True)
+    dy = fx["dy"].to(DEV, dtype)
+    out, aux, none, info = layer(x)
+    assert none is None and out.dtype == dtype and out.shape == fx["out"].shape
+    ((out.float() * dy.float()).sum() + aux.float()).backward()
+    return x, out, aux, info
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_layer_matches_reference_golden(name):
+    fx = load_golden(name)
+    m = fx["meta"]
+    dtype = torch.bfloat16            # the tensor-core path computes in bf16 whatever the storage dtype of the fixture
+    layer = build_multimodal_layer(fx, DEV, dtype)
+    x, out, aux, info = run_layer(layer, fx, dtype)
+    sel, w = layer.last_routing
+    # ---- routing decisions vs the reference's own
+    scores_src = "affinity" if m["competition"] else "gate_softmax"
+    args = SimpleNamespace(**m["args"])
+    exps = [{k: (v.to(dtype) if torch.is_tensor(v) else v) for k, v in e.items()} for e in fx["experts"]]
+    _, _, _, _, dbg = om.competesmoe_forward(fx["x"].to(dtype), fx["gate_w"].to(dtype), exps, m["K"], m["d_out"], args,
+                                             m["competition"])
+    margin = om.topk_margin(dbg[scores_src], m["K"])
+    agree = (sel.cpu().long() == fx["selected"]).all(-1)
+    n_ex = int((~agree).sum())
+    assert bool((margin[~agree] < 1e-3).all()), "routing differs from the reference on a token with margin >= 1e-3"
+    print(f"{name}: {n_ex}/{agree.numel()} low-margin tokens exempt from bit-exact routing")
+    # ---- values
+    rt = 2e-2
+    assert_close_rms(out[agree.to(DEV)], fx["out"][agree], rt, "output")
+    assert_close_rms(w.cpu()[agree], fx["weights"][agree], rt, "routing weights")
+    if n_ex == 0:
+        assert_close_rms(aux, fx["aux"], rt, "aux loss")
+        assert set(info) == set(fx["info"])
+        for k in info:
+            # the diversity loss is a mean of signed cosines near 0: compare with an absolute floor
+            got, ref = float(info[k]), float(fx["info"][k])
+            assert abs(got - ref) <= rt * abs(ref) + 2e-3, (k, got, ref)
+        assert_close_rms(x.grad[agree.to(DEV)], fx["dx"][agree], 3e-2, "dx")
+        if fx["dgate_w"] is not None:
+            assert_close_rms(layer.gate.weight.grad, fx["dgate_w"], 3e-2, "dgate")
+        for e, (mod, ref) in enumerate(zip(layer.experts, fx["dexperts"])):
+            ref_list = list(ref.values())
+            l1, l2 = expert_linears(mod)
+            params = [l1.weight] + ([l1.bias] if l1.bias is not None else []) + [l2.weight] + ([l2.bias] if l2.bias is not None else [])
+            assert len(params) == len(ref_list)
+            for p, r in zip(params, ref_list):
+                assert p.grad is not None
+                assert_close_rms(p.grad, r, 3e-2, f"expert {e} grad {tuple(r.shape)}")
+
+
+def test_upcycled_experts_analytic_kats():
+    """identical experts => output == the dense expert, diversity == 1 - 1/K, balance == 1."""
+    fx = load_golden("mm_siglip_comp_upcycled_f32")
+    m = fx["meta"]
+    layer = build_multimodal_layer(fx, DEV, torch.bfloat16)
+    x, out, aux, info = run_layer(layer, fx, torch.bfloat16)
+    dense = om.expert_forward({k: (v.bfloat16() if torch.is_tensor(v) else v) for k, v in fx["experts"][0].items()},
+                              fx["x"].bfloat16())
+    assert_close_rms(out, dense, 2e-2, "upcycled output")
+    assert abs(float(info["diversity_loss"]) - (1 - 1 / m["K"])) < 5e-3
+    sel, _ = layer.last_routing
+    assert sel.cpu().tolist() == [[[0, 1]] * m["N"]] * m["B"]          # exact ties -> lowest index first
+
+
+def test_checkpoint_layout_and_fused_storage():
+    fx = load_golden("mm_siglip_router_bf16")
+    layer = build_multimodal_layer(fx, DEV, torch.bfloat16)
+    keys = set(layer.state_dict().keys())
+    expect = {"gate.weight", "prob_flips"} | {f"experts.{e}.{n}" for e in range(4) for n in
+                                               ("fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias")}
+    assert keys == expect
+    sd = {k: v.clone() for k, v in layer.state_dict().items()}
+    x = fx["x"].to(DEV, torch.bfloat16)
+    with torch.no_grad():
+        o1 = layer(x)[0]
+    # parameters now alias one flat buffer; loading a state dict must still take effect (sparse upcycling path)
+    w = [e.fc1.weight for e in layer.experts]
+    assert all(w[i].data_ptr() == w[0].data_ptr() + i * w[0].numel() * 2 for i in range(4))
+    sd2 = {k: (torch.zeros_like(v) if "experts.1." in k else v) for k, v in sd.items()}
+    layer.load_state_dict(sd2)
+    with torch.no_grad():
+        o2 = layer(x)[0]
+    assert not torch.equal(o1, o2)
+    layer.load_state_dict(sd)
+    with torch.no_grad():
+        o3 = layer(x)[0]
+    assert torch.equal(o1, o3)                                         # deterministic, bit-identical re-run
+
+
+def test_inference_path_takes_router_branch_without_aux():
+    fx = load_golden("mm_siglip_comp_bf16")
+    layer = build_multimodal_layer(fx, DEV, torch.bfloat16).eval()
+    with torch.no_grad():
+        out, aux, none, info = layer(fx["x"].to(DEV, torch.bfloat16))
+    assert info == {} and float(aux) == 0.0 and none is None
+
+
+@pytest.mark.parametrize("competition", [False, True])
+def test_siglip_shape_against_oracle(competition):
+    """C2' SigLIP MoE MLP shape (1152 -> 4304 -> 1152, GELU-tanh, bias; intermediate size not a multiple of 64)."""
+    torch.manual_seed(0)
+    B, N, D, Fh, E, K = 2, 320, 1152, 4304, 4, 2
+    g = torch.Generator().manual_seed(1236)
+    exps = [{"kind": "mlp", "act": "gelu_tanh", "w1": (torch.randn(Fh, D, generator=g) * D ** -0.5).bfloat16(),
+             "b1": (torch.randn(Fh, generator=g) * 0.1).bfloat16(), "w2": (torch.randn(D, Fh, generator=g) * Fh ** -0.5).bfloat16(),
+             "b2": (torch.randn(D, generator=g) * 0.1).bfloat16()} for _ in range(E)]
+    gate_w = (torch.randn(E, D, generator=g) * 0.02).bfloat16()
+    x = torch.randn(B, N, D, generator=g).bfloat16()
+    dy = torch.randn(B, N, D, generator=g).bfloat16()
+    args = om.default_args()
+    fx = {"meta": dict(d_in=D, d_out=D, E=E, K=K, competition=competition, args=vars(args)), "experts": exps,
+          "gate_w": gate_w, "x": x, "dy": dy, "out": torch.empty(B, N, D)}
+    layer = build_multimodal_layer(fx, DEV, torch.bfloat16)
+    xr = x.clone().requires_grad_(True)
+    o_out, o_aux, _, o_info, dbg = om.competesmoe_forward(xr, gate_w, exps, K, D, args, competition)
+    ((o_out.float() * dy.float()).sum() + o_aux.float()).backward()
+    xg, out, aux, info = run_layer(layer, fx, torch.bfloat16)
+    sel, w = layer.last_routing
+    margin = om.topk_margin(dbg["affinity"] if competition else dbg["gate_softmax"], K)
+    agree = (sel.cpu().long() == dbg["selected"]).all(-1)
+    assert bool((margin[~agree] < 1e-3).all())
+    print(f"siglip-shape competition={competition}: {int((~agree).sum())}/{agree.numel()} low-margin tokens exempt")
+    assert_close_rms(out[agree.to(DEV)], o_out.detach()[agree], 2e-2, "output")
+    assert_close_rms(xg.grad[agree.to(DEV)], xr.grad[agree], 4e-2, "dx")

@@ -1,0 +1,123 @@
+"""The oracle against the committed golden vectors (outputs of the unmodified reference, see oracle/gen_golden.py).
+CPU only; this is what pins the oracle."""
+from types import SimpleNamespace
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import multimodal as om
+from oracle import pretrain as op
+
+from conftest import load_golden
+
+MM = ["mm_siglip_router_f32", "mm_projector_router_f32", "mm_glu_router_f32", "mm_siglip_comp_f32",
+      "mm_projector_comp_f32", "mm_glu_comp_f32", "mm_siglip_comp_hybrid_f32", "mm_siglip_router_bf16",
+      "mm_siglip_comp_bf16", "mm_siglip_comp_upcycled_f32"]
+PT = ["pt_router_f32", "pt_comp_f32", "pt_comp_hybrid_bal_f32", "pt_comp_intopk_f32", "pt_comp_tribrid_f32"]
+
+
+def _req(t):
+    return t.clone().requires_grad_(True)
+
+
+@pytest.mark.parametrize("name", MM)
+def test_multimodal_oracle_matches_reference(name):
+    fx = load_golden(name)
+    m = fx["meta"]
+    args = SimpleNamespace(**m["args"])
+    x, gw = _req(fx["x"]), _req(fx["gate_w"])
+    exps = [{k: (_req(v) if torch.is_tensor(v) else v) for k, v in e.items()} for e in fx["experts"]]
+    out, aux, _, info, dbg = om.competesmoe_forward(x, gw, exps, m["K"], m["d_out"], args, m["competition"])
+    ((out.float() * fx["dy"].float()).sum() + aux.float()).backward()
+    f32 = "float32" in m["dtype"]
+    tol = dict(rtol=1e-5, atol=1e-6) if f32 else dict(rtol=2e-2, atol=2e-2)
+    scores = dbg["affinity"] if m["competition"] else dbg["gate_softmax"]
+    margin = om.topk_margin(scores, m["K"])
+    agree = (fx["selected"] == dbg["selected"]).all(-1)
+    assert bool((margin[~agree] < 1e-3).all())
+    assert int((~agree).sum()) == fx["n_exempt"]
+    if not m["upcycled"]:
+        torch.testing.assert_close(out[agree], fx["out"][agree], **tol)
+        torch.testing.assert_close(x.grad[agree], fx["dx"][agree], **tol)
+    else:
+        # analytic KATs of sparse upcycling: identical experts
+        dense = om.expert_forward(fx["experts"][0], fx["x"])
+        torch.testing.assert_close(out, dense, rtol=1e-4, atol=1e-5)
+        assert abs(float(info["diversity_loss"]) - (1 - 1 / m["K"])) < 1e-5
+    if fx["n_exempt"] == 0:
+        torch.testing.assert_close(aux.float(), fx["aux"].float(), **tol)
+        for k in fx["info"]:
+            torch.testing.assert_close(info[k].float(), fx["info"][k].float(), **tol)
+        if fx["dgate_w"] is not None:
+            torch.testing.assert_close(gw.grad, fx["dgate_w"], **tol)
+        names = {"mlp": {"w1": 0, "b1": 1, "w2": 2, "b2": 3}, "glu": {"w1": 0, "w2": 1}}
+        for e, (ew, ref) in enumerate(zip(exps, fx["dexperts"])):
+            ref_list = list(ref.values())
+            for key, pos in names[ew["kind"]].items():
+                if ew[key].grad is None:
+                    continue
+                torch.testing.assert_close(ew[key].grad, ref_list[pos], **tol)
+
+
+@pytest.mark.parametrize("name", PT)
+def test_pretrain_oracle_matches_reference(name):
+    fx = load_golden(name)
+    m = fx["meta"]
+    args = SimpleNamespace(**m["args"])
+    x, wg, ks, vs = (_req(fx[n]) for n in ("x", "w_gate", "keys", "values"))
+    out, regs, dbg = op.competesmoe_forward(x, wg, ks, vs, m["K"], args, m["competition"])
+    ((out * fx["dy"]).sum() + sum(regs.values())).backward()
+    tol = dict(rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(out, fx["out"], **tol)
+    assert set(regs) == set(fx["regs"])
+    for k in regs:
+        torch.testing.assert_close(regs[k], fx["regs"][k], **tol)
+    for got, ref in ((x.grad, "dx"), (wg.grad, "dw_gate"), (ks.grad, "dkeys"), (vs.grad, "dvalues")):
+        torch.testing.assert_close(got, fx[ref], **tol)
+
+
+def test_cvmm_restatement_matches_triton_interpreter_run():
+    fx = load_golden("cvmm_triton_interp")
+    x, ks, vs, w = (_req(fx[n]) for n in ("x", "keys", "values", "w"))
+    out = op.compute_moe_main(x, fx["sel"], w, ks, vs, F.relu, torch.float32)
+    (out * fx["dy"]).sum().backward()
+    tol = dict(rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(out, fx["out"], **tol)
+    for got, ref in ((x.grad, "dx"), (ks.grad, "dkeys"), (vs.grad, "dvalues"), (w.grad, "dw")):
+        torch.testing.assert_close(got, fx[ref], **tol)
+
+
+def test_cvmm_is_the_einsum_identity():
+    """cvmm == einsum('td,tkdh->tkh', x, keys[sel])."""
+    torch.manual_seed(0)
+    T, K, D, H, E = 40, 2, 16, 8, 5
+    x = torch.randn(T, D)
+    keys = torch.randn(E, D, H)
+    sel = torch.stack([torch.randperm(E)[:K] for _ in range(T)]).int()
+    s = op.prepare_sel2(sel)
+    got = op.cvmm(x, s, keys)
+    ref = torch.einsum("td,tkdh->tkh", x, keys[sel.long()])
+    torch.testing.assert_close(got, ref, rtol=1e-5, atol=1e-5)
+
+
+def test_permutation_maps_are_a_stable_bijection():
+    torch.manual_seed(1)
+    sel = torch.randint(0, 7, (100, 3)).int()
+    s = op.prepare_sel2(sel)
+    flat = sel.flatten()
+    assert sorted(s.out_index.tolist()) == list(range(flat.numel()))
+    assert torch.equal(flat[s.out_index], s.sel.flatten())
+    same = s.sel.flatten()[1:] == s.sel.flatten()[:-1]
+    assert bool((s.out_index[1:][same] > s.out_index[:-1][same]).all())  # stable
+
+
+def test_schedule_respects_cap_and_is_deterministic():
+    draws = torch.rand(200, generator=torch.Generator().manual_seed(3))
+    prior = [torch.ones(200, dtype=torch.bool) for _ in range(2)] + [torch.zeros(200, dtype=torch.bool)]
+    prior[2][::2] = True                      # even steps already have 3 competing layers
+    a = om.build_flip_schedule(200, 0.3, 3, prior, draws)
+    b = om.build_flip_schedule(200, 0.3, 3, prior, draws)
+    assert torch.equal(a, b)
+    assert not bool(a[::2].any())             # full steps never get a 4th competing layer
+    assert int(a.sum()) <= int((draws < 0.3).sum())
