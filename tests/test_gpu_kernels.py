@@ -193,14 +193,16 @@ def test_gemm_linearity_at_full_size(ops):
     r = _route_for_counts(ops, counts)
     D, N = 3072, 16384
     g = torch.Generator(device=DEV).manual_seed(0)
-    a1 = torch.randn(r.row_cap, D, device=DEV, generator=g).bfloat16()
-    a2 = torch.randn(r.row_cap, D, device=DEV, generator=g).bfloat16()
+    # small integers: a1 + a2 is exact in bf16, so the identity holds up to fp32 accumulation order only
+    a1 = torch.randint(-3, 4, (r.row_cap, D), device=DEV, generator=g).bfloat16()
+    a2 = torch.randint(-3, 4, (r.row_cap, D), device=DEV, generator=g).bfloat16()
     w = (torch.randn(4, N, D, device=DEV, generator=g) * 0.02).bfloat16()
-    s = (a1.float() + a2.float()).bfloat16()
-    y1 = ops.gemm_rows(a1, w, w_is_kn=False, route=r, out_dtype=torch.float32)
-    y2 = ops.gemm_rows(a2, w, w_is_kn=False, route=r, out_dtype=torch.float32)
-    ys = ops.gemm_rows(s, w, w_is_kn=False, route=r, out_dtype=torch.float32)
-    assert_close_rms(ys, y1 + y2, 2e-2, "linearity")
+    s = a1 + a2
+    used = int(r.pad_offsets[-1])           # row tiles past the last expert are never written
+    y1 = ops.gemm_rows(a1, w, w_is_kn=False, route=r, out_dtype=torch.float32)[:used]
+    y2 = ops.gemm_rows(a2, w, w_is_kn=False, route=r, out_dtype=torch.float32)[:used]
+    ys = ops.gemm_rows(s, w, w_is_kn=False, route=r, out_dtype=torch.float32)[:used]
+    assert_close_rms(ys, y1 + y2, 1e-4, "linearity")
     # and a spot check of one row tile against torch
     ref = a1[:128].float() @ w[0].float().t()
     assert_close_rms(y1[:128], ref, 1e-3, "tile 0")
