@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""bench.py -- CompeteSMoE MoE-layer forward+backward throughput (tokens/s) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1]): the CompeteSMoE-5.1B-shaped MoE MLP block -- Phi-3.5-mini sized gate_up/down SiLU-GLU
+experts, d=3072, ffn=8192, 4 experts, top-2, bf16, 4096 tokens per GPU, synthetic N(0,1) tokens, random-init weights.
+One "step" = one forward + backward of the layer over one batch (router step: gate -> top-2 -> sparse experts ->
+combine, all gradients).  The competition step (all 4 experts dense + affinity scoring + distillation losses) is timed
+in a second region and reported under "competition"; "mix" is the schedule-weighted blend at rate_flip = 0.05.
+
+Prints ONE JSON line (rank 0).  `value` = tokens/s with inputs resident in HBM, CUDA-event timed, max over ranks;
+`e2e` = the same through the public nn.Module call with HOST buffers (pinned H2D of tokens and upstream gradient and a
+D2H read of the loss inside the timed region); `roofline` = the grouped GEMM's achieved TFLOP/s from per-launch CUDA
+events inside the timed region; `cpu_baseline` = the CPU oracle (port of the reference's PyTorch path) timed on this
+box's host cores on a bounded sample.  `--impl reference` times only that CPU path.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import torch
+import torch.nn as nn
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+D_MODEL, FFN, N_EXPERTS, TOP_K, TOKENS = 3072, 8192, 4, 2, 4096
+RATE_FLIP = 0.05
+WORKLOAD = "competesmoe-5.1b-moe-mlp-block d=3072 ffn=8192 E=4 top2 glu-silu bf16 4096 tokens/gpu fwd+bwd"
+CPU_SAMPLE_TOKENS = 256
+
+
+class GLUExpert(nn.Module):
+    """Phi3MLP-shaped expert (same parameter names: gate_up_proj.weight [2F, D], down_proj.weight [D, F])."""
+
+    def __init__(self, d, f):
+        super().__init__()
+        self.gate_up_proj = nn.Linear(d, 2 * f, bias=False)
+        self.down_proj = nn.Linear(f, d, bias=False)
+        self.activation_fn = nn.SiLU()
+
+
+def layer_args():
+    from types import SimpleNamespace
+    return SimpleNamespace(rate_flip=RATE_FLIP, warm_up=0.0, max_compete_in_iter=3, hybrid=False, router_theta=1.0,
+                           router_loss_coef=0.01, diversity_loss_coef=0.01, bal_comp_loss_coef=0.01,
+                           balance_loss_coef=0.01, router_z_loss_coef=0.001, norm_sigmoid=False, init_weight=True,
+                           moe_name="competesmoe")
+
+
+def flops_per_token(competition: bool) -> float:
+    """F_e = 6*D*F (GLU), router R = 2*D*E; step = 3*(K*F_e + R), competition 3*(E*F_e + R)."""
+    f_e = 6.0 * D_MODEL * FFN
+    r = 2.0 * D_MODEL * N_EXPERTS
+    return 3.0 * ((N_EXPERTS if competition else TOP_K) * f_e + r)
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi sampled every 200 ms while the timed region runs (B200_PROFILING.md clocks line)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        busy = [s for s in sm if s > 0]
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU baseline
+def cpu_reference_step_time(steps: int, warmup: int, tokens: int = CPU_SAMPLE_TOKENS):
+    """The oracle (CPU port of the reference's PyTorch path) on this box's host cores; fp32 like BASELINE configs[0]."""
+    from oracle import multimodal as om
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    g = torch.Generator().manual_seed(1235)
+    exps = [{"kind": "glu", "act": "silu", "w1": (torch.randn(2 * FFN, D_MODEL, generator=g) * 0.02).requires_grad_(True),
+             "w2": (torch.randn(D_MODEL, FFN, generator=g) * 0.02).requires_grad_(True)} for _ in range(N_EXPERTS)]
+    gate_w = (torch.randn(N_EXPERTS, D_MODEL, generator=g) * 0.02).requires_grad_(True)
+    x = torch.randn(1, tokens, D_MODEL, generator=g).requires_grad_(True)
+    dy = torch.randn(1, tokens, D_MODEL, generator=g)
+    args = om.default_args()
+    times = []
+    for i in range(warmup + steps):
+        for t in [x, gate_w] + [e[k] for e in exps for k in ("w1", "w2")]:
+            t.grad = None
+        t0 = time.perf_counter()
+        out, aux, _, _, _ = om.competesmoe_forward(x, gate_w, exps, TOP_K, D_MODEL, args, competition=False)
+        torch.autograd.backward((out, aux), (dy, torch.ones_like(aux)))
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return statistics.median(times), cores, tokens
+
+
+def run_reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = max(1, min(a.steps, 5)), max(1, min(a.warmup, 2))
+    dt, cores, tokens = cpu_reference_step_time(steps, warmup)
+    v = tokens / dt
+    line = {"impl": "reference", "metric": "moe_layer_fwd_bwd_tokens_per_s", "value": v, "unit": "tokens/s",
+            "n_gpus": a.gpus, "steps": steps, "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "step": "router", "sample": f"{tokens} of {TOKENS} tokens per step"},
+            "cpu_baseline": {"value": v, "unit": "tokens/s", "cores": cores, "kind": "port",
+                             "sample": f"{tokens} of {TOKENS} tokens per step, fp32, oracle/multimodal.py"},
+            "e2e": {"value": v, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def build_layer(device):
+    from competesmoe_b200.multimodal import CompeteSMoE
+    torch.manual_seed(0)
+    experts = nn.ModuleList([GLUExpert(D_MODEL, FFN) for _ in range(N_EXPERTS)])
+    layer = CompeteSMoE(D_MODEL, D_MODEL, N_EXPERTS, TOP_K, experts, layer_args())
+    layer = layer.to(device=device, dtype=torch.bfloat16)
+    layer.total_steps, layer.step_warm = 2, 0
+    layer.train()
+    return layer
+
+
+def set_branch(layer, competition: bool):
+    layer.prob_flips = torch.full((2,), bool(competition), device=layer.gate.weight.device)
+    layer.set_current_steps(0)
+
+
+def one_step(layer, x, dy, params):
+    for p in params:
+        p.grad = None
+    x.grad = None
+    out, aux, _, _ = layer(x)
+    torch.autograd.backward((out, aux), (dy, torch.ones_like(aux)))
+    return aux
+
+
+def timed_region(layer, x, dy, params, steps, warmup, dist_on):
+    import torch.distributed as dist
+    for _ in range(warmup):
+        one_step(layer, x, dy, params)
+    if dist_on:
+        dist.barrier()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(steps):
+        one_step(layer, x, dy, params)
+    e.record()
+    torch.cuda.synchronize()
+    if dist_on:
+        dist.barrier()
+    ms = torch.tensor([s.elapsed_time(e)], device=x.device)
+    if dist_on:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms) / steps
+
+
+def e2e_region(layer, x_host, dy_host, params, steps, warmup, dist_on, device):
+    """Public-API call with host buffers: pinned H2D of x and dy, fwd+bwd, D2H of the loss, every step."""
+    import torch.distributed as dist
+    x_dev = torch.empty_like(x_host, device=device).requires_grad_(True)
+    dy_dev = torch.empty_like(dy_host, device=device)
+    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+
+    def step():
+        with torch.no_grad():
+            x_dev.copy_(x_host, non_blocking=True)
+            dy_dev.copy_(dy_host, non_blocking=True)
+        aux = one_step(layer, x_dev, dy_dev, params)
+        loss_host.copy_(aux.detach().float(), non_blocking=True)
+
+    for _ in range(warmup):
+        step()
+    if dist_on:
+        dist.barrier()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(steps):
+        step()
+    e.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([s.elapsed_time(e)], device=device)
+    if dist_on:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    h2d = x_host.numel() * x_host.element_size() + dy_host.numel() * dy_host.element_size()
+    return float(ms) / steps, h2d, loss_host.numel() * loss_host.element_size()
+
+
+def run_ours(a):
+    import torch.distributed as dist
+    from competesmoe_b200 import ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the B200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    dist_on = world > 1
+    if dist_on:
+        dist.init_process_group("nccl", device_id=device)
+    peaks = {}
+    pk = ROOT / "MEASURED_PEAKS.json"
+    if pk.exists():
+        peaks = json.loads(pk.read_text())
+    peak_tf, peak_src = (peaks["bf16_tflops"], "measured (MEASURED_PEAKS.json, burst)") if "bf16_tflops" in peaks else \
+        (1590.0, "fallback (B200_PROFILING.md)")
+
+    layer = build_layer(device)
+    params = [p for p in layer.parameters()]
+    g = torch.Generator().manual_seed(1235 + rank)
+    x_host = torch.randn(1, TOKENS, D_MODEL, generator=g).bfloat16().pin_memory()
+    dy_host = torch.randn(1, TOKENS, D_MODEL, generator=g).bfloat16().pin_memory()
+    x = x_host.to(device).requires_grad_(True)
+    dy = dy_host.to(device)
+
+    # ---- timed region 1: router step, inputs resident in HBM (the headline `value`)
+    set_branch(layer, False)
+    for _ in range(2):
+        one_step(layer, x, dy, params)          # first-call costs (module load, storage fusing) outside any timing
+    sampler = ClockSampler(local) if rank == 0 else None
+    ops.gemm_timing = []
+    launches0 = ops.launch_count
+    ms_router = timed_region(layer, x, dy, params, a.steps, a.warmup, dist_on)
+    launches = (ops.launch_count - launches0) * a.steps // (a.steps + a.warmup)
+    torch.cuda.synchronize()
+    timed = ops.gemm_timing[-(len(ops.gemm_timing) * a.steps // (a.steps + a.warmup)):]
+    ops.gemm_timing = None
+    gemm_ms = [s.elapsed_time(e) for s, e, _, _ in timed]
+    gemm_flops = [f for _, _, f, _ in timed]
+    gemm_tflops = sum(gemm_flops) / (sum(gemm_ms) * 1e-3) / 1e12 if gemm_ms else 0.0
+    gemm_share = sum(gemm_ms) / (ms_router * a.steps) if gemm_ms else 0.0
+
+    # ---- timed region 2: competition step
+    set_branch(layer, True)
+    ms_comp = timed_region(layer, x, dy, params, max(2, a.steps // 2), a.warmup, dist_on)
+    # ---- timed region 3: end to end through the module with host buffers (router step)
+    set_branch(layer, False)
+    ms_e2e, h2d, d2h = e2e_region(layer, x_host, dy_host, params, a.steps, a.warmup, dist_on, device)
+    clocks = sampler.stop() if sampler else None
+
+    if rank == 0:
+        tok = TOKENS * world
+        value = tok / (ms_router * 1e-3)
+        comp = tok / (ms_comp * 1e-3)
+        mix_ms = (1 - RATE_FLIP) * ms_router + RATE_FLIP * ms_comp
+        cpu = None
+        if world == 1:
+            dt, cores, tokens = cpu_reference_step_time(2, 1)
+            cpu = {"value": tokens / dt, "unit": "tokens/s", "cores": cores, "kind": "port",
+                   "sample": f"{tokens} of {TOKENS} tokens per step, fp32, router step, oracle/multimodal.py"}
+        traffic = None
+        tf = ROOT / "profiles" / "gemm_traffic.json"
+        if tf.exists():
+            traffic = json.loads(tf.read_text()).get("dram_bytes_per_launch")
+        line = {
+            "metric": "moe_layer_fwd_bwd_tokens_per_s", "value": value, "unit": "tokens/s", "n_gpus": world,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_router, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "step": "router", "tokens_per_gpu": TOKENS,
+                       "parallelism": "single GPU" if world == 1 else f"{world} independent data-parallel replicas",
+                       "l2": "per-step working set (0.6 GB of expert weights + 0.5 GB activations) exceeds the 126 MB L2; no flush"},
+            "model_tflops": flops_per_token(False) * tok / (ms_router * 1e-3) / 1e12,
+            "model_frac_of_peak": flops_per_token(False) * TOKENS / (ms_router * 1e-3) / 1e12 / peak_tf,
+            "competition": {"ms_per_step": ms_comp, "tokens_per_s": comp,
+                            "model_tflops": flops_per_token(True) * tok / (ms_comp * 1e-3) / 1e12,
+                            "model_frac_of_peak": flops_per_token(True) * TOKENS / (ms_comp * 1e-3) / 1e12 / peak_tf},
+            "mix": {"rate_flip": RATE_FLIP, "ms_per_step": mix_ms, "tokens_per_s": tok / (mix_ms * 1e-3)},
+            "e2e": {"value": tok / (ms_e2e * 1e-3), "unit": "tokens/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},
+            "roofline": {"bound": "tensor", "achieved": gemm_tflops, "peak": peak_tf, "unit": "TFLOP/s",
+                         "frac": gemm_tflops / peak_tf, "traffic": traffic, "kernel": "grouped_gemm_kernel (tcgen05)",
+                         "peak_source": peak_src, "launches_per_step": len(timed) // max(a.steps, 1),
+                         "share_of_step": gemm_share},
+            "cpu_baseline": cpu, "gpu_launches": launches, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if dist_on:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3)
+    if a.impl == "reference":
+        run_reference_arm(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

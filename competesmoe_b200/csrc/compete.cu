@@ -14,7 +14,8 @@ __device__ __forceinline__ float sigmoid_sp(float x) { return x > 20.f ? 1.f : 1
 
 template <typename T>
 __global__ void __launch_bounds__(kWarps * 32)
-affinity_fwd_kernel(const T* __restrict__ y, int E, long long Tn, long long t_pad, int D, float* __restrict__ aff) {
+affinity_fwd_kernel(const T* __restrict__ y, int E, long long Tn, long long t_pad, int D, int round_bf16,
+                    float* __restrict__ aff) {
   const int lane = threadIdx.x & 31;
   const long long total = static_cast<long long>(E) * Tn;
   for (long long i = static_cast<long long>(blockIdx.x) * kWarps + (threadIdx.x >> 5); i < total;
@@ -26,11 +27,17 @@ affinity_fwd_kernel(const T* __restrict__ y, int E, long long Tn, long long t_pa
       float v[8];
       load8(row + c, v);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) s += round_as(softplus_f(v[j]), static_cast<const T*>(nullptr));
+      for (int j = 0; j < 8; ++j) {
+        const float sp = softplus_f(v[j]);
+        s += round_bf16 ? bf16_round(sp) : sp;
+      }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) aff[t * E + e] = round_as(s / static_cast<float>(D), static_cast<const T*>(nullptr));
+    if (lane == 0) {
+      const float m = s / static_cast<float>(D);
+      aff[t * E + e] = round_bf16 ? bf16_round(m) : m;
+    }
   }
 }
 
@@ -74,17 +81,18 @@ inline unsigned row_grid(long long rows) {
 using namespace csmoe;
 
 extern "C" int csmoe_affinity_fwd(const void* y, int32_t dtype, int32_t E, int64_t T_, int64_t t_pad, int32_t D,
-                                  float* aff, void* stream_) {
+                                  int32_t round_dtype, float* aff, void* stream_) {
   CSMOE_CHECK_ARG(y && aff, "csmoe_affinity_fwd: NULL pointer");
   CSMOE_CHECK_ARG(E >= 1 && D > 0 && D % 8 == 0 && t_pad >= T_, "csmoe_affinity_fwd: bad sizes");
   if (T_ == 0) return CSMOE_OK;
   cudaStream_t stream = as_stream(stream_);
   const unsigned grid = row_grid(static_cast<long long>(E) * T_);
+  const int rb = round_dtype == CSMOE_BF16 ? 1 : 0;
   if (dtype == CSMOE_BF16) {
     affinity_fwd_kernel<__nv_bfloat16><<<grid, kWarps * 32, 0, stream>>>(static_cast<const __nv_bfloat16*>(y), E, T_,
-                                                                         t_pad, D, aff);
+                                                                         t_pad, D, rb, aff);
   } else if (dtype == CSMOE_F32) {
-    affinity_fwd_kernel<float><<<grid, kWarps * 32, 0, stream>>>(static_cast<const float*>(y), E, T_, t_pad, D, aff);
+    affinity_fwd_kernel<float><<<grid, kWarps * 32, 0, stream>>>(static_cast<const float*>(y), E, T_, t_pad, D, rb, aff);
   } else {
     CSMOE_CHECK_ARG(false, "csmoe_affinity_fwd: unsupported dtype %d", dtype);
   }

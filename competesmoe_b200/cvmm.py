@@ -1,0 +1,137 @@
+"""Drop-in for the CVMM op boundary (reference: moe_pretrain_model/layers/cvmm.py).
+
+Same public names and argument meaning -- `CVMMSel`, `cvmm_prepare_sel`, `cvmm_prepare_sel2`, `cvmm(x, sel, keys)` --
+but the sort is a stable counting sort on the GPU (csmoe_route_build) and the conditional matmul is the tcgen05 grouped
+GEMM over TMA-staged, expert-major rows instead of Triton pointer gathers; the weight gradient is a deterministic
+grouped GEMM instead of split-K fp32 atomics (cvmm.py:194-345).
+
+    cvmm(x, sel, keys)[out_index[i]] = x[sel_index[i]] @ keys[sel.sel[i]]      (+ weighted reduction over K, :481-483)
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional, Union
+
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import ops
+
+
+@dataclass
+class CVMMSel:
+    raw_sel: torch.Tensor
+    sel: torch.Tensor
+    sel_index: torch.Tensor
+    out_index: Optional[torch.Tensor] = None
+    reduction_weight: Optional[torch.Tensor] = None
+    _route: Optional[ops.Route] = None   # permutation maps of the padded expert-major space (built once per selection)
+
+    def clone(self) -> "CVMMSel":
+        return CVMMSel(self.raw_sel, self.sel, self.sel_index, self.out_index, self.reduction_weight, self._route)
+
+
+def _num_experts_hint(sel: torch.Tensor, n_experts: Optional[int]) -> int:
+    if n_experts is None:
+        raise ValueError("the number of experts is needed to build the routing maps")
+    return n_experts
+
+
+def cvmm_prepare_sel(sel: torch.Tensor, n_experts: int) -> CVMMSel:
+    """cvmm.py:23-26: one selection per row."""
+    route = ops.route_build(sel.reshape(-1, 1), n_experts)
+    return CVMMSel(sel, route.sorted_sel.view_as(sel), route.sort_index, None, None, route)
+
+
+def cvmm_prepare_sel2(sel: torch.Tensor, w: Optional[torch.Tensor] = None, n_experts: Optional[int] = None) -> CVMMSel:
+    """cvmm.py:580-592: K selections per row; sel_index = sorted position // K, out_index = sorted position.
+    The reference infers nothing about E here; pass `n_experts` or let `cvmm` rebuild the maps from `keys.shape[0]`."""
+    k = sel.shape[-1]
+    if n_experts is None:
+        return CVMMSel(sel, None, None, None, w, None)  # completed lazily by cvmm() once E is known
+    route = ops.route_build(sel.reshape(-1, k), n_experts)
+    return CVMMSel(sel, route.sorted_sel.view_as(sel), route.sort_index // k, route.sort_index, w, route)
+
+
+def _complete(sel: CVMMSel, n_experts: int) -> CVMMSel:
+    if sel._route is not None and sel._route.num_experts == n_experts:
+        return sel
+    k = sel.raw_sel.shape[-1]
+    route = ops.route_build(sel.raw_sel.reshape(-1, k), n_experts)
+    sel._route = route
+    if sel.sel is None:
+        sel.sel = route.sorted_sel.view_as(sel.raw_sel)
+        sel.sel_index = route.sort_index // k
+        sel.out_index = route.sort_index
+    return sel
+
+
+def _out_dtype(x: torch.Tensor) -> torch.dtype:
+    """cvmm.py:29-32 get_dtype(): fp32 unless autocast is active."""
+    if torch.is_autocast_enabled():
+        return torch.get_autocast_gpu_dtype()
+    return x.dtype if x.dtype in (torch.bfloat16,) else torch.float32
+
+
+class CVMM(Function):
+    """cvmm.py:460-551."""
+
+    @staticmethod
+    def forward(ctx, x, keys, route: ops.Route, slots_per_row: int, reduction_weight, out_dtype):
+        x2 = x.flatten(end_dim=-2)
+        xb = ops.cast_bf16(x2) if x2.dtype != torch.bfloat16 else x2
+        kb = ops.cast_bf16(keys) if keys.dtype != torch.bfloat16 else keys
+        xp = ops.gather_rows(xb, route, slots_per_src_row=slots_per_row)
+        yp = ops.gemm_rows(xp, kb, w_is_kn=True, route=route, out_dtype=out_dtype)
+        n_slots, K = route.n_slots, route.top_k
+        if reduction_weight is None:
+            out = ops.scatter_reduce(yp, route.slot_to_row, n_slots, 1)           # back to slot order, no reduction
+        else:
+            out = ops.combine_fwd(yp, route.slot_to_row, route.sel, reduction_weight.float(), n_slots // K, K,
+                                  round_w=out_dtype == torch.bfloat16)
+        ctx.route, ctx.slots_per_row = route, slots_per_row
+        ctx.x_shape, ctx.x_dtype, ctx.out_dtype = x.shape, x.dtype, out_dtype
+        ctx.save_for_backward(xp, yp, keys, reduction_weight)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        xp, yp, keys, rw = ctx.saved_tensors
+        route = ctx.route
+        n_slots, K, E = route.n_slots, route.top_k, route.num_experts
+        g2 = g.reshape(-1, g.shape[-1]).contiguous()
+        gb = ops.cast_bf16(g2) if g2.dtype != torch.bfloat16 else g2
+        kb = ops.cast_bf16(keys) if keys.dtype != torch.bfloat16 else keys
+        drw = None
+        if rw is None:
+            gp = ops.gather_rows(gb, route, slots_per_src_row=1)
+        else:
+            ypb = yp if yp.dtype == gb.dtype else yp.to(gb.dtype)
+            drw = ops.combine_bwd_w(ypb, gb, route.slot_to_row, n_slots // K, K).view_as(rw).to(rw.dtype)
+            wv = rw.float()
+            if ctx.out_dtype == torch.bfloat16:
+                wv = wv.bfloat16().float()
+            gp = ops.gather_rows(gb, route, slot_w=wv, slots_per_src_row=K)
+        dkeys = ops.gemm_reduce(xp, gp, E, route=route, out_dtype=keys.dtype)        # [E, k_in, n]
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dxp = ops.gemm_rows(gp, kb, w_is_kn=False, route=route)                 # gp @ keys^T
+            rows_in = n_slots // ctx.slots_per_row
+            dx = ops.scatter_reduce(dxp, route.slot_to_row, rows_in, ctx.slots_per_row).view(ctx.x_shape).to(ctx.x_dtype)
+        return dx, dkeys, None, None, drw, None
+
+
+def cvmm(x: torch.Tensor, sel: Union[torch.Tensor, CVMMSel], keys: torch.Tensor) -> torch.Tensor:
+    """cvmm.py:555-577.  `keys` is [E, k_in, n]."""
+    if not isinstance(sel, CVMMSel):
+        sel = cvmm_prepare_sel(sel, keys.shape[0])
+    sel = _complete(sel, keys.shape[0])
+    # prepare_sel2 pattern: sel_index = pos // K with out_index = pos (K slots share one input row);
+    # after `sel_index = out_index; out_index = None` (or prepare_sel) every slot has its own input row.
+    slots_per_row = sel.raw_sel.shape[-1] if sel.out_index is not None else 1
+    out = CVMM.apply(x, keys, sel._route, slots_per_row, sel.reduction_weight, _out_dtype(x))
+    if sel.reduction_weight is None:
+        return out.view(*sel.raw_sel.shape, keys.shape[-1])
+    return out.view(*sel.reduction_weight.shape[:-1], keys.shape[-1])

@@ -191,8 +191,8 @@ class AffinityFn(Function):
     """aff[t, e] = mean_d softplus(y[e, t, d]) (fp32 tensor holding values rounded to y.dtype)."""
 
     @staticmethod
-    def forward(ctx, y, num_experts: int, T: int, t_pad: int):
-        aff = ops.affinity_fwd(y, num_experts, T, t_pad)
+    def forward(ctx, y, num_experts: int, T: int, t_pad: int, eager_bf16: bool):
+        aff = ops.affinity_fwd(y, num_experts, T, t_pad, eager_bf16)
         ctx.save_for_backward(y)
         ctx.dims = (num_experts, T, t_pad)
         return aff
@@ -202,7 +202,7 @@ class AffinityFn(Function):
     def backward(ctx, daff):
         (y,) = ctx.saved_tensors
         E, T, t_pad = ctx.dims
-        return ops.affinity_bwd(y, daff, E, T, t_pad), None, None, None
+        return ops.affinity_bwd(y, daff, E, T, t_pad), None, None, None, None
 
 
 class SelectCombineFn(Function):

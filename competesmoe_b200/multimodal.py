@@ -237,7 +237,7 @@ class CompeteSMoE(MoeLayer):
         if self._is_competition_step(x):
             y_all = DenseFFNFn.apply(x2, w1, b1, w2, b2, spec)                       # [E * t_pad, Dout]
             t_pad = y_all.shape[0] // E
-            aff = AffinityFn.apply(y_all, E, T, t_pad)                               # [T, E] f32 (x.dtype-rounded)
+            aff = AffinityFn.apply(y_all, E, T, t_pad, x.dtype == torch.bfloat16)                             # [T, E] f32 (x.dtype-rounded)
             aff_softmax = F.softmax(aff, dim=-1, dtype=torch.float32)
             aff_w, aff_idx = TopkRenormFn.apply(aff, K, bool(getattr(self.args, "norm_sigmoid", False)), x.dtype)
             li = aff_idx.long()

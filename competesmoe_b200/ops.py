@@ -22,7 +22,8 @@ __all__ = [
     "affinity_bwd", "ACT_NONE", "ACT_RELU", "ACT_GELU", "ACT_GELU_TANH", "ACT_SILU", "ACT_SILU_GLU",
 ]
 
-launch_count = 0  # number of libcsmoe kernel-launching calls issued (bench.py reports it)
+launch_count = 0  # number of libcsmoe kernels launched so far (bench.py reports the delta over its timed region)
+gemm_timing = None  # when set to a list, every grouped GEMM is bracketed by CUDA events: (start, end, flops, tag)
 
 
 def _dt(t: torch.Tensor) -> int:
@@ -47,9 +48,9 @@ def _p(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
 
 
-def _call(name: str, *args) -> None:
+def _call(name: str, *args, kernels: int = 1) -> None:
     global launch_count
-    launch_count += 1
+    launch_count += kernels
     check(getattr(_lib.load(), name)(*args), name)
 
 
@@ -99,7 +100,8 @@ def route_build(sel: torch.Tensor, num_experts: int) -> Route:
     row_to_slot = torch.empty(row_cap, **i32)
     tile_expert = torch.empty(row_cap // ROW_TILE, **i32)
     _call("csmoe_route_build", _p(flat), n, num_experts, row_cap, _p(counts), _p(offsets), _p(pad_offsets),
-          _p(sorted_sel), _p(sort_index), _p(slot_to_row), _p(row_to_slot), _p(tile_expert), _p(ws), _stream())
+          _p(sorted_sel), _p(sort_index), _p(slot_to_row), _p(row_to_slot), _p(tile_expert), _p(ws), _stream(),
+          kernels=3 if n > 0 else 2)
     return Route(num_experts, top_k, n, row_cap, flat, counts, offsets, pad_offsets, sorted_sel, sort_index,
                  slot_to_row, row_to_slot, tile_expert)
 
@@ -136,16 +138,20 @@ def topk_renorm(scores: torch.Tensor, top_k: int, sigmoid: bool = False, round_d
 
 
 # ----------------------------------------------------------------------------------------------- permutation
-def gather_rows(src: torch.Tensor, route: Route, slot_w: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """src [T, D] -> [row_cap, D] in the padded expert-major space (zeros on padding rows)."""
+def gather_rows(src: torch.Tensor, route: Route, slot_w: Optional[torch.Tensor] = None,
+                slots_per_src_row: Optional[int] = None) -> torch.Tensor:
+    """src [T, D] -> [row_cap, D] in the padded expert-major space (zeros on padding rows).
+    Row r reads src[row_to_slot[r] // slots_per_src_row] (default: the route's top_k, i.e. src is token-major)."""
     _cuda(src, slot_w)
     src = src.contiguous()
     T, D = src.shape
+    k_div = route.top_k if slots_per_src_row is None else slots_per_src_row
+    assert T * k_div == route.n_slots, f"gather_rows: {T} source rows x {k_div} != {route.n_slots} slots"
     dst = torch.empty(route.row_cap, D, dtype=src.dtype, device=src.device)
     if slot_w is not None:
         slot_w = slot_w.reshape(-1).contiguous()
         assert slot_w.dtype == torch.float32 and slot_w.numel() == route.n_slots
-    _call("csmoe_gather_rows", _p(src), _dt(src), T, D, route.top_k, _p(route.row_to_slot), route.row_cap, _p(slot_w),
+    _call("csmoe_gather_rows", _p(src), _dt(src), T, D, k_div, _p(route.row_to_slot), route.row_cap, _p(slot_w),
           _p(dst), _stream())
     return dst
 
@@ -185,8 +191,15 @@ def scatter_reduce(g: torch.Tensor, slot_to_row: torch.Tensor, T: int, top_k: in
 
 
 # ----------------------------------------------------------------------------------------------- grouped GEMM
-def _gemm(args: GemmArgs) -> None:
+def _gemm(args: GemmArgs, flops: float = 0.0, tag: str = "") -> None:
+    if gemm_timing is None:
+        _call("csmoe_grouped_gemm", C.byref(args), _stream())
+        return
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
     _call("csmoe_grouped_gemm", C.byref(args), _stream())
+    end.record()
+    gemm_timing.append((start, end, flops, tag))
 
 
 def gemm_rows(a: torch.Tensor, w: torch.Tensor, *, w_is_kn: bool, route: Optional[Route] = None,
@@ -231,7 +244,8 @@ def gemm_rows(a: torch.Tensor, w: torch.Tensor, *, w_is_kn: bool, route: Optiona
         bias = bias.contiguous()
         assert bias.shape == (E, n)
         g.bias, g.bias_dtype = _p(bias), _dt(bias)
-    _gemm(g)
+    algo_rows = E * dense_rows if dense_rows else route.n_slots
+    _gemm(g, 2.0 * algo_rows * n * k, "rows_kn" if w_is_kn else "rows_nk")
     return (c, pre) if want_preact else c
 
 
@@ -258,7 +272,8 @@ def gemm_reduce(a: torch.Tensor, b: torch.Tensor, num_experts: int, *, route: Op
     g.b, g.ldb = _p(b), b.stride(0)
     c = torch.empty(num_experts, m, n, dtype=out_dtype, device=a.device)
     g.c, g.ldc, g.c_expert_stride, g.c_dtype = _p(c), n, m * n, _dt(c)
-    _gemm(g)
+    algo_rows = num_experts * dense_rows if dense_rows else route.n_slots
+    _gemm(g, 2.0 * algo_rows * m * n, "reduce")
     return c
 
 
@@ -308,12 +323,13 @@ def cast_bf16(src: torch.Tensor) -> torch.Tensor:
 
 
 # ----------------------------------------------------------------------------------------------- competition
-def affinity_fwd(y: torch.Tensor, num_experts: int, T: int, t_pad: int) -> torch.Tensor:
-    """y [E * t_pad, D] -> aff [T, E] f32 (values rounded to y.dtype)."""
+def affinity_fwd(y: torch.Tensor, num_experts: int, T: int, t_pad: int, eager_bf16: bool) -> torch.Tensor:
+    """y [E * t_pad, D] -> aff [T, E] f32.  eager_bf16: round each softplus and the mean to bf16 (eager bf16 modules);
+    otherwise keep fp32 (autocast semantics: softplus and mean run in fp32)."""
     _cuda(y)
     D = y.shape[-1]
     aff = torch.empty(T, num_experts, dtype=torch.float32, device=y.device)
-    _call("csmoe_affinity_fwd", _p(y), _dt(y), num_experts, T, t_pad, D, _p(aff), _stream())
+    _call("csmoe_affinity_fwd", _p(y), _dt(y), num_experts, T, t_pad, D, BF16 if eager_bf16 else F32, _p(aff), _stream())
     return aff
 
 

@@ -1,0 +1,405 @@
+"""Drop-in for the language-pretraining MoE plugin (reference: moe_pretrain_model/layers/moe/{moe.py,competesmoe.py,
+register.py} and the three framework mixins the layer inherits, framework/layers/{regularized,logging,once_per_iter}_layer.py).
+
+Same constructor keywords, `forward(x, *, id_layer)`, schedule hooks, regulariser names (`mlp_ebalance`,
+`mlp_router_loss`, `mlp_comp_diver_loss`, `mlp_comp_ebalance`) and checkpoint layout (`w_gate [E,D]`, `keys [E,D,H]`,
+`values [E,H,D]`, optional `bias [E,H]`, `o_bias [D]`).  The two CVMM calls + eager bmm of the reference's
+`compute_moe_main` are replaced by one fused permute -> grouped GEMM -> activation -> grouped GEMM -> combine path
+(functional.SparseFFNFn); parameters stay fp32 and are cast to bf16 per step, as under the reference's autocast.
+"""
+from __future__ import annotations
+
+import math
+from typing import Any, Callable, Dict, Optional
+
+import torch
+import torch.nn.functional as F
+
+from . import ops
+from .functional import AffinityFn, DenseFFNFn, FFNSpec, GateFn, GatherRowsFn, SelectCombineFn, SparseFFNFn
+from .multimodal import TopkRenormFn
+from .schedule import make_layer_schedule
+
+MOE_REGISTRY: Dict[str, type] = {}
+
+
+def register_moe(*names):
+    def decorate(cls):
+        for name in names:
+            if name in MOE_REGISTRY and MOE_REGISTRY[name] != cls:
+                raise AssertionError(f"Model named '{name}' conflicts with existing model!")
+            MOE_REGISTRY[name] = cls
+        return cls
+    return decorate
+
+
+def get_moe(model_name):
+    try:
+        return MOE_REGISTRY[model_name]
+    except KeyError:
+        raise ValueError(f"Attempted to load moe method'{model_name}', but no model for this name found! "
+                         f"Supported model names: {', '.join(MOE_REGISTRY.keys())}")
+
+
+# ------------------------------------------------------------------------------------------------ mixins
+class RegularizedLayer:
+    """framework/layers/regularized_layer.py:9-62: named regularisers, averaged per name on read, then reset."""
+
+    def __init__(self) -> None:
+        super().__init__()
+        self.reg_accumulated = {}
+        self.reg_counts_n = {}
+        self.regularization_present = False
+
+    @property
+    def reg_enabled(self) -> bool:
+        return self.training and self.regularization_present
+
+    def add_reg(self, loss_fn: Callable[[], torch.Tensor], name: str = "reg"):
+        if self.reg_enabled:
+            v = loss_fn()
+            if name in self.reg_accumulated:
+                self.reg_accumulated[name] = self.reg_accumulated[name] + v
+                self.reg_counts_n[name] += 1
+            else:
+                self.reg_accumulated[name] = v
+                self.reg_counts_n[name] = 1
+
+    def get_reg_loss(self) -> Dict[str, torch.Tensor]:
+        out = {n: self.reg_accumulated[n] / self.reg_counts_n[n] for n in self.reg_accumulated}
+        self.reg_accumulated = {}
+        self.reg_counts_n = {}
+        return out
+
+
+class LoggingLayer:
+    """framework/layers/logging_layer.py:9-52 (running sums of logged scalars)."""
+
+    def __init__(self) -> None:
+        super().__init__()
+        self._logs = {}
+        self._log_counts = {}
+
+    def log(self, name: str, value: Any, drop_old: bool = False):
+        if torch.is_tensor(value):
+            value = value.detach()
+        if name not in self._logs or drop_old or not isinstance(value, (torch.Tensor, float, int)):
+            self._logs[name], self._log_counts[name] = value, 1
+        else:
+            self._logs[name] = self._logs[name] + value
+            self._log_counts[name] += 1
+
+    def get_logs(self) -> Dict[str, Any]:
+        res = {k: (v / self._log_counts[k] if isinstance(v, (torch.Tensor, float, int)) else v) for k, v in self._logs.items()}
+        self._logs, self._log_counts = {}, {}
+        return res
+
+
+class OncePerIterLayer:
+    """framework/layers/once_per_iter_layer.py:1-10."""
+
+    def pre_train_forward(self):
+        pass
+
+    def post_train_forward(self):
+        pass
+
+    def before_loss(self):
+        pass
+
+
+def _activation_code(fn: Callable) -> int:
+    """The reference passes the activation as a callable (tasks/transformer_lm_mixin.py:121-122); identify it by value."""
+    probe = torch.tensor([-2.0, -0.5, 0.0, 0.75, 3.0])
+    got = fn(probe.clone())
+    for code, ref in ((ops.ACT_RELU, F.relu(probe)), (ops.ACT_GELU, F.gelu(probe)),
+                      (ops.ACT_GELU_TANH, F.gelu(probe, approximate="tanh")), (ops.ACT_SILU, F.silu(probe)),
+                      (ops.ACT_NONE, probe)):
+        if torch.allclose(got, ref, atol=1e-6):
+            return code
+    raise NotImplementedError("expert activation is not one of relu / gelu / gelu-tanh / silu / identity")
+
+
+# ------------------------------------------------------------------------------------------------ base layer
+class MoE(LoggingLayer, RegularizedLayer, OncePerIterLayer, torch.nn.Module):
+    """sigma-MoE layout MoE MLP (reference: layers/moe/moe.py:35-138,323-332,373-440)."""
+
+    def __init__(self, dmodel: int, n_experts: int, expert_size: int, n_heads: int, std_gate: float = 1.0,
+                 std_expert: float = 1.0, topk=2, dropout: float = 0, weight_scale: float = 1.0,
+                 selection_mode: str = "sigmoid", perplexity_reg: float = 0.0, perplexity_reg_mode: str = "step",
+                 activation_after_topk: bool = False, activation=F.relu, sel_bias: bool = False, bias: bool = False,
+                 v_dim: Optional[int] = None, expert_dropout: float = 0.0, sync_distributed: bool = False,
+                 selection_dropout: float = 0.0, log_interval: Optional[int] = 100, args=None, is_att=False,
+                 out_dmodel=None, inp_expert=None, out_expert=None):
+        super().__init__()
+        if is_att:
+            raise NotImplementedError("the attention-projection variant (is_att) is outside the MoE-MLP hot path")
+        self.is_att = False
+        self.iter = 0
+        self.k_dim = self.k_vec_dim = dmodel
+        self.v_dim = v_dim if v_dim is not None else dmodel
+        self.n_experts = self.num_experts = self.num_of_experts = n_experts
+        self.expert_size = expert_size
+        self.size = n_experts * expert_size
+        self.n_heads = n_heads
+        self.num_selected = n_heads                      # moe.py:128: top-k is pkm.n_heads, the `topk` argument is ignored
+        self.dropout, self.expert_dropout, self.selection_dropout = dropout, expert_dropout, selection_dropout
+        self.selection_mode, self.perplexity_reg, self.perplexity_reg_mode = selection_mode, perplexity_reg, perplexity_reg_mode
+        self.activation_after_topk = activation_after_topk
+        self.activation = activation
+        self._act_code = _activation_code(activation)
+        self.weight_scale = self.sel_weight_scale = weight_scale
+        self.layer = 0
+        self.was_training = True
+        self.sync_distributed = sync_distributed and torch.distributed.is_initialized()
+        self.log_interval = log_interval
+        self.out_dmodel = out_dmodel if out_dmodel is not None else dmodel
+        self.div = 1
+        self.real_n_experts = 1
+        self.name_moe = "mlp"
+        self.args = args
+        self.training = False
+        self.w_gate = torch.nn.Parameter(torch.empty(n_experts, dmodel))
+        torch.nn.init.normal_(self.w_gate, std=dmodel ** -0.5 * weight_scale)
+        self.register_parameter("values", torch.nn.Parameter(torch.empty(n_experts, expert_size, self.v_dim)))
+        self.register_parameter("keys", torch.nn.Parameter(torch.empty(n_experts, dmodel, expert_size)))
+        torch.nn.init.normal_(self.keys, std=dmodel ** -0.5 * weight_scale)
+        torch.nn.init.normal_(self.values, std=self.size ** -0.5 * weight_scale)
+        if bias:
+            self.bias = torch.nn.Parameter(torch.zeros(n_experts, expert_size))
+            self.o_bias = torch.nn.Parameter(torch.zeros(self.v_dim))
+        else:
+            self.bias = None
+            self.o_bias = None
+        self.dist_experts = None
+        self.entropy_expert_selected, self.entropy_expert_all = [], []
+        self.last_routing = None
+        self.pre_train_forward()
+
+    gate = property(lambda self: (lambda x: F.linear(x, self.w_gate, None)))
+
+    # ---- bookkeeping hooks
+    def pre_train_forward(self):
+        self.total_selections, self.total_gate_softmax, self.total_gate_logits = [], [], []
+
+    def before_loss(self):
+        self.pre_train_forward()
+        if self.training:
+            self.iter += 1
+
+    def add_dist_experts(self, selection=None):
+        sel = selection.reshape(-1, selection.shape[-1]).long()
+        hist = F.one_hot(sel, num_classes=self.num_of_experts).reshape(-1, self.num_of_experts).sum(-2)
+        self.dist_experts = hist if self.dist_experts is None else self.dist_experts + hist
+
+    def get_dist_experts(self):
+        return self.dist_experts
+
+    def add_dist_weight(self, weight, is_all=False):
+        ent = (-(weight * torch.log(weight + 1e-18)).sum(-1)).mean()
+        (self.entropy_expert_all if is_all else self.entropy_expert_selected).append(ent)
+
+    # ---- losses
+    def entropy_balance(self, sel: torch.Tensor) -> torch.Tensor:
+        """moe.py:323-332: minus the entropy of the sequence-averaged routing distribution, averaged over the batch."""
+        s = sel.flatten(1, -2)
+        ls = F.log_softmax(s.float(), dim=-1)
+        lm = ls.logsumexp(-2) - math.log(ls.shape[-2])
+        return (lm * lm.exp()).sum(-1).mean()
+
+    # ---- compute
+    def _compute_dtype(self, x: torch.Tensor) -> torch.dtype:
+        if torch.is_autocast_enabled():
+            return torch.get_autocast_gpu_dtype()
+        return x.dtype
+
+    def _spec(self, cdt: torch.dtype) -> FFNSpec:
+        # CVMM.forward reduces with `reduction_weight.type_as(res) @ res` (cvmm.py:481-483): weight rounded to the op
+        # dtype, fp32 accumulation, one rounding at the end.
+        return FFNSpec(act=self._act_code, kn_layout=True, round_each=False, round_w=cdt == torch.bfloat16)
+
+    def compute_gate(self, x2: torch.Tensor, cdt: torch.dtype):
+        return GateFn.apply(x2.to(cdt), self.w_gate, self.num_selected)
+
+    def _log_relu_pass_rate(self, out):
+        pass  # the hidden activations never leave the fused kernels; the reference logs this only every log_interval
+
+    def compute_moe_main(self, x2, selected, weights, cdt):
+        return SparseFFNFn.apply(x2.to(cdt), weights, selected, self.keys, self.bias, self.values, None, self._spec(cdt))
+
+    def forward(self, x, return_id_experts=False, return_full=True, *args, **kwargs):
+        """Plain sigma-MoE forward (moe.py:418-449)."""
+        B = x.shape[:-1]
+        cdt = self._compute_dtype(x)
+        x2 = x.reshape(-1, x.shape[-1])
+        logits, probs, gw, gidx = self.compute_gate(x2, cdt)
+        if self.training is False:
+            self.add_dist_experts(selection=gidx)
+        out = self.compute_moe_main(x2, gidx, gw, cdt)
+        self.layer += 1
+        self.was_training = self.training
+        res = out.view(*B, self.v_dim)
+        if self.o_bias is not None:
+            res = res + self.o_bias
+        lg = logits.view(*B, -1)
+        self.add_reg(lambda: self.entropy_balance(lg) * (self.args.balance_loss_coef / self.div), f"{self.name_moe}_ebalance")
+        return res
+
+
+# ------------------------------------------------------------------------------------------------ CompeteSMoE
+@register_moe("competesmoe", "competesmoe_b200")
+class CompeteSMoE(MoE):
+    """reference: layers/moe/competesmoe.py:37-616."""
+
+    def __init__(self, dmodel: int, n_experts: int, expert_size: int, n_heads: int, std_gate=1.0, std_expert=1.0, topk=2,
+                 dropout: float = 0, weight_scale: float = 1.0, selection_mode: str = "sigmoid",
+                 perplexity_reg: float = 0.0, perplexity_reg_mode: str = "step", activation_after_topk: bool = False,
+                 activation=F.relu, sel_bias: bool = False, bias: bool = False, v_dim: Optional[int] = None,
+                 expert_dropout: float = 0.0, sync_distributed: bool = False, selection_dropout: float = 0.0,
+                 log_interval: Optional[int] = 100, args=None, std=1, out_dmodel=None, is_att=False, inp_expert=None,
+                 out_expert=None):
+        super().__init__(dmodel=dmodel, n_experts=n_experts, expert_size=expert_size, n_heads=n_heads, topk=topk,
+                         dropout=dropout, weight_scale=weight_scale, selection_mode=selection_mode,
+                         perplexity_reg=perplexity_reg, perplexity_reg_mode=perplexity_reg_mode,
+                         activation_after_topk=activation_after_topk, activation=activation, sel_bias=sel_bias, bias=bias,
+                         v_dim=v_dim, expert_dropout=expert_dropout, sync_distributed=sync_distributed,
+                         selection_dropout=selection_dropout, log_interval=log_interval, args=args,
+                         out_dmodel=out_dmodel, is_att=is_att, out_expert=out_expert, inp_expert=inp_expert,
+                         std_gate=std_gate, std_expert=std_expert)
+        self.warm_up = args.warm_up
+        self.rate_flip = args.rate_flip
+        self.current_steps = 0
+        self.step_warm = None
+        self.is_prob_flips = True
+        assert args.stop_after > 0, f"Warning: stop_after {args.stop_after} < 1, You must setting stop_after > 0"
+        self.total_steps = args.stop_after
+        self.prob_flips_final = {}
+        self.max_compete_in_iter = args.max_compete_in_iter
+        self.nb_diver = 0
+        self._flips_host = {}
+
+    # ---- schedule (competesmoe.py:123-273, :328-329)
+    def set_total_steps(self, id_layer=0):
+        self.step_warm, flags = make_layer_schedule(self.total_steps, self.warm_up, self.rate_flip,
+                                                    self.max_compete_in_iter, self.prob_flips_final)
+        self.flip_steps = self.total_steps - self.step_warm
+        self.prob_flips_final[id_layer] = flags
+        self.is_prob_flips = False
+        return self.prob_flips_final
+
+    def set_current_steps(self, step):
+        self.current_steps = step
+
+    def _is_competition_step(self, x, id_layer) -> bool:
+        """competesmoe.py:528 without the per-call device sync: flags are mirrored on the host per tensor version."""
+        if not x.requires_grad or self.step_warm is None or self.current_steps < self.step_warm:
+            return False
+        pf = self.prob_flips_final[id_layer]
+        key = (id(pf), pf._version, pf.data_ptr())
+        cached = self._flips_host.get(id_layer)
+        if cached is None or cached[0] != key:
+            cached = (key, pf.detach().to("cpu").ne(0).tolist())
+            self._flips_host[id_layer] = cached
+        return bool(cached[1][self.current_steps - self.step_warm])
+
+    def pre_train_forward(self):
+        super().pre_train_forward()
+        self.total_router_gate, self.total_router_affinity = [], []
+
+    def add_perplexity_reg(self):
+        self.pre_train_forward()
+
+    def before_loss(self):
+        self.add_perplexity_reg()
+        if self.training:
+            self.iter += 1
+
+    # ---- policies
+    def compute_gate(self, x2: torch.Tensor, cdt: torch.dtype):
+        """competesmoe.py:456-464: plain, cosine, or weight-normalised gate."""
+        a = self.args
+        if getattr(a, "is_cosine", False) and not getattr(a, "is_norm_weight", False):
+            return GateFn.apply(F.normalize(x2.float(), p=2.0, dim=-1).to(cdt), F.normalize(self.w_gate, p=2.0, dim=-1),
+                                self.num_selected)
+        if getattr(a, "is_norm_weight", False):
+            return GateFn.apply(x2.to(cdt), F.normalize(self.w_gate, p=2.0, dim=-1), self.num_selected)
+        return GateFn.apply(x2.to(cdt), self.w_gate, self.num_selected)
+
+    def router_policy(self, x2, cdt, x_dtype):
+        """competesmoe.py:465-490."""
+        a = self.args
+        assert not (getattr(a, "is_cosine", False) and getattr(a, "is_norm_weight", False)), \
+            "Can not active  both  Cosine and Norm Weigh. Just use one method - Cosine or Norm Weigh to Normalization"
+        logits, probs, gw, gidx = self.compute_gate(x2, cdt)
+        if getattr(a, "norm_sigmoid", False):
+            scale = float(getattr(a, "scale_weight", 1.0))
+            gw, gidx = TopkRenormFn.apply(logits.float() / scale, self.num_selected, True, x_dtype)
+        return gw, gidx, probs, logits
+
+    def router_loss(self, gate_softmax, affinity_softmax):
+        return F.mse_loss(gate_softmax, affinity_softmax)
+
+    def experts_diversity_loss(self, expert_outputs):
+        """competesmoe.py:330-372 on [T, K, D]."""
+        eo = expert_outputs.float()
+        K, D = eo.shape[-2:]
+        nrm = F.normalize(eo, p=2, dim=-1).reshape(-1, K, D)
+        sim = torch.bmm(nrm, nrm.transpose(1, 2)) * (1 - torch.eye(K, device=eo.device))
+        self.nb_diver += K * (K - 1) * nrm.shape[0]
+        return sim.mean()
+
+    def forward(self, x, return_id_experts=False, return_full=True, *args, **kwargs):
+        id_layer = kwargs["id_layer"]
+        assert id_layer is not None, "Layer Id must to not None"
+        a = self.args
+        lead = x.shape[:-1]
+        cdt = self._compute_dtype(x)
+        x2 = x.reshape(-1, x.shape[-1])
+        T, E, K = x2.shape[0], self.n_experts, self.num_selected
+        is_comp = self._is_competition_step(x, id_layer)
+        gate_w, gate_idx, gate_softmax, gate_logits = self.router_policy(x2, cdt, x.dtype)
+        if is_comp:
+            spec = self._spec(cdt)
+            y_all = DenseFFNFn.apply(x2.to(cdt), self.keys, self.bias, self.values, None, spec)   # [E * t_pad, Dv]
+            t_pad = y_all.shape[0] // E
+            aff = AffinityFn.apply(y_all, E, T, t_pad, x.dtype == torch.bfloat16)
+            aff_softmax = F.softmax(aff, dim=-1, dtype=torch.float32)
+            aff_w, aff_idx = TopkRenormFn.apply(aff, K, False, x.dtype)
+            li = aff_idx.long()
+            out = SelectCombineFn.apply(y_all, aff_w, aff_idx, t_pad, spec)
+            topk_out = GatherRowsFn.apply(y_all, aff_idx, t_pad)
+            diver = self.experts_diversity_loss(topk_out)
+            self.add_reg(lambda: diver * a.balance_loss_coef_comp / 2, self.name_moe + "_comp_diver_loss")
+            if a.balance_affinity:
+                bal = self.entropy_balance(aff_softmax.view(*lead, E))
+                self.add_reg(lambda: bal * a.balance_loss_coef_comp / 2, f"{self.name_moe}_comp_ebalance")
+            g_top = lambda idx: torch.gather(gate_softmax, -1, idx)          # noqa: E731
+            a_top = lambda idx: torch.gather(aff_softmax, -1, idx).detach()  # noqa: E731
+            if a.in_topk:
+                rl = self.router_loss(g_top(li), a_top(li))
+            elif a.hybrid:
+                rl = self.router_loss(gate_softmax, aff_softmax.detach()) + self.router_loss(g_top(li), a_top(li)) * a.router_theta
+            elif a.tribrid:
+                gi = gate_idx.long()
+                rl = self.router_loss(gate_softmax, aff_softmax.detach()) + \
+                    self.router_loss(g_top(li), a_top(li)) * a.router_theta + \
+                    self.router_loss(g_top(gi), a_top(gi)) * a.router_theta
+            else:
+                rl = self.router_loss(gate_softmax, aff_softmax.detach())
+            self.add_reg(lambda: rl * a.router_loss_coef, f"{self.name_moe}_router_loss")
+            self.last_routing = (aff_idx.view(*lead, K), aff_w.detach().view(*lead, K))
+        else:
+            out = self.compute_moe_main(x2, gate_idx, gate_w, cdt)
+            lg = gate_logits.view(*lead, E)
+            self.add_reg(lambda: self.entropy_balance(lg) * (a.balance_loss_coef / self.div), f"{self.name_moe}_ebalance")
+            self.last_routing = (gate_idx.view(*lead, K), gate_w.detach().view(*lead, K))
+        self.layer += 1
+        if a.test_only:
+            self.add_dist_experts(selection=gate_idx)
+            self.add_dist_weight(weight=gate_w)
+            self.add_dist_weight(weight=gate_softmax, is_all=True)
+        self.was_training = self.training
+        res = out.view(*lead, self.v_dim)
+        if self.o_bias is not None:
+            res = res + self.o_bias
+        return res

@@ -165,9 +165,11 @@ int csmoe_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream);
 /* ------------------------------------------------------------------------------------------------ competition
  * Neural-response score (moe_model/.../competesmoe.py:240-243; moe_pretrain_model/.../competesmoe.py:399-403):
  * aff[t, e] = mean_d softplus(y[e, t, d]) over dense expert outputs y[E, t_pad, D] (the grouped GEMM's dense layout).
- * Written as fp32 after rounding to `dtype` (the reference stores it in x.dtype). */
-int csmoe_affinity_fwd(const void* y, int32_t dtype, int32_t E, int64_t T, int64_t t_pad, int32_t D, float* aff,
-                       void* stream);
+ * round_dtype = CSMOE_BF16 reproduces eager bf16 arithmetic (each softplus and the mean rounded to bf16, as the
+ * multimodal reference computes it in x.dtype); CSMOE_F32 keeps fp32 (the pretrain reference under autocast, where
+ * softplus and mean run in fp32).  aff is always stored as fp32. */
+int csmoe_affinity_fwd(const void* y, int32_t dtype, int32_t E, int64_t T, int64_t t_pad, int32_t D,
+                       int32_t round_dtype, float* aff, void* stream);
 /* dy[e,t,d] (+)= daff[t,e] * sigmoid(y[e,t,d]) / D. accumulate: add into an existing dy. */
 int csmoe_affinity_bwd(const void* y, const float* daff, int32_t dtype, int32_t E, int64_t T, int64_t t_pad, int32_t D,
                        int32_t accumulate, void* dy, void* stream);

@@ -260,7 +260,7 @@ def test_affinity_fwd_bwd(ops, dtype):
     yr = y.float().requires_grad_(True)
     aff_ref = F.softplus(yr[:, :T]).mean(-1).t()        # [T, E]
     aff_ref.backward(daff)
-    aff = ops.affinity_fwd(y.view(E * t_pad, D).to(DEV), E, T, t_pad)
+    aff = ops.affinity_fwd(y.view(E * t_pad, D).to(DEV), E, T, t_pad, dtype == torch.bfloat16)
     tol = 2e-2 if dtype == torch.bfloat16 else 1e-4
     assert_close_rms(aff, aff_ref.detach(), tol, "affinity")
     dy = ops.affinity_bwd(y.view(E * t_pad, D).to(DEV), daff.to(DEV), E, T, t_pad)

@@ -1,0 +1,138 @@
+"""GPU parity of the pretrain drop-in layer and of the `cvmm` op against the golden vectors of the unmodified reference
+(fp32 fixtures; this path runs under bf16 autocast like the reference's training recipe, hence the 4e-2 tolerance) and
+against the CPU oracle evaluated with op_dtype=bf16 (2e-2)."""
+from types import SimpleNamespace
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import multimodal as om
+from oracle import pretrain as op
+
+from conftest import load_golden
+from helpers import assert_close_rms
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+PT = ["pt_router_f32", "pt_comp_f32", "pt_comp_hybrid_bal_f32", "pt_comp_intopk_f32", "pt_comp_tribrid_f32"]
+
+
+def build_layer(fx):
+    from competesmoe_b200.pretrain import CompeteSMoE
+    m = fx["meta"]
+    args = SimpleNamespace(**m["args"])
+    layer = CompeteSMoE(m["D"], m["E"], m["H"], n_heads=m["K"], args=args, activation=F.relu, selection_mode="gate",
+                        log_interval=None)
+    with torch.no_grad():
+        layer.w_gate.copy_(fx["w_gate"]); layer.keys.copy_(fx["keys"]); layer.values.copy_(fx["values"])
+    layer = layer.to(DEV)
+    layer.train()
+    layer.regularization_present = True
+    layer.step_warm = 0
+    layer.prob_flips_final = {0: torch.full((8,), bool(m["competition"]), device=DEV)}
+    layer.set_current_steps(1)
+    return layer, args
+
+
+@pytest.mark.parametrize("name", PT)
+def test_pretrain_layer_matches_reference_golden(name):
+    fx = load_golden(name)
+    m = fx["meta"]
+    layer, args = build_layer(fx)
+    assert set(layer.state_dict().keys()) == {"w_gate", "keys", "values"}
+    x = fx["x"].to(DEV).requires_grad_(True)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        out = layer(x, id_layer=0)
+        regs = layer.get_reg_loss()
+    assert out.dtype == torch.bfloat16 and out.shape == fx["out"].shape
+    assert set(regs) == set(fx["regs"])
+    ((out.float() * fx["dy"].to(DEV)).sum() + sum(regs.values())).backward()
+    # oracle with the same mixed precision, for the routing margins
+    _, o_regs, dbg = op.competesmoe_forward(fx["x"], fx["w_gate"], fx["keys"], fx["values"], m["K"], args,
+                                            m["competition"], op_dtype=torch.bfloat16)
+    sel, w = layer.last_routing
+    margin = om.topk_margin(dbg["affinity"] if m["competition"] else dbg["gate_softmax"], m["K"])
+    agree = (sel.cpu().long() == fx["selected"]).all(-1)
+    n_ex = int((~agree).sum())
+    # fp32 reference vs bf16 autocast: allow the bf16 resolution of the score (2^-8 relative) on top of the 1e-3 margin
+    assert bool((margin[~agree] < 1e-3 + 4e-3).all()), "routing differs on a token with a clear margin"
+    print(f"{name}: {n_ex}/{agree.numel()} low-margin tokens exempt")
+    assert_close_rms(out[agree.to(DEV)], fx["out"][agree], 4e-2, "output")
+    if n_ex == 0:
+        for k in regs:
+            got, ref = float(regs[k]), float(fx["regs"][k])
+            assert abs(got - ref) <= 4e-2 * abs(ref) + 2e-5, (k, got, ref)
+        assert_close_rms(x.grad, fx["dx"], 6e-2, "dx")
+        assert_close_rms(layer.keys.grad, fx["dkeys"], 6e-2, "dkeys")
+        assert_close_rms(layer.values.grad, fx["dvalues"], 6e-2, "dvalues")
+        assert_close_rms(layer.w_gate.grad, fx["dw_gate"], 6e-2, "dw_gate")
+    assert layer.keys.grad.dtype == torch.float32        # fp32 master parameters keep fp32 gradients
+
+
+def test_cvmm_op_both_call_patterns():
+    """compute_moe_main's two cvmm calls (competesmoe.py:510-522) through the public op, against the golden run of the
+    reference's own Triton kernels on the interpreter."""
+    from competesmoe_b200.cvmm import cvmm, cvmm_prepare_sel2
+    fx = load_golden("cvmm_triton_interp")
+    x = fx["x"].to(DEV).requires_grad_(True)
+    keys = fx["keys"].to(DEV).requires_grad_(True)
+    values = fx["values"].to(DEV).requires_grad_(True)
+    w = fx["w"].to(DEV).requires_grad_(True)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        s = cvmm_prepare_sel2(fx["sel"].to(DEV), n_experts=keys.shape[0])
+        scores = cvmm(x, s, keys)
+        assert scores.shape == fx["scores"].shape
+        s2 = s.clone()
+        s2.reduction_weight = w
+        s2.sel_index = s2.out_index
+        s2.out_index = None
+        out = cvmm(F.relu(scores), s2, values)
+    assert_close_rms(scores, fx["scores"], 4e-2, "scores")
+    assert_close_rms(out, fx["out"], 4e-2, "out")
+    (out.float() * fx["dy"].to(DEV)).sum().backward()
+    assert_close_rms(x.grad, fx["dx"], 6e-2, "dx")
+    assert_close_rms(keys.grad, fx["dkeys"], 6e-2, "dkeys")
+    assert_close_rms(values.grad, fx["dvalues"], 6e-2, "dvalues")
+    assert_close_rms(w.grad, fx["dw"], 6e-2, "dw")
+    # index maps: bit-exact against the (stable) reference maps
+    ref = op.prepare_sel2(fx["sel"])
+    assert torch.equal(s.sel.cpu(), ref.sel) and torch.equal(s.sel_index.cpu(), ref.sel_index)
+    assert torch.equal(s.out_index.cpu(), ref.out_index)
+
+
+@pytest.mark.parametrize("competition", [False, True])
+def test_c1_shape_against_oracle(competition):
+    """BASELINE configs[0] shape: d_model=512, 8 experts, top-2, expert size 128, batch 8 x seq 512 (bf16 autocast)."""
+    from competesmoe_b200.pretrain import CompeteSMoE
+    torch.manual_seed(0)
+    args = op.default_args(stop_after=8)
+    layer = CompeteSMoE(512, 8, 128, n_heads=2, args=args, activation=F.relu, selection_mode="gate", log_interval=None)
+    g = torch.Generator().manual_seed(1234)
+    x = torch.randn(8, 512, 512, generator=g)
+    dy = torch.randn(8, 512, 512, generator=g)
+    xr = x.clone().requires_grad_(True)
+    wg, ks, vs = (p.detach().clone().requires_grad_(True) for p in (layer.w_gate, layer.keys, layer.values))
+    o_out, o_regs, dbg = op.competesmoe_forward(xr, wg, ks, vs, 2, args, competition, op_dtype=torch.bfloat16)
+    ((o_out.float() * dy).sum() + sum(o_regs.values())).backward()
+    layer = layer.to(DEV)
+    layer.train()
+    layer.regularization_present = True
+    layer.step_warm = 0
+    layer.prob_flips_final = {0: torch.full((8,), competition, device=DEV)}
+    layer.set_current_steps(0)
+    xg = x.to(DEV).requires_grad_(True)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        out = layer(xg, id_layer=0)
+        regs = layer.get_reg_loss()
+    ((out.float() * dy.to(DEV)).sum() + sum(regs.values())).backward()
+    sel, _ = layer.last_routing
+    margin = om.topk_margin(dbg["affinity"] if competition else dbg["gate_softmax"], 2)
+    agree = (sel.cpu().long() == dbg["selected"]).all(-1)
+    assert bool((margin[~agree] < 1e-3).all()), "routing differs on a token with margin >= 1e-3"
+    print(f"C1 competition={competition}: {int((~agree).sum())}/{agree.numel()} low-margin tokens exempt")
+    assert_close_rms(out[agree.to(DEV)], o_out.detach()[agree], 2e-2, "output")
+    assert set(regs) == set(o_regs)
+    if int((~agree).sum()) <= agree.numel() // 200:
+        assert_close_rms(layer.keys.grad, ks.grad, 5e-2, "dkeys")
+        assert_close_rms(layer.values.grad, vs.grad, 5e-2, "dvalues")
