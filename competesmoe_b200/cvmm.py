@@ -70,7 +70,7 @@ def _complete(sel: CVMMSel, n_experts: int) -> CVMMSel:
 def _out_dtype(x: torch.Tensor) -> torch.dtype:
     """cvmm.py:29-32 get_dtype(): fp32 unless autocast is active."""
     if torch.is_autocast_enabled():
-        return torch.get_autocast_gpu_dtype()
+        return torch.get_autocast_dtype('cuda')
     return x.dtype if x.dtype in (torch.bfloat16,) else torch.float32
 
 

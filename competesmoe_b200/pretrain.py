@@ -210,7 +210,7 @@ class MoE(LoggingLayer, RegularizedLayer, OncePerIterLayer, torch.nn.Module):
     # ---- compute
     def _compute_dtype(self, x: torch.Tensor) -> torch.dtype:
         if torch.is_autocast_enabled():
-            return torch.get_autocast_gpu_dtype()
+            return torch.get_autocast_dtype('cuda')
         return x.dtype
 
     def _spec(self, cdt: torch.dtype) -> FFNSpec:

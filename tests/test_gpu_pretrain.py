@@ -48,25 +48,36 @@ def test_pretrain_layer_matches_reference_golden(name):
     assert out.dtype == torch.bfloat16 and out.shape == fx["out"].shape
     assert set(regs) == set(fx["regs"])
     ((out.float() * fx["dy"].to(DEV)).sum() + sum(regs.values())).backward()
-    # oracle with the same mixed precision, for the routing margins
-    _, o_regs, dbg = op.competesmoe_forward(fx["x"], fx["w_gate"], fx["keys"], fx["values"], m["K"], args,
-                                            m["competition"], op_dtype=torch.bfloat16)
+    # The oracle (pinned to the reference by these same fp32 fixtures, tests/test_oracle_golden.py) evaluated with the
+    # mixed precision this path uses: the apples-to-apples expectation for gradients.  The router gradient is ill
+    # conditioned on tokens whose two selected experts have nearly equal dw (differences of O(1) numbers), where fp32
+    # and bf16 legitimately differ by tens of percent -- the CPU bf16 oracle shows the same deviation from the fixture.
+    xr, wg, ks, vs = (fx[n].clone().requires_grad_(True) for n in ("x", "w_gate", "keys", "values"))
+    o_out, o_regs, dbg = op.competesmoe_forward(xr, wg, ks, vs, m["K"], args, m["competition"], op_dtype=torch.bfloat16)
+    ((o_out.float() * fx["dy"]).sum() + sum(o_regs.values())).backward()
     sel, w = layer.last_routing
     margin = om.topk_margin(dbg["affinity"] if m["competition"] else dbg["gate_softmax"], m["K"])
-    agree = (sel.cpu().long() == fx["selected"]).all(-1)
+    agree_ref = (sel.cpu().long() == fx["selected"]).all(-1)
+    agree = (sel.cpu().long() == dbg["selected"]).all(-1)
     n_ex = int((~agree).sum())
-    # fp32 reference vs bf16 autocast: allow the bf16 resolution of the score (2^-8 relative) on top of the 1e-3 margin
-    assert bool((margin[~agree] < 1e-3 + 4e-3).all()), "routing differs on a token with a clear margin"
-    print(f"{name}: {n_ex}/{agree.numel()} low-margin tokens exempt")
-    assert_close_rms(out[agree.to(DEV)], fx["out"][agree], 4e-2, "output")
+    assert bool((margin[~agree] < 1e-3).all()), "routing differs from the bf16 oracle on a token with margin >= 1e-3"
+    # vs the fp32 reference run: the bf16 resolution of the scores (2^-8 relative) adds to the 1e-3 margin
+    assert bool((margin[~agree_ref] < 1e-3 + 4e-3).all()), "routing differs from the reference on a clear-margin token"
+    print(f"{name}: {n_ex}/{agree.numel()} low-margin tokens exempt (vs reference fp32 run: {int((~agree_ref).sum())})")
+    both = agree & agree_ref
+    assert_close_rms(out[both.to(DEV)], fx["out"][both], 4e-2, "output vs reference (fp32)")
+    assert_close_rms(out[agree.to(DEV)], o_out.detach()[agree], 2e-2, "output vs oracle (bf16)")
     if n_ex == 0:
         for k in regs:
-            got, ref = float(regs[k]), float(fx["regs"][k])
-            assert abs(got - ref) <= 4e-2 * abs(ref) + 2e-5, (k, got, ref)
-        assert_close_rms(x.grad, fx["dx"], 6e-2, "dx")
-        assert_close_rms(layer.keys.grad, fx["dkeys"], 6e-2, "dkeys")
-        assert_close_rms(layer.values.grad, fx["dvalues"], 6e-2, "dvalues")
-        assert_close_rms(layer.w_gate.grad, fx["dw_gate"], 6e-2, "dw_gate")
+            got, ref = float(regs[k].detach()), float(o_regs[k].detach())
+            assert abs(got - ref) <= 3e-2 * abs(ref) + 2e-5, (k, got, ref)
+            assert abs(got - float(fx["regs"][k])) <= 6e-2 * abs(float(fx["regs"][k])) + 5e-5, (k, got)
+        assert_close_rms(x.grad, xr.grad, 3e-2, "dx")
+        assert_close_rms(layer.keys.grad, ks.grad, 3e-2, "dkeys")
+        assert_close_rms(layer.values.grad, vs.grad, 3e-2, "dvalues")
+        assert_close_rms(layer.w_gate.grad, wg.grad, 3e-2, "dw_gate")
+        assert_close_rms(layer.keys.grad, fx["dkeys"], 6e-2, "dkeys vs reference (fp32)")
+        assert_close_rms(layer.values.grad, fx["dvalues"], 6e-2, "dvalues vs reference (fp32)")
     assert layer.keys.grad.dtype == torch.float32        # fp32 master parameters keep fp32 gradients
 
 
