@@ -30,7 +30,8 @@ class GemmArgs(C.Structure):
         ("bias", vp), ("bias_dtype", i32), ("accumulate", i32),
         ("preact", vp), ("ldpre", i64),
         ("tile_expert", vp), ("pad_offsets", vp),
-        ("max_ctas", i32), ("reserved", i32),
+        ("max_ctas", i32), ("act_bwd", i32),
+        ("aux", vp), ("ldaux", i64),
     ]
 
 
@@ -43,6 +44,10 @@ _SIGNATURES = {
     "csmoe_route_workspace_bytes": (i64, [i64, i32]),
     "csmoe_route_build": (i32, [vp, i64, i32, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "csmoe_router_fwd": (i32, [vp, vp, i32, i64, i32, i32, i32, vp, vp, vp, vp, vp]),
+    "csmoe_router_aux_workspace_bytes": (i64, [i64, i64, i32]),
+    "csmoe_router_aux_fwd": (i32, [vp, i32, vp, vp, i64, i64, i32, i32, vp, vp, vp, vp, vp, vp]),
+    "csmoe_router_bwd_workspace_bytes": (i64, [i64, i32, i32]),
+    "csmoe_router_bwd": (i32, [vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i32, i32, i32, vp, vp, vp, i32, vp, vp]),
     "csmoe_topk_renorm": (i32, [vp, i64, i32, i32, i32, i32, vp, vp, vp]),
     "csmoe_gather_rows": (i32, [vp, i32, i64, i32, i32, vp, i64, vp, vp, vp]),
     "csmoe_combine_fwd": (i32, [vp, i32, i64, i32, i32, vp, vp, vp, i32, vp, vp]),

@@ -38,7 +38,11 @@ struct KParams {
   int c_fp32;
   int bias_fp32;
   int accumulate;
-  int glu_f;          // SILU_GLU: F (n == 2F); 0 otherwise
+  int glu_f;          // GLU epilogues: F (forward: n == 2F and tiles interleave gate|up; backward: n == F)
+  int epi;            // kEpiPlain / kEpiGluFwd / kEpiActBwd / kEpiGluBwd
+  int band;           // n-blocks per rasterisation band
+  const void* aux;    // backward epilogues: the saved pre-activation z
+  long long ldaux;
   const int* tile_expert;
   const int* pad_offsets;
   void* c;
@@ -50,6 +54,8 @@ struct KParams {
   long long total_tiles;
 };
 
+constexpr int kEpiPlain = 0, kEpiGluFwd = 1, kEpiActBwd = 2, kEpiGluBwd = 3;
+
 struct Tile {
   int e, mb, nb, a_row, b_row, nkb;
   bool valid;
@@ -59,8 +65,15 @@ template <int MODE>
 __device__ __forceinline__ Tile decode_tile(const KParams& p, long long t) {
   Tile ti;
   if (MODE == CSMOE_GEMM_ROWS) {
-    ti.mb = static_cast<int>(t % p.num_m_blocks);
-    ti.nb = static_cast<int>(t / p.num_m_blocks);
+    // Bands of `band` n-blocks, m-blocks swept inside a band, n fastest: the ~148 tiles in flight form a roughly
+    // square patch of the output, so both operands are re-used out of L2 while they are hot.
+    const long long band_tiles = static_cast<long long>(p.band) * p.num_m_blocks;
+    const int b = static_cast<int>(t / band_tiles);
+    const int r = static_cast<int>(t % band_tiles);
+    const int nb0 = b * p.band;
+    const int w = min(p.band, p.num_n_blocks - nb0);
+    ti.mb = r / w;
+    ti.nb = nb0 + r % w;
     if (p.dense) {
       ti.e = ti.mb / p.dense_mblocks;
       ti.a_row = (ti.mb % p.dense_mblocks) * kBM + ti.e * p.a_expert_rows;
@@ -75,8 +88,12 @@ __device__ __forceinline__ Tile decode_tile(const KParams& p, long long t) {
     const long long per_e = static_cast<long long>(p.num_m_blocks) * p.num_n_blocks;
     ti.e = static_cast<int>(t / per_e);
     const int r = static_cast<int>(t % per_e);
-    ti.mb = r / p.num_n_blocks;
-    ti.nb = r % p.num_n_blocks;
+    const int band_tiles = p.band * p.num_m_blocks;
+    const int b = r / band_tiles, rr = r % band_tiles;
+    const int nb0 = b * p.band;
+    const int w = min(p.band, p.num_n_blocks - nb0);
+    ti.mb = rr / w;
+    ti.nb = nb0 + rr % w;
     if (p.dense) {
       ti.a_row = ti.e * p.a_expert_rows;
       ti.b_row = ti.e * p.b_expert_rows;
@@ -189,7 +206,13 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           if (MODE == CSMOE_GEMM_ROWS) {
             ptx::tma_load_2d(sa, &tma_a, fb, kb * kBK, ti.a_row);
             if (!B_MN) {
-              ptx::tma_load_3d(sb, &tma_b, fb, kb * kBK, ti.nb * BN, ti.e);
+              if (BN == 256 && p.epi == kEpiGluFwd) {
+                // gate rows [nb*128, +128) then up rows [F + nb*128, +128): one output tile holds both halves
+                ptx::tma_load_3d(sb, &tma_b, fb, kb * kBK, ti.nb * 128, ti.e);
+                ptx::tma_load_3d(sb + 128 * kBK * 2, &tma_b, fb, kb * kBK, p.glu_f + ti.nb * 128, ti.e);
+              } else {
+                ptx::tma_load_3d(sb, &tma_b, fb, kb * kBK, ti.nb * BN, ti.e);
+              }
             } else {
 #pragma unroll
               for (int j = 0; j < BN / 64; ++j)
@@ -279,35 +302,110 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                                : static_cast<const void*>(reinterpret_cast<const __nv_bfloat16*>(p.bias) + boff);
       }
       const uint32_t t_row = tmem_base + acc * BN + (static_cast<uint32_t>(quad * 32) << 16);
+      if (p.epi == kEpiPlain) {
 #pragma unroll 1
-      for (int chunk = 0; chunk < BN / 32; ++chunk) {
-        uint32_t v[32];
-        if (has_acc) {
-          ptx::tmem_ld_32x32b_x32(t_row + chunk * 32, v);
-          ptx::tmem_ld_wait();
-        } else {
+        for (int chunk = 0; chunk < BN / 32; ++chunk) {
+          uint32_t v[32];
+          if (has_acc) {
+            ptx::tmem_ld_32x32b_x32(t_row + chunk * 32, v);
+            ptx::tmem_ld_wait();
+          } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = 0u;
+            for (int i = 0; i < 32; ++i) v[i] = 0u;
+          }
+          const int col0 = ti.nb * BN + chunk * 32;
+          if (row_ok && col0 < p.n) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const int col = col0 + g * 8;
+              if (col < p.n) {
+                float a8[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) a8[i] = __uint_as_float(v[g * 8 + i]);
+                if (p.c_fp32) {
+                  float* c_row = reinterpret_cast<float*>(p.c) + c_off + out_row * p.ldc;
+                  float* pre_row = p.preact ? reinterpret_cast<float*>(p.preact) + out_row * p.ldpre : nullptr;
+                  epilogue_store8<float>(p, a8, c_row, pre_row, bias_row, col);
+                } else {
+                  __nv_bfloat16* c_row = reinterpret_cast<__nv_bfloat16*>(p.c) + c_off + out_row * p.ldc;
+                  __nv_bfloat16* pre_row =
+                      p.preact ? reinterpret_cast<__nv_bfloat16*>(p.preact) + out_row * p.ldpre : nullptr;
+                  epilogue_store8<__nv_bfloat16>(p, a8, c_row, pre_row, bias_row, col);
+                }
+              }
+            }
+          }
         }
-        const int col0 = ti.nb * BN + chunk * 32;
-        if (row_ok && col0 < p.n) {
+      } else if (p.epi == kEpiGluFwd) {
+        // TMEM columns [0,128) hold the gate and [128,256) the up projection of output columns nb*128 .. +128.
+        // z = (gate | up) is stored for the backward pass, h = up * silu(gate) feeds the down projection
+        // (Phi3MLP; each intermediate rounded to bf16 like the eager reference).
+        if constexpr (BN == 256) {
+          __nv_bfloat16* h_row = reinterpret_cast<__nv_bfloat16*>(p.c) + out_row * p.ldc;
+          __nv_bfloat16* z_row = reinterpret_cast<__nv_bfloat16*>(p.preact) + out_row * p.ldpre;
+#pragma unroll 1
+          for (int chunk = 0; chunk < 4; ++chunk) {
+            uint32_t vg[32], vu[32];
+            ptx::tmem_ld_32x32b_x32(t_row + chunk * 32, vg);
+            ptx::tmem_ld_32x32b_x32(t_row + 128 + chunk * 32, vu);
+            ptx::tmem_ld_wait();
+            const int col0 = ti.nb * 128 + chunk * 32;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const int col = col0 + g * 8;
+              if (col < p.glu_f) {
+                float zg[8], zu[8], h[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  zg[i] = bf16_round(__uint_as_float(vg[g * 8 + i]));
+                  zu[i] = bf16_round(__uint_as_float(vu[g * 8 + i]));
+                  h[i] = zu[i] * bf16_round(act_apply(zg[i], CSMOE_ACT_SILU));
+                }
+                store8(z_row + col, zg);
+                store8(z_row + p.glu_f + col, zu);
+                store8(h_row + col, h);
+              }
+            }
+          }
+        }
+      } else {
+        // Backward epilogues: the accumulator is dh; multiply by the activation derivative at the saved z.
+        const __nv_bfloat16* z_row = reinterpret_cast<const __nv_bfloat16*>(p.aux) + out_row * p.ldaux;
+        __nv_bfloat16* c_row = reinterpret_cast<__nv_bfloat16*>(p.c) + c_off + out_row * p.ldc;
+        const bool glu = p.epi == kEpiGluBwd;
+#pragma unroll 1
+        for (int chunk = 0; chunk < BN / 32; ++chunk) {
+          const int col0 = ti.nb * BN + chunk * 32;
+          float z0[4][8], z1[4][8];
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             const int col = col0 + g * 8;
-            if (col < p.n) {
-              float a8[8];
+            if (row_ok && col < p.n) {
+              load8(z_row + col, z0[g]);
+              if (glu) load8(z_row + p.glu_f + col, z1[g]);
+            }
+          }
+          uint32_t v[32];
+          ptx::tmem_ld_32x32b_x32(t_row + chunk * 32, v);
+          ptx::tmem_ld_wait();
 #pragma unroll
-              for (int i = 0; i < 8; ++i) a8[i] = __uint_as_float(v[g * 8 + i]);
-              if (p.c_fp32) {
-                float* c_row = reinterpret_cast<float*>(p.c) + c_off + out_row * p.ldc;
-                float* pre_row = p.preact ? reinterpret_cast<float*>(p.preact) + out_row * p.ldpre : nullptr;
-                epilogue_store8<float>(p, a8, c_row, pre_row, bias_row, col);
-              } else {
-                __nv_bfloat16* c_row = reinterpret_cast<__nv_bfloat16*>(p.c) + c_off + out_row * p.ldc;
-                __nv_bfloat16* pre_row =
-                    p.preact ? reinterpret_cast<__nv_bfloat16*>(p.preact) + out_row * p.ldpre : nullptr;
-                epilogue_store8<__nv_bfloat16>(p, a8, c_row, pre_row, bias_row, col);
+          for (int g = 0; g < 4; ++g) {
+            const int col = col0 + g * 8;
+            if (row_ok && col < p.n) {
+              float d0[8], d1[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float dh = bf16_round(__uint_as_float(v[g * 8 + i]));
+                if (glu) {
+                  const float sg = bf16_round(act_apply(z0[g][i], CSMOE_ACT_SILU));
+                  d1[i] = dh * sg;                                                     // d up
+                  d0[i] = bf16_round(dh * z1[g][i]) * act_grad(z0[g][i], CSMOE_ACT_SILU);  // d gate
+                } else {
+                  d0[i] = dh * act_grad(z0[g][i], p.act);
+                }
               }
+              store8(c_row + col, d0);
+              if (glu) store8(c_row + p.glu_f + col, d1);
             }
           }
         }
@@ -402,7 +500,18 @@ extern "C" int csmoe_grouped_gemm(const csmoe_gemm_args* a, void* stream_) {
                    reinterpret_cast<uintptr_t>(a->c)) % 16 == 0,
                   "csmoe_grouped_gemm: a/b/c must be 16-byte aligned");
   CSMOE_CHECK_ARG(a->c_dtype == CSMOE_F32 || a->c_dtype == CSMOE_BF16, "csmoe_grouped_gemm: bad c_dtype");
-  CSMOE_CHECK_ARG(a->act != CSMOE_ACT_SILU_GLU, "csmoe_grouped_gemm: SILU_GLU is not fused here; use csmoe_act_fwd");
+  const bool glu_fwd = a->act == CSMOE_ACT_SILU_GLU;
+  const bool act_bwd = a->act_bwd != CSMOE_ACT_NONE;
+  if (glu_fwd) {
+    CSMOE_CHECK_ARG(a->mode == CSMOE_GEMM_ROWS && a->b_layout == 0 && a->preact && a->c_dtype == CSMOE_BF16 &&
+                        a->n % 2 == 0 && (a->n / 2) % 8 == 0 && a->bias == nullptr && !act_bwd,
+                    "csmoe_grouped_gemm: fused SILU_GLU needs ROWS mode, [2F,k] weights, bf16 C [m,F], preact [m,2F], no bias");
+  }
+  if (act_bwd) {
+    CSMOE_CHECK_ARG(a->mode == CSMOE_GEMM_ROWS && a->aux && a->c_dtype == CSMOE_BF16 && a->act == CSMOE_ACT_NONE &&
+                        a->bias == nullptr && a->preact == nullptr && a->ldaux % 8 == 0,
+                    "csmoe_grouped_gemm: act_bwd epilogue needs ROWS mode, bf16 C, aux = saved pre-activation, no bias/act");
+  }
   if (a->dense) {
     CSMOE_CHECK_ARG(a->dense_rows > 0 && a->dense_rows % kBM == 0, "csmoe_grouped_gemm: dense_rows must be a multiple of 128");
   } else if (a->mode == CSMOE_GEMM_ROWS) {
@@ -415,7 +524,9 @@ extern "C" int csmoe_grouped_gemm(const csmoe_gemm_args* a, void* stream_) {
 
   cudaStream_t stream = as_stream(stream_);
   const int E = a->num_experts;
-  const bool big_n = a->n > 128;
+  // n as seen by the tile grid: the fused GLU forward produces F output columns from 2F weight rows
+  const long long n_grid = glu_fwd ? a->n / 2 : a->n;
+  const bool big_n = glu_fwd || a->n > 128;
   const int BN = big_n ? 256 : 128;
 
   KParams kp{};
@@ -437,7 +548,21 @@ extern "C" int csmoe_grouped_gemm(const csmoe_gemm_args* a, void* stream_) {
   kp.ldc = a->ldc;
   kp.ldpre = a->ldpre;
   kp.c_expert_stride = a->c_expert_stride;
-  kp.num_n_blocks = static_cast<int>((a->n + BN - 1) / BN);
+  kp.num_n_blocks = glu_fwd ? static_cast<int>((n_grid + 127) / 128) : static_cast<int>((a->n + BN - 1) / BN);
+  kp.band = 8;
+  kp.aux = a->aux;
+  kp.ldaux = a->ldaux;
+  if (glu_fwd) {
+    kp.epi = kEpiGluFwd;
+    kp.glu_f = static_cast<int>(a->n / 2);
+    kp.act = CSMOE_ACT_NONE;
+  } else if (act_bwd) {
+    kp.epi = a->act_bwd == CSMOE_ACT_SILU_GLU ? kEpiGluBwd : kEpiActBwd;
+    kp.glu_f = static_cast<int>(a->n);
+    kp.act = a->act_bwd;
+  } else {
+    kp.epi = kEpiPlain;
+  }
 
   CUtensorMap ma, mb;
   int rc;
@@ -456,7 +581,7 @@ extern "C" int csmoe_grouped_gemm(const csmoe_gemm_args* a, void* stream_) {
       cuuint64_t dims[3] = {(cuuint64_t)a->k, (cuuint64_t)a->n, (cuuint64_t)E};
       cuuint64_t str[2] = {(cuuint64_t)a->ldb * 2, (cuuint64_t)a->b_expert_stride * 2};
       if (E == 1) str[1] = (cuuint64_t)a->ldb * 2 * a->n;
-      cuuint32_t box[3] = {kBK, (cuuint32_t)BN, 1};
+      cuuint32_t box[3] = {kBK, (cuuint32_t)(glu_fwd ? 128 : BN), 1};
       if ((rc = encode_bf16_map(&mb, a->b, 3, dims, str, box)) != CSMOE_OK) return rc;
     } else {
       cuuint64_t dims[3] = {(cuuint64_t)a->n, (cuuint64_t)a->k, (cuuint64_t)E};

@@ -171,6 +171,217 @@ topk_renorm_kernel(const float* __restrict__ scores, long long Tn, int E, int K,
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ aux losses
+// Balance loss (moe.py:90-110) and z-loss (moe.py:71-88) of the router step need, per batch element b and expert e,
+// S[b,e] = sum_n p[b,n,e] and C[b,e] = #{n : top-1(b,n) = e}, plus Z = sum_t logsumexp(logits_t)^2.
+// Stage 1: one CTA per (b, token chunk) writes partial sums; stage 2 (one CTA) adds them in a fixed order
+// (deterministic) and evaluates   balance = E^2 * mean_{b,e}(S/N * C/N),   z = Z / T.
+constexpr int kAuxChunk = 256;  // tokens per stage-1 CTA (8 warps x 32 tokens)
+
+template <typename T>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+router_aux_stage1(const T* __restrict__ logits, const float* __restrict__ probs, const int32_t* __restrict__ topk_idx,
+                  int N, int E, int K, int chunks_per_b, float* __restrict__ partial, float* __restrict__ lse_out) {
+  extern __shared__ float sh[];  // [8 warps][2E + 1]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x / chunks_per_b, c = blockIdx.x % chunks_per_b;
+  const int stride = 2 * E + 1;
+  float s0 = 0.f, s1 = 0.f, c0 = 0.f, c1 = 0.f, zz = 0.f;  // lane l: experts l and l+32
+  const int n0 = c * kAuxChunk + warp * 32;
+  for (int i = 0; i < 32; ++i) {
+    const int n = n0 + i;
+    if (n >= N) break;
+    const long long t = static_cast<long long>(b) * N + n;
+    const bool h0 = lane < E, h1 = lane + 32 < E;
+    const float l0 = h0 ? static_cast<float>(logits[t * E + lane]) : -INFINITY;
+    const float l1 = h1 ? static_cast<float>(logits[t * E + lane + 32]) : -INFINITY;
+    const float m = warp_max(fmaxf(l0, l1));
+    const float se = warp_sum((h0 ? expf(l0 - m) : 0.f) + (h1 ? expf(l1 - m) : 0.f));
+    const float lse = m + logf(se);
+    if (lane == 0 && lse_out) lse_out[t] = lse;
+    zz += lse * lse;
+    if (h0) s0 += probs[t * E + lane];
+    if (h1) s1 += probs[t * E + lane + 32];
+    const int top1 = topk_idx[t * K];
+    if (top1 == lane) c0 += 1.f;
+    if (top1 == lane + 32) c1 += 1.f;
+  }
+  float* mine = sh + warp * stride;
+  if (lane < E) { mine[lane] = s0; mine[E + lane] = c0; }
+  if (lane + 32 < E) { mine[lane + 32] = s1; mine[E + lane + 32] = c1; }
+  if (lane == 0) mine[2 * E] = zz;
+  __syncthreads();
+  for (int i = threadIdx.x; i < stride; i += blockDim.x) {
+    float a = 0.f;
+#pragma unroll
+    for (int w = 0; w < kWarpsPerBlock; ++w) a += sh[w * stride + i];
+    partial[static_cast<long long>(blockIdx.x) * stride + i] = a;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+router_aux_stage2(const float* __restrict__ partial, int B, int N, int E, int chunks_per_b, float* __restrict__ psum,
+                  float* __restrict__ cnt, float* __restrict__ losses) {
+  __shared__ float red[256];
+  const int stride = 2 * E + 1;
+  float bal = 0.f, zz = 0.f;
+  for (int i = threadIdx.x; i < B * E; i += blockDim.x) {
+    const int b = i / E, e = i % E;
+    float s = 0.f, c = 0.f;
+    for (int k = 0; k < chunks_per_b; ++k) {
+      const float* p = partial + static_cast<long long>(b * chunks_per_b + k) * stride;
+      s += p[e];
+      c += p[E + e];
+    }
+    psum[i] = s;
+    cnt[i] = c;
+    bal += (s / N) * (c / N);
+  }
+  for (int i = threadIdx.x; i < B * chunks_per_b; i += blockDim.x) zz += partial[static_cast<long long>(i) * stride + 2 * E];
+  red[threadIdx.x] = bal;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  const float bal_tot = red[0];
+  __syncthreads();
+  red[threadIdx.x] = zz;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    losses[0] = bal_tot / (static_cast<float>(B) * E) * static_cast<float>(E) * E;
+    losses[1] = red[0] / (static_cast<float>(B) * N);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ router backward
+// Stage A (one warp per token): total gradient w.r.t. the gate logits,
+//   dp  = dprobs_in + g_bal * E/(B N^2) * C[b,e] + scatter_k( (dtw_k - sum_j dtw_j w_j) / s )       s = sum_k p_{i_k}
+//   dl  = p * (dp - <dp, p>) + dlogits_in + g_z * (2 lse / T) * p
+// rounded to the activation dtype (the reference back-propagates through a bf16 nn.Linear), then dx[t,:] = dl . Wg.
+template <typename T>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+router_bwd_dx_kernel(const T* __restrict__ wg, const float* __restrict__ probs, const float* __restrict__ topk_w,
+                     const int32_t* __restrict__ topk_idx, const float* __restrict__ dtw, const float* __restrict__ dprobs_in,
+                     const float* __restrict__ dlogits_in, const float* __restrict__ lse, const float* __restrict__ cnt,
+                     const float* __restrict__ g_losses, long long Tn, int N, int B, int D, int E, int K,
+                     float* __restrict__ dl_out, T* __restrict__ dx) {
+  const int lane = threadIdx.x & 31;
+  const long long t = static_cast<long long>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (t >= Tn) return;
+  const bool h0 = lane < E, h1 = lane + 32 < E;
+  const float p0 = h0 ? probs[t * E + lane] : 0.f, p1 = h1 ? probs[t * E + lane + 32] : 0.f;
+  float d0 = (h0 && dprobs_in) ? dprobs_in[t * E + lane] : 0.f;
+  float d1 = (h1 && dprobs_in) ? dprobs_in[t * E + lane + 32] : 0.f;
+  if (g_losses != nullptr && cnt != nullptr) {
+    const int b = static_cast<int>(t / N);
+    const float coef = g_losses[0] * static_cast<float>(E) / (static_cast<float>(B) * N * N);
+    if (h0) d0 += coef * cnt[b * E + lane];
+    if (h1) d1 += coef * cnt[b * E + lane + 32];
+  }
+  if (dtw != nullptr) {
+    float s = 0.f, dot = 0.f;
+    for (int k = 0; k < K; ++k) {
+      const int i = topk_idx[t * K + k];
+      s += probs[t * E + i];
+      dot += dtw[t * K + k] * topk_w[t * K + k];
+    }
+    for (int k = 0; k < K; ++k) {
+      const int i = topk_idx[t * K + k];
+      const float g = (dtw[t * K + k] - dot) / s;
+      if (i == lane) d0 += g;
+      if (i == lane + 32) d1 += g;
+    }
+  }
+  const float inner = warp_sum(d0 * p0 + d1 * p1);
+  float l0 = p0 * (d0 - inner), l1 = p1 * (d1 - inner);
+  if (dlogits_in != nullptr) {
+    if (h0) l0 += dlogits_in[t * E + lane];
+    if (h1) l1 += dlogits_in[t * E + lane + 32];
+  }
+  if (g_losses != nullptr && lse != nullptr) {
+    const float gz = g_losses[1] * 2.f * lse[t] / static_cast<float>(Tn);
+    l0 += gz * p0;
+    l1 += gz * p1;
+  }
+  l0 = round_as(l0, static_cast<const T*>(nullptr));
+  l1 = round_as(l1, static_cast<const T*>(nullptr));
+  if (h0) dl_out[t * E + lane] = l0;
+  if (h1) dl_out[t * E + lane + 32] = l1;
+  if (dx == nullptr) return;
+  for (int d = lane * 8; d < D; d += 256) {
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int e = 0; e < E; ++e) {
+      const float g = __shfl_sync(0xffffffffu, e < 32 ? l0 : l1, e & 31);
+      float wv[8];
+      load8(wg + static_cast<long long>(e) * D + d, wv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaf(g, wv[j], acc[j]);
+    }
+    store8(dx + t * D + d, acc);
+  }
+}
+
+// Stage B: partial dWg[e, :] = sum_{t in chunk} dl[t,e] * x[t,:]  (8 experts per pass), stage C adds the chunks in order.
+constexpr int kDwChunk = 256;
+constexpr int kDwExperts = 8;
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+router_bwd_dw_stage1(const T* __restrict__ x, const float* __restrict__ dl, long long Tn, int D, int E,
+                     float* __restrict__ partial) {
+  __shared__ float sdl[kDwChunk][kDwExperts];
+  const int e0 = blockIdx.z * kDwExperts;
+  const long long t0 = static_cast<long long>(blockIdx.y) * kDwChunk;
+  const int col = (blockIdx.x * 256 + threadIdx.x) * 8;
+  const int nt = static_cast<int>(min(static_cast<long long>(kDwChunk), Tn - t0));
+  for (int i = threadIdx.x; i < kDwChunk * kDwExperts; i += 256) {
+    const int tt = i / kDwExperts, ee = i % kDwExperts;
+    sdl[tt][ee] = (tt < nt && e0 + ee < E) ? dl[(t0 + tt) * E + e0 + ee] : 0.f;
+  }
+  __syncthreads();
+  if (col >= D) return;
+  float acc[kDwExperts][8];
+#pragma unroll
+  for (int e = 0; e < kDwExperts; ++e)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[e][j] = 0.f;
+  for (int tt = 0; tt < nt; ++tt) {
+    float xv[8];
+    load8(x + (t0 + tt) * D + col, xv);
+#pragma unroll
+    for (int e = 0; e < kDwExperts; ++e) {
+      const float g = sdl[tt][e];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[e][j] = fmaf(g, xv[j], acc[e][j]);
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < kDwExperts; ++e) {
+    if (e0 + e < E) store8(partial + (static_cast<long long>(blockIdx.y) * E + e0 + e) * D + col, acc[e]);
+  }
+}
+
+template <typename WT>
+__global__ void __launch_bounds__(256)
+router_bwd_dw_stage2(const float* __restrict__ partial, int n_chunks, long long ED, WT* __restrict__ dwg) {
+  const long long i = (static_cast<long long>(blockIdx.x) * 256 + threadIdx.x) * 8;
+  if (i >= ED) return;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int c = 0; c < n_chunks; ++c) {
+    float v[8];
+    load8(partial + c * ED + i, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += v[j];
+  }
+  store8(dwg + i, acc);
+}
+
 }  // namespace
 }  // namespace csmoe
 
@@ -211,5 +422,93 @@ extern "C" int csmoe_topk_renorm(const float* scores, int64_t T, int32_t E, int3
   topk_renorm_kernel<<<grid, kWarpsPerBlock * 32, 0, as_stream(stream_)>>>(scores, T, E, K, mode, round_dtype, topk_w,
                                                                            topk_idx);
   CSMOE_CHECK_LAUNCH();
+  return CSMOE_OK;
+}
+
+extern "C" int64_t csmoe_router_aux_workspace_bytes(int64_t B, int64_t N, int32_t E) {
+  if (B <= 0 || N <= 0 || E <= 0) return -1;
+  const int64_t chunks = (N + kAuxChunk - 1) / kAuxChunk;
+  return B * chunks * (2 * E + 1) * static_cast<int64_t>(sizeof(float));
+}
+
+extern "C" int csmoe_router_aux_fwd(const void* logits, int32_t dtype, const float* probs, const int32_t* topk_idx,
+                                    int64_t B, int64_t N, int32_t E, int32_t K, float* psum, float* cnt, float* lse,
+                                    float* losses, void* workspace, void* stream_) {
+  CSMOE_CHECK_ARG(logits && probs && topk_idx && psum && cnt && losses && workspace, "csmoe_router_aux_fwd: NULL pointer");
+  CSMOE_CHECK_ARG(E >= 1 && E <= kMaxE && K >= 1 && B >= 1 && N >= 1, "csmoe_router_aux_fwd: bad sizes");
+  cudaStream_t stream = as_stream(stream_);
+  const int chunks = static_cast<int>((N + kAuxChunk - 1) / kAuxChunk);
+  const unsigned grid = static_cast<unsigned>(B * chunks);
+  const size_t smem = kWarpsPerBlock * (2 * E + 1) * sizeof(float);
+  float* partial = static_cast<float*>(workspace);
+  if (dtype == CSMOE_BF16) {
+    router_aux_stage1<__nv_bfloat16><<<grid, kWarpsPerBlock * 32, smem, stream>>>(
+        static_cast<const __nv_bfloat16*>(logits), probs, topk_idx, static_cast<int>(N), E, K, chunks, partial, lse);
+  } else if (dtype == CSMOE_F32) {
+    router_aux_stage1<float><<<grid, kWarpsPerBlock * 32, smem, stream>>>(static_cast<const float*>(logits), probs,
+                                                                          topk_idx, static_cast<int>(N), E, K, chunks,
+                                                                          partial, lse);
+  } else {
+    CSMOE_CHECK_ARG(false, "csmoe_router_aux_fwd: unsupported dtype %d", dtype);
+  }
+  CSMOE_CHECK_LAUNCH();
+  router_aux_stage2<<<1, 256, 0, stream>>>(partial, static_cast<int>(B), static_cast<int>(N), E, chunks, psum, cnt, losses);
+  CSMOE_CHECK_LAUNCH();
+  return CSMOE_OK;
+}
+
+extern "C" int64_t csmoe_router_bwd_workspace_bytes(int64_t T, int32_t D, int32_t E) {
+  if (T < 0 || D <= 0 || E <= 0) return -1;
+  const int64_t chunks = (T + kDwChunk - 1) / kDwChunk;
+  return (chunks > 0 ? chunks : 1) * static_cast<int64_t>(E) * D * static_cast<int64_t>(sizeof(float));
+}
+
+extern "C" int csmoe_router_bwd(const void* x, const void* wg, int32_t x_dtype, const float* probs, const float* topk_w,
+                                const int32_t* topk_idx, const float* dtw, const float* dprobs, const float* dlogits,
+                                const float* lse, const float* cnt, const float* g_losses, int64_t B, int64_t N, int32_t D,
+                                int32_t E, int32_t K, float* dl, void* dx, void* dwg, int32_t wg_dtype, void* workspace,
+                                void* stream_) {
+  CSMOE_CHECK_ARG(x && wg && probs && topk_w && topk_idx && dl, "csmoe_router_bwd: NULL pointer");
+  CSMOE_CHECK_ARG(E >= 1 && E <= kMaxE && K >= 1 && K <= kMaxK && D > 0 && D % 8 == 0 && B >= 1 && N >= 1,
+                  "csmoe_router_bwd: bad sizes");
+  CSMOE_CHECK_ARG(dwg == nullptr || workspace != nullptr, "csmoe_router_bwd: dwg needs a workspace");
+  cudaStream_t stream = as_stream(stream_);
+  const long long T = B * N;
+  const unsigned grid = static_cast<unsigned>((T + kWarpsPerBlock - 1) / kWarpsPerBlock);
+  const int chunks = static_cast<int>((T + kDwChunk - 1) / kDwChunk);
+  dim3 g1((D / 8 + 255) / 256, chunks, (E + kDwExperts - 1) / kDwExperts);
+  const long long ED = static_cast<long long>(E) * D;
+  const unsigned g2 = static_cast<unsigned>((ED / 8 + 255) / 256);
+  float* partial = static_cast<float*>(workspace);
+  if (x_dtype == CSMOE_BF16) {
+    using T_ = __nv_bfloat16;
+    router_bwd_dx_kernel<T_><<<grid, kWarpsPerBlock * 32, 0, stream>>>(
+        static_cast<const T_*>(wg), probs, topk_w, topk_idx, dtw, dprobs, dlogits, lse, cnt, g_losses, T,
+        static_cast<int>(N), static_cast<int>(B), D, E, K, dl, static_cast<T_*>(dx));
+    CSMOE_CHECK_LAUNCH();
+    if (dwg != nullptr) {
+      router_bwd_dw_stage1<T_><<<g1, 256, 0, stream>>>(static_cast<const T_*>(x), dl, T, D, E, partial);
+      CSMOE_CHECK_LAUNCH();
+      if (wg_dtype == CSMOE_BF16)
+        router_bwd_dw_stage2<__nv_bfloat16><<<g2, 256, 0, stream>>>(partial, chunks, ED, static_cast<__nv_bfloat16*>(dwg));
+      else
+        router_bwd_dw_stage2<float><<<g2, 256, 0, stream>>>(partial, chunks, ED, static_cast<float*>(dwg));
+      CSMOE_CHECK_LAUNCH();
+    }
+  } else if (x_dtype == CSMOE_F32) {
+    router_bwd_dx_kernel<float><<<grid, kWarpsPerBlock * 32, 0, stream>>>(
+        static_cast<const float*>(wg), probs, topk_w, topk_idx, dtw, dprobs, dlogits, lse, cnt, g_losses, T,
+        static_cast<int>(N), static_cast<int>(B), D, E, K, dl, static_cast<float*>(dx));
+    CSMOE_CHECK_LAUNCH();
+    if (dwg != nullptr) {
+      router_bwd_dw_stage1<float><<<g1, 256, 0, stream>>>(static_cast<const float*>(x), dl, T, D, E, partial);
+      CSMOE_CHECK_LAUNCH();
+      CSMOE_CHECK_ARG(wg_dtype == CSMOE_F32, "csmoe_router_bwd: fp32 activations need fp32 gate weights");
+      router_bwd_dw_stage2<float><<<g2, 256, 0, stream>>>(partial, chunks, ED, static_cast<float*>(dwg));
+      CSMOE_CHECK_LAUNCH();
+    }
+  } else {
+    CSMOE_CHECK_ARG(false, "csmoe_router_bwd: unsupported dtype %d", x_dtype);
+  }
   return CSMOE_OK;
 }

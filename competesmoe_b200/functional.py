@@ -50,6 +50,9 @@ def _pad_rows(x: torch.Tensor, rows: int) -> torch.Tensor:
 
 def _ffn_first(xp, w1, b1, spec: FFNSpec, **where):
     """z (pre-activation, with bias) and h = act(z) for the first projection."""
+    if spec.glu and not spec.kn_layout and b1 is None:
+        h, z = ops.gemm_rows(xp, w1, w_is_kn=False, act=ops.ACT_SILU_GLU, **where)   # GLU fused in the epilogue
+        return z, h
     if spec.glu:
         z = ops.gemm_rows(xp, w1, w_is_kn=spec.kn_layout, bias=b1, **where)
         return z, ops.act_fwd(z, spec.act)
@@ -62,33 +65,35 @@ def _ffn_first(xp, w1, b1, spec: FFNSpec, **where):
 
 # ------------------------------------------------------------------------------------------------ router
 class GateFn(Function):
-    """(x [T,D], wg [E,D]) -> logits [T,E] (x dtype), probs [T,E] f32, topk_w [T,K] f32, topk_idx [T,K] i32."""
+    """(x [T,D], wg [E,D]) -> logits [T,E] (x dtype), probs [T,E] f32, topk_w [T,K] f32, topk_idx [T,K] i32,
+    losses [2] f32 = (balance loss, z-loss) of the router step (zeros unless want_aux).
+
+    Forward: csmoe_router_fwd (+ csmoe_router_aux_fwd).  Backward: one fused csmoe_router_bwd call folds the routing
+    weight gradient, any incoming d probs / d logits and the two aux-loss gradients into d logits, then dx and dWg."""
 
     @staticmethod
-    def forward(ctx, x, wg, top_k: int):
-        logits, probs, tw, ti = ops.router_fwd(x, wg.to(x.dtype), top_k)
-        ctx.save_for_backward(x, wg, probs, tw, ti)
+    def forward(ctx, x, wg, top_k: int, batch: int, want_aux: bool):
+        wgx = wg if wg.dtype == x.dtype else wg.to(x.dtype)
+        logits, probs, tw, ti = ops.router_fwd(x, wgx, top_k)
+        cnt = lse = None
+        if want_aux:
+            losses, cnt, lse = ops.router_aux_fwd(logits, probs, ti, batch)
+        else:
+            losses = torch.zeros(2, dtype=torch.float32, device=x.device)
+        ctx.save_for_backward(x, wgx, probs, tw, ti, cnt, lse)
+        ctx.batch, ctx.wg_dtype, ctx.want_aux = batch, wg.dtype, want_aux
         ctx.mark_non_differentiable(ti)
-        return logits, probs, tw, ti
+        return logits, probs, tw, ti, losses
 
     @staticmethod
     @once_differentiable
-    def backward(ctx, dlogits, dprobs, dtw, _):
-        x, wg, probs, tw, ti = ctx.saved_tensors
-        idx = ti.long()
-        dp = torch.zeros_like(probs) if dprobs is None else dprobs.float().clone()
-        if dtw is not None:
-            # w_k = p_k / s, s = sum_j p_j over the selected experts
-            s = torch.gather(probs, 1, idx).sum(-1, keepdim=True)
-            dsel = (dtw - (dtw * tw).sum(-1, keepdim=True)) / s
-            dp.scatter_add_(1, idx, dsel)
-        dl = probs * (dp - (dp * probs).sum(-1, keepdim=True))
-        if dlogits is not None:
-            dl = dl + dlogits.float()
-        dl = dl.to(x.dtype)
-        dx = dl @ wg.to(x.dtype) if ctx.needs_input_grad[0] else None
-        dwg = (dl.t() @ x).to(wg.dtype) if ctx.needs_input_grad[1] else None
-        return dx, dwg, None
+    def backward(ctx, dlogits, dprobs, dtw, _, dlosses):
+        x, wgx, probs, tw, ti, cnt, lse = ctx.saved_tensors
+        dx, dwg = ops.router_bwd(x, wgx, probs, tw, ti, ctx.batch, dtw=dtw, dprobs=dprobs, dlogits=dlogits,
+                                 lse=lse if ctx.want_aux else None, cnt=cnt if ctx.want_aux else None,
+                                 g_losses=dlosses if ctx.want_aux else None, need_dx=ctx.needs_input_grad[0],
+                                 need_dwg=ctx.needs_input_grad[1], wg_dtype=ctx.wg_dtype)
+        return dx, dwg, None, None, None
 
 
 # ------------------------------------------------------------------------------------------------ sparse experts
@@ -129,8 +134,8 @@ class SparseFFNFn(Function):
             dw2 = ops.gemm_reduce(h, dyp, E, route=route, out_dtype=w2.dtype)  # [E, H, Dout]
         else:
             dw2 = ops.gemm_reduce(dyp, h, E, route=route, out_dtype=w2.dtype)  # [E, Dout, F]
-        dh = ops.gemm_rows(dyp, w2b, w_is_kn=not spec.kn_layout, route=route)
-        dz = dh if spec.act == ops.ACT_NONE else ops.act_bwd(z, dh, spec.act)
+        # dgrad of the second projection with the activation backward fused into its epilogue: dz = (dy W2) * act'(z)
+        dz = ops.gemm_rows(dyp, w2b, w_is_kn=not spec.kn_layout, route=route, act_bwd=spec.act, aux=z)
         db1 = ops.bias_grad(dz, E, route=route, out_dtype=w1.dtype) if ctx.has_b[0] else None
         if spec.kn_layout:
             dw1 = ops.gemm_reduce(xp, dz, E, route=route, out_dtype=w1.dtype)  # [E, D, H]
@@ -173,8 +178,8 @@ class DenseFFNFn(Function):
             dw2 = ops.gemm_reduce(h, dy, E, dense_rows=t_pad, a_expert_rows=t_pad, b_expert_rows=t_pad, out_dtype=w2.dtype)
         else:
             dw2 = ops.gemm_reduce(dy, h, E, dense_rows=t_pad, a_expert_rows=t_pad, b_expert_rows=t_pad, out_dtype=w2.dtype)
-        dh = ops.gemm_rows(dy, w2b, w_is_kn=not spec.kn_layout, dense_rows=t_pad, a_expert_rows=t_pad)
-        dz = dh if spec.act == ops.ACT_NONE else ops.act_bwd(z, dh, spec.act)
+        dz = ops.gemm_rows(dy, w2b, w_is_kn=not spec.kn_layout, dense_rows=t_pad, a_expert_rows=t_pad,
+                           act_bwd=spec.act, aux=z)
         db1 = ops.bias_grad(dz, E, dense_rows=t_pad, out_dtype=w1.dtype) if ctx.has_b[0] else None
         if spec.kn_layout:
             dw1 = ops.gemm_reduce(xb, dz, E, dense_rows=t_pad, a_expert_rows=0, b_expert_rows=t_pad, out_dtype=w1.dtype)

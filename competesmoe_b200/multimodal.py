@@ -159,9 +159,10 @@ class MoeLayer(nn.Module):
         B, N, D = x.shape
         x2 = x.reshape(B * N, D)
         lay, w1, b1, w2, b2 = self._stacked_weights()
-        logits, probs, gw, gidx = GateFn.apply(x2, self.gate.weight, self.num_selected)
+        logits, probs, gw, gidx, losses = GateFn.apply(x2, self.gate.weight, self.num_selected, B, True)
         out = SparseFFNFn.apply(x2, gw, gidx, w1, b1, w2, b2, self._spec(lay)).view(B, N, self.out_embed_dim)
-        aux, balance_loss, router_z_loss = self.combine_loss(gidx.view(B, N, -1), probs.view(B, N, -1), logits.view(B, N, -1))
+        balance_loss, router_z_loss = losses[0], losses[1]
+        aux = balance_loss * self.args.balance_loss_coef + router_z_loss * self.args.router_z_loss_coef
         infor_aux = {"balance_loss": balance_loss.detach().clone(), "router_z_loss": router_z_loss.detach().clone()}
         if return_id_experts:
             return out, aux, probs.view(B, N, -1)
@@ -219,8 +220,8 @@ class CompeteSMoE(MoeLayer):
         return bool(self._flips_host[self.current_steps - self.step_warm])
 
     # ---- policies
-    def router_policy(self, x2):
-        return GateFn.apply(x2, self.gate.weight, self.num_selected)
+    def router_policy(self, x2, batch, want_aux):
+        return GateFn.apply(x2, self.gate.weight, self.num_selected, batch, want_aux)
 
     def router_loss(self, gate_softmax, affinity_softmax):
         return F.mse_loss(gate_softmax, affinity_softmax)
@@ -231,10 +232,12 @@ class CompeteSMoE(MoeLayer):
         x2 = x.reshape(T, D)
         lay, w1, b1, w2, b2 = self._stacked_weights()
         spec = self._spec(lay)
-        gate_logits, gate_softmax, gate_w, gate_idx = self.router_policy(x2)
-        auxiliary_loss = torch.tensor(0.0, device=x.device, dtype=x.dtype)
+        compete = self._is_competition_step(x)
+        want_aux = (not compete) and (x.requires_grad or return_id_experts)
+        gate_logits, gate_softmax, gate_w, gate_idx, gate_losses = self.router_policy(x2, B, want_aux)
+        auxiliary_loss = x.new_zeros(())
         infor_aux = {}
-        if self._is_competition_step(x):
+        if compete:
             y_all = DenseFFNFn.apply(x2, w1, b1, w2, b2, spec)                       # [E * t_pad, Dout]
             t_pad = y_all.shape[0] // E
             aff = AffinityFn.apply(y_all, E, T, t_pad, x.dtype == torch.bfloat16)                             # [T, E] f32 (x.dtype-rounded)
@@ -258,8 +261,9 @@ class CompeteSMoE(MoeLayer):
         else:
             out = SparseFFNFn.apply(x2, gate_w, gate_idx, w1, b1, w2, b2, spec)
             self.last_routing = (gate_idx.view(B, N, K), gate_w.detach().view(B, N, K))
-            if x.requires_grad or return_id_experts:
-                auxiliary_loss, balance_loss, router_z_loss = self.combine_loss(
-                    gate_idx.view(B, N, K), gate_softmax.view(B, N, E), gate_logits.view(B, N, E))
+            if want_aux:
+                # balance + z losses come out of one fused reduction kernel (moe.py:214-226 combine_loss)
+                balance_loss, router_z_loss = gate_losses[0], gate_losses[1]
+                auxiliary_loss = balance_loss * self.args.balance_loss_coef + router_z_loss * self.args.router_z_loss_coef
                 infor_aux = {"balance_loss": balance_loss.detach().clone(), "router_z_loss": router_z_loss.detach().clone()}
         return out.view(B, N, self.out_embed_dim).to(x.dtype), auxiliary_loss, None, infor_aux

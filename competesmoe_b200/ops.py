@@ -122,6 +122,50 @@ def router_fwd(x: torch.Tensor, wg: torch.Tensor, top_k: int):
     return logits, probs, tw, ti
 
 
+def router_aux_fwd(logits: torch.Tensor, probs: torch.Tensor, topk_idx: torch.Tensor, batch: int):
+    """Balance + z losses of the router step in one pass.  Returns (losses [2] f32 = (balance, z), cnt [B,E], lse [T])."""
+    _cuda(logits, probs, topk_idx)
+    T, E = probs.shape
+    K = topk_idx.shape[1]
+    assert T % batch == 0
+    N = T // batch
+    dev = probs.device
+    lib = _lib.load()
+    ws = torch.empty(int(lib.csmoe_router_aux_workspace_bytes(batch, N, E)) // 4, dtype=torch.float32, device=dev)
+    psum = torch.empty(batch, E, dtype=torch.float32, device=dev)
+    cnt = torch.empty(batch, E, dtype=torch.float32, device=dev)
+    lse = torch.empty(T, dtype=torch.float32, device=dev)
+    losses = torch.empty(2, dtype=torch.float32, device=dev)
+    _call("csmoe_router_aux_fwd", _p(logits), _dt(logits), _p(probs), _p(topk_idx), batch, N, E, K, _p(psum), _p(cnt),
+          _p(lse), _p(losses), _p(ws), _stream(), kernels=2)
+    return losses, cnt, lse
+
+
+def router_bwd(x: torch.Tensor, wg: torch.Tensor, probs: torch.Tensor, topk_w: torch.Tensor, topk_idx: torch.Tensor,
+               batch: int, *, dtw=None, dprobs=None, dlogits=None, lse=None, cnt=None, g_losses=None,
+               need_dx: bool = True, need_dwg: bool = True, wg_dtype: Optional[torch.dtype] = None):
+    """Fused router backward -> (dx [T,D] x.dtype or None, dwg [E,D] or None)."""
+    _cuda(x, wg, probs, topk_w, topk_idx, dtw, dprobs, dlogits, lse, cnt, g_losses)
+    T, D = x.shape
+    E = wg.shape[0]
+    K = topk_idx.shape[1]
+    N = T // batch
+    dev = x.device
+    f32 = lambda t: None if t is None else t.contiguous().float()  # noqa: E731
+    dtw, dprobs, dlogits, g_losses = f32(dtw), f32(dprobs), f32(dlogits), f32(g_losses)
+    wg_dtype = wg_dtype or wg.dtype
+    dl = torch.empty(T, E, dtype=torch.float32, device=dev)
+    dx = torch.empty(T, D, dtype=x.dtype, device=dev) if need_dx else None
+    dwg = torch.empty(E, D, dtype=wg_dtype, device=dev) if need_dwg else None
+    ws = None
+    if need_dwg:
+        ws = torch.empty(int(_lib.load().csmoe_router_bwd_workspace_bytes(T, D, E)) // 4, dtype=torch.float32, device=dev)
+    _call("csmoe_router_bwd", _p(x), _p(wg), _dt(x), _p(probs), _p(topk_w), _p(topk_idx), _p(dtw), _p(dprobs),
+          _p(dlogits), _p(lse), _p(cnt), _p(g_losses), batch, N, D, E, K, _p(dl), _p(dx), _p(dwg),
+          _dt(dwg) if dwg is not None else F32, _p(ws), _stream(), kernels=3 if need_dwg else 1)
+    return dx, dwg
+
+
 def topk_renorm(scores: torch.Tensor, top_k: int, sigmoid: bool = False, round_dtype: torch.dtype = torch.float32,
                 round_out: bool = False):
     """scores [T, E] f32 -> (w [T,K] f32, idx [T,K] i32); w = topk / round(sum topk)."""
@@ -204,15 +248,19 @@ def _gemm(args: GemmArgs, flops: float = 0.0, tag: str = "") -> None:
 
 def gemm_rows(a: torch.Tensor, w: torch.Tensor, *, w_is_kn: bool, route: Optional[Route] = None,
               dense_rows: int = 0, a_expert_rows: int = 0, bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
-              want_preact: bool = False, out_dtype: Optional[torch.dtype] = None):
-    """C[row] = A[row] . W[expert(row)] (+bias, activation).
+              want_preact: bool = False, out_dtype: Optional[torch.dtype] = None, act_bwd: int = ACT_NONE,
+              aux: Optional[torch.Tensor] = None):
+    """C[row] = A[row] . W[expert(row)] with a fused epilogue.
 
     a: [rows, k] bf16.  w: [E, n, k] (w_is_kn=False, nn.Linear layout) or [E, k, n] (w_is_kn=True).
     route given: rows are the padded expert-major space.  dense_rows > 0: every expert processes `dense_rows` rows of
     `a` (shared when a_expert_rows == 0) and C is [E * dense_rows, n].
+    Forward epilogue: + bias, activation; want_preact also returns the pre-activation.  act = ACT_SILU_GLU: w is
+    [E, 2F, k]; returns (h [rows, F], z [rows, 2F]).
+    Backward epilogue (act_bwd, aux = saved z): C = (A . W) * act'(z); ACT_SILU_GLU returns dz [rows, 2F] from dh [rows, F].
     Returns C, or (C, preact) when want_preact.
     """
-    _cuda(a, w, bias)
+    _cuda(a, w, bias, aux)
     assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16, "grouped GEMM operands must be bfloat16"
     assert a.dim() == 2 and w.dim() == 3 and a.stride(1) == 1 and w.stride(2) == 1
     E = w.shape[0]
@@ -220,6 +268,8 @@ def gemm_rows(a: torch.Tensor, w: torch.Tensor, *, w_is_kn: bool, route: Optiona
     n = w.shape[2] if w_is_kn else w.shape[1]
     assert (w.shape[1] if w_is_kn else w.shape[2]) == k, f"contraction mismatch: a {tuple(a.shape)} w {tuple(w.shape)}"
     out_dtype = out_dtype or a.dtype
+    glu_fwd = act == ACT_SILU_GLU
+    glu_bwd = act_bwd == ACT_SILU_GLU
     g = GemmArgs()
     g.mode, g.b_layout, g.num_experts = GEMM_ROWS, 1 if w_is_kn else 0, E
     if dense_rows:
@@ -233,20 +283,25 @@ def gemm_rows(a: torch.Tensor, w: torch.Tensor, *, w_is_kn: bool, route: Optiona
     g.m, g.n, g.k = m, n, k
     g.a, g.lda = _p(a), a.stride(0)
     g.b, g.ldb, g.b_expert_stride = _p(w), w.stride(1), w.stride(0)
-    c = torch.empty(m, n, dtype=out_dtype, device=a.device)
-    g.c, g.ldc, g.c_dtype = _p(c), n, _dt(c)
+    c_cols = n // 2 if glu_fwd else (2 * n if glu_bwd else n)
+    c = torch.empty(m, c_cols, dtype=out_dtype, device=a.device)
+    g.c, g.ldc, g.c_dtype = _p(c), c_cols, _dt(c)
     g.act = act
     pre = None
-    if want_preact:
+    if want_preact or glu_fwd:
         pre = torch.empty(m, n, dtype=out_dtype, device=a.device)
         g.preact, g.ldpre = _p(pre), n
     if bias is not None:
         bias = bias.contiguous()
         assert bias.shape == (E, n)
         g.bias, g.bias_dtype = _p(bias), _dt(bias)
+    if act_bwd != ACT_NONE:
+        assert aux is not None and aux.dtype == torch.bfloat16 and aux.stride(1) == 1 and aux.shape[0] == m
+        assert aux.shape[1] == (2 * n if glu_bwd else n)
+        g.act_bwd, g.aux, g.ldaux = act_bwd, _p(aux), aux.stride(0)
     algo_rows = E * dense_rows if dense_rows else route.n_slots
     _gemm(g, 2.0 * algo_rows * n * k, "rows_kn" if w_is_kn else "rows_nk")
-    return (c, pre) if want_preact else c
+    return (c, pre) if (want_preact or glu_fwd) else c
 
 
 def gemm_reduce(a: torch.Tensor, b: torch.Tensor, num_experts: int, *, route: Optional[Route] = None,

@@ -219,7 +219,7 @@ class MoE(LoggingLayer, RegularizedLayer, OncePerIterLayer, torch.nn.Module):
         return FFNSpec(act=self._act_code, kn_layout=True, round_each=False, round_w=cdt == torch.bfloat16)
 
     def compute_gate(self, x2: torch.Tensor, cdt: torch.dtype):
-        return GateFn.apply(x2.to(cdt), self.w_gate, self.num_selected)
+        return GateFn.apply(x2.to(cdt), self.w_gate, self.num_selected, 1, False)[:4]
 
     def _log_relu_pass_rate(self, out):
         pass  # the hidden activations never leave the fused kernels; the reference logs this only every log_interval
@@ -320,10 +320,10 @@ class CompeteSMoE(MoE):
         a = self.args
         if getattr(a, "is_cosine", False) and not getattr(a, "is_norm_weight", False):
             return GateFn.apply(F.normalize(x2.float(), p=2.0, dim=-1).to(cdt), F.normalize(self.w_gate, p=2.0, dim=-1),
-                                self.num_selected)
+                                self.num_selected, 1, False)[:4]
         if getattr(a, "is_norm_weight", False):
-            return GateFn.apply(x2.to(cdt), F.normalize(self.w_gate, p=2.0, dim=-1), self.num_selected)
-        return GateFn.apply(x2.to(cdt), self.w_gate, self.num_selected)
+            return GateFn.apply(x2.to(cdt), F.normalize(self.w_gate, p=2.0, dim=-1), self.num_selected, 1, False)[:4]
+        return GateFn.apply(x2.to(cdt), self.w_gate, self.num_selected, 1, False)[:4]
 
     def router_policy(self, x2, cdt, x_dtype):
         """competesmoe.py:465-490."""

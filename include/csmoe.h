@@ -79,6 +79,27 @@ int csmoe_router_fwd(const void* x, const void* wg, int32_t x_dtype, int64_t T, 
 int csmoe_topk_renorm(const float* scores, int64_t T, int32_t E, int32_t K, int32_t mode, int32_t round_dtype,
                       float* topk_w, int32_t* topk_idx, void* stream);
 
+/* Router-step auxiliary losses in one pass (moe_model/model/moe/moe.py:71-110,214-226):
+ *   losses[0] = balance = E^2 * mean_{b,e}( mean_n probs[b,n,e] * mean_n [top-1(b,n) == e] )
+ *   losses[1] = z-loss  = mean_t logsumexp(logits_t)^2
+ * Also returns psum[B,E] = sum_n probs, cnt[B,E] = top-1 counts and lse[T] (may be NULL) for the backward pass.
+ * Two-stage, fixed-order reduction (deterministic).  workspace: csmoe_router_aux_workspace_bytes(B, N, E). */
+int64_t csmoe_router_aux_workspace_bytes(int64_t B, int64_t N, int32_t E);
+int csmoe_router_aux_fwd(const void* logits, int32_t dtype, const float* probs, const int32_t* topk_idx, int64_t B,
+                         int64_t N, int32_t E, int32_t K, float* psum, float* cnt, float* lse, float* losses,
+                         void* workspace, void* stream);
+
+/* Router backward, fused: gradient w.r.t. the gate logits from (optional, NULL = absent) the routing-weight gradient
+ * dtw[T,K], an incoming dprobs[T,E] (e.g. router-distillation MSE), an incoming dlogits[T,E], and the balance / z
+ * losses (g_losses[2] = d loss / d balance, d loss / d z on the device; cnt and lse from csmoe_router_aux_fwd);
+ * then dx[T,D] = dl . Wg (may be NULL) and dWg[E,D] = dl^T . x (may be NULL; deterministic two-stage reduction).
+ * dl[T,E] (fp32 storage, values rounded to x_dtype) is an output.  workspace: csmoe_router_bwd_workspace_bytes. */
+int64_t csmoe_router_bwd_workspace_bytes(int64_t T, int32_t D, int32_t E);
+int csmoe_router_bwd(const void* x, const void* wg, int32_t x_dtype, const float* probs, const float* topk_w,
+                     const int32_t* topk_idx, const float* dtw, const float* dprobs, const float* dlogits,
+                     const float* lse, const float* cnt, const float* g_losses, int64_t B, int64_t N, int32_t D, int32_t E,
+                     int32_t K, float* dl, void* dx, void* dwg, int32_t wg_dtype, void* workspace, void* stream);
+
 /* ------------------------------------------------------------------------------------------------ permutation
  * Gather rows of src[T, D] into the padded expert-major space: dst[row] = scale(row) * src[row_to_slot[row] / K],
  * zero for padding rows.  scale = slot_w[slot] when slot_w != NULL (combine backward), else 1.
@@ -113,7 +134,11 @@ int csmoe_scatter_reduce(const void* g, int32_t dtype, int64_t T, int32_t D, int
  *               ROWS: A row tile = tile % (dense_rows/128) (+ e*a_expert_rows), C row = e*dense_rows + ...;
  *               REDUCE: A rows of e start at e*a_expert_rows, B rows at e*b_expert_rows (0 = shared operand).
  * Epilogue    : + bias[e][n] (optional), activation (optional, ROWS only); when preact != NULL the pre-activation value
- *               is also stored (same layout/dtype as C; for SILU_GLU preact is [m, 2F] and C is [m, F] with n = 2F).
+ *               is also stored (same layout/dtype as C).  act = SILU_GLU (ROWS, b_layout 0): B[e] is [2F, k] (gate rows
+ *               then up rows), n = 2F, preact is [m, 2F], C = up * silu(gate) is [m, F]; each output tile computes 128
+ *               gate and the matching 128 up columns so the product never leaves the epilogue.
+ *               act_bwd != NONE (ROWS): C = acc * act'(aux) with aux the saved pre-activation (fused activation
+ *               backward of the dgrad GEMM); act_bwd = SILU_GLU: acc is dh [m, n = F], aux is [m, 2F], C is [m, 2F].
  * All leading dimensions are in elements and must make rows 16-byte aligned; n % 8 == 0. */
 typedef enum csmoe_gemm_mode { CSMOE_GEMM_ROWS = 0, CSMOE_GEMM_REDUCE = 1 } csmoe_gemm_mode;
 
@@ -143,7 +168,9 @@ typedef struct csmoe_gemm_args {
   const int32_t* tile_expert; /* ROWS, !dense: [m / 128] */
   const int32_t* pad_offsets; /* REDUCE, !dense: [num_experts + 1] */
   int32_t max_ctas;        /* 0 = one per SM */
-  int32_t reserved;
+  int32_t act_bwd;         /* ROWS: C = acc * act'(aux) (dgrad through the activation; SILU_GLU: C is [m, 2n]) */
+  const void* aux;         /* saved pre-activation z for act_bwd: [m, n] (SILU_GLU: [m, 2n]), bf16 */
+  int64_t ldaux;
 } csmoe_gemm_args;
 
 int csmoe_grouped_gemm(const csmoe_gemm_args* args, void* stream);
