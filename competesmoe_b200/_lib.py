@@ -32,6 +32,7 @@ class GemmArgs(C.Structure):
         ("tile_expert", vp), ("pad_offsets", vp),
         ("max_ctas", i32), ("act_bwd", i32),
         ("aux", vp), ("ldaux", i64),
+        ("row_tile", i32), ("reserved", i32),
     ]
 
 
@@ -40,9 +41,9 @@ _SIGNATURES = {
     "csmoe_abi_version": (i32, []),
     "csmoe_last_error": (C.c_char_p, []),
     "csmoe_device_supported": (i32, []),
-    "csmoe_route_row_cap": (i64, [i64, i32]),
+    "csmoe_route_row_cap": (i64, [i64, i32, i32]),
     "csmoe_route_workspace_bytes": (i64, [i64, i32]),
-    "csmoe_route_build": (i32, [vp, i64, i32, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "csmoe_route_build": (i32, [vp, i64, i32, i32, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "csmoe_router_fwd": (i32, [vp, vp, i32, i64, i32, i32, i32, vp, vp, vp, vp, vp]),
     "csmoe_router_aux_workspace_bytes": (i64, [i64, i64, i32]),
     "csmoe_router_aux_fwd": (i32, [vp, i32, vp, vp, i64, i64, i32, i32, vp, vp, vp, vp, vp, vp]),

@@ -328,19 +328,19 @@ router_bwd_dx_kernel(const T* __restrict__ wg, const float* __restrict__ probs, 
 }
 
 // Stage B: partial dWg[e, :] = sum_{t in chunk} dl[t,e] * x[t,:]  (8 experts per pass), stage C adds the chunks in order.
-constexpr int kDwChunk = 256;
+constexpr int kDwChunk = 32;   // tokens per stage-1 CTA: T/32 x D/1024 CTAs keep the SMs busy even for E = 4
 constexpr int kDwExperts = 8;
 
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 router_bwd_dw_stage1(const T* __restrict__ x, const float* __restrict__ dl, long long Tn, int D, int E,
                      float* __restrict__ partial) {
   __shared__ float sdl[kDwChunk][kDwExperts];
   const int e0 = blockIdx.z * kDwExperts;
   const long long t0 = static_cast<long long>(blockIdx.y) * kDwChunk;
-  const int col = (blockIdx.x * 256 + threadIdx.x) * 8;
+  const int col = (blockIdx.x * 128 + threadIdx.x) * 8;
   const int nt = static_cast<int>(min(static_cast<long long>(kDwChunk), Tn - t0));
-  for (int i = threadIdx.x; i < kDwChunk * kDwExperts; i += 256) {
+  for (int i = threadIdx.x; i < kDwChunk * kDwExperts; i += 128) {
     const int tt = i / kDwExperts, ee = i % kDwExperts;
     sdl[tt][ee] = (tt < nt && e0 + ee < E) ? dl[(t0 + tt) * E + e0 + ee] : 0.f;
   }
@@ -476,7 +476,7 @@ extern "C" int csmoe_router_bwd(const void* x, const void* wg, int32_t x_dtype, 
   const long long T = B * N;
   const unsigned grid = static_cast<unsigned>((T + kWarpsPerBlock - 1) / kWarpsPerBlock);
   const int chunks = static_cast<int>((T + kDwChunk - 1) / kDwChunk);
-  dim3 g1((D / 8 + 255) / 256, chunks, (E + kDwExperts - 1) / kDwExperts);
+  dim3 g1((D / 8 + 127) / 128, chunks, (E + kDwExperts - 1) / kDwExperts);
   const long long ED = static_cast<long long>(E) * D;
   const unsigned g2 = static_cast<unsigned>((ED / 8 + 255) / 256);
   float* partial = static_cast<float*>(workspace);
@@ -487,7 +487,7 @@ extern "C" int csmoe_router_bwd(const void* x, const void* wg, int32_t x_dtype, 
         static_cast<int>(N), static_cast<int>(B), D, E, K, dl, static_cast<T_*>(dx));
     CSMOE_CHECK_LAUNCH();
     if (dwg != nullptr) {
-      router_bwd_dw_stage1<T_><<<g1, 256, 0, stream>>>(static_cast<const T_*>(x), dl, T, D, E, partial);
+      router_bwd_dw_stage1<T_><<<g1, 128, 0, stream>>>(static_cast<const T_*>(x), dl, T, D, E, partial);
       CSMOE_CHECK_LAUNCH();
       if (wg_dtype == CSMOE_BF16)
         router_bwd_dw_stage2<__nv_bfloat16><<<g2, 256, 0, stream>>>(partial, chunks, ED, static_cast<__nv_bfloat16*>(dwg));
@@ -501,7 +501,7 @@ extern "C" int csmoe_router_bwd(const void* x, const void* wg, int32_t x_dtype, 
         static_cast<int>(N), static_cast<int>(B), D, E, K, dl, static_cast<float*>(dx));
     CSMOE_CHECK_LAUNCH();
     if (dwg != nullptr) {
-      router_bwd_dw_stage1<float><<<g1, 256, 0, stream>>>(static_cast<const float*>(x), dl, T, D, E, partial);
+      router_bwd_dw_stage1<float><<<g1, 128, 0, stream>>>(static_cast<const float*>(x), dl, T, D, E, partial);
       CSMOE_CHECK_LAUNCH();
       CSMOE_CHECK_ARG(wg_dtype == CSMOE_F32, "csmoe_router_bwd: fp32 activations need fp32 gate weights");
       router_bwd_dw_stage2<float><<<g2, 256, 0, stream>>>(partial, chunks, ED, static_cast<float*>(dwg));

@@ -63,7 +63,7 @@ route_hist_kernel(const int32_t* __restrict__ sel, long long n_slots, int E, int
 // Phase B (one CTA): per-expert totals, exclusive scans over experts (plain and padded) and, per expert, the running
 // base of every chunk.  chunk_counts[c][e] is overwritten with the exclusive prefix over chunks.
 __global__ void __launch_bounds__(1024)
-route_scan_kernel(int32_t* __restrict__ chunk_counts, int n_chunks, int E, int32_t* __restrict__ counts,
+route_scan_kernel(int32_t* __restrict__ chunk_counts, int n_chunks, int E, int row_tile, int32_t* __restrict__ counts,
                   int32_t* __restrict__ offsets, int32_t* __restrict__ pad_offsets, int32_t* __restrict__ tile_expert) {
   __shared__ int32_t s_cnt[kMaxExperts];
   __shared__ int32_t s_off[kMaxExperts + 1];
@@ -86,7 +86,7 @@ route_scan_kernel(int32_t* __restrict__ chunk_counts, int n_chunks, int E, int32
       s_off[e] = o;
       s_pad[e] = po;
       o += s_cnt[e];
-      po += (s_cnt[e] + CSMOE_ROW_TILE - 1) / CSMOE_ROW_TILE * CSMOE_ROW_TILE;
+      po += (s_cnt[e] + row_tile - 1) / row_tile * row_tile;
     }
     s_off[E] = o;
     s_pad[E] = po;
@@ -163,10 +163,10 @@ route_scatter_kernel(const int32_t* __restrict__ sel, long long n_slots, int E, 
 
 using namespace csmoe;
 
-extern "C" int64_t csmoe_route_row_cap(int64_t n_slots, int32_t num_experts) {
-  if (n_slots < 0 || num_experts <= 0) return -1;
-  const int64_t worst = n_slots + static_cast<int64_t>(num_experts) * (CSMOE_ROW_TILE - 1);
-  return (worst + CSMOE_ROW_TILE - 1) / CSMOE_ROW_TILE * CSMOE_ROW_TILE;
+extern "C" int64_t csmoe_route_row_cap(int64_t n_slots, int32_t num_experts, int32_t row_tile) {
+  if (n_slots < 0 || num_experts <= 0 || (row_tile != 128 && row_tile != 256)) return -1;
+  const int64_t worst = n_slots + static_cast<int64_t>(num_experts) * (row_tile - 1);
+  return (worst + row_tile - 1) / row_tile * row_tile;
 }
 
 extern "C" int64_t csmoe_route_workspace_bytes(int64_t n_slots, int32_t num_experts) {
@@ -175,7 +175,7 @@ extern "C" int64_t csmoe_route_workspace_bytes(int64_t n_slots, int32_t num_expe
   return (n_chunks > 0 ? n_chunks : 1) * num_experts * static_cast<int64_t>(sizeof(int32_t));
 }
 
-extern "C" int csmoe_route_build(const int32_t* sel, int64_t n_slots, int32_t num_experts, int64_t row_cap,
+extern "C" int csmoe_route_build(const int32_t* sel, int64_t n_slots, int32_t num_experts, int32_t row_tile, int64_t row_cap,
                                  int32_t* counts, int32_t* offsets, int32_t* pad_offsets, int32_t* sorted_sel,
                                  int64_t* sort_index, int32_t* slot_to_row, int32_t* row_to_slot, int32_t* tile_expert,
                                  void* workspace, void* stream_) {
@@ -184,9 +184,10 @@ extern "C" int csmoe_route_build(const int32_t* sel, int64_t n_slots, int32_t nu
   CSMOE_CHECK_ARG(n_slots >= 0 && n_slots < (1ll << 31), "csmoe_route_build: n_slots out of range");
   CSMOE_CHECK_ARG(counts && offsets && pad_offsets && workspace, "csmoe_route_build: counts/offsets/pad_offsets/workspace are required");
   CSMOE_CHECK_ARG(n_slots == 0 || sel != nullptr, "csmoe_route_build: sel is NULL");
-  CSMOE_CHECK_ARG(row_cap % CSMOE_ROW_TILE == 0 && row_cap >= csmoe_route_row_cap(n_slots, num_experts),
+  CSMOE_CHECK_ARG(row_tile == 128 || row_tile == 256, "csmoe_route_build: row_tile must be 128 or 256");
+  CSMOE_CHECK_ARG(row_cap % row_tile == 0 && row_cap >= csmoe_route_row_cap(n_slots, num_experts, row_tile),
                   "csmoe_route_build: row_cap %lld too small (need %lld)", (long long)row_cap,
-                  (long long)csmoe_route_row_cap(n_slots, num_experts));
+                  (long long)csmoe_route_row_cap(n_slots, num_experts, row_tile));
   cudaStream_t stream = as_stream(stream_);
   const int n_chunks = static_cast<int>((n_slots + kChunk - 1) / kChunk);
   int32_t* chunk_counts = reinterpret_cast<int32_t*>(workspace);
@@ -195,7 +196,8 @@ extern "C" int csmoe_route_build(const int32_t* sel, int64_t n_slots, int32_t nu
   route_hist_kernel<<<grid, kThreads, smem, stream>>>(sel, n_slots, num_experts, chunk_counts, row_to_slot, row_cap,
                                                       tile_expert);
   CSMOE_CHECK_LAUNCH();
-  route_scan_kernel<<<1, 1024, 0, stream>>>(chunk_counts, grid, num_experts, counts, offsets, pad_offsets, tile_expert);
+  route_scan_kernel<<<1, 1024, 0, stream>>>(chunk_counts, grid, num_experts, row_tile, counts, offsets, pad_offsets,
+                                            tile_expert);
   CSMOE_CHECK_LAUNCH();
   if (n_chunks > 0) {
     route_scatter_kernel<<<n_chunks, kThreads, smem, stream>>>(sel, n_slots, num_experts, chunk_counts, offsets,

@@ -155,7 +155,7 @@ class DenseFFNFn(Function):
     @staticmethod
     def forward(ctx, x, w1, b1, w2, b2, spec: FFNSpec):
         T = x.shape[0]
-        t_pad = (T + ROW_TILE - 1) // ROW_TILE * ROW_TILE
+        t_pad = (T + 2 * ROW_TILE - 1) // (2 * ROW_TILE) * (2 * ROW_TILE)   # 256: CTA-pair GEMM tiles
         xb = _pad_rows(_bf16(x), t_pad)
         w1b, w2b = _bf16(w1), _bf16(w2)
         z, h = _ffn_first(xb, w1b, b1, spec, dense_rows=t_pad, a_expert_rows=0)

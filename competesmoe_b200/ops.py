@@ -71,13 +71,19 @@ class Route:
     slot_to_row: torch.Tensor  # [n_slots] int32
     row_to_slot: torch.Tensor  # [row_cap] int32, -1 on padding rows
     tile_expert: torch.Tensor  # [row_cap / ROW_TILE] int32, -1 past the end
+    row_tile: int = ROW_TILE   # alignment of the expert segments (256 lets the CTA-pair GEMM run)
 
 
-def route_row_cap(n_slots: int, num_experts: int) -> int:
-    return int(_lib.load().csmoe_route_row_cap(n_slots, num_experts))
+def route_row_cap(n_slots: int, num_experts: int, row_tile: int = ROW_TILE) -> int:
+    return int(_lib.load().csmoe_route_row_cap(n_slots, num_experts, row_tile))
 
 
-def route_build(sel: torch.Tensor, num_experts: int) -> Route:
+def default_row_tile(n_slots: int, num_experts: int) -> int:
+    """256-row expert segments (CTA-pair GEMM tiles) unless the padding would cost more than ~6% extra rows."""
+    return 256 if num_experts * 128 * 16 <= max(n_slots, 1) else ROW_TILE
+
+
+def route_build(sel: torch.Tensor, num_experts: int, row_tile: Optional[int] = None) -> Route:
     """sel: [T, K] (or flat) integer expert ids on CUDA."""
     _cuda(sel)
     top_k = sel.shape[-1] if sel.dim() > 1 else 1
@@ -88,7 +94,9 @@ def route_build(sel: torch.Tensor, num_experts: int) -> Route:
     n = flat.numel()
     dev = flat.device
     lib = _lib.load()
-    row_cap = int(lib.csmoe_route_row_cap(n, num_experts))
+    if row_tile is None:
+        row_tile = default_row_tile(n, num_experts)
+    row_cap = int(lib.csmoe_route_row_cap(n, num_experts, row_tile))
     ws = torch.empty(max(int(lib.csmoe_route_workspace_bytes(n, num_experts)) // 4, 1), dtype=torch.int32, device=dev)
     i32 = dict(dtype=torch.int32, device=dev)
     counts = torch.empty(num_experts, **i32)
@@ -99,11 +107,11 @@ def route_build(sel: torch.Tensor, num_experts: int) -> Route:
     slot_to_row = torch.empty(n, **i32)
     row_to_slot = torch.empty(row_cap, **i32)
     tile_expert = torch.empty(row_cap // ROW_TILE, **i32)
-    _call("csmoe_route_build", _p(flat), n, num_experts, row_cap, _p(counts), _p(offsets), _p(pad_offsets),
+    _call("csmoe_route_build", _p(flat), n, num_experts, row_tile, row_cap, _p(counts), _p(offsets), _p(pad_offsets),
           _p(sorted_sel), _p(sort_index), _p(slot_to_row), _p(row_to_slot), _p(tile_expert), _p(ws), _stream(),
           kernels=3 if n > 0 else 2)
     return Route(num_experts, top_k, n, row_cap, flat, counts, offsets, pad_offsets, sorted_sel, sort_index,
-                 slot_to_row, row_to_slot, tile_expert)
+                 slot_to_row, row_to_slot, tile_expert, row_tile)
 
 
 # ----------------------------------------------------------------------------------------------- router
@@ -280,6 +288,7 @@ def gemm_rows(a: torch.Tensor, w: torch.Tensor, *, w_is_kn: bool, route: Optiona
         assert route is not None and a.shape[0] == route.row_cap
         m = route.row_cap
         g.tile_expert = _p(route.tile_expert)
+        g.row_tile = route.row_tile
     g.m, g.n, g.k = m, n, k
     g.a, g.lda = _p(a), a.stride(0)
     g.b, g.ldb, g.b_expert_stride = _p(w), w.stride(1), w.stride(0)

@@ -53,15 +53,15 @@ int csmoe_device_supported(void);
  *
  * In : sel[T*K] int32 expert id of slot j = t*K + k.
  * Out: counts[E], offsets[E+1] (exclusive scan of counts = the reference's sorted segment boundaries),
- *      pad_offsets[E+1] (segment starts rounded up to CSMOE_ROW_TILE),
+ *      pad_offsets[E+1] (segment starts rounded up to row_tile = 128 or 256; 256 enables the CTA-pair GEMM),
  *      sorted_sel[T*K], sort_index[T*K] (stable argsort of sel: the reference's ssel / out_index; in_index = /K),
  *      slot_to_row[T*K] (row of slot j in the padded expert-major space), row_to_slot[row_cap] (-1 for padding rows),
  *      tile_expert[row_cap/CSMOE_ROW_TILE] (expert owning each row tile, -1 past the end).
- * row_cap must be >= csmoe_route_row_cap(T*K, E).  Any output pointer except counts/offsets/pad_offsets may be NULL.
+ * row_cap must be >= csmoe_route_row_cap(T*K, E, row_tile).  Any output pointer except counts/offsets/pad_offsets may be NULL.
  * workspace: csmoe_route_workspace_bytes(T*K, E) bytes. */
-int64_t csmoe_route_row_cap(int64_t n_slots, int32_t num_experts);
+int64_t csmoe_route_row_cap(int64_t n_slots, int32_t num_experts, int32_t row_tile);
 int64_t csmoe_route_workspace_bytes(int64_t n_slots, int32_t num_experts);
-int csmoe_route_build(const int32_t* sel, int64_t n_slots, int32_t num_experts, int64_t row_cap, int32_t* counts,
+int csmoe_route_build(const int32_t* sel, int64_t n_slots, int32_t num_experts, int32_t row_tile, int64_t row_cap, int32_t* counts,
                       int32_t* offsets, int32_t* pad_offsets, int32_t* sorted_sel, int64_t* sort_index,
                       int32_t* slot_to_row, int32_t* row_to_slot, int32_t* tile_expert, void* workspace, void* stream);
 
@@ -171,6 +171,9 @@ typedef struct csmoe_gemm_args {
   int32_t act_bwd;         /* ROWS: C = acc * act'(aux) (dgrad through the activation; SILU_GLU: C is [m, 2n]) */
   const void* aux;         /* saved pre-activation z for act_bwd: [m, n] (SILU_GLU: [m, 2n]), bf16 */
   int64_t ldaux;
+  int32_t row_tile;        /* ROWS, !dense: the row_tile the routing maps were built with (128 or 256); 256 lets the
+                              CTA-pair (cta_group::2, 256 x 256 tile) kernel run */
+  int32_t reserved;
 } csmoe_gemm_args;
 
 int csmoe_grouped_gemm(const csmoe_gemm_args* args, void* stream);

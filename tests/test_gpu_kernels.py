@@ -19,15 +19,16 @@ def ops():
 
 
 # ------------------------------------------------------------------------------------------------ routing metadata
+@pytest.mark.parametrize("row_tile", [128, 256])
 @pytest.mark.parametrize("T,K,E", [(1, 1, 1), (7, 2, 4), (4096, 2, 4), (4096, 2, 8), (3000, 8, 64), (65536, 8, 64),
                                    (513, 3, 1000)])
-def test_route_build_bit_exact(ops, T, K, E):
+def test_route_build_bit_exact(ops, T, K, E, row_tile):
     g = torch.Generator().manual_seed(T + K + E)
     sel = torch.stack([torch.randperm(E, generator=g)[:K] for _ in range(min(T, 512))])
     sel = sel.repeat((T + sel.shape[0] - 1) // sel.shape[0], 1)[:T].int()
     if E >= 4:
         sel[sel == 1] = 0            # leave expert 1 empty, make expert 0 hot (duplicates within a token are fine here)
-    r = ops.route_build(sel.to(DEV), E)
+    r = ops.route_build(sel.to(DEV), E, row_tile=row_tile)
     ref = op.prepare_sel2(sel)       # stable argsort = the reference's maps after canonicalisation
     flat = sel.flatten()
     counts = torch.bincount(flat.long(), minlength=E)
@@ -36,7 +37,7 @@ def test_route_build_bit_exact(ops, T, K, E):
     assert torch.equal(r.sorted_sel.cpu(), ref.sel.flatten())
     assert torch.equal(r.sort_index.cpu(), ref.out_index)
     assert torch.equal(r.sort_index.cpu() // K, ref.sel_index)
-    pad = F.pad(((counts + 127) // 128 * 128).cumsum(0), (1, 0))
+    pad = F.pad(((counts + row_tile - 1) // row_tile * row_tile).cumsum(0), (1, 0))
     assert torch.equal(r.pad_offsets.cpu().long(), pad)
     # slot <-> row maps are mutually inverse and expert-major
     s2r, r2s = r.slot_to_row.cpu().long(), r.row_to_slot.cpu().long()
@@ -143,17 +144,18 @@ def test_combine_order_matches_reference_rounding(ops):
 
 
 # ------------------------------------------------------------------------------------------------ grouped GEMM
-def _route_for_counts(ops, counts):
+def _route_for_counts(ops, counts, row_tile=128):
     sel = torch.cat([torch.full((c,), e, dtype=torch.int32) for e, c in enumerate(counts)])
-    return ops.route_build(sel.view(-1, 1).to(DEV), len(counts))
+    return ops.route_build(sel.view(-1, 1).to(DEV), len(counts), row_tile=row_tile)
 
 
+@pytest.mark.parametrize("row_tile", [128, 256])     # 256: the CTA-pair (cta_group::2) kernel where n >= 256
 @pytest.mark.parametrize("kn", [False, True])
 @pytest.mark.parametrize("counts,n,k", [([128], 256, 64), ([300, 0, 77, 513], 4304, 1152), ([300, 0, 77, 513], 1152, 4304),
                                         ([100, 200, 300], 128, 512), ([5, 5, 5, 5, 5, 5, 5, 5], 64, 1024)])
-def test_gemm_rows(ops, kn, counts, n, k):
+def test_gemm_rows(ops, kn, counts, n, k, row_tile):
     E = len(counts)
-    r = _route_for_counts(ops, counts)
+    r = _route_for_counts(ops, counts, row_tile)
     g = torch.Generator().manual_seed(n + k)
     a = torch.zeros(r.row_cap, k, dtype=torch.bfloat16)
     pad = r.pad_offsets.cpu().tolist()
@@ -169,11 +171,12 @@ def test_gemm_rows(ops, kn, counts, n, k):
         assert_close_rms(c_[pad[e]:pad[e] + cnt], F.gelu(z.float(), approximate="tanh"), 2e-2, f"act e={e}")
 
 
+@pytest.mark.parametrize("row_tile", [128, 256])
 @pytest.mark.parametrize("counts,m,n", [([128], 128, 256), ([300, 0, 77, 513], 4304, 1152), ([300, 0, 77, 513], 1152, 4304),
                                         ([100, 200, 300], 512, 128)])
-def test_gemm_reduce(ops, counts, m, n):
+def test_gemm_reduce(ops, counts, m, n, row_tile):
     E = len(counts)
-    r = _route_for_counts(ops, counts)
+    r = _route_for_counts(ops, counts, row_tile)
     g = torch.Generator().manual_seed(m + n)
     a = torch.zeros(r.row_cap, m, dtype=torch.bfloat16)
     b = torch.zeros(r.row_cap, n, dtype=torch.bfloat16)
@@ -187,10 +190,88 @@ def test_gemm_reduce(ops, counts, m, n):
         assert_close_rms(out[e], ref, 1e-4, f"wgrad e={e}")
 
 
+@pytest.mark.parametrize("row_tile", [128, 256])
+def test_gemm_fused_glu_forward_and_backward_epilogues(ops, row_tile):
+    counts = [300, 0, 77, 513]
+    E, D, Fh = 4, 512, 384
+    r = _route_for_counts(ops, counts, row_tile)
+    g = torch.Generator().manual_seed(11)
+    pad = r.pad_offsets.cpu().tolist()
+    x = torch.zeros(r.row_cap, D, dtype=torch.bfloat16)
+    dy = torch.zeros(r.row_cap, D, dtype=torch.bfloat16)
+    for e, c in enumerate(counts):
+        x[pad[e]:pad[e] + c] = torch.randn(c, D, generator=g).bfloat16()
+        dy[pad[e]:pad[e] + c] = torch.randn(c, D, generator=g).bfloat16()
+    w1 = (torch.randn(E, 2 * Fh, D, generator=g) / D ** 0.5).bfloat16()
+    w2 = (torch.randn(E, D, Fh, generator=g) / Fh ** 0.5).bfloat16()
+    h, z = ops.gemm_rows(x.to(DEV), w1.to(DEV), w_is_kn=False, route=r, act=ops.ACT_SILU_GLU)
+    assert h.shape == (r.row_cap, Fh) and z.shape == (r.row_cap, 2 * Fh)
+    dz = ops.gemm_rows(dy.to(DEV), w2.to(DEV), w_is_kn=True, route=r, act_bwd=ops.ACT_SILU_GLU, aux=z)
+    assert dz.shape == (r.row_cap, 2 * Fh)
+    for e, c in enumerate(counts):
+        if c == 0:
+            continue
+        sl = slice(pad[e], pad[e] + c)
+        zr = (x[sl].float() @ w1[e].float().t()).bfloat16()
+        assert_close_rms(z[sl], zr, 2e-2, f"z e={e}")
+        zz = z[sl].cpu().float().requires_grad_(True)
+        gate, up = zz.chunk(2, dim=-1)
+        hr = up * F.silu(gate)
+        assert_close_rms(h[sl], hr.detach(), 2e-2, f"h e={e}")
+        dh = (dy[sl].float() @ w2[e].float()).bfloat16().float()
+        hr.backward(dh)
+        assert_close_rms(dz[sl], zz.grad, 3e-2, f"dz e={e}")
+
+
+@pytest.mark.parametrize("act", ["ACT_RELU", "ACT_GELU_TANH"])
+def test_gemm_fused_activation_backward(ops, act):
+    counts = [200, 131]
+    E, D, Fh = 2, 256, 520
+    r = _route_for_counts(ops, counts, 128)
+    g = torch.Generator().manual_seed(12)
+    pad = r.pad_offsets.cpu().tolist()
+    z = torch.randn(r.row_cap, Fh, generator=g).bfloat16()
+    dy = torch.randn(r.row_cap, D, generator=g).bfloat16()
+    w2 = (torch.randn(E, D, Fh, generator=g) / Fh ** 0.5).bfloat16()
+    code = getattr(ops, act)
+    dz = ops.gemm_rows(dy.to(DEV), w2.to(DEV), w_is_kn=True, route=r, act_bwd=code, aux=z.to(DEV))
+    fn = F.relu if act == "ACT_RELU" else (lambda t: F.gelu(t, approximate="tanh"))
+    for e, c in enumerate(counts):
+        sl = slice(pad[e], pad[e] + c)
+        zz = z[sl].float().requires_grad_(True)
+        fn(zz).backward((dy[sl].float() @ w2[e].float()).bfloat16().float())
+        assert_close_rms(dz[sl], zz.grad, 3e-2, f"dz e={e}")
+
+
+def test_router_aux_and_backward_match_autograd(ops):
+    """csmoe_router_aux_fwd / csmoe_router_bwd against torch autograd of the reference formulas (moe.py:71-132)."""
+    B, N, D, E, K = 3, 200, 256, 8, 2
+    g = torch.Generator().manual_seed(13)
+    x = torch.randn(B * N, D, generator=g)
+    wg = torch.randn(E, D, generator=g) * 0.05
+    dtw = torch.randn(B * N, K, generator=g)
+    dpx = torch.randn(B * N, E, generator=g) * 0.1
+    xr, wr = x.clone().requires_grad_(True), wg.clone().requires_grad_(True)
+    w_ref, idx_ref, p_ref, l_ref = om.router_policy(xr.view(B, N, D), wr, K)
+    bal = om.balanceloss(idx_ref, p_ref, E)
+    zl = om.zloss(l_ref)
+    loss = 0.7 * bal + 0.3 * zl + (w_ref * dtw.view(B, N, K)).sum() + (p_ref * dpx.view(B, N, E)).sum()
+    loss.backward()
+    logits, probs, tw, ti = ops.router_fwd(x.to(DEV), wg.to(DEV), K)
+    assert torch.equal(ti.cpu().long().view(B, N, K), idx_ref)
+    losses, cnt, lse = ops.router_aux_fwd(logits, probs, ti, B)
+    torch.testing.assert_close(losses.cpu(), torch.stack([bal, zl]).detach(), rtol=1e-4, atol=1e-6)
+    gl = torch.tensor([0.7, 0.3], device=DEV)
+    dx, dwg = ops.router_bwd(x.to(DEV), wg.to(DEV), probs, tw, ti, B, dtw=dtw.to(DEV), dprobs=dpx.to(DEV), lse=lse,
+                             cnt=cnt, g_losses=gl)
+    assert_close_rms(dx, xr.grad, 1e-3, "dx")
+    assert_close_rms(dwg, wr.grad, 1e-3, "dwg")
+
+
 def test_gemm_linearity_at_full_size(ops):
     """Size-independent property at the bench shape (C2 rows x D x 2F): G(a1 + a2) == G(a1) + G(a2) up to rounding."""
     counts = [2048] * 4
-    r = _route_for_counts(ops, counts)
+    r = _route_for_counts(ops, counts, 256)
     D, N = 3072, 16384
     g = torch.Generator(device=DEV).manual_seed(0)
     # small integers: a1 + a2 is exact in bf16, so the identity holds up to fp32 accumulation order only

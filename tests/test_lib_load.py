@@ -30,9 +30,11 @@ def test_library_exports_every_declared_symbol():
 
 def test_row_cap_and_workspace_queries():
     lib = _lib.load()
-    assert lib.csmoe_route_row_cap(8192, 4) == 8704  # 8192 + 4*127 rounded up to 128
-    assert lib.csmoe_route_row_cap(0, 1) == 128
-    assert lib.csmoe_route_row_cap(10, 0) == -1
+    assert lib.csmoe_route_row_cap(8192, 4, 128) == 8704  # 8192 + 4*127 rounded up to 128
+    assert lib.csmoe_route_row_cap(8192, 4, 256) == 9216  # 8192 + 4*255 rounded up to 256
+    assert lib.csmoe_route_row_cap(0, 1, 128) == 128
+    assert lib.csmoe_route_row_cap(10, 0, 128) == -1
+    assert lib.csmoe_route_row_cap(10, 4, 100) == -1
     assert lib.csmoe_route_workspace_bytes(4096, 8) == 2 * 8 * 4
 
 
