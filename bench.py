@@ -276,6 +276,12 @@ def run_ours(a):
     gemm_flops = [f for _, _, f, _ in timed]
     gemm_tflops = sum(gemm_flops) / (sum(gemm_ms) * 1e-3) / 1e12 if gemm_ms else 0.0
     gemm_share = sum(gemm_ms) / (ms_router * a.steps) if gemm_ms else 0.0
+    per_step = len(timed) // max(a.steps, 1)
+    gemm_detail = []
+    for i in range(per_step):
+        ms_i = [gemm_ms[j] for j in range(i, len(timed), per_step)]
+        gemm_detail.append({"kind": timed[i][3], "ms": round(statistics.median(ms_i), 4),
+                            "tflops": round(timed[i][2] / (statistics.median(ms_i) * 1e-3) / 1e12, 1)})
 
     # ---- timed region 2: competition step
     set_branch(layer, True)
@@ -317,7 +323,7 @@ def run_ours(a):
             "roofline": {"bound": "tensor", "achieved": gemm_tflops, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": gemm_tflops / peak_tf, "traffic": traffic, "kernel": "grouped_gemm_kernel (tcgen05)",
                          "peak_source": peak_src, "launches_per_step": len(timed) // max(a.steps, 1),
-                         "share_of_step": gemm_share},
+                         "share_of_step": gemm_share, "per_launch": gemm_detail},
             "cpu_baseline": cpu, "gpu_launches": launches, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)

@@ -18,8 +18,17 @@ import torch
 from torch.autograd import Function
 from torch.autograd.function import once_differentiable
 
+import os
+
 from . import ops
 from ._lib import ROW_TILE
+
+# Epilogue fusion switches (measured on B200 at the bench shape, profiles/r01b_*):
+#   forward  GLU in the GEMM-1 epilogue: same time as GEMM + separate kernel, one launch and one HBM pass fewer -> on.
+#   backward act'(z) in the dgrad-2 epilogue: the row-strided z reads make that epilogue longer than its main loop
+#   (0.57 ms vs 0.33 + 0.17 ms) -> off by default until the epilogue I/O is staged through shared memory.
+_FUSE_FWD = os.environ.get("CSMOE_FUSE_EPILOGUE_FWD", "1") != "0"
+_FUSE_BWD = os.environ.get("CSMOE_FUSE_EPILOGUE_BWD", "0") != "0"
 
 
 @dataclass(frozen=True)
@@ -50,7 +59,7 @@ def _pad_rows(x: torch.Tensor, rows: int) -> torch.Tensor:
 
 def _ffn_first(xp, w1, b1, spec: FFNSpec, **where):
     """z (pre-activation, with bias) and h = act(z) for the first projection."""
-    if spec.glu and not spec.kn_layout and b1 is None:
+    if spec.glu and not spec.kn_layout and b1 is None and _FUSE_FWD:
         h, z = ops.gemm_rows(xp, w1, w_is_kn=False, act=ops.ACT_SILU_GLU, **where)   # GLU fused in the epilogue
         return z, h
     if spec.glu:
@@ -135,7 +144,11 @@ class SparseFFNFn(Function):
         else:
             dw2 = ops.gemm_reduce(dyp, h, E, route=route, out_dtype=w2.dtype)  # [E, Dout, F]
         # dgrad of the second projection with the activation backward fused into its epilogue: dz = (dy W2) * act'(z)
-        dz = ops.gemm_rows(dyp, w2b, w_is_kn=not spec.kn_layout, route=route, act_bwd=spec.act, aux=z)
+        if _FUSE_BWD:
+            dz = ops.gemm_rows(dyp, w2b, w_is_kn=not spec.kn_layout, route=route, act_bwd=spec.act, aux=z)
+        else:
+            dh = ops.gemm_rows(dyp, w2b, w_is_kn=not spec.kn_layout, route=route)
+            dz = dh if spec.act == ops.ACT_NONE else ops.act_bwd(z, dh, spec.act)
         db1 = ops.bias_grad(dz, E, route=route, out_dtype=w1.dtype) if ctx.has_b[0] else None
         if spec.kn_layout:
             dw1 = ops.gemm_reduce(xp, dz, E, route=route, out_dtype=w1.dtype)  # [E, D, H]
@@ -178,8 +191,12 @@ class DenseFFNFn(Function):
             dw2 = ops.gemm_reduce(h, dy, E, dense_rows=t_pad, a_expert_rows=t_pad, b_expert_rows=t_pad, out_dtype=w2.dtype)
         else:
             dw2 = ops.gemm_reduce(dy, h, E, dense_rows=t_pad, a_expert_rows=t_pad, b_expert_rows=t_pad, out_dtype=w2.dtype)
-        dz = ops.gemm_rows(dy, w2b, w_is_kn=not spec.kn_layout, dense_rows=t_pad, a_expert_rows=t_pad,
-                           act_bwd=spec.act, aux=z)
+        if _FUSE_BWD:
+            dz = ops.gemm_rows(dy, w2b, w_is_kn=not spec.kn_layout, dense_rows=t_pad, a_expert_rows=t_pad,
+                               act_bwd=spec.act, aux=z)
+        else:
+            dh = ops.gemm_rows(dy, w2b, w_is_kn=not spec.kn_layout, dense_rows=t_pad, a_expert_rows=t_pad)
+            dz = dh if spec.act == ops.ACT_NONE else ops.act_bwd(z, dh, spec.act)
         db1 = ops.bias_grad(dz, E, dense_rows=t_pad, out_dtype=w1.dtype) if ctx.has_b[0] else None
         if spec.kn_layout:
             dw1 = ops.gemm_reduce(xb, dz, E, dense_rows=t_pad, a_expert_rows=0, b_expert_rows=t_pad, out_dtype=w1.dtype)
