@@ -75,7 +75,7 @@ class MoeLayer(nn.Module):
     """Base layer: gate + experts + the loss helpers every router shares (reference: moe.py:8-132,214-226)."""
 
     def __init__(self, in_embed_dim=768, out_embed_dim=768, num_of_experts=4, num_selected=2, expert=None, args=None):
-        super().__init__()
+        nn.Module.__init__(self)   # explicit: under integrate.bind_multimodal the next class in the MRO is the reference's MoeLayer
         self.in_embed_dim = in_embed_dim
         self.out_embed_dim = out_embed_dim
         self.num_of_experts = num_of_experts
@@ -174,7 +174,7 @@ class CompeteSMoE(MoeLayer):
     """CompeteSMoE layer (reference: moe_model/model/moe/competesmoe.py:9-415)."""
 
     def __init__(self, in_embed_dim=768, out_embed_dim=768, num_of_experts=4, num_selected=2, expert=None, args=None):
-        super().__init__(in_embed_dim, out_embed_dim, num_of_experts, num_selected, expert, args)
+        MoeLayer.__init__(self, in_embed_dim, out_embed_dim, num_of_experts, num_selected, expert, args)
         if args is None or not hasattr(args, "rate_flip"):
             raise ValueError("The 'args' parameter must have the attribute 'rate_flip'.")
         if not hasattr(args, "warm_up"):

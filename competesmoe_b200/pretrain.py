@@ -46,7 +46,6 @@ class RegularizedLayer:
     """framework/layers/regularized_layer.py:9-62: named regularisers, averaged per name on read, then reset."""
 
     def __init__(self) -> None:
-        super().__init__()
         self.reg_accumulated = {}
         self.reg_counts_n = {}
         self.regularization_present = False
@@ -76,7 +75,6 @@ class LoggingLayer:
     """framework/layers/logging_layer.py:9-52 (running sums of logged scalars)."""
 
     def __init__(self) -> None:
-        super().__init__()
         self._logs = {}
         self._log_counts = {}
 
@@ -131,7 +129,11 @@ class MoE(LoggingLayer, RegularizedLayer, OncePerIterLayer, torch.nn.Module):
                  v_dim: Optional[int] = None, expert_dropout: float = 0.0, sync_distributed: bool = False,
                  selection_dropout: float = 0.0, log_interval: Optional[int] = 100, args=None, is_att=False,
                  out_dmodel=None, inp_expert=None, out_expert=None):
-        super().__init__()
+        # explicit initialisation (no cooperative super().__init__): under integrate.bind_pretrain the reference's
+        # MoE follows in the MRO and its __init__ must not run
+        torch.nn.Module.__init__(self)
+        LoggingLayer.__init__(self)
+        RegularizedLayer.__init__(self)
         if is_att:
             raise NotImplementedError("the attention-projection variant (is_att) is outside the MoE-MLP hot path")
         self.is_att = False
@@ -258,7 +260,7 @@ class CompeteSMoE(MoE):
                  expert_dropout: float = 0.0, sync_distributed: bool = False, selection_dropout: float = 0.0,
                  log_interval: Optional[int] = 100, args=None, std=1, out_dmodel=None, is_att=False, inp_expert=None,
                  out_expert=None):
-        super().__init__(dmodel=dmodel, n_experts=n_experts, expert_size=expert_size, n_heads=n_heads, topk=topk,
+        MoE.__init__(self, dmodel=dmodel, n_experts=n_experts, expert_size=expert_size, n_heads=n_heads, topk=topk,
                          dropout=dropout, weight_scale=weight_scale, selection_mode=selection_mode,
                          perplexity_reg=perplexity_reg, perplexity_reg_mode=perplexity_reg_mode,
                          activation_after_topk=activation_after_topk, activation=activation, sel_bias=sel_bias, bias=bias,
