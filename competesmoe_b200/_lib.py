@@ -33,6 +33,7 @@ class GemmArgs(C.Structure):
         ("max_ctas", i32), ("act_bwd", i32),
         ("aux", vp), ("ldaux", i64),
         ("row_tile", i32), ("reserved", i32),
+        ("c_rows", vp),
     ]
 
 
@@ -61,6 +62,16 @@ _SIGNATURES = {
     "csmoe_cast_f32_bf16": (i32, [vp, vp, i64, vp]),
     "csmoe_affinity_fwd": (i32, [vp, i32, i32, i64, i64, i32, i32, vp, vp]),
     "csmoe_affinity_bwd": (i32, [vp, vp, i32, i32, i64, i64, i32, i32, vp, vp]),
+    "csmoe_ep_ipc_handle_bytes": (i32, []),
+    "csmoe_ep_alloc": (i32, [i64, C.POINTER(vp), vp]),
+    "csmoe_ep_open": (i32, [vp, C.POINTER(vp)]),
+    "csmoe_ep_close": (i32, [vp]),
+    "csmoe_ep_free": (i32, [vp]),
+    "csmoe_ep_barrier": (i32, [vp, vp, i32, i32, vp]),
+    "csmoe_ep_exchange_plan": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i64, vp, vp, vp, vp, vp]),
+    "csmoe_ep_dispatch": (i32, [vp, i32, i32, i32, i64, vp, vp, vp, vp, i32, vp, vp, vp, i32, i32, vp]),
+    "csmoe_ep_row_ptrs": (i32, [vp, vp, vp, vp, i32, i64, vp, i64, i32, i32, vp, vp, i32, vp]),
+    "csmoe_ep_push_rows": (i32, [vp, i32, i64, i32, i64, vp, vp]),
 }
 
 _lock = threading.Lock()

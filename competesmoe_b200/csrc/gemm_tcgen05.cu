@@ -47,6 +47,7 @@ struct KParams {
   int num_m_pairs;    // CTA-pair kernel: number of 256-row blocks
   const void* aux;    // backward epilogues: the saved pre-activation z
   long long ldaux;
+  const unsigned long long* c_rows;  // plain ROWS epilogue: per-row destination address (expert-parallel return), 0 = skip
   const int* tile_expert;
   const int* pad_offsets;
   void* c;
@@ -163,6 +164,12 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, const Tile& ti, 
                            : static_cast<const void*>(reinterpret_cast<const __nv_bfloat16*>(p.bias) + boff);
   }
   if (p.epi == kEpiPlain) {
+    // Expert-parallel return: the row goes straight to its slot in the source rank's buffer (peer memory over NVLink).
+    unsigned long long row_ptr = 0ull;
+    if (MODE == CSMOE_GEMM_ROWS && p.c_rows != nullptr) {
+      row_ptr = __ldg(p.c_rows + out_row);
+      row_ok = row_ptr != 0ull;
+    }
 #pragma unroll 1
     for (int chunk = half * (BN / 64); chunk < (half + 1) * (BN / 64); ++chunk) {
       uint32_t v[32];
@@ -183,11 +190,13 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, const Tile& ti, 
 #pragma unroll
             for (int i = 0; i < 8; ++i) a8[i] = __uint_as_float(v[g * 8 + i]);
             if (p.c_fp32) {
-              float* c_row = reinterpret_cast<float*>(p.c) + c_off + out_row * p.ldc;
+              float* c_row = row_ptr ? reinterpret_cast<float*>(row_ptr)
+                                     : reinterpret_cast<float*>(p.c) + c_off + out_row * p.ldc;
               float* pre_row = p.preact ? reinterpret_cast<float*>(p.preact) + out_row * p.ldpre : nullptr;
               epilogue_store8<float>(p, a8, c_row, pre_row, bias_row, col);
             } else {
-              __nv_bfloat16* c_row = reinterpret_cast<__nv_bfloat16*>(p.c) + c_off + out_row * p.ldc;
+              __nv_bfloat16* c_row = row_ptr ? reinterpret_cast<__nv_bfloat16*>(row_ptr)
+                                             : reinterpret_cast<__nv_bfloat16*>(p.c) + c_off + out_row * p.ldc;
               __nv_bfloat16* pre_row =
                   p.preact ? reinterpret_cast<__nv_bfloat16*>(p.preact) + out_row * p.ldpre : nullptr;
               epilogue_store8<__nv_bfloat16>(p, a8, c_row, pre_row, bias_row, col);
@@ -756,7 +765,10 @@ using namespace csmoe;
 
 extern "C" int csmoe_grouped_gemm(const csmoe_gemm_args* a, void* stream_) {
   CSMOE_CHECK_ARG(a != nullptr, "csmoe_grouped_gemm: args is NULL");
-  CSMOE_CHECK_ARG(a->a && a->b && a->c, "csmoe_grouped_gemm: a/b/c must be non-NULL");
+  CSMOE_CHECK_ARG(a->a && a->b && (a->c || a->c_rows), "csmoe_grouped_gemm: a/b/c must be non-NULL");
+  CSMOE_CHECK_ARG(a->c_rows == nullptr || (a->mode == CSMOE_GEMM_ROWS && a->act == CSMOE_ACT_NONE &&
+                                           a->act_bwd == CSMOE_ACT_NONE && a->preact == nullptr && !a->accumulate),
+                  "csmoe_grouped_gemm: c_rows (per-row destinations) needs ROWS mode and the plain (bias-only) epilogue");
   CSMOE_CHECK_ARG(a->mode == CSMOE_GEMM_ROWS || a->mode == CSMOE_GEMM_REDUCE, "csmoe_grouped_gemm: bad mode %d", a->mode);
   CSMOE_CHECK_ARG(a->num_experts >= 1, "csmoe_grouped_gemm: num_experts must be >= 1");
   CSMOE_CHECK_ARG(a->m > 0 && a->n > 0 && a->k > 0, "csmoe_grouped_gemm: m, n, k must be positive");
@@ -829,6 +841,7 @@ extern "C" int csmoe_grouped_gemm(const csmoe_gemm_args* a, void* stream_) {
   kp.band = 8;
   kp.aux = a->aux;
   kp.ldaux = a->ldaux;
+  kp.c_rows = reinterpret_cast<const unsigned long long*>(a->c_rows);
   if (glu_fwd) {
     kp.epi = kEpiGluFwd;
     kp.glu_f = static_cast<int>(a->n / 2);

@@ -1,0 +1,356 @@
+"""Expert parallelism (stage 6): experts sharded over the ranks of a process group, tokens stay data-parallel.
+
+Rank r of P owns experts [r*E/P, (r+1)*E/P).  `torch.distributed` is used for plumbing only (exchanging CUDA IPC
+handles once, all-gather / reduce-scatter of expert weights for the rare competition step); the data path is
+libcsmoe kernels that store straight into peer HBM over NVLink (csrc/ep.cu):
+
+    forward   route_build -> exchange_plan (counts to all peers + barrier + layout) -> dispatch (permute + send)
+              -> barrier -> row_ptrs -> grouped GEMM 1 -> grouped GEMM 2 whose epilogue writes every output row into the
+              source rank's return buffer -> barrier -> local gate-weighted combine
+    backward  dispatch(w * dout) -> barrier -> wgrad / dgrad GEMMs, the last of which returns dx rows the same way
+              -> barrier -> local reduce over k
+
+No host synchronisation and no host-side split sizes: buffer capacities are static worst cases (every slot of every
+rank routed to one rank), so the step stays CUDA-graph capturable.  The reference has no counterpart (data-parallel
+only).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import _lib, ops
+from ._lib import ROW_TILE, check
+from .functional import FFNSpec, _bf16, _ffn_first, _FUSE_BWD
+
+MAX_EXPERTS = 1024
+_CTRL_BYTES = 4096 + 16 * MAX_EXPERTS * 4   # flags, epoch, counts_all[P<=16][E<=1024]
+
+
+# ------------------------------------------------------------------------------------------------ host mirror of the plan
+def plan_host(counts_all: torch.Tensor, rank: int, row_tile: int):
+    """Pure-integer mirror of ep_exchange_plan_kernel (csrc/ep.cu), used by the CPU tests and as its specification.
+
+    counts_all [P, E]: rows rank s sends to expert e.  Returns (dest_base [E], recv_counts [E/P], recv_pad_offsets [E/P+1]).
+    Every rank derives the same layout from the same matrix: inside owner o's receive space expert e starts at the
+    row_tile-aligned prefix sum of the totals of o's experts, and inside an expert rows are ordered by source rank."""
+    P, E = counts_all.shape
+    El = E // P
+    c = counts_all.to(torch.int64)
+    total = c.sum(0)
+    before = c[:rank].sum(0)
+    padded = (total + row_tile - 1) // row_tile * row_tile
+    start = torch.zeros(E, dtype=torch.int64)
+    end = torch.zeros(P, dtype=torch.int64)
+    for o in range(P):
+        run = 0
+        for el in range(El):
+            start[o * El + el] = run
+            run += int(padded[o * El + el])
+        end[o] = run
+    dest_base = start + before
+    recv_counts = total[rank * El:(rank + 1) * El]
+    recv_pad = torch.cat([start[rank * El:(rank + 1) * El], end[rank:rank + 1]])
+    return dest_base.to(torch.int32), recv_counts.to(torch.int32), recv_pad.to(torch.int32)
+
+
+def recv_row_cap(world: int, max_slots_per_rank: int, experts_per_rank: int, row_tile: int) -> int:
+    """Static capacity of a receive buffer: every slot of every rank lands on this rank."""
+    n = world * max_slots_per_rank
+    worst = n + experts_per_rank * (row_tile - 1)
+    return (worst + row_tile - 1) // row_tile * row_tile
+
+
+# ------------------------------------------------------------------------------------------------ symmetric memory
+class _CAI:
+    """Minimal __cuda_array_interface__ holder so torch can alias memory that libcsmoe allocated."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+class SymmetricBuffer:
+    """The same allocation on every rank of the group, each mapped into every other rank's address space."""
+
+    def __init__(self, local_ptr: int, peer_ptrs: List[int], nbytes: int, device: torch.device):
+        self.local_ptr, self.peer_ptrs, self.nbytes, self.device = local_ptr, peer_ptrs, nbytes, device
+        self._bytes = torch.as_tensor(_CAI(local_ptr, nbytes), device=device)
+
+    def peers(self, offset: int = 0):
+        """Host array of P device pointers (entry r = this buffer on rank r, shifted by `offset` bytes)."""
+        arr = (C.c_void_p * len(self.peer_ptrs))()
+        for i, p in enumerate(self.peer_ptrs):
+            arr[i] = p + offset
+        return arr
+
+    def tensor(self, offset: int, shape, dtype: torch.dtype) -> torch.Tensor:
+        n = 1
+        for s in shape:
+            n *= s
+        nb = n * torch.empty((), dtype=dtype).element_size()
+        assert offset + nb <= self.nbytes, "symmetric buffer too small"
+        return self._bytes[offset:offset + nb].view(dtype).view(*shape)
+
+
+class EPGroup:
+    """Process-group-wide state: rank / world, the control block (barrier flags, epoch, count matrix) and scratch."""
+
+    def __init__(self, group: Optional[dist.ProcessGroup] = None, device: Optional[torch.device] = None):
+        self.group = group
+        on = dist.is_available() and dist.is_initialized()
+        self.world = dist.get_world_size(group) if on else 1
+        self.rank = dist.get_rank(group) if on else 0
+        assert self.world <= 16, "libcsmoe expert parallelism supports up to 16 ranks per group"
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        self._owned: List[SymmetricBuffer] = []
+        self.ctrl = self.alloc(_CTRL_BYTES)
+        self._flags = self.ctrl.peers(0)
+        self._counts_all = self.ctrl.peers(4096)
+        self._epoch_ptr = self.ctrl.local_ptr + 2048
+        self._scratch = {}
+        self._identity = {}
+
+    # ---- memory
+    def alloc(self, nbytes: int) -> SymmetricBuffer:
+        """Collective: every rank of the group must call this in the same order with the same size."""
+        lib = _lib.load()
+        nbytes = (int(nbytes) + 255) // 256 * 256
+        hb = lib.csmoe_ep_ipc_handle_bytes()
+        handle = C.create_string_buffer(hb)
+        ptr = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(lib.csmoe_ep_alloc(nbytes, C.byref(ptr), handle), "csmoe_ep_alloc")
+            peers = [0] * self.world
+            peers[self.rank] = ptr.value
+            if self.world > 1:
+                handles: List[Optional[bytes]] = [None] * self.world
+                dist.all_gather_object(handles, bytes(handle.raw), group=self.group)
+                for r, h in enumerate(handles):
+                    if r == self.rank:
+                        continue
+                    p = C.c_void_p()
+                    check(lib.csmoe_ep_open(C.create_string_buffer(h, hb), C.byref(p)), "csmoe_ep_open")
+                    peers[r] = p.value
+                dist.barrier(group=self.group)
+        buf = SymmetricBuffer(ptr.value, peers, nbytes, self.device)
+        self._owned.append(buf)
+        return buf
+
+    def scratch(self, name: str, nbytes: int) -> SymmetricBuffer:
+        """Group-wide scratch (consumed inside one forward or one backward); grown collectively on demand."""
+        buf = self._scratch.get(name)
+        if buf is None or buf.nbytes < nbytes:
+            buf = self.alloc(nbytes)
+            self._scratch[name] = buf
+        return buf
+
+    def identity(self, n: int) -> torch.Tensor:
+        t = self._identity.get(n)
+        if t is None:
+            t = torch.arange(n, dtype=torch.int32, device=self.device)
+            self._identity[n] = t
+        return t
+
+    def close(self):
+        lib = _lib.load()
+        torch.cuda.synchronize(self.device)
+        if self.world > 1:
+            dist.barrier(group=self.group)
+        for buf in self._owned:
+            for r, p in enumerate(buf.peer_ptrs):
+                if r != self.rank and p:
+                    lib.csmoe_ep_close(p)
+        if self.world > 1:
+            dist.barrier(group=self.group)
+        for buf in self._owned:
+            lib.csmoe_ep_free(buf.local_ptr)
+        self._owned.clear()
+
+    # ---- kernels
+    def barrier(self):
+        ops._call("csmoe_ep_barrier", self._flags, self._epoch_ptr, self.rank, self.world, ops._stream())
+
+    def exchange_plan(self, counts: torch.Tensor, num_experts: int, row_tile: int, row_cap: int) -> "EPPlan":
+        assert num_experts % self.world == 0 and num_experts <= MAX_EXPERTS
+        El = num_experts // self.world
+        i32 = dict(dtype=torch.int32, device=counts.device)
+        dest_base = torch.empty(num_experts, **i32)
+        recv_counts = torch.empty(El, **i32)
+        recv_pad = torch.empty(El + 1, **i32)
+        tile_expert = torch.empty(row_cap // ROW_TILE, **i32)
+        ops._call("csmoe_ep_exchange_plan", counts.data_ptr(), self._counts_all, self._flags, self._epoch_ptr, self.rank,
+                  self.world, num_experts, row_tile, row_cap, dest_base.data_ptr(), recv_counts.data_ptr(),
+                  recv_pad.data_ptr(), tile_expert.data_ptr(), ops._stream())
+        return EPPlan(num_experts, El, row_tile, row_cap, dest_base, recv_counts, recv_pad, tile_expert)
+
+    def dispatch(self, src: torch.Tensor, top_k: int, route: ops.Route, plan: "EPPlan", recv, tags=None,
+                 slot_w: Optional[torch.Tensor] = None):
+        src = src.contiguous()
+        if slot_w is not None:
+            slot_w = slot_w.reshape(-1).contiguous()
+            assert slot_w.dtype == torch.float32
+        ops._call("csmoe_ep_dispatch", src.data_ptr(), ops._dt(src), src.shape[1], top_k, route.n_slots,
+                  route.sel.data_ptr(), route.slot_to_row.data_ptr(), route.pad_offsets.data_ptr(),
+                  plan.dest_base.data_ptr(), plan.experts_per_rank, ops._p(slot_w), recv, tags, self.rank, self.world,
+                  ops._stream())
+
+    def row_ptrs(self, tags: Optional[torch.Tensor], plan: "EPPlan", ret, ret_ld: int, dtype: torch.dtype,
+                 recv: Optional[torch.Tensor], want_ptrs: bool = True) -> Optional[torch.Tensor]:
+        c_rows = torch.empty(plan.row_cap, dtype=torch.int64, device=self.device) if want_ptrs else None
+        dt = _lib.BF16 if dtype == torch.bfloat16 else _lib.F32
+        ops._call("csmoe_ep_row_ptrs", ops._p(tags), plan.tile_expert.data_ptr(), plan.recv_counts.data_ptr(),
+                  plan.recv_pad_offsets.data_ptr(), plan.experts_per_rank, plan.row_cap, ret, ret_ld, dt, self.world,
+                  ops._p(c_rows), ops._p(recv), recv.shape[1] if recv is not None else 0, ops._stream())
+        return c_rows
+
+
+@dataclass
+class EPPlan:
+    num_experts: int
+    experts_per_rank: int
+    row_tile: int
+    row_cap: int
+    dest_base: torch.Tensor
+    recv_counts: torch.Tensor
+    recv_pad_offsets: torch.Tensor
+    tile_expert: torch.Tensor
+
+    def local_route(self, n_slots_hint: int) -> ops.Route:
+        """The received rows as a Route the grouped GEMM understands (only the fields it reads are filled)."""
+        return ops.Route(self.experts_per_rank, 1, n_slots_hint, self.row_cap, None, self.recv_counts, None,
+                         self.recv_pad_offsets, None, None, None, None, self.tile_expert, self.row_tile)
+
+
+class EPLayerState:
+    """Per-layer exchange buffers that must live from forward to backward (the received tokens are the activations
+    autograd would have saved anyway).  One outstanding forward per layer."""
+
+    def __init__(self, group: EPGroup, num_experts: int, top_k: int, d_in: int, d_out: int, max_tokens: int,
+                 row_tile: int = 256):
+        assert num_experts % group.world == 0, "the number of experts must be a multiple of the EP group size"
+        self.group, self.E, self.K, self.D, self.Dout = group, num_experts, top_k, d_in, d_out
+        self.El = num_experts // group.world
+        self.max_tokens = max_tokens
+        self.row_tile = row_tile
+        self.max_slots = max_tokens * top_k
+        self.row_cap = recv_row_cap(group.world, self.max_slots, self.El, row_tile)
+        self.recv_x = group.alloc(self.row_cap * d_in * 2)
+        self.tags = group.alloc(self.row_cap * 8)
+        self.ret_y = group.alloc(self.max_slots * d_out * 2)
+        # backward-only scratch is shared by every layer of the group (consumed inside one backward call)
+        group.scratch("recv_dy", self.row_cap * d_out * 2)
+        group.scratch("ret_dx", self.max_slots * d_in * 2)
+
+
+# ------------------------------------------------------------------------------------------------ weights for the dense step
+class AllGatherExpertsFn(Function):
+    """[E/P, ...] local expert parameters -> [E, ...] on every rank; backward = reduce-scatter of the gradient.
+    Used by the (rare) competition step, where every expert sees every token and moving 2*E*F_e bytes of weights is
+    cheaper than moving the tokens K-fold."""
+
+    @staticmethod
+    def forward(ctx, w_local, group: EPGroup):
+        ctx.group = group
+        if group.world == 1:
+            return w_local
+        out = torch.empty((group.world * w_local.shape[0], *w_local.shape[1:]), dtype=w_local.dtype, device=w_local.device)
+        dist.all_gather_into_tensor(out, w_local.contiguous(), group=group.group)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        group = ctx.group
+        if group.world == 1:
+            return g, None
+        out = torch.empty((g.shape[0] // group.world, *g.shape[1:]), dtype=g.dtype, device=g.device)
+        dist.reduce_scatter_tensor(out, g.contiguous(), op=dist.ReduceOp.SUM, group=group.group)
+        return out, None
+
+
+def gather_experts(w_local: Optional[torch.Tensor], group: EPGroup) -> Optional[torch.Tensor]:
+    return None if w_local is None else AllGatherExpertsFn.apply(w_local, group)
+
+
+# ------------------------------------------------------------------------------------------------ sparse experts, EP
+class EPSparseFFNFn(Function):
+    """out[t] = sum_k w[t,k] * FFN_{sel[t,k]}(x[t]) with the experts sharded over the group (w1/b1/w2/b2 hold the
+    LOCAL experts only, sel indexes GLOBAL experts)."""
+
+    @staticmethod
+    def forward(ctx, x, w, sel, w1, b1, w2, b2, spec: FFNSpec, st: EPLayerState):
+        g = st.group
+        T, K = sel.shape
+        assert T <= st.max_tokens and K == st.K, f"EP layer sized for {st.max_tokens} tokens x top-{st.K}, got {T} x {K}"
+        xb = _bf16(x)
+        w1b, w2b = _bf16(w1), _bf16(w2)
+        route = ops.route_build(sel, st.E, row_tile=ROW_TILE)
+        plan = g.exchange_plan(route.counts, st.E, st.row_tile, st.row_cap)
+        g.dispatch(xb, K, route, plan, st.recv_x.peers(), st.tags.peers())
+        g.barrier()
+        xp = st.recv_x.tensor(0, (st.row_cap, st.D), torch.bfloat16)
+        tags = st.tags.tensor(0, (st.row_cap,), torch.int64)
+        c_rows = g.row_ptrs(tags, plan, st.ret_y.peers(), st.Dout, torch.bfloat16, xp)
+        lr = plan.local_route(T * K)
+        z, h = _ffn_first(xp, w1b, b1, spec, route=lr)
+        ops.gemm_rows(h, w2b, w_is_kn=spec.kn_layout, bias=b2, route=lr, c_rows=c_rows)   # output rows land on their source ranks
+        g.barrier()
+        y = st.ret_y.tensor(0, (T * K, st.Dout), torch.bfloat16)
+        ident = g.identity(T * K)
+        out = ops.combine_fwd(y, ident, route.sel, w, T, K, round_each=spec.round_each, round_w=spec.round_w)
+        ctx.st, ctx.spec, ctx.route, ctx.plan = st, spec, route, plan
+        ctx.x_dtype, ctx.has_b = x.dtype, (b1 is not None, b2 is not None)
+        ctx.save_for_backward(z, h, w, w1, w2)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        z, h, w, w1, w2 = ctx.saved_tensors
+        st, spec, route, plan = ctx.st, ctx.spec, ctx.route, ctx.plan
+        g = st.group
+        T, K, El = route.n_slots // route.top_k, route.top_k, st.El
+        w1b, w2b = _bf16(w1), _bf16(w2)
+        dout = _bf16(dout.contiguous())
+        ident = g.identity(T * K)
+        y = st.ret_y.tensor(0, (T * K, st.Dout), torch.bfloat16)
+        xp = st.recv_x.tensor(0, (st.row_cap, st.D), torch.bfloat16)
+        tags = st.tags.tensor(0, (st.row_cap,), torch.int64)
+        dw = ops.combine_bwd_w(y, dout, ident, T, K) if ctx.needs_input_grad[1] else None
+        wu = w.to(torch.bfloat16).float() if spec.round_w else w
+        recv_dy = g.scratch("recv_dy", st.row_cap * st.Dout * 2)
+        ret_dx = g.scratch("ret_dx", st.max_slots * st.D * 2)
+        g.dispatch(dout, K, route, plan, recv_dy.peers(), None, slot_w=wu)
+        g.barrier()
+        dyp = recv_dy.tensor(0, (st.row_cap, st.Dout), torch.bfloat16)
+        c_rows = g.row_ptrs(tags, plan, ret_dx.peers(), st.D, torch.bfloat16, dyp)
+        lr = plan.local_route(T * K)
+        db2 = ops.bias_grad(dyp, El, route=lr, out_dtype=w2.dtype) if ctx.has_b[1] else None
+        if spec.kn_layout:
+            dw2 = ops.gemm_reduce(h, dyp, El, route=lr, out_dtype=w2.dtype)
+        else:
+            dw2 = ops.gemm_reduce(dyp, h, El, route=lr, out_dtype=w2.dtype)
+        if _FUSE_BWD:
+            dz = ops.gemm_rows(dyp, w2b, w_is_kn=not spec.kn_layout, route=lr, act_bwd=spec.act, aux=z)
+        else:
+            dh = ops.gemm_rows(dyp, w2b, w_is_kn=not spec.kn_layout, route=lr)
+            dz = dh if spec.act == ops.ACT_NONE else ops.act_bwd(z, dh, spec.act)
+        db1 = ops.bias_grad(dz, El, route=lr, out_dtype=w1.dtype) if ctx.has_b[0] else None
+        if spec.kn_layout:
+            dw1 = ops.gemm_reduce(xp, dz, El, route=lr, out_dtype=w1.dtype)
+        else:
+            dw1 = ops.gemm_reduce(dz, xp, El, route=lr, out_dtype=w1.dtype)
+        # dx rows go straight back to their source ranks (always executed: the barrier sequence must match on all ranks)
+        ops.gemm_rows(dz, w1b, w_is_kn=not spec.kn_layout, route=lr, c_rows=c_rows)
+        g.barrier()
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dxs = ret_dx.tensor(0, (T * K, st.D), torch.bfloat16)
+            dx = ops.scatter_reduce(dxs, ident, T, K).to(ctx.x_dtype)
+        return dx, dw, None, dw1, db1, dw2, db2, None, None

@@ -93,6 +93,38 @@ class MoeLayer(nn.Module):
         self.is_vision = False
         self.log_metrics = {}
         self._layout: Optional[X.ExpertLayout] = None
+        self._ep = None            # ep.EPLayerState once enable_expert_parallel() was called
+        self.ep_expert_offset = 0  # global index of experts[0] under expert parallelism
+
+    # ---- expert parallelism (no counterpart in the reference, which is data-parallel only)
+    def enable_expert_parallel(self, group, max_tokens: int, row_tile: int = 256):
+        """Shard the experts over `group` (a competesmoe_b200.ep.EPGroup): this rank keeps experts
+        [rank*E/P, (rank+1)*E/P) as `experts.{0..E/P-1}`; the gate stays replicated.  `max_tokens` = the largest B*N this
+        rank will ever pass to forward (sizes the peer-mapped exchange buffers).  Call after loading a full checkpoint."""
+        from .ep import EPLayerState
+        E, P = self.num_of_experts, group.world
+        if E % P != 0:
+            raise ValueError(f"{E} experts cannot be split over an expert-parallel group of {P} ranks")
+        El = E // P
+        self.ep_expert_offset = group.rank * El
+        self.experts = nn.ModuleList([self.experts[i] for i in range(self.ep_expert_offset, self.ep_expert_offset + El)])
+        self._layout = None
+        self._ep = EPLayerState(group, E, self.num_selected, self.in_embed_dim, self.out_embed_dim, max_tokens, row_tile)
+        return self
+
+    def _sparse_ffn(self, x2, gw, gidx, w1, b1, w2, b2, spec):
+        if self._ep is None:
+            return SparseFFNFn.apply(x2, gw, gidx, w1, b1, w2, b2, spec)
+        from .ep import EPSparseFFNFn
+        return EPSparseFFNFn.apply(x2, gw, gidx, w1, b1, w2, b2, spec, self._ep)
+
+    def _all_expert_weights(self, w1, b1, w2, b2):
+        """Competition step under expert parallelism: every rank needs every expert (all-gather, grads reduce-scatter)."""
+        if self._ep is None or self._ep.group.world == 1:
+            return w1, b1, w2, b2
+        from .ep import gather_experts
+        g = self._ep.group
+        return gather_experts(w1, g), gather_experts(b1, g), gather_experts(w2, g), gather_experts(b2, g)
 
     # ---- initialisation (moe.py:50-70)
     def init_gate_weights(self, std=0.02):
@@ -160,7 +192,7 @@ class MoeLayer(nn.Module):
         x2 = x.reshape(B * N, D)
         lay, w1, b1, w2, b2 = self._stacked_weights()
         logits, probs, gw, gidx, losses = GateFn.apply(x2, self.gate.weight, self.num_selected, B, True)
-        out = SparseFFNFn.apply(x2, gw, gidx, w1, b1, w2, b2, self._spec(lay)).view(B, N, self.out_embed_dim)
+        out = self._sparse_ffn(x2, gw, gidx, w1, b1, w2, b2, self._spec(lay)).view(B, N, self.out_embed_dim)
         balance_loss, router_z_loss = losses[0], losses[1]
         aux = balance_loss * self.args.balance_loss_coef + router_z_loss * self.args.router_z_loss_coef
         infor_aux = {"balance_loss": balance_loss.detach().clone(), "router_z_loss": router_z_loss.detach().clone()}
@@ -238,6 +270,7 @@ class CompeteSMoE(MoeLayer):
         auxiliary_loss = x.new_zeros(())
         infor_aux = {}
         if compete:
+            w1, b1, w2, b2 = self._all_expert_weights(w1, b1, w2, b2)
             y_all = DenseFFNFn.apply(x2, w1, b1, w2, b2, spec)                       # [E * t_pad, Dout]
             t_pad = y_all.shape[0] // E
             aff = AffinityFn.apply(y_all, E, T, t_pad, x.dtype == torch.bfloat16)                             # [T, E] f32 (x.dtype-rounded)
@@ -259,7 +292,7 @@ class CompeteSMoE(MoeLayer):
             infor_aux = {"balance_loss": balance_loss.detach().clone(), "diversity_loss": diversity_loss.detach().clone(),
                          "routerloss": routerloss.detach().clone()}
         else:
-            out = SparseFFNFn.apply(x2, gate_w, gate_idx, w1, b1, w2, b2, spec)
+            out = self._sparse_ffn(x2, gate_w, gate_idx, w1, b1, w2, b2, spec)
             self.last_routing = (gate_idx.view(B, N, K), gate_w.detach().view(B, N, K))
             if want_aux:
                 # balance + z losses come out of one fused reduction kernel (moe.py:214-226 combine_loss)

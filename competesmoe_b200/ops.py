@@ -257,7 +257,7 @@ def _gemm(args: GemmArgs, flops: float = 0.0, tag: str = "") -> None:
 def gemm_rows(a: torch.Tensor, w: torch.Tensor, *, w_is_kn: bool, route: Optional[Route] = None,
               dense_rows: int = 0, a_expert_rows: int = 0, bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
               want_preact: bool = False, out_dtype: Optional[torch.dtype] = None, act_bwd: int = ACT_NONE,
-              aux: Optional[torch.Tensor] = None):
+              aux: Optional[torch.Tensor] = None, c_rows: Optional[torch.Tensor] = None):
     """C[row] = A[row] . W[expert(row)] with a fused epilogue.
 
     a: [rows, k] bf16.  w: [E, n, k] (w_is_kn=False, nn.Linear layout) or [E, k, n] (w_is_kn=True).
@@ -266,6 +266,8 @@ def gemm_rows(a: torch.Tensor, w: torch.Tensor, *, w_is_kn: bool, route: Optiona
     Forward epilogue: + bias, activation; want_preact also returns the pre-activation.  act = ACT_SILU_GLU: w is
     [E, 2F, k]; returns (h [rows, F], z [rows, 2F]).
     Backward epilogue (act_bwd, aux = saved z): C = (A . W) * act'(z); ACT_SILU_GLU returns dz [rows, 2F] from dh [rows, F].
+    c_rows [rows] int64 (expert-parallel return): output row r is stored at address c_rows[r] (0 = skipped) instead of a
+    local C; nothing is returned.
     Returns C, or (C, preact) when want_preact.
     """
     _cuda(a, w, bias, aux)
@@ -293,8 +295,14 @@ def gemm_rows(a: torch.Tensor, w: torch.Tensor, *, w_is_kn: bool, route: Optiona
     g.a, g.lda = _p(a), a.stride(0)
     g.b, g.ldb, g.b_expert_stride = _p(w), w.stride(1), w.stride(0)
     c_cols = n // 2 if glu_fwd else (2 * n if glu_bwd else n)
-    c = torch.empty(m, c_cols, dtype=out_dtype, device=a.device)
-    g.c, g.ldc, g.c_dtype = _p(c), c_cols, _dt(c)
+    if c_rows is not None:
+        assert c_rows.dtype == torch.int64 and c_rows.numel() >= m and act == ACT_NONE and act_bwd == ACT_NONE
+        assert not want_preact and out_dtype in (torch.bfloat16, torch.float32)
+        c = None
+        g.c, g.ldc, g.c_dtype, g.c_rows = None, c_cols, BF16 if out_dtype == torch.bfloat16 else F32, _p(c_rows)
+    else:
+        c = torch.empty(m, c_cols, dtype=out_dtype, device=a.device)
+        g.c, g.ldc, g.c_dtype = _p(c), c_cols, _dt(c)
     g.act = act
     pre = None
     if want_preact or glu_fwd:

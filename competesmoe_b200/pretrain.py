@@ -180,6 +180,34 @@ class MoE(LoggingLayer, RegularizedLayer, OncePerIterLayer, torch.nn.Module):
 
     gate = property(lambda self: (lambda x: F.linear(x, self.w_gate, None)))
 
+    # ---- expert parallelism (no counterpart in the reference, which is data-parallel only)
+    _ep = None
+
+    def enable_expert_parallel(self, group, max_tokens: int, row_tile: int = 128):
+        """Shard keys / values (/ bias) over `group` (competesmoe_b200.ep.EPGroup): this rank keeps the slices
+        [rank*E/P, (rank+1)*E/P) along dim 0; w_gate (and o_bias) stay replicated.  `max_tokens` = the largest number of
+        tokens this rank passes to forward.  Call after loading a full checkpoint."""
+        from .ep import EPLayerState
+        E, P = self.n_experts, group.world
+        if E % P != 0:
+            raise ValueError(f"{E} experts cannot be split over an expert-parallel group of {P} ranks")
+        El = E // P
+        lo = group.rank * El
+        for name in ("keys", "values", "bias"):
+            p = getattr(self, name)
+            if p is not None:
+                setattr(self, name, torch.nn.Parameter(p.detach()[lo:lo + El].clone(), requires_grad=p.requires_grad))
+        self.ep_expert_offset = lo
+        self._ep = EPLayerState(group, E, self.num_selected, self.k_vec_dim, self.v_dim, max_tokens, row_tile)
+        return self
+
+    def _all_expert_weights(self):
+        if self._ep is None or self._ep.group.world == 1:
+            return self.keys, self.bias, self.values
+        from .ep import gather_experts
+        g = self._ep.group
+        return gather_experts(self.keys, g), gather_experts(self.bias, g), gather_experts(self.values, g)
+
     # ---- bookkeeping hooks
     def pre_train_forward(self):
         self.total_selections, self.total_gate_softmax, self.total_gate_logits = [], [], []
@@ -227,6 +255,10 @@ class MoE(LoggingLayer, RegularizedLayer, OncePerIterLayer, torch.nn.Module):
         pass  # the hidden activations never leave the fused kernels; the reference logs this only every log_interval
 
     def compute_moe_main(self, x2, selected, weights, cdt):
+        if self._ep is not None:
+            from .ep import EPSparseFFNFn
+            return EPSparseFFNFn.apply(x2.to(cdt), weights, selected, self.keys, self.bias, self.values, None,
+                                       self._spec(cdt), self._ep)
         return SparseFFNFn.apply(x2.to(cdt), weights, selected, self.keys, self.bias, self.values, None, self._spec(cdt))
 
     def forward(self, x, return_id_experts=False, return_full=True, *args, **kwargs):
@@ -362,7 +394,8 @@ class CompeteSMoE(MoE):
         gate_w, gate_idx, gate_softmax, gate_logits = self.router_policy(x2, cdt, x.dtype)
         if is_comp:
             spec = self._spec(cdt)
-            y_all = DenseFFNFn.apply(x2.to(cdt), self.keys, self.bias, self.values, None, spec)   # [E * t_pad, Dv]
+            keys, bias, values = self._all_expert_weights()
+            y_all = DenseFFNFn.apply(x2.to(cdt), keys, bias, values, None, spec)   # [E * t_pad, Dv]
             t_pad = y_all.shape[0] // E
             aff = AffinityFn.apply(y_all, E, T, t_pad, x.dtype == torch.bfloat16)
             aff_softmax = F.softmax(aff, dim=-1, dtype=torch.float32)

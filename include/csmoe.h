@@ -1,8 +1,9 @@
 /* csmoe.h — C ABI of libcsmoe.so: the B200 (sm_100a) kernels behind CompeteSMoE's sparse-MoE layer.
  *
  * Every entry point takes raw device pointers, sizes and a cudaStream_t (passed as void*), returns 0 on success or a
- * negative csmoe_status, never allocates device memory, never synchronises the host with the device and is therefore
- * CUDA-graph capturable.  The caller (PyTorch on the host side) owns all buffers.
+ * negative csmoe_status, never allocates device memory (except csmoe_ep_alloc, which exists to make IPC-exportable
+ * exchange buffers), never synchronises the host with the device and is therefore CUDA-graph capturable.  The caller
+ * (PyTorch on the host side) owns all other buffers.
  *
  * The reference (Fsoft-AIC/CompeteSMoE) has no native interface; each entry point below names the Python code it
  * replaces (paths relative to the reference root).  See INTEGRATION.md for the binding a maintainer would add.
@@ -174,6 +175,9 @@ typedef struct csmoe_gemm_args {
   int32_t row_tile;        /* ROWS, !dense: the row_tile the routing maps were built with (128 or 256); 256 lets the
                               CTA-pair (cta_group::2, 256 x 256 tile) kernel run */
   int32_t reserved;
+  const uint64_t* c_rows;  /* ROWS, plain epilogue: when non-NULL, output row r is stored at address c_rows[r] (0 = row
+                              skipped) instead of c + r*ldc -- the expert-parallel return path: the down projection
+                              writes each row straight into the source rank's buffer (peer memory).  c may be NULL. */
 } csmoe_gemm_args;
 
 int csmoe_grouped_gemm(const csmoe_gemm_args* args, void* stream);
@@ -203,6 +207,50 @@ int csmoe_affinity_fwd(const void* y, int32_t dtype, int32_t E, int64_t T, int64
 /* dy[e,t,d] (+)= daff[t,e] * sigmoid(y[e,t,d]) / D. accumulate: add into an existing dy. */
 int csmoe_affinity_bwd(const void* y, const float* daff, int32_t dtype, int32_t E, int64_t T, int64_t t_pad, int32_t D,
                        int32_t accumulate, void* dy, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ expert parallelism
+ * One process per GPU; rank r of P owns experts [r*E/P, (r+1)*E/P).  Exchange buffers are allocated by the library
+ * (cudaMalloc, so that they can be exported with CUDA IPC) and mapped into every peer once; after that dispatch and
+ * return are kernels that store straight into peer HBM over NVLink.  The reference has no counterpart: it is
+ * data-parallel only (moe_pretrain_model/framework/task/simple_task.py:403-413, moe_model/train/train.py:1474-1480).
+ * "peer arrays" below are HOST arrays of P device pointers, entry r = the same buffer on rank r (own rank: local ptr).
+ * These are the only entry points that allocate device memory (csmoe_ep_alloc) -- everything else is caller-owned. */
+#define CSMOE_EP_MAX_RANKS 16
+int csmoe_ep_ipc_handle_bytes(void);
+/* cudaMalloc + zero-fill `bytes`; writes csmoe_ep_ipc_handle_bytes() bytes of IPC handle to handle_out (may be NULL). */
+int csmoe_ep_alloc(int64_t bytes, void** ptr, void* handle_out);
+int csmoe_ep_open(const void* handle, void** ptr);  /* map a peer's allocation (enables peer access lazily) */
+int csmoe_ep_close(void* ptr);
+int csmoe_ep_free(void* ptr);
+/* Cross-rank barrier on the stream: flags = peer array of int32[P] flag vectors, epoch = this rank's device counter.
+ * Release/acquire at system scope: everything the calling rank stored to peer memory before the barrier is visible to
+ * the peers' kernels after it.  Every rank must issue the same sequence of barrier-containing calls. */
+int csmoe_ep_barrier(const void* const* flags, int32_t* epoch, int32_t rank, int32_t P, void* stream);
+/* Publish counts[E] (this rank's rows per expert, from csmoe_route_build) into every peer's counts_all[P][E], barrier,
+ * then derive: dest_base[E] = row in the owner's receive space where this rank's rows for expert e start;
+ * recv_counts[E/P], recv_pad_offsets[E/P + 1], tile_expert[row_cap/128] = padded expert-major layout (segments
+ * aligned to row_tile, rows ordered by source rank, then source order) of the rows this rank receives.
+ * row_cap >= csmoe_route_row_cap(P * n_slots_max, E/P, row_tile) is the static capacity of the receive buffers. */
+int csmoe_ep_exchange_plan(const int32_t* counts, const void* const* counts_all, const void* const* flags, int32_t* epoch,
+                           int32_t rank, int32_t P, int32_t E, int32_t row_tile, int64_t row_cap, int32_t* dest_base,
+                           int32_t* recv_counts, int32_t* recv_pad_offsets, int32_t* tile_expert, void* stream);
+/* Permute + send: row src[j / K] (scaled by slot_w[j] when given) of slot j goes to row
+ * dest_base[sel[j]] + (slot_to_row[j] - pad_offsets[sel[j]]) of peer sel[j] / experts_per_rank's recv buffer [row_cap, D];
+ * tags (peer array of int64[row_cap], may be NULL) receives (rank << 32 | j) for the return trip. */
+int csmoe_ep_dispatch(const void* src, int32_t dtype, int32_t D, int32_t K, int64_t n_slots, const int32_t* sel,
+                      const int32_t* slot_to_row, const int32_t* pad_offsets, const int32_t* dest_base,
+                      int32_t experts_per_rank, const float* slot_w, const void* const* recv, const void* const* tags,
+                      int32_t rank, int32_t P, void* stream);
+/* Receiver side, after the barrier that follows dispatch: c_rows[r] (may be NULL) = address of row `slot` of peer
+ * `src`'s return buffer ret[src] ([n_slots, ret_ld] of `dtype`) for valid rows, 0 for padding; and the padding rows of
+ * recv [row_cap, D] (may be NULL) are zeroed (the wgrad GEMM contracts over whole padded segments). */
+int csmoe_ep_row_ptrs(const int64_t* tags, const int32_t* tile_expert, const int32_t* recv_counts,
+                      const int32_t* recv_pad_offsets, int32_t experts_per_rank, int64_t row_cap, const void* const* ret,
+                      int64_t ret_ld, int32_t dtype, int32_t P, uint64_t* c_rows, void* recv, int32_t D, void* stream);
+/* Stand-alone return transfer (the grouped GEMM's c_rows epilogue does the same inside the down projection):
+ * row r of src [rows, ld] is copied to address dst_rows[r] unless that is 0. */
+int csmoe_ep_push_rows(const void* src, int32_t dtype, int64_t ld, int32_t D, int64_t rows, const uint64_t* dst_rows,
+                       void* stream);
 
 #ifdef __cplusplus
 }
