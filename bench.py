@@ -153,12 +153,15 @@ def run_reference_arm(a):
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
-def build_layer(device):
+def build_layer(device, ep_group=None):
     from competesmoe_b200.multimodal import CompeteSMoE
     torch.manual_seed(0)
     experts = nn.ModuleList([GLUExpert(D_MODEL, FFN) for _ in range(N_EXPERTS)])
     layer = CompeteSMoE(D_MODEL, D_MODEL, N_EXPERTS, TOP_K, experts, layer_args())
     layer = layer.to(device=device, dtype=torch.bfloat16)
+    if ep_group is not None:
+        layer.enable_expert_parallel(ep_group, max_tokens=TOKENS)   # this rank keeps E / P experts
+        torch.cuda.empty_cache()
     layer.total_steps, layer.step_warm = 2, 0
     layer.train()
     return layer
@@ -252,7 +255,19 @@ def run_ours(a):
     peak_tf, peak_src = (peaks["bf16_tflops"], "measured (MEASURED_PEAKS.json, burst)") if "bf16_tflops" in peaks else \
         (1590.0, "fallback (B200_PROFILING.md)")
 
-    layer = build_layer(device)
+    # N > 1: expert parallelism (north_star stage 6).  The 4 experts are sharded over EP groups of P = min(N, 4) ranks
+    # (N = 8: two replicas of an EP4 group); tokens stay data-parallel, 4096 per GPU (weak scaling).
+    ep_group, ep_p = None, 1
+    if dist_on and a.parallel != "replicas":
+        from competesmoe_b200.ep import EPGroup
+        ep_p = max(p for p in (1, 2, 4) if p <= world and world % p == 0 and N_EXPERTS % p == 0)
+        my_pg = None
+        for g0 in range(0, world, ep_p):
+            pg = dist.new_group(list(range(g0, g0 + ep_p)))
+            if g0 <= rank < g0 + ep_p:
+                my_pg = pg
+        ep_group = EPGroup(my_pg, device)
+    layer = build_layer(device, ep_group)
     params = [p for p in layer.parameters()]
     g = torch.Generator().manual_seed(1235 + rank)
     x_host = torch.randn(1, TOKENS, D_MODEL, generator=g).bfloat16().pin_memory()
@@ -310,7 +325,9 @@ def run_ours(a):
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_router, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "step": "router", "tokens_per_gpu": TOKENS,
-                       "parallelism": "single GPU" if world == 1 else f"{world} independent data-parallel replicas",
+                       "parallelism": "single GPU" if world == 1 else (
+                           f"EP{ep_p} x DP{world // ep_p}: experts sharded over NVLink peer memory, tokens data-parallel"
+                           if ep_group is not None else f"{world} independent data-parallel replicas"),
                        "l2": "per-step working set (0.6 GB of expert weights + 0.5 GB activations) exceeds the 126 MB L2; no flush"},
             "model_tflops": flops_per_token(False) * tok / (ms_router * 1e-3) / 1e12,
             "model_frac_of_peak": flops_per_token(False) * TOKENS / (ms_router * 1e-3) / 1e12 / peak_tf,
@@ -327,6 +344,8 @@ def run_ours(a):
             "cpu_baseline": cpu, "gpu_launches": launches, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
+    if ep_group is not None:
+        ep_group.close()
     if dist_on:
         dist.destroy_process_group()
 
@@ -337,6 +356,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--parallel", default="ep", choices=["ep", "replicas"],
+                    help="N > 1: expert-parallel groups (default) or N independent replicas of the layer")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3)
     if a.impl == "reference":
