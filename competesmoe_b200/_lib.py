@@ -62,6 +62,8 @@ _SIGNATURES = {
     "csmoe_cast_f32_bf16": (i32, [vp, vp, i64, vp]),
     "csmoe_affinity_fwd": (i32, [vp, i32, i32, i64, i64, i32, i32, vp, vp]),
     "csmoe_affinity_bwd": (i32, [vp, vp, i32, i32, i64, i64, i32, i32, vp, vp]),
+    "csmoe_diversity_fwd": (i32, [vp, i32, i64, i64, i32, i32, vp, vp, vp, vp, vp, vp]),
+    "csmoe_compete_bwd": (i32, [vp, i32, i32, i64, i64, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "csmoe_ep_ipc_handle_bytes": (i32, []),
     "csmoe_ep_alloc": (i32, [i64, C.POINTER(vp), vp]),
     "csmoe_ep_open": (i32, [vp, C.POINTER(vp)]),

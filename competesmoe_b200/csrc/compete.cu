@@ -69,6 +69,157 @@ affinity_bwd_kernel(const T* __restrict__ y, const float* __restrict__ daff, int
   }
 }
 
+
+// ---- diversity loss of the selected experts' outputs (moe_model/model/moe/competesmoe.py:180-218,
+// moe_pretrain_model/layers/moe/competesmoe.py:330-372): per token, the K x K cosine-similarity matrix of its selected
+// rows; loss = sum of the off-diagonal entries / (T*K*K).  One warp per token; the K rows are read once.
+constexpr int kMaxK = 8;
+
+template <typename T, int KT>
+__global__ void __launch_bounds__(kWarps * 32)
+diversity_fwd_kernel(const T* __restrict__ y, long long Tn, long long t_pad, int D, int K,
+                     const int32_t* __restrict__ sel, float* __restrict__ inv_norm, float* __restrict__ sim,
+                     float* __restrict__ partial) {
+  const int lane = threadIdx.x & 31;
+  for (long long t = static_cast<long long>(blockIdx.x) * kWarps + (threadIdx.x >> 5); t < Tn;
+       t += static_cast<long long>(gridDim.x) * kWarps) {
+    const T* rows[KT];
+#pragma unroll
+    for (int k = 0; k < KT; ++k) rows[k] = y + (static_cast<long long>(k < K ? sel[t * K + k] : 0) * t_pad + t) * D;
+    float dot[KT * (KT + 1) / 2];
+#pragma unroll
+    for (int i = 0; i < KT * (KT + 1) / 2; ++i) dot[i] = 0.f;
+    for (int c = lane * 8; c < D; c += 256) {
+      float v[KT][8];
+#pragma unroll
+      for (int k = 0; k < KT; ++k)
+        if (k < K) load8(rows[k] + c, v[k]);
+#pragma unroll
+      for (int k = 0, i = 0; k < KT; ++k)
+#pragma unroll
+        for (int l = k; l < KT; ++l, ++i)
+          if (l < K) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dot[i] = fmaf(v[k][j], v[l][j], dot[i]);
+          }
+    }
+#pragma unroll
+    for (int i = 0; i < KT * (KT + 1) / 2; ++i)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) dot[i] += __shfl_xor_sync(0xffffffffu, dot[i], o);
+    float inv[KT];
+#pragma unroll
+    for (int k = 0, i = 0; k < KT; ++k) {
+      inv[k] = 1.f / fmaxf(sqrtf(dot[i]), 1e-12f);   // F.normalize: x / max(||x||, eps)
+      i += KT - k;
+    }
+    float off = 0.f;
+#pragma unroll
+    for (int k = 0, i = 0; k < KT; ++k)
+#pragma unroll
+      for (int l = k; l < KT; ++l, ++i)
+        if (l < K) {
+          const float s = dot[i] * inv[k] * inv[l];
+          if (lane == 0) {
+            sim[(t * K + k) * K + l] = s;
+            sim[(t * K + l) * K + k] = s;
+          }
+          if (l != k) off += 2.f * s;
+        }
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < KT; ++k)
+        if (k < K) inv_norm[t * K + k] = inv[k];
+      partial[t] = off;
+    }
+  }
+}
+
+// Fixed-order sum of partial[0..n) * scale -> out[0] (one block: deterministic).
+__global__ void __launch_bounds__(1024) sum_scale_kernel(const float* __restrict__ partial, long long n, float scale,
+                                                         float* __restrict__ out) {
+  __shared__ float sh[1024];
+  float s = 0.f;
+  for (long long i = threadIdx.x; i < n; i += 1024) s += partial[i];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = sh[0] * scale;
+}
+
+// ---- one pass that writes the whole gradient of the dense expert outputs in a competition step:
+//   dy[e,t,:] = daff[t,e] * sigmoid(y[e,t,:]) / D                                   (neural-response score)
+//             + [e == sel[t,k]] * ( w[t,k] * dout[t,:]                              (gate-weighted combine)
+//                                   + g_div * 2/(T*K*K) * inv_k * (sum_{l != k} n_l - n_k * sum_{l != k} sim[k,l]) )
+// with n_k = y[sel_k,t,:] * inv_k.  Rows t in [T, t_pad) are zeroed (the wgrad GEMMs contract over padded rows).
+// Replaces three autograd branches (affinity, gather + normalize + bmm, index_copy) and the adds that joined them.
+template <typename T, int KT>
+__global__ void __launch_bounds__(kWarps * 32)
+compete_bwd_kernel(const T* __restrict__ y, int E, long long Tn, long long t_pad, int D, int K,
+                   const float* __restrict__ daff, const int32_t* __restrict__ sel, const float* __restrict__ w,
+                   const T* __restrict__ dout, const float* __restrict__ inv_norm, const float* __restrict__ sim,
+                   const float* __restrict__ g_div, T* __restrict__ dy) {
+  const int lane = threadIdx.x & 31;
+  const float inv_d = 1.f / static_cast<float>(D);
+  const float gd = g_div ? g_div[0] * 2.f / (static_cast<float>(Tn) * K * K) : 0.f;
+  for (long long t = static_cast<long long>(blockIdx.x) * kWarps + (threadIdx.x >> 5); t < t_pad;
+       t += static_cast<long long>(gridDim.x) * kWarps) {
+    if (t >= Tn) {
+      const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int e = 0; e < E; ++e)
+        for (int c = lane * 8; c < D; c += 256) store8(dy + (e * t_pad + t) * D + c, z);
+      continue;
+    }
+    int se[KT];
+    float wk[KT], ik[KT], ak[KT], rs[KT];
+#pragma unroll
+    for (int k = 0; k < KT; ++k) {
+      se[k] = k < K ? sel[t * K + k] : -1;
+      wk[k] = (k < K && dout) ? w[t * K + k] : 0.f;
+      ik[k] = (k < K && g_div) ? inv_norm[t * K + k] : 0.f;
+      ak[k] = gd * ik[k];
+      rs[k] = 0.f;
+      if (k < K && g_div)
+        for (int l = 0; l < K; ++l)
+          if (l != k) rs[k] += sim[(t * K + k) * K + l];
+    }
+    for (int c = lane * 8; c < D; c += 256) {
+      float nsum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, g[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (g_div) {
+#pragma unroll
+        for (int k = 0; k < KT; ++k)
+          if (k < K) {
+            float v[8];
+            load8(y + (static_cast<long long>(se[k]) * t_pad + t) * D + c, v);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) nsum[j] = fmaf(v[j], ik[k], nsum[j]);
+          }
+      }
+      if (dout) load8(dout + t * D + c, g);
+#pragma unroll 4
+      for (int e = 0; e < E; ++e) {
+        const long long off = (e * t_pad + t) * D + c;
+        float v[8], o[8];
+        load8(y + off, v);
+        const float ga = daff ? daff[t * E + e] * inv_d : 0.f;
+        float wsel = 0.f, asel = 0.f, isel = 0.f, rsel = 0.f;
+#pragma unroll
+        for (int k = 0; k < KT; ++k)
+          if (se[k] == e) { wsel = wk[k]; asel = ak[k]; isel = ik[k]; rsel = rs[k]; }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float n = v[j] * isel;
+          o[j] = ga * sigmoid_sp(v[j]) + wsel * g[j] + asel * (nsum[j] - n - n * rsel);
+        }
+        store8(dy + off, o);
+      }
+    }
+  }
+}
+
 inline unsigned row_grid(long long rows) {
   const long long blocks = (rows + kWarps - 1) / kWarps;
   const long long cap = static_cast<long long>(num_sms() > 0 ? num_sms() : 148) * 16;
@@ -116,6 +267,56 @@ extern "C" int csmoe_affinity_bwd(const void* y, const float* daff, int32_t dtyp
   } else {
     CSMOE_CHECK_ARG(false, "csmoe_affinity_bwd: unsupported dtype %d", dtype);
   }
+  CSMOE_CHECK_LAUNCH();
+  return CSMOE_OK;
+}
+
+#define DISPATCH_DTYPE_K(dtype, K, ...)                                      \
+  if ((dtype) == CSMOE_BF16) {                                               \
+    using T = __nv_bfloat16;                                                 \
+    if ((K) <= 2) { constexpr int KT = 2; __VA_ARGS__; }                     \
+    else if ((K) <= 4) { constexpr int KT = 4; __VA_ARGS__; }                \
+    else { constexpr int KT = 8; __VA_ARGS__; }                              \
+  } else if ((dtype) == CSMOE_F32) {                                         \
+    using T = float;                                                         \
+    if ((K) <= 2) { constexpr int KT = 2; __VA_ARGS__; }                     \
+    else if ((K) <= 4) { constexpr int KT = 4; __VA_ARGS__; }                \
+    else { constexpr int KT = 8; __VA_ARGS__; }                              \
+  } else {                                                                   \
+    CSMOE_CHECK_ARG(false, "unsupported dtype %d", (dtype));                 \
+  }
+
+extern "C" int csmoe_diversity_fwd(const void* y, int32_t dtype, int64_t T_, int64_t t_pad, int32_t D, int32_t K,
+                                   const int32_t* sel, float* inv_norm, float* sim, float* partial, float* loss,
+                                   void* stream_) {
+  CSMOE_CHECK_ARG(y && sel && inv_norm && sim && partial && loss, "csmoe_diversity_fwd: NULL pointer");
+  CSMOE_CHECK_ARG(D > 0 && D % 8 == 0 && K >= 1 && K <= kMaxK && t_pad >= T_,
+                  "csmoe_diversity_fwd: D %% 8 == 0, 1 <= K <= %d, t_pad >= T", kMaxK);
+  cudaStream_t stream = as_stream(stream_);
+  if (T_ > 0) {
+    DISPATCH_DTYPE_K(dtype, K, (diversity_fwd_kernel<T, KT><<<row_grid(T_), kWarps * 32, 0, stream>>>(
+                                   static_cast<const T*>(y), T_, t_pad, D, K, sel, inv_norm, sim, partial)));
+    CSMOE_CHECK_LAUNCH();
+  }
+  const float scale = T_ > 0 ? 1.f / (static_cast<float>(T_) * K * K) : 0.f;
+  sum_scale_kernel<<<1, 1024, 0, stream>>>(partial, T_, scale, loss);
+  CSMOE_CHECK_LAUNCH();
+  return CSMOE_OK;
+}
+
+extern "C" int csmoe_compete_bwd(const void* y, int32_t dtype, int32_t E, int64_t T_, int64_t t_pad, int32_t D,
+                                 int32_t K, const float* daff, const int32_t* sel, const float* w, const void* dout,
+                                 const float* inv_norm, const float* sim, const float* g_div, void* dy, void* stream_) {
+  CSMOE_CHECK_ARG(y && sel && dy, "csmoe_compete_bwd: NULL pointer");
+  CSMOE_CHECK_ARG(!dout || w, "csmoe_compete_bwd: dout needs the combine weights");
+  CSMOE_CHECK_ARG(!g_div || (inv_norm && sim), "csmoe_compete_bwd: g_div needs the saved norms and similarities");
+  CSMOE_CHECK_ARG(E >= 1 && D > 0 && D % 8 == 0 && K >= 1 && K <= kMaxK && t_pad >= T_,
+                  "csmoe_compete_bwd: D %% 8 == 0, 1 <= K <= %d, t_pad >= T", kMaxK);
+  if (t_pad == 0) return CSMOE_OK;
+  cudaStream_t stream = as_stream(stream_);
+  DISPATCH_DTYPE_K(dtype, K, (compete_bwd_kernel<T, KT><<<row_grid(t_pad), kWarps * 32, 0, stream>>>(
+                                 static_cast<const T*>(y), E, T_, t_pad, D, K, daff, sel, w, static_cast<const T*>(dout),
+                                 inv_norm, sim, g_div, static_cast<T*>(dy))));
   CSMOE_CHECK_LAUNCH();
   return CSMOE_OK;
 }

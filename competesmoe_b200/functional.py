@@ -5,6 +5,8 @@
   DenseFFNFn    every expert on every token (competition step)           reference: competesmoe.py:240-245 / :399-403
   AffinityFn    mean softplus score of each (token, expert)              reference: competesmoe.py:243 / :403
   SelectCombineFn  gate-weighted sum of the selected dense outputs        reference: recomputed by compute_moe (:374)
+  CompeteTailFn everything downstream of the dense expert outputs of a competition step (score, top-k, combine,
+                diversity loss) with ONE backward kernel for d(dense outputs)  reference: competesmoe.py:219-259,:371-374
 
 Stacked expert weights use one of two layouts: "nk" = [E, n, k] (nn.Linear.weight) or "kn" = [E, k, n] (sigma-MoE
 keys / values).  All GEMM operands are bfloat16; fp32 accumulation happens in TMEM.
@@ -273,3 +275,54 @@ class GatherRowsFn(Function):
         dy = torch.zeros(ctx.shape, dtype=g.dtype, device=g.device)
         dy.index_copy_(0, rows, g.reshape(rows.numel(), -1))
         return dy, None, None
+
+
+class CompeteTailFn(Function):
+    """y [E * t_pad, D] -> (aff [T,E] f32, w [T,K] f32, idx [T,K] i32, out [T,D], diversity loss [] f32).
+
+    The competition step's consumers of the dense expert outputs in one autograd node: neural-response score
+    (competesmoe.py:243), top-k + renormalisation (:249-254, weights stay attached to the scores), gate-weighted sum of
+    the selected outputs (what compute_moe recomputes at :374) and the diversity loss of the selected outputs (:180-218).
+    Backward joins the three gradient sources of y in a single kernel (csmoe_compete_bwd) instead of three autograd
+    branches summed in the activation dtype."""
+
+    @staticmethod
+    def forward(ctx, y, num_experts: int, T: int, t_pad: int, top_k: int, sigmoid: bool, x_dtype: torch.dtype,
+                spec: FFNSpec):
+        eager_bf16 = x_dtype == torch.bfloat16
+        aff = ops.affinity_fwd(y, num_experts, T, t_pad, eager_bf16)
+        w, idx = ops.topk_renorm(aff, top_k, sigmoid=sigmoid, round_dtype=x_dtype, round_out=eager_bf16)
+        rows = (idx.long() * t_pad + torch.arange(T, device=idx.device).unsqueeze(1)).to(torch.int32).reshape(-1)
+        out = ops.combine_fwd(y, rows, idx.reshape(-1), w, T, top_k, round_each=spec.round_each, round_w=spec.round_w)
+        div, inv_norm, sim = ops.diversity_fwd(y, idx, T, t_pad)
+        ctx.save_for_backward(y, aff, w, idx, rows, inv_norm, sim)
+        ctx.dims = (num_experts, T, t_pad, top_k, sigmoid, spec)
+        ctx.mark_non_differentiable(idx)
+        return aff, w, idx, out, div
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, daff, dw_ext, _, dout, ddiv):
+        y, aff, w, idx, rows, inv_norm, sim = ctx.saved_tensors
+        E, T, t_pad, K, sigmoid, spec = ctx.dims
+        dw = dw_ext
+        if dout is not None:
+            dout = dout.contiguous().to(y.dtype)
+            dwc = ops.combine_bwd_w(y, dout, rows, T, K)
+            dw = dwc if dw is None else dw + dwc
+        if dw is not None:
+            # top-k renormalisation backward: w = v / sum(v), v = scores (or sigmoid(scores)) at idx
+            li = idx.long()
+            v = torch.gather(aff, 1, li)
+            if sigmoid:
+                v = torch.sigmoid(v)
+            dv = (dw - (dw * w).sum(-1, keepdim=True)) / v.sum(-1, keepdim=True)
+            if sigmoid:
+                dv = dv * v * (1 - v)
+            ds = torch.zeros_like(aff).scatter_add_(1, li, dv)
+            daff = ds if daff is None else daff + ds
+        wu = w.to(torch.bfloat16).float() if spec.round_w else w
+        dy = ops.compete_bwd(y, E, T, t_pad, idx, daff=daff, w=wu if dout is not None else None, dout=dout,
+                             inv_norm=inv_norm if ddiv is not None else None, sim=sim if ddiv is not None else None,
+                             g_div=ddiv)
+        return dy, None, None, None, None, None, None, None

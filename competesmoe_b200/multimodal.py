@@ -18,7 +18,7 @@ from torch.autograd.function import once_differentiable
 
 from . import experts as X
 from . import ops
-from .functional import AffinityFn, DenseFFNFn, FFNSpec, GateFn, GatherRowsFn, SelectCombineFn, SparseFFNFn
+from .functional import CompeteTailFn, DenseFFNFn, FFNSpec, GateFn, SparseFFNFn
 from .schedule import make_layer_schedule
 
 MOE_REGISTRY: Dict[str, type] = {}
@@ -273,21 +273,20 @@ class CompeteSMoE(MoeLayer):
             w1, b1, w2, b2 = self._all_expert_weights(w1, b1, w2, b2)
             y_all = DenseFFNFn.apply(x2, w1, b1, w2, b2, spec)                       # [E * t_pad, Dout]
             t_pad = y_all.shape[0] // E
-            aff = AffinityFn.apply(y_all, E, T, t_pad, x.dtype == torch.bfloat16)                             # [T, E] f32 (x.dtype-rounded)
+            # score, top-k, combine (the selected experts' outputs are reused from the dense pass instead of being
+            # recomputed as compute_moe does at competesmoe.py:374) and diversity loss: one autograd node
+            aff, aff_w, aff_idx, out, diversity_loss = CompeteTailFn.apply(
+                y_all, E, T, t_pad, K, bool(getattr(self.args, "norm_sigmoid", False)), x.dtype, spec)
             aff_softmax = F.softmax(aff, dim=-1, dtype=torch.float32)
-            aff_w, aff_idx = TopkRenormFn.apply(aff, K, bool(getattr(self.args, "norm_sigmoid", False)), x.dtype)
             li = aff_idx.long()
             if getattr(self.args, "hybrid", False):
                 routerloss = self.router_loss(gate_softmax, aff_softmax.detach()) + self.router_loss(
                     torch.gather(gate_softmax, -1, li), torch.gather(aff_softmax, -1, li).detach()) * self.args.router_theta
             else:
                 routerloss = self.router_loss(gate_softmax, aff_softmax.detach())
-            diversity_loss = self.experts_diversity_loss(GatherRowsFn.apply(y_all, aff_idx, t_pad))
             balance_loss = self.balanceloss(aff_idx.view(B, N, K), aff_softmax.view(B, N, E))
             auxiliary_loss = routerloss * self.args.router_loss_coef + diversity_loss * self.args.diversity_loss_coef + \
                 balance_loss * self.args.bal_comp_loss_coef
-            # the selected experts' outputs were already computed by the dense pass: reuse instead of recomputing
-            out = SelectCombineFn.apply(y_all, aff_w, aff_idx, t_pad, spec)
             self.last_routing = (aff_idx.view(B, N, K), aff_w.detach().view(B, N, K))
             infor_aux = {"balance_loss": balance_loss.detach().clone(), "diversity_loss": diversity_loss.detach().clone(),
                          "routerloss": routerloss.detach().clone()}

@@ -19,7 +19,7 @@ from ._lib import (ACT_GELU, ACT_GELU_TANH, ACT_NONE, ACT_RELU, ACT_SILU, ACT_SI
 __all__ = [
     "Route", "route_build", "router_fwd", "topk_renorm", "gather_rows", "combine_fwd", "combine_bwd_w",
     "scatter_reduce", "gemm_rows", "gemm_reduce", "act_fwd", "act_bwd", "bias_grad", "cast_bf16", "affinity_fwd",
-    "affinity_bwd", "ACT_NONE", "ACT_RELU", "ACT_GELU", "ACT_GELU_TANH", "ACT_SILU", "ACT_SILU_GLU",
+    "affinity_bwd", "diversity_fwd", "compete_bwd", "ACT_NONE", "ACT_RELU", "ACT_GELU", "ACT_GELU_TANH", "ACT_SILU", "ACT_SILU_GLU",
 ]
 
 launch_count = 0  # number of libcsmoe kernels launched so far (bench.py reports the delta over its timed region)
@@ -415,3 +415,40 @@ def affinity_bwd(y: torch.Tensor, daff: torch.Tensor, num_experts: int, T: int, 
         out = torch.zeros_like(y) if t_pad != T else torch.empty_like(y)
     _call("csmoe_affinity_bwd", _p(y), _p(daff), _dt(y), num_experts, T, t_pad, D, 1 if acc else 0, _p(out), _stream())
     return out
+
+
+def diversity_fwd(y: torch.Tensor, sel: torch.Tensor, T: int, t_pad: int):
+    """y [E * t_pad, D], sel [T, K] i32 -> (loss [] f32, inv_norm [T,K] f32, sim [T,K,K] f32): mean off-diagonal cosine
+    similarity between each token's K selected expert outputs (competesmoe.py:180-218)."""
+    _cuda(y, sel)
+    assert sel.dtype == torch.int32 and sel.is_contiguous()
+    K = sel.shape[1]
+    D = y.shape[-1]
+    f32 = dict(dtype=torch.float32, device=y.device)
+    inv_norm = torch.empty(T, K, **f32)
+    sim = torch.empty(T, K, K, **f32)
+    partial = torch.empty(max(T, 1), **f32)
+    loss = torch.empty((), **f32)
+    _call("csmoe_diversity_fwd", _p(y), _dt(y), T, t_pad, D, K, _p(sel), _p(inv_norm), _p(sim), _p(partial), _p(loss),
+          _stream(), kernels=2 if T > 0 else 1)
+    return loss, inv_norm, sim
+
+
+def compete_bwd(y: torch.Tensor, num_experts: int, T: int, t_pad: int, sel: torch.Tensor, *,
+                daff: Optional[torch.Tensor] = None, w: Optional[torch.Tensor] = None,
+                dout: Optional[torch.Tensor] = None, inv_norm: Optional[torch.Tensor] = None,
+                sim: Optional[torch.Tensor] = None, g_div: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Gradient of the dense expert outputs y [E * t_pad, D] from the three consumers of a competition step (score,
+    combine, diversity loss) in one pass; see csmoe_compete_bwd in include/csmoe.h."""
+    _cuda(y, sel, daff, w, dout, inv_norm, sim, g_div)
+    K = sel.shape[1]
+    D = y.shape[-1]
+    f32c = lambda t: None if t is None else t.contiguous().float()  # noqa: E731
+    daff, w, g_div = f32c(daff), f32c(w), f32c(g_div)
+    if dout is not None:
+        dout = dout.contiguous()
+        assert dout.dtype == y.dtype and dout.shape == (T, D)
+    dy = torch.empty_like(y)
+    _call("csmoe_compete_bwd", _p(y), _dt(y), num_experts, T, t_pad, D, K, _p(daff), _p(sel), _p(w), _p(dout),
+          _p(inv_norm), _p(sim), _p(g_div), _p(dy), _stream())
+    return dy

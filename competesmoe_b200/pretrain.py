@@ -16,7 +16,7 @@ import torch
 import torch.nn.functional as F
 
 from . import ops
-from .functional import AffinityFn, DenseFFNFn, FFNSpec, GateFn, GatherRowsFn, SelectCombineFn, SparseFFNFn
+from .functional import CompeteTailFn, DenseFFNFn, FFNSpec, GateFn, SparseFFNFn
 from .multimodal import TopkRenormFn
 from .schedule import make_layer_schedule
 
@@ -397,13 +397,10 @@ class CompeteSMoE(MoE):
             keys, bias, values = self._all_expert_weights()
             y_all = DenseFFNFn.apply(x2.to(cdt), keys, bias, values, None, spec)   # [E * t_pad, Dv]
             t_pad = y_all.shape[0] // E
-            aff = AffinityFn.apply(y_all, E, T, t_pad, x.dtype == torch.bfloat16)
+            aff, aff_w, aff_idx, out, diver = CompeteTailFn.apply(y_all, E, T, t_pad, K, False, x.dtype, spec)
+            self.nb_diver += K * (K - 1) * T
             aff_softmax = F.softmax(aff, dim=-1, dtype=torch.float32)
-            aff_w, aff_idx = TopkRenormFn.apply(aff, K, False, x.dtype)
             li = aff_idx.long()
-            out = SelectCombineFn.apply(y_all, aff_w, aff_idx, t_pad, spec)
-            topk_out = GatherRowsFn.apply(y_all, aff_idx, t_pad)
-            diver = self.experts_diversity_loss(topk_out)
             self.add_reg(lambda: diver * a.balance_loss_coef_comp / 2, self.name_moe + "_comp_diver_loss")
             if a.balance_affinity:
                 bal = self.entropy_balance(aff_softmax.view(*lead, E))

@@ -208,6 +208,21 @@ int csmoe_affinity_fwd(const void* y, int32_t dtype, int32_t E, int64_t T, int64
 int csmoe_affinity_bwd(const void* y, const float* daff, int32_t dtype, int32_t E, int64_t T, int64_t t_pad, int32_t D,
                        int32_t accumulate, void* dy, void* stream);
 
+/* Diversity loss of the selected experts' outputs (moe_model/.../competesmoe.py:180-218; moe_pretrain_model/.../
+ * competesmoe.py:330-372): per token the K x K cosine-similarity matrix of rows y[sel[t,k], t, :] (fp32 math,
+ * F.normalize eps 1e-12); loss[0] = sum of off-diagonal entries / (T*K*K), reduced in a fixed order.
+ * Saved for backward: inv_norm [T,K], sim [T,K,K]; partial [T] is scratch. */
+int csmoe_diversity_fwd(const void* y, int32_t dtype, int64_t T, int64_t t_pad, int32_t D, int32_t K, const int32_t* sel,
+                        float* inv_norm, float* sim, float* partial, float* loss, void* stream);
+/* Whole gradient of the dense expert outputs y[E, t_pad, D] of a competition step in one pass (replaces the autograd
+ * of competition_policy + compute_moe + experts_diversity_loss, moe_model/.../competesmoe.py:219-259,:371-374):
+ *   dy[e,t,:] = daff[t,e] * sigmoid(y) / D + [e == sel[t,k]] * (w[t,k] * dout[t,:] + d(diversity)/dy * g_div[0]).
+ * daff [T,E], (w [T,K], dout [T,D] of y's dtype), (inv_norm, sim, g_div = device scalar) may each be NULL = that
+ * term is absent.  Rows t in [T, t_pad) of dy are zeroed. */
+int csmoe_compete_bwd(const void* y, int32_t dtype, int32_t E, int64_t T, int64_t t_pad, int32_t D, int32_t K,
+                      const float* daff, const int32_t* sel, const float* w, const void* dout, const float* inv_norm,
+                      const float* sim, const float* g_div, void* dy, void* stream);
+
 /* ------------------------------------------------------------------------------------------------ expert parallelism
  * One process per GPU; rank r of P owns experts [r*E/P, (r+1)*E/P).  Exchange buffers are allocated by the library
  * (cudaMalloc, so that they can be exported with CUDA IPC) and mapped into every peer once; after that dispatch and

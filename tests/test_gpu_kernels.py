@@ -346,3 +346,44 @@ def test_affinity_fwd_bwd(ops, dtype):
     assert_close_rms(aff, aff_ref.detach(), tol, "affinity")
     dy = ops.affinity_bwd(y.view(E * t_pad, D).to(DEV), daff.to(DEV), E, T, t_pad)
     assert_close_rms(dy.view(E, t_pad, D), yr.grad, tol, "affinity bwd")
+
+
+# ------------------------------------------------------------------------------------------------ competition tail
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("E,K,T,t_pad,D", [(4, 2, 300, 512, 1152), (8, 1, 5, 256, 64), (64, 8, 130, 256, 1024),
+                                           (6, 3, 257, 512, 264)])
+def test_diversity_and_fused_competition_backward(ops, dtype, E, K, T, t_pad, D):
+    """csmoe_diversity_fwd / csmoe_compete_bwd against autograd of the reference formulas (competesmoe.py:180-259)."""
+    g = torch.Generator().manual_seed(E * 1000 + K)
+    y = torch.randn(E, t_pad, D, generator=g).to(dtype).to(DEV)
+    scores = torch.rand(T, E, generator=g)
+    sel = scores.topk(K, dim=-1).indices.int().to(DEV)
+    w = torch.rand(T, K, generator=g).to(DEV)
+    daff = torch.randn(T, E, generator=g).to(DEV)
+    dout = torch.randn(T, D, generator=g).to(dtype).to(DEV)
+    g_div = torch.tensor(0.7, device=DEV)
+
+    loss, inv_norm, sim = ops.diversity_fwd(y.view(E * t_pad, D), sel, T, t_pad)
+    dy = ops.compete_bwd(y.view(E * t_pad, D), E, T, t_pad, sel, daff=daff, w=w, dout=dout, inv_norm=inv_norm, sim=sim,
+                         g_div=g_div).view(E, t_pad, D)
+
+    yr = y.float().requires_grad_(True)
+    tok = torch.arange(T, device=DEV).unsqueeze(1)
+    top = yr[sel.long(), tok]                                             # [T, K, D]
+    nrm = F.normalize(top, p=2, dim=-1)
+    simr = torch.bmm(nrm, nrm.transpose(1, 2))
+    lossr = (simr * (1 - torch.eye(K, device=DEV))).mean()
+    aff = F.softplus(yr[:, :T]).mean(-1).t()                              # [T, E]
+    out = (w.unsqueeze(-1) * top).sum(1)
+    total = (aff * daff).sum() + (out * dout.float()).sum() + lossr * g_div
+    (dyr,) = torch.autograd.grad(total, yr)
+
+    assert abs(loss.item() - lossr.item()) < 1e-5 + 1e-4 * abs(lossr.item())
+    torch.testing.assert_close(sim, simr.detach(), rtol=1e-4, atol=1e-5)
+    assert bool((dy[:, T:] == 0).all())
+    tol = 2e-2 if dtype == torch.bfloat16 else 1e-4
+    assert_close_rms(dy.float(), dyr, rtol=tol, what="d(dense outputs)")
+    # each term on its own (NULL pointers switch the others off)
+    only_aff = ops.compete_bwd(y.view(E * t_pad, D), E, T, t_pad, sel, daff=daff).view(E, t_pad, D)
+    (ref_aff,) = torch.autograd.grad((F.softplus(yr[:, :T]).mean(-1).t() * daff).sum(), yr)
+    assert_close_rms(only_aff.float(), ref_aff, rtol=tol, what="score term")
