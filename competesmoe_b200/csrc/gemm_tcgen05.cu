@@ -57,7 +57,20 @@ struct KParams {
   long long ldpre;
   long long c_expert_stride;
   long long total_tiles;
+  int dbg_mode;       // tuning experiments (CSMOE_GEMM_DBG): 1 = no TMA loads after the first pipeline fill, 2 = no MMAs
+  int direct_epi;     // 1 = register-direct (row per thread) epilogue stores instead of the staged, coalesced ones
+  unsigned long long* stats;  // debug (CSMOE_GEMM_STATS=1): per CTA {producer wait, mma wait full, mma wait tempty, epilogue, total, tiles}
 };
+
+__device__ __forceinline__ void timed_wait(uint32_t bar, uint32_t parity, bool on, unsigned long long& acc) {
+  if (!on) {
+    ptx::mbar_wait(bar, parity);
+    return;
+  }
+  const long long t0 = clock64();
+  ptx::mbar_wait(bar, parity);
+  acc += static_cast<unsigned long long>(clock64() - t0);
+}
 
 constexpr int kEpiPlain = 0, kEpiGluFwd = 1, kEpiActBwd = 2, kEpiGluBwd = 3;
 
@@ -209,16 +222,17 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, const Tile& ti, 
     // TMEM columns [0,128) hold the gate and [128,256) the up projection of output columns nb*128 .. +128.
     // z = (gate | up) is stored for the backward pass, h = up * silu(gate) feeds the down projection
     // (Phi3MLP; each intermediate rounded to bf16 like the eager reference).
-    if constexpr (BN == 256) {
+    if constexpr (BN >= 256) {
+      constexpr int kGate = BN / 2;          // TMEM columns [0, kGate) = gate, [kGate, BN) = up, of kGate output columns
       __nv_bfloat16* h_row = reinterpret_cast<__nv_bfloat16*>(p.c) + out_row * p.ldc;
       __nv_bfloat16* z_row = reinterpret_cast<__nv_bfloat16*>(p.preact) + out_row * p.ldpre;
 #pragma unroll 1
-      for (int chunk = half * 2; chunk < half * 2 + 2; ++chunk) {
+      for (int chunk = half * (kGate / 64); chunk < (half + 1) * (kGate / 64); ++chunk) {
         uint32_t vg[32], vu[32];
         ptx::tmem_ld_32x32b_x32(t_row + chunk * 32, vg);
-        ptx::tmem_ld_32x32b_x32(t_row + 128 + chunk * 32, vu);
+        ptx::tmem_ld_32x32b_x32(t_row + kGate + chunk * 32, vu);
         ptx::tmem_ld_wait();
-        const int col0 = ti.nb * 128 + chunk * 32;
+        const int col0 = ti.nb * kGate + chunk * 32;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           const int col = col0 + g * 8;
@@ -281,6 +295,242 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, const Tile& ti, 
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ staged epilogue
+// tcgen05.ld hands every thread one output ROW (lane = TMEM lane), so storing from registers makes each warp-level
+// store touch 32 different rows, 16 bytes each: 32 partial-sector L2 writes per instruction.  The staged epilogue
+// instead transposes 32-row x 32-column groups through a per-warp shared-memory tile (4 KiB, 16-byte chunks
+// XOR-swizzled so both directions are bank-conflict free) and writes / reads global memory with 64- or 128-byte
+// contiguous row segments, several rows per instruction.  The same tile stages the saved pre-activation z that the
+// backward epilogues read.
+constexpr int kStageTileBytes = 32 * 128;
+
+// Row pitch P = 32 columns * element size: 64 (bf16) or 128 (fp32) bytes.
+template <int P>
+__device__ __forceinline__ uint32_t stg_addr(uint32_t stg, int row, int chunk) {
+  if (P == 128) return stg + row * 128 + ((chunk ^ (row & 7)) << 4);
+  return stg + row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4);
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ unsigned long long shfl_u64(unsigned long long v, int src) {
+  const uint32_t lo = __shfl_sync(0xffffffffu, static_cast<uint32_t>(v), src);
+  const uint32_t hi = __shfl_sync(0xffffffffu, static_cast<uint32_t>(v >> 32), src);
+  return (static_cast<unsigned long long>(hi) << 32) | lo;
+}
+
+// This thread's 32 values f[] (one row, 32 consecutive columns) -> global: row r of the group goes to byte address
+// row_base(r) + col_byte; row_base is held by lane r (0 = row not stored).  `valid_cols` <= 32 columns are written.
+template <bool FP32>
+__device__ __forceinline__ void staged_store32(uint32_t stg, int lane, const float (&f)[32], unsigned long long my_row_base,
+                                               long long col_byte, int valid_cols) {
+  constexpr int P = FP32 ? 128 : 64;
+  constexpr int kChunks = P / 16;          // 16-byte chunks per row
+  constexpr int kRowsPerIt = 32 / kChunks;  // rows covered by one warp-wide 16-byte access
+  if (FP32) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      sts128(stg_addr<P>(stg, lane, c), __float_as_uint(f[4 * c]), __float_as_uint(f[4 * c + 1]),
+             __float_as_uint(f[4 * c + 2]), __float_as_uint(f[4 * c + 3]));
+  } else {
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      sts128(stg_addr<P>(stg, lane, c), pack_bf16(f[8 * c], f[8 * c + 1]), pack_bf16(f[8 * c + 2], f[8 * c + 3]),
+             pack_bf16(f[8 * c + 4], f[8 * c + 5]), pack_bf16(f[8 * c + 6], f[8 * c + 7]));
+  }
+  __syncwarp();
+  const int chunk = lane % kChunks;
+  const bool col_ok = chunk * (FP32 ? 4 : 8) < valid_cols;
+#pragma unroll
+  for (int it = 0; it < 32 / kRowsPerIt; ++it) {
+    const int r = it * kRowsPerIt + lane / kChunks;
+    const unsigned long long base = shfl_u64(my_row_base, r);
+    const uint4 v = lds128(stg_addr<P>(stg, r, chunk));
+    if (base != 0ull && col_ok) *reinterpret_cast<uint4*>(base + col_byte + chunk * 16) = v;
+  }
+  __syncwarp();
+}
+
+// Saved bf16 pre-activations: 32 rows x 32 columns from global (row r at byte address row_base(r) + col_byte, held by
+// lane r; 0 = row absent -> zeros) into this thread's z[32] (its own row).
+__device__ __forceinline__ void staged_load32_bf16(uint32_t stg, int lane, float (&z)[32], unsigned long long my_row_base,
+                                                   long long col_byte, int valid_cols) {
+  constexpr int P = 64;
+  const int chunk = lane & 3;
+  const bool col_ok = chunk * 8 < valid_cols;
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int r = it * 8 + (lane >> 2);
+    const unsigned long long base = shfl_u64(my_row_base, r);
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (base != 0ull && col_ok) v = *reinterpret_cast<const uint4*>(base + col_byte + chunk * 16);
+    sts128(stg_addr<P>(stg, r, chunk), v.x, v.y, v.z, v.w);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const uint4 v = lds128(stg_addr<P>(stg, lane, c));
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+      z[8 * c + 2 * i] = t.x;
+      z[8 * c + 2 * i + 1] = t.y;
+    }
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ void tmem_ld32_f(uint32_t taddr, bool has_acc, float (&f)[32]) {
+  if (has_acc) {
+    uint32_t v[32];
+    ptx::tmem_ld_32x32b_x32(taddr, v);
+    ptx::tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) f[i] = 0.f;
+  }
+}
+
+// One output tile of this warp: rows row0 .. row0+31 (lane = row), the half of the tile's BN columns given by `half`.
+// `t_row` = TMEM address of the warp's lane quadrant in the accumulator, `stg` = the warp's staging tile.
+template <int MODE, int BN>
+__device__ __forceinline__ void epilogue_tile_staged(const KParams& p, const Tile& ti, uint32_t t_row, bool has_acc,
+                                                     long long row0, int half, int lane, uint32_t stg) {
+  const long long my_row = row0 + lane;
+  bool row_ok = true;
+  long long c_off = 0;
+  if (MODE == CSMOE_GEMM_REDUCE) {
+    row_ok = my_row < p.m_valid;
+    c_off = static_cast<long long>(ti.e) * p.c_expert_stride;
+  }
+  const int esz = p.c_fp32 ? 4 : 2;
+  unsigned long long my_c = 0ull;
+  if (MODE == CSMOE_GEMM_ROWS && p.c_rows != nullptr)
+    my_c = __ldg(p.c_rows + my_row);   // expert-parallel return: the row's slot in the source rank's buffer (0 = skip)
+  else if (row_ok)
+    my_c = reinterpret_cast<unsigned long long>(p.c) + static_cast<unsigned long long>((c_off + my_row * p.ldc) * esz);
+
+  if (p.epi == kEpiPlain) {
+    const unsigned long long my_pre =
+        (p.preact != nullptr && row_ok) ? reinterpret_cast<unsigned long long>(p.preact) + static_cast<unsigned long long>(my_row * p.ldpre * esz)
+                                        : 0ull;
+    const long long boff = static_cast<long long>(ti.e) * p.n;
+#pragma unroll 1
+    for (int g = 0; g < BN / 64; ++g) {
+      const int tcol = half * (BN / 2) + g * 32;
+      const int col0 = ti.nb * BN + tcol;
+      if (col0 >= p.n) break;
+      const int valid = min(32, p.n - col0);
+      float f[32];
+      tmem_ld32_f(t_row + tcol, has_acc, f);
+      if (p.bias != nullptr) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (c * 8 < valid) {
+            float b[8];
+            if (p.bias_fp32)
+              load8(reinterpret_cast<const float*>(p.bias) + boff + col0 + c * 8, b);
+            else
+              load8(reinterpret_cast<const __nv_bfloat16*>(p.bias) + boff + col0 + c * 8, b);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[c * 8 + i] += b[i];
+          }
+        }
+      }
+      if (p.act != CSMOE_ACT_NONE || p.preact != nullptr) {
+        if (!p.c_fp32) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = bf16_round(f[i]);
+        }
+        if (p.preact != nullptr) {
+          if (p.c_fp32)
+            staged_store32<true>(stg, lane, f, my_pre, static_cast<long long>(col0) * 4, valid);
+          else
+            staged_store32<false>(stg, lane, f, my_pre, static_cast<long long>(col0) * 2, valid);
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) f[i] = act_apply(f[i], p.act);
+      }
+      if (p.c_fp32)
+        staged_store32<true>(stg, lane, f, my_c, static_cast<long long>(col0) * 4, valid);
+      else
+        staged_store32<false>(stg, lane, f, my_c, static_cast<long long>(col0) * 2, valid);
+    }
+  } else if (p.epi == kEpiGluFwd) {
+    // TMEM columns [0, BN/2) hold the gate and [BN/2, BN) the up projection of BN/2 output columns.  z = (gate | up) is
+    // stored for the backward pass, h = up * silu(gate) feeds the down projection (Phi3MLP; each intermediate rounded
+    // to bf16 like the eager reference).
+    if constexpr (BN >= 256) {
+      constexpr int kGate = BN / 2;
+      const unsigned long long my_z = reinterpret_cast<unsigned long long>(p.preact) + static_cast<unsigned long long>(my_row * p.ldpre * 2);
+#pragma unroll 1
+      for (int g = 0; g < kGate / 64; ++g) {
+        const int tcol = half * (kGate / 2) + g * 32;
+        const int col0 = ti.nb * kGate + tcol;
+        if (col0 >= p.glu_f) break;
+        const int valid = min(32, p.glu_f - col0);
+        float zg[32], zu[32];
+        tmem_ld32_f(t_row + tcol, has_acc, zg);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) zg[i] = bf16_round(zg[i]);
+        staged_store32<false>(stg, lane, zg, my_z, static_cast<long long>(col0) * 2, valid);
+        tmem_ld32_f(t_row + kGate + tcol, has_acc, zu);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) zu[i] = bf16_round(zu[i]);
+        staged_store32<false>(stg, lane, zu, my_z, static_cast<long long>(p.glu_f + col0) * 2, valid);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) zu[i] *= bf16_round(act_apply(zg[i], CSMOE_ACT_SILU));
+        staged_store32<false>(stg, lane, zu, my_c, static_cast<long long>(col0) * 2, valid);
+      }
+    }
+  } else {
+    // Backward epilogues: the accumulator is dh; multiply by the activation derivative at the saved z (bf16).
+    const bool glu = p.epi == kEpiGluBwd;
+    const unsigned long long my_z =
+        row_ok ? reinterpret_cast<unsigned long long>(p.aux) + static_cast<unsigned long long>(my_row * p.ldaux * 2) : 0ull;
+#pragma unroll 1
+    for (int g = 0; g < BN / 64; ++g) {
+      const int tcol = half * (BN / 2) + g * 32;
+      const int col0 = ti.nb * BN + tcol;
+      if (col0 >= p.n) break;
+      const int valid = min(32, p.n - col0);
+      float z0[32], dh[32];
+      staged_load32_bf16(stg, lane, z0, my_z, static_cast<long long>(col0) * 2, valid);
+      tmem_ld32_f(t_row + tcol, has_acc, dh);
+      if (glu) {
+        float z1[32];
+        staged_load32_bf16(stg, lane, z1, my_z, static_cast<long long>(p.glu_f + col0) * 2, valid);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float d = bf16_round(dh[i]);
+          const float sg = bf16_round(act_apply(z0[i], CSMOE_ACT_SILU));
+          z1[i] = bf16_round(d * z1[i]) * act_grad(z0[i], CSMOE_ACT_SILU);   // d gate
+          dh[i] = d * sg;                                                      // d up
+        }
+        staged_store32<false>(stg, lane, z1, my_c, static_cast<long long>(col0) * 2, valid);
+        staged_store32<false>(stg, lane, dh, my_c, static_cast<long long>(p.glu_f + col0) * 2, valid);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) dh[i] = bf16_round(dh[i]) * act_grad(z0[i], p.act);
+        staged_store32<false>(stg, lane, dh, my_c, static_cast<long long>(col0) * 2, valid);
+      }
+    }
+  }
+}
+
 template <int MODE, bool B_MN, int BN>
 __global__ void __launch_bounds__(kThreads, 1)
 grouped_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const KParams p) {
@@ -294,7 +544,8 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + kStages * kStageBytes;
+  const uint32_t stg_base = smem_base + kStages * kStageBytes;   // 8 epilogue warps x 4 KiB staging tiles
+  const uint32_t bar_base = stg_base + kEpiWarps * kStageTileBytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
@@ -428,7 +679,10 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       }
       const long long out_row = static_cast<long long>(ti.mb) * kBM + row_in_tile;
       const uint32_t t_row = tmem_base + acc * BN + (static_cast<uint32_t>(quad * 32) << 16);
-      epilogue_tile<MODE, BN>(p, ti, t_row, has_acc, out_row, half);
+      if (p.direct_epi)
+        epilogue_tile<MODE, BN>(p, ti, t_row, has_acc, out_row, half);
+      else
+        epilogue_tile_staged<MODE, BN>(p, ti, t_row, has_acc, out_row - lane, half, lane, stg_base + (warp - 2) * kStageTileBytes);
       if (has_acc) {
         ptx::tc_fence_before();
         __syncwarp();
@@ -522,7 +776,8 @@ grouped_gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + kPairStages * kPairStageBytes;
+  const uint32_t stg_base = smem_base + kPairStages * kPairStageBytes;
+  const uint32_t bar_base = stg_base + kEpiWarps * kStageTileBytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kPairStages + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kPairStages + a); };
@@ -562,16 +817,30 @@ grouped_gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
   ptx::cluster_sync();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  const bool st_on = p.stats != nullptr;
+  const long long st_t0 = st_on ? clock64() : 0;
+  const unsigned long long st_g0 = st_on ? ptx::globaltimer() : 0ull;
 
   if (warp == 0) {
     // ===================================================== TMA producer (both CTAs)
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
+      unsigned long long w_empty = 0;
+      int dbg_filled = 0;
       for (long long t = cluster_id; t < p.total_tiles; t += num_clusters) {
         const Tile ti = decode_tile_pair<MODE>(p, t, rank);
         if (!ti.valid) continue;
         for (int kb = 0; kb < ti.nkb; ++kb) {
-          ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+          timed_wait(empty_bar(stage), phase ^ 1u, st_on, w_empty);
+          if ((p.dbg_mode & 1) && dbg_filled >= kPairStages) {
+            if (leader) ptx::mbar_arrive(full_bar(stage));
+            if (++stage == kPairStages) {
+              stage = 0;
+              phase ^= 1u;
+            }
+            continue;
+          }
+          ++dbg_filled;
           if (leader) ptx::mbar_arrive_expect_tx(full_bar(stage), 2 * kPairStageBytes);
           const uint32_t fb = ptx::mapa(full_bar(stage), 0);  // the leader's barrier collects both CTAs' bytes
           const uint32_t sa = smem_base + stage * kPairStageBytes;
@@ -603,19 +872,22 @@ grouped_gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
           }
         }
       }
+      if (st_on) p.stats[blockIdx.x * 8 + 0] = w_empty;
     }
   } else if (warp == 1) {
     // ===================================================== MMA issuer (leader CTA only)
     if (leader && lane == 0) {
+      unsigned long long w_full = 0, w_tempty = 0, n_tiles = 0;
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
       for (long long t = cluster_id; t < p.total_tiles; t += num_clusters) {
         const Tile ti = decode_tile_pair<MODE>(p, t, rank);
         if (!ti.valid || ti.nkb == 0) continue;
-        ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        ++n_tiles;
+        timed_wait(tempty_bar(acc), acc_phase ^ 1u, st_on, w_tempty);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < ti.nkb; ++kb) {
-          ptx::mbar_wait(full_bar(stage), phase);
+          timed_wait(full_bar(stage), phase, st_on, w_full);
           ptx::tc_fence_after();
           const uint32_t sa = smem_base + stage * kPairStageBytes;
           const uint32_t sb = sa + kABytes;
@@ -625,7 +897,7 @@ grouped_gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
                                         : ptx::make_smem_desc_sw128(sa + k * 32, 16, 1024);
             const uint64_t bdesc = kBMn ? ptx::make_smem_desc_sw128(sb + k * 2048, kSubTileBytes, 1024)
                                         : ptx::make_smem_desc_sw128(sb + k * 32, 16, 1024);
-            ptx::umma_f16_cg2(d_tmem, adesc, bdesc, kIdesc, (kb | k) != 0 ? 1u : 0u);
+            if (!(p.dbg_mode & 2)) ptx::umma_f16_cg2(d_tmem, adesc, bdesc, kIdesc, (kb | k) != 0 ? 1u : 0u);
           }
           ptx::umma_commit_cg2_mc(empty_bar(stage), 0x3);
           if (++stage == kPairStages) {
@@ -639,12 +911,18 @@ grouped_gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
           acc_phase ^= 1u;
         }
       }
+      if (st_on) {
+        p.stats[blockIdx.x * 8 + 1] = w_full;
+        p.stats[blockIdx.x * 8 + 2] = w_tempty;
+        p.stats[blockIdx.x * 8 + 5] = n_tiles;
+      }
     }
   } else {
     // ===================================================== epilogue (both CTAs; 8 warps each)
     const int quad = warp & 3;
     const int half = (warp - 2) >> 2;
     const int row_in_tile = quad * 32 + lane;
+    unsigned long long epi_cycles = 0;
     uint32_t acc = 0, acc_phase = 0;
     for (long long t = cluster_id; t < p.total_tiles; t += num_clusters) {
       const Tile ti = decode_tile_pair<MODE>(p, t, rank);
@@ -656,7 +934,11 @@ grouped_gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
       }
       const long long out_row = static_cast<long long>(ti.mb) * 256 + rank * kBM + row_in_tile;
       const uint32_t t_row = tmem_base + acc * BN + (static_cast<uint32_t>(quad * 32) << 16);
-      epilogue_tile<MODE, BN>(p, ti, t_row, has_acc, out_row, half);
+      const long long e0 = st_on ? clock64() : 0;
+      if (p.direct_epi)
+        epilogue_tile<MODE, BN>(p, ti, t_row, has_acc, out_row, half);
+      else
+        epilogue_tile_staged<MODE, BN>(p, ti, t_row, has_acc, out_row - lane, half, lane, stg_base + (warp - 2) * kStageTileBytes);
       if (has_acc) {
         ptx::tc_fence_before();
         __syncwarp();
@@ -664,19 +946,238 @@ grouped_gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
           if (leader)
             ptx::mbar_arrive(tempty_bar(acc));
           else
-            ptx::mbar_arrive_remote(ptx::mapa(tempty_bar(acc), 0));
+            ptx::mbar_arrive_remote_relaxed(ptx::mapa(tempty_bar(acc), 0));
         }
         if (++acc == kAccStages) {
           acc = 0;
           acc_phase ^= 1u;
         }
       }
+      if (st_on) epi_cycles += static_cast<unsigned long long>(clock64() - e0);
     }
+    if (st_on && warp == 2 && lane == 0) p.stats[blockIdx.x * 8 + 3] = epi_cycles;
   }
 
+  if (st_on && threadIdx.x == 0) {
+    p.stats[blockIdx.x * 8 + 4] = static_cast<unsigned long long>(clock64() - st_t0);
+    p.stats[blockIdx.x * 8 + 6] = ptx::globaltimer() - st_g0;
+  }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::cluster_sync();  // the peer's smem / barriers must outlive the leader's last MMA and commit
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc_cg2(tmem_base, kTmemCols);
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------ wide CTA-pair kernel
+// The 256 x 256 pair kernel moves 64 KiB from L2 to the two SMs per 64-deep k-block: at cuBLAS-level tensor rates that
+// is 11-12 TB/s, the practical ceiling of the L2 -> SM fabric on this part (ncu: lts2xbar 10.5 TB/s, the kernel's
+// limiter; profiles/r01c_gemm_l2_bound.md).  This variant gives each pair a 256 x 512 tile: every A k-block is reused
+// for two 256-column MMAs, so the traffic per flop drops by a quarter (48 KiB per CTA per k-block for twice the math).
+// The accumulator takes all 512 TMEM columns, so the epilogue of a tile is no longer hidden behind the next tile's
+// MMAs (TMA prefetch of the next tile still overlaps it); that costs ~4k cycles per tile (TMEM reads at 64 B/clk)
+// against >= 32k cycles of MMAs.
+constexpr int kWideStages = 4;
+constexpr int kWideHalfBytes = 128 * kBK * 2;                       // one CTA's share of one 256-column half: 16 KiB
+constexpr int kWideStageBytes = kABytes + 2 * kWideHalfBytes;       // 48 KiB per CTA per stage
+
+template <int MODE, bool B_MN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+grouped_gemm_wide_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                         const KParams p) {
+  constexpr int BN = 512;
+  constexpr bool kAMn = (MODE == CSMOE_GEMM_REDUCE);
+  constexpr bool kBMn = kAMn || B_MN;
+  constexpr uint32_t kTmemCols = 512;
+  constexpr uint32_t kIdesc = ptx::make_idesc_bf16(256, 256, kAMn, kBMn);
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t stg_base = smem_base + kWideStages * kWideStageBytes;
+  const uint32_t bar_base = stg_base + kEpiWarps * kStageTileBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kWideStages + s); };
+  const uint32_t tfull_bar = bar_base + 8u * (2 * kWideStages);
+  const uint32_t tempty_bar = bar_base + 8u * (2 * kWideStages + 1);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kWideStages + 2);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int rank = static_cast<int>(ptx::cluster_ctarank());
+  const bool leader = rank == 0;
+  const long long cluster_id = blockIdx.x >> 1;
+  const long long num_clusters = gridDim.x >> 1;
+  const bool glu = p.epi == kEpiGluFwd;
+  // halves of the tile that hold valid output columns (the last n-block of a plain GEMM may need only one)
+  auto tile_halves = [&](const Tile& ti) { return (glu || ti.nb * BN + 256 < p.n) ? 2 : 1; };
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tma_a);
+    ptx::prefetch_tmap(&tma_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kWideStages; ++s) {
+      ptx::mbar_init(full_bar(s), 1);
+      ptx::mbar_init(empty_bar(s), 1);
+    }
+    ptx::mbar_init(tfull_bar, 1);
+    ptx::mbar_init(tempty_bar, 2 * kEpiWarps);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc_cg2(tmem_slot, kTmemCols);
+    ptx::tmem_relinquish_cg2();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  const bool st_on = p.stats != nullptr;
+  const long long st_t0 = st_on ? clock64() : 0;
+  const unsigned long long st_g0 = st_on ? ptx::globaltimer() : 0ull;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer (both CTAs)
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      unsigned long long w_empty = 0;
+      for (long long t = cluster_id; t < p.total_tiles; t += num_clusters) {
+        const Tile ti = decode_tile_pair<MODE>(p, t, rank);
+        if (!ti.valid) continue;
+        const int halves = tile_halves(ti);
+        const uint32_t bytes = 2u * (kABytes + halves * kWideHalfBytes);
+        for (int kb = 0; kb < ti.nkb; ++kb) {
+          timed_wait(empty_bar(stage), phase ^ 1u, st_on, w_empty);
+          if (leader) ptx::mbar_arrive_expect_tx(full_bar(stage), bytes);
+          const uint32_t fb = ptx::mapa(full_bar(stage), 0);
+          const uint32_t sa = smem_base + stage * kWideStageBytes;
+          const uint32_t sb = sa + kABytes;
+          if (MODE == CSMOE_GEMM_ROWS) {
+            ptx::tma_load_2d_cg2(sa, &tma_a, fb, kb * kBK, ti.a_row);
+            for (int h = 0; h < halves; ++h) {
+              if (!B_MN) {
+                const int brow = glu ? h * p.glu_f + ti.nb * 256 + rank * 128 : ti.nb * BN + h * 256 + rank * 128;
+                ptx::tma_load_3d_cg2(sb + h * kWideHalfBytes, &tma_b, fb, kb * kBK, brow, ti.e);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+                  ptx::tma_load_3d_cg2(sb + h * kWideHalfBytes + j * kSubTileBytes, &tma_b, fb,
+                                       ti.nb * BN + h * 256 + rank * 128 + j * 64, kb * kBK, ti.e);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+              ptx::tma_load_2d_cg2(sa + j * kSubTileBytes, &tma_a, fb, ti.mb * 256 + rank * 128 + j * 64,
+                                   ti.a_row + kb * kBK);
+            for (int h = 0; h < halves; ++h)
+#pragma unroll
+              for (int j = 0; j < 2; ++j)
+                ptx::tma_load_2d_cg2(sb + h * kWideHalfBytes + j * kSubTileBytes, &tma_b, fb,
+                                     ti.nb * BN + h * 256 + rank * 128 + j * 64, ti.b_row + kb * kBK);
+          }
+          if (++stage == kWideStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+      if (st_on) p.stats[blockIdx.x * 8 + 0] = w_empty;
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer (leader CTA only)
+    if (leader && lane == 0) {
+      unsigned long long w_full = 0, w_tempty = 0, n_tiles = 0;
+      uint32_t stage = 0, phase = 0, acc_phase = 0;
+      for (long long t = cluster_id; t < p.total_tiles; t += num_clusters) {
+        const Tile ti = decode_tile_pair<MODE>(p, t, rank);
+        if (!ti.valid || ti.nkb == 0) continue;
+        ++n_tiles;
+        const int halves = tile_halves(ti);
+        timed_wait(tempty_bar, acc_phase ^ 1u, st_on, w_tempty);
+        ptx::tc_fence_after();
+        for (int kb = 0; kb < ti.nkb; ++kb) {
+          timed_wait(full_bar(stage), phase, st_on, w_full);
+          ptx::tc_fence_after();
+          const uint32_t sa = smem_base + stage * kWideStageBytes;
+          const uint32_t sb = sa + kABytes;
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            const uint64_t adesc = kAMn ? ptx::make_smem_desc_sw128(sa + k * 2048, kSubTileBytes, 1024)
+                                        : ptx::make_smem_desc_sw128(sa + k * 32, 16, 1024);
+            for (int h = 0; h < halves; ++h) {
+              const uint32_t sbh = sb + h * kWideHalfBytes;
+              const uint64_t bdesc = kBMn ? ptx::make_smem_desc_sw128(sbh + k * 2048, kSubTileBytes, 1024)
+                                          : ptx::make_smem_desc_sw128(sbh + k * 32, 16, 1024);
+              ptx::umma_f16_cg2(tmem_base + h * 256, adesc, bdesc, kIdesc, (kb | k) != 0 ? 1u : 0u);
+            }
+          }
+          ptx::umma_commit_cg2_mc(empty_bar(stage), 0x3);
+          if (++stage == kWideStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        ptx::umma_commit_cg2_mc(tfull_bar, 0x3);
+        acc_phase ^= 1u;
+      }
+      if (st_on) {
+        p.stats[blockIdx.x * 8 + 1] = w_full;
+        p.stats[blockIdx.x * 8 + 2] = w_tempty;
+        p.stats[blockIdx.x * 8 + 5] = n_tiles;
+      }
+    }
+  } else {
+    // ===================================================== epilogue (both CTAs; 8 warps each, 256 columns per warp)
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int row_in_tile = quad * 32 + lane;
+    unsigned long long epi_cycles = 0;
+    uint32_t acc_phase = 0;
+    for (long long t = cluster_id; t < p.total_tiles; t += num_clusters) {
+      const Tile ti = decode_tile_pair<MODE>(p, t, rank);
+      if (!ti.valid) continue;
+      const bool has_acc = ti.nkb > 0;
+      if (has_acc) {
+        ptx::mbar_wait(tfull_bar, acc_phase);
+        ptx::tc_fence_after();
+      }
+      const long long out_row = static_cast<long long>(ti.mb) * 256 + rank * kBM + row_in_tile;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+      const long long e0 = st_on ? clock64() : 0;
+      if (p.direct_epi)
+        epilogue_tile<MODE, BN>(p, ti, t_row, has_acc, out_row, half);
+      else
+        epilogue_tile_staged<MODE, BN>(p, ti, t_row, has_acc, out_row - lane, half, lane, stg_base + (warp - 2) * kStageTileBytes);
+      if (has_acc) {
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (leader)
+            ptx::mbar_arrive(tempty_bar);
+          else
+            ptx::mbar_arrive_remote_relaxed(ptx::mapa(tempty_bar, 0));
+        }
+        acc_phase ^= 1u;
+      }
+      if (st_on) epi_cycles += static_cast<unsigned long long>(clock64() - e0);
+    }
+    if (st_on && warp == 2 && lane == 0) p.stats[blockIdx.x * 8 + 3] = epi_cycles;
+  }
+
+  if (st_on && threadIdx.x == 0) {
+    p.stats[blockIdx.x * 8 + 4] = static_cast<unsigned long long>(clock64() - st_t0);
+    p.stats[blockIdx.x * 8 + 6] = ptx::globaltimer() - st_g0;
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync();
   if (warp == 2) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc_cg2(tmem_base, kTmemCols);
@@ -723,7 +1224,7 @@ int encode_bf16_map(CUtensorMap* map, const void* base, int rank, const cuuint64
 template <int MODE, bool B_MN, int BN>
 int launch(const CUtensorMap& ma, const CUtensorMap& mb, const KParams& kp, int grid, cudaStream_t stream) {
   constexpr int kStages = (BN == 256) ? 4 : 6;
-  constexpr int kSmem = kStages * (kABytes + BN * kBK * 2) + 1024 + 256;
+  constexpr int kSmem = kStages * (kABytes + BN * kBK * 2) + kEpiWarps * kStageTileBytes + 1024 + 256;
   auto kern = grouped_gemm_kernel<MODE, B_MN, BN>;
   static bool configured = false;  // per instantiation; benign race (idempotent attribute set)
   if (!configured) {
@@ -737,7 +1238,7 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const KParams& kp, int 
 
 template <int MODE, bool B_MN>
 int launch_pair(const CUtensorMap& ma, const CUtensorMap& mb, const KParams& kp, int clusters, cudaStream_t stream) {
-  constexpr int kSmem = kPairStages * kPairStageBytes + 1024 + 256;
+  constexpr int kSmem = kPairStages * kPairStageBytes + kEpiWarps * kStageTileBytes + 1024 + 256;
   auto kern = grouped_gemm_pair_kernel<MODE, B_MN>;
   static bool configured = false;
   if (!configured) {
@@ -747,6 +1248,77 @@ int launch_pair(const CUtensorMap& ma, const CUtensorMap& mb, const KParams& kp,
   kern<<<2 * clusters, kThreads, kSmem, stream>>>(ma, mb, kp);
   CSMOE_CHECK_LAUNCH();
   return CSMOE_OK;
+}
+
+template <int MODE, bool B_MN>
+int launch_wide(const CUtensorMap& ma, const CUtensorMap& mb, const KParams& kp, int clusters, cudaStream_t stream) {
+  constexpr int kSmem = kWideStages * kWideStageBytes + kEpiWarps * kStageTileBytes + 1024 + 256;
+  auto kern = grouped_gemm_wide_kernel<MODE, B_MN>;
+  static bool configured = false;
+  if (!configured) {
+    CSMOE_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    configured = true;
+  }
+  kern<<<2 * clusters, kThreads, kSmem, stream>>>(ma, mb, kp);
+  CSMOE_CHECK_LAUNCH();
+  return CSMOE_OK;
+}
+
+// CSMOE_GEMM_WIDE: bit 0 = ROWS launches, bit 1 = REDUCE launches may use the 256 x 512 kernel (default 3; 0 = never)
+int wide_mask() {
+  static const int m = []() {
+    const char* v = getenv("CSMOE_GEMM_WIDE");
+    return v == nullptr ? 3 : atoi(v);
+  }();
+  return m;
+}
+
+// CSMOE_GEMM_STATS=1: per-role wait-cycle counters of the pair / wide kernels, printed to stderr after every launch
+// (synchronises the stream: a bring-up / tuning aid, never on in production).
+unsigned long long* stats_buffer() {
+  static unsigned long long* buf = []() -> unsigned long long* {
+    const char* v = getenv("CSMOE_GEMM_STATS");
+    if (v == nullptr || v[0] == '0') return nullptr;
+    void* p = nullptr;
+    if (cudaMalloc(&p, 256 * 8 * sizeof(unsigned long long)) != cudaSuccess) return nullptr;
+    return static_cast<unsigned long long*>(p);
+  }();
+  return buf;
+}
+
+void print_stats(const char* what, const KParams& kp, int ctas, cudaStream_t stream) {
+  unsigned long long h[256 * 8];
+  cudaStreamSynchronize(stream);
+  cudaMemcpy(h, kp.stats, sizeof(unsigned long long) * 8 * ctas, cudaMemcpyDeviceToHost);
+  double s[6] = {0, 0, 0, 0, 0, 0}, ep = 0, tot_max = 0;
+  for (int c = 0; c < ctas; ++c) {
+    if (c % 2 == 0) {
+      for (int i = 0; i < 6; ++i) s[i] += static_cast<double>(h[c * 8 + i]);
+    } else {
+      ep += static_cast<double>(h[c * 8 + 3]);
+    }
+    if (static_cast<double>(h[c * 8 + 4]) > tot_max) tot_max = static_cast<double>(h[c * 8 + 4]);
+  }
+  const double n = ctas / 2;
+  fprintf(stderr, "[csmoe gemm stats] SM clock %.0f MHz; ", 1e3 * static_cast<double>(h[4]) / static_cast<double>(h[6] ? h[6] : 1));
+  fprintf(stderr,
+          "%s tiles/cluster %.2f total %.0f cyc (max %.0f) | leader: producer-wait-empty %.1f%% "
+          "mma-wait-full %.1f%% mma-wait-tempty %.1f%% epilogue-busy %.1f%% (peer %.1f%%) | epilogue cyc/tile %.0f\n",
+          what, s[5] / n, s[4] / n, tot_max, 100 * s[0] / s[4], 100 * s[1] / s[4], 100 * s[2] / s[4], 100 * s[3] / s[4],
+          100 * ep / s[4], s[3] / (s[5] > 0 ? s[5] : 1));
+}
+
+// Epilogue store path.  Measured on B200 (scripts/gemm_bench.py, profiles/r01d_gemm_tuning.md): the staged, coalesced
+// stores win where a tile writes several outputs (fused GLU forward: z gate, z up and h, +7 %), are neutral for the
+// plain single-output epilogue and lose ~9 % in wgrad, whose main loop is shared-memory-bandwidth bound and feels the
+// extra st.shared / ld.shared traffic.  CSMOE_GEMM_EPI=direct|staged forces one path for A/B runs.
+int epilogue_override() {
+  static const int v = []() {
+    const char* e = getenv("CSMOE_GEMM_EPI");
+    if (e == nullptr) return 0;
+    return e[0] == 'd' ? 1 : (e[0] == 's' ? 2 : 0);
+  }();
+  return v;
 }
 
 // CSMOE_GEMM_PAIR=0 disables the CTA-pair kernel (A/B comparisons, bring-up)
@@ -842,6 +1414,11 @@ extern "C" int csmoe_grouped_gemm(const csmoe_gemm_args* a, void* stream_) {
   kp.aux = a->aux;
   kp.ldaux = a->ldaux;
   kp.c_rows = reinterpret_cast<const unsigned long long*>(a->c_rows);
+  kp.direct_epi = 1;  // decided once the epilogue kind is known (below)
+  {
+    static const int dbg = []() { const char* v = getenv("CSMOE_GEMM_DBG"); return v ? atoi(v) : 0; }();
+    kp.dbg_mode = dbg;
+  }
   if (glu_fwd) {
     kp.epi = kEpiGluFwd;
     kp.glu_f = static_cast<int>(a->n / 2);
@@ -853,6 +1430,8 @@ extern "C" int csmoe_grouped_gemm(const csmoe_gemm_args* a, void* stream_) {
   } else {
     kp.epi = kEpiPlain;
   }
+  kp.direct_epi = kp.epi == kEpiGluFwd ? 0 : 1;
+  if (epilogue_override() != 0 && !a->accumulate) kp.direct_epi = epilogue_override() == 1 ? 1 : 0;
 
   CUtensorMap ma, mb;
   int rc;
@@ -903,12 +1482,51 @@ extern "C" int csmoe_grouped_gemm(const csmoe_gemm_args* a, void* stream_) {
   if (kp.total_tiles == 0) return CSMOE_OK;
   if (pair) {
     kp.num_m_pairs = a->mode == CSMOE_GEMM_ROWS ? kp.num_m_blocks / 2 : static_cast<int>((a->m + 255) / 256);
+    // 256 x 512 tiles when the output is wide enough that the second half is (almost) never padding
+    // ... and the k loop is long enough to amortise the exposed epilogue (measured on B200, gemm_bench.py: k = 8192
+    // +12 %, k = 16384 +8 %, k = 3072 -2 %; wgrad, whose k loop is one expert's rows, loses 10 %).  CSMOE_GEMM_WIDE
+    // bits 2 / 3 force it for every ROWS / REDUCE launch.
+    const int wm = wide_mask();
+    const bool long_k = a->mode == CSMOE_GEMM_ROWS ? a->k >= 4096 || (wm & 4) : (wm & 8) != 0;
+    const bool wide = n_grid >= 512 && (n_grid % 512 == 0 || n_grid >= 2048) && long_k &&
+                      (wm & (a->mode == CSMOE_GEMM_ROWS ? 1 : 2)) != 0;
+    if (wide) kp.num_n_blocks = glu_fwd ? static_cast<int>((n_grid + 255) / 256) : static_cast<int>((a->n + 511) / 512);
     const long long per = static_cast<long long>(kp.num_m_pairs) * kp.num_n_blocks;
     kp.total_tiles = a->mode == CSMOE_GEMM_ROWS ? per : per * E;
     int clusters = num_sms() / 2;
     if (clusters <= 0) return CSMOE_ERR_CUDA;
     if (a->max_ctas > 1 && a->max_ctas / 2 < clusters) clusters = a->max_ctas / 2;
     if (kp.total_tiles < clusters) clusters = static_cast<int>(kp.total_tiles);
+    kp.stats = stats_buffer();
+    if (kp.stats != nullptr) {
+      cudaMemsetAsync(kp.stats, 0, 256 * 8 * sizeof(unsigned long long), stream);
+      int rc2;
+      if (wide) {
+        if (a->mode == CSMOE_GEMM_ROWS)
+          rc2 = a->b_layout == 0 ? launch_wide<CSMOE_GEMM_ROWS, false>(ma, mb, kp, clusters, stream)
+                                 : launch_wide<CSMOE_GEMM_ROWS, true>(ma, mb, kp, clusters, stream);
+        else
+          rc2 = launch_wide<CSMOE_GEMM_REDUCE, true>(ma, mb, kp, clusters, stream);
+      } else if (a->mode == CSMOE_GEMM_ROWS) {
+        rc2 = a->b_layout == 0 ? launch_pair<CSMOE_GEMM_ROWS, false>(ma, mb, kp, clusters, stream)
+                               : launch_pair<CSMOE_GEMM_ROWS, true>(ma, mb, kp, clusters, stream);
+      } else {
+        rc2 = launch_pair<CSMOE_GEMM_REDUCE, true>(ma, mb, kp, clusters, stream);
+      }
+      if (rc2 == CSMOE_OK) {
+        char what[96];
+        snprintf(what, sizeof(what), "%s mode=%d b_layout=%d epi=%d n=%lld k=%lld", wide ? "wide" : "pair", a->mode,
+                 a->b_layout, kp.epi, (long long)a->n, (long long)a->k);
+        print_stats(what, kp, 2 * clusters, stream);
+      }
+      return rc2;
+    }
+    if (wide) {
+      if (a->mode == CSMOE_GEMM_ROWS)
+        return a->b_layout == 0 ? launch_wide<CSMOE_GEMM_ROWS, false>(ma, mb, kp, clusters, stream)
+                                : launch_wide<CSMOE_GEMM_ROWS, true>(ma, mb, kp, clusters, stream);
+      return launch_wide<CSMOE_GEMM_REDUCE, true>(ma, mb, kp, clusters, stream);
+    }
     if (a->mode == CSMOE_GEMM_ROWS)
       return a->b_layout == 0 ? launch_pair<CSMOE_GEMM_ROWS, false>(ma, mb, kp, clusters, stream)
                               : launch_pair<CSMOE_GEMM_ROWS, true>(ma, mb, kp, clusters, stream);

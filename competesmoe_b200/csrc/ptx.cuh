@@ -72,6 +72,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+__device__ __forceinline__ unsigned long long globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 // ---------------------------------------------------------------- clusters
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -90,6 +96,12 @@ __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
 }
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// Same without release semantics: no MEMBAR.GPU in front of the arrive, so the caller's earlier *global* stores are
+// not waited for.  Used to hand a TMEM accumulator stage back to the MMA issuer: the only ordering needed is that the
+// tcgen05.ld's have completed, which tcgen05.wait::ld + tcgen05.fence::before_thread_sync already guarantee.
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 
 // ---------------------------------------------------------------- TMA

@@ -387,3 +387,23 @@ def test_diversity_and_fused_competition_backward(ops, dtype, E, K, T, t_pad, D)
     only_aff = ops.compete_bwd(y.view(E * t_pad, D), E, T, t_pad, sel, daff=daff).view(E, t_pad, D)
     (ref_aff,) = torch.autograd.grad((F.softplus(yr[:, :T]).mean(-1).t() * daff).sum(), yr)
     assert_close_rms(only_aff.float(), ref_aff, rtol=tol, what="score term")
+
+
+# ------------------------------------------------------------------------------------------------ GEMM variants
+@pytest.mark.parametrize("env", [
+    {"CSMOE_GEMM_EPI": "staged", "CSMOE_GEMM_WIDE": "15"},   # staged epilogue everywhere, 256x512 tiles wherever legal
+    {"CSMOE_GEMM_EPI": "direct", "CSMOE_GEMM_WIDE": "0"},    # register-direct epilogue, 256x256 CTA-pair tiles only
+    {"CSMOE_GEMM_PAIR": "0"},                                 # single-CTA kernels only
+])
+def test_gemm_kernel_variants_in_subprocess(env):
+    """The kernel / epilogue variant is picked per launch by shape; the switches that force one variant are read once
+    per process, so the GEMM tests are re-run in a child process under each setting."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("CSMOE_VARIANT_CHILD"):
+        pytest.skip("already inside a variant run")
+    child_env = dict(os.environ, CSMOE_VARIANT_CHILD="1", **env)
+    r = subprocess.run([sys.executable, "-m", "pytest", __file__, "-q", "-x", "-m", "gpu", "-k", "gemm and not variants"],
+                       env=child_env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
