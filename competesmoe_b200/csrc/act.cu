@@ -12,12 +12,13 @@ constexpr int kThreads = 256;
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 act_fwd_kernel(const T* __restrict__ z, long long rows, long long cols, long long ldz, int act, T* __restrict__ h,
-               long long ldh) {
+               long long ldh, const int32_t* __restrict__ tile_expert) {
   const long long vec_per_row = cols / 8;
   const long long total = rows * vec_per_row;
   for (long long i = static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * kThreads) {
     const long long r = i / vec_per_row, c = (i % vec_per_row) * 8;
+    if (tile_expert != nullptr && __ldg(tile_expert + (r >> 7)) < 0) continue;   // row tile past the routed rows
     float v[8], o[8];
     if (act == CSMOE_ACT_SILU_GLU) {
       float u[8];
@@ -40,12 +41,13 @@ act_fwd_kernel(const T* __restrict__ z, long long rows, long long cols, long lon
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 act_bwd_kernel(const T* __restrict__ z, const T* __restrict__ dh, long long rows, long long cols, long long ldz,
-               long long ldh, int act, T* __restrict__ dz) {
+               long long ldh, int act, T* __restrict__ dz, const int32_t* __restrict__ tile_expert) {
   const long long vec_per_row = cols / 8;
   const long long total = rows * vec_per_row;
   for (long long i = static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * kThreads) {
     const long long r = i / vec_per_row, c = (i % vec_per_row) * 8;
+    if (tile_expert != nullptr && __ldg(tile_expert + (r >> 7)) < 0) continue;
     float v[8], g[8], o[8];
     load8(dh + r * ldh + c, g);
     if (act == CSMOE_ACT_SILU_GLU) {
@@ -138,7 +140,7 @@ inline unsigned flat_grid(long long work_items) {
 using namespace csmoe;
 
 extern "C" int csmoe_act_fwd(const void* z, int32_t dtype, int64_t rows, int64_t cols, int64_t ldz, int32_t act,
-                             void* h, int64_t ldh, void* stream_) {
+                             void* h, int64_t ldh, const int32_t* tile_expert, void* stream_) {
   CSMOE_CHECK_ARG(z && h, "csmoe_act_fwd: NULL pointer");
   CSMOE_CHECK_ARG(cols > 0 && cols % 8 == 0 && ldz % 8 == 0 && ldh % 8 == 0, "csmoe_act_fwd: cols/ld must be multiples of 8");
   CSMOE_CHECK_ARG(act >= CSMOE_ACT_NONE && act <= CSMOE_ACT_SILU_GLU, "csmoe_act_fwd: bad act %d", act);
@@ -147,10 +149,10 @@ extern "C" int csmoe_act_fwd(const void* z, int32_t dtype, int64_t rows, int64_t
   const unsigned grid = flat_grid(rows * (cols / 8));
   if (dtype == CSMOE_BF16) {
     act_fwd_kernel<__nv_bfloat16><<<grid, kThreads, 0, stream>>>(static_cast<const __nv_bfloat16*>(z), rows, cols, ldz,
-                                                                 act, static_cast<__nv_bfloat16*>(h), ldh);
+                                                                 act, static_cast<__nv_bfloat16*>(h), ldh, tile_expert);
   } else if (dtype == CSMOE_F32) {
     act_fwd_kernel<float><<<grid, kThreads, 0, stream>>>(static_cast<const float*>(z), rows, cols, ldz, act,
-                                                         static_cast<float*>(h), ldh);
+                                                         static_cast<float*>(h), ldh, tile_expert);
   } else {
     CSMOE_CHECK_ARG(false, "csmoe_act_fwd: unsupported dtype %d", dtype);
   }
@@ -159,7 +161,7 @@ extern "C" int csmoe_act_fwd(const void* z, int32_t dtype, int64_t rows, int64_t
 }
 
 extern "C" int csmoe_act_bwd(const void* z, const void* dh, int32_t dtype, int64_t rows, int64_t cols, int64_t ldz,
-                             int64_t ldh, int32_t act, void* dz, void* stream_) {
+                             int64_t ldh, int32_t act, void* dz, const int32_t* tile_expert, void* stream_) {
   CSMOE_CHECK_ARG(z && dh && dz, "csmoe_act_bwd: NULL pointer");
   CSMOE_CHECK_ARG(cols > 0 && cols % 8 == 0 && ldz % 8 == 0 && ldh % 8 == 0, "csmoe_act_bwd: cols/ld must be multiples of 8");
   CSMOE_CHECK_ARG(act >= CSMOE_ACT_NONE && act <= CSMOE_ACT_SILU_GLU, "csmoe_act_bwd: bad act %d", act);
@@ -169,10 +171,10 @@ extern "C" int csmoe_act_bwd(const void* z, const void* dh, int32_t dtype, int64
   if (dtype == CSMOE_BF16) {
     act_bwd_kernel<__nv_bfloat16><<<grid, kThreads, 0, stream>>>(static_cast<const __nv_bfloat16*>(z),
                                                                  static_cast<const __nv_bfloat16*>(dh), rows, cols, ldz,
-                                                                 ldh, act, static_cast<__nv_bfloat16*>(dz));
+                                                                 ldh, act, static_cast<__nv_bfloat16*>(dz), tile_expert);
   } else if (dtype == CSMOE_F32) {
     act_bwd_kernel<float><<<grid, kThreads, 0, stream>>>(static_cast<const float*>(z), static_cast<const float*>(dh),
-                                                         rows, cols, ldz, ldh, act, static_cast<float*>(dz));
+                                                         rows, cols, ldz, ldh, act, static_cast<float*>(dz), tile_expert);
   } else {
     CSMOE_CHECK_ARG(false, "csmoe_act_bwd: unsupported dtype %d", dtype);
   }

@@ -340,7 +340,7 @@ class EPSparseFFNFn(Function):
             dz = ops.gemm_rows(dyp, w2b, w_is_kn=not spec.kn_layout, route=lr, act_bwd=spec.act, aux=z)
         else:
             dh = ops.gemm_rows(dyp, w2b, w_is_kn=not spec.kn_layout, route=lr)
-            dz = dh if spec.act == ops.ACT_NONE else ops.act_bwd(z, dh, spec.act)
+            dz = dh if spec.act == ops.ACT_NONE else ops.act_bwd(z, dh, spec.act, lr)
         db1 = ops.bias_grad(dz, El, route=lr, out_dtype=w1.dtype) if ctx.has_b[0] else None
         if spec.kn_layout:
             dw1 = ops.gemm_reduce(xp, dz, El, route=lr, out_dtype=w1.dtype)

@@ -66,7 +66,7 @@ def _ffn_first(xp, w1, b1, spec: FFNSpec, **where):
         return z, h
     if spec.glu:
         z = ops.gemm_rows(xp, w1, w_is_kn=spec.kn_layout, bias=b1, **where)
-        return z, ops.act_fwd(z, spec.act)
+        return z, ops.act_fwd(z, spec.act, where.get("route"))
     if spec.act == ops.ACT_NONE:
         z = ops.gemm_rows(xp, w1, w_is_kn=spec.kn_layout, bias=b1, **where)
         return z, z
@@ -150,7 +150,7 @@ class SparseFFNFn(Function):
             dz = ops.gemm_rows(dyp, w2b, w_is_kn=not spec.kn_layout, route=route, act_bwd=spec.act, aux=z)
         else:
             dh = ops.gemm_rows(dyp, w2b, w_is_kn=not spec.kn_layout, route=route)
-            dz = dh if spec.act == ops.ACT_NONE else ops.act_bwd(z, dh, spec.act)
+            dz = dh if spec.act == ops.ACT_NONE else ops.act_bwd(z, dh, spec.act, route)
         db1 = ops.bias_grad(dz, E, route=route, out_dtype=w1.dtype) if ctx.has_b[0] else None
         if spec.kn_layout:
             dw1 = ops.gemm_reduce(xp, dz, E, route=route, out_dtype=w1.dtype)  # [E, D, H]

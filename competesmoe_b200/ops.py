@@ -350,24 +350,32 @@ def gemm_reduce(a: torch.Tensor, b: torch.Tensor, num_experts: int, *, route: Op
 
 
 # ----------------------------------------------------------------------------------------------- elementwise
-def act_fwd(z: torch.Tensor, act: int) -> torch.Tensor:
+def _tile_map(route: Optional[Route], rows: int):
+    """The route's tile map when `rows` is its padded row space (row tiles past the routed rows are skipped)."""
+    if route is None or route.tile_expert is None or rows != route.row_cap:
+        return None
+    return route.tile_expert.data_ptr()
+
+
+def act_fwd(z: torch.Tensor, act: int, route: Optional[Route] = None) -> torch.Tensor:
     _cuda(z)
     assert z.dim() == 2 and z.stride(1) == 1
     rows = z.shape[0]
     cols = z.shape[1] // 2 if act == ACT_SILU_GLU else z.shape[1]
     h = torch.empty(rows, cols, dtype=z.dtype, device=z.device)
-    _call("csmoe_act_fwd", _p(z), _dt(z), rows, cols, z.stride(0), act, _p(h), cols, _stream())
+    _call("csmoe_act_fwd", _p(z), _dt(z), rows, cols, z.stride(0), act, _p(h), cols, _tile_map(route, rows), _stream())
     return h
 
 
-def act_bwd(z: torch.Tensor, dh: torch.Tensor, act: int) -> torch.Tensor:
+def act_bwd(z: torch.Tensor, dh: torch.Tensor, act: int, route: Optional[Route] = None) -> torch.Tensor:
     _cuda(z, dh)
     dh = dh.contiguous()
     rows = z.shape[0]
     cols = z.shape[1] // 2 if act == ACT_SILU_GLU else z.shape[1]
     assert dh.shape == (rows, cols) and dh.dtype == z.dtype
     dz = torch.empty_like(z)
-    _call("csmoe_act_bwd", _p(z), _p(dh), _dt(z), rows, cols, z.stride(0), cols, act, _p(dz), _stream())
+    _call("csmoe_act_bwd", _p(z), _p(dh), _dt(z), rows, cols, z.stride(0), cols, act, _p(dz), _tile_map(route, rows),
+          _stream())
     return dz
 
 

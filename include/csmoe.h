@@ -184,11 +184,13 @@ int csmoe_grouped_gemm(const csmoe_gemm_args* args, void* stream);
 
 /* ------------------------------------------------------------------------------------------------ activations
  * Elementwise forward/backward used where the activation is not fused into a GEMM epilogue.
- * fwd: h = act(z).  GLU: z is [rows, 2F], h is [rows, F].   bwd: dz = dh * act'(z). */
+ * fwd: h = act(z).  GLU: z is [rows, 2F], h is [rows, F].   bwd: dz = dh * act'(z).
+ * tile_expert (may be NULL): the routing's [rows / 128] tile map; 128-row tiles with a negative entry hold no routed
+ * rows and are skipped (their outputs are left untouched) -- the padded row space is sized for the worst case. */
 int csmoe_act_fwd(const void* z, int32_t dtype, int64_t rows, int64_t cols, int64_t ldz, int32_t act, void* h,
-                  int64_t ldh, void* stream);
+                  int64_t ldh, const int32_t* tile_expert, void* stream);
 int csmoe_act_bwd(const void* z, const void* dh, int32_t dtype, int64_t rows, int64_t cols, int64_t ldz, int64_t ldh,
-                  int32_t act, void* dz, void* stream);
+                  int32_t act, void* dz, const int32_t* tile_expert, void* stream);
 /* Column sums of g[rows of e, n] per expert -> dbias[e, n] (fp32 accumulate, written as `out_dtype`). */
 int csmoe_bias_grad(const void* g, int32_t dtype, int64_t ldg, int32_t n, int32_t num_experts,
                     const int32_t* pad_offsets, int32_t dense, int64_t dense_rows, void* dbias, int32_t out_dtype,
