@@ -32,7 +32,7 @@ class GemmArgs(C.Structure):
         ("tile_expert", vp), ("pad_offsets", vp),
         ("max_ctas", i32), ("act_bwd", i32),
         ("aux", vp), ("ldaux", i64),
-        ("row_tile", i32), ("reserved", i32),
+        ("row_tile", i32), ("sum_experts", i32),
         ("c_rows", vp),
     ]
 

@@ -9,8 +9,11 @@ namespace {
 
 constexpr int kWarps = 8;
 
-__device__ __forceinline__ float softplus_f(float x) { return x > 20.f ? x : log1pf(expf(x)); }
-__device__ __forceinline__ float sigmoid_sp(float x) { return x > 20.f ? 1.f : 1.f / (1.f + expf(-x)); }
+// softplus(x) = max(x, 0) + log(1 + exp(-|x|)): the argument of the log is in (1, 2], where the fast intrinsics are
+// accurate to ~1e-7 absolute -- far below the bf16 / fp32-mean resolution of the score -- and the kernel stays HBM bound
+// instead of being bound by log1pf / expf (measured: 780 -> ~200 us on [64 x 8192 x 1024]).
+__device__ __forceinline__ float softplus_f(float x) { return fmaxf(x, 0.f) + __logf(1.f + __expf(-fabsf(x))); }
+__device__ __forceinline__ float sigmoid_sp(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 
 template <typename T>
 __global__ void __launch_bounds__(kWarps * 32)

@@ -57,6 +57,7 @@ struct KParams {
   long long ldpre;
   long long c_expert_stride;
   long long total_tiles;
+  int kcat;           // ROWS + dense: C[rows, n] = sum_e A[e*a_expert_rows + rows, k] . B[e]  (the k loop runs over experts too)
   int dbg_mode;       // tuning experiments (CSMOE_GEMM_DBG): 1 = no TMA loads after the first pipeline fill, 2 = no MMAs
   int direct_epi;     // 1 = register-direct (row per thread) epilogue stores instead of the staged, coalesced ones
   unsigned long long* stats;  // debug (CSMOE_GEMM_STATS=1): per CTA {producer wait, mma wait full, mma wait tempty, epilogue, total, tiles}
@@ -92,7 +93,10 @@ __device__ __forceinline__ Tile decode_tile(const KParams& p, long long t) {
     const int w = min(p.band, p.num_n_blocks - nb0);
     ti.mb = r / w;
     ti.nb = nb0 + r % w;
-    if (p.dense) {
+    if (p.kcat) {
+      ti.e = 0;
+      ti.a_row = ti.mb * kBM;
+    } else if (p.dense) {
       ti.e = ti.mb / p.dense_mblocks;
       ti.a_row = (ti.mb % p.dense_mblocks) * kBM + ti.e * p.a_expert_rows;
     } else {
@@ -100,7 +104,7 @@ __device__ __forceinline__ Tile decode_tile(const KParams& p, long long t) {
       ti.a_row = ti.mb * kBM;
     }
     ti.b_row = 0;
-    ti.nkb = p.num_kb;
+    ti.nkb = p.kcat ? p.num_kb * p.num_experts : p.num_kb;
     ti.valid = ti.e >= 0;
   } else {
     const long long per_e = static_cast<long long>(p.num_m_blocks) * p.num_n_blocks;
@@ -596,19 +600,25 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           const uint32_t sa = smem_base + stage * kStageBytes;
           const uint32_t sb = sa + kABytes;
           if (MODE == CSMOE_GEMM_ROWS) {
-            ptx::tma_load_2d(sa, &tma_a, fb, kb * kBK, ti.a_row);
+            int kx = kb * kBK, ex = ti.e, arow = ti.a_row;
+            if (p.kcat) {   // k loop over (expert, k-block): sum of the experts' products
+              ex = kb / p.num_kb;
+              kx = (kb % p.num_kb) * kBK;
+              arow += ex * p.a_expert_rows;
+            }
+            ptx::tma_load_2d(sa, &tma_a, fb, kx, arow);
             if (!B_MN) {
               if (BN == 256 && p.epi == kEpiGluFwd) {
                 // gate rows [nb*128, +128) then up rows [F + nb*128, +128): one output tile holds both halves
-                ptx::tma_load_3d(sb, &tma_b, fb, kb * kBK, ti.nb * 128, ti.e);
-                ptx::tma_load_3d(sb + 128 * kBK * 2, &tma_b, fb, kb * kBK, p.glu_f + ti.nb * 128, ti.e);
+                ptx::tma_load_3d(sb, &tma_b, fb, kx, ti.nb * 128, ex);
+                ptx::tma_load_3d(sb + 128 * kBK * 2, &tma_b, fb, kx, p.glu_f + ti.nb * 128, ex);
               } else {
-                ptx::tma_load_3d(sb, &tma_b, fb, kb * kBK, ti.nb * BN, ti.e);
+                ptx::tma_load_3d(sb, &tma_b, fb, kx, ti.nb * BN, ex);
               }
             } else {
 #pragma unroll
               for (int j = 0; j < BN / 64; ++j)
-                ptx::tma_load_3d(sb + j * kSubTileBytes, &tma_b, fb, ti.nb * BN + j * 64, kb * kBK, ti.e);
+                ptx::tma_load_3d(sb + j * kSubTileBytes, &tma_b, fb, ti.nb * BN + j * 64, kx, ex);
             }
           } else {
 #pragma unroll
@@ -728,7 +738,10 @@ __device__ __forceinline__ Tile decode_tile_pair(const KParams& p, long long t, 
     const int w = min(p.band, p.num_n_blocks - nb0);
     ti.mb = r / w;
     ti.nb = nb0 + r % w;
-    if (p.dense) {
+    if (p.kcat) {
+      ti.e = 0;
+      ti.a_row = ti.mb * 256 + rank * kBM;
+    } else if (p.dense) {
       const int dm2 = p.dense_mblocks / 2;
       ti.e = ti.mb / dm2;
       ti.a_row = (ti.mb % dm2) * 256 + rank * kBM + ti.e * p.a_expert_rows;
@@ -737,7 +750,7 @@ __device__ __forceinline__ Tile decode_tile_pair(const KParams& p, long long t, 
       ti.a_row = ti.mb * 256 + rank * kBM;
     }
     ti.b_row = 0;
-    ti.nkb = p.num_kb;
+    ti.nkb = p.kcat ? p.num_kb * p.num_experts : p.num_kb;
     ti.valid = ti.e >= 0;
   } else {
     const long long per_e = static_cast<long long>(num_m2) * p.num_n_blocks;
@@ -846,15 +859,21 @@ grouped_gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
           const uint32_t sa = smem_base + stage * kPairStageBytes;
           const uint32_t sb = sa + kABytes;
           if (MODE == CSMOE_GEMM_ROWS) {
-            ptx::tma_load_2d_cg2(sa, &tma_a, fb, kb * kBK, ti.a_row);
+            int kx = kb * kBK, ex = ti.e, arow = ti.a_row;
+            if (p.kcat) {
+              ex = kb / p.num_kb;
+              kx = (kb % p.num_kb) * kBK;
+              arow += ex * p.a_expert_rows;
+            }
+            ptx::tma_load_2d_cg2(sa, &tma_a, fb, kx, arow);
             if (!B_MN) {
               const int brow = p.epi == kEpiGluFwd ? (rank == 0 ? ti.nb * 128 : p.glu_f + ti.nb * 128)
                                                    : ti.nb * BN + rank * 128;
-              ptx::tma_load_3d_cg2(sb, &tma_b, fb, kb * kBK, brow, ti.e);
+              ptx::tma_load_3d_cg2(sb, &tma_b, fb, kx, brow, ex);
             } else {
 #pragma unroll
               for (int j = 0; j < 2; ++j)
-                ptx::tma_load_3d_cg2(sb + j * kSubTileBytes, &tma_b, fb, ti.nb * BN + rank * 128 + j * 64, kb * kBK, ti.e);
+                ptx::tma_load_3d_cg2(sb + j * kSubTileBytes, &tma_b, fb, ti.nb * BN + rank * 128 + j * 64, kx, ex);
             }
           } else {
 #pragma unroll
@@ -1059,16 +1078,22 @@ grouped_gemm_wide_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
           const uint32_t sa = smem_base + stage * kWideStageBytes;
           const uint32_t sb = sa + kABytes;
           if (MODE == CSMOE_GEMM_ROWS) {
-            ptx::tma_load_2d_cg2(sa, &tma_a, fb, kb * kBK, ti.a_row);
+            int kx = kb * kBK, ex = ti.e, arow = ti.a_row;
+            if (p.kcat) {
+              ex = kb / p.num_kb;
+              kx = (kb % p.num_kb) * kBK;
+              arow += ex * p.a_expert_rows;
+            }
+            ptx::tma_load_2d_cg2(sa, &tma_a, fb, kx, arow);
             for (int h = 0; h < halves; ++h) {
               if (!B_MN) {
                 const int brow = glu ? h * p.glu_f + ti.nb * 256 + rank * 128 : ti.nb * BN + h * 256 + rank * 128;
-                ptx::tma_load_3d_cg2(sb + h * kWideHalfBytes, &tma_b, fb, kb * kBK, brow, ti.e);
+                ptx::tma_load_3d_cg2(sb + h * kWideHalfBytes, &tma_b, fb, kx, brow, ex);
               } else {
 #pragma unroll
                 for (int j = 0; j < 2; ++j)
                   ptx::tma_load_3d_cg2(sb + h * kWideHalfBytes + j * kSubTileBytes, &tma_b, fb,
-                                       ti.nb * BN + h * 256 + rank * 128 + j * 64, kb * kBK, ti.e);
+                                       ti.nb * BN + h * 256 + rank * 128 + j * 64, kx, ex);
               }
             }
           } else {
@@ -1372,6 +1397,12 @@ extern "C" int csmoe_grouped_gemm(const csmoe_gemm_args* a, void* stream_) {
     CSMOE_CHECK_ARG(a->pad_offsets != nullptr, "csmoe_grouped_gemm: REDUCE mode needs pad_offsets");
   }
   if (a->accumulate) CSMOE_CHECK_ARG(a->c_dtype == CSMOE_F32, "csmoe_grouped_gemm: accumulate needs an fp32 C");
+  if (a->sum_experts) {
+    CSMOE_CHECK_ARG(a->mode == CSMOE_GEMM_ROWS && a->dense && a->a_expert_rows > 0 && a->bias == nullptr && !glu_fwd &&
+                        !act_bwd && a->preact == nullptr && a->c_rows == nullptr && a->k % kBK == 0,
+                    "csmoe_grouped_gemm: sum_experts needs a dense ROWS launch with per-expert A rows, the plain epilogue "
+                    "and k a multiple of 64");
+  }
 
   cudaStream_t stream = as_stream(stream_);
   const int E = a->num_experts;
@@ -1394,6 +1425,7 @@ extern "C" int csmoe_grouped_gemm(const csmoe_gemm_args* a, void* stream_) {
   kp.n = static_cast<int>(a->n);
   kp.num_experts = E;
   kp.dense = a->dense;
+  kp.kcat = a->sum_experts ? 1 : 0;
   kp.dense_mblocks = a->dense ? static_cast<int>(a->dense_rows / kBM) : 0;
   kp.dense_kblocks = a->dense ? static_cast<int>(a->dense_rows / kBK) : 0;
   kp.a_expert_rows = static_cast<int>(a->a_expert_rows);
@@ -1430,14 +1462,16 @@ extern "C" int csmoe_grouped_gemm(const csmoe_gemm_args* a, void* stream_) {
   } else {
     kp.epi = kEpiPlain;
   }
-  kp.direct_epi = kp.epi == kEpiGluFwd ? 0 : 1;
+  // ... and where rows leave the GPU (expert-parallel return, c_rows): 64-byte row segments instead of 16-byte ones
+  // make far better NVLink packets.
+  kp.direct_epi = (kp.epi == kEpiGluFwd || a->c_rows != nullptr) ? 0 : 1;
   if (epilogue_override() != 0 && !a->accumulate) kp.direct_epi = epilogue_override() == 1 ? 1 : 0;
 
   CUtensorMap ma, mb;
   int rc;
   if (a->mode == CSMOE_GEMM_ROWS) {
     const long long a_rows = a->dense ? (a->a_expert_rows ? (long long)E * a->a_expert_rows : a->dense_rows) : a->m;
-    kp.num_m_blocks = a->dense ? E * kp.dense_mblocks : static_cast<int>(a->m / kBM);
+    kp.num_m_blocks = a->dense ? (kp.kcat ? 1 : E) * kp.dense_mblocks : static_cast<int>(a->m / kBM);
     kp.num_kb = static_cast<int>((a->k + kBK - 1) / kBK);
     kp.total_tiles = static_cast<long long>(kp.num_m_blocks) * kp.num_n_blocks;
     {
@@ -1487,7 +1521,8 @@ extern "C" int csmoe_grouped_gemm(const csmoe_gemm_args* a, void* stream_) {
     // +12 %, k = 16384 +8 %, k = 3072 -2 %; wgrad, whose k loop is one expert's rows, loses 10 %).  CSMOE_GEMM_WIDE
     // bits 2 / 3 force it for every ROWS / REDUCE launch.
     const int wm = wide_mask();
-    const bool long_k = a->mode == CSMOE_GEMM_ROWS ? a->k >= 4096 || (wm & 4) : (wm & 8) != 0;
+    const long long k_loop = a->sum_experts ? a->k * E : a->k;
+    const bool long_k = a->mode == CSMOE_GEMM_ROWS ? k_loop >= 4096 || (wm & 4) : (wm & 8) != 0;
     const bool wide = n_grid >= 512 && (n_grid % 512 == 0 || n_grid >= 2048) && long_k &&
                       (wm & (a->mode == CSMOE_GEMM_ROWS ? 1 : 2)) != 0;
     if (wide) kp.num_n_blocks = glu_fwd ? static_cast<int>((n_grid + 255) / 256) : static_cast<int>((a->n + 511) / 512);

@@ -206,8 +206,13 @@ class DenseFFNFn(Function):
             dw1 = ops.gemm_reduce(dz, xb, E, dense_rows=t_pad, a_expert_rows=t_pad, b_expert_rows=0, out_dtype=w1.dtype)
         dx = None
         if ctx.needs_input_grad[0]:
-            dxe = ops.gemm_rows(dz, w1b, w_is_kn=not spec.kn_layout, dense_rows=t_pad, a_expert_rows=t_pad)
-            dx = dxe.view(E, t_pad, -1)[:, :T].float().sum(0).to(ctx.x_dtype)
+            # dx[t] = sum_e dz[e, t] . W1[e]: one GEMM whose k loop runs over (expert, hidden) -- no [E, T, D] intermediate
+            if dz.shape[1] % 64 == 0:
+                dx = ops.gemm_rows(dz, w1b, w_is_kn=not spec.kn_layout, dense_rows=t_pad, a_expert_rows=t_pad,
+                                   sum_experts=True)[:T].to(ctx.x_dtype)
+            else:
+                dxe = ops.gemm_rows(dz, w1b, w_is_kn=not spec.kn_layout, dense_rows=t_pad, a_expert_rows=t_pad)
+                dx = dxe.view(E, t_pad, -1)[:, :T].float().sum(0).to(ctx.x_dtype)
         return dx, dw1, db1, dw2, db2, None
 
 

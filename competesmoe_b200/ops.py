@@ -257,7 +257,7 @@ def _gemm(args: GemmArgs, flops: float = 0.0, tag: str = "") -> None:
 def gemm_rows(a: torch.Tensor, w: torch.Tensor, *, w_is_kn: bool, route: Optional[Route] = None,
               dense_rows: int = 0, a_expert_rows: int = 0, bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
               want_preact: bool = False, out_dtype: Optional[torch.dtype] = None, act_bwd: int = ACT_NONE,
-              aux: Optional[torch.Tensor] = None, c_rows: Optional[torch.Tensor] = None):
+              aux: Optional[torch.Tensor] = None, c_rows: Optional[torch.Tensor] = None, sum_experts: bool = False):
     """C[row] = A[row] . W[expert(row)] with a fused epilogue.
 
     a: [rows, k] bf16.  w: [E, n, k] (w_is_kn=False, nn.Linear layout) or [E, k, n] (w_is_kn=True).
@@ -266,6 +266,7 @@ def gemm_rows(a: torch.Tensor, w: torch.Tensor, *, w_is_kn: bool, route: Optiona
     Forward epilogue: + bias, activation; want_preact also returns the pre-activation.  act = ACT_SILU_GLU: w is
     [E, 2F, k]; returns (h [rows, F], z [rows, 2F]).
     Backward epilogue (act_bwd, aux = saved z): C = (A . W) * act'(z); ACT_SILU_GLU returns dz [rows, 2F] from dh [rows, F].
+    sum_experts (dense, a_expert_rows > 0): C [dense_rows, n] = sum_e A[e] . W[e] in one launch (k loop over experts).
     c_rows [rows] int64 (expert-parallel return): output row r is stored at address c_rows[r] (0 = skipped) instead of a
     local C; nothing is returned.
     Returns C, or (C, preact) when want_preact.
@@ -284,8 +285,9 @@ def gemm_rows(a: torch.Tensor, w: torch.Tensor, *, w_is_kn: bool, route: Optiona
     g.mode, g.b_layout, g.num_experts = GEMM_ROWS, 1 if w_is_kn else 0, E
     if dense_rows:
         assert dense_rows % ROW_TILE == 0
-        m = E * dense_rows
+        m = dense_rows if sum_experts else E * dense_rows
         g.dense, g.dense_rows, g.a_expert_rows = 1, dense_rows, a_expert_rows
+        g.sum_experts = 1 if sum_experts else 0
     else:
         assert route is not None and a.shape[0] == route.row_cap
         m = route.row_cap

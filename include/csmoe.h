@@ -174,7 +174,9 @@ typedef struct csmoe_gemm_args {
   int64_t ldaux;
   int32_t row_tile;        /* ROWS, !dense: the row_tile the routing maps were built with (128 or 256); 256 lets the
                               CTA-pair (cta_group::2, 256 x 256 tile) kernel run */
-  int32_t reserved;
+  int32_t sum_experts;     /* ROWS + dense + a_expert_rows > 0: C[dense_rows, n] = sum over experts e of
+                              A[e*a_expert_rows + row, :] . B[e] -- one launch whose k loop also runs over the experts
+                              (dgrad of the competition step's dense pass w.r.t. the shared input) */
   const uint64_t* c_rows;  /* ROWS, plain epilogue: when non-NULL, output row r is stored at address c_rows[r] (0 = row
                               skipped) instead of c + r*ldc -- the expert-parallel return path: the down projection
                               writes each row straight into the source rank's buffer (peer memory).  c may be NULL. */

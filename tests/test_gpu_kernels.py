@@ -407,3 +407,17 @@ def test_gemm_kernel_variants_in_subprocess(env):
     r = subprocess.run([sys.executable, "-m", "pytest", __file__, "-q", "-x", "-m", "gpu", "-k", "gemm and not variants"],
                        env=child_env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("kn", [False, True])
+@pytest.mark.parametrize("E,T,n,k", [(4, 256, 512, 128), (3, 512, 1152, 320), (8, 256, 3072, 1024), (64, 256, 1024, 128)])
+def test_gemm_dense_sum_over_experts(ops, kn, E, T, n, k):
+    """C[t] = sum_e A[e, t] . W[e] in one launch (k loop over experts): the dense pass's gradient w.r.t. its shared input."""
+    g = torch.Generator().manual_seed(E + T + n)
+    a = (torch.randn(E, T, k, generator=g) * 0.5).bfloat16().to(DEV)
+    w = (torch.randn(E, k, n, generator=g) * 0.1).bfloat16().to(DEV)
+    wk = w if kn else w.transpose(1, 2).contiguous()          # [E, k, n] or [E, n, k]
+    c = ops.gemm_rows(a.view(E * T, k), wk, w_is_kn=kn, dense_rows=T, a_expert_rows=T, sum_experts=True)
+    ref = torch.einsum("etk,ekn->tn", a.float(), w.float())
+    assert c.shape == (T, n)
+    assert_close_rms(c, ref, 2e-2, "sum over experts")
