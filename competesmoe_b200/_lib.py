@@ -34,6 +34,7 @@ class GemmArgs(C.Structure):
         ("aux", vp), ("ldaux", i64),
         ("row_tile", i32), ("sum_experts", i32),
         ("c_rows", vp),
+        ("rowsum", vp), ("rowsum_round", i32), ("reserved2", i32),
     ]
 
 
@@ -61,6 +62,7 @@ _SIGNATURES = {
     "csmoe_bias_grad": (i32, [vp, i32, i64, i32, i32, vp, i32, i64, vp, i32, vp]),
     "csmoe_cast_f32_bf16": (i32, [vp, vp, i64, vp]),
     "csmoe_affinity_fwd": (i32, [vp, i32, i32, i64, i64, i32, i32, vp, vp]),
+    "csmoe_affinity_from_rowsum": (i32, [vp, i32, i32, i64, i64, i32, i32, vp, vp]),
     "csmoe_affinity_bwd": (i32, [vp, vp, i32, i32, i64, i64, i32, i32, vp, vp]),
     "csmoe_diversity_fwd": (i32, [vp, i32, i64, i64, i32, i32, vp, vp, vp, vp, vp, vp]),
     "csmoe_compete_bwd": (i32, [vp, i32, i32, i64, i64, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]),

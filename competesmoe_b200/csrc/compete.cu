@@ -44,6 +44,22 @@ affinity_fwd_kernel(const T* __restrict__ y, int E, long long Tn, long long t_pa
   }
 }
 
+// Finish the score from the per-(row, 64-column group) sums the GEMM epilogue wrote.
+__global__ void __launch_bounds__(256)
+affinity_from_rowsum_kernel(const float* __restrict__ rowsum, int groups, int E, long long Tn, long long t_pad, int D,
+                            int round_bf16, float* __restrict__ aff) {
+  const long long total = static_cast<long long>(E) * Tn;
+  for (long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * 256) {
+    const long long e = i / Tn, t = i % Tn;
+    const float* r = rowsum + (e * t_pad + t) * groups;
+    float s = 0.f;
+    for (int g = 0; g < groups; ++g) s += r[g];
+    const float m = s / static_cast<float>(D);
+    aff[t * E + e] = round_bf16 ? bf16_round(m) : m;
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kWarps * 32)
 affinity_bwd_kernel(const T* __restrict__ y, const float* __restrict__ daff, int E, long long Tn, long long t_pad, int D,
@@ -250,6 +266,19 @@ extern "C" int csmoe_affinity_fwd(const void* y, int32_t dtype, int32_t E, int64
   } else {
     CSMOE_CHECK_ARG(false, "csmoe_affinity_fwd: unsupported dtype %d", dtype);
   }
+  CSMOE_CHECK_LAUNCH();
+  return CSMOE_OK;
+}
+
+extern "C" int csmoe_affinity_from_rowsum(const float* rowsum, int32_t groups, int32_t E, int64_t T_, int64_t t_pad,
+                                          int32_t D, int32_t round_dtype, float* aff, void* stream_) {
+  CSMOE_CHECK_ARG(rowsum && aff, "csmoe_affinity_from_rowsum: NULL pointer");
+  CSMOE_CHECK_ARG(E >= 1 && D > 0 && groups == (D + 63) / 64 && t_pad >= T_, "csmoe_affinity_from_rowsum: bad sizes");
+  if (T_ == 0) return CSMOE_OK;
+  const long long total = static_cast<long long>(E) * T_;
+  const unsigned grid = static_cast<unsigned>((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+  affinity_from_rowsum_kernel<<<grid, 256, 0, as_stream(stream_)>>>(rowsum, groups, E, T_, t_pad, D,
+                                                                    round_dtype == CSMOE_BF16 ? 1 : 0, aff);
   CSMOE_CHECK_LAUNCH();
   return CSMOE_OK;
 }

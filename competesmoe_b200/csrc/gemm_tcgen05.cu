@@ -57,6 +57,9 @@ struct KParams {
   long long ldpre;
   long long c_expert_stride;
   long long total_tiles;
+  float* rowsum;      // plain ROWS epilogue: rowsum[row, col/64] = sum over the 64-column group of softplus(stored value)
+  int rowsum_ld;      // (the competition step's neural-response score, reduced in the epilogue); groups per row
+  int rowsum_round;   // 1 = round every softplus to bf16 first (eager bf16 reference arithmetic)
   int kcat;           // ROWS + dense: C[rows, n] = sum_e A[e*a_expert_rows + rows, k] . B[e]  (the k loop runs over experts too)
   int dbg_mode;       // tuning experiments (CSMOE_GEMM_DBG): 1 = no TMA loads after the first pipeline fill, 2 = no MMAs
   int direct_epi;     // 1 = register-direct (row per thread) epilogue stores instead of the staged, coalesced ones
@@ -131,9 +134,11 @@ __device__ __forceinline__ Tile decode_tile(const KParams& p, long long t) {
   return ti;
 }
 
+__device__ __forceinline__ float softplus_fast(float x) { return fmaxf(x, 0.f) + __logf(1.f + __expf(-fabsf(x))); }
+
 template <typename OutT>
 __device__ __forceinline__ void epilogue_store8(const KParams& p, const float (&acc)[8], OutT* c_row, OutT* pre_row,
-                                                const void* bias_row, int col) {
+                                                const void* bias_row, int col, float* rs = nullptr) {
   float z[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) z[i] = acc[i];
@@ -160,6 +165,13 @@ __device__ __forceinline__ void epilogue_store8(const KParams& p, const float (&
     for (int i = 0; i < 8; ++i) z[i] = act_apply(z[i], p.act);
   }
   store8(c_row + col, z);
+  if (rs != nullptr) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float sp = softplus_fast(round_as(z[i], static_cast<const OutT*>(nullptr)));   // of the value as stored
+      *rs += p.rowsum_round ? bf16_round(sp) : sp;
+    }
+  }
 }
 
 // One output tile (this CTA's 128 rows x BN columns) from TMEM to global memory.  `t_row` = TMEM address of this warp's
@@ -187,6 +199,8 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, const Tile& ti, 
       row_ptr = __ldg(p.c_rows + out_row);
       row_ok = row_ptr != 0ull;
     }
+    float rs = 0.f;
+    float* rs_ptr = (MODE == CSMOE_GEMM_ROWS && p.rowsum != nullptr) ? &rs : nullptr;
 #pragma unroll 1
     for (int chunk = half * (BN / 64); chunk < (half + 1) * (BN / 64); ++chunk) {
       uint32_t v[32];
@@ -210,16 +224,21 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, const Tile& ti, 
               float* c_row = row_ptr ? reinterpret_cast<float*>(row_ptr)
                                      : reinterpret_cast<float*>(p.c) + c_off + out_row * p.ldc;
               float* pre_row = p.preact ? reinterpret_cast<float*>(p.preact) + out_row * p.ldpre : nullptr;
-              epilogue_store8<float>(p, a8, c_row, pre_row, bias_row, col);
+              epilogue_store8<float>(p, a8, c_row, pre_row, bias_row, col, rs_ptr);
             } else {
               __nv_bfloat16* c_row = row_ptr ? reinterpret_cast<__nv_bfloat16*>(row_ptr)
                                              : reinterpret_cast<__nv_bfloat16*>(p.c) + c_off + out_row * p.ldc;
               __nv_bfloat16* pre_row =
                   p.preact ? reinterpret_cast<__nv_bfloat16*>(p.preact) + out_row * p.ldpre : nullptr;
-              epilogue_store8<__nv_bfloat16>(p, a8, c_row, pre_row, bias_row, col);
+              epilogue_store8<__nv_bfloat16>(p, a8, c_row, pre_row, bias_row, col, rs_ptr);
             }
           }
         }
+      }
+      // every second 32-column chunk closes a 64-column group of the row-sum output
+      if (rs_ptr != nullptr && (chunk & 1)) {
+        if (col0 - 32 < p.n) p.rowsum[out_row * p.rowsum_ld + (col0 >> 6)] = rs;
+        rs = 0.f;
       }
     }
   } else if (p.epi == kEpiGluFwd) {
@@ -1397,6 +1416,10 @@ extern "C" int csmoe_grouped_gemm(const csmoe_gemm_args* a, void* stream_) {
     CSMOE_CHECK_ARG(a->pad_offsets != nullptr, "csmoe_grouped_gemm: REDUCE mode needs pad_offsets");
   }
   if (a->accumulate) CSMOE_CHECK_ARG(a->c_dtype == CSMOE_F32, "csmoe_grouped_gemm: accumulate needs an fp32 C");
+  if (a->rowsum != nullptr) {
+    CSMOE_CHECK_ARG(a->mode == CSMOE_GEMM_ROWS && !glu_fwd && !act_bwd && a->c_rows == nullptr && a->c != nullptr,
+                    "csmoe_grouped_gemm: rowsum needs a ROWS launch with the plain epilogue and a local C");
+  }
   if (a->sum_experts) {
     CSMOE_CHECK_ARG(a->mode == CSMOE_GEMM_ROWS && a->dense && a->a_expert_rows > 0 && a->bias == nullptr && !glu_fwd &&
                         !act_bwd && a->preact == nullptr && a->c_rows == nullptr && a->k % kBK == 0,
@@ -1426,6 +1449,9 @@ extern "C" int csmoe_grouped_gemm(const csmoe_gemm_args* a, void* stream_) {
   kp.num_experts = E;
   kp.dense = a->dense;
   kp.kcat = a->sum_experts ? 1 : 0;
+  kp.rowsum = a->rowsum;
+  kp.rowsum_ld = static_cast<int>((a->n + 63) / 64);
+  kp.rowsum_round = a->rowsum_round;
   kp.dense_mblocks = a->dense ? static_cast<int>(a->dense_rows / kBM) : 0;
   kp.dense_kblocks = a->dense ? static_cast<int>(a->dense_rows / kBK) : 0;
   kp.a_expert_rows = static_cast<int>(a->a_expert_rows);
@@ -1465,7 +1491,8 @@ extern "C" int csmoe_grouped_gemm(const csmoe_gemm_args* a, void* stream_) {
   // ... and where rows leave the GPU (expert-parallel return, c_rows): 64-byte row segments instead of 16-byte ones
   // make far better NVLink packets.
   kp.direct_epi = (kp.epi == kEpiGluFwd || a->c_rows != nullptr) ? 0 : 1;
-  if (epilogue_override() != 0 && !a->accumulate) kp.direct_epi = epilogue_override() == 1 ? 1 : 0;
+  if (a->rowsum != nullptr) kp.direct_epi = 1;
+  if (epilogue_override() != 0 && !a->accumulate && a->rowsum == nullptr) kp.direct_epi = epilogue_override() == 1 ? 1 : 0;
 
   CUtensorMap ma, mb;
   int rc;

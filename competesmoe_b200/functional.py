@@ -31,6 +31,10 @@ from ._lib import ROW_TILE
 #   (0.57 ms vs 0.33 + 0.17 ms) -> off by default until the epilogue I/O is staged through shared memory.
 _FUSE_FWD = os.environ.get("CSMOE_FUSE_EPILOGUE_FWD", "1") != "0"
 _FUSE_BWD = os.environ.get("CSMOE_FUSE_EPILOGUE_BWD", "0") != "0"
+#   competition score (mean softplus of the dense outputs) reduced in the down projection's epilogue: "1" always,
+#   "0" never (stand-alone csmoe_affinity_fwd re-reads y), "auto" = only where that GEMM's main loop is long enough to
+#   hide the extra epilogue math (contraction >= 1024; the sigma-MoE shapes with H = 128 are epilogue bound).
+_SCORE_EPILOGUE = os.environ.get("CSMOE_SCORE_EPILOGUE", "auto")
 
 
 @dataclass(frozen=True)
@@ -165,24 +169,37 @@ class SparseFFNFn(Function):
 
 # ------------------------------------------------------------------------------------------------ dense experts
 class DenseFFNFn(Function):
-    """y[e, t] = FFN_e(x[t]) for every expert and token -> [E * t_pad, Dout] (t_pad = T rounded up to the row tile)."""
+    """y[e, t] = FFN_e(x[t]) for every expert and token -> [E * t_pad, Dout] (t_pad = T rounded up to the row tile).
+
+    score_round (None / bool): also return rowsum [E * t_pad, ceil(Dout / 64)] = per-64-column sums of softplus(y),
+    reduced in the epilogue of the down projection (north-star stage 2: the neural-response score never re-reads y);
+    the bool selects eager-bf16 rounding of every softplus.  The row sums carry no gradient: CompeteTailFn
+    differentiates the score through y."""
 
     @staticmethod
-    def forward(ctx, x, w1, b1, w2, b2, spec: FFNSpec):
+    def forward(ctx, x, w1, b1, w2, b2, spec: FFNSpec, score_round: Optional[bool] = None):
         T = x.shape[0]
         t_pad = (T + 2 * ROW_TILE - 1) // (2 * ROW_TILE) * (2 * ROW_TILE)   # 256: CTA-pair GEMM tiles
         xb = _pad_rows(_bf16(x), t_pad)
         w1b, w2b = _bf16(w1), _bf16(w2)
         z, h = _ffn_first(xb, w1b, b1, spec, dense_rows=t_pad, a_expert_rows=0)
-        y = ops.gemm_rows(h, w2b, w_is_kn=spec.kn_layout, bias=b2, dense_rows=t_pad, a_expert_rows=t_pad)
+        fuse_score = score_round is not None and (_SCORE_EPILOGUE == "1" or (_SCORE_EPILOGUE == "auto" and h.shape[1] >= 1024))
+        y = ops.gemm_rows(h, w2b, w_is_kn=spec.kn_layout, bias=b2, dense_rows=t_pad, a_expert_rows=t_pad,
+                          rowsum_softplus=score_round if fuse_score else None)
         ctx.spec, ctx.T, ctx.t_pad, ctx.x_dtype = spec, T, t_pad, x.dtype
         ctx.has_b = (b1 is not None, b2 is not None)
         ctx.save_for_backward(xb, z, h, w1, w2)
-        return y
+        if score_round is None:
+            return y
+        if not fuse_score:
+            return y, None
+        y, rowsum = y
+        ctx.mark_non_differentiable(rowsum)
+        return y, rowsum
 
     @staticmethod
     @once_differentiable
-    def backward(ctx, dy):
+    def backward(ctx, dy, _drowsum=None):
         xb, z, h, w1, w2 = ctx.saved_tensors
         spec, T, t_pad = ctx.spec, ctx.T, ctx.t_pad
         E = w1.shape[0]
@@ -213,7 +230,7 @@ class DenseFFNFn(Function):
             else:
                 dxe = ops.gemm_rows(dz, w1b, w_is_kn=not spec.kn_layout, dense_rows=t_pad, a_expert_rows=t_pad)
                 dx = dxe.view(E, t_pad, -1)[:, :T].float().sum(0).to(ctx.x_dtype)
-        return dx, dw1, db1, dw2, db2, None
+        return dx, dw1, db1, dw2, db2, None, None
 
 
 class AffinityFn(Function):
@@ -293,9 +310,12 @@ class CompeteTailFn(Function):
 
     @staticmethod
     def forward(ctx, y, num_experts: int, T: int, t_pad: int, top_k: int, sigmoid: bool, x_dtype: torch.dtype,
-                spec: FFNSpec):
+                spec: FFNSpec, rowsum: Optional[torch.Tensor] = None):
         eager_bf16 = x_dtype == torch.bfloat16
-        aff = ops.affinity_fwd(y, num_experts, T, t_pad, eager_bf16)
+        if rowsum is not None:   # the score was reduced in the down projection's epilogue: y is not read again
+            aff = ops.affinity_from_rowsum(rowsum, num_experts, T, t_pad, y.shape[1], eager_bf16)
+        else:
+            aff = ops.affinity_fwd(y, num_experts, T, t_pad, eager_bf16)
         w, idx = ops.topk_renorm(aff, top_k, sigmoid=sigmoid, round_dtype=x_dtype, round_out=eager_bf16)
         rows = (idx.long() * t_pad + torch.arange(T, device=idx.device).unsqueeze(1)).to(torch.int32).reshape(-1)
         out = ops.combine_fwd(y, rows, idx.reshape(-1), w, T, top_k, round_each=spec.round_each, round_w=spec.round_w)
@@ -330,4 +350,4 @@ class CompeteTailFn(Function):
         dy = ops.compete_bwd(y, E, T, t_pad, idx, daff=daff, w=wu if dout is not None else None, dout=dout,
                              inv_norm=inv_norm if ddiv is not None else None, sim=sim if ddiv is not None else None,
                              g_div=ddiv)
-        return dy, None, None, None, None, None, None, None
+        return dy, None, None, None, None, None, None, None, None

@@ -271,12 +271,13 @@ class CompeteSMoE(MoeLayer):
         infor_aux = {}
         if compete:
             w1, b1, w2, b2 = self._all_expert_weights(w1, b1, w2, b2)
-            y_all = DenseFFNFn.apply(x2, w1, b1, w2, b2, spec)                       # [E * t_pad, Dout]
+            # dense pass; the per-row softplus sums of the score come out of the down projection's epilogue
+            y_all, score_sums = DenseFFNFn.apply(x2, w1, b1, w2, b2, spec, x.dtype == torch.bfloat16)   # [E * t_pad, Dout]
             t_pad = y_all.shape[0] // E
             # score, top-k, combine (the selected experts' outputs are reused from the dense pass instead of being
             # recomputed as compute_moe does at competesmoe.py:374) and diversity loss: one autograd node
             aff, aff_w, aff_idx, out, diversity_loss = CompeteTailFn.apply(
-                y_all, E, T, t_pad, K, bool(getattr(self.args, "norm_sigmoid", False)), x.dtype, spec)
+                y_all, E, T, t_pad, K, bool(getattr(self.args, "norm_sigmoid", False)), x.dtype, spec, score_sums)
             aff_softmax = F.softmax(aff, dim=-1, dtype=torch.float32)
             li = aff_idx.long()
             if getattr(self.args, "hybrid", False):

@@ -19,7 +19,7 @@ from ._lib import (ACT_GELU, ACT_GELU_TANH, ACT_NONE, ACT_RELU, ACT_SILU, ACT_SI
 __all__ = [
     "Route", "route_build", "router_fwd", "topk_renorm", "gather_rows", "combine_fwd", "combine_bwd_w",
     "scatter_reduce", "gemm_rows", "gemm_reduce", "act_fwd", "act_bwd", "bias_grad", "cast_bf16", "affinity_fwd",
-    "affinity_bwd", "diversity_fwd", "compete_bwd", "ACT_NONE", "ACT_RELU", "ACT_GELU", "ACT_GELU_TANH", "ACT_SILU", "ACT_SILU_GLU",
+    "affinity_bwd", "affinity_from_rowsum", "diversity_fwd", "compete_bwd", "ACT_NONE", "ACT_RELU", "ACT_GELU", "ACT_GELU_TANH", "ACT_SILU", "ACT_SILU_GLU",
 ]
 
 launch_count = 0  # number of libcsmoe kernels launched so far (bench.py reports the delta over its timed region)
@@ -257,7 +257,8 @@ def _gemm(args: GemmArgs, flops: float = 0.0, tag: str = "") -> None:
 def gemm_rows(a: torch.Tensor, w: torch.Tensor, *, w_is_kn: bool, route: Optional[Route] = None,
               dense_rows: int = 0, a_expert_rows: int = 0, bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
               want_preact: bool = False, out_dtype: Optional[torch.dtype] = None, act_bwd: int = ACT_NONE,
-              aux: Optional[torch.Tensor] = None, c_rows: Optional[torch.Tensor] = None, sum_experts: bool = False):
+              aux: Optional[torch.Tensor] = None, c_rows: Optional[torch.Tensor] = None, sum_experts: bool = False,
+              rowsum_softplus: Optional[bool] = None):
     """C[row] = A[row] . W[expert(row)] with a fused epilogue.
 
     a: [rows, k] bf16.  w: [E, n, k] (w_is_kn=False, nn.Linear layout) or [E, k, n] (w_is_kn=True).
@@ -267,6 +268,8 @@ def gemm_rows(a: torch.Tensor, w: torch.Tensor, *, w_is_kn: bool, route: Optiona
     [E, 2F, k]; returns (h [rows, F], z [rows, 2F]).
     Backward epilogue (act_bwd, aux = saved z): C = (A . W) * act'(z); ACT_SILU_GLU returns dz [rows, 2F] from dh [rows, F].
     sum_experts (dense, a_expert_rows > 0): C [dense_rows, n] = sum_e A[e] . W[e] in one launch (k loop over experts).
+    rowsum_softplus (None = off; True / False = round every softplus to bf16 or not): additionally returns
+    rowsum [rows, ceil(n / 64)] f32, the per-64-column sums of softplus(C) (the competition score, see affinity_from_rowsum).
     c_rows [rows] int64 (expert-parallel return): output row r is stored at address c_rows[r] (0 = skipped) instead of a
     local C; nothing is returned.
     Returns C, or (C, preact) when want_preact.
@@ -318,8 +321,15 @@ def gemm_rows(a: torch.Tensor, w: torch.Tensor, *, w_is_kn: bool, route: Optiona
         assert aux is not None and aux.dtype == torch.bfloat16 and aux.stride(1) == 1 and aux.shape[0] == m
         assert aux.shape[1] == (2 * n if glu_bwd else n)
         g.act_bwd, g.aux, g.ldaux = act_bwd, _p(aux), aux.stride(0)
+    rs = None
+    if rowsum_softplus is not None:
+        assert c is not None and not glu_fwd and act_bwd == ACT_NONE and not want_preact
+        rs = torch.empty(m, (n + 63) // 64, dtype=torch.float32, device=a.device)
+        g.rowsum, g.rowsum_round = _p(rs), 1 if rowsum_softplus else 0
     algo_rows = E * dense_rows if dense_rows else route.n_slots
     _gemm(g, 2.0 * algo_rows * n * k, "rows_kn" if w_is_kn else "rows_nk")
+    if rs is not None:
+        return c, rs
     return (c, pre) if (want_preact or glu_fwd) else c
 
 
@@ -412,6 +422,16 @@ def affinity_fwd(y: torch.Tensor, num_experts: int, T: int, t_pad: int, eager_bf
     D = y.shape[-1]
     aff = torch.empty(T, num_experts, dtype=torch.float32, device=y.device)
     _call("csmoe_affinity_fwd", _p(y), _dt(y), num_experts, T, t_pad, D, BF16 if eager_bf16 else F32, _p(aff), _stream())
+    return aff
+
+
+def affinity_from_rowsum(rowsum: torch.Tensor, num_experts: int, T: int, t_pad: int, D: int, eager_bf16: bool) -> torch.Tensor:
+    """rowsum [E * t_pad, ceil(D / 64)] (from gemm_rows(..., rowsum_softplus=...)) -> aff [T, E] f32."""
+    _cuda(rowsum)
+    assert rowsum.dtype == torch.float32 and rowsum.is_contiguous() and rowsum.shape == (num_experts * t_pad, (D + 63) // 64)
+    aff = torch.empty(T, num_experts, dtype=torch.float32, device=rowsum.device)
+    _call("csmoe_affinity_from_rowsum", _p(rowsum), rowsum.shape[1], num_experts, T, t_pad, D, BF16 if eager_bf16 else F32,
+          _p(aff), _stream())
     return aff
 
 

@@ -395,9 +395,10 @@ class CompeteSMoE(MoE):
         if is_comp:
             spec = self._spec(cdt)
             keys, bias, values = self._all_expert_weights()
-            y_all = DenseFFNFn.apply(x2.to(cdt), keys, bias, values, None, spec)   # [E * t_pad, Dv]
+            y_all, score_sums = DenseFFNFn.apply(x2.to(cdt), keys, bias, values, None, spec,
+                                                 x.dtype == torch.bfloat16)          # [E * t_pad, Dv]
             t_pad = y_all.shape[0] // E
-            aff, aff_w, aff_idx, out, diver = CompeteTailFn.apply(y_all, E, T, t_pad, K, False, x.dtype, spec)
+            aff, aff_w, aff_idx, out, diver = CompeteTailFn.apply(y_all, E, T, t_pad, K, False, x.dtype, spec, score_sums)
             self.nb_diver += K * (K - 1) * T
             aff_softmax = F.softmax(aff, dim=-1, dtype=torch.float32)
             li = aff_idx.long()

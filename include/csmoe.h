@@ -180,6 +180,13 @@ typedef struct csmoe_gemm_args {
   const uint64_t* c_rows;  /* ROWS, plain epilogue: when non-NULL, output row r is stored at address c_rows[r] (0 = row
                               skipped) instead of c + r*ldc -- the expert-parallel return path: the down projection
                               writes each row straight into the source rank's buffer (peer memory).  c may be NULL. */
+  float* rowsum;           /* ROWS, plain epilogue, may be NULL: rowsum[row * ceil(n/64) + g] = sum over output columns
+                              [64g, 64g+64) of softplus(C[row, col]) (of the value as stored) -- the competition step's
+                              neural-response score reduced in the epilogue of the experts' down projection
+                              (moe_model/.../competesmoe.py:243: mean(softplus(out_i), -1)); csmoe_affinity_from_rowsum
+                              finishes the mean.  Rows of skipped tiles are not written. */
+  int32_t rowsum_round;    /* 1: round every softplus to bf16 before summing (eager bf16 reference arithmetic) */
+  int32_t reserved2;
 } csmoe_gemm_args;
 
 int csmoe_grouped_gemm(const csmoe_gemm_args* args, void* stream);
@@ -208,6 +215,10 @@ int csmoe_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream);
  * softplus and mean run in fp32).  aff is always stored as fp32. */
 int csmoe_affinity_fwd(const void* y, int32_t dtype, int32_t E, int64_t T, int64_t t_pad, int32_t D,
                        int32_t round_dtype, float* aff, void* stream);
+/* aff[t, e] = (sum_g rowsum[(e * t_pad + t) * groups + g]) / D, rounded to bf16 when round_dtype = CSMOE_BF16: finishes the
+ * score from the row sums the grouped GEMM's epilogue produced (csmoe_gemm_args.rowsum). */
+int csmoe_affinity_from_rowsum(const float* rowsum, int32_t groups, int32_t E, int64_t T, int64_t t_pad, int32_t D,
+                               int32_t round_dtype, float* aff, void* stream);
 /* dy[e,t,d] (+)= daff[t,e] * sigmoid(y[e,t,d]) / D. accumulate: add into an existing dy. */
 int csmoe_affinity_bwd(const void* y, const float* daff, int32_t dtype, int32_t E, int64_t T, int64_t t_pad, int32_t D,
                        int32_t accumulate, void* dy, void* stream);

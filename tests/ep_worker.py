@@ -168,7 +168,8 @@ def main():
     group = EPGroup(None, dev)
     try:
         for comp in (False, True):
-            run_multimodal(group, dev, kind="mlp", E=4, K=2, D=256, Fh=520, B=2, N=200, competition=comp)
+            # the expert count must be a multiple of the group size: 4 experts up to 4 ranks, 8 on an 8-GPU box
+            run_multimodal(group, dev, kind="mlp", E=4 if world <= 4 else 8, K=2, D=256, Fh=520, B=2, N=200, competition=comp)
             run_multimodal(group, dev, kind="glu", E=8, K=2, D=512, Fh=1024, B=1, N=1000, competition=comp)
             run_pretrain(group, dev, E=16, K=4, D=256, H=128, B=2, N=300, competition=comp)
         # ragged: a rank with very few tokens, top-1, more experts than tokens

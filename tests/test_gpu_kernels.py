@@ -421,3 +421,22 @@ def test_gemm_dense_sum_over_experts(ops, kn, E, T, n, k):
     ref = torch.einsum("etk,ekn->tn", a.float(), w.float())
     assert c.shape == (T, n)
     assert_close_rms(c, ref, 2e-2, "sum over experts")
+
+
+@pytest.mark.parametrize("eager_bf16", [True, False])
+@pytest.mark.parametrize("E,T,n,k,kn", [(4, 256, 1152, 320, False), (8, 512, 1024, 128, True), (3, 256, 96, 64, True)])
+def test_gemm_epilogue_score_matches_affinity_kernel(ops, eager_bf16, E, T, n, k, kn):
+    """The neural-response score reduced in the down projection's epilogue (csmoe_gemm_args.rowsum) against the
+    stand-alone kernel that re-reads the dense outputs, and against torch (competesmoe.py:243)."""
+    g = torch.Generator().manual_seed(E * n + k)
+    h = (torch.randn(E * T, k, generator=g) * 0.5).bfloat16().to(DEV)
+    w = (torch.randn(E, k, n, generator=g) * 0.2).bfloat16().to(DEV)
+    wk = w if kn else w.transpose(1, 2).contiguous()
+    y, rs = ops.gemm_rows(h, wk, w_is_kn=kn, dense_rows=T, a_expert_rows=T, rowsum_softplus=eager_bf16)
+    aff = ops.affinity_from_rowsum(rs, E, T - 7, T, n, eager_bf16)
+    ref_kernel = ops.affinity_fwd(y, E, T - 7, T, eager_bf16)
+    sp = F.softplus(y.float().view(E, T, n)[:, :T - 7])
+    ref = (sp.bfloat16().float() if eager_bf16 else sp).mean(-1).t()
+    tol = 2 ** -8 if eager_bf16 else 1e-5           # one bf16 ulp when the result is rounded to bf16
+    assert float((aff - ref_kernel).abs().max() / ref_kernel.abs().max()) <= tol
+    assert float((aff - ref).abs().max() / ref.abs().max()) <= tol
