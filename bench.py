@@ -246,28 +246,48 @@ def timed_region(layer, x, dy, params, steps, warmup, dist_on):
 
 
 def e2e_region(layer, x_host, dy_host, params, steps, warmup, dist_on, device):
-    """Public-API call with host buffers: pinned H2D of x and dy, fwd+bwd, D2H of the loss, every step."""
+    """Public-API call with host buffers: every step's tokens and upstream gradient are copied from pinned host memory
+    (H2D) and the loss is read back (D2H) inside the timed region.  The copies of step i+1 are issued on a second
+    stream into the other half of a double buffer while step i computes (what a prefetching data loader does); the
+    compute stream waits on the copy's event before it touches a buffer, and the copy stream waits until the previous
+    user of that buffer is done."""
     import torch.distributed as dist
-    x_dev = torch.empty_like(x_host, device=device).requires_grad_(True)
-    dy_dev = torch.empty_like(dy_host, device=device)
+    main = torch.cuda.current_stream(device)
+    copy = torch.cuda.Stream(device)
+    bufs = [(torch.empty_like(x_host, device=device).requires_grad_(True), torch.empty_like(dy_host, device=device))
+            for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
     loss_host = torch.empty((), dtype=torch.float32).pin_memory()
 
-    def step():
-        with torch.no_grad():
+    def prefetch(i):
+        x_dev, dy_dev = bufs[i % 2]
+        with torch.cuda.stream(copy), torch.no_grad():
+            copy.wait_event(consumed[i % 2])
             x_dev.copy_(x_host, non_blocking=True)
             dy_dev.copy_(dy_host, non_blocking=True)
-        aux = one_step(layer, x_dev, dy_dev, params)
-        loss_host.copy_(aux.detach().float(), non_blocking=True)
+            ready[i % 2].record(copy)
 
-    for _ in range(warmup):
-        step()
+    def run(n):
+        for e in consumed:
+            e.record(main)
+        prefetch(0)
+        for i in range(n):
+            if i + 1 < n:
+                prefetch(i + 1)
+            x_dev, dy_dev = bufs[i % 2]
+            main.wait_event(ready[i % 2])
+            aux = one_step(layer, x_dev, dy_dev, params)
+            consumed[i % 2].record(main)
+            loss_host.copy_(aux.detach().float(), non_blocking=True)
+
+    run(warmup)
     if dist_on:
         dist.barrier()
     torch.cuda.synchronize()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
-    for _ in range(steps):
-        step()
+    run(steps)
     e.record()
     torch.cuda.synchronize()
     ms = torch.tensor([s.elapsed_time(e)], device=device)
