@@ -353,13 +353,31 @@ def run_ours(a):
     gemm_ms = [s.elapsed_time(e) for s, e, _, _ in timed]
     gemm_flops = [f for _, _, f, _ in timed]
     gemm_tflops = sum(gemm_flops) / (sum(gemm_ms) * 1e-3) / 1e12 if gemm_ms else 0.0
-    gemm_share = sum(gemm_ms) / (ms_router * a.steps) if gemm_ms else 0.0
+    gemm_share = sum(gemm_ms) / (ms_router * a.steps) if gemm_ms else 0.0   # of the eager pass the events were taken in
     per_step = len(timed) // max(a.steps, 1)
     gemm_detail = []
     for i in range(per_step):
         ms_i = [gemm_ms[j] for j in range(i, len(timed), per_step)]
         gemm_detail.append({"kind": timed[i][3], "ms": round(statistics.median(ms_i), 4),
                             "tflops": round(timed[i][2] / (statistics.median(ms_i) * 1e-3) / 1e12, 1)})
+
+    # ---- timed region 1b: the same call with the layer's CUDA-graph mode on (layer.enable_cuda_graphs(): forward and
+    # backward replayed from captured graphs behind the unchanged nn.Module call).  Not available under expert
+    # parallelism.  When it works it is the headline `value`; the eager number stays in the line as "eager".
+    ms_graph = None
+    if ep_group is None and a.graphs:
+        try:
+            layer.enable_cuda_graphs()
+            one_step(layer, x, dy, params)          # capture (router branch)
+            ms_graph = timed_region(layer, x, dy, params, a.steps, a.warmup, dist_on)
+        except Exception as exc:   # a capture failure must not cost the eager numbers
+            print(f"bench: CUDA-graph mode disabled: {exc}", file=sys.stderr)
+            layer.enable_cuda_graphs(False)
+            torch.cuda.synchronize()
+            ms_graph = None
+    ms_eager = ms_router
+    if ms_graph is not None:
+        ms_router = ms_graph
 
     # ---- timed region 2: competition step
     set_branch(layer, True)
@@ -388,6 +406,7 @@ def run_ours(a):
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_router, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "step": "router", "tokens_per_gpu": TOKENS,
+                       "cuda_graphs": ms_graph is not None,
                        "parallelism": "single GPU" if world == 1 else (
                            f"EP{ep_p} x DP{world // ep_p}: experts sharded over NVLink peer memory, tokens data-parallel"
                            if ep_group is not None else f"{world} independent data-parallel replicas"),
@@ -397,6 +416,8 @@ def run_ours(a):
             "competition": {"ms_per_step": ms_comp, "tokens_per_s": comp,
                             "model_tflops": flops_per_token(True) * tok / (ms_comp * 1e-3) / 1e12,
                             "model_frac_of_peak": flops_per_token(True) * TOKENS / (ms_comp * 1e-3) / 1e12 / peak_tf},
+            "eager": {"ms_per_step": ms_eager, "tokens_per_s": tok / (ms_eager * 1e-3),
+                      "note": "same call without CUDA graphs; the roofline's per-launch events were taken in this pass"},
             "mix": {"rate_flip": RATE_FLIP, "ms_per_step": mix_ms, "tokens_per_s": tok / (mix_ms * 1e-3)},
             "e2e": {"value": tok / (ms_e2e * 1e-3), "unit": "tokens/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},
@@ -419,6 +440,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--graphs", type=int, default=1, help="1: use the layer's CUDA-graph mode where available (single GPU / replicas)")
     ap.add_argument("--parallel", default="ep", choices=["ep", "replicas"],
                     help="N > 1: expert-parallel groups (default) or N independent replicas of the layer")
     a = ap.parse_args()

@@ -95,6 +95,43 @@ class MoeLayer(nn.Module):
         self._layout: Optional[X.ExpertLayout] = None
         self._ep = None            # ep.EPLayerState once enable_expert_parallel() was called
         self.ep_expert_offset = 0  # global index of experts[0] under expert parallelism
+        self._graphs = None        # {key: captured step} once enable_cuda_graphs() was called
+
+    # ---- CUDA graphs (no counterpart in the reference, whose step has a host sync per expert and per layer)
+    def enable_cuda_graphs(self, enabled: bool = True):
+        """Opt in: training-mode calls with a CUDA input that requires grad are replayed from captured CUDA graphs (one
+        forward graph + one backward graph per (branch, shape, dtype), torch.cuda.make_graphed_callables), removing the
+        per-kernel launch gaps of the ~40-launch step.  Everything else (eval, no-grad, autocast, expert parallelism,
+        return_id_experts) takes the normal path.  Parameters may change value between calls, not storage."""
+        self._graphs = {} if enabled else None
+        return self
+
+    def _graph_eligible(self, x, return_id_experts) -> bool:
+        return (self._graphs is not None and self._ep is None and self.training and x.is_cuda and x.requires_grad
+                and torch.is_grad_enabled() and not return_id_experts and not torch.is_autocast_enabled()
+                and not torch.cuda.is_current_stream_capturing())
+
+    def _graphed_call(self, x, branch: bool):
+        self._stacked_weights()          # storage fusing re-points expert .data once: do it before keying on pointers
+        params = tuple(p for p in self.parameters() if p.requires_grad)
+        key = (branch, tuple(x.shape), x.dtype, tuple(p.data_ptr() for p in params))
+        entry = self._graphs.get(key)
+        if entry is None:
+            names: List[str] = []
+
+            def fn(xx, *_params):
+                out, aux, _, info = self._forward_impl(xx, False)
+                names[:] = sorted(info)
+                return (out, aux) + tuple(info[k] for k in names)
+
+            sample = x.detach().clone().requires_grad_(True)
+            graphed = torch.cuda.make_graphed_callables(fn, (sample,) + params)
+            entry = (graphed, names, self.last_routing)
+            self._graphs[key] = entry
+        graphed, names, routing = entry
+        res = graphed(x, *params)
+        self.last_routing = routing     # static tensors of this graph, refreshed by the replay
+        return res[0], res[1], None, dict(zip(names, res[2:]))
 
     # ---- expert parallelism (no counterpart in the reference, which is data-parallel only; SURVEY.md 8e)
     def enable_expert_parallel(self, group, max_tokens: int, row_tile: int = 256):
@@ -259,6 +296,11 @@ class CompeteSMoE(MoeLayer):
         return F.mse_loss(gate_softmax, affinity_softmax)
 
     def forward(self, x, return_id_experts=False, is_vision=False):
+        if self._graph_eligible(x, return_id_experts):
+            return self._graphed_call(x, self._is_competition_step(x))
+        return self._forward_impl(x, return_id_experts)
+
+    def _forward_impl(self, x, return_id_experts=False):
         B, N, D = x.shape
         T, E, K = B * N, self.num_of_experts, self.num_selected
         x2 = x.reshape(T, D)

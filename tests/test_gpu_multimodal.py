@@ -146,3 +146,66 @@ def test_siglip_shape_against_oracle(competition):
     print(f"siglip-shape competition={competition}: {int((~agree).sum())}/{agree.numel()} low-margin tokens exempt")
     assert_close_rms(out[agree.to(DEV)], o_out.detach()[agree], 2e-2, "output")
     assert_close_rms(xg.grad[agree.to(DEV)], xr.grad[agree], 4e-2, "dx")
+
+
+@pytest.mark.parametrize("name", ["mm_siglip_router_bf16", "mm_siglip_comp_bf16", "mm_glu_router_f32"])
+def test_whole_step_cuda_graph_replay_matches_eager(name):
+    """competesmoe_b200.graphs.GraphedStep: forward + backward of the layer captured once and replayed (the step has no
+    host sync, so it is capturable).  Replays on fresh inputs must reproduce the eager step bit for bit."""
+    from competesmoe_b200.graphs import GraphedStep
+    fx = load_golden(name)
+    dtype = torch.bfloat16
+    layer = build_multimodal_layer(fx, DEV, dtype)
+    comp = bool(fx["meta"]["competition"])
+    g = torch.Generator().manual_seed(7)
+    step = GraphedStep(layer, fx["x"].to(DEV, dtype))
+    for trial in range(2):      # second trial: new inputs through the same captured graph
+        x_cpu = fx["x"] if trial == 0 else torch.randn(fx["x"].shape, generator=g)
+        dy_cpu = fx["dy"] if trial == 0 else torch.randn(fx["dy"].shape, generator=g)
+        out_g, aux_g = step.run(x_cpu.to(DEV, dtype), dy_cpu.to(DEV, dtype), branch=comp)
+        out_g, aux_g, dx_g = out_g.clone(), aux_g.clone(), step.dx.clone()
+        grads_g = {n: p.grad.clone() for n, p in layer.named_parameters() if p.grad is not None}
+        for p in layer.parameters():
+            p.grad = None
+        x = x_cpu.to(DEV, dtype).requires_grad_(True)
+        out, aux, _, _ = layer(x)
+        torch.autograd.backward((out, aux), (dy_cpu.to(DEV, dtype), torch.ones_like(aux)))
+        assert torch.equal(out_g, out) and torch.equal(aux_g, aux) and torch.equal(dx_g, x.grad)
+        assert set(grads_g) == {n for n, p in layer.named_parameters() if p.grad is not None}
+        for n, p in layer.named_parameters():
+            if p.grad is not None:
+                assert torch.equal(grads_g[n], p.grad), n
+
+
+@pytest.mark.parametrize("name", ["mm_siglip_router_bf16", "mm_siglip_comp_bf16", "mm_glu_comp_f32"])
+def test_layer_cuda_graph_mode_matches_eager(name):
+    """layer.enable_cuda_graphs(): the unchanged nn.Module call, replayed from captured forward / backward graphs, gives
+    the eager call's outputs, losses, routing and gradients bit for bit -- on the capture inputs and on fresh ones."""
+    fx = load_golden(name)
+    dtype = torch.bfloat16
+    eager = build_multimodal_layer(fx, DEV, dtype)
+    graphed = build_multimodal_layer(fx, DEV, dtype).enable_cuda_graphs()
+    g = torch.Generator().manual_seed(11)
+    for trial in range(3):
+        x_cpu = fx["x"] if trial == 0 else torch.randn(fx["x"].shape, generator=g)
+        dy = (fx["dy"] if trial == 0 else torch.randn(fx["dy"].shape, generator=g)).to(DEV, dtype)
+        res = []
+        for layer in (eager, graphed):
+            for p in layer.parameters():
+                p.grad = None
+            x = x_cpu.to(DEV, dtype).requires_grad_(True)
+            out, aux, none, info = layer(x)
+            assert none is None
+            torch.autograd.backward((out, aux), (dy, torch.ones_like(aux)))
+            res.append((out.clone(), aux.clone(), x.grad.clone(), {k: v.clone() for k, v in info.items()},
+                        layer.last_routing[0].clone(), {n: p.grad.clone() for n, p in layer.named_parameters() if p.grad is not None}))
+        (o0, a0, dx0, i0, r0, g0), (o1, a1, dx1, i1, r1, g1) = res
+        assert torch.equal(o0, o1) and torch.equal(a0, a1) and torch.equal(dx0, dx1) and torch.equal(r0, r1)
+        assert set(i0) == set(i1) and all(torch.equal(i0[k], i1[k]) for k in i0)
+        assert set(g0) == set(g1) and all(torch.equal(g0[k], g1[k]) for k in g0)
+    assert len(graphed._graphs) == 1
+    # eval / no-grad calls bypass the graphs
+    graphed.eval()
+    with torch.no_grad():
+        out, aux, _, _ = graphed(fx["x"].to(DEV, dtype))
+    assert out.shape == fx["out"].shape
