@@ -37,6 +37,18 @@ def bind_multimodal(register_module, moe_module, names=("competesmoe_b200",), ov
     return _bind(register_module.MOE_REGISTRY, CompeteSMoE, moe_module.MoeLayer, names, overwrite)
 
 
+def bind_multimodal_siblings(register_module, moe_module, suffix: str = "_b200", overwrite: bool = False) -> Dict[str, type]:
+    """The sibling routers (smoe, smoe_sigmoidgating, xmoe, smoe_perturbed, smoe_share, deepseekv3) under
+    `<name><suffix>`; `suffix="", overwrite=True` replaces the stock classes in place."""
+    from . import siblings
+    from .multimodal import MOE_REGISTRY as ours
+    out = {}
+    for name in ("smoe", "smoe_sigmoidgating", "xmoe", "smoe_perturbed", "smoe_share", "deepseekv3"):
+        out[name] = _bind(register_module.MOE_REGISTRY, ours[name], moe_module.MoeLayer, (name + suffix,), overwrite)
+    del siblings
+    return out
+
+
 def bind_pretrain(register_module, moe_module, names=("competesmoe_b200",), overwrite: bool = False) -> type:
     """register_module = layers.moe.register, moe_module = layers.moe.moe of moe_pretrain_model."""
     from .pretrain import CompeteSMoE

@@ -157,12 +157,111 @@ def gen_multimodal(ref_mods, name, kind, d_in, d_out, f, E, K, B, N, competition
           f"info={ {k: round(float(v), 6) for k, v in info.items()} }")
 
 
+def sibling_gate_params(name, layer):
+    if name in ("xmoe", "smoe_perturbed"):
+        return {"inp_reduction_w": layer.inp_reduction.weight, "expert_embeddings": layer.expert_embeddings}
+    return {"gate_w": layer.gate.weight}
+
+
+def gen_sibling(ref_mods, fixture, moe_name, kind, d_in, d_out, f, E, K, B, N, dtype=torch.float32, seed=0,
+                requires_grad=True):
+    """Fixtures for the sibling routers (smoe.py, smoe_sigmoidgating.py, xmoe.py, smoe_perturbed.py, shard_smoe.py,
+    deepseekv3.py): same recipe as gen_multimodal, the oracle is oracle/siblings.py."""
+    from oracle import multimodal as om
+    from oracle import siblings as osb
+
+    torch.manual_seed(seed)
+    args = mm_args(moe_name=moe_name)
+    with quiet():
+        if moe_name in ("smoe_share", "deepseekv3"):      # these deep-copy ONE expert module (shard_smoe.py:33)
+            expert = build_expert(kind, d_in, d_out, f, ref_mods)
+        else:
+            expert = nn.ModuleList([build_expert(kind, d_in, d_out, f, ref_mods) for _ in range(E)])
+        layer = ref_mods["get_moe"](moe_name)(in_embed_dim=d_in, out_embed_dim=d_out, num_of_experts=E, num_selected=K,
+                                              expert=expert, args=args)
+        if moe_name in ("smoe_share", "deepseekv3"):      # de-correlate the copies so that routing is not all ties
+            g0 = torch.Generator().manual_seed(100 + seed)
+            with torch.no_grad():
+                for m in layer.experts:
+                    for p_ in m.parameters():
+                        p_.add_(torch.randn(p_.shape, generator=g0) * 0.05)
+        layer = layer.to(dtype)
+    g = torch.Generator().manual_seed(4321 + seed)
+    x = torch.randn(B, N, d_in, generator=g).to(dtype).requires_grad_(requires_grad)
+    dy = torch.randn(B, N, d_out, generator=g).to(dtype)
+    gate0 = {k: v.detach().clone() for k, v in sibling_gate_params(moe_name, layer).items()}   # before the in-place renorm
+    captured = {}
+    orig = layer.compute_moe
+
+    def spy(selected_experts, weights, results, x, *a, **kw):
+        captured["selected"] = selected_experts.detach().clone()
+        captured["weights"] = weights.detach().clone()
+        return orig(selected_experts, weights, results, x, *a, **kw)
+
+    layer.compute_moe = spy
+    with quiet():
+        res = layer(x)
+    out, aux, info = res[0], res[1], res[3]
+    if requires_grad:
+        ((out.float() * dy.float()).sum() + aux.float()).backward()
+    gate_after = {k: v.detach().clone() for k, v in sibling_gate_params(moe_name, layer).items()}
+    gate_grads = {k: (None if v.grad is None else v.grad.clone()) for k, v in sibling_gate_params(moe_name, layer).items()}
+    fx = {
+        "meta": dict(name=fixture, moe_name=moe_name, kind=kind, d_in=d_in, d_out=d_out, f=f, E=E, K=K, B=B, N=N,
+                     dtype=str(dtype), args=vars(args), requires_grad=requires_grad),
+        "x": x.detach().clone(), "dy": dy, "gate": gate0, "gate_after": gate_after, "dgate": gate_grads,
+        "experts": [{k: (v.detach().clone() if torch.is_tensor(v) else v)
+                     for k, v in expert_weights(kind, m).items()} for m in layer.experts],
+        "out": out.detach().clone(), "aux": aux.detach().clone(), "info": {k: v.clone() for k, v in info.items()},
+        "dx": x.grad.clone() if requires_grad else None,
+        "dexperts": [{n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None} for m in layer.experts],
+        "selected": captured["selected"], "weights": captured["weights"],
+    }
+    # ---- pin the oracle
+    x2 = fx["x"].clone().requires_grad_(requires_grad)
+    gate = {k: v.clone().requires_grad_(True) for k, v in gate0.items()}
+    exps = [{k: (v.clone().requires_grad_(True) if torch.is_tensor(v) else v) for k, v in e.items()} for e in fx["experts"]]
+    o_out, o_aux, _, o_info, dbg = osb.sibling_forward(moe_name, x2, gate, exps, K, d_out, args)
+    if requires_grad:
+        ((o_out.float() * dy.float()).sum() + o_aux.float()).backward()
+    tol = dict(rtol=1e-5, atol=1e-6) if dtype == torch.float32 else dict(rtol=2e-2, atol=2e-2)
+    k_eff = K - 1 if moe_name in ("smoe_share", "deepseekv3") else K
+    scores = torch.sigmoid(dbg["gate_logits"]) if moe_name == "smoe_sigmoidgating" else dbg["gate_softmax"]
+    margin = om.topk_margin(scores, k_eff)
+    agree = (captured["selected"] == dbg["selected"]).all(-1)
+    assert bool((margin[~agree] < 1e-3).all()), "routing differs on a token with margin >= 1e-3"
+    n_exempt = int((~agree).sum())
+    torch.testing.assert_close(o_out[agree], fx["out"][agree], **tol)
+    torch.testing.assert_close(captured["weights"][agree].float(), dbg["weights"][agree].float(), **tol)
+    if requires_grad:
+        torch.testing.assert_close(x2.grad[agree], fx["dx"][agree], **tol)
+    if n_exempt == 0:
+        torch.testing.assert_close(o_aux.float(), fx["aux"].float(), **tol)
+        for k_ in info:
+            torch.testing.assert_close(o_info[k_].float(), info[k_].float(), **tol)
+        for k_, v in gate.items():
+            if fx["dgate"][k_] is not None:
+                torch.testing.assert_close(v.grad, fx["dgate"][k_], **tol)
+    for k_, v in gate.items():      # the in-place rescaling of expert_embeddings is part of the contract
+        torch.testing.assert_close(v.detach(), gate_after[k_], **tol)
+    fx["selected_oracle"] = dbg["selected"].clone()
+    fx["n_exempt"] = n_exempt
+    torch.save(fx, OUT / f"{fixture}.pt")
+    print(f"  wrote {fixture}.pt  ({moe_name}: oracle == reference, {n_exempt} low-margin tokens exempt)  "
+          f"aux={float(aux.detach()):.6f}")
+
+
 def load_multimodal_reference():
     sys.path.insert(0, str(REF))
     with quiet():
         importlib.import_module("moe_model.model.moe")
         reg = importlib.import_module("moe_model.model.moe.register")
         siglip = importlib.import_module("moe_model.model.multimodal_encoder.siglip_smoe")
+        try:   # deepseekv3.py is not imported by the package __init__ (so not registered); it needs `loguru`
+            importlib.import_module("loguru")
+        except ImportError:
+            sys.modules["loguru"] = types.ModuleType("loguru")
+        importlib.import_module("moe_model.model.moe.deepseekv3")
     return {"get_moe": reg.get_moe, "siglip": siglip}
 
 
@@ -341,8 +440,24 @@ def gen_cvmm_interpreter(name="cvmm_triton_interp"):
     print(f"  wrote {name}.pt  (oracle cvmm == reference Triton kernels on the interpreter)")
 
 
+def gen_all_siblings(mm):
+    print("multimodal sibling routers:")
+    gen_sibling(mm, "sib_smoe_f32", "smoe", "siglip", 64, 64, 128, 4, 2, 2, 24, seed=10)
+    gen_sibling(mm, "sib_smoe_bf16", "smoe", "siglip", 64, 64, 128, 4, 2, 2, 24, dtype=torch.bfloat16, seed=11)
+    gen_sibling(mm, "sib_sigmoid_f32", "smoe_sigmoidgating", "projector", 48, 64, 64, 4, 2, 2, 16, seed=12)
+    gen_sibling(mm, "sib_sigmoid_bf16", "smoe_sigmoidgating", "siglip", 64, 64, 128, 4, 2, 2, 24, dtype=torch.bfloat16, seed=13)
+    gen_sibling(mm, "sib_xmoe_f32", "xmoe", "siglip", 64, 64, 128, 8, 2, 2, 24, seed=14)
+    gen_sibling(mm, "sib_perturbed_f32", "smoe_perturbed", "glu", 64, 64, 96, 8, 2, 2, 16, seed=15)
+    gen_sibling(mm, "sib_share_f32", "smoe_share", "siglip", 64, 64, 128, 5, 3, 2, 24, seed=16)
+    gen_sibling(mm, "sib_deepseekv3_f32", "deepseekv3", "siglip", 64, 64, 128, 5, 3, 2, 24, seed=17)
+    gen_sibling(mm, "sib_deepseekv3_nograd_f32", "deepseekv3", "siglip", 64, 64, 128, 5, 3, 2, 16, seed=18, requires_grad=False)
+
+
 def main():
     OUT.mkdir(parents=True, exist_ok=True)
+    if "--siblings-only" in sys.argv:
+        gen_all_siblings(load_multimodal_reference())
+        return
     if os.environ.get("TRITON_INTERPRET") == "1":
         gen_cvmm_interpreter()
         return
@@ -358,6 +473,7 @@ def main():
     gen_multimodal(mm, "mm_siglip_router_bf16", "siglip", 64, 64, 128, 4, 2, 2, 24, False, dtype=torch.bfloat16, seed=4)
     gen_multimodal(mm, "mm_siglip_comp_bf16", "siglip", 64, 64, 128, 4, 2, 2, 24, True, dtype=torch.bfloat16, seed=4)
     gen_multimodal(mm, "mm_siglip_comp_upcycled_f32", "siglip", 64, 64, 128, 4, 2, 2, 16, True, upcycled=True, seed=5)
+    gen_all_siblings(mm)
     print("pretrain reference (moe_pretrain_model/layers/moe):")
     pm = load_pretrain_reference()
     gen_pretrain(pm, "pt_router_f32", 64, 8, 32, 2, 2, 32, False)

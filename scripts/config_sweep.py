@@ -41,8 +41,9 @@ def mm_args():
 
 
 class Case:
-    def __init__(self, name, kind, T, D, hidden, E, K, d_out=None, autocast=True, note=""):
+    def __init__(self, name, kind, T, D, hidden, E, K, d_out=None, autocast=True, note="", moe_name="competesmoe"):
         self.name, self.kind, self.T, self.D, self.hidden, self.E, self.K = name, kind, T, D, hidden, E, K
+        self.moe_name = moe_name
         self.d_out = d_out or D
         self.autocast, self.note = autocast, note
 
@@ -53,6 +54,8 @@ class Case:
 
     def flops_per_token(self, competition):
         r = 2.0 * self.D * self.E
+        if self.moe_name in ("smoe_share", "deepseekv3"):      # k-1 routed choices + the shared expert = k expert passes
+            return 3.0 * (self.K * self.f_e() + 2.0 * self.D * (self.E - 1))
         return 3.0 * ((self.E if competition else self.K) * self.f_e() + r)
 
     def bytes_per_token_router(self, s=2):
@@ -85,7 +88,9 @@ def build(case: Case, dev, ep):
             ((out.float() * dy).sum() + sum(regs.values())).backward()
         x_dtype = torch.float32
     else:
-        from competesmoe_b200.multimodal import CompeteSMoE
+        from competesmoe_b200 import siblings  # noqa: F401  (registers smoe, xmoe, ...)
+        from competesmoe_b200.multimodal import get_moe
+        CompeteSMoE = get_moe(case.moe_name)
         if case.kind == "siglip":
             experts = nn.ModuleList([MLPExpert(case.D, case.hidden, case.d_out, "gelu_tanh") for _ in range(case.E)])
         else:   # projector: Sequential(Linear, GELU, Linear)
@@ -98,8 +103,9 @@ def build(case: Case, dev, ep):
             layer.enable_expert_parallel(ep, max_tokens=case.T)
 
         def set_branch(comp):
-            layer.prob_flips = torch.full((2,), bool(comp), device=dev)
-            layer.set_current_steps(0)
+            if case.moe_name == "competesmoe":
+                layer.prob_flips = torch.full((2,), bool(comp), device=dev)
+                layer.set_current_steps(0)
 
         def step(x, dy):
             out, aux, _, _ = layer(x)
@@ -117,7 +123,7 @@ def time_case(case: Case, dev, ep, steps, warmup, dist_on):
     x = torch.randn(1, case.T, case.D, generator=g).to(x_dtype).to(dev).requires_grad_(True)
     dy = torch.randn(1, case.T, case.d_out, generator=g).to(dev)
     res = {}
-    for comp in (False, True):
+    for comp in ((False, True) if case.moe_name == "competesmoe" else (False,)):
         set_branch(comp)
 
         def one():
@@ -189,6 +195,10 @@ def cases(world):
     cs.append(Case("C5/C2' SigLIP MoE MLP d=1152 F=4304 E=4 K=2 gelu-tanh+bias, 12800 tokens/GPU", "siglip", 12800, 1152, 4304, 4, 2))
     cs.append(Case("C5/C2' projector MoE 2304->3072->3072 E=4 K=2 gelu+bias, 1280 tokens/GPU", "projector", 1280, 2304, 3072, 4, 2,
                    d_out=3072))
+    for nm, E, K in (("smoe", 4, 2), ("smoe_sigmoidgating", 4, 2), ("xmoe", 4, 2), ("smoe_perturbed", 4, 2),
+                     ("smoe_share", 5, 3), ("deepseekv3", 5, 3)):
+        cs.append(Case(f"S sibling router {nm}: SigLIP MoE MLP d=1152 F=4304 E={E} K={K}, 12800 tokens", "siglip", 12800, 1152,
+                       4304, E, K, moe_name=nm))
     return cs
 
 
@@ -211,7 +221,7 @@ def main():
     for case in cases(world):
         if a.only and not case.name.startswith(a.only):
             continue
-        if world > 1 and not case.name.startswith(("C4", "C5")):
+        if (world > 1 and not case.name.startswith(("C4", "C5"))) or (case.name.startswith("S ") and not a.only.startswith("S")):
             continue
         ep = None
         if world > 1:
@@ -235,7 +245,7 @@ def main():
               f"unfused-algorithm GB/s per GPU | % of {PEAK_GBS:.0f} GB/s |")
         print("|---|---|---|---:|---:|---:|---:|---:|---:|")
         for case, res, p in rows:
-            for comp in (False, True):
+            for comp in sorted(res):
                 ms = res[comp]
                 tf = case.flops_per_token(comp) * case.T / (ms * 1e-3) / 1e12
                 gbs = case.bytes_per_token_router() * case.T / (ms * 1e-3) / 1e9 if not comp else float("nan")

@@ -132,3 +132,41 @@ def test_pretrain_binding_registers_and_matches_checkpoint_layout(tmp_path, monk
                 sys.modules[k] = v
         for k in [k for k in sys.modules if k.startswith(("layers.", "framework."))]:
             sys.modules.pop(k, None)
+
+
+def test_sibling_routers_bind_and_match_reference_state_dicts():
+    """competesmoe_b200.integrate.bind_multimodal_siblings: every sibling router is a subclass of the reference's
+    MoeLayer, is found through the reference's get_moe, and has the reference class's state_dict keys and shapes."""
+    sys.path.insert(0, str(REF))
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            import moe_model.model.moe  # noqa: F401
+            reg = importlib.import_module("moe_model.model.moe.register")
+            base = importlib.import_module("moe_model.model.moe.moe")
+    finally:
+        sys.path.remove(str(REF))
+    from competesmoe_b200.integrate import bind_multimodal_siblings
+    bound = bind_multimodal_siblings(reg, base, suffix="_b200", overwrite=True)
+
+    def expert():
+        m = nn.Module()
+        m.fc1, m.fc2, m.activation_fn = nn.Linear(32, 48), nn.Linear(48, 32), nn.GELU(approximate="tanh")
+        return m
+
+    for name in ("smoe", "smoe_sigmoidgating", "xmoe", "smoe_perturbed", "smoe_share"):   # deepseekv3 is not registered upstream
+        cls = reg.get_moe(name + "_b200")
+        assert cls is bound[name] and issubclass(cls, base.MoeLayer)
+        single = name == "smoe_share"      # the reference deep-copies one module there (shard_smoe.py:33)
+        E = 5 if single else 4
+        mk = (lambda: expert()) if single else (lambda: nn.ModuleList([expert() for _ in range(E)]))
+        torch.manual_seed(0)
+        ours = cls(in_embed_dim=32, out_embed_dim=32, num_of_experts=E, num_selected=2, expert=mk(), args=_mm_args())
+        with contextlib.redirect_stdout(io.StringIO()):
+            theirs = reg.get_moe(name)(in_embed_dim=32, out_embed_dim=32, num_of_experts=E, num_selected=2, expert=mk(),
+                                       args=_mm_args())
+        sd_o, sd_t = ours.state_dict(), theirs.state_dict()
+        assert sorted(sd_o) == sorted(sd_t), (name, sorted(set(sd_o) ^ set(sd_t)))
+        assert all(sd_o[k].shape == sd_t[k].shape for k in sd_o), name
+        gate_key = "expert_embeddings" if name in ("xmoe", "smoe_perturbed") else "gate.weight"
+        assert torch.equal(sd_o[gate_key], sd_t[gate_key]), f"{name}: seeded gate init differs"
+        ours.load_state_dict(sd_t)

@@ -121,3 +121,40 @@ def test_schedule_respects_cap_and_is_deterministic():
     assert torch.equal(a, b)
     assert not bool(a[::2].any())             # full steps never get a 4th competing layer
     assert int(a.sum()) <= int((draws < 0.3).sum())
+
+
+SIB = ["sib_smoe_f32", "sib_smoe_bf16", "sib_sigmoid_f32", "sib_sigmoid_bf16", "sib_xmoe_f32", "sib_perturbed_f32",
+       "sib_share_f32", "sib_deepseekv3_f32", "sib_deepseekv3_nograd_f32"]
+
+
+@pytest.mark.parametrize("name", SIB)
+def test_sibling_router_oracle_matches_reference(name):
+    """oracle/siblings.py against the outputs of the unmodified reference classes (smoe, smoe_sigmoidgating, xmoe,
+    smoe_perturbed, smoe_share, deepseekv3)."""
+    from oracle import siblings as osb
+    fx = load_golden(name)
+    m = fx["meta"]
+    args = SimpleNamespace(**m["args"])
+    x = fx["x"].clone().requires_grad_(m["requires_grad"])
+    gate = {k: _req(v) for k, v in fx["gate"].items()}
+    exps = [{k: (_req(v) if torch.is_tensor(v) else v) for k, v in e.items()} for e in fx["experts"]]
+    out, aux, _, info, dbg = osb.sibling_forward(m["moe_name"], x, gate, exps, m["K"], m["d_out"], args)
+    if m["requires_grad"]:
+        ((out.float() * fx["dy"].float()).sum() + aux.float()).backward()
+    tol = dict(rtol=1e-5, atol=1e-6) if "float32" in m["dtype"] else dict(rtol=2e-2, atol=2e-2)
+    agree = (fx["selected"] == dbg["selected"]).all(-1)
+    assert int((~agree).sum()) == fx["n_exempt"]
+    torch.testing.assert_close(out[agree], fx["out"][agree], **tol)
+    torch.testing.assert_close(dbg["weights"][agree].float(), fx["weights"][agree].float(), **tol)
+    assert set(info) == set(fx["info"])
+    for k, v in gate.items():                                  # in-place rescaling of the expert embeddings
+        torch.testing.assert_close(v.detach(), fx["gate_after"][k], **tol)
+    if m["requires_grad"]:
+        torch.testing.assert_close(x.grad[agree], fx["dx"][agree], **tol)
+    if fx["n_exempt"] == 0:
+        torch.testing.assert_close(aux.float(), fx["aux"].float(), **tol)
+        for k in fx["info"]:
+            torch.testing.assert_close(info[k].float(), fx["info"][k].float(), **tol)
+        for k, v in gate.items():
+            if fx["dgate"][k] is not None:
+                torch.testing.assert_close(v.grad, fx["dgate"][k], **tol)
