@@ -8,6 +8,7 @@ namespace csmoe {
 namespace {
 
 constexpr int kThreads = 256;
+constexpr int kBiasGradSplits = 16;
 
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
@@ -26,13 +27,14 @@ act_fwd_kernel(const T* __restrict__ z, long long rows, long long cols, long lon
       load8(z + r * ldz + cols + c, u);   // up
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float s = round_as(act_apply(v[j], CSMOE_ACT_SILU), static_cast<const T*>(nullptr));
+        const float s = round_as(act_apply(v[j], CSMOE_ACT_SILU, sizeof(T) == 2), static_cast<const T*>(nullptr));
         o[j] = u[j] * s;
       }
     } else {
       load8(z + r * ldz + c, v);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = act_apply(v[j], act);
+      for (int j = 0; j < 8; ++j) o[j] = v[j];
+      act_apply_vec<8>(o, act, sizeof(T) == 2);
     }
     store8(h + r * ldh + c, o);
   }
@@ -56,27 +58,30 @@ act_bwd_kernel(const T* __restrict__ z, const T* __restrict__ dh, long long rows
       load8(z + r * ldz + cols + c, u);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float s = round_as(act_apply(v[j], CSMOE_ACT_SILU), static_cast<const T*>(nullptr));
+        const float s = round_as(act_apply(v[j], CSMOE_ACT_SILU, sizeof(T) == 2), static_cast<const T*>(nullptr));
         du[j] = g[j] * s;
         const float ds = round_as(g[j] * u[j], static_cast<const T*>(nullptr));
-        o[j] = ds * act_grad(v[j], CSMOE_ACT_SILU);
+        o[j] = ds * act_grad(v[j], CSMOE_ACT_SILU, sizeof(T) == 2);
       }
       store8(dz + r * ldz + c, o);
       store8(dz + r * ldz + cols + c, du);
     } else {
       load8(z + r * ldz + c, v);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = g[j] * act_grad(v[j], act);
+      for (int j = 0; j < 8; ++j) o[j] = g[j];
+      act_grad_vec<8>(o, v, act, sizeof(T) == 2);
       store8(dz + r * ldz + c, o);
     }
   }
 }
 
-// dbias[e][n]: grid (ceil(n / 256), E); block = 32 column-vectors x 8 row lanes.
+// dbias[e][n]: grid (ceil(n / 256), E, row splits); block = 32 column-vectors x 8 row lanes.  Each split reduces a
+// contiguous share of the expert's rows; with more than one split the partial sums go to `partial`
+// [splits, E, n] (fp32) and bias_grad_finish_kernel adds them in split order (deterministic, no atomics).
 template <typename T, typename OutT>
 __global__ void __launch_bounds__(256)
 bias_grad_kernel(const T* __restrict__ g, long long ldg, int n, const int32_t* __restrict__ pad_offsets, int dense,
-                 long long dense_rows, OutT* __restrict__ dbias) {
+                 long long dense_rows, OutT* __restrict__ dbias, float* __restrict__ partial) {
   __shared__ float red[8][32][8];
   const int e = blockIdx.y;
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
@@ -88,6 +93,12 @@ bias_grad_kernel(const T* __restrict__ g, long long ldg, int n, const int32_t* _
   } else {
     r0 = pad_offsets[e];
     r1 = pad_offsets[e + 1];
+  }
+  const int splits = gridDim.z;
+  if (splits > 1) {
+    const long long span = ((r1 - r0 + splits - 1) / splits + 7) / 8 * 8;
+    r0 += blockIdx.z * span;
+    r1 = r0 + span < r1 ? r0 + span : r1;
   }
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (col < n) {
@@ -109,8 +120,26 @@ bias_grad_kernel(const T* __restrict__ g, long long ldg, int n, const int32_t* _
 #pragma unroll
       for (int y = 0; y < 8; ++y) s[j] += red[y][cx][j];
     }
-    store8(dbias + static_cast<long long>(e) * n + col, s);
+    if (splits > 1)
+      store8(partial + (static_cast<long long>(blockIdx.z) * gridDim.y + e) * n + col, s);
+    else
+      store8(dbias + static_cast<long long>(e) * n + col, s);
   }
+}
+
+template <typename OutT>
+__global__ void __launch_bounds__(256)
+bias_grad_finish_kernel(const float* __restrict__ partial, int splits, long long en, OutT* __restrict__ dbias) {
+  const long long i = (static_cast<long long>(blockIdx.x) * 256 + threadIdx.x) * 8;
+  if (i >= en) return;
+  float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int z = 0; z < splits; ++z) {
+    float v[8];
+    load8(partial + z * en + i, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] += v[j];
+  }
+  store8(dbias + i, s);
 }
 
 __global__ void __launch_bounds__(kThreads)
@@ -182,18 +211,30 @@ extern "C" int csmoe_act_bwd(const void* z, const void* dh, int32_t dtype, int64
   return CSMOE_OK;
 }
 
+extern "C" int64_t csmoe_bias_grad_workspace_bytes(int32_t n, int32_t num_experts) {
+  if (n <= 0 || num_experts <= 0) return -1;
+  return static_cast<int64_t>(kBiasGradSplits) * num_experts * n * static_cast<int64_t>(sizeof(float));
+}
+
 extern "C" int csmoe_bias_grad(const void* g, int32_t dtype, int64_t ldg, int32_t n, int32_t num_experts,
                                const int32_t* pad_offsets, int32_t dense, int64_t dense_rows, void* dbias,
-                               int32_t out_dtype, void* stream_) {
+                               int32_t out_dtype, void* workspace, void* stream_) {
   CSMOE_CHECK_ARG(g && dbias, "csmoe_bias_grad: NULL pointer");
   CSMOE_CHECK_ARG(dense || pad_offsets, "csmoe_bias_grad: pad_offsets required unless dense");
   CSMOE_CHECK_ARG(n > 0 && n % 8 == 0 && ldg % 8 == 0, "csmoe_bias_grad: n/ldg must be multiples of 8");
   CSMOE_CHECK_ARG(num_experts >= 1 && num_experts <= 65535, "csmoe_bias_grad: bad num_experts");
   cudaStream_t stream = as_stream(stream_);
-  dim3 grid((n + 255) / 256, num_experts);
+  // few experts x few column blocks would leave most SMs idle: split each expert's rows when a workspace is given
+  const int col_blocks = (n + 255) / 256;
+  const int splits = (workspace != nullptr && col_blocks * num_experts < 4 * 148) ? kBiasGradSplits : 1;
+  dim3 grid(col_blocks, num_experts, splits);
+  float* partial = static_cast<float*>(workspace);
+  const long long en = static_cast<long long>(num_experts) * n;
+  const unsigned fin_grid = static_cast<unsigned>((en / 8 + 255) / 256);
 #define LAUNCH_BG(T, O)                                                                                             \
   bias_grad_kernel<T, O><<<grid, 256, 0, stream>>>(static_cast<const T*>(g), ldg, n, pad_offsets, dense, dense_rows, \
-                                                   static_cast<O*>(dbias))
+                                                   static_cast<O*>(dbias), partial);                                \
+  if (splits > 1) bias_grad_finish_kernel<O><<<fin_grid, 256, 0, stream>>>(partial, splits, en, static_cast<O*>(dbias))
   if (dtype == CSMOE_BF16 && out_dtype == CSMOE_BF16) {
     LAUNCH_BG(__nv_bfloat16, __nv_bfloat16);
   } else if (dtype == CSMOE_BF16 && out_dtype == CSMOE_F32) {

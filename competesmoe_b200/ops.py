@@ -398,8 +398,10 @@ def bias_grad(g: torch.Tensor, num_experts: int, *, route: Optional[Route] = Non
     out_dtype = out_dtype or g.dtype
     db = torch.empty(num_experts, n, dtype=out_dtype, device=g.device)
     po = None if dense_rows else _p(route.pad_offsets)
+    ws = torch.empty(int(_lib.load().csmoe_bias_grad_workspace_bytes(n, num_experts)) // 4, dtype=torch.float32,
+                     device=g.device)
     _call("csmoe_bias_grad", _p(g), _dt(g), g.stride(0), n, num_experts, po, 1 if dense_rows else 0, dense_rows, _p(db),
-          _dt(db), _stream())
+          _dt(db), _p(ws), _stream(), kernels=2)
     return db
 
 

@@ -200,10 +200,13 @@ int csmoe_act_fwd(const void* z, int32_t dtype, int64_t rows, int64_t cols, int6
                   int64_t ldh, const int32_t* tile_expert, void* stream);
 int csmoe_act_bwd(const void* z, const void* dh, int32_t dtype, int64_t rows, int64_t cols, int64_t ldz, int64_t ldh,
                   int32_t act, void* dz, const int32_t* tile_expert, void* stream);
-/* Column sums of g[rows of e, n] per expert -> dbias[e, n] (fp32 accumulate, written as `out_dtype`). */
+/* Column sums of g[rows of e, n] per expert -> dbias[e, n] (fp32 accumulate, written as `out_dtype`).  workspace (may
+ * be NULL; csmoe_bias_grad_workspace_bytes(n, E) bytes): lets the kernel split every expert's rows over several CTAs
+ * and add the partial sums in a fixed order (deterministic); without it one CTA column reduces all rows of an expert. */
+int64_t csmoe_bias_grad_workspace_bytes(int32_t n, int32_t num_experts);
 int csmoe_bias_grad(const void* g, int32_t dtype, int64_t ldg, int32_t n, int32_t num_experts,
                     const int32_t* pad_offsets, int32_t dense, int64_t dense_rows, void* dbias, int32_t out_dtype,
-                    void* stream);
+                    void* workspace, void* stream);
 /* dst = (bf16) src, n elements. */
 int csmoe_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream);
 

@@ -219,9 +219,9 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     rows = []
     for case in cases(world):
-        if a.only and not case.name.startswith(a.only):
+        if a.only and a.only not in case.name:
             continue
-        if (world > 1 and not case.name.startswith(("C4", "C5"))) or (case.name.startswith("S ") and not a.only.startswith("S")):
+        if (world > 1 and not case.name.startswith(("C4", "C5"))) or (case.name.startswith("S ") and "sibling" not in a.only and not a.only.startswith("S ")):
             continue
         ep = None
         if world > 1:

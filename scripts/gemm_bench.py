@@ -13,6 +13,7 @@ from competesmoe_b200 import ops  # noqa: E402
 dev = torch.device("cuda")
 torch.manual_seed(0)
 ITERS = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+SHAPE = sys.argv[2] if len(sys.argv) > 2 else "c2"
 T, K, E, D, F = 4096, 2, 4, 3072, 8192
 
 
@@ -29,8 +30,46 @@ def timeit(fn, iters=ITERS):
     return s.elapsed_time(e) / iters
 
 
+def siglip():
+    """C2' / C5: SigLIP-so400m MoE MLP, fc1 [4304, 1152] + bias, GELU-tanh, fc2 [1152, 4304] + bias, 12800 tokens top-2."""
+    T, K, E, D, F = 12800, 2, 4, 1152, 4304
+    g = torch.Generator().manual_seed(1)
+    sel = torch.stack([torch.randperm(E, generator=g)[:K] for _ in range(T)]).int().to(dev)
+    route = ops.route_build(sel, E)
+    rows, n_rows = route.row_cap, T * K
+    print(f"siglip: row_tile={route.row_tile} row_cap={rows} counts={route.counts.tolist()}")
+    bf = dict(device=dev, dtype=torch.bfloat16)
+    xp, h, dy, z = torch.randn(rows, D, **bf), torch.randn(rows, F, **bf), torch.randn(rows, D, **bf), torch.randn(rows, F, **bf)
+    w1, w2 = torch.randn(E, F, D, **bf) * 0.02, torch.randn(E, D, F, **bf) * 0.02
+    b1, b2 = torch.randn(E, F, **bf), torch.randn(E, D, **bf)
+    fl = 2 * n_rows * D * F
+    cases = [
+        ("fc1 + bias + GELU-tanh, z and h stored ", lambda: ops.gemm_rows(xp, w1, w_is_kn=False, bias=b1, act=ops.ACT_GELU_TANH, want_preact=True, route=route)),
+        ("fc1 + bias + GELU-tanh, h only         ", lambda: ops.gemm_rows(xp, w1, w_is_kn=False, bias=b1, act=ops.ACT_GELU_TANH, route=route)),
+        ("fc1 + bias + ReLU, z and h stored      ", lambda: ops.gemm_rows(xp, w1, w_is_kn=False, bias=b1, act=ops.ACT_RELU, want_preact=True, route=route)),
+        ("fc1 + bias + ReLU, h only              ", lambda: ops.gemm_rows(xp, w1, w_is_kn=False, bias=b1, act=ops.ACT_RELU, route=route)),
+        ("fc1 + bias + SiLU, z and h stored      ", lambda: ops.gemm_rows(xp, w1, w_is_kn=False, bias=b1, act=ops.ACT_SILU, want_preact=True, route=route)),
+        ("fc1 + bias only                        ", lambda: ops.gemm_rows(xp, w1, w_is_kn=False, bias=b1, route=route)),
+        ("fc1 plain                              ", lambda: ops.gemm_rows(xp, w1, w_is_kn=False, route=route)),
+        ("fc2 + bias                             ", lambda: ops.gemm_rows(h, w2, w_is_kn=False, bias=b2, route=route)),
+        ("dgrad2 dy.W2                           ", lambda: ops.gemm_rows(dy, w2, w_is_kn=True, route=route)),
+        ("dgrad1 dz.W1                           ", lambda: ops.gemm_rows(z, w1, w_is_kn=True, route=route)),
+        ("wgrad2 dy^T.h                          ", lambda: ops.gemm_reduce(dy, h, E, route=route, out_dtype=torch.bfloat16)),
+        ("wgrad1 dz^T.x                          ", lambda: ops.gemm_reduce(z, xp, E, route=route, out_dtype=torch.bfloat16)),
+    ]
+    for name, fn in cases:
+        ms = timeit(fn)
+        print(f"{name}: {ms:.4f} ms  {fl / ms / 1e9:7.1f} TFLOP/s", flush=True)
+    for name, fn in [("cuBLAS [25600x1152].[1152x4304]", lambda: torch.matmul(xp[:n_rows], w1[0].t())),
+                     ("cuBLAS [25600x4304].[4304x1152]", lambda: torch.matmul(h[:n_rows], w2[0].t()))]:
+        ms = timeit(fn)
+        print(f"{name}: {ms:.4f} ms  {fl / ms / 1e9:7.1f} TFLOP/s", flush=True)
+
+
 def main():
     print(torch.cuda.get_device_name(0), flush=True)
+    if SHAPE == "siglip":
+        return siglip()
     g = torch.Generator().manual_seed(1)
     sel = torch.stack([torch.randperm(E, generator=g)[:K] for _ in range(T)]).int().to(dev)
     route = ops.route_build(sel, E)
