@@ -51,6 +51,7 @@ _SIGNATURES = {
     "csmoe_router_aux_fwd": (i32, [vp, i32, vp, vp, i64, i64, i32, i32, vp, vp, vp, vp, vp, vp]),
     "csmoe_router_bwd_workspace_bytes": (i64, [i64, i32, i32]),
     "csmoe_router_bwd": (i32, [vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i32, i32, i32, vp, vp, vp, i32, vp, vp]),
+    "csmoe_router_from_logits": (i32, [vp, i32, i64, i32, i32, vp, vp, vp, vp]),
     "csmoe_topk_renorm": (i32, [vp, i64, i32, i32, i32, i32, vp, vp, vp]),
     "csmoe_gather_rows": (i32, [vp, i32, i64, i32, i32, vp, i64, vp, vp, vp]),
     "csmoe_combine_fwd": (i32, [vp, i32, i64, i32, i32, vp, vp, vp, i32, vp, vp]),

@@ -134,6 +134,43 @@ router_fwd_kernel(const T* __restrict__ x, const T* __restrict__ wg, long long T
   }
 }
 
+// Softmax + top-k + renormalisation from logits that a tensor-core GEMM already produced (many experts: the skinny
+// CUDA-core dot products of router_fwd_kernel cost 64 warp reductions per token at E = 64).  Same outputs and rounding
+// points as router_fwd_kernel; logits are read in the activation dtype.
+template <typename T>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+router_from_logits_kernel(const T* __restrict__ logits, long long Tn, int E, int K, float* __restrict__ probs,
+                          float* __restrict__ topk_w, int32_t* __restrict__ topk_idx) {
+  const int lane = threadIdx.x & 31;
+  const long long t = static_cast<long long>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (t >= Tn) return;
+  const bool has0 = lane < E, has1 = lane + 32 < E;
+  const float l0 = has0 ? static_cast<float>(logits[t * E + lane]) : -INFINITY;
+  const float l1 = has1 ? static_cast<float>(logits[t * E + lane + 32]) : -INFINITY;
+  const float m = warp_max(fmaxf(l0, l1));
+  const float e0v = has0 ? expf(l0 - m) : 0.f, e1v = has1 ? expf(l1 - m) : 0.f;
+  const float denom = warp_sum(e0v + e1v);
+  const float p0 = e0v / denom, p1 = e1v / denom;
+  if (has0) probs[t * E + lane] = p0;
+  if (has1) probs[t * E + lane + 32] = p1;
+  float tv[kMaxK];
+  int ti[kMaxK];
+  warp_topk(p0, p1, lane, E, K, tv, ti);
+  if (lane == 0) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < kMaxK; ++k)
+      if (k < K) s += tv[k];
+    s = round_as(s, static_cast<const T*>(nullptr));
+#pragma unroll
+    for (int k = 0; k < kMaxK; ++k)
+      if (k < K) {
+        topk_w[t * K + k] = tv[k] / s;
+        topk_idx[t * K + k] = ti[k];
+      }
+  }
+}
+
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 topk_renorm_kernel(const float* __restrict__ scores, long long Tn, int E, int K, int mode, int round_dtype,
                    float* __restrict__ topk_w, int32_t* __restrict__ topk_idx) {
@@ -407,6 +444,26 @@ extern "C" int csmoe_router_fwd(const void* x, const void* wg, int32_t x_dtype, 
                                                                        static_cast<float*>(logits), probs, topk_w, topk_idx);
   } else {
     CSMOE_CHECK_ARG(false, "csmoe_router_fwd: unsupported dtype %d", x_dtype);
+  }
+  CSMOE_CHECK_LAUNCH();
+  return CSMOE_OK;
+}
+
+extern "C" int csmoe_router_from_logits(const void* logits, int32_t dtype, int64_t T, int32_t E, int32_t K, float* probs,
+                                        float* topk_w, int32_t* topk_idx, void* stream_) {
+  CSMOE_CHECK_ARG(logits && probs && topk_w && topk_idx, "csmoe_router_from_logits: NULL pointer");
+  CSMOE_CHECK_ARG(E >= 1 && E <= kMaxE && K >= 1 && K <= kMaxK && K <= E && T >= 0, "csmoe_router_from_logits: bad sizes");
+  if (T == 0) return CSMOE_OK;
+  const unsigned grid = static_cast<unsigned>((T + kWarpsPerBlock - 1) / kWarpsPerBlock);
+  cudaStream_t stream = as_stream(stream_);
+  if (dtype == CSMOE_BF16) {
+    router_from_logits_kernel<__nv_bfloat16><<<grid, kWarpsPerBlock * 32, 0, stream>>>(
+        static_cast<const __nv_bfloat16*>(logits), T, E, K, probs, topk_w, topk_idx);
+  } else if (dtype == CSMOE_F32) {
+    router_from_logits_kernel<float><<<grid, kWarpsPerBlock * 32, 0, stream>>>(static_cast<const float*>(logits), T, E, K,
+                                                                               probs, topk_w, topk_idx);
+  } else {
+    CSMOE_CHECK_ARG(false, "csmoe_router_from_logits: unsupported dtype %d", dtype);
   }
   CSMOE_CHECK_LAUNCH();
   return CSMOE_OK;

@@ -115,6 +115,14 @@ def route_build(sel: torch.Tensor, num_experts: int, row_tile: Optional[int] = N
 
 
 # ----------------------------------------------------------------------------------------------- router
+_ROUTER_GEMM = __import__("os").environ.get("CSMOE_ROUTER_GEMM", "1") != "0"
+
+
+def _router_gemm_ok(T: int, D: int, E: int, dtype: torch.dtype) -> bool:
+    """Gate GEMM on the tensor cores: worth it (and legal for the grouped GEMM) from ~16 experts on bf16 activations."""
+    return _ROUTER_GEMM and dtype == torch.bfloat16 and E >= 16 and E % 8 == 0 and T >= 256 and T % ROW_TILE == 0 and D % 64 == 0
+
+
 def router_fwd(x: torch.Tensor, wg: torch.Tensor, top_k: int):
     """x [T, D], wg [E, D] (same dtype) -> logits [T,E] (x dtype), probs [T,E] f32, topk_w [T,K] f32, topk_idx [T,K] i32."""
     _cuda(x, wg)
@@ -122,10 +130,15 @@ def router_fwd(x: torch.Tensor, wg: torch.Tensor, top_k: int):
     x, wg = x.contiguous(), wg.contiguous()
     T, D = x.shape
     E = wg.shape[0]
-    logits = torch.empty(T, E, dtype=x.dtype, device=x.device)
     probs = torch.empty(T, E, dtype=torch.float32, device=x.device)
     tw = torch.empty(T, top_k, dtype=torch.float32, device=x.device)
     ti = torch.empty(T, top_k, dtype=torch.int32, device=x.device)
+    if _router_gemm_ok(T, D, E, x.dtype):
+        # many experts: logits = x . Wg^T as a one-"expert" dense grouped GEMM, then softmax / top-k from the logits
+        logits = gemm_rows(x, wg.unsqueeze(0), w_is_kn=False, dense_rows=T, a_expert_rows=0)
+        _call("csmoe_router_from_logits", _p(logits), _dt(logits), T, E, top_k, _p(probs), _p(tw), _p(ti), _stream())
+        return logits, probs, tw, ti
+    logits = torch.empty(T, E, dtype=x.dtype, device=x.device)
     _call("csmoe_router_fwd", _p(x), _p(wg), _dt(x), T, D, E, top_k, _p(logits), _p(probs), _p(tw), _p(ti), _stream())
     return logits, probs, tw, ti
 
@@ -163,6 +176,15 @@ def router_bwd(x: torch.Tensor, wg: torch.Tensor, probs: torch.Tensor, topk_w: t
     dtw, dprobs, dlogits, g_losses = f32(dtw), f32(dprobs), f32(dlogits), f32(g_losses)
     wg_dtype = wg_dtype or wg.dtype
     dl = torch.empty(T, E, dtype=torch.float32, device=dev)
+    if _router_gemm_ok(T, D, E, x.dtype) and wg_dtype in (torch.bfloat16, torch.float32):
+        # many experts: only d logits comes from the fused kernel; dx = dl . Wg and dWg = dl^T . x run on the tensor
+        # cores with dl rounded to the activation dtype (what autograd hands the reference's bf16 gate Linear)
+        _call("csmoe_router_bwd", _p(x), _p(wg), _dt(x), _p(probs), _p(topk_w), _p(topk_idx), _p(dtw), _p(dprobs),
+              _p(dlogits), _p(lse), _p(cnt), _p(g_losses), batch, N, D, E, K, _p(dl), None, None, F32, None, _stream())
+        dlb = dl.to(x.dtype)
+        dx = gemm_rows(dlb, wg.unsqueeze(0), w_is_kn=True, dense_rows=T, a_expert_rows=0) if need_dx else None
+        dwg = gemm_reduce(dlb, x, 1, dense_rows=T, out_dtype=wg_dtype)[0] if need_dwg else None
+        return dx, dwg
     dx = torch.empty(T, D, dtype=x.dtype, device=dev) if need_dx else None
     dwg = torch.empty(E, D, dtype=wg_dtype, device=dev) if need_dwg else None
     ws = None

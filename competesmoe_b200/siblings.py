@@ -12,6 +12,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import ops
 from .functional import DenseFFNFn, GateFn
 from .multimodal import MoeLayer, TopkRenormFn, register_moe
 
@@ -113,10 +114,11 @@ class _CosineGateLayer(MoeLayer):
         ok = gate_logits.isfinite()
         gate_logits = torch.where(ok, gate_logits, gate_logits.masked_fill(~ok, float("inf")).min())
         gate_softmax = F.softmax(gate_logits / self.temperature, dim=-1, dtype=torch.float).to(x.dtype)
-        kept, gidx = torch.sort(gate_softmax.float(), dim=-1, descending=True, stable=True)   # ties: lowest index first
-        kept, gidx = kept[:, :K].to(x.dtype), gidx[:, :K].int()
+        # indices from the top-k kernel (ties: lowest index first), values gathered so that autograd sees them
+        _, gidx = ops.topk_renorm(gate_softmax.detach().float(), K)
+        kept = torch.gather(gate_softmax, 1, gidx.long())
         gw = torch.softmax(kept, dim=-1).float()
-        out = self._sparse_ffn(x2, gw, gidx.contiguous(), w1, b1, w2, b2, self._spec(lay))
+        out = self._sparse_ffn(x2, gw, gidx, w1, b1, w2, b2, self._spec(lay))
         aux, info = x.new_zeros(()), {}
         if x.requires_grad:
             aux, bal, z = self.combine_loss(gidx.view(B, N, K), gate_softmax.view(B, N, E), gate_logits.view(B, N, E))

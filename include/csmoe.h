@@ -75,6 +75,10 @@ int csmoe_route_build(const int32_t* sel, int64_t n_slots, int32_t num_experts, 
 int csmoe_router_fwd(const void* x, const void* wg, int32_t x_dtype, int64_t T, int32_t D, int32_t E, int32_t K,
                      void* logits, float* probs, float* topk_w, int32_t* topk_idx, void* stream);
 
+/* The softmax / top-k / renormalisation half of csmoe_router_fwd for logits [T, E] that were produced elsewhere (the
+ * gate GEMM on the tensor cores when E is large: csmoe_grouped_gemm with one "expert" = the gate matrix). */
+int csmoe_router_from_logits(const void* logits, int32_t dtype, int64_t T, int32_t E, int32_t K, float* probs,
+                             float* topk_w, int32_t* topk_idx, void* stream);
 /* Top-k over given fp32 scores[T,E] (competition step: affinity scores; moe_model/.../competesmoe.py:249-254).
  * mode 0: w = topk values; mode 1: w = sigmoid(topk values) (norm_sigmoid).  Then w /= round_to(dtype)(sum w). */
 int csmoe_topk_renorm(const float* scores, int64_t T, int32_t E, int32_t K, int32_t mode, int32_t round_dtype,
