@@ -453,10 +453,91 @@ def gen_all_siblings(mm):
     gen_sibling(mm, "sib_deepseekv3_nograd_f32", "deepseekv3", "siglip", 64, 64, 128, 5, 3, 2, 16, seed=18, requires_grad=False)
 
 
+PT_SIBLING_MODULES = {"smoe": "smoe", "smoe_sigmoid": "smoeut_norm", "xmoe": "xmoe", "smoe_perturbed": "smoe_perturbed",
+                      "deepseekv2": "deepseekv2", "deepseekv3": "deepseekv3"}
+PT_SIBLING_EXTRA = {"xmoe": ("expert_embeddings", "expert_sel"), "smoe_perturbed": ("expert_embeddings", "expert_sel"),
+                    "deepseekv2": ("keys_shared", "values_shared"),
+                    "deepseekv3": ("keys_shared", "values_shared", "e_score_correction_bias")}
+
+
+def gen_pretrain_sibling(pm, fixture, moe_name, D, E, H, K, B, N, seed=0):
+    """Unmodified reference sibling layer (smoe.py, smoeut_norm.py, xmoe.py, smoe_perturbed.py, deepseekv2.py,
+    deepseekv3.py) with its `cvmm` name bound to the oracle's per-expert restatement, as in gen_pretrain."""
+    from oracle import pretrain as op
+    from oracle import pretrain_siblings as ops_
+
+    def cvmm_standin(x, sel, keys):
+        if not isinstance(sel, pm["cvmm"].CVMMSel):
+            sel = pm["cvmm"].cvmm_prepare_sel(sel, keys.shape[0])
+        s = op.Sel(sel.raw_sel, sel.sel, sel.sel_index, sel.out_index, sel.reduction_weight)
+        return op.cvmm(x, s, keys, torch.float32)
+
+    with quiet():
+        mod = importlib.import_module("layers.moe." + PT_SIBLING_MODULES[moe_name])
+    pm["base"].cvmm = cvmm_standin
+    mod.cvmm = cvmm_standin
+    args = pt_args()
+    torch.manual_seed(seed)
+    with quiet():
+        layer = pm["get_moe"](moe_name)(D, E, H, n_heads=K, args=args, activation=F.relu, selection_mode="gate",
+                                        log_interval=None)
+    layer.train()
+    layer.regularization_present = True
+    names = ("w_gate", "keys", "values") + PT_SIBLING_EXTRA.get(moe_name, ())
+    before = {n: getattr(layer, n).detach().clone() for n in names}          # xmoe rescales expert_embeddings in forward
+    g = torch.Generator().manual_seed(1234 + seed)
+    x = torch.randn(B, N, D, generator=g).requires_grad_(True)
+    dy = torch.randn(B, N, D, generator=g)
+    out = layer(x)
+    regs = layer.get_reg_loss()
+    loss = (out * dy).sum() + sum(regs.values())
+    loss.backward()
+    fx = {"meta": dict(name=fixture, moe_name=moe_name, D=D, E=E, H=H, K=K, B=B, N=N, args=vars(args)),
+          "x": x.detach().clone(), "dy": dy, "params": before, "out": out.detach().clone(),
+          "regs": {k: v.detach().clone() for k, v in regs.items()}, "dx": x.grad.clone(),
+          "grads": {n: (getattr(layer, n).grad.clone() if getattr(layer, n).grad is not None else None) for n in names}}
+    if "expert_embeddings" in before:
+        fx["expert_embeddings_after"] = layer.expert_embeddings.detach().clone()
+    # oracle replay
+    x2 = fx["x"].clone().requires_grad_(True)
+    p2 = {n: v.clone().requires_grad_(True) for n, v in before.items()}
+    o_out, o_regs, dbg = ops_.sibling_forward(moe_name, x2, p2, K, args)
+    ((o_out * dy).sum() + sum(o_regs.values())).backward()
+    tol = dict(rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(o_out, fx["out"], **tol)
+    assert set(o_regs) == set(regs), (set(o_regs), set(regs))
+    for k_ in regs:
+        torch.testing.assert_close(o_regs[k_], fx["regs"][k_], **tol)
+    torch.testing.assert_close(x2.grad, fx["dx"], **tol)
+    for n in names:
+        if fx["grads"][n] is None:
+            assert p2[n].grad is None or float(p2[n].grad.abs().max()) == 0.0, n
+        else:
+            torch.testing.assert_close(p2[n].grad, fx["grads"][n], **tol)
+    if "expert_embeddings" in before:
+        torch.testing.assert_close(p2["expert_embeddings"].detach(), fx["expert_embeddings_after"], **tol)
+    fx["selected"] = dbg["selected"].clone()
+    torch.save(fx, OUT / f"{fixture}.pt")
+    print(f"  wrote {fixture}.pt  (oracle == reference)  regs={ {k: round(float(v), 6) for k, v in regs.items()} }")
+
+
+def gen_all_pretrain_siblings(pm):
+    print("pretrain sibling routers:")
+    gen_pretrain_sibling(pm, "ptsib_smoe_f32", "smoe", 64, 8, 32, 2, 2, 32, seed=20)
+    gen_pretrain_sibling(pm, "ptsib_sigmoid_f32", "smoe_sigmoid", 64, 8, 32, 2, 2, 32, seed=21)
+    gen_pretrain_sibling(pm, "ptsib_xmoe_f32", "xmoe", 64, 8, 32, 2, 2, 24, seed=22)
+    gen_pretrain_sibling(pm, "ptsib_perturbed_f32", "smoe_perturbed", 64, 16, 16, 4, 2, 16, seed=23)
+    gen_pretrain_sibling(pm, "ptsib_deepseekv2_f32", "deepseekv2", 64, 8, 32, 2, 2, 24, seed=24)
+    gen_pretrain_sibling(pm, "ptsib_deepseekv3_f32", "deepseekv3", 64, 16, 16, 4, 2, 16, seed=25)
+
+
 def main():
     OUT.mkdir(parents=True, exist_ok=True)
     if "--siblings-only" in sys.argv:
         gen_all_siblings(load_multimodal_reference())
+        return
+    if "--pretrain-siblings-only" in sys.argv:
+        gen_all_pretrain_siblings(load_pretrain_reference())
         return
     if os.environ.get("TRITON_INTERPRET") == "1":
         gen_cvmm_interpreter()
@@ -482,6 +563,7 @@ def main():
                  router_theta=0.5)
     gen_pretrain(pm, "pt_comp_intopk_f32", 64, 8, 32, 2, 2, 16, True, seed=3, in_topk=True)
     gen_pretrain(pm, "pt_comp_tribrid_f32", 64, 8, 32, 2, 2, 16, True, seed=4, tribrid=True)
+    gen_all_pretrain_siblings(pm)
     print("done; now run:  TRITON_INTERPRET=1 python -m oracle.gen_golden")
 
 

@@ -158,3 +158,33 @@ def test_sibling_router_oracle_matches_reference(name):
         for k, v in gate.items():
             if fx["dgate"][k] is not None:
                 torch.testing.assert_close(v.grad, fx["dgate"][k], **tol)
+
+
+PTSIB = ["ptsib_smoe_f32", "ptsib_sigmoid_f32", "ptsib_xmoe_f32", "ptsib_perturbed_f32", "ptsib_deepseekv2_f32",
+         "ptsib_deepseekv3_f32"]
+
+
+@pytest.mark.parametrize("name", PTSIB)
+def test_pretrain_sibling_oracle_matches_reference(name):
+    """oracle/pretrain_siblings.py against the unmodified reference classes of moe_pretrain_model/layers/moe (smoe,
+    smoe_sigmoid, xmoe, smoe_perturbed, deepseekv2, deepseekv3)."""
+    from oracle import pretrain_siblings as ops_
+    fx = load_golden(name)
+    m = fx["meta"]
+    args = SimpleNamespace(**m["args"])
+    x = fx["x"].clone().requires_grad_(True)
+    params = {k: _req(v) for k, v in fx["params"].items()}
+    out, regs, dbg = ops_.sibling_forward(m["moe_name"], x, params, m["K"], args)
+    ((out * fx["dy"]).sum() + sum(regs.values())).backward()
+    tol = dict(rtol=1e-4, atol=1e-6)
+    assert torch.equal(dbg["selected"], fx["selected"])
+    torch.testing.assert_close(out, fx["out"], **tol)
+    assert set(regs) == set(fx["regs"])
+    for k in regs:
+        torch.testing.assert_close(regs[k], fx["regs"][k], **tol)
+    torch.testing.assert_close(x.grad, fx["dx"], **tol)
+    for k, g in fx["grads"].items():
+        if g is not None:
+            torch.testing.assert_close(params[k].grad, g, **tol)
+    if "expert_embeddings_after" in fx:
+        torch.testing.assert_close(params["expert_embeddings"].detach(), fx["expert_embeddings_after"], **tol)
