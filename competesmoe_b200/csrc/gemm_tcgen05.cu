@@ -44,6 +44,7 @@ struct KParams {
   int glu_f;          // GLU epilogues: F (forward: n == 2F and tiles interleave gate|up; backward: n == F)
   int epi;            // kEpiPlain / kEpiGluFwd / kEpiActBwd / kEpiGluBwd
   int band;           // n-blocks per rasterisation band
+  int raster_m;       // pair / wide ROWS launches: 1 = bands of m-blocks with m fastest (see decode_tile_pair)
   int num_m_pairs;    // CTA-pair kernel: number of 256-row blocks
   const void* aux;    // backward epilogues: the saved pre-activation z
   long long ldaux;
@@ -63,6 +64,7 @@ struct KParams {
   int kcat;           // ROWS + dense: C[rows, n] = sum_e A[e*a_expert_rows + rows, k] . B[e]  (the k loop runs over experts too)
   int dbg_mode;       // tuning experiments (CSMOE_GEMM_DBG): 1 = no TMA loads after the first pipeline fill, 2 = no MMAs
   int direct_epi;     // 1 = register-direct (row per thread) epilogue stores instead of the staged, coalesced ones
+  int tma_epi;        // staged epilogue only: 1 = the staged 32 x 32 groups leave through TMA stores (tensor maps tma_c / tma_p)
   unsigned long long* stats;  // debug (CSMOE_GEMM_STATS=1): per CTA {producer wait, mma wait full, mma wait tempty, epilogue, total, tiles}
 };
 
@@ -346,6 +348,9 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+__device__ __forceinline__ float2 unpack_bf16(uint32_t w) {
+  return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
 __device__ __forceinline__ unsigned long long shfl_u64(unsigned long long v, int src) {
   const uint32_t lo = __shfl_sync(0xffffffffu, static_cast<uint32_t>(v), src);
   const uint32_t hi = __shfl_sync(0xffffffffu, static_cast<uint32_t>(v >> 32), src);
@@ -554,9 +559,159 @@ __device__ __forceinline__ void epilogue_tile_staged(const KParams& p, const Til
   }
 }
 
+// ------------------------------------------------------------------------------------------------ TMA-store epilogue
+// Plain (bias / activation / saved pre-activation) and fused-GLU epilogues whose outputs are row-major matrices: every
+// 32 x 32 group is packed into the warp's staging tile and leaves through one TMA store, and the tcgen05.ld of group
+// g+1 is in flight while group g is converted and staged (TMEM reads, 64 B/clk per SM, are what bounds this path).
+template <bool FP32>
+__device__ __forceinline__ void tma_store_packed(uint32_t stg, int lane, const uint32_t (&w)[FP32 ? 32 : 16],
+                                                 const CUtensorMap* map, int col, int row, int e, uint32_t& slot) {
+  // w: this thread's row of the group, 32 fp32 words (FP32) or 16 packed bf16 pairs
+  constexpr int P = FP32 ? 128 : 64;
+  const uint32_t buf = FP32 ? stg : stg + (slot & 1u) * 2048u;
+  ++slot;
+  if (lane == 0) {
+    if (FP32)
+      ptx::bulk_wait_group_read<0>();
+    else
+      ptx::bulk_wait_group_read<1>();
+  }
+  __syncwarp();
+#pragma unroll
+  for (int c = 0; c < P / 16; ++c) sts128(stg_addr<P>(buf, lane, c), w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+  ptx::fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    ptx::tma_store_3d(map, buf, col, row, e);
+    ptx::bulk_commit_group();
+  }
+}
+
+template <int MODE, int BN>
+__device__ __forceinline__ void epilogue_tile_tma(const KParams& p, const Tile& ti, uint32_t t_row, bool has_acc, int row0,
+                                                  int half, int lane, uint32_t stg, const CUtensorMap* map_c,
+                                                  const CUtensorMap* map_p, uint32_t& slot) {
+  const int te = MODE == CSMOE_GEMM_REDUCE ? ti.e : 0;
+  if (p.epi == kEpiPlain) {
+    constexpr int G = BN / 64;                        // 32-column groups per warp
+    const long long boff = static_cast<long long>(ti.e) * p.n;
+    const bool want_round = p.act != CSMOE_ACT_NONE || p.preact != nullptr;
+    uint32_t v[32];
+    if (has_acc) ptx::tmem_ld_32x32b_x32(t_row + half * (BN / 2), v);
+#pragma unroll 1
+    for (int g = 0; g < G; ++g) {
+      const int tcol = half * (BN / 2) + g * 32;
+      const int col0 = ti.nb * BN + tcol;
+      const bool more = has_acc && g + 1 < G;
+      if (has_acc) ptx::tmem_ld_wait_dep(v);
+      if (col0 >= p.n) {
+        if (more) ptx::tmem_ld_32x32b_x32(t_row + tcol + 32, v);
+        continue;
+      }
+      float f[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) f[i] = has_acc ? __uint_as_float(v[i]) : 0.f;
+      if (p.bias != nullptr) {
+        const int valid = min(32, p.n - col0);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (c * 8 < valid) {
+            float b[8];
+            if (p.bias_fp32)
+              load8(reinterpret_cast<const float*>(p.bias) + boff + col0 + c * 8, b);
+            else
+              load8(reinterpret_cast<const __nv_bfloat16*>(p.bias) + boff + col0 + c * 8, b);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[c * 8 + i] += b[i];
+          }
+        }
+      }
+      if (p.c_fp32) {
+        uint32_t w[32];
+        if (want_round) {
+          if (p.preact != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) w[i] = __float_as_uint(f[i]);
+            tma_store_packed<true>(stg, lane, w, map_p, col0, row0, te, slot);
+          }
+          act_apply_vec<32>(f, p.act, false);
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) w[i] = __float_as_uint(f[i]);
+        if (more) ptx::tmem_ld_32x32b_x32(t_row + tcol + 32, v);   // streams in while this group is staged and stored
+        tma_store_packed<true>(stg, lane, w, map_c, col0, row0, te, slot);
+      } else {
+        uint32_t w[16];
+        if (want_round) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            w[i] = pack_bf16(f[2 * i], f[2 * i + 1]);
+            const float2 t = unpack_bf16(w[i]);
+            f[2 * i] = t.x;
+            f[2 * i + 1] = t.y;
+          }
+          if (p.preact != nullptr) tma_store_packed<false>(stg, lane, w, map_p, col0, row0, te, slot);
+          act_apply_vec<32>(f, p.act, true);
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) w[i] = pack_bf16(f[2 * i], f[2 * i + 1]);
+        if (more) ptx::tmem_ld_32x32b_x32(t_row + tcol + 32, v);
+        tma_store_packed<false>(stg, lane, w, map_c, col0, row0, te, slot);
+      }
+    }
+  } else if (p.epi == kEpiGluFwd) {
+    // TMEM columns [0, BN/2) = gate, [BN/2, BN) = up of BN/2 output columns; z = (gate | up) saved for backward,
+    // h = up * silu(gate), every intermediate rounded to bf16 like the eager reference (Phi3MLP).
+    if constexpr (BN >= 256) {
+      constexpr int kGate = BN / 2;
+      constexpr int G = kGate / 64;
+      uint32_t vg[32], vu[32];
+      if (has_acc) {
+        ptx::tmem_ld_32x32b_x32(t_row + half * (kGate / 2), vg);
+        ptx::tmem_ld_32x32b_x32(t_row + kGate + half * (kGate / 2), vu);
+      }
+#pragma unroll 1
+      for (int g = 0; g < G; ++g) {
+        const int tcol = half * (kGate / 2) + g * 32;
+        const int col0 = ti.nb * kGate + tcol;
+        uint32_t wg[16], wu[16];
+        if (has_acc) {
+          ptx::tmem_ld_wait_dep(vg);
+          ptx::tmem_ld_wait_dep(vu);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            wg[i] = pack_bf16(__uint_as_float(vg[2 * i]), __uint_as_float(vg[2 * i + 1]));
+            wu[i] = pack_bf16(__uint_as_float(vu[2 * i]), __uint_as_float(vu[2 * i + 1]));
+          }
+          if (g + 1 < G) {                               // next group's accumulators stream in during the SiLU math
+            ptx::tmem_ld_32x32b_x32(t_row + tcol + 32, vg);
+            ptx::tmem_ld_32x32b_x32(t_row + kGate + tcol + 32, vu);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) wg[i] = wu[i] = 0u;
+        }
+        if (col0 < p.glu_f) {
+          tma_store_packed<false>(stg, lane, wg, map_p, col0, row0, 0, slot);
+          tma_store_packed<false>(stg, lane, wu, map_p, p.glu_f + col0, row0, 0, slot);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float2 zg = unpack_bf16(wg[i]);
+            const float2 zu = unpack_bf16(wu[i]);
+            wg[i] = pack_bf16(zu.x * bf16_round(act_apply(zg.x, CSMOE_ACT_SILU, true)),
+                              zu.y * bf16_round(act_apply(zg.y, CSMOE_ACT_SILU, true)));
+          }
+          tma_store_packed<false>(stg, lane, wg, map_c, col0, row0, 0, slot);
+        }
+      }
+    }
+  }
+}
+
 template <int MODE, bool B_MN, int BN>
 __global__ void __launch_bounds__(kThreads, 1)
-grouped_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const KParams p) {
+grouped_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                    const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ CUtensorMap tma_p, const KParams p) {
   constexpr bool kAMn = (MODE == CSMOE_GEMM_REDUCE);
   constexpr bool kBMn = kAMn || B_MN;
   constexpr int kBBytes = BN * kBK * 2;
@@ -697,7 +852,7 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     const int quad = warp & 3;
     const int half = (warp - 2) >> 2;
     const int row_in_tile = quad * 32 + lane;
-    uint32_t acc = 0, acc_phase = 0;
+    uint32_t acc = 0, acc_phase = 0, tma_slot = 0;
     for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
       const Tile ti = decode_tile<MODE>(p, t);
       if (!ti.valid) continue;
@@ -708,7 +863,10 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       }
       const long long out_row = static_cast<long long>(ti.mb) * kBM + row_in_tile;
       const uint32_t t_row = tmem_base + acc * BN + (static_cast<uint32_t>(quad * 32) << 16);
-      if (p.direct_epi)
+      if (p.tma_epi)
+        epilogue_tile_tma<MODE, BN>(p, ti, t_row, has_acc, ti.mb * kBM + quad * 32, half, lane,
+                                    stg_base + (warp - 2) * kStageTileBytes, &tma_c, &tma_p, tma_slot);
+      else if (p.direct_epi)
         epilogue_tile<MODE, BN>(p, ti, t_row, has_acc, out_row, half);
       else
         epilogue_tile_staged<MODE, BN>(p, ti, t_row, has_acc, out_row - lane, half, lane, stg_base + (warp - 2) * kStageTileBytes);
@@ -722,6 +880,7 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         }
       }
     }
+    if (p.tma_epi && lane == 0) ptx::bulk_wait_group<0>();   // the staging tiles must outlive their TMA stores
   }
 
   ptx::tc_fence_before();
@@ -750,13 +909,24 @@ __device__ __forceinline__ Tile decode_tile_pair(const KParams& p, long long t, 
   Tile ti;
   const int num_m2 = p.num_m_pairs;
   if (MODE == CSMOE_GEMM_ROWS) {
-    const long long band_tiles = static_cast<long long>(p.band) * num_m2;
-    const int b = static_cast<int>(t / band_tiles);
-    const int r = static_cast<int>(t % band_tiles);
-    const int nb0 = b * p.band;
-    const int w = min(p.band, p.num_n_blocks - nb0);
-    ti.mb = r / w;
-    ti.nb = nb0 + r % w;
+    if (p.raster_m) {
+      // bands of `band` m-blocks, m fastest inside a band: neighbouring clusters ask for the same B tile at the same time
+      const long long band_tiles = static_cast<long long>(p.band) * p.num_n_blocks;
+      const int b = static_cast<int>(t / band_tiles);
+      const int r = static_cast<int>(t % band_tiles);
+      const int mb0 = b * p.band;
+      const int w = min(p.band, num_m2 - mb0);
+      ti.nb = r / w;
+      ti.mb = mb0 + r % w;
+    } else {
+      const long long band_tiles = static_cast<long long>(p.band) * num_m2;
+      const int b = static_cast<int>(t / band_tiles);
+      const int r = static_cast<int>(t % band_tiles);
+      const int nb0 = b * p.band;
+      const int w = min(p.band, p.num_n_blocks - nb0);
+      ti.mb = r / w;
+      ti.nb = nb0 + r % w;
+    }
     if (p.kcat) {
       ti.e = 0;
       ti.a_row = ti.mb * 256 + rank * kBM;
@@ -799,6 +969,7 @@ __device__ __forceinline__ Tile decode_tile_pair(const KParams& p, long long t, 
 template <int MODE, bool B_MN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 grouped_gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                         const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ CUtensorMap tma_p,
                          const KParams p) {
   constexpr int BN = 256;
   constexpr bool kAMn = (MODE == CSMOE_GEMM_REDUCE);
@@ -961,6 +1132,7 @@ grouped_gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
     const int half = (warp - 2) >> 2;
     const int row_in_tile = quad * 32 + lane;
     unsigned long long epi_cycles = 0;
+    uint32_t tma_slot = 0;
     uint32_t acc = 0, acc_phase = 0;
     for (long long t = cluster_id; t < p.total_tiles; t += num_clusters) {
       const Tile ti = decode_tile_pair<MODE>(p, t, rank);
@@ -973,7 +1145,10 @@ grouped_gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
       const long long out_row = static_cast<long long>(ti.mb) * 256 + rank * kBM + row_in_tile;
       const uint32_t t_row = tmem_base + acc * BN + (static_cast<uint32_t>(quad * 32) << 16);
       const long long e0 = st_on ? clock64() : 0;
-      if (p.direct_epi)
+      if (p.tma_epi)
+        epilogue_tile_tma<MODE, BN>(p, ti, t_row, has_acc, ti.mb * 256 + rank * kBM + quad * 32, half, lane,
+                                    stg_base + (warp - 2) * kStageTileBytes, &tma_c, &tma_p, tma_slot);
+      else if (p.direct_epi)
         epilogue_tile<MODE, BN>(p, ti, t_row, has_acc, out_row, half);
       else
         epilogue_tile_staged<MODE, BN>(p, ti, t_row, has_acc, out_row - lane, half, lane, stg_base + (warp - 2) * kStageTileBytes);
@@ -993,6 +1168,7 @@ grouped_gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
       }
       if (st_on) epi_cycles += static_cast<unsigned long long>(clock64() - e0);
     }
+    if (p.tma_epi && lane == 0) ptx::bulk_wait_group<0>();   // the staging tiles must outlive their TMA stores
     if (st_on && warp == 2 && lane == 0) p.stats[blockIdx.x * 8 + 3] = epi_cycles;
   }
 
@@ -1025,6 +1201,7 @@ constexpr int kWideStageBytes = kABytes + 2 * kWideHalfBytes;       // 48 KiB pe
 template <int MODE, bool B_MN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 grouped_gemm_wide_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                         const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ CUtensorMap tma_p,
                          const KParams p) {
   constexpr int BN = 512;
   constexpr bool kAMn = (MODE == CSMOE_GEMM_REDUCE);
@@ -1085,6 +1262,7 @@ grouped_gemm_wide_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       unsigned long long w_empty = 0;
+      int dbg_filled = 0;
       for (long long t = cluster_id; t < p.total_tiles; t += num_clusters) {
         const Tile ti = decode_tile_pair<MODE>(p, t, rank);
         if (!ti.valid) continue;
@@ -1092,6 +1270,15 @@ grouped_gemm_wide_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
         const uint32_t bytes = 2u * (kABytes + halves * kWideHalfBytes);
         for (int kb = 0; kb < ti.nkb; ++kb) {
           timed_wait(empty_bar(stage), phase ^ 1u, st_on, w_empty);
+          if ((p.dbg_mode & 1) && dbg_filled >= kWideStages) {
+            if (leader) ptx::mbar_arrive(full_bar(stage));
+            if (++stage == kWideStages) {
+              stage = 0;
+              phase ^= 1u;
+            }
+            continue;
+          }
+          ++dbg_filled;
           if (leader) ptx::mbar_arrive_expect_tx(full_bar(stage), bytes);
           const uint32_t fb = ptx::mapa(full_bar(stage), 0);
           const uint32_t sa = smem_base + stage * kWideStageBytes;
@@ -1159,7 +1346,7 @@ grouped_gemm_wide_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
               const uint32_t sbh = sb + h * kWideHalfBytes;
               const uint64_t bdesc = kBMn ? ptx::make_smem_desc_sw128(sbh + k * 2048, kSubTileBytes, 1024)
                                           : ptx::make_smem_desc_sw128(sbh + k * 32, 16, 1024);
-              ptx::umma_f16_cg2(tmem_base + h * 256, adesc, bdesc, kIdesc, (kb | k) != 0 ? 1u : 0u);
+              if (!(p.dbg_mode & 2)) ptx::umma_f16_cg2(tmem_base + h * 256, adesc, bdesc, kIdesc, (kb | k) != 0 ? 1u : 0u);
             }
           }
           ptx::umma_commit_cg2_mc(empty_bar(stage), 0x3);
@@ -1183,6 +1370,7 @@ grouped_gemm_wide_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
     const int half = (warp - 2) >> 2;
     const int row_in_tile = quad * 32 + lane;
     unsigned long long epi_cycles = 0;
+    uint32_t tma_slot = 0;
     uint32_t acc_phase = 0;
     for (long long t = cluster_id; t < p.total_tiles; t += num_clusters) {
       const Tile ti = decode_tile_pair<MODE>(p, t, rank);
@@ -1195,7 +1383,10 @@ grouped_gemm_wide_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
       const long long out_row = static_cast<long long>(ti.mb) * 256 + rank * kBM + row_in_tile;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
       const long long e0 = st_on ? clock64() : 0;
-      if (p.direct_epi)
+      if (p.tma_epi)
+        epilogue_tile_tma<MODE, BN>(p, ti, t_row, has_acc, ti.mb * 256 + rank * kBM + quad * 32, half, lane,
+                                    stg_base + (warp - 2) * kStageTileBytes, &tma_c, &tma_p, tma_slot);
+      else if (p.direct_epi)
         epilogue_tile<MODE, BN>(p, ti, t_row, has_acc, out_row, half);
       else
         epilogue_tile_staged<MODE, BN>(p, ti, t_row, has_acc, out_row - lane, half, lane, stg_base + (warp - 2) * kStageTileBytes);
@@ -1212,6 +1403,7 @@ grouped_gemm_wide_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
       }
       if (st_on) epi_cycles += static_cast<unsigned long long>(clock64() - e0);
     }
+    if (p.tma_epi && lane == 0) ptx::bulk_wait_group<0>();   // the staging tiles must outlive their TMA stores
     if (st_on && warp == 2 && lane == 0) p.stats[blockIdx.x * 8 + 3] = epi_cycles;
   }
 
@@ -1265,8 +1457,38 @@ int encode_bf16_map(CUtensorMap* map, const void* base, int rank, const cuuint64
   return CSMOE_OK;
 }
 
+// Output map for the TMA-store epilogue: [experts][rows][cols] of bf16 / fp32, 32 x 32 boxes, swizzle = the staging
+// tile's (64-byte rows for bf16, 128-byte rows for fp32).
+int encode_out_map(CUtensorMap* map, const void* base, bool fp32, long long cols, long long rows, long long experts,
+                   long long ld, long long expert_stride) {
+  EncodeFn fn = get_encode_fn();
+  if (fn == nullptr) {
+    set_error("cuTensorMapEncodeTiled is not available (no CUDA driver?)");
+    return CSMOE_ERR_DRIVER;
+  }
+  const cuuint64_t esz = fp32 ? 4 : 2;
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)experts};
+  cuuint64_t str[2] = {(cuuint64_t)ld * esz, (cuuint64_t)(experts > 1 ? expert_stride : rows * ld) * esz};
+  cuuint32_t box[3] = {32, 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, fp32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base),
+                  dims, str, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  fp32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (output map) failed: CUresult %d (dims %lld,%lld,%lld ld %lld)", (int)r, cols, rows,
+              experts, ld);
+    return CSMOE_ERR_DRIVER;
+  }
+  return CSMOE_OK;
+}
+
+struct Maps {
+  CUtensorMap a, b, c, p;
+};
+
 template <int MODE, bool B_MN, int BN>
-int launch(const CUtensorMap& ma, const CUtensorMap& mb, const KParams& kp, int grid, cudaStream_t stream) {
+int launch(const Maps& m, const KParams& kp, int grid, cudaStream_t stream) {
   constexpr int kStages = (BN == 256) ? 4 : 6;
   constexpr int kSmem = kStages * (kABytes + BN * kBK * 2) + kEpiWarps * kStageTileBytes + 1024 + 256;
   auto kern = grouped_gemm_kernel<MODE, B_MN, BN>;
@@ -1275,13 +1497,13 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const KParams& kp, int 
     CSMOE_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     configured = true;
   }
-  kern<<<grid, kThreads, kSmem, stream>>>(ma, mb, kp);
+  kern<<<grid, kThreads, kSmem, stream>>>(m.a, m.b, m.c, m.p, kp);
   CSMOE_CHECK_LAUNCH();
   return CSMOE_OK;
 }
 
 template <int MODE, bool B_MN>
-int launch_pair(const CUtensorMap& ma, const CUtensorMap& mb, const KParams& kp, int clusters, cudaStream_t stream) {
+int launch_pair(const Maps& m, const KParams& kp, int clusters, cudaStream_t stream) {
   constexpr int kSmem = kPairStages * kPairStageBytes + kEpiWarps * kStageTileBytes + 1024 + 256;
   auto kern = grouped_gemm_pair_kernel<MODE, B_MN>;
   static bool configured = false;
@@ -1289,13 +1511,13 @@ int launch_pair(const CUtensorMap& ma, const CUtensorMap& mb, const KParams& kp,
     CSMOE_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     configured = true;
   }
-  kern<<<2 * clusters, kThreads, kSmem, stream>>>(ma, mb, kp);
+  kern<<<2 * clusters, kThreads, kSmem, stream>>>(m.a, m.b, m.c, m.p, kp);
   CSMOE_CHECK_LAUNCH();
   return CSMOE_OK;
 }
 
 template <int MODE, bool B_MN>
-int launch_wide(const CUtensorMap& ma, const CUtensorMap& mb, const KParams& kp, int clusters, cudaStream_t stream) {
+int launch_wide(const Maps& m, const KParams& kp, int clusters, cudaStream_t stream) {
   constexpr int kSmem = kWideStages * kWideStageBytes + kEpiWarps * kStageTileBytes + 1024 + 256;
   auto kern = grouped_gemm_wide_kernel<MODE, B_MN>;
   static bool configured = false;
@@ -1303,7 +1525,7 @@ int launch_wide(const CUtensorMap& ma, const CUtensorMap& mb, const KParams& kp,
     CSMOE_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     configured = true;
   }
-  kern<<<2 * clusters, kThreads, kSmem, stream>>>(ma, mb, kp);
+  kern<<<2 * clusters, kThreads, kSmem, stream>>>(m.a, m.b, m.c, m.p, kp);
   CSMOE_CHECK_LAUNCH();
   return CSMOE_OK;
 }
@@ -1360,9 +1582,18 @@ int epilogue_override() {
   static const int v = []() {
     const char* e = getenv("CSMOE_GEMM_EPI");
     if (e == nullptr) return 0;
-    return e[0] == 'd' ? 1 : (e[0] == 's' ? 2 : 0);
+    return e[0] == 'd' ? 1 : (e[0] == 's' ? 2 : (e[0] == 't' ? 3 : 0));
   }();
   return v;
+}
+
+// CSMOE_GEMM_TMA: bit 0 = ROWS, bit 1 = REDUCE launches use the TMA-store epilogue by default (default 3)
+bool tma_default(int mode) {
+  static const int m = []() {
+    const char* v = getenv("CSMOE_GEMM_TMA");
+    return v == nullptr ? 3 : atoi(v);
+  }();
+  return (m & (mode == CSMOE_GEMM_ROWS ? 1 : 2)) != 0;
 }
 
 // CSMOE_GEMM_PAIR=0 disables the CTA-pair kernel (A/B comparisons, bring-up)
@@ -1468,7 +1699,14 @@ extern "C" int csmoe_grouped_gemm(const csmoe_gemm_args* a, void* stream_) {
   kp.ldpre = a->ldpre;
   kp.c_expert_stride = a->c_expert_stride;
   kp.num_n_blocks = glu_fwd ? static_cast<int>((n_grid + 127) / 128) : static_cast<int>((a->n + BN - 1) / BN);
-  kp.band = 8;
+  {
+    static const int band = []() { const char* v = getenv("CSMOE_GEMM_BAND"); return v ? atoi(v) : 8; }();
+    kp.band = band > 0 ? band : 8;
+    // m-fastest raster (neighbouring clusters share the B tile, one expert's weights stay hot in L2 while its row
+    // band is swept): DRAM reads of the fc1 launch 1.45 -> 0.75 GB, +7 % (profiles/r01k_gemm_epilogue.md).
+    static const int rm = []() { const char* v = getenv("CSMOE_GEMM_RASTER"); return v ? atoi(v) : 1; }();
+    kp.raster_m = rm;
+  }
   kp.aux = a->aux;
   kp.ldaux = a->ldaux;
   kp.c_rows = reinterpret_cast<const unsigned long long*>(a->c_rows);
@@ -1497,8 +1735,21 @@ extern "C" int csmoe_grouped_gemm(const csmoe_gemm_args* a, void* stream_) {
                       ? 0 : 1;
   if (a->rowsum != nullptr) kp.direct_epi = 1;
   if (epilogue_override() != 0 && !a->accumulate && a->rowsum == nullptr) kp.direct_epi = epilogue_override() == 1 ? 1 : 0;
+  // TMA-store epilogue (the staged groups leave through cp.async.bulk.tensor instead of ld.shared + st.global): every
+  // launch whose outputs are plain row-major matrices.  CSMOE_GEMM_EPI=tma forces it where legal, =staged / =direct
+  // switch it off.
+  const bool tma_legal = a->c_rows == nullptr && a->c != nullptr && !a->accumulate && a->rowsum == nullptr &&
+                         (kp.epi == kEpiPlain || (kp.epi == kEpiGluFwd && kp.glu_f % 32 == 0)) &&
+                         (a->preact == nullptr || (a->ldpre % (a->c_dtype == CSMOE_F32 ? 4 : 8) == 0 &&
+                                                   reinterpret_cast<uintptr_t>(a->preact) % 16 == 0));
+  if (tma_legal && (epilogue_override() == 3 || (epilogue_override() == 0 && tma_default(a->mode)))) {
+    kp.direct_epi = 0;
+    kp.tma_epi = 1;
+  }
 
-  CUtensorMap ma, mb;
+  Maps maps{};
+  CUtensorMap& ma = maps.a;
+  CUtensorMap& mb = maps.b;
   int rc;
   if (a->mode == CSMOE_GEMM_ROWS) {
     const long long a_rows = a->dense ? (a->a_expert_rows ? (long long)E * a->a_expert_rows : a->dense_rows) : a->m;
@@ -1545,6 +1796,18 @@ extern "C" int csmoe_grouped_gemm(const csmoe_gemm_args* a, void* stream_) {
     }
   }
   if (kp.total_tiles == 0) return CSMOE_OK;
+  if (kp.tma_epi) {
+    const bool f32 = a->c_dtype == CSMOE_F32;
+    if (a->mode == CSMOE_GEMM_ROWS) {
+      const long long c_rows_total = static_cast<long long>(kp.num_m_blocks) * kBM;
+      if ((rc = encode_out_map(&maps.c, a->c, f32, glu_fwd ? n_grid : a->n, c_rows_total, 1, a->ldc, 0)) != CSMOE_OK) return rc;
+      if (a->preact != nullptr &&
+          (rc = encode_out_map(&maps.p, a->preact, f32, a->n, c_rows_total, 1, a->ldpre, 0)) != CSMOE_OK)
+        return rc;
+    } else {
+      if ((rc = encode_out_map(&maps.c, a->c, f32, a->n, a->m, E, a->ldc, a->c_expert_stride)) != CSMOE_OK) return rc;
+    }
+  }
   if (pair) {
     kp.num_m_pairs = a->mode == CSMOE_GEMM_ROWS ? kp.num_m_blocks / 2 : static_cast<int>((a->m + 255) / 256);
     // 256 x 512 tiles when the output is wide enough that the second half is (almost) never padding
@@ -1553,7 +1816,11 @@ extern "C" int csmoe_grouped_gemm(const csmoe_gemm_args* a, void* stream_) {
     // bits 2 / 3 force it for every ROWS / REDUCE launch.
     const int wm = wide_mask();
     const long long k_loop = a->sum_experts ? a->k * E : a->k;
-    const bool long_k = a->mode == CSMOE_GEMM_ROWS ? k_loop >= 4096 || (wm & 4) : (wm & 8) != 0;
+    // REDUCE (wgrad): the exposed epilogue is paid back by the 25 % lower operand traffic only when the launch has many
+    // waves of 256 x 512 tiles (wgrad of fc1 at the bench shape: +9 %; of fc2, 10 waves: -6 %).
+    const long long wide_tiles = static_cast<long long>(kp.num_m_pairs) * ((a->n + 511) / 512) * E;
+    const bool long_k = a->mode == CSMOE_GEMM_ROWS ? k_loop >= 4096 || (wm & 4)
+                                                   : (wm & 8) != 0 || wide_tiles >= 16LL * (num_sms() / 2);
     const bool wide = n_grid >= 512 && (n_grid % 512 == 0 || n_grid >= 2048) && long_k &&
                       (wm & (a->mode == CSMOE_GEMM_ROWS ? 1 : 2)) != 0;
     if (wide) kp.num_n_blocks = glu_fwd ? static_cast<int>((n_grid + 255) / 256) : static_cast<int>((a->n + 511) / 512);
@@ -1569,15 +1836,15 @@ extern "C" int csmoe_grouped_gemm(const csmoe_gemm_args* a, void* stream_) {
       int rc2;
       if (wide) {
         if (a->mode == CSMOE_GEMM_ROWS)
-          rc2 = a->b_layout == 0 ? launch_wide<CSMOE_GEMM_ROWS, false>(ma, mb, kp, clusters, stream)
-                                 : launch_wide<CSMOE_GEMM_ROWS, true>(ma, mb, kp, clusters, stream);
+          rc2 = a->b_layout == 0 ? launch_wide<CSMOE_GEMM_ROWS, false>(maps, kp, clusters, stream)
+                                 : launch_wide<CSMOE_GEMM_ROWS, true>(maps, kp, clusters, stream);
         else
-          rc2 = launch_wide<CSMOE_GEMM_REDUCE, true>(ma, mb, kp, clusters, stream);
+          rc2 = launch_wide<CSMOE_GEMM_REDUCE, true>(maps, kp, clusters, stream);
       } else if (a->mode == CSMOE_GEMM_ROWS) {
-        rc2 = a->b_layout == 0 ? launch_pair<CSMOE_GEMM_ROWS, false>(ma, mb, kp, clusters, stream)
-                               : launch_pair<CSMOE_GEMM_ROWS, true>(ma, mb, kp, clusters, stream);
+        rc2 = a->b_layout == 0 ? launch_pair<CSMOE_GEMM_ROWS, false>(maps, kp, clusters, stream)
+                               : launch_pair<CSMOE_GEMM_ROWS, true>(maps, kp, clusters, stream);
       } else {
-        rc2 = launch_pair<CSMOE_GEMM_REDUCE, true>(ma, mb, kp, clusters, stream);
+        rc2 = launch_pair<CSMOE_GEMM_REDUCE, true>(maps, kp, clusters, stream);
       }
       if (rc2 == CSMOE_OK) {
         char what[96];
@@ -1589,14 +1856,14 @@ extern "C" int csmoe_grouped_gemm(const csmoe_gemm_args* a, void* stream_) {
     }
     if (wide) {
       if (a->mode == CSMOE_GEMM_ROWS)
-        return a->b_layout == 0 ? launch_wide<CSMOE_GEMM_ROWS, false>(ma, mb, kp, clusters, stream)
-                                : launch_wide<CSMOE_GEMM_ROWS, true>(ma, mb, kp, clusters, stream);
-      return launch_wide<CSMOE_GEMM_REDUCE, true>(ma, mb, kp, clusters, stream);
+        return a->b_layout == 0 ? launch_wide<CSMOE_GEMM_ROWS, false>(maps, kp, clusters, stream)
+                                : launch_wide<CSMOE_GEMM_ROWS, true>(maps, kp, clusters, stream);
+      return launch_wide<CSMOE_GEMM_REDUCE, true>(maps, kp, clusters, stream);
     }
     if (a->mode == CSMOE_GEMM_ROWS)
-      return a->b_layout == 0 ? launch_pair<CSMOE_GEMM_ROWS, false>(ma, mb, kp, clusters, stream)
-                              : launch_pair<CSMOE_GEMM_ROWS, true>(ma, mb, kp, clusters, stream);
-    return launch_pair<CSMOE_GEMM_REDUCE, true>(ma, mb, kp, clusters, stream);
+      return a->b_layout == 0 ? launch_pair<CSMOE_GEMM_ROWS, false>(maps, kp, clusters, stream)
+                              : launch_pair<CSMOE_GEMM_ROWS, true>(maps, kp, clusters, stream);
+    return launch_pair<CSMOE_GEMM_REDUCE, true>(maps, kp, clusters, stream);
   }
   int grid = num_sms();
   if (grid <= 0) return CSMOE_ERR_CUDA;
@@ -1605,11 +1872,11 @@ extern "C" int csmoe_grouped_gemm(const csmoe_gemm_args* a, void* stream_) {
 
   if (a->mode == CSMOE_GEMM_ROWS) {
     if (a->b_layout == 0)
-      return big_n ? launch<CSMOE_GEMM_ROWS, false, 256>(ma, mb, kp, grid, stream)
-                   : launch<CSMOE_GEMM_ROWS, false, 128>(ma, mb, kp, grid, stream);
-    return big_n ? launch<CSMOE_GEMM_ROWS, true, 256>(ma, mb, kp, grid, stream)
-                 : launch<CSMOE_GEMM_ROWS, true, 128>(ma, mb, kp, grid, stream);
+      return big_n ? launch<CSMOE_GEMM_ROWS, false, 256>(maps, kp, grid, stream)
+                   : launch<CSMOE_GEMM_ROWS, false, 128>(maps, kp, grid, stream);
+    return big_n ? launch<CSMOE_GEMM_ROWS, true, 256>(maps, kp, grid, stream)
+                 : launch<CSMOE_GEMM_ROWS, true, 128>(maps, kp, grid, stream);
   }
-  return big_n ? launch<CSMOE_GEMM_REDUCE, true, 256>(ma, mb, kp, grid, stream)
-               : launch<CSMOE_GEMM_REDUCE, true, 128>(ma, mb, kp, grid, stream);
+  return big_n ? launch<CSMOE_GEMM_REDUCE, true, 256>(maps, kp, grid, stream)
+               : launch<CSMOE_GEMM_REDUCE, true, 128>(maps, kp, grid, stream);
 }
