@@ -84,10 +84,11 @@ class CVMM(Function):
         kb = ops.cast_bf16(keys) if keys.dtype != torch.bfloat16 else keys
         xp = ops.gather_rows(xb, route, slots_per_src_row=slots_per_row)
         yp = ops.gemm_rows(xp, kb, w_is_kn=True, route=route, out_dtype=out_dtype)
-        n_slots, K = route.n_slots, route.top_k
+        n_slots = route.n_slots
         if reduction_weight is None:
             out = ops.scatter_reduce(yp, route.slot_to_row, n_slots, 1)           # back to slot order, no reduction
         else:
+            K = reduction_weight.shape[-1]           # slots reduced into one output row (top-k, or heads x top-k)
             out = ops.combine_fwd(yp, route.slot_to_row, route.sel, reduction_weight.float(), n_slots // K, K,
                                   round_w=out_dtype == torch.bfloat16)
         ctx.route, ctx.slots_per_row = route, slots_per_row
@@ -100,7 +101,8 @@ class CVMM(Function):
     def backward(ctx, g):
         xp, yp, keys, rw = ctx.saved_tensors
         route = ctx.route
-        n_slots, K, E = route.n_slots, route.top_k, route.num_experts
+        n_slots, E = route.n_slots, route.num_experts
+        K = rw.shape[-1] if rw is not None else 1
         g2 = g.reshape(-1, g.shape[-1]).contiguous()
         gb = ops.cast_bf16(g2) if g2.dtype != torch.bfloat16 else g2
         kb = ops.cast_bf16(keys) if keys.dtype != torch.bfloat16 else keys
@@ -130,8 +132,21 @@ def cvmm(x: torch.Tensor, sel: Union[torch.Tensor, CVMMSel], keys: torch.Tensor)
     sel = _complete(sel, keys.shape[0])
     # prepare_sel2 pattern: sel_index = pos // K with out_index = pos (K slots share one input row);
     # after `sel_index = out_index; out_index = None` (or prepare_sel) every slot has its own input row.
-    slots_per_row = sel.raw_sel.shape[-1] if sel.out_index is not None else 1
-    out = CVMM.apply(x, keys, sel._route, slots_per_row, sel.reduction_weight, _out_dtype(x))
+    # MoE attention (full_moe_relative_attention.py:453-458) re-divides: sel_index = out_index // k on per-head inputs
+    # with the reduction weight flattened over (heads, k) -- any uniform `pos // c` pattern is recovered from the
+    # number of input rows, and the reduction group is the last dimension of reduction_weight.
+    n_slots = sel._route.n_slots
+    if sel.out_index is None:
+        slots_per_row = 1
+    else:
+        rows_in = x.numel() // x.shape[-1]
+        if rows_in == 0 or n_slots % rows_in != 0:
+            raise ValueError(f"cvmm: {rows_in} input rows do not divide the {n_slots} selection slots")
+        slots_per_row = n_slots // rows_in
+    rw = sel.reduction_weight
+    if rw is not None and (rw.shape[-1] > 8 or n_slots % rw.shape[-1] != 0):
+        raise ValueError(f"cvmm: reduction over {rw.shape[-1]} slots per output row is not supported (1..8, dividing {n_slots})")
+    out = CVMM.apply(x, keys, sel._route, slots_per_row, rw, _out_dtype(x))
     if sel.reduction_weight is None:
         return out.view(*sel.raw_sel.shape, keys.shape[-1])
     return out.view(*sel.reduction_weight.shape[:-1], keys.shape[-1])

@@ -145,3 +145,49 @@ def test_c1_shape_against_oracle(competition):
     if int((~agree).sum()) <= agree.numel() // 200:
         assert_close_rms(layer.keys.grad, ks.grad, 5e-2, "dkeys")
         assert_close_rms(layer.values.grad, vs.grad, 5e-2, "dvalues")
+
+
+def test_cvmm_moe_attention_call_patterns():
+    """The two extra selection layouts SwitchHead-style MoE attention feeds the same op
+    (layers/transformer/full_moe_relative_attention.py:453-458): per-head selections [T, heads, k] with
+    (a) one input row per token shared by heads x k slots (q/k/v projections) and (b) one input row per (token, head) with
+    the reduction weight flattened over (heads, k) (output projection).  Checked against the CPU oracle's cvmm."""
+    from competesmoe_b200.cvmm import cvmm, cvmm_prepare_sel2
+    torch.manual_seed(7)
+    T, heads, k, E, D, dh = 80, 4, 2, 6, 64, 32
+    sel = torch.stack([torch.stack([torch.randperm(E)[:k] for _ in range(heads)]) for _ in range(T)]).int()
+    w = torch.rand(T, heads, k)
+    ref_sel = op.prepare_sel2(sel)
+    # (a) q-style: x [T, D] -> [T, heads, k, dh] without reduction; every slot of a token reads the token's row
+    x = torch.randn(T, D)
+    wq = torch.randn(E, D, dh) / D ** 0.5
+    sa = op.Sel(ref_sel.raw_sel, ref_sel.sel, ref_sel.out_index // (heads * k), ref_sel.out_index, None)
+    ref_a = op.cvmm(x, sa, wq)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        s = cvmm_prepare_sel2(sel.to(DEV), n_experts=E)
+        s.sel_index = s.out_index // (heads * k)
+        got_a = cvmm(x.to(DEV), s, wq.to(DEV))
+    assert got_a.shape == ref_a.shape == (T, heads, k, dh)
+    assert_close_rms(got_a, ref_a, 3e-2, "q-style projection")
+    # (b) o-style: x [T, heads, dh] -> [T, D], weighted over heads x k
+    xo = torch.randn(T, heads, dh).requires_grad_(True)
+    wo = (torch.randn(E, dh, D) / dh ** 0.5).requires_grad_(True)
+    wr = w.clone().requires_grad_(True)
+    sb = op.Sel(ref_sel.raw_sel, ref_sel.sel, ref_sel.out_index // k, ref_sel.out_index, wr.flatten(-2))
+    ref_b = op.cvmm(xo, sb, wo)
+    dy = torch.randn(T, D)
+    (ref_b * dy).sum().backward()
+    xg = xo.detach().to(DEV).requires_grad_(True)
+    wg = wo.detach().to(DEV).requires_grad_(True)
+    wrg = w.to(DEV).requires_grad_(True)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        o_sel = cvmm_prepare_sel2(sel.to(DEV), wrg, n_experts=E).clone()
+        o_sel.sel_index = o_sel.out_index // o_sel.reduction_weight.shape[-1]
+        o_sel.reduction_weight = o_sel.reduction_weight.flatten(-2)
+        got_b = cvmm(xg, o_sel, wg)
+    assert got_b.shape == ref_b.shape == (T, D)
+    assert_close_rms(got_b, ref_b.detach(), 3e-2, "o-style projection")
+    (got_b.float() * dy.to(DEV)).sum().backward()
+    assert_close_rms(xg.grad, xo.grad, 4e-2, "dx")
+    assert_close_rms(wg.grad, wo.grad, 4e-2, "dW")
+    assert_close_rms(wrg.grad, wr.grad, 4e-2, "d reduction_weight")

@@ -188,3 +188,19 @@ def test_pretrain_sibling_oracle_matches_reference(name):
             torch.testing.assert_close(params[k].grad, g, **tol)
     if "expert_embeddings_after" in fx:
         torch.testing.assert_close(params["expert_embeddings"].detach(), fx["expert_embeddings_after"], **tol)
+
+
+def test_cvmm_oracle_moe_attention_layouts_match_einsum():
+    """Known-answer test of oracle cvmm for the selection layouts of MoE attention
+    (full_moe_relative_attention.py:453-458): per-head selections with re-divided sel_index / flattened reduction weight."""
+    torch.manual_seed(7)
+    T, heads, k, E, D, dh = 20, 4, 2, 6, 16, 8
+    sel = torch.stack([torch.stack([torch.randperm(E)[:k] for _ in range(heads)]) for _ in range(T)]).int()
+    w = torch.rand(T, heads, k)
+    rs = op.prepare_sel2(sel)
+    x, wq = torch.randn(T, D), torch.randn(E, D, dh)
+    a = op.cvmm(x, op.Sel(rs.raw_sel, rs.sel, rs.out_index // (heads * k), rs.out_index, None), wq)
+    torch.testing.assert_close(a, torch.einsum("td,thkdn->thkn", x, wq[sel.long()]), rtol=1e-5, atol=1e-5)
+    xo, wo = torch.randn(T, heads, dh), torch.randn(E, dh, D)
+    b = op.cvmm(xo, op.Sel(rs.raw_sel, rs.sel, rs.out_index // k, rs.out_index, w.flatten(-2)), wo)
+    torch.testing.assert_close(b, torch.einsum("thk,thd,thkdn->tn", w, xo, wo[sel.long()]), rtol=1e-5, atol=1e-5)
