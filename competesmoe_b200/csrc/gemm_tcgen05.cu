@@ -64,7 +64,10 @@ struct KParams {
   int kcat;           // ROWS + dense: C[rows, n] = sum_e A[e*a_expert_rows + rows, k] . B[e]  (the k loop runs over experts too)
   int dbg_mode;       // tuning experiments (CSMOE_GEMM_DBG): 1 = no TMA loads after the first pipeline fill, 2 = no MMAs
   int direct_epi;     // 1 = register-direct (row per thread) epilogue stores instead of the staged, coalesced ones
-  int tma_epi;        // staged epilogue only: 1 = the staged 32 x 32 groups leave through TMA stores (tensor maps tma_c / tma_p)
+  int tma_epi;        // 1 = 32 x 32 groups leave through TMA stores (tensor maps tma_c / tma_p); 2 = backward epilogue of the
+                      // pair kernel: the saved pre-activation arrives by TMA loads (tma_z) as well
+  int stages;         // pair kernel: operand stages in use (6, or 5 when the epilogue needs 8 KiB of staging per warp)
+  int stg_bytes;      // pair kernel: staging bytes per epilogue warp (4096 / 8192)
   unsigned long long* stats;  // debug (CSMOE_GEMM_STATS=1): per CTA {producer wait, mma wait full, mma wait tempty, epilogue, total, tiles}
 };
 
@@ -708,6 +711,87 @@ __device__ __forceinline__ void epilogue_tile_tma(const KParams& p, const Tile& 
   }
 }
 
+// Backward epilogues (dz = dh * act'(z), GLU: d gate | d up) with the saved pre-activation z arriving through TMA loads
+// into the warp's staging tile instead of per-thread global loads: z of group g+1 is in flight while group g is
+// computed, and the results leave through TMA stores.  Staging per warp (8 KiB): [0, 4 K) z (gate | up), [4 K, 8 K) the
+// two output slots.  `zbar` is this warp's mbarrier, `zphase` its parity.
+template <int BN>
+__device__ __forceinline__ void epilogue_tile_bwd_tma(const KParams& p, const Tile& ti, uint32_t t_row, bool has_acc, int row0,
+                                                      int half, int lane, uint32_t stg, const CUtensorMap* map_c,
+                                                      const CUtensorMap* map_z, uint32_t zbar, uint32_t& zphase,
+                                                      uint32_t& slot) {
+  constexpr int G = BN / 64;
+  const bool glu = p.epi == kEpiGluBwd;
+  const uint32_t zin = stg, outb = stg + 4096u;
+  const int colbase = ti.nb * BN + half * (BN / 2);
+  if (lane == 0 && colbase < p.n) {
+    ptx::mbar_arrive_expect_tx(zbar, glu ? 4096u : 2048u);
+    ptx::tma_load_3d(zin, map_z, zbar, colbase, row0, 0);
+    if (glu) ptx::tma_load_3d(zin + 2048u, map_z, zbar, p.glu_f + colbase, row0, 0);
+  }
+#pragma unroll 1
+  for (int g = 0; g < G; ++g) {
+    const int tcol = half * (BN / 2) + g * 32;
+    const int col0 = ti.nb * BN + tcol;
+    if (col0 >= p.n) break;
+    uint32_t v[32];
+    if (has_acc) ptx::tmem_ld_32x32b_x32(t_row + tcol, v);
+    ptx::mbar_wait(zbar, zphase);
+    zphase ^= 1u;
+    uint32_t zg[16], zu[16];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const uint4 a = lds128(stg_addr<64>(zin, lane, c));
+      zg[4 * c] = a.x, zg[4 * c + 1] = a.y, zg[4 * c + 2] = a.z, zg[4 * c + 3] = a.w;
+    }
+    if (glu) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const uint4 a = lds128(stg_addr<64>(zin + 2048u, lane, c));
+        zu[4 * c] = a.x, zu[4 * c + 1] = a.y, zu[4 * c + 2] = a.z, zu[4 * c + 3] = a.w;
+      }
+    }
+    __syncwarp();                                    // every lane has read z: the tile may be refilled
+    if (lane == 0 && g + 1 < G && col0 + 32 < p.n) {
+      ptx::mbar_arrive_expect_tx(zbar, glu ? 4096u : 2048u);
+      ptx::tma_load_3d(zin, map_z, zbar, col0 + 32, row0, 0);
+      if (glu) ptx::tma_load_3d(zin + 2048u, map_z, zbar, p.glu_f + col0 + 32, row0, 0);
+    }
+    if (has_acc) {
+      ptx::tmem_ld_wait_dep(v);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = 0u;
+    }
+    if (glu) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float2 z0 = unpack_bf16(zg[i]), z1 = unpack_bf16(zu[i]);
+        const float da = bf16_round(__uint_as_float(v[2 * i])), db = bf16_round(__uint_as_float(v[2 * i + 1]));
+        const float sa = bf16_round(act_apply(z0.x, CSMOE_ACT_SILU, true)), sb = bf16_round(act_apply(z0.y, CSMOE_ACT_SILU, true));
+        zu[i] = pack_bf16(da * sa, db * sb);                                                     // d up
+        zg[i] = pack_bf16(bf16_round(da * z1.x) * act_grad(z0.x, CSMOE_ACT_SILU, true),
+                          bf16_round(db * z1.y) * act_grad(z0.y, CSMOE_ACT_SILU, true));          // d gate
+      }
+      tma_store_packed<false>(outb, lane, zg, map_c, col0, row0, 0, slot);
+      tma_store_packed<false>(outb, lane, zu, map_c, p.glu_f + col0, row0, 0, slot);
+    } else {
+      float dh[32], z0[32];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float2 z = unpack_bf16(zg[i]);
+        z0[2 * i] = z.x, z0[2 * i + 1] = z.y;
+        dh[2 * i] = bf16_round(__uint_as_float(v[2 * i]));
+        dh[2 * i + 1] = bf16_round(__uint_as_float(v[2 * i + 1]));
+      }
+      act_grad_vec<32>(dh, z0, p.act, true);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) zg[i] = pack_bf16(dh[2 * i], dh[2 * i + 1]);
+      tma_store_packed<false>(outb, lane, zg, map_c, col0, row0, 0, slot);
+    }
+  }
+}
+
 template <int MODE, bool B_MN, int BN>
 __global__ void __launch_bounds__(kThreads, 1)
 grouped_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
@@ -970,7 +1054,7 @@ template <int MODE, bool B_MN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 grouped_gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                          const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ CUtensorMap tma_p,
-                         const KParams p) {
+                         const __grid_constant__ CUtensorMap tma_z, const KParams p) {
   constexpr int BN = 256;
   constexpr bool kAMn = (MODE == CSMOE_GEMM_REDUCE);
   constexpr bool kBMn = kAMn || B_MN;
@@ -979,13 +1063,15 @@ grouped_gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t stg_base = smem_base + kPairStages * kPairStageBytes;
-  const uint32_t bar_base = stg_base + kEpiWarps * kStageTileBytes;
+  const int n_stages = p.stages;
+  const uint32_t stg_base = smem_base + n_stages * kPairStageBytes;
+  const uint32_t bar_base = stg_base + kEpiWarps * p.stg_bytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kPairStages + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kPairStages + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kPairStages + kAccStages + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * kPairStages + 2 * kAccStages);
+  auto z_bar = [&](int w) { return bar_base + 8u * (2 * kPairStages + 2 * kAccStages + 2 + w); };
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
 
@@ -1009,6 +1095,7 @@ grouped_gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
       ptx::mbar_init(tfull_bar(a), 1);
       ptx::mbar_init(tempty_bar(a), 2 * kEpiWarps);
     }
+    for (int w = 0; w < kEpiWarps; ++w) ptx::mbar_init(z_bar(w), 1);
     ptx::fence_barrier_init();
   }
   if (warp == 2) {
@@ -1035,9 +1122,9 @@ grouped_gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
         if (!ti.valid) continue;
         for (int kb = 0; kb < ti.nkb; ++kb) {
           timed_wait(empty_bar(stage), phase ^ 1u, st_on, w_empty);
-          if ((p.dbg_mode & 1) && dbg_filled >= kPairStages) {
+          if ((p.dbg_mode & 1) && dbg_filled >= n_stages) {
             if (leader) ptx::mbar_arrive(full_bar(stage));
-            if (++stage == kPairStages) {
+            if (++stage == n_stages) {
               stage = 0;
               phase ^= 1u;
             }
@@ -1075,7 +1162,7 @@ grouped_gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
               ptx::tma_load_2d_cg2(sb + j * kSubTileBytes, &tma_b, fb, ti.nb * BN + rank * 128 + j * 64,
                                    ti.b_row + kb * kBK);
           }
-          if (++stage == kPairStages) {
+          if (++stage == n_stages) {
             stage = 0;
             phase ^= 1u;
           }
@@ -1109,7 +1196,7 @@ grouped_gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
             if (!(p.dbg_mode & 2)) ptx::umma_f16_cg2(d_tmem, adesc, bdesc, kIdesc, (kb | k) != 0 ? 1u : 0u);
           }
           ptx::umma_commit_cg2_mc(empty_bar(stage), 0x3);
-          if (++stage == kPairStages) {
+          if (++stage == n_stages) {
             stage = 0;
             phase ^= 1u;
           }
@@ -1132,7 +1219,7 @@ grouped_gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
     const int half = (warp - 2) >> 2;
     const int row_in_tile = quad * 32 + lane;
     unsigned long long epi_cycles = 0;
-    uint32_t tma_slot = 0;
+    uint32_t tma_slot = 0, z_phase = 0;
     uint32_t acc = 0, acc_phase = 0;
     for (long long t = cluster_id; t < p.total_tiles; t += num_clusters) {
       const Tile ti = decode_tile_pair<MODE>(p, t, rank);
@@ -1145,13 +1232,16 @@ grouped_gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
       const long long out_row = static_cast<long long>(ti.mb) * 256 + rank * kBM + row_in_tile;
       const uint32_t t_row = tmem_base + acc * BN + (static_cast<uint32_t>(quad * 32) << 16);
       const long long e0 = st_on ? clock64() : 0;
-      if (p.tma_epi)
+      if (MODE == CSMOE_GEMM_ROWS && p.tma_epi == 2)
+        epilogue_tile_bwd_tma<BN>(p, ti, t_row, has_acc, ti.mb * 256 + rank * kBM + quad * 32, half, lane,
+                                  stg_base + (warp - 2) * p.stg_bytes, &tma_c, &tma_z, z_bar(warp - 2), z_phase, tma_slot);
+      else if (p.tma_epi)
         epilogue_tile_tma<MODE, BN>(p, ti, t_row, has_acc, ti.mb * 256 + rank * kBM + quad * 32, half, lane,
-                                    stg_base + (warp - 2) * kStageTileBytes, &tma_c, &tma_p, tma_slot);
+                                    stg_base + (warp - 2) * p.stg_bytes, &tma_c, &tma_p, tma_slot);
       else if (p.direct_epi)
         epilogue_tile<MODE, BN>(p, ti, t_row, has_acc, out_row, half);
       else
-        epilogue_tile_staged<MODE, BN>(p, ti, t_row, has_acc, out_row - lane, half, lane, stg_base + (warp - 2) * kStageTileBytes);
+        epilogue_tile_staged<MODE, BN>(p, ti, t_row, has_acc, out_row - lane, half, lane, stg_base + (warp - 2) * p.stg_bytes);
       if (has_acc) {
         ptx::tc_fence_before();
         __syncwarp();
@@ -1484,7 +1574,7 @@ int encode_out_map(CUtensorMap* map, const void* base, bool fp32, long long cols
 }
 
 struct Maps {
-  CUtensorMap a, b, c, p;
+  CUtensorMap a, b, c, p, z;
 };
 
 template <int MODE, bool B_MN, int BN>
@@ -1504,14 +1594,16 @@ int launch(const Maps& m, const KParams& kp, int grid, cudaStream_t stream) {
 
 template <int MODE, bool B_MN>
 int launch_pair(const Maps& m, const KParams& kp, int clusters, cudaStream_t stream) {
-  constexpr int kSmem = kPairStages * kPairStageBytes + kEpiWarps * kStageTileBytes + 1024 + 256;
+  // 6 stages + 4 KiB of staging per epilogue warp, or 5 stages + 8 KiB (TMA-fed backward epilogue)
+  constexpr int kSmem = (kPairStages - 1) * kPairStageBytes + kEpiWarps * 2 * kStageTileBytes + 1024 + 256;
+  static_assert(kSmem >= kPairStages * kPairStageBytes + kEpiWarps * kStageTileBytes + 1024 + 256, "pair kernel smem");
   auto kern = grouped_gemm_pair_kernel<MODE, B_MN>;
   static bool configured = false;
   if (!configured) {
     CSMOE_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     configured = true;
   }
-  kern<<<2 * clusters, kThreads, kSmem, stream>>>(m.a, m.b, m.c, m.p, kp);
+  kern<<<2 * clusters, kThreads, kSmem, stream>>>(m.a, m.b, m.c, m.p, m.z, kp);
   CSMOE_CHECK_LAUNCH();
   return CSMOE_OK;
 }
@@ -1746,6 +1838,14 @@ extern "C" int csmoe_grouped_gemm(const csmoe_gemm_args* a, void* stream_) {
     kp.direct_epi = 0;
     kp.tma_epi = 1;
   }
+  kp.stages = kPairStages;
+  kp.stg_bytes = kStageTileBytes;
+  // backward epilogues on the pair kernel: saved pre-activation through TMA loads (CSMOE_GEMM_BWD_TMA=0 switches it off)
+  static const bool bwd_tma = []() { const char* v = getenv("CSMOE_GEMM_BWD_TMA"); return v == nullptr || v[0] != '0'; }();
+  const bool bwd_tma_legal = bwd_tma && act_bwd && pair && a->c != nullptr && a->c_rows == nullptr &&
+                             (kp.epi != kEpiGluBwd || kp.glu_f % 32 == 0) &&
+                             reinterpret_cast<uintptr_t>(a->aux) % 16 == 0 && epilogue_override() != 1 &&
+                             epilogue_override() != 2;
 
   Maps maps{};
   CUtensorMap& ma = maps.a;
@@ -1796,7 +1896,17 @@ extern "C" int csmoe_grouped_gemm(const csmoe_gemm_args* a, void* stream_) {
     }
   }
   if (kp.total_tiles == 0) return CSMOE_OK;
-  if (kp.tma_epi) {
+  if (bwd_tma_legal) {
+    // (wide launches never carry a backward epilogue: see the dispatch rule below)
+    const long long c_rows_total = static_cast<long long>(kp.num_m_blocks) * kBM;
+    const long long cols = kp.epi == kEpiGluBwd ? 2LL * a->n : a->n;
+    if ((rc = encode_out_map(&maps.c, a->c, false, cols, c_rows_total, 1, a->ldc, 0)) != CSMOE_OK) return rc;
+    if ((rc = encode_out_map(&maps.z, a->aux, false, cols, c_rows_total, 1, a->ldaux, 0)) != CSMOE_OK) return rc;
+    kp.tma_epi = 2;
+    kp.direct_epi = 0;
+    kp.stages = kPairStages - 1;
+    kp.stg_bytes = 2 * kStageTileBytes;
+  } else if (kp.tma_epi) {
     const bool f32 = a->c_dtype == CSMOE_F32;
     if (a->mode == CSMOE_GEMM_ROWS) {
       const long long c_rows_total = static_cast<long long>(kp.num_m_blocks) * kBM;
@@ -1821,7 +1931,7 @@ extern "C" int csmoe_grouped_gemm(const csmoe_gemm_args* a, void* stream_) {
     const long long wide_tiles = static_cast<long long>(kp.num_m_pairs) * ((a->n + 511) / 512) * E;
     const bool long_k = a->mode == CSMOE_GEMM_ROWS ? k_loop >= 4096 || (wm & 4)
                                                    : (wm & 8) != 0 || wide_tiles >= 16LL * (num_sms() / 2);
-    const bool wide = n_grid >= 512 && (n_grid % 512 == 0 || n_grid >= 2048) && long_k &&
+    const bool wide = n_grid >= 512 && (n_grid % 512 == 0 || n_grid >= 2048) && long_k && kp.tma_epi != 2 &&
                       (wm & (a->mode == CSMOE_GEMM_ROWS ? 1 : 2)) != 0;
     if (wide) kp.num_n_blocks = glu_fwd ? static_cast<int>((n_grid + 255) / 256) : static_cast<int>((a->n + 511) / 512);
     const long long per = static_cast<long long>(kp.num_m_pairs) * kp.num_n_blocks;

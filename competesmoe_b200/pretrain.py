@@ -208,6 +208,74 @@ class MoE(LoggingLayer, RegularizedLayer, OncePerIterLayer, torch.nn.Module):
         g = self._ep.group
         return gather_experts(self.keys, g), gather_experts(self.bias, g), gather_experts(self.values, g)
 
+    # ---- CUDA graphs (no counterpart in the reference, whose cvmm path re-tunes and syncs on the host)
+    _graphs = None
+    _graphable = True            # False for layers that modify a parameter in place inside forward (xmoe, smoe_perturbed)
+    _graph_skip = ()             # parameters the forward never reads (they cannot be inputs of the captured backward)
+
+    def enable_cuda_graphs(self, enabled: bool = True):
+        """Opt in: training-mode calls with a CUDA input that requires grad are replayed from captured CUDA graphs (one
+        forward + one backward graph per (step kind, shape, dtype, autocast state); torch.cuda.make_graphed_callables
+        behind the unchanged `layer(x, id_layer=...)` call).  At the sigma-MoE shapes (H = 128) the ~80 launches of a step
+        take longer to issue from Python than to run, so this is worth 1.5-4x there.  Regularisers still arrive through
+        `add_reg` under their usual names.  Eval / no-grad / expert-parallel / test_only calls take the normal path."""
+        if enabled and self._graphs is None:
+            self._graphs = {}
+            self._eager_forward = self.forward
+            self.forward = self._graph_forward
+        elif not enabled and self._graphs is not None:
+            self._graphs = None
+            self.forward = self._eager_forward
+        return self
+
+    def _graph_forward(self, x, *args, **kwargs):
+        eligible = (self._graphable and self._ep is None and self.training and torch.is_tensor(x) and x.is_cuda
+                    and x.requires_grad and torch.is_grad_enabled() and not getattr(self.args, "test_only", False)
+                    and not torch.cuda.is_current_stream_capturing() and not args
+                    and set(kwargs) <= {"id_layer"})
+        if not eligible:
+            return self._eager_forward(x, *args, **kwargs)
+        autocast = torch.is_autocast_enabled()
+        adt = torch.get_autocast_dtype("cuda")
+        id_layer = kwargs.get("id_layer")
+        probe = getattr(self, "_is_competition_step", None)
+        branch = bool(probe(x, id_layer)) if probe is not None else False
+        params = tuple(p for n, p in self.named_parameters() if p.requires_grad and n not in self._graph_skip)
+        reg_on = self.reg_enabled
+        key = (branch, id_layer, tuple(x.shape), x.dtype, autocast, adt, reg_on,
+               tuple(p.data_ptr() for p in params))
+        entry = self._graphs.get(key)
+        if entry is None:
+            names = []
+            keep = (self.layer, getattr(self, "nb_diver", 0))
+
+            def fn(xx, *_params):
+                collected = []
+                self.add_reg = (lambda loss_fn, name="reg": collected.append((name, loss_fn()))) if reg_on else \
+                    (lambda loss_fn, name="reg": None)
+                try:
+                    with torch.autocast("cuda", dtype=adt, enabled=autocast, cache_enabled=False):
+                        out = self._eager_forward(xx, **kwargs)
+                finally:
+                    del self.add_reg
+                names[:] = [n for n, _ in collected]
+                return (out,) + tuple(t for _, t in collected)
+
+            sample = x.detach().clone().requires_grad_(True)
+            with torch.autocast("cuda", dtype=adt, enabled=autocast, cache_enabled=False):
+                graphed = torch.cuda.make_graphed_callables(fn, (sample,) + params)
+            self.layer, self.nb_diver = keep
+            entry = (graphed, list(names), self.last_routing)
+            self._graphs[key] = entry
+        graphed, names, routing = entry
+        res = graphed(x, *params)
+        for name, t in zip(names, res[1:]):
+            self.add_reg(lambda t=t: t, name)
+        self.last_routing = routing          # static tensors of this graph, refreshed by the replay
+        self.layer += 1
+        self.was_training = self.training
+        return res[0]
+
     # ---- bookkeeping hooks
     def pre_train_forward(self):
         self.total_selections, self.total_gate_softmax, self.total_gate_logits = [], [], []

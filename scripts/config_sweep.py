@@ -24,6 +24,7 @@ sys.path.insert(0, str(ROOT / "tests"))
 from helpers import MLPExpert  # noqa: E402
 
 PEAK_TF, PEAK_GBS = 1607.8, 6554.9   # MEASURED_PEAKS.json (burst bf16, HBM copy)
+GRAPHS = False                        # --graphs: the layers' opt-in CUDA-graph mode (single GPU)
 
 
 def pretrain_args():
@@ -76,6 +77,8 @@ def build(case: Case, dev, ep):
         layer.step_warm = 0
         if ep is not None:
             layer.enable_expert_parallel(ep, max_tokens=case.T)
+        elif GRAPHS:
+            layer.enable_cuda_graphs()
 
         def set_branch(comp):
             layer.prob_flips_final = {0: torch.full((8,), bool(comp), device=dev)}
@@ -101,6 +104,8 @@ def build(case: Case, dev, ep):
         layer.train()
         if ep is not None:
             layer.enable_expert_parallel(ep, max_tokens=case.T)
+        elif GRAPHS and hasattr(layer, "enable_cuda_graphs"):
+            layer.enable_cuda_graphs()
 
         def set_branch(comp):
             if case.moe_name == "competesmoe":
@@ -208,7 +213,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--only", default="")
     ap.add_argument("--profile", action="store_true", help="print the per-kernel timeline (torch.profiler) of each selected case")
+    ap.add_argument("--graphs", action="store_true", help="enable the layers' CUDA-graph mode (single-GPU cases)")
     a = ap.parse_args()
+    global GRAPHS
+    GRAPHS = a.graphs
     world, rank, local = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", "1"), ("RANK", "0"), ("LOCAL_RANK", "0")))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)

@@ -191,3 +191,37 @@ def test_cvmm_moe_attention_call_patterns():
     assert_close_rms(xg.grad, xo.grad, 4e-2, "dx")
     assert_close_rms(wg.grad, wo.grad, 4e-2, "dW")
     assert_close_rms(wrg.grad, wr.grad, 4e-2, "d reduction_weight")
+
+
+@pytest.mark.parametrize("name", ["pt_router_f32", "pt_comp_f32", "pt_comp_hybrid_bal_f32"])
+def test_pretrain_layer_cuda_graph_mode_matches_eager(name):
+    """layer.enable_cuda_graphs(): the unchanged `layer(x, id_layer=0)` call under autocast, replayed from captured
+    graphs, gives the eager call's output, regularisers, routing and gradients bit for bit -- on the capture inputs and
+    on fresh ones."""
+    fx = load_golden(name)
+    eager, _ = build_layer(fx)
+    graphed, _ = build_layer(fx)
+    graphed.enable_cuda_graphs()
+    g = torch.Generator().manual_seed(11)
+    for trial in range(3):
+        x_cpu = fx["x"] if trial == 0 else torch.randn(fx["x"].shape, generator=g)
+        dy = (fx["dy"] if trial == 0 else torch.randn(fx["dy"].shape, generator=g)).to(DEV)
+        res = []
+        for layer in (eager, graphed):
+            for p in layer.parameters():
+                p.grad = None
+            x = x_cpu.to(DEV).requires_grad_(True)
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                out = layer(x, id_layer=0)
+                regs = layer.get_reg_loss()
+            ((out.float() * dy).sum() + sum(regs.values())).backward()
+            res.append((out.clone(), {k: v.detach().clone() for k, v in regs.items()}, x.grad.clone(),
+                        layer.last_routing[0].clone(), {n: p.grad.clone() for n, p in layer.named_parameters()}))
+        (o0, r0, dx0, s0, g0), (o1, r1, dx1, s1, g1) = res
+        assert torch.equal(o0, o1) and torch.equal(dx0, dx1) and torch.equal(s0, s1)
+        assert set(r0) == set(r1) and all(torch.equal(r0[k], r1[k]) for k in r0), (r0, r1)
+        assert set(g0) == set(g1) and all(torch.equal(g0[k], g1[k]) for k in g0)
+    assert len(graphed._graphs) == 1 and graphed.layer == eager.layer
+    graphed.eval()
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        assert graphed(fx["x"].to(DEV), id_layer=0).shape == fx["out"].shape

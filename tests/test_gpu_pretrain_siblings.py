@@ -71,3 +71,46 @@ def test_pretrain_sibling_matches_reference_golden(name):
                 assert g is None or float(g.abs().max()) == 0.0, k
             else:
                 assert_close_rms(g, pr[k].grad, 4e-2, f"d{k}")
+
+
+@pytest.mark.parametrize("name", ["ptsib_smoe_f32", "ptsib_deepseekv3_f32", "ptsib_xmoe_f32"])
+def test_pretrain_sibling_cuda_graph_mode_matches_eager(name):
+    """enable_cuda_graphs() on the sibling routers: bit-identical to the eager call (xmoe rescales a parameter in place
+    inside forward, is marked not graphable and must silently take the eager path)."""
+    import competesmoe_b200.pretrain_siblings  # noqa: F401
+    from competesmoe_b200.pretrain import get_moe
+    fx = load_golden(name)
+    m = fx["meta"]
+    args = SimpleNamespace(**m["args"])
+    layers = []
+    for graphs in (False, True):
+        layer = get_moe(m["moe_name"])(m["D"], m["E"], m["H"], n_heads=m["K"], args=args, activation=F.relu,
+                                       selection_mode="gate", log_interval=None)
+        with torch.no_grad():
+            for k, v in fx["params"].items():
+                getattr(layer, k).copy_(v)
+        layer = layer.to(DEV)
+        layer.train()
+        layer.regularization_present = True
+        if graphs:
+            layer.enable_cuda_graphs()
+        layers.append(layer)
+    g = torch.Generator().manual_seed(5)
+    for trial in range(2):
+        x_cpu = fx["x"] if trial == 0 else torch.randn(fx["x"].shape, generator=g)
+        res = []
+        for layer in layers:
+            for p in layer.parameters():
+                p.grad = None
+            x = x_cpu.to(DEV).requires_grad_(True)
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                out = layer(x)
+                regs = layer.get_reg_loss()
+            ((out.float() * fx["dy"].to(DEV)).sum() + sum(regs.values())).backward()
+            res.append((out.clone(), {k: v.detach().clone() for k, v in regs.items()}, x.grad.clone(),
+                        {n: p.grad.clone() for n, p in layer.named_parameters() if p.grad is not None}))
+        (o0, r0, dx0, g0), (o1, r1, dx1, g1) = res
+        assert torch.equal(o0, o1) and torch.equal(dx0, dx1)
+        assert set(r0) == set(r1) and all(torch.equal(r0[k], r1[k]) for k in r0)
+        assert set(g0) == set(g1) and all(torch.equal(g0[k], g1[k]) for k in g0)
+    assert len(layers[1]._graphs) == (0 if "xmoe" in name else 1)
