@@ -55,6 +55,18 @@ def bind_pretrain(register_module, moe_module, names=("competesmoe_b200",), over
     return _bind(register_module.MOE_REGISTRY, CompeteSMoE, moe_module.MoE, names, overwrite)
 
 
+def bind_pretrain_siblings(register_module, moe_module, suffix: str = "_b200", overwrite: bool = False) -> Dict[str, type]:
+    """The pretrain-plugin sibling routers (smoe, smoe_sigmoid, xmoe, smoe_perturbed, deepseekv2, deepseekv3;
+    moe_pretrain_model/layers/moe/*.py) under `<name><suffix>`; `suffix="", overwrite=True` replaces them in place."""
+    from . import pretrain_siblings
+    from .pretrain import MOE_REGISTRY as ours
+    out = {}
+    for name in ("smoe", "smoe_sigmoid", "xmoe", "smoe_perturbed", "deepseekv2", "deepseekv3"):
+        out[name] = _bind(register_module.MOE_REGISTRY, ours[name], moe_module.MoE, (name + suffix,), overwrite)
+    del pretrain_siblings
+    return out
+
+
 def bind_cvmm(layers_module) -> None:
     """Replace the Triton op at the package level (moe_pretrain_model/layers/__init__.py:2 re-exports it and the
     11 call sites import `cvmm, cvmm_prepare_sel, cvmm_prepare_sel2, CVMMSel` from there)."""

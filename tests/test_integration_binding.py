@@ -66,6 +66,9 @@ def test_multimodal_binding_registers_and_matches_checkpoint_layout():
     assert ours.current_steps == 3 and hasattr(ours, "total_steps")
 
 
+_CVMM_MOD = None
+
+
 def _pretrain_shim():
     R = str(REF / "moe_pretrain_model")
     sys.path.insert(0, R)
@@ -78,7 +81,12 @@ def _pretrain_shim():
 
     saved = {k: sys.modules.get(k) for k in ("layers", "layers.moe", "framework")}
     L, LM, Fw = stub("layers", R + "/layers"), stub("layers.moe", R + "/layers/moe"), stub("framework", R + "/framework")
-    cv = importlib.import_module("layers.cvmm")
+    global _CVMM_MOD
+    if _CVMM_MOD is None:          # layers/cvmm.py defines a torch.library op: it can be imported once per process
+        _CVMM_MOD = importlib.import_module("layers.cvmm")
+    else:
+        sys.modules["layers.cvmm"] = _CVMM_MOD
+    cv = _CVMM_MOD
     L.cvmm, L.cvmm_prepare_sel = cv.cvmm, cv.cvmm_prepare_sel
     Fw.utils = importlib.import_module("framework.utils")
     Fw.layers = importlib.import_module("framework.layers")
@@ -170,3 +178,39 @@ def test_sibling_routers_bind_and_match_reference_state_dicts():
         gate_key = "expert_embeddings" if name in ("xmoe", "smoe_perturbed") else "gate.weight"
         assert torch.equal(sd_o[gate_key], sd_t[gate_key]), f"{name}: seeded gate init differs"
         ours.load_state_dict(sd_t)
+
+
+def test_pretrain_sibling_routers_bind_and_match_reference_state_dicts(tmp_path, monkeypatch):
+    """competesmoe_b200.integrate.bind_pretrain_siblings: every pretrain-plugin sibling is a subclass of the reference's
+    MoE, is found through the reference's get_moe, and has the reference class's state_dict keys and shapes."""
+    monkeypatch.chdir(tmp_path)
+    try:
+        L, base, reg, saved, R = _pretrain_shim()
+        for mod in ("smoe", "smoeut_norm", "xmoe", "smoe_perturbed", "deepseekv2", "deepseekv3"):
+            importlib.import_module("layers.moe." + mod)
+    except Exception as e:  # pragma: no cover - the reference tree changed
+        pytest.skip(f"reference import shim failed: {e}")
+    try:
+        from competesmoe_b200.integrate import bind_pretrain_siblings
+        bound = bind_pretrain_siblings(reg, base, suffix="_b200", overwrite=True)
+        ns = SimpleNamespace(balance_loss_coef=0.01, test_only=False)
+        kw = dict(n_heads=2, args=ns, activation=F.relu, selection_mode="gate", log_interval=None)
+        for name in ("smoe", "smoe_sigmoid", "xmoe", "smoe_perturbed", "deepseekv2", "deepseekv3"):
+            cls = reg.get_moe(name + "_b200")
+            assert cls is bound[name] and issubclass(cls, base.MoE)
+            ours = cls(64, 8, 16, **kw)
+            with contextlib.redirect_stdout(io.StringIO()):
+                theirs = reg.get_moe(name)(64, 8, 16, **kw)
+            sd_o, sd_t = ours.state_dict(), theirs.state_dict()
+            assert sorted(sd_o) == sorted(sd_t), (name, sorted(set(sd_o) ^ set(sd_t)))
+            assert all(sd_o[k].shape == sd_t[k].shape for k in sd_o), name
+            ours.load_state_dict(sd_t, strict=True)
+    finally:
+        sys.path.remove(R)
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+        for k in [k for k in sys.modules if k.startswith(("layers.", "framework."))]:
+            sys.modules.pop(k, None)
