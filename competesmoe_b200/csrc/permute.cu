@@ -28,10 +28,15 @@ gather_rows_kernel(const T* __restrict__ src, int D, int K, const int32_t* __res
     }
     const T* s = src + static_cast<long long>(slot / K) * D;
     if (slot_w == nullptr) {
-      for (int c = lane * 8; c < D; c += 256) {
-        float v[8];
-        load8(s + c, v);
-        store8(d + c, v);
+      // four 16-byte loads per lane in flight before the first store (one at a time left the copy latency bound)
+      for (int c0 = lane * 8; c0 < D; c0 += 1024) {
+        float v[4][8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (c0 + i * 256 < D) load8(s + c0 + i * 256, v[i]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (c0 + i * 256 < D) store8(d + c0 + i * 256, v[i]);
       }
     } else {
       const float w = slot_w[slot];

@@ -18,4 +18,8 @@ ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $out/
 python bench.py --steps 2 --warmup 3 > $out/${tag}_plain2.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:grouped_gemm -s 30 -c 6 -o $out/${tag}_gemm_full \
     python bench.py --steps 2 --warmup 3 > $out/${tag}_ncu2.log 2>&1
+python bench.py --steps 2 --warmup 3 > $out/${tag}_plain3.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
+    -k regex:'gather_rows|combine|scatter_reduce|act_bwd|router|route_|compete|affinity|diversity' -c 300 --csv \
+    --log-file $out/${tag}_hbm.csv python bench.py --steps 2 --warmup 3 > $out/${tag}_ncu3.log 2>&1
 ls -la $out | tail -20

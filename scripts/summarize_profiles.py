@@ -108,6 +108,47 @@ def full(tag: str, cmd: str, pattern: str):
     print(f"wrote profiles/{tag}_gemm_ncu_full.md ({len(data)} launches)")
 
 
+def hbm(tag: str, cmd: str):
+    """Third ncu pass of gpu_round.sh: DRAM byte counters of the bandwidth-bound kernels (permute, combine, activation
+    backward, router) inside the bench step -> profiles/<tag>_hbm_ncu.md (achieved GB/s = DRAM bytes / kernel time)."""
+    path = OUT / f"{tag}_hbm.csv"
+    if not path.exists():
+        print("no", path)
+        return
+    text = path.read_text()
+    rows = list(csv.DictReader(io.StringIO(text[text.find('"ID"'):])))
+    per = defaultdict(dict)
+    for r in rows:
+        v = float(r["Metric Value"].replace(",", ""))
+        u = (r.get("Metric Unit") or "").lower()
+        scale = {"gbyte": 1e9, "mbyte": 1e6, "kbyte": 1e3, "byte": 1.0, "usecond": 1e-6, "us": 1e-6, "nsecond": 1e-9,
+                 "ns": 1e-9, "msecond": 1e-3, "ms": 1e-3, "%": 1.0}.get(u, 1.0)
+        per[(r["ID"], short(r["Kernel Name"]))][r["Metric Name"]] = v * scale
+    agg = defaultdict(lambda: [0.0, 0.0, 0.0, 0])
+    for (_, k), m in per.items():
+        a = agg[k]
+        a[0] += m.get("gpu__time_duration.sum", 0.0)
+        a[1] += m.get("dram__bytes_read.sum", 0.0)
+        a[2] += m.get("dram__bytes_write.sum", 0.0)
+        a[3] += 1
+    lines = [f"# {tag} -- DRAM traffic of the bandwidth-bound kernels inside the bench step (ncu)", "",
+             "Command (B200, after the same command exited 0 without ncu):", "",
+             f"    ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none "
+             f"-k regex:'gather_rows|combine|scatter_reduce|act_bwd|router|route_|compete|affinity|diversity' --csv "
+             f"--log-file gpurun_out/{tag}_hbm.csv {cmd}", "",
+             "Per-launch averages; GB/s = (DRAM read + write) / kernel time, against the measured copy bandwidth 6555 GB/s "
+             "(cold-cache, serialised launches: inside the step the producer's output is partly L2 resident, so DRAM bytes can "
+             "be below the algorithmic bytes).", "",
+             "| kernel | launches | us / launch | DRAM read MB | DRAM write MB | GB/s | % of 6555 |", "|---|---:|---:|---:|---:|---:|---:|"]
+    for k, (t, rd, wr, n) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
+        if t <= 0:
+            continue
+        gbs = (rd + wr) / t / 1e9
+        lines.append(f"| `{k[:70]}` | {n} | {1e6 * t / n:.1f} | {rd / n / 1e6:.1f} | {wr / n / 1e6:.1f} | {gbs:.0f} | {100 * gbs / 6554.9:.1f} |")
+    (PROF / f"{tag}_hbm_ncu.md").write_text("\n".join(lines) + "\n")
+    print(f"wrote profiles/{tag}_hbm_ncu.md ({len(per)} launches)")
+
+
 if __name__ == "__main__":
     tag = sys.argv[1]
     pattern = sys.argv[2] if len(sys.argv) > 2 else "grouped_gemm"
@@ -115,3 +156,4 @@ if __name__ == "__main__":
     PROF.mkdir(exist_ok=True)
     launches(tag, cmd)
     full(tag, cmd, pattern)
+    hbm(tag, cmd)
