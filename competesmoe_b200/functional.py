@@ -130,6 +130,8 @@ class SparseFFNFn(Function):
         ctx.x_dtype = x.dtype
         ctx.has_b = (b1 is not None, b2 is not None)
         ctx.save_for_backward(xp, z, h, y, w, w1, w2)
+        # fp32 master weights (pretrain under autocast): keep the bf16 copies of this step for the backward pass
+        ctx.wb = (w1b if w1b is not w1 else None, w2b if w2b is not w2 else None)
         return out
 
     @staticmethod
@@ -138,7 +140,8 @@ class SparseFFNFn(Function):
         xp, z, h, y, w, w1, w2 = ctx.saved_tensors
         route, spec = ctx.route, ctx.spec
         T, K, E = route.n_slots // route.top_k, route.top_k, route.num_experts
-        w1b, w2b = _bf16(w1), _bf16(w2)
+        w1b = ctx.wb[0] if ctx.wb[0] is not None else _bf16(w1)
+        w2b = ctx.wb[1] if ctx.wb[1] is not None else _bf16(w2)
         dout = _bf16(dout.contiguous())
         need = ctx.needs_input_grad
         dw = ops.combine_bwd_w(y, dout, route.slot_to_row, T, K) if need[1] else None

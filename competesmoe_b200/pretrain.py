@@ -311,13 +311,27 @@ class MoE(LoggingLayer, RegularizedLayer, OncePerIterLayer, torch.nn.Module):
             return torch.get_autocast_dtype('cuda')
         return x.dtype
 
+    _cast_memo = None
+
+    def _cast(self, x2: torch.Tensor, cdt: torch.dtype) -> torch.Tensor:
+        """x in the compute dtype, cast once per forward: the gate and the expert path (and the dense competition pass)
+        share one copy and one autograd node instead of a cast each (autocast would cast per consumer too)."""
+        if x2.dtype == cdt:
+            return x2
+        m = self._cast_memo
+        if m is not None and m[0] is x2 and m[1] == cdt:
+            return m[2]
+        y = x2.to(cdt)
+        self._cast_memo = (x2, cdt, y)
+        return y
+
     def _spec(self, cdt: torch.dtype) -> FFNSpec:
         # CVMM.forward reduces with `reduction_weight.type_as(res) @ res` (cvmm.py:481-483): weight rounded to the op
         # dtype, fp32 accumulation, one rounding at the end.
         return FFNSpec(act=self._act_code, kn_layout=True, round_each=False, round_w=cdt == torch.bfloat16)
 
     def compute_gate(self, x2: torch.Tensor, cdt: torch.dtype):
-        return GateFn.apply(x2.to(cdt), self.w_gate, self.num_selected, 1, False)[:4]
+        return GateFn.apply(self._cast(x2, cdt), self.w_gate, self.num_selected, 1, False)[:4]
 
     def _log_relu_pass_rate(self, out):
         pass  # the hidden activations never leave the fused kernels; the reference logs this only every log_interval
@@ -325,9 +339,9 @@ class MoE(LoggingLayer, RegularizedLayer, OncePerIterLayer, torch.nn.Module):
     def compute_moe_main(self, x2, selected, weights, cdt):
         if self._ep is not None:
             from .ep import EPSparseFFNFn
-            return EPSparseFFNFn.apply(x2.to(cdt), weights, selected, self.keys, self.bias, self.values, None,
+            return EPSparseFFNFn.apply(self._cast(x2, cdt), weights, selected, self.keys, self.bias, self.values, None,
                                        self._spec(cdt), self._ep)
-        return SparseFFNFn.apply(x2.to(cdt), weights, selected, self.keys, self.bias, self.values, None, self._spec(cdt))
+        return SparseFFNFn.apply(self._cast(x2, cdt), weights, selected, self.keys, self.bias, self.values, None, self._spec(cdt))
 
     def forward(self, x, return_id_experts=False, return_full=True, *args, **kwargs):
         """Plain sigma-MoE forward (moe.py:418-449)."""
@@ -424,8 +438,8 @@ class CompeteSMoE(MoE):
             return GateFn.apply(F.normalize(x2.float(), p=2.0, dim=-1).to(cdt), F.normalize(self.w_gate, p=2.0, dim=-1),
                                 self.num_selected, 1, False)[:4]
         if getattr(a, "is_norm_weight", False):
-            return GateFn.apply(x2.to(cdt), F.normalize(self.w_gate, p=2.0, dim=-1), self.num_selected, 1, False)[:4]
-        return GateFn.apply(x2.to(cdt), self.w_gate, self.num_selected, 1, False)[:4]
+            return GateFn.apply(self._cast(x2, cdt), F.normalize(self.w_gate, p=2.0, dim=-1), self.num_selected, 1, False)[:4]
+        return GateFn.apply(self._cast(x2, cdt), self.w_gate, self.num_selected, 1, False)[:4]
 
     def router_policy(self, x2, cdt, x_dtype):
         """competesmoe.py:465-490."""
@@ -463,7 +477,7 @@ class CompeteSMoE(MoE):
         if is_comp:
             spec = self._spec(cdt)
             keys, bias, values = self._all_expert_weights()
-            y_all, score_sums = DenseFFNFn.apply(x2.to(cdt), keys, bias, values, None, spec,
+            y_all, score_sums = DenseFFNFn.apply(self._cast(x2, cdt), keys, bias, values, None, spec,
                                                  x.dtype == torch.bfloat16)          # [E * t_pad, Dv]
             t_pad = y_all.shape[0] // E
             aff, aff_w, aff_idx, out, diver = CompeteTailFn.apply(y_all, E, T, t_pad, K, False, x.dtype, spec, score_sums)

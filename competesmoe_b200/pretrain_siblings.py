@@ -92,7 +92,7 @@ class _CosineGate(_SiblingBase):
         cdt = self._compute_dtype(x)
         K = self.num_selected
         x2 = x.reshape(-1, x.shape[-1])
-        reduced = GateFn.apply(x2.to(cdt), self.expert_sel, 1, 1, False)[0]          # D -> E/2 projection in the router kernel
+        reduced = GateFn.apply(self._cast(x2, cdt), self.expert_sel, 1, 1, False)[0]          # D -> E/2 projection in the router kernel
         if self.sel_bias is not None:
             reduced = reduced + self.sel_bias.to(reduced.dtype)
         with torch.no_grad():
@@ -139,7 +139,7 @@ class _SharedExpert(_SiblingBase):
         self.bias_shared = torch.nn.Parameter(torch.zeros(1, hs)) if bias else None
 
     def _shared_out(self, x2, cdt):
-        y = DenseFFNFn.apply(x2.to(cdt), self.keys_shared, self.bias_shared, self.values_shared, None, self._spec(cdt))
+        y = DenseFFNFn.apply(self._cast(x2, cdt), self.keys_shared, self.bias_shared, self.values_shared, None, self._spec(cdt))
         return y[:x2.shape[0]]
 
 
