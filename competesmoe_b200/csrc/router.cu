@@ -80,16 +80,24 @@ router_fwd_kernel(const T* __restrict__ x, const T* __restrict__ wg, long long T
   constexpr int EC = 4;
   for (int e0 = 0; e0 < E; e0 += EC) {
     float acc[EC] = {0.f, 0.f, 0.f, 0.f};
-    for (int d = lane * 8; d < D; d += 256) {
-      float xv[8];
-      load8(xr + d, xv);
+    for (int d0 = lane * 8; d0 < D; d0 += 1024) {     // four 16-byte x loads in flight per lane (same summation order)
+      float xv[4][8];
 #pragma unroll
-      for (int i = 0; i < EC; ++i) {
-        if (e0 + i < E) {
-          float wv[8];
-          load8(wg + static_cast<long long>(e0 + i) * D + d, wv);
+      for (int u = 0; u < 4; ++u)
+        if (d0 + u * 256 < D) load8(xr + d0 + u * 256, xv[u]);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[i] = fmaf(xv[j], wv[j], acc[i]);
+      for (int u = 0; u < 4; ++u) {
+        const int d = d0 + u * 256;
+        if (d < D) {
+#pragma unroll
+          for (int i = 0; i < EC; ++i) {
+            if (e0 + i < E) {
+              float wv[8];
+              load8(wg + static_cast<long long>(e0 + i) * D + d, wv);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) acc[i] = fmaf(xv[u][j], wv[j], acc[i]);
+            }
+          }
         }
       }
     }
@@ -226,6 +234,34 @@ router_aux_stage1(const T* __restrict__ logits, const float* __restrict__ probs,
   const int stride = 2 * E + 1;
   float s0 = 0.f, s1 = 0.f, c0 = 0.f, c1 = 0.f, zz = 0.f;  // lane l: experts l and l+32
   const int n0 = c * kAuxChunk + warp * 32;
+  if (E <= 8) {
+    // few experts: one token per lane (the expert-per-lane loop below would walk 32 tokens serially with E lanes busy)
+    const int n = n0 + lane;
+    const bool ok = n < N;
+    const long long t = static_cast<long long>(b) * N + (ok ? n : 0);
+    float lg[8], m = -INFINITY;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      lg[e] = (ok && e < E) ? static_cast<float>(logits[t * E + e]) : -INFINITY;
+      m = fmaxf(m, lg[e]);
+    }
+    float se = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+      if (e < E) se += expf(lg[e] - m);
+    const float lse = ok ? m + logf(se) : 0.f;
+    if (ok && lse_out) lse_out[t] = lse;
+    zz = warp_sum(lse * lse);
+    const int top1 = ok ? topk_idx[t * K] : -1;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      if (e < E) {
+        const float ps = warp_sum(ok ? probs[t * E + e] : 0.f);
+        const float cs = warp_sum(top1 == e ? 1.f : 0.f);
+        if (lane == e) { s0 = ps; c0 = cs; }
+      }
+    }
+  } else
   for (int i = 0; i < 32; ++i) {
     const int n = n0 + i;
     if (n >= N) break;
@@ -388,14 +424,21 @@ router_bwd_dw_stage1(const T* __restrict__ x, const float* __restrict__ dl, long
   for (int e = 0; e < kDwExperts; ++e)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[e][j] = 0.f;
-  for (int tt = 0; tt < nt; ++tt) {
-    float xv[8];
-    load8(x + (t0 + tt) * D + col, xv);
+  for (int t4 = 0; t4 < nt; t4 += 4) {            // four token rows in flight per thread; summation order unchanged
+    float xv[4][8];
 #pragma unroll
-    for (int e = 0; e < kDwExperts; ++e) {
-      const float g = sdl[tt][e];
+    for (int u = 0; u < 4; ++u)
+      if (t4 + u < nt) load8(x + (t0 + t4 + u) * D + col, xv[u]);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[e][j] = fmaf(g, xv[j], acc[e][j]);
+    for (int u = 0; u < 4; ++u) {
+      if (t4 + u < nt) {
+#pragma unroll
+        for (int e = 0; e < kDwExperts; ++e) {
+          const float g = sdl[t4 + u][e];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[e][j] = fmaf(g, xv[u][j], acc[e][j]);
+        }
+      }
     }
   }
 #pragma unroll
@@ -404,19 +447,34 @@ router_bwd_dw_stage1(const T* __restrict__ x, const float* __restrict__ dl, long
   }
 }
 
+// dWg[i] = sum over chunks of partial[c][i] in a fixed order: 32 chunk lanes x 8 column vectors per block, lane l adds
+// chunks l, l+32, ... and lane 0 adds the 32 lane sums in lane order (deterministic; the earlier one-thread-per-vector
+// loop walked all T/32 chunks serially: 55 us at T = 12800).
 template <typename WT>
 __global__ void __launch_bounds__(256)
 router_bwd_dw_stage2(const float* __restrict__ partial, int n_chunks, long long ED, WT* __restrict__ dwg) {
-  const long long i = (static_cast<long long>(blockIdx.x) * 256 + threadIdx.x) * 8;
-  if (i >= ED) return;
+  __shared__ float red[32][8][8];
+  const int v = threadIdx.x & 7, cl = threadIdx.x >> 3;
+  const long long i = (static_cast<long long>(blockIdx.x) * 8 + v) * 8;
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (int c = 0; c < n_chunks; ++c) {
-    float v[8];
-    load8(partial + c * ED + i, v);
+  if (i < ED) {
+    for (int c = cl; c < n_chunks; c += 32) {
+      float t[8];
+      load8(partial + c * ED + i, t);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] += v[j];
+      for (int j = 0; j < 8; ++j) acc[j] += t[j];
+    }
   }
-  store8(dwg + i, acc);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[cl][v][j] = acc[j];
+  __syncthreads();
+  if (cl == 0 && i < ED) {
+#pragma unroll 1
+    for (int l = 1; l < 32; ++l)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += red[l][v][j];
+    store8(dwg + i, acc);
+  }
 }
 
 }  // namespace
@@ -535,7 +593,7 @@ extern "C" int csmoe_router_bwd(const void* x, const void* wg, int32_t x_dtype, 
   const int chunks = static_cast<int>((T + kDwChunk - 1) / kDwChunk);
   dim3 g1((D / 8 + 127) / 128, chunks, (E + kDwExperts - 1) / kDwExperts);
   const long long ED = static_cast<long long>(E) * D;
-  const unsigned g2 = static_cast<unsigned>((ED / 8 + 255) / 256);
+  const unsigned g2 = static_cast<unsigned>((ED / 8 + 7) / 8);
   float* partial = static_cast<float*>(workspace);
   if (x_dtype == CSMOE_BF16) {
     using T_ = __nv_bfloat16;
