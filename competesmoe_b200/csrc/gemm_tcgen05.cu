@@ -989,13 +989,14 @@ constexpr int kPairBBytes = 128 * kBK * 2;
 constexpr int kPairStageBytes = kABytes + kPairBBytes;  // 32 KiB per CTA per stage
 
 template <int MODE>
-__device__ __forceinline__ Tile decode_tile_pair(const KParams& p, long long t, int rank) {
+__device__ __forceinline__ Tile decode_tile_pair(const KParams& p, long long t, int rank, int num_n = -1) {
   Tile ti;
   const int num_m2 = p.num_m_pairs;
+  if (num_n < 0) num_n = p.num_n_blocks;
   if (MODE == CSMOE_GEMM_ROWS) {
     if (p.raster_m) {
       // bands of `band` m-blocks, m fastest inside a band: neighbouring clusters ask for the same B tile at the same time
-      const long long band_tiles = static_cast<long long>(p.band) * p.num_n_blocks;
+      const long long band_tiles = static_cast<long long>(p.band) * num_n;
       const int b = static_cast<int>(t / band_tiles);
       const int r = static_cast<int>(t % band_tiles);
       const int mb0 = b * p.band;
@@ -1007,7 +1008,7 @@ __device__ __forceinline__ Tile decode_tile_pair(const KParams& p, long long t, 
       const int b = static_cast<int>(t / band_tiles);
       const int r = static_cast<int>(t % band_tiles);
       const int nb0 = b * p.band;
-      const int w = min(p.band, p.num_n_blocks - nb0);
+      const int w = min(p.band, num_n - nb0);
       ti.mb = r / w;
       ti.nb = nb0 + r % w;
     }
@@ -1026,13 +1027,13 @@ __device__ __forceinline__ Tile decode_tile_pair(const KParams& p, long long t, 
     ti.nkb = p.kcat ? p.num_kb * p.num_experts : p.num_kb;
     ti.valid = ti.e >= 0;
   } else {
-    const long long per_e = static_cast<long long>(num_m2) * p.num_n_blocks;
+    const long long per_e = static_cast<long long>(num_m2) * num_n;
     ti.e = static_cast<int>(t / per_e);
     const int r = static_cast<int>(t % per_e);
     const int band_tiles = p.band * num_m2;
     const int b = r / band_tiles, rr = r % band_tiles;
     const int nb0 = b * p.band;
-    const int w = min(p.band, p.num_n_blocks - nb0);
+    const int w = min(p.band, num_n - nb0);
     ti.mb = rr / w;
     ti.nb = nb0 + rr % w;
     if (p.dense) {
@@ -1050,11 +1051,16 @@ __device__ __forceinline__ Tile decode_tile_pair(const KParams& p, long long t, 
   return ti;
 }
 
-template <int MODE, bool B_MN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
-grouped_gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                         const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ CUtensorMap tma_p,
-                         const __grid_constant__ CUtensorMap tma_z, const KParams p) {
+// CL = CTAs per cluster.  CL == 2: one pair.  CL == 4: two pairs that work on the same 256 rows and on neighbouring
+// n-blocks (nb = 2 * nb2 + pair); every CTA fetches only half of its 128 x 64 A sub-tile and multicasts it to the CTA at
+// the same position in the other pair, so the L2 -> SM traffic per CTA and k-block drops from 32 to 24 KiB (the pair
+// kernel's limiter) while both pairs keep their double-buffered accumulators.  A stage is then
+// written by loads of both pairs, so the empty barriers count one tcgen05.commit per pair (multicast to all four CTAs)
+// and the two pairs advance through the k loop in lockstep.
+template <int MODE, bool B_MN, int CL>
+__device__ __forceinline__ void pair_kernel_body(const CUtensorMap& tma_a, const CUtensorMap& tma_b, const CUtensorMap& tma_c,
+                                                 const CUtensorMap& tma_p, const CUtensorMap& tma_z, const KParams& p) {
+  static_assert(CL == 2 || CL == 4, "cluster of one or two CTA pairs");
   constexpr int BN = 256;
   constexpr bool kAMn = (MODE == CSMOE_GEMM_REDUCE);
   constexpr bool kBMn = kAMn || B_MN;
@@ -1077,10 +1083,20 @@ grouped_gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int rank = static_cast<int>(ptx::cluster_ctarank());
+  const int crank = static_cast<int>(ptx::cluster_ctarank());   // 0 .. CL-1
+  const int rank = crank & 1;                                    // position inside the pair
+  const int pair = crank >> 1;                                   // which pair of the cluster
   const bool leader = rank == 0;
-  const long long cluster_id = blockIdx.x >> 1;
-  const long long num_clusters = gridDim.x >> 1;
+  const long long cluster_id = blockIdx.x / CL;
+  const long long num_clusters = gridDim.x / CL;
+  const int num_n = CL == 4 ? (p.num_n_blocks + 1) / 2 : p.num_n_blocks;     // n-block groups a cluster iterates over
+  const uint16_t pair_mask = static_cast<uint16_t>(0x3u << (2 * pair));      // the two CTAs of this pair
+  const uint16_t all_mask = static_cast<uint16_t>((1u << CL) - 1u);
+  auto tile_of = [&](long long t) {
+    Tile ti = decode_tile_pair<MODE>(p, t, rank, num_n);
+    if (CL == 4) ti.nb = 2 * ti.nb + pair;
+    return ti;
+  };
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tma_a);
@@ -1089,7 +1105,7 @@ grouped_gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kPairStages; ++s) {
       ptx::mbar_init(full_bar(s), 1);
-      ptx::mbar_init(empty_bar(s), 1);
+      ptx::mbar_init(empty_bar(s), CL / 2);
     }
     for (int a = 0; a < kAccStages; ++a) {
       ptx::mbar_init(tfull_bar(a), 1);
@@ -1118,7 +1134,7 @@ grouped_gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
       unsigned long long w_empty = 0;
       int dbg_filled = 0;
       for (long long t = cluster_id; t < p.total_tiles; t += num_clusters) {
-        const Tile ti = decode_tile_pair<MODE>(p, t, rank);
+        const Tile ti = tile_of(t);
         if (!ti.valid) continue;
         for (int kb = 0; kb < ti.nkb; ++kb) {
           timed_wait(empty_bar(stage), phase ^ 1u, st_on, w_empty);
@@ -1132,7 +1148,8 @@ grouped_gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
           }
           ++dbg_filled;
           if (leader) ptx::mbar_arrive_expect_tx(full_bar(stage), 2 * kPairStageBytes);
-          const uint32_t fb = ptx::mapa(full_bar(stage), 0);  // the leader's barrier collects both CTAs' bytes
+          // the pair leader's barrier collects both CTAs' bytes
+          const uint32_t fb = CL == 2 ? ptx::mapa(full_bar(stage), 0) : (full_bar(stage) & ptx::kPeerBitMask);
           const uint32_t sa = smem_base + stage * kPairStageBytes;
           const uint32_t sb = sa + kABytes;
           if (MODE == CSMOE_GEMM_ROWS) {
@@ -1142,7 +1159,12 @@ grouped_gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
               kx = (kb % p.num_kb) * kBK;
               arow += ex * p.a_expert_rows;
             }
-            ptx::tma_load_2d_cg2(sa, &tma_a, fb, kx, arow);
+            if (CL == 2) {
+              ptx::tma_load_2d_cg2(sa, &tma_a, fb, kx, arow);
+            } else {   // this CTA's half of the 128 rows, delivered to both pairs
+              ptx::tma_load_2d_cg2_mc(sa + pair * (kABytes / 2), &tma_a, fb, kx, arow + pair * 64,
+                                      static_cast<uint16_t>((1u << crank) | (1u << (crank ^ 2))));
+            }
             if (!B_MN) {
               const int brow = p.epi == kEpiGluFwd ? (rank == 0 ? ti.nb * 128 : p.glu_f + ti.nb * 128)
                                                    : ti.nb * BN + rank * 128;
@@ -1153,10 +1175,15 @@ grouped_gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
                 ptx::tma_load_3d_cg2(sb + j * kSubTileBytes, &tma_b, fb, ti.nb * BN + rank * 128 + j * 64, kx, ex);
             }
           } else {
+            if (CL == 2) {
 #pragma unroll
-            for (int j = 0; j < 2; ++j)
-              ptx::tma_load_2d_cg2(sa + j * kSubTileBytes, &tma_a, fb, ti.mb * 256 + rank * 128 + j * 64,
-                                   ti.a_row + kb * kBK);
+              for (int j = 0; j < 2; ++j)
+                ptx::tma_load_2d_cg2(sa + j * kSubTileBytes, &tma_a, fb, ti.mb * 256 + rank * 128 + j * 64,
+                                     ti.a_row + kb * kBK);
+            } else {
+              ptx::tma_load_2d_cg2_mc(sa + pair * kSubTileBytes, &tma_a, fb, ti.mb * 256 + rank * 128 + pair * 64,
+                                      ti.a_row + kb * kBK, static_cast<uint16_t>((1u << crank) | (1u << (crank ^ 2))));
+            }
 #pragma unroll
             for (int j = 0; j < 2; ++j)
               ptx::tma_load_2d_cg2(sb + j * kSubTileBytes, &tma_b, fb, ti.nb * BN + rank * 128 + j * 64,
@@ -1176,7 +1203,7 @@ grouped_gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
       unsigned long long w_full = 0, w_tempty = 0, n_tiles = 0;
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
       for (long long t = cluster_id; t < p.total_tiles; t += num_clusters) {
-        const Tile ti = decode_tile_pair<MODE>(p, t, rank);
+        const Tile ti = tile_of(t);
         if (!ti.valid || ti.nkb == 0) continue;
         ++n_tiles;
         timed_wait(tempty_bar(acc), acc_phase ^ 1u, st_on, w_tempty);
@@ -1195,13 +1222,13 @@ grouped_gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
                                         : ptx::make_smem_desc_sw128(sb + k * 32, 16, 1024);
             if (!(p.dbg_mode & 2)) ptx::umma_f16_cg2(d_tmem, adesc, bdesc, kIdesc, (kb | k) != 0 ? 1u : 0u);
           }
-          ptx::umma_commit_cg2_mc(empty_bar(stage), 0x3);
+          ptx::umma_commit_cg2_mc(empty_bar(stage), all_mask);
           if (++stage == n_stages) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        ptx::umma_commit_cg2_mc(tfull_bar(acc), 0x3);
+        ptx::umma_commit_cg2_mc(tfull_bar(acc), pair_mask);
         if (++acc == kAccStages) {
           acc = 0;
           acc_phase ^= 1u;
@@ -1222,7 +1249,7 @@ grouped_gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
     uint32_t tma_slot = 0, z_phase = 0;
     uint32_t acc = 0, acc_phase = 0;
     for (long long t = cluster_id; t < p.total_tiles; t += num_clusters) {
-      const Tile ti = decode_tile_pair<MODE>(p, t, rank);
+      const Tile ti = tile_of(t);
       if (!ti.valid) continue;
       const bool has_acc = ti.nkb > 0;
       if (has_acc) {
@@ -1249,7 +1276,7 @@ grouped_gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
           if (leader)
             ptx::mbar_arrive(tempty_bar(acc));
           else
-            ptx::mbar_arrive_remote_relaxed(ptx::mapa(tempty_bar(acc), 0));
+            ptx::mbar_arrive_remote_relaxed(ptx::mapa(tempty_bar(acc), crank & ~1));
         }
         if (++acc == kAccStages) {
           acc = 0;
@@ -1273,6 +1300,22 @@ grouped_gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
     ptx::tc_fence_after();
     ptx::tmem_dealloc_cg2(tmem_base, kTmemCols);
   }
+}
+
+template <int MODE, bool B_MN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+grouped_gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                         const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ CUtensorMap tma_p,
+                         const __grid_constant__ CUtensorMap tma_z, const KParams p) {
+  pair_kernel_body<MODE, B_MN, 2>(tma_a, tma_b, tma_c, tma_p, tma_z, p);
+}
+
+template <int MODE, bool B_MN>
+__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(kThreads, 1)
+grouped_gemm_quad_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                         const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ CUtensorMap tma_p,
+                         const __grid_constant__ CUtensorMap tma_z, const KParams p) {
+  pair_kernel_body<MODE, B_MN, 4>(tma_a, tma_b, tma_c, tma_p, tma_z, p);
 }
 
 
@@ -1575,6 +1618,7 @@ int encode_out_map(CUtensorMap* map, const void* base, bool fp32, long long cols
 
 struct Maps {
   CUtensorMap a, b, c, p, z;
+  CUtensorMap aq;   // A with half-height boxes (quad clusters); swapped into `a` when that kernel is chosen
 };
 
 template <int MODE, bool B_MN, int BN>
@@ -1604,6 +1648,39 @@ int launch_pair(const Maps& m, const KParams& kp, int clusters, cudaStream_t str
     configured = true;
   }
   kern<<<2 * clusters, kThreads, kSmem, stream>>>(m.a, m.b, m.c, m.p, m.z, kp);
+  CSMOE_CHECK_LAUNCH();
+  return CSMOE_OK;
+}
+
+// Clusters of 4 (two pairs sharing A through multicast).  Returns the number of co-resident clusters through `cap` when
+// `clusters` <= 0 (query only).
+template <int MODE, bool B_MN>
+int launch_quad(const Maps& m, const KParams& kp, int clusters, cudaStream_t stream, int* cap = nullptr) {
+  constexpr int kSmem = (kPairStages - 1) * kPairStageBytes + kEpiWarps * 2 * kStageTileBytes + 1024 + 256;
+  auto kern = grouped_gemm_quad_kernel<MODE, B_MN>;
+  static bool configured = false;
+  static int max_clusters = 0;
+  if (!configured) {
+    CSMOE_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(4 * 64);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = kSmem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 4;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    CSMOE_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+    max_clusters = n;
+    configured = true;
+  }
+  if (cap != nullptr) *cap = max_clusters;
+  if (clusters <= 0) return CSMOE_OK;
+  kern<<<4 * clusters, kThreads, kSmem, stream>>>(m.a, m.b, m.c, m.p, m.z, kp);
   CSMOE_CHECK_LAUNCH();
   return CSMOE_OK;
 }
@@ -1688,6 +1765,16 @@ bool tma_default(int mode) {
   return (m & (mode == CSMOE_GEMM_ROWS ? 1 : 2)) != 0;
 }
 
+// CSMOE_GEMM_QUAD: bit 0 = ROWS, bit 1 = REDUCE launches of the 256 x 256 kernel run as clusters of two pairs with the A
+// operand multicast (default 0 until measured; see pair_kernel_body)
+int quad_mask() {
+  static const int m = []() {
+    const char* v = getenv("CSMOE_GEMM_QUAD");
+    return v == nullptr ? 0 : atoi(v);
+  }();
+  return m;
+}
+
 // CSMOE_GEMM_PAIR=0 disables the CTA-pair kernel (A/B comparisons, bring-up)
 bool pair_enabled() {
   static const bool on = []() {
@@ -1766,6 +1853,9 @@ extern "C" int csmoe_grouped_gemm(const csmoe_gemm_args* a, void* stream_) {
   } else {
     pair = pair && a->m >= 256;
   }
+
+  // clusters of two pairs (A multicast): plain pair launches only (no per-row destinations; the n-blocks come in twos)
+  const bool quad = pair && (quad_mask() & (a->mode == CSMOE_GEMM_ROWS ? 1 : 2)) != 0 && a->c_rows == nullptr;
 
   KParams kp{};
   kp.n = static_cast<int>(a->n);
@@ -1861,8 +1951,10 @@ extern "C" int csmoe_grouped_gemm(const csmoe_gemm_args* a, void* stream_) {
     {
       cuuint64_t dims[2] = {(cuuint64_t)a->k, (cuuint64_t)a_rows};
       cuuint64_t str[1] = {(cuuint64_t)a->lda * 2};
-      cuuint32_t box[2] = {kBK, kBM};
+      cuuint32_t box[2] = {kBK, kBM};   // (a cluster of two pairs loads the 128 rows as two multicast halves)
+      cuuint32_t box_q[2] = {kBK, kBM / 2};
       if ((rc = encode_bf16_map(&ma, a->a, 2, dims, str, box)) != CSMOE_OK) return rc;
+      if (quad && (rc = encode_bf16_map(&maps.aq, a->a, 2, dims, str, box_q)) != CSMOE_OK) return rc;
     }
     if (a->b_layout == 0) {
       cuuint64_t dims[3] = {(cuuint64_t)a->k, (cuuint64_t)a->n, (cuuint64_t)E};
@@ -1937,6 +2029,36 @@ extern "C" int csmoe_grouped_gemm(const csmoe_gemm_args* a, void* stream_) {
     const bool wide = n_grid >= 512 && (n_grid % 512 == 0 || n_grid >= 2048) && long_k && kp.tma_epi != 2 &&
                       (wm & (a->mode == CSMOE_GEMM_ROWS ? 1 : 2)) != 0;
     if (wide) kp.num_n_blocks = glu_fwd ? static_cast<int>((n_grid + 255) / 256) : static_cast<int>((a->n + 511) / 512);
+    if (quad && !wide) {
+      // two pairs per cluster on neighbouring n-blocks: the cluster iterates over ceil(n-blocks / 2) groups
+      const long long per_q = static_cast<long long>(kp.num_m_pairs) * ((kp.num_n_blocks + 1) / 2);
+      kp.total_tiles = a->mode == CSMOE_GEMM_ROWS ? per_q : per_q * E;
+      if (a->mode == CSMOE_GEMM_ROWS) maps.a = maps.aq;
+      int cap = 0, rcq;
+#define CSMOE_QUAD(CL_) (a->mode == CSMOE_GEMM_ROWS                                                                        \
+                             ? (a->b_layout == 0 ? launch_quad<CSMOE_GEMM_ROWS, false>(maps, kp, CL_, stream, &cap)       \
+                                                 : launch_quad<CSMOE_GEMM_ROWS, true>(maps, kp, CL_, stream, &cap))       \
+                             : launch_quad<CSMOE_GEMM_REDUCE, true>(maps, kp, CL_, stream, &cap))
+      if ((rcq = CSMOE_QUAD(0)) != CSMOE_OK) return rcq;     // occupancy query (cached after the first call)
+      int clusters_q = cap;
+      if (clusters_q <= 0) {
+        set_error("csmoe_grouped_gemm: no cluster of 4 CTAs fits on this device");
+        return CSMOE_ERR_CUDA;
+      }
+      if (a->max_ctas > 3 && a->max_ctas / 4 < clusters_q) clusters_q = a->max_ctas / 4;
+      if (kp.total_tiles < clusters_q) clusters_q = static_cast<int>(kp.total_tiles);
+      kp.stats = stats_buffer();
+      if (kp.stats != nullptr) cudaMemsetAsync(kp.stats, 0, 256 * 8 * sizeof(unsigned long long), stream);
+      rcq = CSMOE_QUAD(clusters_q);
+#undef CSMOE_QUAD
+      if (rcq == CSMOE_OK && kp.stats != nullptr) {
+        char what[96];
+        snprintf(what, sizeof(what), "quad(%d clusters) mode=%d b_layout=%d epi=%d n=%lld k=%lld", clusters_q, a->mode,
+                 a->b_layout, kp.epi, (long long)a->n, (long long)a->k);
+        print_stats(what, kp, 4 * clusters_q, stream);
+      }
+      return rcq;
+    }
     const long long per = static_cast<long long>(kp.num_m_pairs) * kp.num_n_blocks;
     kp.total_tiles = a->mode == CSMOE_GEMM_ROWS ? per : per * E;
     int clusters = num_sms() / 2;

@@ -137,6 +137,19 @@ __device__ __forceinline__ void tma_load_3d_cg2(uint32_t dst, const CUtensorMap*
       : "memory");
 }
 
+// cta_group::2 + multicast: the box lands at the same CTA-relative offset in every CTA of `cta_mask`, and each
+// destination's bytes are counted on the barrier at `bar`'s offset in that destination's pair leader (`bar` is the local
+// barrier address with the peer bit cleared, as in CUTLASS' SM100_TMA_2SM_LOAD_MULTICAST).
+__device__ __forceinline__ void tma_load_2d_cg2_mc(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1,
+                                                   uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+      "[%0], [%1, {%4, %5}], [%2], %3;" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "h"(cta_mask), "r"(c0), "r"(c1)
+      : "memory");
+}
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // shared::cluster address of the same offset in the even CTA of a pair
+
 // TMA stores (shared::cta -> global through a tensor map; bulk async-group completion)
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
