@@ -58,6 +58,29 @@ __device__ __forceinline__ void load8(const float* p, float (&f)[8]) {
   f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
   f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
 }
+// Raw 8-element loads (kept packed while several are in flight: 4 registers per bf16 vector instead of 8 floats).
+struct Raw8bf { uint4 u; };
+struct Raw8f { float4 a, b; };
+__device__ __forceinline__ Raw8bf load8_raw(const __nv_bfloat16* p) { return Raw8bf{*reinterpret_cast<const uint4*>(p)}; }
+__device__ __forceinline__ Raw8f load8_raw(const float* p) {
+  return Raw8f{*reinterpret_cast<const float4*>(p), *reinterpret_cast<const float4*>(p + 4)};
+}
+__device__ __forceinline__ void unpack8(const Raw8bf& r, float (&f)[8]) {
+  const uint32_t w[4] = {r.u.x, r.u.y, r.u.z, r.u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = __uint_as_float(w[i] << 16);
+    f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+__device__ __forceinline__ void unpack8(const Raw8f& r, float (&f)[8]) {
+  f[0] = r.a.x; f[1] = r.a.y; f[2] = r.a.z; f[3] = r.a.w;
+  f[4] = r.b.x; f[5] = r.b.y; f[6] = r.b.z; f[7] = r.b.w;
+}
+template <typename T> struct Raw8;
+template <> struct Raw8<__nv_bfloat16> { using type = Raw8bf; };
+template <> struct Raw8<float> { using type = Raw8f; };
+
 __device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&f)[8]) {
   uint4 u;
   __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);

@@ -51,26 +51,36 @@ gather_rows_kernel(const T* __restrict__ src, int D, int K, const int32_t* __res
   }
 }
 
+// The three kernels below are templated on KT = K rounded up to 2 / 4 / 8 (registers and predicated work scale with it:
+// with the runtime K <= 8 form the K = 2 shapes ran at 84 registers and 2 CTAs / SM) and, where the work is elementwise
+// over columns, one warp owns (token, block of 1024 columns) so that few-token / wide-row shapes (T = 4096, D = 3072)
+// still fill the machine.
+constexpr int kColBlock = 1024;
+
 // out[t] = sum_k w[t,k] * y[row(t,k)], slots visited in ascending expert id (ties: ascending k).
 // flags bit0: round the running sum to T after every term (moe.py:204 accumulates in the output dtype);
 // flags bit1: round w to T before use (cvmm.py:483 `reduction_weight.type_as(res)`).
-template <typename T>
+template <typename T, int KT>
 __global__ void __launch_bounds__(kWarps * 32)
 combine_fwd_kernel(const T* __restrict__ y, long long Tn, int D, int K, const int32_t* __restrict__ slot_to_row,
                    const int32_t* __restrict__ sel, const float* __restrict__ w, int flags, T* __restrict__ out) {
   const int lane = threadIdx.x & 31;
-  for (long long t = static_cast<long long>(blockIdx.x) * kWarps + (threadIdx.x >> 5); t < Tn;
-       t += static_cast<long long>(gridDim.x) * kWarps) {
-    int order[kMaxK];
-    int key[kMaxK];
+  const int nblk = (D + kColBlock - 1) / kColBlock;
+  const long long units = Tn * nblk;
+  for (long long u = static_cast<long long>(blockIdx.x) * kWarps + (threadIdx.x >> 5); u < units;
+       u += static_cast<long long>(gridDim.x) * kWarps) {
+    const long long t = u / nblk;
+    const int c_lo = static_cast<int>(u % nblk) * kColBlock, c_hi = min(D, c_lo + kColBlock);
+    int order[KT];
+    int key[KT];
 #pragma unroll
-    for (int k = 0; k < kMaxK; ++k) {
+    for (int k = 0; k < KT; ++k) {
       order[k] = k;
       key[k] = k < K ? sel[t * K + k] : 0x7fffffff;
     }
-    // insertion sort (stable) of at most 8 keys; lane-uniform
+    // insertion sort (stable) of at most KT keys; lane-uniform
 #pragma unroll
-    for (int i = 1; i < kMaxK; ++i) {
+    for (int i = 1; i < KT; ++i) {
 #pragma unroll
       for (int j = i; j > 0; --j) {
         if (key[j] < key[j - 1]) {
@@ -79,10 +89,12 @@ combine_fwd_kernel(const T* __restrict__ y, long long Tn, int D, int K, const in
         }
       }
     }
-    long long rows[kMaxK];
-    float ws[kMaxK];
+    int rows[KT];
+    float ws[KT];
 #pragma unroll
-    for (int i = 0; i < kMaxK; ++i) {
+    for (int i = 0; i < KT; ++i) {
+      rows[i] = 0;
+      ws[i] = 0.f;
       if (i < K) {
         const long long s = t * K + order[i];
         rows[i] = slot_to_row[s];
@@ -91,13 +103,17 @@ combine_fwd_kernel(const T* __restrict__ y, long long Tn, int D, int K, const in
         ws[i] = wv;
       }
     }
-    for (int c = lane * 8; c < D; c += 256) {
+    for (int c = c_lo + lane * 8; c < c_hi; c += 256) {
       float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      typename Raw8<T>::type raw[KT];
 #pragma unroll
-      for (int i = 0; i < kMaxK; ++i) {
+      for (int i = 0; i < KT; ++i)
+        if (i < K) raw[i] = load8_raw(y + static_cast<long long>(rows[i]) * D + c);
+#pragma unroll
+      for (int i = 0; i < KT; ++i) {
         if (i < K) {
           float v[8];
-          load8(y + rows[i] * D + c, v);
+          unpack8(raw[i], v);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             acc[j] = fmaf(ws[i], v[j], acc[j]);
@@ -111,35 +127,39 @@ combine_fwd_kernel(const T* __restrict__ y, long long Tn, int D, int K, const in
 }
 
 // dw[t,k] = <dout[t], y[row(t,k)]>
-template <typename T>
+template <typename T, int KT>
 __global__ void __launch_bounds__(kWarps * 32)
 combine_bwd_w_kernel(const T* __restrict__ y, const T* __restrict__ dout, long long Tn, int D, int K,
                      const int32_t* __restrict__ slot_to_row, float* __restrict__ dw) {
   const int lane = threadIdx.x & 31;
   for (long long t = static_cast<long long>(blockIdx.x) * kWarps + (threadIdx.x >> 5); t < Tn;
        t += static_cast<long long>(gridDim.x) * kWarps) {
-    float acc[kMaxK];
-    long long rows[kMaxK];
+    float acc[KT];
+    int rows[KT];
 #pragma unroll
-    for (int k = 0; k < kMaxK; ++k) {
+    for (int k = 0; k < KT; ++k) {
       acc[k] = 0.f;
       rows[k] = k < K ? slot_to_row[t * K + k] : 0;
     }
     for (int c = lane * 8; c < D; c += 256) {
       float g[8];
+      typename Raw8<T>::type raw[KT];
       load8(dout + t * D + c, g);
 #pragma unroll
-      for (int k = 0; k < kMaxK; ++k) {
+      for (int k = 0; k < KT; ++k)
+        if (k < K) raw[k] = load8_raw(y + static_cast<long long>(rows[k]) * D + c);
+#pragma unroll
+      for (int k = 0; k < KT; ++k) {
         if (k < K) {
           float v[8];
-          load8(y + rows[k] * D + c, v);
+          unpack8(raw[k], v);
 #pragma unroll
           for (int j = 0; j < 8; ++j) acc[k] = fmaf(g[j], v[j], acc[k]);
         }
       }
     }
 #pragma unroll
-    for (int k = 0; k < kMaxK; ++k) {
+    for (int k = 0; k < KT; ++k) {
       if (k < K) {
         float s = acc[k];
 #pragma unroll
@@ -151,24 +171,32 @@ combine_bwd_w_kernel(const T* __restrict__ y, const T* __restrict__ dout, long l
 }
 
 // dx[t] (+)= sum_k g[row(t,k)]   (fp32 sum in k order, one rounding)
-template <typename T>
+template <typename T, int KT>
 __global__ void __launch_bounds__(kWarps * 32)
 scatter_reduce_kernel(const T* __restrict__ g, long long Tn, int D, int K, const int32_t* __restrict__ slot_to_row,
                       int accumulate, T* __restrict__ dx) {
   const int lane = threadIdx.x & 31;
-  for (long long t = static_cast<long long>(blockIdx.x) * kWarps + (threadIdx.x >> 5); t < Tn;
-       t += static_cast<long long>(gridDim.x) * kWarps) {
-    long long rows[kMaxK];
+  const int nblk = (D + kColBlock - 1) / kColBlock;
+  const long long units = Tn * nblk;
+  for (long long u = static_cast<long long>(blockIdx.x) * kWarps + (threadIdx.x >> 5); u < units;
+       u += static_cast<long long>(gridDim.x) * kWarps) {
+    const long long t = u / nblk;
+    const int c_lo = static_cast<int>(u % nblk) * kColBlock, c_hi = min(D, c_lo + kColBlock);
+    int rows[KT];
 #pragma unroll
-    for (int k = 0; k < kMaxK; ++k) rows[k] = k < K ? slot_to_row[t * K + k] : 0;
-    for (int c = lane * 8; c < D; c += 256) {
+    for (int k = 0; k < KT; ++k) rows[k] = k < K ? slot_to_row[t * K + k] : 0;
+    for (int c = c_lo + lane * 8; c < c_hi; c += 256) {
       float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      typename Raw8<T>::type raw[KT];
       if (accumulate) load8(dx + t * D + c, acc);
 #pragma unroll
-      for (int k = 0; k < kMaxK; ++k) {
+      for (int k = 0; k < KT; ++k)
+        if (k < K) raw[k] = load8_raw(g + static_cast<long long>(rows[k]) * D + c);
+#pragma unroll
+      for (int k = 0; k < KT; ++k) {
         if (k < K) {
           float v[8];
-          load8(g + rows[k] * D + c, v);
+          unpack8(raw[k], v);
 #pragma unroll
           for (int j = 0; j < 8; ++j) acc[j] += v[j];
         }
@@ -188,6 +216,11 @@ inline unsigned row_grid(long long rows) {
 }  // namespace csmoe
 
 using namespace csmoe;
+
+#define DISPATCH_KT(K, ...)                                  \
+  if ((K) <= 2) { constexpr int KT = 2; __VA_ARGS__; }       \
+  else if ((K) <= 4) { constexpr int KT = 4; __VA_ARGS__; }   \
+  else { constexpr int KT = 8; __VA_ARGS__; }
 
 #define DISPATCH_DTYPE(dtype, ...)                          \
   if ((dtype) == CSMOE_BF16) {                              \
@@ -221,8 +254,9 @@ extern "C" int csmoe_combine_fwd(const void* y, int32_t dtype, int64_t T_, int32
   CSMOE_CHECK_ARG(D > 0 && D % 8 == 0 && K >= 1 && K <= kMaxK, "csmoe_combine_fwd: D %% 8 == 0 and 1 <= K <= %d", kMaxK);
   if (T_ == 0) return CSMOE_OK;
   cudaStream_t stream = as_stream(stream_);
-  DISPATCH_DTYPE(dtype, (combine_fwd_kernel<T><<<row_grid(T_), kWarps * 32, 0, stream>>>(
-                            static_cast<const T*>(y), T_, D, K, slot_to_row, sel, w, flags, static_cast<T*>(out))));
+  const long long units = T_ * ((D + kColBlock - 1) / kColBlock);
+  DISPATCH_DTYPE(dtype, DISPATCH_KT(K, (combine_fwd_kernel<T, KT><<<row_grid(units), kWarps * 32, 0, stream>>>(
+                                          static_cast<const T*>(y), T_, D, K, slot_to_row, sel, w, flags, static_cast<T*>(out)))));
   CSMOE_CHECK_LAUNCH();
   return CSMOE_OK;
 }
@@ -233,8 +267,8 @@ extern "C" int csmoe_combine_bwd_w(const void* y, const void* dout, int32_t dtyp
   CSMOE_CHECK_ARG(D > 0 && D % 8 == 0 && K >= 1 && K <= kMaxK, "csmoe_combine_bwd_w: D %% 8 == 0 and 1 <= K <= %d", kMaxK);
   if (T_ == 0) return CSMOE_OK;
   cudaStream_t stream = as_stream(stream_);
-  DISPATCH_DTYPE(dtype, (combine_bwd_w_kernel<T><<<row_grid(T_), kWarps * 32, 0, stream>>>(
-                            static_cast<const T*>(y), static_cast<const T*>(dout), T_, D, K, slot_to_row, dw)));
+  DISPATCH_DTYPE(dtype, DISPATCH_KT(K, (combine_bwd_w_kernel<T, KT><<<row_grid(T_), kWarps * 32, 0, stream>>>(
+                                          static_cast<const T*>(y), static_cast<const T*>(dout), T_, D, K, slot_to_row, dw))));
   CSMOE_CHECK_LAUNCH();
   return CSMOE_OK;
 }
@@ -245,8 +279,9 @@ extern "C" int csmoe_scatter_reduce(const void* g, int32_t dtype, int64_t T_, in
   CSMOE_CHECK_ARG(D > 0 && D % 8 == 0 && K >= 1 && K <= kMaxK, "csmoe_scatter_reduce: D %% 8 == 0 and 1 <= K <= %d", kMaxK);
   if (T_ == 0) return CSMOE_OK;
   cudaStream_t stream = as_stream(stream_);
-  DISPATCH_DTYPE(dtype, (scatter_reduce_kernel<T><<<row_grid(T_), kWarps * 32, 0, stream>>>(
-                            static_cast<const T*>(g), T_, D, K, slot_to_row, accumulate, static_cast<T*>(dx))));
+  const long long units = T_ * ((D + kColBlock - 1) / kColBlock);
+  DISPATCH_DTYPE(dtype, DISPATCH_KT(K, (scatter_reduce_kernel<T, KT><<<row_grid(units), kWarps * 32, 0, stream>>>(
+                                          static_cast<const T*>(g), T_, D, K, slot_to_row, accumulate, static_cast<T*>(dx)))));
   CSMOE_CHECK_LAUNCH();
   return CSMOE_OK;
 }
