@@ -11,41 +11,46 @@ namespace {
 constexpr int kWarps = 8;
 constexpr int kMaxK = 8;
 
-// dst[row] = scale * src[slot / K]   (zero for padding rows)
+// dst[row] = scale * src[slot / K]   (zero for padding rows); one warp per (row, block of 1024 columns)
+constexpr int kGatherCols = 1024;
+
 template <typename T>
 __global__ void __launch_bounds__(kWarps * 32)
 gather_rows_kernel(const T* __restrict__ src, int D, int K, const int32_t* __restrict__ row_to_slot, long long row_cap,
                    const float* __restrict__ slot_w, T* __restrict__ dst) {
   const int lane = threadIdx.x & 31;
-  for (long long row = static_cast<long long>(blockIdx.x) * kWarps + (threadIdx.x >> 5); row < row_cap;
-       row += static_cast<long long>(gridDim.x) * kWarps) {
+  const int nblk = (D + kGatherCols - 1) / kGatherCols;
+  const long long units = row_cap * nblk;
+  for (long long u = static_cast<long long>(blockIdx.x) * kWarps + (threadIdx.x >> 5); u < units;
+       u += static_cast<long long>(gridDim.x) * kWarps) {
+    const long long row = u / nblk;
+    const int c0 = static_cast<int>(u % nblk) * kGatherCols + lane * 8;
     const int slot = row_to_slot[row];
     T* d = dst + row * D;
     if (slot < 0) {
       const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      for (int c = lane * 8; c < D; c += 256) store8(d + c, z);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (c0 + i * 256 < D) store8(d + c0 + i * 256, z);
       continue;
     }
     const T* s = src + static_cast<long long>(slot / K) * D;
-    if (slot_w == nullptr) {
-      // four 16-byte loads per lane in flight before the first store (one at a time left the copy latency bound)
-      for (int c0 = lane * 8; c0 < D; c0 += 1024) {
-        float v[4][8];
+    // four 16-byte loads per lane in flight before the first store
+    typename Raw8<T>::type raw[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          if (c0 + i * 256 < D) load8(s + c0 + i * 256, v[i]);
+    for (int i = 0; i < 4; ++i)
+      if (c0 + i * 256 < D) raw[i] = load8_raw(s + c0 + i * 256);
+    const float w = slot_w != nullptr ? slot_w[slot] : 1.f;
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          if (c0 + i * 256 < D) store8(d + c0 + i * 256, v[i]);
-      }
-    } else {
-      const float w = slot_w[slot];
-      for (int c = lane * 8; c < D; c += 256) {
+    for (int i = 0; i < 4; ++i) {
+      if (c0 + i * 256 < D) {
         float v[8];
-        load8(s + c, v);
+        unpack8(raw[i], v);
+        if (slot_w != nullptr) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] *= w;
-        store8(d + c, v);
+          for (int j = 0; j < 8; ++j) v[j] *= w;
+        }
+        store8(d + c0 + i * 256, v);
       }
     }
   }
@@ -241,7 +246,7 @@ extern "C" int csmoe_gather_rows(const void* src, int32_t dtype, int64_t T_, int
   (void)T_;
   if (row_cap == 0) return CSMOE_OK;
   cudaStream_t stream = as_stream(stream_);
-  DISPATCH_DTYPE(dtype, (gather_rows_kernel<T><<<row_grid(row_cap), kWarps * 32, 0, stream>>>(
+  DISPATCH_DTYPE(dtype, (gather_rows_kernel<T><<<row_grid(row_cap * ((D + kGatherCols - 1) / kGatherCols)), kWarps * 32, 0, stream>>>(
                             static_cast<const T*>(src), D, K, row_to_slot, row_cap, slot_w, static_cast<T*>(dst))));
   CSMOE_CHECK_LAUNCH();
   return CSMOE_OK;
