@@ -198,6 +198,61 @@ def profile_case(case: Case, dev, ep):
     torch.cuda.empty_cache()
 
 
+def cpu_baseline_rows():
+    """the reference's algorithm (the oracle port, fp32) timed on this box's host cores beside the GPU
+    numbers -- C1 at its full size (BASELINE configs[0] is this CPU-runnable case) and the SigLIP MoE MLP of C2'/C5 on a
+    bounded sample of its tokens.  A reported baseline, not the target."""
+    import time
+    from oracle import multimodal as om
+    from oracle import pretrain as opr
+    torch.set_num_threads(os.cpu_count() or 1)
+    cores = torch.get_num_threads()
+    rows = []
+
+    def timeit(step, n=3):
+        step()
+        ts = []
+        for _ in range(n):
+            t0 = time.perf_counter()
+            step()
+            ts.append(time.perf_counter() - t0)
+        return sorted(ts)[len(ts) // 2]
+
+    g = torch.Generator().manual_seed(1234)
+    D, E, H, K, T = 512, 8, 128, 2, 4096
+    wg = (torch.randn(E, D, generator=g) * D ** -0.5).requires_grad_(True)
+    keys = (torch.randn(E, D, H, generator=g) * D ** -0.5).requires_grad_(True)
+    values = (torch.randn(E, H, D, generator=g) * (E * H) ** -0.5).requires_grad_(True)
+    x = torch.randn(8, 512, D, generator=g).requires_grad_(True)
+    dy = torch.randn(8, 512, D, generator=g)
+    for comp in (False, True):
+        def step():
+            for t in (wg, keys, values, x):
+                t.grad = None
+            out, regs, _ = opr.competesmoe_forward(x, wg, keys, values, K, pretrain_args(), comp)
+            ((out * dy).sum() + sum(regs.values())).backward()
+        dt = timeit(step)
+        rows.append(f"| C1 pretrain layer d=512 E=8 K=2 H=128 T=8x512, fp32, CPU oracle port ({cores} threads) | host | "
+                    f"{'competition' if comp else 'router'} | {dt * 1e3:.1f} | {T / dt:,.0f} | - | - | - | - |")
+    D, F_, E, K, T = 1152, 4304, 4, 2, 640
+    exps = []
+    for _ in range(E):
+        exps.append({"kind": "mlp", "act": "gelu_tanh",
+                     "w1": (torch.randn(F_, D, generator=g) * 0.02).requires_grad_(True), "b1": torch.zeros(F_, requires_grad=True),
+                     "w2": (torch.randn(D, F_, generator=g) * 0.02).requires_grad_(True), "b2": torch.zeros(D, requires_grad=True)})
+    gw = (torch.randn(E, D, generator=g) * 0.02).requires_grad_(True)
+    x = torch.randn(1, T, D, generator=g).requires_grad_(True)
+    dy = torch.randn(1, T, D, generator=g)
+
+    def step2():
+        out, aux, _, _, _ = om.competesmoe_forward(x, gw, exps, K, D, om.default_args(), False)
+        ((out * dy).sum() + aux).backward()
+    dt = timeit(step2, 2)
+    rows.append(f"| C5/C2' SigLIP MoE MLP d=1152 F=4304 E=4 K=2, fp32, CPU oracle port ({cores} threads), {T} of 12800 tokens | host | "
+                f"router | {dt * 1e3:.1f} | {T / dt:,.0f} | - | - | - | - |")
+    return rows
+
+
 def cases(world):
     cs = [Case("C1 pretrain layer d=512 E=8 K=2 H=128 T=8x512 (fp32 in, bf16 autocast)", "pretrain", 4096, 512, 128, 8, 2)]
     for E, K in ((8, 2), (16, 2), (32, 2), (64, 2), (64, 8)):
@@ -221,6 +276,7 @@ def main():
     ap.add_argument("--only", default="")
     ap.add_argument("--profile", action="store_true", help="print the per-kernel timeline (torch.profiler) of each selected case")
     ap.add_argument("--graphs", action="store_true", help="enable the layers' CUDA-graph mode (single-GPU cases)")
+    ap.add_argument("--cpu-baseline", action="store_true", help="append the CPU oracle port timed on this box (C1, C2' sample)")
     a = ap.parse_args()
     global GRAPHS
     GRAPHS = a.graphs
@@ -267,6 +323,9 @@ def main():
                 print(f"| {case.name} | {world} (EP{p}) | {'competition' if comp else 'router'} | {ms:.3f} | "
                       f"{case.T * world / (ms * 1e-3):,.0f} | {tf:.1f} | {100 * tf / PEAK_TF:.1f} | "
                       f"{gbs:.0f} | {100 * gbs / PEAK_GBS:.1f} |")
+        if a.cpu_baseline and world == 1:
+            for line in cpu_baseline_rows():
+                print(line)
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
