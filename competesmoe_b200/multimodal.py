@@ -104,7 +104,46 @@ class MoeLayer(nn.Module):
         per-kernel launch gaps of the ~40-launch step.  Everything else (eval, no-grad, autocast, expert parallelism,
         return_id_experts) takes the normal path.  Parameters may change value between calls, not storage."""
         self._graphs = {} if enabled else None
+        # layers without their own graph dispatch (the sibling routers) get it through an instance-level wrapper
+        if not hasattr(type(self), "_forward_impl"):
+            if enabled and "_eager_forward" not in self.__dict__:
+                self._eager_forward = self.forward
+                self.forward = self._wrapped_graph_forward
+            elif not enabled and "_eager_forward" in self.__dict__:
+                self.forward = self._eager_forward
+                del self._eager_forward
         return self
+
+    _inplace_params = ()     # parameters a forward call rescales in place (xmoe / smoe_perturbed: expert_embeddings)
+
+    def _wrapped_graph_forward(self, x, return_id_experts=False, is_vision=False):
+        if not self._graph_eligible(x, return_id_experts):
+            return self._eager_forward(x, return_id_experts, is_vision)
+        self._stacked_weights()
+        params = tuple(p for p in self.parameters() if p.requires_grad)
+        key = (bool(is_vision), tuple(x.shape), x.dtype, tuple(p.data_ptr() for p in params))
+        entry = self._graphs.get(key)
+        if entry is None:
+            names: List[str] = []
+            # capture runs the forward several times: put back what it rescales so that the first replay is call no. 1
+            keep = {n: getattr(self, n).detach().clone() for n in self._inplace_params}
+
+            def fn(xx, *_params):
+                out, aux, _, info = self._eager_forward(xx, False, is_vision)
+                names[:] = sorted(info)
+                return (out, aux) + tuple(info[k] for k in names)
+
+            sample = x.detach().clone().requires_grad_(True)
+            graphed = torch.cuda.make_graphed_callables(fn, (sample,) + params, allow_unused_input=True)
+            with torch.no_grad():
+                for n, v in keep.items():
+                    getattr(self, n).copy_(v)
+            entry = (graphed, list(names), self.last_routing)
+            self._graphs[key] = entry
+        graphed, names, routing = entry
+        res = graphed(x, *params)
+        self.last_routing = routing
+        return res[0], res[1], None, dict(zip(names, res[2:]))
 
     def _graph_eligible(self, x, return_id_experts) -> bool:
         return (self._graphs is not None and self._ep is None and self.training and x.is_cuda and x.requires_grad

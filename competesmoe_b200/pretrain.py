@@ -210,8 +210,8 @@ class MoE(LoggingLayer, RegularizedLayer, OncePerIterLayer, torch.nn.Module):
 
     # ---- CUDA graphs (no counterpart in the reference, whose cvmm path re-tunes and syncs on the host)
     _graphs = None
-    _graphable = True            # False for layers that modify a parameter in place inside forward (xmoe, smoe_perturbed)
-    _graph_skip = ()             # parameters the forward never reads (they cannot be inputs of the captured backward)
+    _graphable = True
+    _inplace_params = ()         # parameters a forward call rescales in place (xmoe / smoe_perturbed: expert_embeddings)
 
     def enable_cuda_graphs(self, enabled: bool = True):
         """Opt in: training-mode calls with a CUDA input that requires grad are replayed from captured CUDA graphs (one
@@ -240,7 +240,7 @@ class MoE(LoggingLayer, RegularizedLayer, OncePerIterLayer, torch.nn.Module):
         id_layer = kwargs.get("id_layer")
         probe = getattr(self, "_is_competition_step", None)
         branch = bool(probe(x, id_layer)) if probe is not None else False
-        params = tuple(p for n, p in self.named_parameters() if p.requires_grad and n not in self._graph_skip)
+        params = tuple(p for p in self.parameters() if p.requires_grad)
         reg_on = self.reg_enabled
         key = (branch, id_layer, tuple(x.shape), x.dtype, autocast, adt, reg_on,
                tuple(p.data_ptr() for p in params))
@@ -248,6 +248,8 @@ class MoE(LoggingLayer, RegularizedLayer, OncePerIterLayer, torch.nn.Module):
         if entry is None:
             names = []
             keep = (self.layer, getattr(self, "nb_diver", 0))
+            # capture runs the forward several times: put back what it rescales so that the first replay is call no. 1
+            keep_p = {n: getattr(self, n).detach().clone() for n in self._inplace_params}
 
             def fn(xx, *_params):
                 collected = []
@@ -263,8 +265,11 @@ class MoE(LoggingLayer, RegularizedLayer, OncePerIterLayer, torch.nn.Module):
 
             sample = x.detach().clone().requires_grad_(True)
             with torch.autocast("cuda", dtype=adt, enabled=autocast, cache_enabled=False):
-                graphed = torch.cuda.make_graphed_callables(fn, (sample,) + params)
+                graphed = torch.cuda.make_graphed_callables(fn, (sample,) + params, allow_unused_input=True)
             self.layer, self.nb_diver = keep
+            with torch.no_grad():
+                for n, v in keep_p.items():
+                    getattr(self, n).copy_(v)
             entry = (graphed, list(names), self.last_routing)
             self._graphs[key] = entry
         graphed, names, routing = entry

@@ -68,7 +68,7 @@ class SMoEUTNorm(_SiblingBase):
 class _CosineGate(_SiblingBase):
     """Shared body of xmoe.py:37-197 and smoe_perturbed.py:39-197 (cosine gate over an E/2-dimensional projection)."""
     theta = 0.0
-    _graphable = False           # forward rescales expert_embeddings in place
+    _inplace_params = ("expert_embeddings",)   # rescaled by every forward call (restored after graph capture)
 
     def _init_cosine(self, sel_bias: bool):
         self.reduction_dim = int(self.n_experts / 2)
@@ -165,7 +165,6 @@ class DeepSeekV2(_SharedExpert):
 class DeepSeekV3(_SharedExpert):
     """reference: deepseekv3.py:38-190 -- top-k of sigmoid(logits) divided by their sum (+1e-20), scaling factor 1;
     `e_score_correction_bias` exists as a parameter and is not used by the forward."""
-    _graph_skip = ("e_score_correction_bias",)
 
     def __init__(self, dmodel, *a, weight_scale: float = 1.0, bias: bool = False, **kw):
         super().__init__(dmodel, *a, weight_scale=weight_scale, bias=bias, **kw)

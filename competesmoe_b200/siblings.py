@@ -80,6 +80,7 @@ class _CosineGateLayer(MoeLayer):
     (perturbed) cosine similarity with per-expert embeddings of norm 1.5, softmax at temperature 0.3, top-k, softmax
     over the kept probabilities."""
     theta = 0.0
+    _inplace_params = ("expert_embeddings",)
 
     def _init_cosine_gate(self, in_embed_dim, num_of_experts):
         self.register_parameter("expert_embeddings", nn.Parameter(torch.empty(num_of_experts, int(num_of_experts / 2))))

@@ -75,8 +75,8 @@ def test_pretrain_sibling_matches_reference_golden(name):
 
 @pytest.mark.parametrize("name", ["ptsib_smoe_f32", "ptsib_deepseekv3_f32", "ptsib_xmoe_f32"])
 def test_pretrain_sibling_cuda_graph_mode_matches_eager(name):
-    """enable_cuda_graphs() on the sibling routers: bit-identical to the eager call (xmoe rescales a parameter in place
-    inside forward, is marked not graphable and must silently take the eager path)."""
+    """enable_cuda_graphs() on the sibling routers: bit-identical to the eager call, including xmoe whose forward
+    rescales `expert_embeddings` in place (the capture's own forward runs are undone)."""
     import competesmoe_b200.pretrain_siblings  # noqa: F401
     from competesmoe_b200.pretrain import get_moe
     fx = load_golden(name)
@@ -96,7 +96,7 @@ def test_pretrain_sibling_cuda_graph_mode_matches_eager(name):
             layer.enable_cuda_graphs()
         layers.append(layer)
     g = torch.Generator().manual_seed(5)
-    for trial in range(2):
+    for trial in range(3):
         x_cpu = fx["x"] if trial == 0 else torch.randn(fx["x"].shape, generator=g)
         res = []
         for layer in layers:
@@ -113,4 +113,6 @@ def test_pretrain_sibling_cuda_graph_mode_matches_eager(name):
         assert torch.equal(o0, o1) and torch.equal(dx0, dx1)
         assert set(r0) == set(r1) and all(torch.equal(r0[k], r1[k]) for k in r0)
         assert set(g0) == set(g1) and all(torch.equal(g0[k], g1[k]) for k in g0)
-    assert len(layers[1]._graphs) == (0 if "xmoe" in name else 1)
+    assert len(layers[1]._graphs) == 1
+    if hasattr(layers[0], "expert_embeddings"):
+        assert torch.equal(layers[0].expert_embeddings, layers[1].expert_embeddings)
