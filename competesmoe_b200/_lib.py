@@ -62,6 +62,7 @@ _SIGNATURES = {
     "csmoe_act_bwd": (i32, [vp, vp, i32, i64, i64, i64, i64, i32, vp, vp, vp]),
     "csmoe_bias_grad_workspace_bytes": (i64, [i32, i32]),
     "csmoe_bias_grad": (i32, [vp, i32, i64, i32, i32, vp, i32, i64, vp, i32, vp, vp]),
+    "csmoe_act_bwd_bias": (i32, [vp, vp, i32, i64, i64, i32, i32, vp, i32, i64, i32, vp, vp, i32, vp, vp]),
     "csmoe_cast_f32_bf16": (i32, [vp, vp, i64, vp]),
     "csmoe_affinity_fwd": (i32, [vp, i32, i32, i64, i64, i32, i32, vp, vp]),
     "csmoe_affinity_from_rowsum": (i32, [vp, i32, i32, i64, i64, i32, i32, vp, vp]),

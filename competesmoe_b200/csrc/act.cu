@@ -78,10 +78,14 @@ act_bwd_kernel(const T* __restrict__ z, const T* __restrict__ dh, long long rows
 // dbias[e][n]: grid (ceil(n / 256), E, row splits); block = 32 column-vectors x 8 row lanes.  Each split reduces a
 // contiguous share of the expert's rows; with more than one split the partial sums go to `partial`
 // [splits, E, n] (fp32) and bias_grad_finish_kernel adds them in split order (deterministic, no atomics).
-template <typename T, typename OutT>
+// FUSED: g is dh, and the kernel first forms dz = dh * act'(z) (stored to `dz`, rounded to T) and sums that: the
+// activation backward and the bias gradient of the first projection in one pass over dh / z (the separate bias_grad
+// pass re-read the [rows, F] gradient it had just written: 229 MB at the SigLIP shape).
+template <typename T, typename OutT, bool FUSED>
 __global__ void __launch_bounds__(256)
 bias_grad_kernel(const T* __restrict__ g, long long ldg, int n, const int32_t* __restrict__ pad_offsets, int dense,
-                 long long dense_rows, OutT* __restrict__ dbias, float* __restrict__ partial) {
+                 long long dense_rows, OutT* __restrict__ dbias, float* __restrict__ partial,
+                 const T* __restrict__ z = nullptr, long long ldz = 0, int act = 0, T* __restrict__ dz = nullptr) {
   __shared__ float red[8][32][8];
   const int e = blockIdx.y;
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
@@ -105,6 +109,14 @@ bias_grad_kernel(const T* __restrict__ g, long long ldg, int n, const int32_t* _
     for (long long r = r0 + ry; r < r1; r += 8) {
       float v[8];
       load8(g + r * ldg + col, v);
+      if (FUSED) {
+        float zz[8];
+        load8(z + r * ldz + col, zz);
+        act_grad_vec<8>(v, zz, act, sizeof(T) == 2);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = round_as(v[j], static_cast<const T*>(nullptr));
+        store8(dz + r * ldz + col, v);
+      }
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] += v[j];
     }
@@ -216,13 +228,15 @@ extern "C" int64_t csmoe_bias_grad_workspace_bytes(int32_t n, int32_t num_expert
   return static_cast<int64_t>(kBiasGradSplits) * num_experts * n * static_cast<int64_t>(sizeof(float));
 }
 
-extern "C" int csmoe_bias_grad(const void* g, int32_t dtype, int64_t ldg, int32_t n, int32_t num_experts,
-                               const int32_t* pad_offsets, int32_t dense, int64_t dense_rows, void* dbias,
-                               int32_t out_dtype, void* workspace, void* stream_) {
-  CSMOE_CHECK_ARG(g && dbias, "csmoe_bias_grad: NULL pointer");
-  CSMOE_CHECK_ARG(dense || pad_offsets, "csmoe_bias_grad: pad_offsets required unless dense");
-  CSMOE_CHECK_ARG(n > 0 && n % 8 == 0 && ldg % 8 == 0, "csmoe_bias_grad: n/ldg must be multiples of 8");
-  CSMOE_CHECK_ARG(num_experts >= 1 && num_experts <= 65535, "csmoe_bias_grad: bad num_experts");
+namespace {
+// Shared launcher of csmoe_bias_grad (z == nullptr) and csmoe_act_bwd_bias (z, dz given).
+int bias_grad_launch(const char* what, const void* g, int32_t dtype, int64_t ldg, int32_t n, int32_t num_experts,
+                     const int32_t* pad_offsets, int32_t dense, int64_t dense_rows, void* dbias, int32_t out_dtype,
+                     void* workspace, const void* z, int64_t ldz, int32_t act, void* dz, void* stream_) {
+  CSMOE_CHECK_ARG(g && dbias, "%s: NULL pointer", what);
+  CSMOE_CHECK_ARG(dense || pad_offsets, "%s: pad_offsets required unless dense", what);
+  CSMOE_CHECK_ARG(n > 0 && n % 8 == 0 && ldg % 8 == 0 && ldz % 8 == 0, "%s: n/ld must be multiples of 8", what);
+  CSMOE_CHECK_ARG(num_experts >= 1 && num_experts <= 65535, "%s: bad num_experts", what);
   cudaStream_t stream = as_stream(stream_);
   // few experts x few column blocks would leave most SMs idle: split each expert's rows when a workspace is given
   const int col_blocks = (n + 255) / 256;
@@ -231,9 +245,14 @@ extern "C" int csmoe_bias_grad(const void* g, int32_t dtype, int64_t ldg, int32_
   float* partial = static_cast<float*>(workspace);
   const long long en = static_cast<long long>(num_experts) * n;
   const unsigned fin_grid = static_cast<unsigned>((en / 8 + 255) / 256);
-#define LAUNCH_BG(T, O)                                                                                             \
-  bias_grad_kernel<T, O><<<grid, 256, 0, stream>>>(static_cast<const T*>(g), ldg, n, pad_offsets, dense, dense_rows, \
-                                                   static_cast<O*>(dbias), partial);                                \
+#define LAUNCH_BG(T, O)                                                                                               \
+  if (z != nullptr)                                                                                                   \
+    bias_grad_kernel<T, O, true><<<grid, 256, 0, stream>>>(static_cast<const T*>(g), ldg, n, pad_offsets, dense,      \
+                                                           dense_rows, static_cast<O*>(dbias), partial,              \
+                                                           static_cast<const T*>(z), ldz, act, static_cast<T*>(dz)); \
+  else                                                                                                                \
+    bias_grad_kernel<T, O, false><<<grid, 256, 0, stream>>>(static_cast<const T*>(g), ldg, n, pad_offsets, dense,     \
+                                                            dense_rows, static_cast<O*>(dbias), partial);            \
   if (splits > 1) bias_grad_finish_kernel<O><<<fin_grid, 256, 0, stream>>>(partial, splits, en, static_cast<O*>(dbias))
   if (dtype == CSMOE_BF16 && out_dtype == CSMOE_BF16) {
     LAUNCH_BG(__nv_bfloat16, __nv_bfloat16);
@@ -242,11 +261,29 @@ extern "C" int csmoe_bias_grad(const void* g, int32_t dtype, int64_t ldg, int32_
   } else if (dtype == CSMOE_F32 && out_dtype == CSMOE_F32) {
     LAUNCH_BG(float, float);
   } else {
-    CSMOE_CHECK_ARG(false, "csmoe_bias_grad: unsupported dtype combination %d -> %d", dtype, out_dtype);
+    CSMOE_CHECK_ARG(false, "%s: unsupported dtype combination %d -> %d", what, dtype, out_dtype);
   }
 #undef LAUNCH_BG
   CSMOE_CHECK_LAUNCH();
   return CSMOE_OK;
+}
+}  // namespace
+
+extern "C" int csmoe_bias_grad(const void* g, int32_t dtype, int64_t ldg, int32_t n, int32_t num_experts,
+                               const int32_t* pad_offsets, int32_t dense, int64_t dense_rows, void* dbias,
+                               int32_t out_dtype, void* workspace, void* stream_) {
+  return bias_grad_launch("csmoe_bias_grad", g, dtype, ldg, n, num_experts, pad_offsets, dense, dense_rows, dbias, out_dtype,
+                          workspace, nullptr, 0, 0, nullptr, stream_);
+}
+
+extern "C" int csmoe_act_bwd_bias(const void* z, const void* dh, int32_t dtype, int64_t ldz, int64_t ldh, int32_t n,
+                                  int32_t num_experts, const int32_t* pad_offsets, int32_t dense, int64_t dense_rows,
+                                  int32_t act, void* dz, void* dbias, int32_t out_dtype, void* workspace, void* stream_) {
+  CSMOE_CHECK_ARG(z && dz, "csmoe_act_bwd_bias: NULL pointer");
+  CSMOE_CHECK_ARG(act == CSMOE_ACT_RELU || act == CSMOE_ACT_GELU || act == CSMOE_ACT_GELU_TANH || act == CSMOE_ACT_SILU,
+                  "csmoe_act_bwd_bias: activation %d has no elementwise backward here", act);
+  return bias_grad_launch("csmoe_act_bwd_bias", dh, dtype, ldh, n, num_experts, pad_offsets, dense, dense_rows, dbias,
+                          out_dtype, workspace, z, ldz, act, dz, stream_);
 }
 
 extern "C" int csmoe_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream_) {

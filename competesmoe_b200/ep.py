@@ -27,7 +27,7 @@ from torch.autograd.function import once_differentiable
 
 from . import _lib, ops
 from ._lib import ROW_TILE, check
-from .functional import FFNSpec, _bf16, _ffn_first, _FUSE_BWD
+from .functional import FFNSpec, _bf16, _ffn_first, _FUSE_ACT_BIAS, _FUSE_BWD
 
 MAX_EXPERTS = 1024
 _CTRL_BYTES = 4096 + 16 * MAX_EXPERTS * 4   # flags, epoch, counts_all[P<=16][E<=1024]
@@ -336,12 +336,17 @@ class EPSparseFFNFn(Function):
             dw2 = ops.gemm_reduce(h, dyp, El, route=lr, out_dtype=w2.dtype)
         else:
             dw2 = ops.gemm_reduce(dyp, h, El, route=lr, out_dtype=w2.dtype)
+        db1 = None
         if _FUSE_BWD:
             dz = ops.gemm_rows(dyp, w2b, w_is_kn=not spec.kn_layout, route=lr, act_bwd=spec.act, aux=z)
+            db1 = ops.bias_grad(dz, El, route=lr, out_dtype=w1.dtype) if ctx.has_b[0] else None
         else:
             dh = ops.gemm_rows(dyp, w2b, w_is_kn=not spec.kn_layout, route=lr)
-            dz = dh if spec.act == ops.ACT_NONE else ops.act_bwd(z, dh, spec.act, lr)
-        db1 = ops.bias_grad(dz, El, route=lr, out_dtype=w1.dtype) if ctx.has_b[0] else None
+            if ctx.has_b[0] and _FUSE_ACT_BIAS and spec.act not in (ops.ACT_NONE, ops.ACT_SILU_GLU):
+                dz, db1 = ops.act_bwd_bias(z, dh, spec.act, El, route=lr, out_dtype=w1.dtype)
+            else:
+                dz = dh if spec.act == ops.ACT_NONE else ops.act_bwd(z, dh, spec.act, lr)
+                db1 = ops.bias_grad(dz, El, route=lr, out_dtype=w1.dtype) if ctx.has_b[0] else None
         if spec.kn_layout:
             dw1 = ops.gemm_reduce(xp, dz, El, route=lr, out_dtype=w1.dtype)
         else:

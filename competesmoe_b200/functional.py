@@ -31,6 +31,8 @@ from ._lib import ROW_TILE
 #   (0.57 ms vs 0.33 + 0.17 ms) -> off by default until the epilogue I/O is staged through shared memory.
 _FUSE_FWD = os.environ.get("CSMOE_FUSE_EPILOGUE_FWD", "1") != "0"
 _FUSE_BWD = os.environ.get("CSMOE_FUSE_EPILOGUE_BWD", "0") != "0"
+# activation backward + bias gradient of the first projection in one kernel (csmoe_act_bwd_bias)
+_FUSE_ACT_BIAS = os.environ.get("CSMOE_FUSE_ACT_BIAS", "1") != "0"
 #   competition score (mean softplus of the dense outputs) reduced in the down projection's epilogue: "1" always,
 #   "0" never (stand-alone csmoe_affinity_fwd re-reads y), "auto" = only where that GEMM's main loop is long enough to
 #   hide the extra epilogue math (contraction >= 1024; the sigma-MoE shapes with H = 128 are epilogue bound).
@@ -153,12 +155,19 @@ class SparseFFNFn(Function):
         else:
             dw2 = ops.gemm_reduce(dyp, h, E, route=route, out_dtype=w2.dtype)  # [E, Dout, F]
         # dgrad of the second projection with the activation backward fused into its epilogue: dz = (dy W2) * act'(z)
+        fused_db1 = False
         if _FUSE_BWD:
             dz = ops.gemm_rows(dyp, w2b, w_is_kn=not spec.kn_layout, route=route, act_bwd=spec.act, aux=z)
         else:
             dh = ops.gemm_rows(dyp, w2b, w_is_kn=not spec.kn_layout, route=route)
-            dz = dh if spec.act == ops.ACT_NONE else ops.act_bwd(z, dh, spec.act, route)
-        db1 = ops.bias_grad(dz, E, route=route, out_dtype=w1.dtype) if ctx.has_b[0] else None
+            if ctx.has_b[0] and _FUSE_ACT_BIAS and spec.act not in (ops.ACT_NONE, ops.ACT_SILU_GLU):
+                # activation backward + bias gradient in one pass over dh / z
+                dz, db1 = ops.act_bwd_bias(z, dh, spec.act, E, route=route, out_dtype=w1.dtype)
+                fused_db1 = True
+            else:
+                dz = dh if spec.act == ops.ACT_NONE else ops.act_bwd(z, dh, spec.act, route)
+        if not fused_db1:
+            db1 = ops.bias_grad(dz, E, route=route, out_dtype=w1.dtype) if ctx.has_b[0] else None
         if spec.kn_layout:
             dw1 = ops.gemm_reduce(xp, dz, E, route=route, out_dtype=w1.dtype)  # [E, D, H]
         else:
@@ -213,13 +222,19 @@ class DenseFFNFn(Function):
             dw2 = ops.gemm_reduce(h, dy, E, dense_rows=t_pad, a_expert_rows=t_pad, b_expert_rows=t_pad, out_dtype=w2.dtype)
         else:
             dw2 = ops.gemm_reduce(dy, h, E, dense_rows=t_pad, a_expert_rows=t_pad, b_expert_rows=t_pad, out_dtype=w2.dtype)
+        fused_db1 = False
         if _FUSE_BWD:
             dz = ops.gemm_rows(dy, w2b, w_is_kn=not spec.kn_layout, dense_rows=t_pad, a_expert_rows=t_pad,
                                act_bwd=spec.act, aux=z)
         else:
             dh = ops.gemm_rows(dy, w2b, w_is_kn=not spec.kn_layout, dense_rows=t_pad, a_expert_rows=t_pad)
-            dz = dh if spec.act == ops.ACT_NONE else ops.act_bwd(z, dh, spec.act)
-        db1 = ops.bias_grad(dz, E, dense_rows=t_pad, out_dtype=w1.dtype) if ctx.has_b[0] else None
+            if ctx.has_b[0] and _FUSE_ACT_BIAS and spec.act not in (ops.ACT_NONE, ops.ACT_SILU_GLU):
+                dz, db1 = ops.act_bwd_bias(z, dh, spec.act, E, dense_rows=t_pad, out_dtype=w1.dtype)
+                fused_db1 = True
+            else:
+                dz = dh if spec.act == ops.ACT_NONE else ops.act_bwd(z, dh, spec.act)
+        if not fused_db1:
+            db1 = ops.bias_grad(dz, E, dense_rows=t_pad, out_dtype=w1.dtype) if ctx.has_b[0] else None
         if spec.kn_layout:
             dw1 = ops.gemm_reduce(xb, dz, E, dense_rows=t_pad, a_expert_rows=0, b_expert_rows=t_pad, out_dtype=w1.dtype)
         else:

@@ -18,7 +18,7 @@ from ._lib import (ACT_GELU, ACT_GELU_TANH, ACT_NONE, ACT_RELU, ACT_SILU, ACT_SI
 
 __all__ = [
     "Route", "route_build", "router_fwd", "topk_renorm", "gather_rows", "combine_fwd", "combine_bwd_w",
-    "scatter_reduce", "gemm_rows", "gemm_reduce", "act_fwd", "act_bwd", "bias_grad", "cast_bf16", "affinity_fwd",
+    "scatter_reduce", "gemm_rows", "gemm_reduce", "act_fwd", "act_bwd", "act_bwd_bias", "bias_grad", "cast_bf16", "affinity_fwd",
     "affinity_bwd", "affinity_from_rowsum", "diversity_fwd", "compete_bwd", "ACT_NONE", "ACT_RELU", "ACT_GELU", "ACT_GELU_TANH", "ACT_SILU", "ACT_SILU_GLU",
 ]
 
@@ -425,6 +425,24 @@ def bias_grad(g: torch.Tensor, num_experts: int, *, route: Optional[Route] = Non
     _call("csmoe_bias_grad", _p(g), _dt(g), g.stride(0), n, num_experts, po, 1 if dense_rows else 0, dense_rows, _p(db),
           _dt(db), _p(ws), _stream(), kernels=2)
     return db
+
+
+def act_bwd_bias(z: torch.Tensor, dh: torch.Tensor, act: int, num_experts: int, *, route: Optional[Route] = None,
+                 dense_rows: int = 0, out_dtype: Optional[torch.dtype] = None):
+    """(dz, dbias): dz = dh * act'(z) and its per-expert column sums in one pass (activation backward + bias gradient of
+    the first projection)."""
+    _cuda(z, dh)
+    assert z.dtype == dh.dtype and z.shape == dh.shape and z.stride(1) == 1 and dh.stride(1) == 1
+    n = z.shape[1]
+    out_dtype = out_dtype or z.dtype
+    dz = torch.empty_like(z)
+    db = torch.empty(num_experts, n, dtype=out_dtype, device=z.device)
+    po = None if dense_rows else _p(route.pad_offsets)
+    ws = torch.empty(int(_lib.load().csmoe_bias_grad_workspace_bytes(n, num_experts)) // 4, dtype=torch.float32,
+                     device=z.device)
+    _call("csmoe_act_bwd_bias", _p(z), _p(dh), _dt(z), z.stride(0), dh.stride(0), n, num_experts, po,
+          1 if dense_rows else 0, dense_rows, act, _p(dz), _p(db), _dt(db), _p(ws), _stream(), kernels=2)
+    return dz, db
 
 
 def cast_bf16(src: torch.Tensor) -> torch.Tensor:

@@ -211,6 +211,13 @@ int64_t csmoe_bias_grad_workspace_bytes(int32_t n, int32_t num_experts);
 int csmoe_bias_grad(const void* g, int32_t dtype, int64_t ldg, int32_t n, int32_t num_experts,
                     const int32_t* pad_offsets, int32_t dense, int64_t dense_rows, void* dbias, int32_t out_dtype,
                     void* workspace, void* stream);
+/* Activation backward and bias gradient of the first projection in one pass: dz[r, :] = dh[r, :] * act'(z[r, :])
+ * (rounded to the activation dtype, stored) and dbias[e, :] = sum over expert e's rows of dz -- the two steps autograd
+ * runs after `expert.fc1` / `experts[i][0]` (moe_model/model/moe/moe.py:196-204 backward).  Same row ranges, workspace
+ * and determinism as csmoe_bias_grad; act = RELU / GELU / GELU_TANH / SILU. */
+int csmoe_act_bwd_bias(const void* z, const void* dh, int32_t dtype, int64_t ldz, int64_t ldh, int32_t n,
+                       int32_t num_experts, const int32_t* pad_offsets, int32_t dense, int64_t dense_rows, int32_t act,
+                       void* dz, void* dbias, int32_t out_dtype, void* workspace, void* stream);
 /* dst = (bf16) src, n elements. */
 int csmoe_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream);
 

@@ -441,3 +441,30 @@ def test_gemm_epilogue_score_matches_affinity_kernel(ops, eager_bf16, E, T, n, k
     tol = 2 ** -8 if eager_bf16 else 1e-5           # one bf16 ulp when the result is rounded to bf16
     assert float((aff - ref_kernel).abs().max() / ref_kernel.abs().max()) <= tol
     assert float((aff - ref).abs().max() / ref.abs().max()) <= tol
+
+
+@pytest.mark.parametrize("act", ["relu", "gelu", "gelu_tanh", "silu"])
+@pytest.mark.parametrize("dense", [False, True])
+def test_act_bwd_bias_matches_separate_kernels(ops, act, dense):
+    """csmoe_act_bwd_bias = csmoe_act_bwd followed by csmoe_bias_grad, bit for bit (dz is rounded before it is summed)."""
+    code = {"relu": ops.ACT_RELU, "gelu": ops.ACT_GELU, "gelu_tanh": ops.ACT_GELU_TANH, "silu": ops.ACT_SILU}[act]
+    torch.manual_seed(5)
+    E, n = 4, 520
+    if dense:
+        rows, route, kw = E * 256, None, dict(dense_rows=256)
+    else:
+        sel = torch.stack([torch.randperm(E)[:2] for _ in range(333)]).int().to(DEV)
+        route = ops.route_build(sel, E)
+        rows, kw = route.row_cap, dict(route=route)
+    z = torch.randn(rows, n, device=DEV, dtype=torch.bfloat16)
+    dh = torch.randn(rows, n, device=DEV, dtype=torch.bfloat16)
+    dz_ref = ops.act_bwd(z, dh, code, route)
+    db_ref = ops.bias_grad(dz_ref, E, **kw)
+    dz, db = ops.act_bwd_bias(z, dh, code, E, **kw)
+    if dense:
+        assert torch.equal(dz, dz_ref)
+    else:
+        po = route.pad_offsets.cpu().tolist()
+        for e in range(E):
+            assert torch.equal(dz[po[e]:po[e + 1]], dz_ref[po[e]:po[e + 1]])
+    assert torch.equal(db, db_ref)
