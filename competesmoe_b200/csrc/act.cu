@@ -43,12 +43,16 @@ act_fwd_kernel(const T* __restrict__ z, long long rows, long long cols, long lon
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 act_bwd_kernel(const T* __restrict__ z, const T* __restrict__ dh, long long rows, long long cols, long long ldz,
-               long long ldh, int act, T* __restrict__ dz, const int32_t* __restrict__ tile_expert) {
-  const long long vec_per_row = cols / 8;
-  const long long total = rows * vec_per_row;
-  for (long long i = static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * kThreads) {
-    const long long r = i / vec_per_row, c = (i % vec_per_row) * 8;
+               long long ldh, int act, T* __restrict__ dz, const int32_t* __restrict__ tile_expert, int tpr_log2) {
+  // grid.x x block: column vectors of a row, grid.y: rows (strided) -- no 64-bit division per vector, and the saved
+  // pre-activation / incoming gradient of one row are read as whole contiguous segments
+  // (`tpr_log2`: threads per row of the block, a power of two <= 256, so narrow matrices keep every thread busy)
+  const int tpr = 1 << tpr_log2;
+  const long long c = (static_cast<long long>(blockIdx.x) * tpr + (threadIdx.x & (tpr - 1))) * 8;
+  if (c >= cols) return;
+  const int rpb = kThreads >> tpr_log2;
+  for (long long r = static_cast<long long>(blockIdx.y) * rpb + (threadIdx.x >> tpr_log2); r < rows;
+       r += static_cast<long long>(gridDim.y) * rpb) {
     if (tile_expert != nullptr && __ldg(tile_expert + (r >> 7)) < 0) continue;
     float v[8], g[8], o[8];
     load8(dh + r * ldh + c, g);
@@ -208,14 +212,21 @@ extern "C" int csmoe_act_bwd(const void* z, const void* dh, int32_t dtype, int64
   CSMOE_CHECK_ARG(act >= CSMOE_ACT_NONE && act <= CSMOE_ACT_SILU_GLU, "csmoe_act_bwd: bad act %d", act);
   if (rows == 0) return CSMOE_OK;
   cudaStream_t stream = as_stream(stream_);
-  const unsigned grid = flat_grid(rows * (cols / 8));
+  int tpr_log2 = 8;
+  while (tpr_log2 > 0 && (1 << (tpr_log2 - 1)) >= cols / 8) --tpr_log2;
+  const int tpr = 1 << tpr_log2, rpb = kThreads >> tpr_log2;
+  const unsigned gx = static_cast<unsigned>((cols / 8 + tpr - 1) / tpr);
+  const long long row_blocks = (rows + rpb - 1) / rpb;
+  const long long want_y = (148LL * 16 + gx - 1) / gx;     // ~16 CTAs per SM in flight
+  const dim3 grid(gx, static_cast<unsigned>(row_blocks < want_y ? row_blocks : want_y));
   if (dtype == CSMOE_BF16) {
     act_bwd_kernel<__nv_bfloat16><<<grid, kThreads, 0, stream>>>(static_cast<const __nv_bfloat16*>(z),
                                                                  static_cast<const __nv_bfloat16*>(dh), rows, cols, ldz,
-                                                                 ldh, act, static_cast<__nv_bfloat16*>(dz), tile_expert);
+                                                                 ldh, act, static_cast<__nv_bfloat16*>(dz), tile_expert, tpr_log2);
   } else if (dtype == CSMOE_F32) {
     act_bwd_kernel<float><<<grid, kThreads, 0, stream>>>(static_cast<const float*>(z), static_cast<const float*>(dh),
-                                                         rows, cols, ldz, ldh, act, static_cast<float*>(dz), tile_expert);
+                                                         rows, cols, ldz, ldh, act, static_cast<float*>(dz), tile_expert,
+                                                         tpr_log2);
   } else {
     CSMOE_CHECK_ARG(false, "csmoe_act_bwd: unsupported dtype %d", dtype);
   }
