@@ -8,9 +8,29 @@ picks one per call exactly like the reference's `prob_flips[...] == 1` test.
 """
 from __future__ import annotations
 
+import contextlib
+import gc
 from typing import Dict, Optional, Tuple
 
 import torch
+
+
+@contextlib.contextmanager
+def capture_guard():
+    """Around every graph capture: collect garbage first and keep the cyclic collector off until the capture has ended.
+    A layer in graph mode is part of a reference cycle (layer -> captured callable -> closure -> layer), so an *old*
+    layer's CUDA graphs and their private memory pool are destroyed whenever the collector happens to run -- and a
+    cudaGraphExecDestroy / cudaFree in the middle of another capture invalidates that capture
+    (cudaErrorStreamCaptureInvalidated; seen with several graph-mode layers created one after the other)."""
+    gc.collect()
+    torch.cuda.synchronize()
+    was_enabled = gc.isenabled()
+    gc.disable()
+    try:
+        yield
+    finally:
+        if was_enabled:
+            gc.enable()
 
 
 class GraphedStep:
@@ -58,7 +78,7 @@ class GraphedStep:
             p.grad = None
         self.x.grad = None
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g, pool=self.pool):
+        with capture_guard(), torch.cuda.graph(g, pool=self.pool):
             out, aux = self._step()
         if self.pool is None:
             self.pool = g.pool()

@@ -19,6 +19,7 @@ from torch.autograd.function import once_differentiable
 from . import experts as X
 from . import ops
 from .functional import CompeteTailFn, DenseFFNFn, FFNSpec, GateFn, SparseFFNFn
+from .graphs import capture_guard
 from .schedule import make_layer_schedule
 
 MOE_REGISTRY: Dict[str, type] = {}
@@ -134,7 +135,8 @@ class MoeLayer(nn.Module):
                 return (out, aux) + tuple(info[k] for k in names)
 
             sample = x.detach().clone().requires_grad_(True)
-            graphed = torch.cuda.make_graphed_callables(fn, (sample,) + params, allow_unused_input=True)
+            with capture_guard():
+                graphed = torch.cuda.make_graphed_callables(fn, (sample,) + params, allow_unused_input=True)
             with torch.no_grad():
                 for n, v in keep.items():
                     getattr(self, n).copy_(v)
@@ -164,7 +166,8 @@ class MoeLayer(nn.Module):
                 return (out, aux) + tuple(info[k] for k in names)
 
             sample = x.detach().clone().requires_grad_(True)
-            graphed = torch.cuda.make_graphed_callables(fn, (sample,) + params)
+            with capture_guard():
+                graphed = torch.cuda.make_graphed_callables(fn, (sample,) + params)
             entry = (graphed, names, self.last_routing)
             self._graphs[key] = entry
         graphed, names, routing = entry

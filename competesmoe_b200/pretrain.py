@@ -17,6 +17,7 @@ import torch.nn.functional as F
 
 from . import ops
 from .functional import CompeteTailFn, DenseFFNFn, FFNSpec, GateFn, SparseFFNFn
+from .graphs import capture_guard
 from .multimodal import TopkRenormFn
 from .schedule import make_layer_schedule
 
@@ -264,7 +265,7 @@ class MoE(LoggingLayer, RegularizedLayer, OncePerIterLayer, torch.nn.Module):
                 return (out,) + tuple(t for _, t in collected)
 
             sample = x.detach().clone().requires_grad_(True)
-            with torch.autocast("cuda", dtype=adt, enabled=autocast, cache_enabled=False):
+            with capture_guard(), torch.autocast("cuda", dtype=adt, enabled=autocast, cache_enabled=False):
                 graphed = torch.cuda.make_graphed_callables(fn, (sample,) + params, allow_unused_input=True)
             self.layer, self.nb_diver = keep
             with torch.no_grad():
