@@ -531,8 +531,21 @@ def gen_all_pretrain_siblings(pm):
     gen_pretrain_sibling(pm, "ptsib_deepseekv3_f32", "deepseekv3", 64, 16, 16, 4, 2, 16, seed=25)
 
 
+def gen_gate_variants(mm, pm):
+    """Gate / score variants behind `args` flags (competesmoe.py:456-483 pretrain; competesmoe.py:243-247 multimodal)."""
+    print("gate variants:")
+    gen_pretrain(pm, "pt_router_cosine_f32", 64, 8, 32, 2, 2, 24, False, seed=30, is_cosine=True)
+    gen_pretrain(pm, "pt_router_normweight_f32", 64, 8, 32, 2, 2, 24, False, seed=31, is_norm_weight=True)
+    gen_pretrain(pm, "pt_router_normsigmoid_f32", 64, 8, 32, 2, 2, 24, False, seed=32, norm_sigmoid=True, scale_weight=2.0)
+    gen_pretrain(pm, "pt_comp_cosine_f32", 64, 8, 32, 2, 2, 16, True, seed=33, is_cosine=True)
+    gen_multimodal(mm, "mm_siglip_comp_normsigmoid_f32", "siglip", 64, 64, 128, 4, 2, 2, 16, True, seed=34, norm_sigmoid=True)
+
+
 def main():
     OUT.mkdir(parents=True, exist_ok=True)
+    if "--gate-variants-only" in sys.argv:
+        gen_gate_variants(load_multimodal_reference(), load_pretrain_reference())
+        return
     if "--siblings-only" in sys.argv:
         gen_all_siblings(load_multimodal_reference())
         return
@@ -564,6 +577,7 @@ def main():
     gen_pretrain(pm, "pt_comp_intopk_f32", 64, 8, 32, 2, 2, 16, True, seed=3, in_topk=True)
     gen_pretrain(pm, "pt_comp_tribrid_f32", 64, 8, 32, 2, 2, 16, True, seed=4, tribrid=True)
     gen_all_pretrain_siblings(pm)
+    gen_gate_variants(mm, pm)
     print("done; now run:  TRITON_INTERPRET=1 python -m oracle.gen_golden")
 
 

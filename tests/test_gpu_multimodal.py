@@ -16,7 +16,7 @@ DEV = "cuda"
 
 CASES = ["mm_siglip_router_bf16", "mm_siglip_comp_bf16", "mm_siglip_router_f32", "mm_projector_router_f32",
          "mm_glu_router_f32", "mm_siglip_comp_f32", "mm_projector_comp_f32", "mm_glu_comp_f32",
-         "mm_siglip_comp_hybrid_f32"]
+         "mm_siglip_comp_hybrid_f32", "mm_siglip_comp_normsigmoid_f32"]
 
 
 def run_layer(layer, fx, dtype):
@@ -42,10 +42,16 @@ def test_layer_matches_reference_golden(name):
     exps = [{k: (v.to(dtype) if torch.is_tensor(v) else v) for k, v in e.items()} for e in fx["experts"]]
     _, _, _, _, dbg = om.competesmoe_forward(fx["x"].to(dtype), fx["gate_w"].to(dtype), exps, m["K"], m["d_out"], args,
                                              m["competition"])
-    margin = om.topk_margin(dbg[scores_src], m["K"])
+    scores, thr = dbg[scores_src], 1e-3
+    if m["competition"] and getattr(args, "norm_sigmoid", False):
+        # the selection runs on sigmoid(score) (competesmoe.py:243-247), which squeezes the scores into a range where bf16
+        # resolves 2^-8: an fp32 reference run and this bf16 path then differ on tokens within two bf16 steps of a tie
+        scores = torch.sigmoid(scores)
+        thr = 1e-3 + (2 * 2.0 ** -8 if "float32" in m["dtype"] else 0.0)
+    margin = om.topk_margin(scores, m["K"])
     agree = (sel.cpu().long() == fx["selected"]).all(-1)
     n_ex = int((~agree).sum())
-    assert bool((margin[~agree] < 1e-3).all()), "routing differs from the reference on a token with margin >= 1e-3"
+    assert bool((margin[~agree] <= thr).all()), "routing differs from the reference on a token with a clear margin"
     print(f"{name}: {n_ex}/{agree.numel()} low-margin tokens exempt from bit-exact routing")
     # ---- values.  bf16 fixtures: the north-star's bf16 rtol 2e-2.  f32 fixtures are reference outputs computed in
     # fp32 while this path computes in bf16 on the tensor cores, so they get twice that.

@@ -15,7 +15,8 @@ from helpers import assert_close_rms
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
-PT = ["pt_router_f32", "pt_comp_f32", "pt_comp_hybrid_bal_f32", "pt_comp_intopk_f32", "pt_comp_tribrid_f32"]
+PT = ["pt_router_f32", "pt_comp_f32", "pt_comp_hybrid_bal_f32", "pt_comp_intopk_f32", "pt_comp_tribrid_f32",
+      "pt_router_cosine_f32", "pt_router_normweight_f32", "pt_router_normsigmoid_f32", "pt_comp_cosine_f32"]
 
 
 def build_layer(fx):
