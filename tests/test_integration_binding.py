@@ -214,3 +214,86 @@ def test_pretrain_sibling_routers_bind_and_match_reference_state_dicts(tmp_path,
                 sys.modules[k] = v
         for k in [k for k in sys.modules if k.startswith(("layers.", "framework."))]:
             sys.modules.pop(k, None)
+
+
+def test_schedule_matches_reference_bit_for_bit_multimodal():
+    """set_total_steps of the drop-in against the reference's own (competesmoe.py:35-179): same seed -> the same
+    competition flags for a chain of layers, with the per-step cap (`max_compete_in_iter`) biting so that the shift-left /
+    shift-right placement is exercised, and the same warm-up offset."""
+    sys.path.insert(0, str(REF))
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            import moe_model.model.moe  # noqa: F401
+            reg = importlib.import_module("moe_model.model.moe.register")
+    finally:
+        sys.path.remove(str(REF))
+    from competesmoe_b200.multimodal import CompeteSMoE
+
+    def expert():
+        m = nn.Module()
+        m.fc1, m.fc2, m.activation_fn = nn.Linear(16, 24), nn.Linear(24, 16), nn.GELU(approximate="tanh")
+        return m
+
+    for rate, cap, warm, total, n_layers in ((0.5, 2, 0.0, 60, 5), (0.3, 1, 0.25, 80, 4), (0.9, 3, 0.1, 50, 6)):
+        args = _mm_args()
+        args.rate_flip, args.max_compete_in_iter, args.warm_up = rate, cap, warm
+        results = []
+        for make in (lambda: reg.get_moe("competesmoe"), lambda: CompeteSMoE):
+            with contextlib.redirect_stdout(io.StringIO()):
+                layers = [make()(in_embed_dim=16, out_embed_dim=16, num_of_experts=4, num_selected=2,
+                                 expert=nn.ModuleList([expert() for _ in range(4)]), args=args) for _ in range(n_layers)]
+                torch.manual_seed(1234)
+                acc = {}
+                for i, layer in enumerate(layers):
+                    acc = layer.set_total_steps(total, id_layer=i, prob_flips_final=acc)
+            results.append(([layer.prob_flips.clone().bool() for layer in layers], [layer.step_warm for layer in layers],
+                            {k: v.clone().bool() for k, v in acc.items()}))
+        (f_ref, w_ref, a_ref), (f_our, w_our, a_our) = results
+        assert w_ref == w_our
+        assert sorted(a_ref) == sorted(a_our)
+        for a, b in zip(f_ref, f_our):
+            assert a.shape == b.shape and torch.equal(a.cpu(), b.cpu())
+        per_step = torch.stack([f.cpu() for f in f_our]).sum(0)
+        assert int(per_step.max()) <= cap
+
+
+def test_schedule_matches_reference_bit_for_bit_pretrain(tmp_path, monkeypatch):
+    """Same for the pretrain plugin (layers/moe/competesmoe.py:123-273): the LM assigns one shared `prob_flips_final`
+    dict to every layer (transformer_lm_mixin.py:265-267) and calls set_total_steps(id_layer) layer by layer."""
+    monkeypatch.chdir(tmp_path)   # the reference appends to ./file_path.txt
+    try:
+        L, base, reg, saved, R = _pretrain_shim()
+    except Exception as e:  # pragma: no cover - the reference tree changed
+        pytest.skip(f"reference import shim failed: {e}")
+    try:
+        from competesmoe_b200.pretrain import CompeteSMoE
+        for rate, cap, warm, total, n_layers in ((0.5, 2, 0.0, 60, 5), (0.3, 1, 0.25, 80, 4)):
+            ns = SimpleNamespace(warm_up=warm, rate_flip=rate, stop_after=total, max_compete_in_iter=cap, is_cosine=False,
+                                 is_norm_weight=False, norm_sigmoid=False, scale_weight=1.0, hybrid=False, tribrid=False,
+                                 in_topk=False, balance_affinity=False, balance_loss_coef=0.01,
+                                 balance_loss_coef_comp=0.01, router_loss_coef=0.01, router_theta=1.0, test_only=False)
+            kw = dict(n_heads=2, args=ns, activation=F.relu, selection_mode="gate", log_interval=None)
+            results = []
+            for cls in (reg.get_moe("competesmoe"), CompeteSMoE):
+                with contextlib.redirect_stdout(io.StringIO()):
+                    layers = [cls(32, 4, 8, **kw) for _ in range(n_layers)]
+                    shared = {}
+                    torch.manual_seed(99)
+                    for i, layer in enumerate(layers):
+                        layer.prob_flips_final = shared
+                        shared = layer.set_total_steps(id_layer=i)
+                results.append(({k: v.clone().bool().cpu() for k, v in shared.items()}, [layer.step_warm for layer in layers]))
+            (f_ref, w_ref), (f_our, w_our) = results
+            assert w_ref == w_our and sorted(f_ref) == sorted(f_our) == list(range(n_layers))
+            for k in f_ref:
+                assert torch.equal(f_ref[k], f_our[k]), k
+            assert int(torch.stack(list(f_our.values())).sum(0).max()) <= cap
+    finally:
+        sys.path.remove(R)
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+        for k in [k for k in sys.modules if k.startswith(("layers.", "framework."))]:
+            sys.modules.pop(k, None)
