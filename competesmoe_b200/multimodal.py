@@ -115,6 +115,14 @@ class MoeLayer(nn.Module):
                 del self._eager_forward
         return self
 
+    def __getstate__(self):
+        """copy.deepcopy / pickling: captured CUDA graphs belong to this instance's storage and are not copied -- the
+        copy keeps graph mode switched on and captures its own graphs on first use."""
+        state = self.__dict__.copy()
+        if state.get("_graphs") is not None:
+            state["_graphs"] = {}
+        return state
+
     _inplace_params = ()     # parameters a forward call rescales in place (xmoe / smoe_perturbed: expert_embeddings)
 
     def _wrapped_graph_forward(self, x, return_id_experts=False, is_vision=False):

@@ -229,6 +229,14 @@ class MoE(LoggingLayer, RegularizedLayer, OncePerIterLayer, torch.nn.Module):
             self.forward = self._eager_forward
         return self
 
+    def __getstate__(self):
+        """copy.deepcopy / pickling: captured CUDA graphs belong to this instance's storage and are not copied -- the
+        copy keeps graph mode switched on and captures its own graphs on first use."""
+        state = self.__dict__.copy()
+        if state.get("_graphs") is not None:
+            state["_graphs"] = {}
+        return state
+
     def _graph_forward(self, x, *args, **kwargs):
         eligible = (self._graphable and self._ep is None and self.training and torch.is_tensor(x) and x.is_cuda
                     and x.requires_grad and torch.is_grad_enabled() and not getattr(self.args, "test_only", False)

@@ -205,3 +205,33 @@ def test_cvmm_oracle_moe_attention_layouts_match_einsum():
     xo, wo = torch.randn(T, heads, dh), torch.randn(E, dh, D)
     b = op.cvmm(xo, op.Sel(rs.raw_sel, rs.sel, rs.out_index // k, rs.out_index, w.flatten(-2)), wo)
     torch.testing.assert_close(b, torch.einsum("thk,thd,thkdn->tn", w, xo, wo[sel.long()]), rtol=1e-5, atol=1e-5)
+
+
+def test_graph_mode_layers_deepcopy_cleanly():
+    """enable_cuda_graphs() installs an instance-level forward; a deep copy (EMA / checkpoint averaging copies whole
+    modules) must bind the copy's forward to the copy and must not carry captured graphs over.  CPU only: nothing is
+    captured here, the wrapper falls through to the eager forward for non-CUDA inputs."""
+    import copy
+    import torch.nn as nn
+    from types import SimpleNamespace
+    import competesmoe_b200.pretrain_siblings  # noqa: F401
+    from competesmoe_b200 import siblings  # noqa: F401
+    from competesmoe_b200.multimodal import get_moe as get_mm
+    from competesmoe_b200.pretrain import get_moe as get_pt
+    pt = get_pt("smoe")(32, 4, 8, n_heads=2, args=SimpleNamespace(balance_loss_coef=0.01, test_only=False),
+                        activation=F.relu, selection_mode="gate", log_interval=None).enable_cuda_graphs()
+    pt._graphs["fake"] = object()
+    cp = copy.deepcopy(pt)
+    assert cp.forward.__self__ is cp and cp._eager_forward.__self__ is cp and cp._graphs == {}
+    assert pt._graphs != {} and pt.forward.__self__ is pt
+
+    def expert():
+        m = nn.Module()
+        m.fc1, m.fc2, m.activation_fn = nn.Linear(16, 24), nn.Linear(24, 16), nn.GELU(approximate="tanh")
+        return m
+    mm = get_mm("smoe")(16, 16, 4, 2, nn.ModuleList([expert() for _ in range(4)]), om.default_args()).enable_cuda_graphs()
+    mm._graphs["fake"] = object()
+    cm = copy.deepcopy(mm)
+    assert cm.forward.__self__ is cm and cm._graphs == {} and mm._graphs != {}
+    cm.enable_cuda_graphs(False)
+    assert "forward" not in cm.__dict__ or cm.forward.__func__ is type(cm).forward
