@@ -57,3 +57,17 @@ def test_ops_refuse_cpu_tensors():
     from competesmoe_b200 import ops
     with pytest.raises(RuntimeError, match="no CPU path"):
         ops.router_fwd(torch.zeros(4, 64), torch.zeros(4, 64), 2)
+
+
+def test_header_is_plain_c():
+    """include/csmoe.h is the drop-in boundary: it must compile as C (cgo / JNI / ctypes-style bindings include it as is)
+    and as C++."""
+    import shutil
+    import subprocess
+    from pathlib import Path
+    hdr = Path(__file__).resolve().parent.parent / "include" / "csmoe.h"
+    for cc, args in (("gcc", ["-x", "c", "-std=c11"]), ("g++", ["-x", "c++", "-std=c++17"])):
+        if shutil.which(cc) is None:
+            continue
+        r = subprocess.run([cc, *args, "-fsyntax-only", "-Wall", "-Werror", str(hdr)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
