@@ -98,7 +98,11 @@ def load() -> C.CDLL:
     with _lock:
         if _lib is not None:
             return _lib
-        if not LIB_PATH.exists():
+        # build() is a digest compare of csrc/ + include/ against lib/libcsmoe.stamp when the library exists, and a
+        # rebuild when they differ: a stale binary (lib/ is git-ignored and survives checkouts) would pass the symbol
+        # check below and then misread csmoe_gemm_args.  CSMOE_SKIP_BUILD_CHECK=1 loads whatever is there.
+        import os
+        if not LIB_PATH.exists() or os.environ.get("CSMOE_SKIP_BUILD_CHECK", "0") != "1":
             from . import build as _build
 
             _build.build()

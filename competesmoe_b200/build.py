@@ -60,8 +60,14 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     LIBDIR.mkdir(exist_ok=True)
     nvcc = _nvcc()
 
+    headers = [p for p in deps if p not in srcs]
+
     def compile_one(src: Path) -> Path:
         obj = OBJDIR / (src.stem + ".o")
+        # per-object stamp: a source is recompiled only when it, a header or the flags changed
+        ostamp, odigest = OBJDIR / (src.stem + ".stamp"), _digest([src] + headers)
+        if not force and not verbose and obj.exists() and ostamp.exists() and ostamp.read_text() == odigest:
+            return obj
         cmd = [nvcc, *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
@@ -70,6 +76,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
             raise RuntimeError(f"nvcc failed for {src.name}:\n{r.stdout}\n{r.stderr}")
         if verbose:
             print(r.stderr)
+        ostamp.write_text(odigest)
         return obj
 
     with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:

@@ -27,40 +27,50 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// Total order on floats for the selection: an order-preserving integer key, NaN (either sign) sorted as the largest
+// value, which is where torch.topk puts it.  Comparisons on the key are total, so all lanes always agree on the winner
+// and a token with non-finite scores still gets K distinct, in-range expert ids (the loss then goes NaN exactly like the
+// reference's; nothing indexes out of bounds downstream).
+__device__ __forceinline__ unsigned order_key(float v) {
+  const unsigned b = __float_as_uint(v);
+  if ((b & 0x7fffffffu) > 0x7f800000u) return 0xffffffffu;   // NaN
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
 // Warp-wide selection of the K largest of up to 64 values (lane l holds experts l and l+32).
-// Emits (value, index) pairs in descending order to lane-uniform arrays.
+// Emits (value, index) pairs in descending order to lane-uniform arrays.  Ties: lowest expert index first.
+// Requires K <= E (checked on the host): then every round has an untaken valid candidate and the sentinel never wins.
 __device__ __forceinline__ void warp_topk(float v0, float v1, int lane, int E, int K, float (&out_v)[kMaxK],
                                           int (&out_i)[kMaxK]) {
-  const float NEG = -INFINITY;
-  if (lane >= E) v0 = NEG;
-  if (lane + 32 >= E) v1 = NEG;
   bool t0 = lane >= E, t1 = lane + 32 >= E;  // taken / invalid
+  const unsigned k0 = order_key(v0), k1 = order_key(v1);
 #pragma unroll
   for (int k = 0; k < kMaxK; ++k) {
     if (k >= K) break;
-    float bv;
+    unsigned bk;
     int bi;
     // local best (lower index wins ties): candidate 0 has the lower index
-    if (!t0 && (t1 || v0 >= v1)) {
-      bv = v0;
+    if (!t0 && (t1 || k0 >= k1)) {
+      bk = k0;
       bi = lane;
     } else if (!t1) {
-      bv = v1;
+      bk = k1;
       bi = lane + 32;
     } else {
-      bv = NEG;
+      bk = 0u;            // below the key of every valid value (-inf maps to 0x007fffff)
       bi = 0x7fffffff;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const unsigned ok = __shfl_xor_sync(0xffffffffu, bk, o);
       const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (ov > bv || (ov == bv && oi < bi)) {
-        bv = ov;
+      if (ok > bk || (ok == bk && oi < bi)) {
+        bk = ok;
         bi = oi;
       }
     }
-    out_v[k] = bv;
+    if (bi == 0x7fffffff) bi = k < E ? k : 0;   // unreachable for K <= E; keeps the index in range regardless
+    out_v[k] = __shfl_sync(0xffffffffu, bi >= 32 ? v1 : v0, bi & 31);
     out_i[k] = bi;
     if (bi == lane) t0 = true;
     if (bi == lane + 32) t1 = true;

@@ -15,6 +15,11 @@ constexpr int kWarps = kThreads / 32;
 constexpr int kPerWarp = kChunk / kWarps;
 constexpr int kMaxExperts = 1024;
 
+// Expert ids come from this library's own top-k kernels or, through the public cvmm_prepare_sel, from the caller.  An id
+// outside [0, E) is clamped into range so that a bad index can never become an out-of-bounds shared / global write here
+// or in the gather / combine kernels that consume the maps (the reference would raise a device-side assert instead).
+__device__ __forceinline__ int clamp_expert(int e, int E) { return e < 0 ? 0 : (e >= E ? E - 1 : e); }
+
 __device__ __forceinline__ unsigned lanemask_lt() {
   unsigned m;
   asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
@@ -35,7 +40,7 @@ route_hist_kernel(const int32_t* __restrict__ sel, long long n_slots, int E, int
   for (int it = 0; it < kPerWarp / 32; ++it) {
     const long long j = base + it * 32 + lane;
     const bool ok = j < n_slots;
-    const int e = ok ? sel[j] : -1;
+    const int e = ok ? clamp_expert(sel[j], E) : -1;
     const unsigned peers = __match_any_sync(0xffffffffu, e);
     if (ok && (peers & lanemask_lt()) == 0) mine[e] += __popc(peers);
     __syncwarp();
@@ -120,7 +125,7 @@ route_scatter_kernel(const int32_t* __restrict__ sel, long long n_slots, int E, 
   for (int it = 0; it < kPerWarp / 32; ++it) {
     const long long j = base + it * 32 + lane;
     const bool ok = j < n_slots;
-    const int e = ok ? sel[j] : -1;
+    const int e = ok ? clamp_expert(sel[j], E) : -1;
     const unsigned peers = __match_any_sync(0xffffffffu, e);
     if (ok && (peers & lanemask_lt()) == 0) mine[e] += __popc(peers);
     __syncwarp();
@@ -141,7 +146,7 @@ route_scatter_kernel(const int32_t* __restrict__ sel, long long n_slots, int E, 
   for (int it = 0; it < kPerWarp / 32; ++it) {
     const long long j = base + it * 32 + lane;
     const bool ok = j < n_slots;
-    const int e = ok ? sel[j] : -1;
+    const int e = ok ? clamp_expert(sel[j], E) : -1;
     const unsigned peers = __match_any_sync(0xffffffffu, e);
     if (ok) {
       const int rank = mine[e] + __popc(peers & lanemask_lt());

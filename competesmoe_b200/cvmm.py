@@ -27,9 +27,46 @@ class CVMMSel:
     out_index: Optional[torch.Tensor] = None
     reduction_weight: Optional[torch.Tensor] = None
     _route: Optional[ops.Route] = None   # permutation maps of the padded expert-major space (built once per selection)
+    _checked: Optional[tuple] = None     # identity of the (sel_index, out_index) pair last verified against _route
 
     def clone(self) -> "CVMMSel":
-        return CVMMSel(self.raw_sel, self.sel, self.sel_index, self.out_index, self.reduction_weight, self._route)
+        return CVMMSel(self.raw_sel, self.sel, self.sel_index, self.out_index, self.reduction_weight, self._route,
+                       self._checked)
+
+
+# The grouped GEMM addresses rows through the maps of `_route` (built from raw_sel), not through sel_index / out_index.
+# Those two tensors are public and callers do rewrite them (competesmoe.py:516-521, full_moe_relative_attention.py:453-458),
+# so before they are ignored they are verified to be one of the layouts the maps can express:
+#   out_index is None : sel_index == sort_index                 (every slot reads its own input row, output in slot order)
+#   out_index given   : out_index == sort_index, sel_index == sort_index // c   (c slots share one input row)
+# Anything else raises NotImplementedError instead of silently computing the wrong rows.  The check costs one
+# device->host sync per distinct (sel_index, out_index) pair; it is skipped while a CUDA graph is being captured and can
+# be switched off with `competesmoe_b200.cvmm.CHECK_SEL_INDEX = False` once a call site is known to be good.
+CHECK_SEL_INDEX = True
+
+
+def _ident(t: Optional[torch.Tensor]):
+    return None if t is None else (t.data_ptr(), t._version, tuple(t.shape))
+
+
+def _verify_index_layout(sel: CVMMSel, slots_per_row: int) -> None:
+    if not CHECK_SEL_INDEX or torch.cuda.is_current_stream_capturing():
+        return
+    key = (_ident(sel.sel_index), _ident(sel.out_index), slots_per_row)
+    if sel._checked == key:
+        return
+    si = sel._route.sort_index
+    ok = sel.sel_index is not None and sel.sel_index.numel() == si.numel()
+    if ok and sel.out_index is not None:
+        ok = sel.out_index.numel() == si.numel() and bool(
+            (sel.out_index.reshape(-1) == si).all() & (sel.sel_index.reshape(-1) == si // slots_per_row).all())
+    elif ok:
+        ok = bool((sel.sel_index.reshape(-1) == si).all())
+    if not ok:
+        raise NotImplementedError(
+            "cvmm: sel_index / out_index are not the stable-sort maps of raw_sel (`pos // c` with out_index = pos, or "
+            "sel_index = pos with out_index = None); arbitrary index tensors are not supported by the grouped-GEMM path")
+    sel._checked = key
 
 
 def _num_experts_hint(sel: torch.Tensor, n_experts: Optional[int]) -> int:
@@ -41,7 +78,8 @@ def _num_experts_hint(sel: torch.Tensor, n_experts: Optional[int]) -> int:
 def cvmm_prepare_sel(sel: torch.Tensor, n_experts: int) -> CVMMSel:
     """cvmm.py:23-26: one selection per row."""
     route = ops.route_build(sel.reshape(-1, 1), n_experts)
-    return CVMMSel(sel, route.sorted_sel.view_as(sel), route.sort_index, None, None, route)
+    return CVMMSel(sel, route.sorted_sel.view_as(sel), route.sort_index, None, None, route,
+                   (_ident(route.sort_index), None, 1))
 
 
 def cvmm_prepare_sel2(sel: torch.Tensor, w: Optional[torch.Tensor] = None, n_experts: Optional[int] = None) -> CVMMSel:
@@ -51,7 +89,9 @@ def cvmm_prepare_sel2(sel: torch.Tensor, w: Optional[torch.Tensor] = None, n_exp
     if n_experts is None:
         return CVMMSel(sel, None, None, None, w, None)  # completed lazily by cvmm() once E is known
     route = ops.route_build(sel.reshape(-1, k), n_experts)
-    return CVMMSel(sel, route.sorted_sel.view_as(sel), route.sort_index // k, route.sort_index, w, route)
+    in_index = route.sort_index // k
+    return CVMMSel(sel, route.sorted_sel.view_as(sel), in_index, route.sort_index, w, route,
+                   (_ident(in_index), _ident(route.sort_index), k))   # built here: correct by construction
 
 
 def _complete(sel: CVMMSel, n_experts: int) -> CVMMSel:
@@ -64,14 +104,15 @@ def _complete(sel: CVMMSel, n_experts: int) -> CVMMSel:
         sel.sel = route.sorted_sel.view_as(sel.raw_sel)
         sel.sel_index = route.sort_index // k
         sel.out_index = route.sort_index
+        sel._checked = (_ident(sel.sel_index), _ident(sel.out_index), k)
     return sel
 
 
 def _out_dtype(x: torch.Tensor) -> torch.dtype:
-    """cvmm.py:29-32 get_dtype(): fp32 unless autocast is active."""
+    """cvmm.py:29-32 get_dtype(): the autocast dtype when autocast is active, else fp32 -- whatever the input dtype."""
     if torch.is_autocast_enabled():
         return torch.get_autocast_dtype('cuda')
-    return x.dtype if x.dtype in (torch.bfloat16,) else torch.float32
+    return torch.float32
 
 
 class CVMM(Function):
@@ -143,6 +184,7 @@ def cvmm(x: torch.Tensor, sel: Union[torch.Tensor, CVMMSel], keys: torch.Tensor)
         if rows_in == 0 or n_slots % rows_in != 0:
             raise ValueError(f"cvmm: {rows_in} input rows do not divide the {n_slots} selection slots")
         slots_per_row = n_slots // rows_in
+    _verify_index_layout(sel, slots_per_row)
     rw = sel.reduction_weight
     if rw is not None and (rw.shape[-1] > 8 or n_slots % rw.shape[-1] != 0):
         raise ValueError(f"cvmm: reduction over {rw.shape[-1]} slots per output row is not supported (1..8, dividing {n_slots})")

@@ -278,6 +278,69 @@ def gather_experts(w_local: Optional[torch.Tensor], group: EPGroup) -> Optional[
     return None if w_local is None else AllGatherExpertsFn.apply(w_local, group)
 
 
+# ------------------------------------------------------------------------------------------------ checkpoints under EP
+_PRETRAIN_SHARDED = ("keys", "values", "bias")
+
+
+def full_state_dict(layer, group=None) -> dict:
+    """COLLECTIVE over the layer's expert-parallel group.  The layer's state dict in the REFERENCE layout -- multimodal:
+    `experts.{global e}.<child>.{weight,bias}`; pretrain: `keys / values / bias` with all E experts along dim 0 -- with
+    the expert shards all-gathered, identical on every rank.  This is what a rank-0 `torch.save` must write: after
+    `enable_expert_parallel` the plain `state_dict()` holds only this rank's experts, renumbered from 0."""
+    g = group or layer._ep.group
+    P = g.world
+    sd = {k: v.detach() for k, v in layer.state_dict().items()}
+    if P == 1:
+        return sd
+
+    def gather(t):
+        parts = [torch.empty_like(t) for _ in range(P)]
+        dist.all_gather(parts, t.contiguous(), group=g.group)
+        return parts
+
+    out = {}
+    if hasattr(layer, "experts"):                                  # multimodal plugin: one module per local expert
+        El = len(layer.experts)
+        for k in sorted(sd):
+            if not k.startswith("experts."):
+                out[k] = sd[k]
+                continue
+            _, i, rest = k.split(".", 2)
+            for r, part in enumerate(gather(sd[k])):
+                out[f"experts.{r * El + int(i)}.{rest}"] = part
+    else:                                                          # pretrain plugin: stacked [E/P, ...] parameters
+        for k in sorted(sd):
+            out[k] = torch.cat(gather(sd[k]), dim=0) if k in _PRETRAIN_SHARDED else sd[k]
+    return out
+
+
+def load_full_state_dict(layer, state_dict: dict, group=None, strict: bool = True):
+    """Load a reference-layout (all experts) state dict into an expert-parallel layer: every rank keeps its own slice.
+    No communication; every rank must be handed the same full dict."""
+    g = group or layer._ep.group
+    P, r = g.world, g.rank
+    if P == 1:
+        return layer.load_state_dict(state_dict, strict=strict)
+    local = {}
+    if hasattr(layer, "experts"):
+        El = len(layer.experts)
+        for k, v in state_dict.items():
+            if k.startswith("experts."):
+                _, e, rest = k.split(".", 2)
+                if r * El <= int(e) < (r + 1) * El:
+                    local[f"experts.{int(e) - r * El}.{rest}"] = v
+            else:
+                local[k] = v
+    else:
+        for k, v in state_dict.items():
+            if k in _PRETRAIN_SHARDED:
+                El = v.shape[0] // P
+                local[k] = v[r * El:(r + 1) * El]
+            else:
+                local[k] = v
+    return layer.load_state_dict(local, strict=strict)
+
+
 # ------------------------------------------------------------------------------------------------ sparse experts, EP
 class EPSparseFFNFn(Function):
     """out[t] = sum_k w[t,k] * FFN_{sel[t,k]}(x[t]) with the experts sharded over the group (w1/b1/w2/b2 hold the

@@ -46,6 +46,7 @@ class FFNSpec:
     kn_layout: bool = False  # False: w1 [E,F,D], w2 [E,Dout,F] (nn.Linear);  True: w1 [E,D,H], w2 [E,H,Dout] (sigma-MoE)
     round_each: bool = True  # combine: round the running sum to the activation dtype after every expert (moe.py:204)
     round_w: bool = False    # combine: round the routing weight to the activation dtype first (cvmm.py:483)
+    return_hidden: bool = False  # SparseFFNFn also returns h = act(z) [row_cap, H] (non-differentiable; relu_pass_rate log)
 
     @property
     def glu(self) -> bool:
@@ -134,11 +135,15 @@ class SparseFFNFn(Function):
         ctx.save_for_backward(xp, z, h, y, w, w1, w2)
         # fp32 master weights (pretrain under autocast): keep the bf16 copies of this step for the backward pass
         ctx.wb = (w1b if w1b is not w1 else None, w2b if w2b is not w2 else None)
+        if spec.return_hidden:
+            hd = h.detach()
+            ctx.mark_non_differentiable(hd)
+            return out, hd
         return out
 
     @staticmethod
     @once_differentiable
-    def backward(ctx, dout):
+    def backward(ctx, dout, _dh=None):
         xp, z, h, y, w, w1, w2 = ctx.saved_tensors
         route, spec = ctx.route, ctx.spec
         T, K, E = route.n_slots // route.top_k, route.top_k, route.num_experts

@@ -187,17 +187,33 @@ class MoeLayer(nn.Module):
     def enable_expert_parallel(self, group, max_tokens: int, row_tile: int = 256):
         """Shard the experts over `group` (a competesmoe_b200.ep.EPGroup): this rank keeps experts
         [rank*E/P, (rank+1)*E/P) as `experts.{0..E/P-1}`; the gate stays replicated.  `max_tokens` = the largest B*N this
-        rank will ever pass to forward (sizes the peer-mapped exchange buffers).  Call after loading a full checkpoint."""
+        rank will ever pass to forward (sizes the peer-mapped exchange buffers).  Call after loading a full checkpoint and
+        BEFORE the optimizer is built (the other experts' parameters leave the module).  Afterwards `state_dict()` holds
+        this rank's experts only, renumbered from 0; use `full_state_dict()` / `load_full_state_dict()` for checkpoints
+        in the reference layout (`experts.{global e}...`)."""
         from .ep import EPLayerState
-        E, P = self.num_of_experts, group.world
-        if E % P != 0:
-            raise ValueError(f"{E} experts cannot be split over an expert-parallel group of {P} ranks")
-        El = E // P
-        self.ep_expert_offset = group.rank * El
+        self._shard_experts(group.rank, group.world)
+        self._ep = EPLayerState(group, self.num_of_experts, self.num_selected, self.in_embed_dim, self.out_embed_dim,
+                                max_tokens, row_tile)
+        return self
+
+    def _shard_experts(self, rank: int, world: int):
+        E = self.num_of_experts
+        if E % world != 0:
+            raise ValueError(f"{E} experts cannot be split over an expert-parallel group of {world} ranks")
+        El = E // world
+        self.ep_expert_offset = rank * El
         self.experts = nn.ModuleList([self.experts[i] for i in range(self.ep_expert_offset, self.ep_expert_offset + El)])
         self._layout = None
-        self._ep = EPLayerState(group, E, self.num_selected, self.in_embed_dim, self.out_embed_dim, max_tokens, row_tile)
-        return self
+
+    def full_state_dict(self, group=None):
+        """Collective: the reference-layout state dict with every expert (ep.full_state_dict)."""
+        from .ep import full_state_dict
+        return full_state_dict(self, group)
+
+    def load_full_state_dict(self, state_dict, group=None, strict: bool = True):
+        from .ep import load_full_state_dict
+        return load_full_state_dict(self, state_dict, group, strict)
 
     def _sparse_ffn(self, x2, gw, gidx, w1, b1, w2, b2, spec):
         if self._ep is None:

@@ -9,6 +9,7 @@ Same constructor keywords, `forward(x, *, id_layer)`, schedule hooks, regularise
 """
 from __future__ import annotations
 
+import dataclasses
 import math
 from typing import Any, Callable, Dict, Optional
 
@@ -187,20 +188,38 @@ class MoE(LoggingLayer, RegularizedLayer, OncePerIterLayer, torch.nn.Module):
     def enable_expert_parallel(self, group, max_tokens: int, row_tile: int = 128):
         """Shard keys / values (/ bias) over `group` (competesmoe_b200.ep.EPGroup): this rank keeps the slices
         [rank*E/P, (rank+1)*E/P) along dim 0; w_gate (and o_bias) stay replicated.  `max_tokens` = the largest number of
-        tokens this rank passes to forward.  Call after loading a full checkpoint."""
+        tokens this rank passes to forward.  Call after loading a full checkpoint and BEFORE the optimizer is built: the
+        sharded tensors are new Parameters, an optimizer created earlier would keep updating the old full-size ones.
+        Afterwards `state_dict()` holds this rank's shard only; use `full_state_dict()` / `load_full_state_dict()` for
+        checkpoints in the reference layout."""
         from .ep import EPLayerState
-        E, P = self.n_experts, group.world
-        if E % P != 0:
-            raise ValueError(f"{E} experts cannot be split over an expert-parallel group of {P} ranks")
-        El = E // P
-        lo = group.rank * El
+        self._shard_experts(group.rank, group.world)
+        self._ep = EPLayerState(group, self.n_experts, self.num_selected, self.k_vec_dim, self.v_dim, max_tokens, row_tile)
+        return self
+
+    def _shard_experts(self, rank: int, world: int):
+        E = self.n_experts
+        if E % world != 0:
+            raise ValueError(f"{E} experts cannot be split over an expert-parallel group of {world} ranks")
+        if any(getattr(self, n) is not None and getattr(self, n).grad is not None for n in ("keys", "values", "bias")):
+            raise RuntimeError("enable_expert_parallel() must run before training starts (and before the optimizer is "
+                               "created): the expert parameters are replaced by their local shards")
+        El = E // world
+        lo = rank * El
         for name in ("keys", "values", "bias"):
             p = getattr(self, name)
             if p is not None:
                 setattr(self, name, torch.nn.Parameter(p.detach()[lo:lo + El].clone(), requires_grad=p.requires_grad))
         self.ep_expert_offset = lo
-        self._ep = EPLayerState(group, E, self.num_selected, self.k_vec_dim, self.v_dim, max_tokens, row_tile)
-        return self
+
+    def full_state_dict(self, group=None):
+        """Collective: the reference-layout state dict with every expert (ep.full_state_dict)."""
+        from .ep import full_state_dict
+        return full_state_dict(self, group)
+
+    def load_full_state_dict(self, state_dict, group=None, strict: bool = True):
+        from .ep import load_full_state_dict
+        return load_full_state_dict(self, state_dict, group, strict)
 
     def _all_expert_weights(self):
         if self._ep is None or self._ep.group.world == 1:
@@ -347,14 +366,28 @@ class MoE(LoggingLayer, RegularizedLayer, OncePerIterLayer, torch.nn.Module):
     def compute_gate(self, x2: torch.Tensor, cdt: torch.dtype):
         return GateFn.apply(self._cast(x2, cdt), self.w_gate, self.num_selected, 1, False)[:4]
 
-    def _log_relu_pass_rate(self, out):
-        pass  # the hidden activations never leave the fused kernels; the reference logs this only every log_interval
+    def _plot_training(self) -> bool:
+        """moe.py:405: `self.train and log_interval is not None and iter % log_interval == 0` (`self.train` is the bound
+        method there, i.e. always true).  Not logged from inside a CUDA-graph capture (the flag changes per iteration)."""
+        return (self.log_interval is not None and self.iter % self.log_interval == 0
+                and not (torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()))
+
+    def _log_relu_pass_rate(self, h, n_slots: int):
+        """moe.py:405-414: fraction of positive hidden activations.  h is the padded expert-major [row_cap, H] buffer;
+        padding rows are zero, so they never count, and the denominator is the number of routed activations."""
+        with torch.no_grad():
+            self.log("relu_pass_rate", (h > 0).sum().float() / float(n_slots * h.shape[1]))
 
     def compute_moe_main(self, x2, selected, weights, cdt):
         if self._ep is not None:
             from .ep import EPSparseFFNFn
             return EPSparseFFNFn.apply(self._cast(x2, cdt), weights, selected, self.keys, self.bias, self.values, None,
                                        self._spec(cdt), self._ep)
+        if self._plot_training():
+            spec = dataclasses.replace(self._spec(cdt), return_hidden=True)
+            out, h = SparseFFNFn.apply(self._cast(x2, cdt), weights, selected, self.keys, self.bias, self.values, None, spec)
+            self._log_relu_pass_rate(h, selected.numel())
+            return out
         return SparseFFNFn.apply(self._cast(x2, cdt), weights, selected, self.keys, self.bias, self.values, None, self._spec(cdt))
 
     def forward(self, x, return_id_experts=False, return_full=True, *args, **kwargs):
@@ -362,7 +395,8 @@ class MoE(LoggingLayer, RegularizedLayer, OncePerIterLayer, torch.nn.Module):
         B = x.shape[:-1]
         cdt = self._compute_dtype(x)
         x2 = x.reshape(-1, x.shape[-1])
-        logits, probs, gw, gidx = self.compute_gate(x2, cdt)
+        logits, probs, _, gidx = self.compute_gate(x2, cdt)
+        gw = torch.gather(probs, 1, gidx.long())     # moe.py:373-393 topk_expert: the raw top-k probabilities, no renormalisation
         if self.training is False:
             self.add_dist_experts(selection=gidx)
         out = self.compute_moe_main(x2, gidx, gw, cdt)
@@ -491,10 +525,15 @@ class CompeteSMoE(MoE):
         if is_comp:
             spec = self._spec(cdt)
             keys, bias, values = self._all_expert_weights()
-            y_all, score_sums = DenseFFNFn.apply(self._cast(x2, cdt), keys, bias, values, None, spec,
+            # competition_policy_mlp_faster (:381-414) scores every expert WITHOUT the hidden bias; compute_moe_main then
+            # recomputes the selected experts with it (moe.py:400-401).  Without a bias the two coincide and the selected
+            # outputs are reused from the dense pass; with one the sparse path runs on the competition's selection.
+            y_all, score_sums = DenseFFNFn.apply(self._cast(x2, cdt), keys, None, values, None, spec,
                                                  x.dtype == torch.bfloat16)          # [E * t_pad, Dv]
             t_pad = y_all.shape[0] // E
             aff, aff_w, aff_idx, out, diver = CompeteTailFn.apply(y_all, E, T, t_pad, K, False, x.dtype, spec, score_sums)
+            if self.bias is not None:
+                out = self.compute_moe_main(x2, aff_idx, aff_w, cdt)
             self.nb_diver += K * (K - 1) * T
             aff_softmax = F.softmax(aff, dim=-1, dtype=torch.float32)
             li = aff_idx.long()

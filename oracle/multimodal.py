@@ -62,16 +62,26 @@ def stable_topk(scores: torch.Tensor, k: int):
     return torch.gather(scores, -1, order), order
 
 
-def router_policy(x: torch.Tensor, gate_w: torch.Tensor, k: int):
+def _topk_or_forced(scores: torch.Tensor, k: int, forced: Optional[torch.Tensor]):
+    """stable_topk, or -- parity tests that compare values under IDENTICAL routing -- the scores at `forced` indices
+    (the routing decision itself is compared separately, with the north-star's low-margin rule)."""
+    if forced is None:
+        return stable_topk(scores, k)
+    forced = forced.long().view(*scores.shape[:-1], k)
+    return torch.gather(scores, -1, forced), forced
+
+
+def router_policy(x: torch.Tensor, gate_w: torch.Tensor, k: int, forced: Optional[torch.Tensor] = None):
     """competesmoe.py:301-320 + moe.py:113-132."""
     gate_logits = F.linear(x, gate_w)
     gate_softmax = F.softmax(gate_logits, dim=-1, dtype=torch.float32)
-    weights, selected = stable_topk(gate_softmax, k)
+    weights, selected = _topk_or_forced(gate_softmax, k, forced)
     weights = weights / torch.sum(weights, dim=-1, keepdim=True).to(x.dtype)
     return weights, selected, gate_softmax, gate_logits
 
 
-def competition_policy(x: torch.Tensor, experts: Sequence[ExpertW], k: int, norm_sigmoid: bool = False):
+def competition_policy(x: torch.Tensor, experts: Sequence[ExpertW], k: int, norm_sigmoid: bool = False,
+                       forced: Optional[torch.Tensor] = None):
     """competesmoe.py:219-259: run every expert on every token, score = mean softplus(output)."""
     B, N, _ = x.shape
     E = len(experts)
@@ -84,9 +94,9 @@ def competition_policy(x: torch.Tensor, experts: Sequence[ExpertW], k: int, norm
     expert_outputs = torch.cat(outs, dim=2)
     affinity_softmax = F.softmax(affinity, dim=-1, dtype=torch.float32)
     if norm_sigmoid:
-        weights, selected = stable_topk(torch.sigmoid(affinity), k)
+        weights, selected = _topk_or_forced(torch.sigmoid(affinity), k, forced)
     else:
-        weights, selected = stable_topk(affinity, k)
+        weights, selected = _topk_or_forced(affinity, k, forced)
     weights = weights / torch.sum(weights, dim=-1, keepdim=True).to(x.dtype)
     idx = selected.unsqueeze(-1).expand(B, N, k, expert_outputs.size(-1))
     topk_outputs = torch.gather(expert_outputs, dim=2, index=idx)
@@ -137,18 +147,23 @@ def router_loss(gate_softmax: torch.Tensor, affinity_softmax: torch.Tensor) -> t
 
 # ------------------------------------------------------------------------------------------------ the layer
 def competesmoe_forward(x: torch.Tensor, gate_w: torch.Tensor, experts: Sequence[ExpertW], k: int, out_dim: int,
-                        args: SimpleNamespace, competition: bool, return_id_experts: bool = False):
+                        args: SimpleNamespace, competition: bool, return_id_experts: bool = False,
+                        forced_selected: Optional[torch.Tensor] = None):
     """competesmoe.py:337-415.  `competition` stands for the schedule test at :347
     (x.requires_grad and current_steps >= step_warm and prob_flips[...] == 1).
-    Returns (output, auxiliary_loss, None, infor_aux, debug) where debug holds the routing tensors for parity tests."""
+    Returns (output, auxiliary_loss, None, infor_aux, debug) where debug holds the routing tensors for parity tests.
+    `forced_selected` [B,N,K]: evaluate the step under that routing decision (of the branch taken) instead of the
+    oracle's own top-k; debug["own_selected"] still holds the oracle's decision."""
     E = len(experts)
-    gate_weights, gate_sel, gate_softmax, gate_logits = router_policy(x, gate_w, k)
+    gate_weights, gate_sel, gate_softmax, gate_logits = router_policy(
+        x, gate_w, k, None if competition else forced_selected)
     auxiliary_loss = torch.tensor(0.0, dtype=x.dtype)
     infor_aux: Dict[str, torch.Tensor] = {}
     debug = {"gate_selected": gate_sel, "gate_weights": gate_weights, "gate_softmax": gate_softmax,
              "gate_logits": gate_logits}
     if competition:
-        aff_w, aff_sel, aff_softmax, aff, topk_out = competition_policy(x, experts, k, getattr(args, "norm_sigmoid", False))
+        aff_w, aff_sel, aff_softmax, aff, topk_out = competition_policy(x, experts, k, getattr(args, "norm_sigmoid", False),
+                                                                        forced_selected)
         if getattr(args, "hybrid", False):
             g_topk = torch.gather(gate_softmax, dim=-1, index=aff_sel)
             a_topk = torch.gather(aff_softmax, dim=-1, index=aff_sel)
@@ -164,6 +179,8 @@ def competesmoe_forward(x: torch.Tensor, gate_w: torch.Tensor, experts: Sequence
         infor_aux = {"balance_loss": balance.detach().clone(), "diversity_loss": diversity.detach().clone(),
                      "routerloss": routerloss.detach().clone()}
         debug.update(selected=aff_sel, weights=aff_w, affinity=aff, affinity_softmax=aff_softmax)
+        sc = torch.sigmoid(aff) if getattr(args, "norm_sigmoid", False) else aff
+        debug["own_selected"] = stable_topk(sc.detach(), k)[1]
     else:
         output = compute_moe(x, experts, gate_sel, gate_weights, out_dim)
         if x.requires_grad or return_id_experts:
@@ -172,6 +189,7 @@ def competesmoe_forward(x: torch.Tensor, gate_w: torch.Tensor, experts: Sequence
             auxiliary_loss = balance * args.balance_loss_coef + z * args.router_z_loss_coef   # moe.py:214-226
             infor_aux = {"balance_loss": balance.detach().clone(), "router_z_loss": z.detach().clone()}
         debug.update(selected=gate_sel, weights=gate_weights)
+        debug["own_selected"] = stable_topk(gate_softmax.detach(), k)[1]
     return output, auxiliary_loss, None, infor_aux, debug
 
 

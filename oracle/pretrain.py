@@ -16,7 +16,7 @@ from typing import Callable, Dict, Optional
 import torch
 import torch.nn.functional as F
 
-from .multimodal import stable_topk
+from .multimodal import _topk_or_forced, stable_topk
 
 
 def default_args(**kw) -> SimpleNamespace:
@@ -107,21 +107,21 @@ def compute_gate(x, w_gate, args, op_dtype):
     return F.linear(x.to(op_dtype), w_gate.to(op_dtype))
 
 
-def router_policy(x, w_gate, k, args, op_dtype):
-    """competesmoe.py:465-490."""
+def router_policy(x, w_gate, k, args, op_dtype, forced=None):
+    """competesmoe.py:465-490.  `forced`: see oracle.multimodal._topk_or_forced."""
     logits = compute_gate(x, w_gate, args, op_dtype)
     if getattr(args, "norm_sigmoid", False):
         gate_softmax = F.softmax(logits, dim=-1, dtype=torch.float32)
-        weights, selected = stable_topk(logits, k)
+        weights, selected = _topk_or_forced(logits, k, forced)
         weights = torch.sigmoid(weights / getattr(args, "scale_weight", 1.0))
     else:
         gate_softmax = F.softmax(logits, dim=-1, dtype=torch.float32)
-        weights, selected = stable_topk(gate_softmax, k)
+        weights, selected = _topk_or_forced(gate_softmax, k, forced)
     weights = weights / torch.sum(weights, dim=-1, keepdim=True).to(x.dtype)
     return weights, selected, gate_softmax, logits
 
 
-def competition_policy(x, keys, values, k, activation, op_dtype):
+def competition_policy(x, keys, values, k, activation, op_dtype, forced=None):
     """competesmoe.py:381-414 (competition_policy_mlp_faster): dense all-expert pass, score = mean softplus."""
     B, N, D = x.shape
     eo = torch.matmul(x.reshape(-1, D).to(op_dtype), keys.to(op_dtype))          # [E, T, H]
@@ -130,7 +130,7 @@ def competition_policy(x, keys, values, k, activation, op_dtype):
     eo = eo.transpose(1, 0)                                                      # [T, E, Dv]
     aff = torch.mean(F.softplus(eo.float()), dim=-1).view(B, N, -1)
     aff_softmax = F.softmax(aff, dim=-1, dtype=torch.float32)
-    weights, selected = stable_topk(aff, k)
+    weights, selected = _topk_or_forced(aff, k, forced)
     weights = weights / torch.sum(weights, dim=-1, keepdim=True).to(x.dtype)
     eo = eo.reshape(B, N, *eo.shape[1:])
     idx = selected.unsqueeze(-1).expand(B, N, k, eo.size(-1))
@@ -153,13 +153,15 @@ def compute_moe_main(x, selected, weights, keys, values, activation, op_dtype, b
 
 def competesmoe_forward(x: torch.Tensor, w_gate: torch.Tensor, keys: torch.Tensor, values: torch.Tensor, k: int,
                         args: SimpleNamespace, competition: bool, activation: Callable = F.relu,
-                        op_dtype: torch.dtype = torch.float32, bias=None, o_bias=None):
-    """competesmoe.py:524-616.  Returns (output [B,N,Dv], regs: name -> loss as passed to add_reg, debug)."""
+                        op_dtype: torch.dtype = torch.float32, bias=None, o_bias=None, forced_selected=None):
+    """competesmoe.py:524-616.  Returns (output [B,N,Dv], regs: name -> loss as passed to add_reg, debug).
+    `forced_selected` [B,N,K]: evaluate the branch taken under that routing decision (parity of values under identical
+    routing); debug["own_selected"] keeps the oracle's own decision."""
     regs: Dict[str, torch.Tensor] = {}
-    gw, gsel, gsoft, glogits = router_policy(x, w_gate, k, args, op_dtype)
+    gw, gsel, gsoft, glogits = router_policy(x, w_gate, k, args, op_dtype, None if competition else forced_selected)
     debug = {"gate_selected": gsel, "gate_weights": gw, "gate_softmax": gsoft, "gate_logits": glogits}
     if competition:
-        aw, asel, asoft, aff, topk_out = competition_policy(x, keys, values, k, activation, op_dtype)
+        aw, asel, asoft, aff, topk_out = competition_policy(x, keys, values, k, activation, op_dtype, forced_selected)
         out = compute_moe_main(x, asel, aw, keys, values, activation, op_dtype, bias)
         regs["mlp_comp_diver_loss"] = experts_diversity_loss(topk_out) * args.balance_loss_coef_comp / 2
         if args.balance_affinity:
@@ -176,11 +178,13 @@ def competesmoe_forward(x: torch.Tensor, w_gate: torch.Tensor, keys: torch.Tenso
         else:
             rl = router_loss(gsoft, asoft.detach())
         regs["mlp_router_loss"] = rl * args.router_loss_coef
-        debug.update(selected=asel, weights=aw, affinity=aff, affinity_softmax=asoft)
+        debug.update(selected=asel, weights=aw, affinity=aff, affinity_softmax=asoft,
+                     own_selected=stable_topk(aff.detach(), k)[1])
     else:
         out = compute_moe_main(x, gsel, gw, keys, values, activation, op_dtype, bias)
         regs["mlp_ebalance"] = entropy_balance(glogits) * (args.balance_loss_coef / 1)
-        debug.update(selected=gsel, weights=gw)
+        debug.update(selected=gsel, weights=gw, own_selected=stable_topk(
+            (glogits if getattr(args, "norm_sigmoid", False) else gsoft).detach(), k)[1])
     res = out.view(*x.shape[:-1], values.shape[-1])
     if o_bias is not None:
         res = res + o_bias

@@ -1,0 +1,251 @@
+"""Layer-level parity AT THE SHAPES THE BENCH AND BASELINE.json NAME, against the CPU oracle on the same seeded inputs:
+
+  C2   configs[1]: multimodal CompeteSMoE, Phi-3.5 SiLU-GLU experts d=3072 ffn=8192, E=4 top-2, 4096 tokens, bf16
+  C2'  projector-shaped experts 2304 -> 3072 -> 3072 (GELU, bias), E=4 top-2, 5 x 256 tokens, bf16
+  C4   configs[3]: pretrain CompeteSMoE D=1024, H=128, E=64 top-8, 4 x 1024 tokens, bf16 autocast over fp32 parameters
+  C3   configs[2] end points: E=8 top-2 and E=64 top-8 are covered by C1 (test_gpu_pretrain.py) and C4
+  bias pretrain layer with `bias=True` (hidden bias [E,H] + output bias [D]), router and competition step
+
+Both steps (router, competition); outputs, dx, the gate gradient, EVERY expert gradient and every loss.
+
+Routing decisions are compared with the oracle's own top-k bit-exactly, except on tokens whose top-k margin is below
+1e-3 (north_star), which are counted and printed.  Values are then compared under IDENTICAL routing: the oracle is
+evaluated with this path's selection (`forced_selected`), so every token and every gradient element takes part.
+Tolerance: bf16 rtol 2e-2 with an atol of rtol x RMS(reference tensor) -- the north-star's figure; the measured error of
+every tensor is printed so that the margin is on record (`pytest -s`)."""
+from types import SimpleNamespace
+
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from oracle import multimodal as om
+from oracle import pretrain as op
+
+from helpers import GLUExpert, assert_close_rms, expert_linears
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+RTOL = 2e-2
+
+
+def band_err(got, ref):
+    """max |got - ref| / (|ref| + rms(ref)): the quantity assert_close_rms bounds by rtol."""
+    got, ref = got.detach().float().cpu(), ref.detach().float().cpu()
+    rms = ref.pow(2).mean().sqrt()
+    return float(((got - ref).abs() / (ref.abs() + rms + 1e-30)).max())
+
+
+def check(got, ref, what, rtol=RTOL):
+    print(f"    {what:34s} band error {band_err(got, ref):.3e} (limit {rtol:.0e})")
+    assert_close_rms(got.detach(), ref.detach(), rtol, what)
+
+
+def routing_report(tag, sel_gpu, own, scores, k):
+    agree = (sel_gpu.cpu().long().reshape(own.shape) == own).all(-1)
+    margin = om.topk_margin(scores.detach(), k)
+    n_ex = int((~agree).sum())
+    assert bool((margin[~agree] < 1e-3).all()), f"{tag}: routing differs from the oracle on a token with margin >= 1e-3"
+    print(f"{tag}: routing bit-exact on {agree.numel() - n_ex}/{agree.numel()} tokens; {n_ex} differ, all with a "
+          f"top-k margin < 1e-3 (tokens with margin < 1e-3 overall: {int((margin < 1e-3).sum())})")
+
+
+# ------------------------------------------------------------------------------------------------ multimodal
+def _mm_case(experts_mod, exps, D_in, D_out, E, K, B, N, competition, seed):
+    from competesmoe_b200.multimodal import CompeteSMoE
+    args = om.default_args()
+    layer = CompeteSMoE(D_in, D_out, E, K, experts_mod, args).to(DEV, torch.bfloat16)
+    layer.total_steps, layer.step_warm = 4, 0
+    layer.prob_flips = torch.full((4,), bool(competition), device=DEV)
+    layer.set_current_steps(1)
+    gate_w = layer.gate.weight.detach().cpu().clone()
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, N, D_in, generator=g).bfloat16()
+    dy = torch.randn(B, N, D_out, generator=g).bfloat16()
+    xg = x.to(DEV).requires_grad_(True)
+    out, aux, none, info = layer(xg)
+    assert none is None and out.dtype == torch.bfloat16 and out.shape == (B, N, D_out)
+    ((out.float() * dy.to(DEV).float()).sum() + aux.float()).backward()
+    sel, w = layer.last_routing
+    # oracle under the same routing
+    leaves = [gate_w.requires_grad_(True)]
+    for e in exps:
+        for kk in ("w1", "b1", "w2", "b2"):
+            if e.get(kk) is not None:
+                e[kk] = e[kk].detach().clone().requires_grad_(True)
+                leaves.append(e[kk])
+    xr = x.clone().requires_grad_(True)
+    o_out, o_aux, _, o_info, dbg = om.competesmoe_forward(xr, gate_w, exps, K, D_out, args, competition,
+                                                          forced_selected=sel.cpu().long())
+    ((o_out.float() * dy.float()).sum() + o_aux.float()).backward()
+    return layer, xg, out, aux, info, sel, w, xr, o_out, o_aux, o_info, dbg, gate_w, exps
+
+
+def _mm_compare(tag, K, competition, layer, xg, out, aux, info, sel, w, xr, o_out, o_aux, o_info, dbg, gate_w, exps):
+    routing_report(tag, sel, dbg["own_selected"], dbg["affinity"] if competition else dbg["gate_softmax"], K)
+    check(out, o_out, "output")
+    check(w, dbg["weights"], "routing weights")
+    check(aux, o_aux, "auxiliary loss")
+    assert set(info) == set(o_info)
+    for k in info:
+        got, ref = float(info[k]), float(o_info[k])
+        print(f"    loss {k:29s} {got:.6f} (oracle {ref:.6f})")
+        assert abs(got - ref) <= RTOL * abs(ref) + 2e-3, (k, got, ref)
+    check(xg.grad, xr.grad, "dx")
+    check(layer.gate.weight.grad, gate_w.grad, "d gate.weight")
+    for e, (mod, ew) in enumerate(zip(layer.experts, exps)):
+        l1, l2 = expert_linears(mod)
+        check(l1.weight.grad, ew["w1"].grad, f"expert {e} d first.weight")
+        check(l2.weight.grad, ew["w2"].grad, f"expert {e} d second.weight")
+        if l1.bias is not None:
+            check(l1.bias.grad, ew["b1"].grad, f"expert {e} d first.bias")
+            check(l2.bias.grad, ew["b2"].grad, f"expert {e} d second.bias")
+
+
+@pytest.mark.parametrize("competition", [False, True], ids=["router", "competition"])
+def test_c2_bench_config_layer_matches_oracle(competition):
+    """BASELINE.json configs[1] exactly as bench.py builds it (bench.build_layer): d=3072, ffn=8192, 4 experts, top-2,
+    SiLU-GLU, bf16, one batch of 4096 tokens.  Reference: moe_model/model/moe/competesmoe.py:337-415."""
+    D, Fh, E, K, T = 3072, 8192, 4, 2, 4096
+    torch.manual_seed(0)
+    mods = nn.ModuleList([GLUExpert(D, Fh) for _ in range(E)])
+    exps = [{"kind": "glu", "act": "silu", "w1": m.gate_up_proj.weight.detach().bfloat16(),
+             "w2": m.down_proj.weight.detach().bfloat16()} for m in mods]
+    res = _mm_case(mods, exps, D, D, E, K, 1, T, competition, seed=1235)
+    _mm_compare(f"C2 {'competition' if competition else 'router'} step", K, competition, *res)
+
+
+@pytest.mark.parametrize("competition", [False, True], ids=["router", "competition"])
+def test_projector_real_dims_layer_matches_oracle(competition):
+    """The MoE projector the reference trains (multimodal_projector/builder.py:56-67): Sequential(Linear(2304, 3072),
+    GELU, Linear(3072, 3072)) experts, E=4 top-2, 5 samples x 256 image tokens."""
+    D_in, D_out, E, K, B, N = 2304, 3072, 4, 2, 5, 256
+    torch.manual_seed(1)
+    mods = nn.ModuleList([nn.Sequential(nn.Linear(D_in, D_out), nn.GELU(), nn.Linear(D_out, D_out)) for _ in range(E)])
+    exps = [{"kind": "mlp", "act": "gelu", "w1": m[0].weight.detach().bfloat16(), "b1": m[0].bias.detach().bfloat16(),
+             "w2": m[2].weight.detach().bfloat16(), "b2": m[2].bias.detach().bfloat16()} for m in mods]
+    res = _mm_case(mods, exps, D_in, D_out, E, K, B, N, competition, seed=1239)
+    _mm_compare(f"projector {'competition' if competition else 'router'} step", K, competition, *res)
+
+
+# ------------------------------------------------------------------------------------------------ pretrain
+def _pt_case(D, H, E, K, B, N, competition, seed, bias=False, args_kw=None):
+    from competesmoe_b200.pretrain import CompeteSMoE
+    torch.manual_seed(0)
+    args = op.default_args(stop_after=8, **(args_kw or {}))
+    layer = CompeteSMoE(D, E, H, n_heads=K, args=args, activation=F.relu, selection_mode="gate", log_interval=None,
+                        bias=bias)
+    if bias:
+        with torch.no_grad():
+            layer.bias.normal_(0, 0.3)
+            layer.o_bias.normal_(0, 0.3)
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, N, D, generator=g)
+    dy = torch.randn(B, N, D, generator=g)
+    names = ["w_gate", "keys", "values"] + (["bias", "o_bias"] if bias else [])
+    ref_p = {n: getattr(layer, n).detach().clone().requires_grad_(True) for n in names}
+    layer = layer.to(DEV)
+    layer.train()
+    layer.regularization_present = True
+    layer.step_warm = 0
+    layer.prob_flips_final = {0: torch.full((8,), bool(competition), device=DEV)}
+    layer.set_current_steps(0)
+    xg = x.to(DEV).requires_grad_(True)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        out = layer(xg, id_layer=0)
+        regs = layer.get_reg_loss()
+    assert out.dtype == torch.bfloat16
+    ((out.float() * dy.to(DEV)).sum() + sum(regs.values())).backward()
+    sel, w = layer.last_routing
+    xr = x.clone().requires_grad_(True)
+    o_out, o_regs, dbg = op.competesmoe_forward(xr, ref_p["w_gate"], ref_p["keys"], ref_p["values"], K, args, competition,
+                                                op_dtype=torch.bfloat16, bias=ref_p.get("bias"), o_bias=ref_p.get("o_bias"),
+                                                forced_selected=sel.cpu().long())
+    ((o_out.float() * dy).sum() + sum(o_regs.values())).backward()
+    return layer, names, ref_p, xg, out, regs, sel, w, xr, o_out, o_regs, dbg
+
+
+def _pt_compare(tag, K, competition, layer, names, ref_p, xg, out, regs, sel, w, xr, o_out, o_regs, dbg):
+    routing_report(tag, sel, dbg["own_selected"], dbg["affinity"] if competition else dbg["gate_softmax"], K)
+    check(out, o_out, "output")
+    check(w, dbg["weights"], "routing weights")
+    assert set(regs) == set(o_regs)
+    for k in regs:
+        got, ref = float(regs[k].detach()), float(o_regs[k].detach())
+        print(f"    reg {k:30s} {got:.6e} (oracle {ref:.6e})")
+        assert abs(got - ref) <= RTOL * abs(ref) + 2e-5, (k, got, ref)
+    check(xg.grad, xr.grad, "dx")
+    for n in names:
+        p = getattr(layer, n)
+        assert p.grad is not None and p.grad.dtype == torch.float32, n
+        check(p.grad, ref_p[n].grad, f"d {n}")
+
+
+@pytest.mark.parametrize("competition", [False, True], ids=["router", "competition"])
+def test_c4_pretrain_config_layer_matches_oracle(competition):
+    """BASELINE.json configs[3] (and the E=64 end of the configs[2] sweep): d_model=1024, expert size 128, 64 experts,
+    top-8, sequences of 1024, bf16 autocast over fp32 parameters (sweeps/slimpajama_moe_no_attmoe_154M_competesmoe.yaml;
+    moe_pretrain_model/layers/moe/competesmoe.py:524-616), 4 x 1024 tokens."""
+    res = _pt_case(1024, 128, 64, 8, 4, 1024, competition, seed=1237)
+    _pt_compare(f"C4 {'competition' if competition else 'router'} step", 8, competition, *res)
+
+
+@pytest.mark.parametrize("competition", [False, True], ids=["router", "competition"])
+def test_c3_mid_sweep_layer_matches_oracle(competition):
+    """configs[2] mid-sweep point: D=1024, H=128, 16 experts top-2, 2 x 1024 tokens, hybrid router loss + balance on the
+    affinity (the two optional regularisers of the competition step)."""
+    res = _pt_case(1024, 128, 16, 2, 2, 1024, competition, seed=1238, args_kw=dict(hybrid=True, balance_affinity=True))
+    _pt_compare(f"C3(E=16) {'competition' if competition else 'router'} step", 2, competition, *res)
+
+
+@pytest.mark.parametrize("competition", [False, True], ids=["router", "competition"])
+def test_pretrain_bias_path_matches_oracle(competition):
+    """`-moe.bias 1` (moe.py:129-134, :400-401, competesmoe.py:613-614): hidden bias[E,H] inside the selected experts,
+    o_bias[D] on the layer output; the competition's dense scoring pass runs WITHOUT the bias (:381-414)."""
+    res = _pt_case(256, 64, 8, 2, 2, 192, competition, seed=1240, bias=True)
+    _pt_compare(f"bias=True {'competition' if competition else 'router'} step", 2, competition, *res)
+
+
+def test_base_moe_forward_uses_raw_topk_probabilities():
+    """moe.py:418-449 / :373-393: the plain sigma-MoE forward weights the experts with the raw top-k softmax
+    probabilities (no renormalisation)."""
+    from competesmoe_b200.pretrain import MoE
+    torch.manual_seed(0)
+    D, H, E, K, B, N = 256, 64, 8, 2, 2, 128
+    args = op.default_args()
+    layer = MoE(D, E, H, n_heads=K, args=args, activation=F.relu, selection_mode="gate", log_interval=None)
+    wg, ks, vs = (p.detach().clone() for p in (layer.w_gate, layer.keys, layer.values))
+    layer = layer.to(DEV).train()
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(B, N, D, generator=g)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        out = layer(x.to(DEV).requires_grad_(True))
+    logits = F.linear(x.bfloat16(), wg.bfloat16())
+    probs = F.softmax(logits, dim=-1, dtype=torch.float32)
+    w, sel = om.stable_topk(probs, K)
+    ref = op.compute_moe_main(x, sel, w, ks, vs, F.relu, torch.bfloat16)
+    check(out, ref.view(B, N, D), "base MoE output")
+
+
+def test_relu_pass_rate_is_logged_every_log_interval():
+    """moe.py:405-414."""
+    from competesmoe_b200.pretrain import CompeteSMoE
+    torch.manual_seed(0)
+    D, H, E, K = 256, 64, 8, 2
+    args = op.default_args(stop_after=8)
+    layer = CompeteSMoE(D, E, H, n_heads=K, args=args, activation=F.relu, selection_mode="gate", log_interval=2).to(DEV)
+    layer.train()
+    layer.step_warm = 0
+    layer.prob_flips_final = {0: torch.zeros(8, dtype=torch.bool, device=DEV)}
+    x = torch.randn(2, 64, D, device=DEV, requires_grad=True)
+    seen = []
+    for it in range(4):
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            layer(x, id_layer=0)
+        logs = layer.get_logs()
+        seen.append("relu_pass_rate" in logs)
+        if seen[-1]:
+            assert 0.3 < float(logs["relu_pass_rate"]) < 0.7          # relu of zero-mean scores passes about half
+        layer.before_loss()
+    assert seen == [True, False, True, False]

@@ -235,3 +235,27 @@ def test_graph_mode_layers_deepcopy_cleanly():
     assert cm.forward.__self__ is cm and cm._graphs == {} and mm._graphs != {}
     cm.enable_cuda_graphs(False)
     assert "forward" not in cm.__dict__ or cm.forward.__func__ is type(cm).forward
+
+
+def test_forced_selection_reproduces_own_selection():
+    """`forced_selected` (used by the full-size GPU parity tests to compare values under identical routing) with the
+    oracle's own decision is the unforced evaluation, bit for bit, in both oracles and both branches."""
+    import torch.nn.functional as F
+    from oracle import multimodal as om
+    from oracle import pretrain as op
+    g = torch.Generator().manual_seed(5)
+    D, Fh, E, K = 32, 48, 6, 2
+    exps = [{"kind": "mlp", "act": "gelu", "w1": torch.randn(Fh, D, generator=g) * 0.2, "b1": torch.randn(Fh, generator=g) * 0.1,
+             "w2": torch.randn(D, Fh, generator=g) * 0.2, "b2": torch.randn(D, generator=g) * 0.1} for _ in range(E)]
+    gate_w = torch.randn(E, D, generator=g) * 0.3
+    x = torch.randn(2, 24, D, generator=g)
+    for comp in (False, True):
+        a = om.competesmoe_forward(x, gate_w, exps, K, D, om.default_args(), comp)
+        b = om.competesmoe_forward(x, gate_w, exps, K, D, om.default_args(), comp, forced_selected=a[4]["selected"])
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[4]["own_selected"], a[4]["selected"])
+    wg, ks, vs = torch.randn(E, D, generator=g) * 0.3, torch.randn(E, D, 16, generator=g) * 0.2, torch.randn(E, 16, D, generator=g) * 0.2
+    for comp in (False, True):
+        a = op.competesmoe_forward(x, wg, ks, vs, K, op.default_args(), comp)
+        b = op.competesmoe_forward(x, wg, ks, vs, K, op.default_args(), comp, forced_selected=a[2]["selected"])
+        assert torch.equal(a[0], b[0]) and torch.equal(a[2]["own_selected"], a[2]["selected"])
+        assert all(torch.equal(a[1][k], b[1][k]) for k in a[1])
