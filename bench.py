@@ -12,8 +12,13 @@ in a second region and reported under "competition"; "mix" is the schedule-weigh
 Prints ONE JSON line (rank 0).  `value` = tokens/s with inputs resident in HBM, CUDA-event timed, max over ranks;
 `e2e` = the same through the public nn.Module call with HOST buffers (pinned H2D of tokens and upstream gradient and a
 D2H read of the loss inside the timed region); `roofline` = the grouped GEMM's achieved TFLOP/s from per-launch CUDA
-events inside the timed region; `cpu_baseline` = the CPU oracle (port of the reference's PyTorch path) timed on this
-box's host cores on a bounded sample.  `--impl reference` times only that CPU path.
+events inside the timed region; `cpu_baseline` = the reference's CPU path timed on this box's host cores on a bounded sample
+(the reference's own modules when /root/reference is importable, else the oracle port -- `kind` says which).
+`configs` = the other BASELINE.json shapes (C1, the C3 sweep, C4, C5) at one GPU, router and competition step each;
+`hbm_stage` = achieved HBM GB/s of the permute / combine kernels; at N > 1 `ep_parity` (tests/ep_worker.py run on the
+job's ranks + a bitwise check of the bench layer against its unsharded copy) and `c4_ep` (configs[3] expert-parallel
+over all N ranks next to the unsharded layer on every GPU).  `--impl reference` times only the CPU path, at the
+requested --steps / --warmup, on all 4096 tokens of the workload.
 """
 from __future__ import annotations
 
@@ -152,46 +157,119 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU baseline
-def cpu_reference_step_time(steps: int, warmup: int, tokens: int = CPU_SAMPLE_TOKENS):
-    """The oracle (CPU port of the reference's PyTorch path) on this box's host cores; fp32 like BASELINE configs[0]."""
+REFERENCE_ROOTS = [os.environ.get("CSMOE_REFERENCE_ROOT", ""), "/root/reference"]
+
+
+class _GLUForward(GLUExpert):
+    """GLUExpert with the Phi3MLP forward (the reference layer deep-copies / calls whatever module it is handed)."""
+
+    def forward(self, x):
+        gate, up = self.gate_up_proj(x).chunk(2, dim=-1)
+        return self.down_proj(up * self.activation_fn(gate))
+
+
+def _reference_layer():
+    """The UNMODIFIED reference CompeteSMoE (moe_model/model/moe/competesmoe.py:9) when its tree is importable on this
+    machine (the build container; it does not travel to the GPU box), else None."""
+    import contextlib
+    import importlib
+    import io
+    for root in REFERENCE_ROOTS:
+        if root and (Path(root) / "moe_model" / "model" / "moe" / "competesmoe.py").exists():
+            try:
+                sys.path.insert(0, root)
+                with contextlib.redirect_stdout(io.StringIO()):
+                    importlib.import_module("moe_model.model.moe")
+                    reg = importlib.import_module("moe_model.model.moe.register")
+                return reg.get_moe("competesmoe"), root
+            except Exception as exc:       # missing optional dependency etc.: fall back to the port, say why
+                print(f"bench: reference at {root} not importable ({exc!r}); timing the oracle port", file=sys.stderr)
+            finally:
+                if sys.path and sys.path[0] == root:
+                    sys.path.pop(0)
+    return None, None
+
+
+def cpu_reference_step_time(steps: int, warmup: int, tokens: int = TOKENS, device: str = "cpu"):
+    """One router step (fwd + bwd) of the workload on the host cores, fp32 like BASELINE configs[0]: the reference's own
+    module when importable, else the oracle (CPU port of the same PyTorch path).  Returns (median s/step, cores, tokens,
+    kind, source).  device="cuda" runs the same eager code on the GPU (informational: the reference's GPU path)."""
     from oracle import multimodal as om
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    dt = torch.float32 if device == "cpu" else torch.bfloat16
     g = torch.Generator().manual_seed(1235)
-    exps = [{"kind": "glu", "act": "silu", "w1": (torch.randn(2 * FFN, D_MODEL, generator=g) * 0.02).requires_grad_(True),
-             "w2": (torch.randn(D_MODEL, FFN, generator=g) * 0.02).requires_grad_(True)} for _ in range(N_EXPERTS)]
-    gate_w = (torch.randn(N_EXPERTS, D_MODEL, generator=g) * 0.02).requires_grad_(True)
-    x = torch.randn(1, tokens, D_MODEL, generator=g).requires_grad_(True)
-    dy = torch.randn(1, tokens, D_MODEL, generator=g)
-    args = om.default_args()
+    x = torch.randn(1, tokens, D_MODEL, generator=g).to(device, dt).requires_grad_(True)
+    dy = torch.randn(1, tokens, D_MODEL, generator=g).to(device, dt)
+    ref_cls, root = _reference_layer() if device == "cpu" else (None, None)
+    if ref_cls is not None:
+        torch.manual_seed(0)
+        experts = nn.ModuleList([_GLUForward(D_MODEL, FFN) for _ in range(N_EXPERTS)])
+        layer = ref_cls(in_embed_dim=D_MODEL, out_embed_dim=D_MODEL, num_of_experts=N_EXPERTS, num_selected=TOP_K,
+                        expert=experts, args=layer_args())
+        layer.total_steps, layer.step_warm, layer.current_steps = 2, 0, 0
+        layer.prob_flips = torch.zeros(2)
+        layer.train()
+        leaves = list(layer.parameters())
+
+        def step():
+            out, aux, _, _ = layer(x)
+            torch.autograd.backward((out, aux), (dy, torch.ones_like(aux)))
+        kind, source = "reference", f"{root}/moe_model/model/moe/competesmoe.py (unmodified)"
+    else:
+        exps = [{"kind": "glu", "act": "silu",
+                 "w1": (torch.randn(2 * FFN, D_MODEL, generator=g) * 0.02).to(device, dt).requires_grad_(True),
+                 "w2": (torch.randn(D_MODEL, FFN, generator=g) * 0.02).to(device, dt).requires_grad_(True)} for _ in range(N_EXPERTS)]
+        gate_w = (torch.randn(N_EXPERTS, D_MODEL, generator=g) * 0.02).to(device, dt).requires_grad_(True)
+        leaves = [gate_w] + [e[k] for e in exps for k in ("w1", "w2")]
+        args = om.default_args()
+
+        def step():
+            out, aux, _, _, _ = om.competesmoe_forward(x, gate_w, exps, TOP_K, D_MODEL, args, competition=False)
+            torch.autograd.backward((out, aux), (dy, torch.ones_like(aux)))
+        kind, source = "port", "oracle/multimodal.py"
     times = []
     for i in range(warmup + steps):
-        for t in [x, gate_w] + [e[k] for e in exps for k in ("w1", "w2")]:
+        for t in [x] + leaves:
             t.grad = None
+        if device != "cpu":
+            torch.cuda.synchronize()
         t0 = time.perf_counter()
-        out, aux, _, _, _ = om.competesmoe_forward(x, gate_w, exps, TOP_K, D_MODEL, args, competition=False)
-        torch.autograd.backward((out, aux), (dy, torch.ones_like(aux)))
-        dt = time.perf_counter() - t0
+        step()
+        if device != "cpu":
+            torch.cuda.synchronize()
         if i >= warmup:
-            times.append(dt)
-    return statistics.median(times), cores, tokens
+            times.append(time.perf_counter() - t0)
+    return statistics.median(times), cores, tokens, kind, source
 
 
 def run_reference_arm(a):
+    """The reference's CPU implementation of the path on this box's host cores: every one of the requested --steps
+    (after --warmup) is one fwd + bwd router step over ALL 4096 tokens of the workload (about 2-3 s each on 16 cores)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps, warmup = max(1, min(a.steps, 5)), max(1, min(a.warmup, 2))
-    dt, cores, tokens = cpu_reference_step_time(steps, warmup)
+    steps, warmup = max(1, a.steps), max(1, a.warmup)
+    dt, cores, tokens, kind, source = cpu_reference_step_time(steps, warmup)
     v = tokens / dt
+    sample = f"all {tokens} tokens of the workload per step, fp32, router step, {source}"
     line = {"impl": "reference", "metric": "moe_layer_fwd_bwd_tokens_per_s", "value": v, "unit": "tokens/s",
             "n_gpus": a.gpus, "steps": steps, "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "step": "router", "sample": f"{tokens} of {TOKENS} tokens per step"},
-            "cpu_baseline": {"value": v, "unit": "tokens/s", "cores": cores, "kind": "port",
-                             "sample": f"{tokens} of {TOKENS} tokens per step, fp32, oracle/multimodal.py"},
+            "config": {"workload": WORKLOAD, "step": "router", "tokens_per_gpu": TOKENS,
+                       "note": "CPU arm: one process on the host cores whatever --gpus says"},
+            "cpu_baseline": {"value": v, "unit": "tokens/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": v, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    if torch.cuda.is_available():
+        # informational (BASELINE.md section 3): the same eager per-expert loop (torch.where + cuBLAS per expert, one host
+        # sync per expert) on the B200 in bf16 -- what the reference's GPU path does at this shape
+        try:
+            gdt, _, _, _, gsrc = cpu_reference_step_time(max(3, min(steps, 10)), 2, device="cuda")
+            line["gpu_eager_loop"] = {"value": tokens / gdt, "unit": "tokens/s", "ms_per_step": gdt * 1e3, "dtype": "bf16",
+                                      "what": f"{gsrc} run on cuda:0 (eager PyTorch / cuBLAS, none of this repo's kernels)"}
+        except Exception as exc:
+            line["gpu_eager_loop"] = {"unavailable": repr(exc)}
     print(json.dumps(line), flush=True)
 
 
@@ -297,6 +375,170 @@ def e2e_region(layer, x_host, dy_host, params, steps, warmup, dist_on, device):
     return float(ms) / steps, h2d, loss_host.numel() * loss_host.element_size()
 
 
+# ------------------------------------------------------------------------------------------------ extra sections
+def hbm_stage_gbs(device, peak_gbs):
+    """Achieved HBM bandwidth of the permutation / combine kernels (north_star stages 3 and 5) at the bench shape, each
+    timed alone with CUDA events, a 256 MiB buffer overwritten between iterations (L2 flush).  Algorithmic bytes per
+    SURVEY.md 8(d): gather reads T*D*s + the map, writes T*K*D*s; combine reads T*K*D*s + maps, writes T*D*s."""
+    from competesmoe_b200 import ops
+    T, K, E, D, s = TOKENS, TOP_K, N_EXPERTS, D_MODEL, 2
+    g = torch.Generator().manual_seed(3)
+    sel = torch.stack([torch.randperm(E, generator=g)[:K] for _ in range(T)]).int().to(device)
+    w = torch.rand(T, K, generator=g).to(device)
+    x = torch.randn(T, D, generator=g).to(device, torch.bfloat16)
+    route = ops.route_build(sel, E)
+    y = torch.randn(route.row_cap, D, device=device, dtype=torch.bfloat16)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+    cases = {
+        "gather_rows": (lambda: ops.gather_rows(x, route), T * D * s + T * K * D * s + route.row_cap * 4),
+        "combine_fwd": (lambda: ops.combine_fwd(y, route.slot_to_row, route.sel, w, T, K, round_each=True),
+                        T * K * D * s + T * D * s + T * K * 12),
+        "scatter_reduce": (lambda: ops.scatter_reduce(y, route.slot_to_row, T, K), T * K * D * s + T * D * s),
+    }
+    out = {}
+    for name, (fn, nbytes) in cases.items():
+        for _ in range(2):
+            fn()
+        tot = 0.0
+        for _ in range(8):
+            flush.fill_(1)
+            s0, e0 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            fn()
+            e0.record()
+            torch.cuda.synchronize()
+            tot += s0.elapsed_time(e0)
+        us = tot / 8 * 1e3
+        out[name] = {"us": round(us, 2), "algorithmic_bytes": nbytes, "gbs": round(nbytes / us / 1e3, 1),
+                     "frac_of_hbm_peak": round(nbytes / us / 1e3 / peak_gbs, 4)}
+    del flush
+    torch.cuda.empty_cache()
+    return out
+
+
+def named_configs(device, steps, peak_tf, peak_gbs):
+    """BASELINE.json configs[0], [2], [3], [4] at one GPU (shapes: SURVEY.md section 8 table), router and competition
+    step, fwd + bwd, inputs resident in HBM, CUDA events; the layers' CUDA-graph mode (`graphed_ms`) and the plain call
+    (`eager_ms`, with the number of libcsmoe launches per step).  Fractions: model FLOPs per SURVEY.md 8(d) against the
+    bf16 peak; for the sigma-MoE shapes (H = 128, HBM-bound) the unfused algorithmic bytes of the expert path against the
+    HBM peak."""
+    sys.path.insert(0, str(ROOT / "scripts"))
+    import config_sweep as cs
+    out = {}
+    for case in cs.cases(1):
+        if case.key.startswith("S_"):
+            continue
+        try:
+            case.launches = {}
+            eager = cs.time_case(case, device, None, max(3, steps // 4), 2, False, graphs=False)
+            launches = dict(case.launches)
+            graphed = cs.time_case(case, device, None, steps, 3, False, graphs=True)
+        except Exception as exc:   # one config failing must not cost the headline line
+            out[case.key] = {"error": repr(exc)}
+            torch.cuda.synchronize()
+            continue
+        entry = {"what": case.name, "tokens": case.T}
+        for comp, nm in ((False, "router"), (True, "competition")):
+            ms = min(graphed[comp], eager[comp])
+            tf = case.flops_per_token(comp) * case.T / (ms * 1e-3) / 1e12
+            e = {"ms_per_step": round(ms, 4), "graphed_ms": round(graphed[comp], 4), "eager_ms": round(eager[comp], 4),
+                 "launches_per_step": launches.get(comp), "tokens_per_s": round(case.T / (ms * 1e-3), 1),
+                 "model_tflops": round(tf, 2), "frac_of_bf16_peak": round(tf / peak_tf, 4)}
+            if not comp and case.kind == "pretrain":
+                gbs = case.bytes_per_token_router() * case.T / (ms * 1e-3) / 1e9
+                e.update(unfused_algorithmic_gbs=round(gbs, 1), frac_of_hbm_peak=round(gbs / peak_gbs, 4))
+            entry[nm] = e
+        out[case.key] = entry
+    return out
+
+
+def ep_parity_section(device, world, rank, bench_layer, x, dy, params):
+    """Expert-parallel parity on the ranks of THIS job: (1) tests/ep_worker.py (outputs, dx, every expert / gate gradient
+    of sharded vs unsharded layers, both plugins, both steps, ragged case) on a world-wide EP group; (2) the bench layer
+    itself against an unsharded copy of the same full layer on this rank's tokens -- the router step's output and dx do
+    not depend on where a row is computed, so they must agree bit for bit.  Any failure is reported, not swallowed."""
+    import torch.distributed as dist
+    res = {"world": world, "ok": True, "cases": []}
+    try:
+        sys.path.insert(0, str(ROOT / "tests"))
+        import ep_worker as ew
+        from competesmoe_b200.ep import EPGroup
+        group = EPGroup(None, device)
+        try:
+            for comp in (False, True):
+                ew.run_multimodal(group, device, kind="mlp", E=4 if world <= 4 else 8, K=2, D=256, Fh=520, B=2, N=200, competition=comp)
+                ew.run_multimodal(group, device, kind="glu", E=8, K=2, D=512, Fh=1024, B=1, N=1000, competition=comp)
+                ew.run_pretrain(group, device, E=16, K=4, D=256, H=128, B=2, N=300, competition=comp)
+                res["cases"] += [f"multimodal mlp {'comp' if comp else 'router'}", f"multimodal glu {'comp' if comp else 'router'}",
+                                 f"pretrain E=16 K=4 {'comp' if comp else 'router'}"]
+            ew.run_multimodal(group, device, kind="mlp", E=8, K=1, D=128, Fh=256, B=1, N=3 + 5 * group.rank, competition=False,
+                              max_tokens=3 + 5 * (group.world - 1))
+            res["cases"].append("ragged top-1")
+        finally:
+            group.close()
+        # (2) the bench layer against its unsharded twin (same seed -> same full weights)
+        local = build_layer(device, None)
+        set_branch(local, False)
+        set_branch(bench_layer, False)
+        xl = x.detach().clone().requires_grad_(True)
+        for p in local.parameters():
+            p.grad = None
+        out_l, aux_l, _, _ = local(xl)
+        torch.autograd.backward((out_l, aux_l), (dy, torch.ones_like(aux_l)))
+        for p in params:
+            p.grad = None
+        x.grad = None
+        out_e, aux_e, _, _ = bench_layer(x)
+        torch.autograd.backward((out_e, aux_e), (dy, torch.ones_like(aux_e)))
+        same = bool(torch.equal(out_e, out_l)) and bool(torch.equal(x.grad, xl.grad)) and \
+            bool(torch.equal(bench_layer.last_routing[0], local.last_routing[0]))
+        flag = torch.tensor([0 if same else 1], device=device)
+        dist.all_reduce(flag)
+        res["bench_layer_bitwise"] = int(flag) == 0
+        res["ok"] = res["ok"] and res["bench_layer_bitwise"]
+        del local, out_l, aux_l, xl
+        torch.cuda.empty_cache()
+    except Exception as exc:
+        res["ok"] = False
+        res["error"] = repr(exc)[:500]
+    if rank == 0:
+        print(f"EP parity {'ok' if res['ok'] else 'FAILED'} world={world}: {len(res['cases'])} ep_worker cases"
+              f"{', bench layer bitwise equal to its unsharded copy' if res.get('bench_layer_bitwise') else ''}"
+              f"{' -- ' + res['error'] if 'error' in res else ''}", file=sys.stderr, flush=True)
+    return res
+
+
+def c4_ep_section(device, world, rank, steps):
+    """BASELINE.json configs[3] (d=1024, H=128, 64 experts, top-8, bf16 autocast): 8192 tokens per GPU (N = 8 gives the
+    yaml's global batch of 64 x 1024), expert-parallel over all N ranks, next to the UNSHARDED layer running the same
+    per-GPU batch on every GPU at the same time (the 1-GPU program under the same power conditions).
+    efficiency = local_ms / ep_ms = tokens/s(N) / (N * tokens/s(1))."""
+    import torch.distributed as dist
+    sys.path.insert(0, str(ROOT / "scripts"))
+    import config_sweep as cs
+    from competesmoe_b200.ep import EPGroup
+    case = cs.Case("C4 pretrain LM layer d=1024 E=64 K=8 H=128, 8192 tokens/GPU", "pretrain", 8192, 1024, 128, 64, 8, key="C4")
+    out = {"what": case.name, "tokens_per_gpu": case.T, "world": world}
+    try:
+        local_eager = cs.time_case(case, device, None, steps, 3, True, graphs=False)
+        local_graph = cs.time_case(case, device, None, steps, 3, True, graphs=True)
+        group = EPGroup(None, device)
+        try:
+            ep = cs.time_case(case, device, group, steps, 3, True, graphs=False)
+        finally:
+            group.close()
+        for comp, nm in ((False, "router"), (True, "competition")):
+            best_local = min(local_eager[comp], local_graph[comp])
+            out[nm] = {"ep_ms": round(ep[comp], 4), "local_eager_ms": round(local_eager[comp], 4),
+                       "local_graphed_ms": round(local_graph[comp], 4),
+                       "tokens_per_s": round(case.T * world / (ep[comp] * 1e-3), 1),
+                       "efficiency_vs_local_best": round(best_local / ep[comp], 4),
+                       "efficiency_vs_local_eager": round(local_eager[comp] / ep[comp], 4)}
+    except Exception as exc:
+        out["error"] = repr(exc)[:500]
+    return out
+
+
 def run_ours(a):
     import torch.distributed as dist
     from competesmoe_b200 import ops
@@ -317,6 +559,7 @@ def run_ours(a):
         peaks = json.loads(pk.read_text())
     peak_tf, peak_src = (peaks["bf16_tflops"], "measured (MEASURED_PEAKS.json, burst)") if "bf16_tflops" in peaks else \
         (1590.0, "fallback (B200_PROFILING.md)")
+    peak_gbs = float(peaks.get("hbm_gbs", 6550.0))
 
     # N > 1: expert parallelism (north_star stage 6).  The 4 experts are sharded over EP groups of P = min(N, 4) ranks
     # (N = 8: two replicas of an EP4 group); tokens stay data-parallel, 4096 per GPU (weak scaling).
@@ -388,6 +631,16 @@ def run_ours(a):
     ms_e2e, h2d, d2h = e2e_region(layer, x_host, dy_host, params, a.steps, a.warmup, dist_on, device)
     clocks = sampler.stop() if sampler else None
 
+    # ---- outside the headline regions: the stage-3/5 kernels alone, the other named shapes, expert-parallel parity
+    hbm_stage = hbm_stage_gbs(device, peak_gbs) if a.sections else None
+    ep_parity = c4_ep = configs = None
+    if a.sections and ep_group is not None:
+        ep_parity = ep_parity_section(device, world, rank, layer, x, dy, params)
+    if a.sections and dist_on and 64 % world == 0:
+        c4_ep = c4_ep_section(device, world, rank, max(5, a.steps // 2))
+    if a.sections and world == 1:
+        configs = named_configs(device, max(6, a.steps // 2), peak_tf, peak_gbs)
+
     if rank == 0:
         tok = TOKENS * world
         value = tok / (ms_router * 1e-3)
@@ -395,9 +648,9 @@ def run_ours(a):
         mix_ms = (1 - RATE_FLIP) * ms_router + RATE_FLIP * ms_comp
         cpu = None
         if world == 1:
-            dt, cores, tokens = cpu_reference_step_time(2, 1)
-            cpu = {"value": tokens / dt, "unit": "tokens/s", "cores": cores, "kind": "port",
-                   "sample": f"{tokens} of {TOKENS} tokens per step, fp32, router step, oracle/multimodal.py"}
+            dt, cores, tokens, kind, source = cpu_reference_step_time(3, 1)
+            cpu = {"value": tokens / dt, "unit": "tokens/s", "cores": cores, "kind": kind,
+                   "sample": f"3 steps (after 1 warm-up) over all {tokens} tokens of the workload, fp32, router step, {source}"}
         traffic = None
         tf = ROOT / "profiles" / "gemm_traffic.json"
         if tf.exists():
@@ -429,7 +682,10 @@ def run_ours(a):
                          "peak_source": peak_src, "launches_per_step": len(timed) // max(a.steps, 1),
                          "share_of_step": gemm_share, "per_launch": gemm_detail},
             "cpu_baseline": cpu, "gpu_launches": launches, "clocks": clocks,
+            "hbm_stage": hbm_stage, "configs": configs, "ep_parity": ep_parity, "c4_ep": c4_ep,
         }
+        if traffic is not None:
+            line["roofline"]["traffic_source"] = "profiles/gemm_traffic.json (ncu --set full of the same launches, committed; not re-measured in this run)"
         print(json.dumps(line), flush=True)
     if ep_group is not None:
         ep_group.close()
@@ -444,6 +700,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--graphs", type=int, default=1, help="1: use the layer's CUDA-graph mode where available (single GPU / replicas)")
+    ap.add_argument("--sections", type=int, default=1,
+                    help="1: also report hbm_stage, the other named configs (N=1), EP parity and C4 expert-parallel (N>1)")
     ap.add_argument("--parallel", default="ep", choices=["ep", "replicas"],
                     help="N > 1: expert-parallel groups (default) or N independent replicas of the layer")
     a = ap.parse_args()

@@ -69,6 +69,13 @@ _SIGNATURES = {
     "csmoe_affinity_bwd": (i32, [vp, vp, i32, i32, i64, i64, i32, i32, vp, vp]),
     "csmoe_diversity_fwd": (i32, [vp, i32, i64, i64, i32, i32, vp, vp, vp, vp, vp, vp]),
     "csmoe_compete_bwd": (i32, [vp, i32, i32, i64, i64, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "csmoe_losses_workspace_bytes": (i64, [i64, i64, i32]),
+    "csmoe_losses_fwd": (i32, [vp, vp, vp, vp, i64, i64, i32, i32, vp, vp, vp, vp, vp, vp, vp]),
+    "csmoe_losses_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, i64, i64, i32, i32, vp, vp, vp]),
+    "csmoe_entropy_balance_fwd": (i32, [vp, i64, i64, i32, vp, vp, vp, vp]),
+    "csmoe_entropy_balance_bwd": (i32, [vp, vp, i64, i64, i32, vp, vp]),
+    "csmoe_topk_renorm_bwd": (i32, [vp, vp, vp, vp, i64, i32, i32, i32, i32, vp, vp]),
+    "csmoe_dense_rows": (i32, [vp, i64, i32, i64, vp, vp]),
     "csmoe_ep_ipc_handle_bytes": (i32, []),
     "csmoe_ep_alloc": (i32, [i64, C.POINTER(vp), vp]),
     "csmoe_ep_open": (i32, [vp, C.POINTER(vp)]),

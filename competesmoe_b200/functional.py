@@ -5,6 +5,9 @@
   DenseFFNFn    every expert on every token (competition step)           reference: competesmoe.py:240-245 / :399-403
   AffinityFn    mean softplus score of each (token, expert)              reference: competesmoe.py:243 / :403
   SelectCombineFn  gate-weighted sum of the selected dense outputs        reference: recomputed by compute_moe (:374)
+  CompeteLossesFn  softmax(affinity) + distillation MSE variants + balance / entropy balance on the affinity, one kernel
+                   pair forward, one backward   reference: competesmoe.py:322-335,350-371 / layers/moe/competesmoe.py:541-593
+  EntropyBalanceFn router-step entropy balance of the pretrain layer from the router's probabilities (moe.py:323-332)
   CompeteTailFn everything downstream of the dense expert outputs of a competition step (score, top-k, combine,
                 diversity loss) with ONE backward kernel for d(dense outputs)  reference: competesmoe.py:219-259,:371-374
 
@@ -46,7 +49,7 @@ class FFNSpec:
     kn_layout: bool = False  # False: w1 [E,F,D], w2 [E,Dout,F] (nn.Linear);  True: w1 [E,D,H], w2 [E,H,Dout] (sigma-MoE)
     round_each: bool = True  # combine: round the running sum to the activation dtype after every expert (moe.py:204)
     round_w: bool = False    # combine: round the routing weight to the activation dtype first (cvmm.py:483)
-    return_hidden: bool = False  # SparseFFNFn also returns h = act(z) [row_cap, H] (non-differentiable; relu_pass_rate log)
+    return_hidden: bool = False  # SparseFFNFn also returns (h = act(z) [row_cap, H], row_to_slot) for the relu_pass_rate log
 
     @property
     def glu(self) -> bool:
@@ -137,13 +140,13 @@ class SparseFFNFn(Function):
         ctx.wb = (w1b if w1b is not w1 else None, w2b if w2b is not w2 else None)
         if spec.return_hidden:
             hd = h.detach()
-            ctx.mark_non_differentiable(hd)
-            return out, hd
+            ctx.mark_non_differentiable(hd, route.row_to_slot)
+            return out, hd, route.row_to_slot
         return out
 
     @staticmethod
     @once_differentiable
-    def backward(ctx, dout, _dh=None):
+    def backward(ctx, dout, _dh=None, _dmap=None):
         xp, z, h, y, w, w1, w2 = ctx.saved_tensors
         route, spec = ctx.route, ctx.spec
         T, K, E = route.n_slots // route.top_k, route.top_k, route.num_experts
@@ -340,7 +343,7 @@ class CompeteTailFn(Function):
         else:
             aff = ops.affinity_fwd(y, num_experts, T, t_pad, eager_bf16)
         w, idx = ops.topk_renorm(aff, top_k, sigmoid=sigmoid, round_dtype=x_dtype, round_out=eager_bf16)
-        rows = (idx.long() * t_pad + torch.arange(T, device=idx.device).unsqueeze(1)).to(torch.int32).reshape(-1)
+        rows = ops.dense_rows(idx, t_pad)
         out = ops.combine_fwd(y, rows, idx.reshape(-1), w, T, top_k, round_each=spec.round_each, round_w=spec.round_w)
         div, inv_norm, sim = ops.diversity_fwd(y, idx, T, t_pad)
         ctx.save_for_backward(y, aff, w, idx, rows, inv_norm, sim)
@@ -359,18 +362,55 @@ class CompeteTailFn(Function):
             dwc = ops.combine_bwd_w(y, dout, rows, T, K)
             dw = dwc if dw is None else dw + dwc
         if dw is not None:
-            # top-k renormalisation backward: w = v / sum(v), v = scores (or sigmoid(scores)) at idx
-            li = idx.long()
-            v = torch.gather(aff, 1, li)
-            if sigmoid:
-                v = torch.sigmoid(v)
-            dv = (dw - (dw * w).sum(-1, keepdim=True)) / v.sum(-1, keepdim=True)
-            if sigmoid:
-                dv = dv * v * (1 - v)
-            ds = torch.zeros_like(aff).scatter_add_(1, li, dv)
-            daff = ds if daff is None else daff + ds
+            # top-k renormalisation backward (w = v / sum(v), v = scores or sigmoid(scores) at idx), added to the incoming
+            # d aff in the same kernel
+            daff = ops.topk_renorm_bwd(aff, w, idx, dw, sigmoid, out=None if daff is None else daff.contiguous().float().clone())
         wu = w.to(torch.bfloat16).float() if spec.round_w else w
         dy = ops.compete_bwd(y, E, T, t_pad, idx, daff=daff, w=wu if dout is not None else None, dout=dout,
                              inv_norm=inv_norm if ddiv is not None else None, sim=sim if ddiv is not None else None,
                              g_div=ddiv)
         return dy, None, None, None, None, None, None, None, None
+
+
+# ------------------------------------------------------------------------------------------------ losses
+class CompeteLossesFn(Function):
+    """(p [T,E] gate softmax, aff [T,E] scores, aff_idx [T,K] i32, gate_idx [T,K] i32 or None) -> (q [T,E], losses [5]).
+
+    q = softmax(aff) (not differentiable here: its only consumers are the losses below);
+    losses = (MSE(p, q), MSE at aff_idx, MSE at gate_idx, multimodal balance(aff_idx, q), pretrain entropy_balance(q)).
+    Gradients: p from the three MSE terms (q detached, as in the reference), aff from the two balance terms."""
+
+    @staticmethod
+    def forward(ctx, p, aff, aff_idx, gate_idx, batch: int):
+        q, losses, cnt, colr = ops.losses_fwd(p, aff, aff_idx, gate_idx, batch)
+        ctx.save_for_backward(p, q, aff_idx, gate_idx, cnt, colr)
+        ctx.batch = batch
+        ctx.mark_non_differentiable(q)
+        return q, losses
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, _dq, dlosses):
+        p, q, aff_idx, gate_idx, cnt, colr = ctx.saved_tensors
+        if dlosses is None:
+            return None, None, None, None, None
+        dp, daff = ops.losses_bwd(p, q, aff_idx, gate_idx, cnt, colr, dlosses, ctx.batch)
+        return (dp if ctx.needs_input_grad[0] else None), (daff if ctx.needs_input_grad[1] else None), None, None, None
+
+
+class EntropyBalanceFn(Function):
+    """probs [T,E] f32 (batch-major, T = batch * N) -> mean_b sum_e m log m with m = mean_n probs: the pretrain layer's
+    `entropy_balance(gate_logits)` (layers/moe/moe.py:323-332; log_softmax(logits) is the log of these probabilities)."""
+
+    @staticmethod
+    def forward(ctx, probs, batch: int):
+        loss, colr = ops.entropy_balance_fwd(probs, batch)
+        ctx.save_for_backward(colr)
+        ctx.dims = (batch, probs.shape[0] // batch)
+        return loss
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        (colr,) = ctx.saved_tensors
+        return ops.entropy_balance_bwd(colr, g, *ctx.dims), None

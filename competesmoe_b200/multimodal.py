@@ -18,7 +18,7 @@ from torch.autograd.function import once_differentiable
 
 from . import experts as X
 from . import ops
-from .functional import CompeteTailFn, DenseFFNFn, FFNSpec, GateFn, SparseFFNFn
+from .functional import CompeteLossesFn, CompeteTailFn, DenseFFNFn, FFNSpec, GateFn, SparseFFNFn
 from .graphs import capture_guard
 from .schedule import make_layer_schedule
 
@@ -60,16 +60,7 @@ class TopkRenormFn(Function):
     @once_differentiable
     def backward(ctx, dw, _):
         scores, w, idx = ctx.saved_tensors
-        li = idx.long()
-        v = torch.gather(scores, 1, li)
-        if ctx.sigmoid:
-            v = torch.sigmoid(v)
-        s = v.sum(-1, keepdim=True)
-        dv = (dw - (dw * w).sum(-1, keepdim=True)) / s
-        if ctx.sigmoid:
-            dv = dv * v * (1 - v)
-        ds = torch.zeros_like(scores).scatter_add_(1, li, dv)
-        return ds, None, None, None
+        return ops.topk_renorm_bwd(scores, w, idx, dw, ctx.sigmoid), None, None, None
 
 
 class MoeLayer(nn.Module):
@@ -102,8 +93,8 @@ class MoeLayer(nn.Module):
     def enable_cuda_graphs(self, enabled: bool = True):
         """Opt in: training-mode calls with a CUDA input that requires grad are replayed from captured CUDA graphs (one
         forward graph + one backward graph per (branch, shape, dtype), torch.cuda.make_graphed_callables), removing the
-        per-kernel launch gaps of the ~40-launch step.  Everything else (eval, no-grad, autocast, expert parallelism,
-        return_id_experts) takes the normal path.  Parameters may change value between calls, not storage."""
+        per-kernel launch gaps of the ~40-launch step; CUDA autocast state is part of the graph key.  Everything else (eval,
+        no-grad, expert parallelism, return_id_experts) takes the normal path.  Parameters may change value between calls, not storage."""
         self._graphs = {} if enabled else None
         # layers without their own graph dispatch (the sibling routers) get it through an instance-level wrapper
         if not hasattr(type(self), "_forward_impl"):
@@ -130,7 +121,8 @@ class MoeLayer(nn.Module):
             return self._eager_forward(x, return_id_experts, is_vision)
         self._stacked_weights()
         params = tuple(p for p in self.parameters() if p.requires_grad)
-        key = (bool(is_vision), tuple(x.shape), x.dtype, tuple(p.data_ptr() for p in params))
+        ac_on, ac_dt = self._autocast_state()
+        key = (bool(is_vision), tuple(x.shape), x.dtype, ac_on, ac_dt, tuple(p.data_ptr() for p in params))
         entry = self._graphs.get(key)
         if entry is None:
             names: List[str] = []
@@ -138,12 +130,13 @@ class MoeLayer(nn.Module):
             keep = {n: getattr(self, n).detach().clone() for n in self._inplace_params}
 
             def fn(xx, *_params):
-                out, aux, _, info = self._eager_forward(xx, False, is_vision)
+                with torch.autocast("cuda", dtype=ac_dt, enabled=ac_on, cache_enabled=False):
+                    out, aux, _, info = self._eager_forward(xx, False, is_vision)
                 names[:] = sorted(info)
                 return (out, aux) + tuple(info[k] for k in names)
 
             sample = x.detach().clone().requires_grad_(True)
-            with capture_guard():
+            with capture_guard(), torch.autocast("cuda", dtype=ac_dt, enabled=ac_on, cache_enabled=False):
                 graphed = torch.cuda.make_graphed_callables(fn, (sample,) + params, allow_unused_input=True)
             with torch.no_grad():
                 for n, v in keep.items():
@@ -157,24 +150,32 @@ class MoeLayer(nn.Module):
 
     def _graph_eligible(self, x, return_id_experts) -> bool:
         return (self._graphs is not None and self._ep is None and self.training and x.is_cuda and x.requires_grad
-                and torch.is_grad_enabled() and not return_id_experts and not torch.is_autocast_enabled()
+                and torch.is_grad_enabled() and not return_id_experts
                 and not torch.cuda.is_current_stream_capturing())
+
+    @staticmethod
+    def _autocast_state():
+        """(enabled, dtype) of CUDA autocast: part of the graph key, and re-entered (weight cache off) around the capture
+        so that the captured forward sees what the eager call would."""
+        return torch.is_autocast_enabled(), torch.get_autocast_dtype("cuda")
 
     def _graphed_call(self, x, branch: bool):
         self._stacked_weights()          # storage fusing re-points expert .data once: do it before keying on pointers
         params = tuple(p for p in self.parameters() if p.requires_grad)
-        key = (branch, tuple(x.shape), x.dtype, tuple(p.data_ptr() for p in params))
+        ac_on, ac_dt = self._autocast_state()
+        key = (branch, tuple(x.shape), x.dtype, ac_on, ac_dt, tuple(p.data_ptr() for p in params))
         entry = self._graphs.get(key)
         if entry is None:
             names: List[str] = []
 
             def fn(xx, *_params):
-                out, aux, _, info = self._forward_impl(xx, False)
+                with torch.autocast("cuda", dtype=ac_dt, enabled=ac_on, cache_enabled=False):
+                    out, aux, _, info = self._forward_impl(xx, False)
                 names[:] = sorted(info)
                 return (out, aux) + tuple(info[k] for k in names)
 
             sample = x.detach().clone().requires_grad_(True)
-            with capture_guard():
+            with capture_guard(), torch.autocast("cuda", dtype=ac_dt, enabled=ac_on, cache_enabled=False):
                 graphed = torch.cuda.make_graphed_callables(fn, (sample,) + params)
             entry = (graphed, names, self.last_routing)
             self._graphs[key] = entry
@@ -386,14 +387,14 @@ class CompeteSMoE(MoeLayer):
             # recomputed as compute_moe does at competesmoe.py:374) and diversity loss: one autograd node
             aff, aff_w, aff_idx, out, diversity_loss = CompeteTailFn.apply(
                 y_all, E, T, t_pad, K, bool(getattr(self.args, "norm_sigmoid", False)), x.dtype, spec, score_sums)
-            aff_softmax = F.softmax(aff, dim=-1, dtype=torch.float32)
-            li = aff_idx.long()
+            # softmax(affinity), distillation MSE (+ the hybrid top-k term) and the balance loss on the affinity: one kernel
+            # pair forward and one backward (competesmoe.py:350-371, moe.py:90-110)
+            _, comp_losses = CompeteLossesFn.apply(gate_softmax, aff, aff_idx, None, B)
             if getattr(self.args, "hybrid", False):
-                routerloss = self.router_loss(gate_softmax, aff_softmax.detach()) + self.router_loss(
-                    torch.gather(gate_softmax, -1, li), torch.gather(aff_softmax, -1, li).detach()) * self.args.router_theta
+                routerloss = comp_losses[0] + comp_losses[1] * self.args.router_theta
             else:
-                routerloss = self.router_loss(gate_softmax, aff_softmax.detach())
-            balance_loss = self.balanceloss(aff_idx.view(B, N, K), aff_softmax.view(B, N, E))
+                routerloss = comp_losses[0]
+            balance_loss = comp_losses[3]
             auxiliary_loss = routerloss * self.args.router_loss_coef + diversity_loss * self.args.diversity_loss_coef + \
                 balance_loss * self.args.bal_comp_loss_coef
             self.last_routing = (aff_idx.view(B, N, K), aff_w.detach().view(B, N, K))

@@ -524,3 +524,84 @@ def compete_bwd(y: torch.Tensor, num_experts: int, T: int, t_pad: int, sel: torc
     _call("csmoe_compete_bwd", _p(y), _dt(y), num_experts, T, t_pad, D, K, _p(daff), _p(sel), _p(w), _p(dout),
           _p(inv_norm), _p(sim), _p(g_div), _p(dy), _stream())
     return dy
+
+
+# ----------------------------------------------------------------------------------------------- losses
+def losses_fwd(p: torch.Tensor, aff: torch.Tensor, aff_idx: torch.Tensor, gate_idx: Optional[torch.Tensor], batch: int):
+    """Competition-step losses (csmoe_losses_fwd) -> (q [T,E], losses [5], cnt [B,E], colr [B,E])."""
+    _cuda(p, aff, aff_idx, gate_idx)
+    T, E = p.shape
+    K = aff_idx.shape[1]
+    assert T % batch == 0 and p.dtype == torch.float32 and aff.dtype == torch.float32 and aff_idx.dtype == torch.int32
+    N = T // batch
+    p, aff, aff_idx = p.contiguous(), aff.contiguous(), aff_idx.contiguous()
+    gate_idx = None if gate_idx is None else gate_idx.contiguous()
+    f32 = dict(dtype=torch.float32, device=p.device)
+    ws = torch.empty(int(_lib.load().csmoe_losses_workspace_bytes(batch, N, E)) // 4, **f32)
+    q = torch.empty(T, E, **f32)
+    colq, cnt, colr = (torch.empty(batch, E, **f32) for _ in range(3))
+    losses = torch.empty(5, **f32)
+    _call("csmoe_losses_fwd", _p(p), _p(aff), _p(aff_idx), _p(gate_idx), batch, N, E, K, _p(q), _p(colq), _p(cnt), _p(colr),
+          _p(losses), _p(ws), _stream(), kernels=2)
+    return q, losses, cnt, colr
+
+
+def losses_bwd(p, q, aff_idx, gate_idx, cnt, colr, g: torch.Tensor, batch: int):
+    """-> (dp [T,E], daff [T,E]); g [5] f32 on the device."""
+    _cuda(p, q, aff_idx, gate_idx, cnt, colr, g)
+    T, E = p.shape
+    K = aff_idx.shape[1]
+    g = g.contiguous().float()
+    dp = torch.empty_like(p)
+    daff = torch.empty_like(p)
+    _call("csmoe_losses_bwd", _p(p), _p(q), _p(aff_idx), _p(gate_idx), _p(cnt), _p(colr), _p(g), batch, T // batch, E, K,
+          _p(dp), _p(daff), _stream())
+    return dp, daff
+
+
+def entropy_balance_fwd(probs: torch.Tensor, batch: int):
+    """-> (loss [] f32, colr [B,E]) with loss = mean_b sum_e m log m, m = mean_n probs."""
+    _cuda(probs)
+    T, E = probs.shape
+    assert T % batch == 0 and probs.dtype == torch.float32
+    probs = probs.contiguous()
+    N = T // batch
+    f32 = dict(dtype=torch.float32, device=probs.device)
+    ws = torch.empty(int(_lib.load().csmoe_losses_workspace_bytes(batch, N, E)) // 4, **f32)
+    colr = torch.empty(batch, E, **f32)
+    loss = torch.empty(1, **f32)
+    _call("csmoe_entropy_balance_fwd", _p(probs), batch, N, E, _p(colr), _p(loss), _p(ws), _stream(), kernels=2)
+    return loss[0], colr
+
+
+def entropy_balance_bwd(colr: torch.Tensor, g: torch.Tensor, batch: int, N: int) -> torch.Tensor:
+    _cuda(colr, g)
+    E = colr.shape[1]
+    g = g.reshape(1).contiguous().float()
+    dprobs = torch.empty(batch * N, E, dtype=torch.float32, device=colr.device)
+    _call("csmoe_entropy_balance_bwd", _p(colr), _p(g), batch, N, E, _p(dprobs), _stream())
+    return dprobs
+
+
+def topk_renorm_bwd(scores, w, idx, dw, sigmoid: bool, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """d scores [T,E] of csmoe_topk_renorm; added into `out` when given."""
+    _cuda(scores, w, idx, dw, out)
+    T, E = scores.shape
+    K = idx.shape[1]
+    dw = dw.contiguous().float()
+    acc = out is not None
+    if out is None:
+        out = torch.empty_like(scores)
+    assert out.dtype == torch.float32 and out.is_contiguous()
+    _call("csmoe_topk_renorm_bwd", _p(scores), _p(w), _p(idx), _p(dw), T, E, K, 1 if sigmoid else 0, 1 if acc else 0, _p(out),
+          _stream())
+    return out
+
+
+def dense_rows(idx: torch.Tensor, t_pad: int) -> torch.Tensor:
+    """[T,K] i32 expert ids -> flat i32 row indices idx * t_pad + t into the dense [E * t_pad, D] outputs."""
+    _cuda(idx)
+    T, K = idx.shape
+    rows = torch.empty(T * K, dtype=torch.int32, device=idx.device)
+    _call("csmoe_dense_rows", _p(idx.contiguous()), T, K, t_pad, _p(rows), _stream())
+    return rows

@@ -17,7 +17,7 @@ import torch
 import torch.nn.functional as F
 
 from . import ops
-from .functional import CompeteTailFn, DenseFFNFn, FFNSpec, GateFn, SparseFFNFn
+from .functional import CompeteLossesFn, CompeteTailFn, DenseFFNFn, EntropyBalanceFn, FFNSpec, GateFn, SparseFFNFn
 from .graphs import capture_guard
 from .multimodal import TopkRenormFn
 from .schedule import make_layer_schedule
@@ -372,11 +372,13 @@ class MoE(LoggingLayer, RegularizedLayer, OncePerIterLayer, torch.nn.Module):
         return (self.log_interval is not None and self.iter % self.log_interval == 0
                 and not (torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()))
 
-    def _log_relu_pass_rate(self, h, n_slots: int):
-        """moe.py:405-414: fraction of positive hidden activations.  h is the padded expert-major [row_cap, H] buffer;
-        padding rows are zero, so they never count, and the denominator is the number of routed activations."""
+    def _log_relu_pass_rate(self, h, row_to_slot, n_slots: int):
+        """moe.py:405-414: fraction of positive hidden activations.  h is the padded expert-major [row_cap, H] buffer:
+        only rows that hold a routed slot count (padding rows inside a tile are zero, tiles past the end are never
+        written), and the denominator is the number of routed activations."""
         with torch.no_grad():
-            self.log("relu_pass_rate", (h > 0).sum().float() / float(n_slots * h.shape[1]))
+            routed = (row_to_slot >= 0).unsqueeze(1)
+            self.log("relu_pass_rate", ((h > 0) & routed).sum().float() / float(n_slots * h.shape[1]))
 
     def compute_moe_main(self, x2, selected, weights, cdt):
         if self._ep is not None:
@@ -385,8 +387,9 @@ class MoE(LoggingLayer, RegularizedLayer, OncePerIterLayer, torch.nn.Module):
                                        self._spec(cdt), self._ep)
         if self._plot_training():
             spec = dataclasses.replace(self._spec(cdt), return_hidden=True)
-            out, h = SparseFFNFn.apply(self._cast(x2, cdt), weights, selected, self.keys, self.bias, self.values, None, spec)
-            self._log_relu_pass_rate(h, selected.numel())
+            out, h, row_to_slot = SparseFFNFn.apply(self._cast(x2, cdt), weights, selected, self.keys, self.bias, self.values,
+                                                    None, spec)
+            self._log_relu_pass_rate(h, row_to_slot, selected.numel())
             return out
         return SparseFFNFn.apply(self._cast(x2, cdt), weights, selected, self.keys, self.bias, self.values, None, self._spec(cdt))
 
@@ -532,34 +535,31 @@ class CompeteSMoE(MoE):
                                                  x.dtype == torch.bfloat16)          # [E * t_pad, Dv]
             t_pad = y_all.shape[0] // E
             aff, aff_w, aff_idx, out, diver = CompeteTailFn.apply(y_all, E, T, t_pad, K, False, x.dtype, spec, score_sums)
+            self.nb_diver += K * (K - 1) * T
             if self.bias is not None:
                 out = self.compute_moe_main(x2, aff_idx, aff_w, cdt)
-            self.nb_diver += K * (K - 1) * T
-            aff_softmax = F.softmax(aff, dim=-1, dtype=torch.float32)
-            li = aff_idx.long()
+            # softmax(affinity), every router-loss variant and the entropy balance on the affinity from one kernel pair
+            # (competesmoe.py:541-593): losses = (MSE, MSE at the competition's top-k, MSE at the router's top-k, -, ebalance)
+            _, cl = CompeteLossesFn.apply(gate_softmax, aff, aff_idx, gate_idx if a.tribrid and not (a.in_topk or a.hybrid) else None,
+                                          lead[0] if len(lead) > 1 else 1)
             self.add_reg(lambda: diver * a.balance_loss_coef_comp / 2, self.name_moe + "_comp_diver_loss")
             if a.balance_affinity:
-                bal = self.entropy_balance(aff_softmax.view(*lead, E))
-                self.add_reg(lambda: bal * a.balance_loss_coef_comp / 2, f"{self.name_moe}_comp_ebalance")
-            g_top = lambda idx: torch.gather(gate_softmax, -1, idx)          # noqa: E731
-            a_top = lambda idx: torch.gather(aff_softmax, -1, idx).detach()  # noqa: E731
+                self.add_reg(lambda: cl[4] * a.balance_loss_coef_comp / 2, f"{self.name_moe}_comp_ebalance")
             if a.in_topk:
-                rl = self.router_loss(g_top(li), a_top(li))
+                rl = cl[1]
             elif a.hybrid:
-                rl = self.router_loss(gate_softmax, aff_softmax.detach()) + self.router_loss(g_top(li), a_top(li)) * a.router_theta
+                rl = cl[0] + cl[1] * a.router_theta
             elif a.tribrid:
-                gi = gate_idx.long()
-                rl = self.router_loss(gate_softmax, aff_softmax.detach()) + \
-                    self.router_loss(g_top(li), a_top(li)) * a.router_theta + \
-                    self.router_loss(g_top(gi), a_top(gi)) * a.router_theta
+                rl = cl[0] + cl[1] * a.router_theta + cl[2] * a.router_theta
             else:
-                rl = self.router_loss(gate_softmax, aff_softmax.detach())
+                rl = cl[0]
             self.add_reg(lambda: rl * a.router_loss_coef, f"{self.name_moe}_router_loss")
             self.last_routing = (aff_idx.view(*lead, K), aff_w.detach().view(*lead, K))
         else:
             out = self.compute_moe_main(x2, gate_idx, gate_w, cdt)
-            lg = gate_logits.view(*lead, E)
-            self.add_reg(lambda: self.entropy_balance(lg) * (a.balance_loss_coef / self.div), f"{self.name_moe}_ebalance")
+            if self.reg_enabled:   # entropy_balance(gate_logits) (:603-605) from the router kernel's probabilities
+                eb = EntropyBalanceFn.apply(gate_softmax, lead[0] if len(lead) > 1 else 1)
+                self.add_reg(lambda: eb * (a.balance_loss_coef / self.div), f"{self.name_moe}_ebalance")
             self.last_routing = (gate_idx.view(*lead, K), gate_w.detach().view(*lead, K))
         self.layer += 1
         if a.test_only:

@@ -252,6 +252,45 @@ int csmoe_compete_bwd(const void* y, int32_t dtype, int32_t E, int64_t T, int64_
                       const float* daff, const int32_t* sel, const float* w, const void* dout, const float* inv_norm,
                       const float* sim, const float* g_div, void* dy, void* stream);
 
+/* ------------------------------------------------------------------------------------------------ losses
+ * Competition-step losses in one pass over [T, E] (T = B * N tokens, batch-major) + a fixed-order reduction.  Replaces
+ * F.softmax(affinity), the router-distillation MSE and its in_topk / hybrid / tribrid gathers, balanceloss(aff_idx,
+ * aff_softmax) and entropy_balance(aff_softmax): moe_model/model/moe/competesmoe.py:322-335,350-371, moe.py:90-110;
+ * moe_pretrain_model/layers/moe/competesmoe.py:541-593, layers/moe/moe.py:323-332.
+ *   in : p [T,E] gate softmax, aff [T,E] affinity scores, aff_idx [T,K] competition top-k, gate_idx [T,K] router top-k
+ *        (may be NULL: losses[2] = 0)
+ *   out: q [T,E] = softmax(aff);  losses[5]:
+ *        [0] mean_{t,e}(p - q)^2                         F.mse_loss(gate_softmax, affinity_softmax)
+ *        [1] mean_{t,k}(p - q)^2 at aff_idx              F.mse_loss of the gathered top-k columns (hybrid / in_topk)
+ *        [2] the same at gate_idx                         (tribrid)
+ *        [3] mean_{b,e}(mean_n q * mean_n onehot(aff_idx[..., 0])) * E^2      balanceloss on the affinity (multimodal)
+ *        [4] mean_b sum_e m log m,  m = mean_n softmax(q)                      entropy_balance(aff_softmax) (pretrain)
+ *        colq / cnt / colr [B,E]: per-batch column sums of q, top-1 counts and column sums of softmax(q) (for backward).
+ * workspace: csmoe_losses_workspace_bytes(B, N, E) bytes.  E <= 64, K <= 8, B <= 65535. */
+int64_t csmoe_losses_workspace_bytes(int64_t B, int64_t N, int32_t E);
+int csmoe_losses_fwd(const float* p, const float* aff, const int32_t* aff_idx, const int32_t* gate_idx, int64_t B,
+                     int64_t N, int32_t E, int32_t K, float* q, float* colq, float* cnt, float* colr, float* losses,
+                     void* workspace, void* stream);
+/* g[5] (device) = d(total)/d(losses[i]).  dp [T,E]: gradient of the MSE terms w.r.t. the gate softmax (q is detached
+ * there, as in the reference); daff [T,E]: gradient of terms [3] and [4] w.r.t. the affinity scores, through q. */
+int csmoe_losses_bwd(const float* p, const float* q, const int32_t* aff_idx, const int32_t* gate_idx, const float* cnt,
+                     const float* colr, const float* g, int64_t B, int64_t N, int32_t E, int32_t K, float* dp,
+                     float* daff, void* stream);
+/* Router-step regulariser of the pretrain layer, entropy_balance(gate_logits) (layers/moe/moe.py:323-332), from the
+ * probabilities the router kernel already produced: loss[0] = mean_b sum_e m log m with m[b,e] = mean_n probs[b,n,e];
+ * colr [B,E] = sum_n probs.  Backward: dprobs[t,e] = g[0] * (log m[b,e] + 1) / (B * N).  Same workspace query. */
+int csmoe_entropy_balance_fwd(const float* probs, int64_t B, int64_t N, int32_t E, float* colr, float* loss,
+                              void* workspace, void* stream);
+int csmoe_entropy_balance_bwd(const float* colr, const float* g, int64_t B, int64_t N, int32_t E, float* dprobs,
+                              void* stream);
+/* Backward of csmoe_topk_renorm: w = v / sum(v) with v = scores (or sigmoid(scores)) at idx; dscores [T,E] is written
+ * (accumulate = 0) or added to (1).  The renormalised weights stay attached to the scores in the reference
+ * (competesmoe.py:249-254), so this runs in every competition step. */
+int csmoe_topk_renorm_bwd(const float* scores, const float* w, const int32_t* idx, const float* dw, int64_t T, int32_t E,
+                          int32_t K, int32_t sigmoid, int32_t accumulate, float* dscores, void* stream);
+/* rows[t*K + k] = idx[t,k] * t_pad + t: where the selected experts' rows sit in the dense outputs y[E, t_pad, D]. */
+int csmoe_dense_rows(const int32_t* idx, int64_t T, int32_t K, int64_t t_pad, int32_t* rows, void* stream);
+
 /* ------------------------------------------------------------------------------------------------ expert parallelism
  * One process per GPU; rank r of P owns experts [r*E/P, (r+1)*E/P).  Exchange buffers are allocated by the library
  * (cudaMalloc, so that they can be exported with CUDA IPC) and mapped into every peer once; after that dispatch and

@@ -85,7 +85,7 @@ def competition_policy(x: torch.Tensor, experts: Sequence[ExpertW], k: int, norm
     """competesmoe.py:219-259: run every expert on every token, score = mean softplus(output)."""
     B, N, _ = x.shape
     E = len(experts)
-    affinity = torch.zeros(B, N, E, dtype=x.dtype)
+    affinity = torch.zeros(B, N, E, dtype=x.dtype, device=x.device)
     outs = []
     for i, ew in enumerate(experts):
         out_i = expert_forward(ew, x)
@@ -108,7 +108,7 @@ def compute_moe(x: torch.Tensor, experts: Sequence[ExpertW], selected: torch.Ten
                 out_dim: int) -> torch.Tensor:
     """moe.py:172-213: loop over experts in ascending id, gather rows, run the expert, weighted in-place add."""
     B, N, _ = x.shape
-    results = torch.zeros(B, N, out_dim, dtype=x.dtype)
+    results = torch.zeros(B, N, out_dim, dtype=x.dtype, device=x.device)
     for i, ew in enumerate(experts):
         b_idx, t_idx, k_idx = torch.where(selected == i)
         out = expert_forward(ew, x[b_idx, t_idx])
@@ -136,7 +136,7 @@ def experts_diversity_loss(topk_outputs: torch.Tensor) -> torch.Tensor:
     B, N, K, D = eo.shape
     nrm = F.normalize(eo, p=2, dim=-1).view(B * N, K, D)
     sim = torch.bmm(nrm, nrm.transpose(1, 2))
-    sim = sim * (1 - torch.eye(K))
+    sim = sim * (1 - torch.eye(K, device=sim.device))
     return sim.mean()
 
 
@@ -157,7 +157,7 @@ def competesmoe_forward(x: torch.Tensor, gate_w: torch.Tensor, experts: Sequence
     E = len(experts)
     gate_weights, gate_sel, gate_softmax, gate_logits = router_policy(
         x, gate_w, k, None if competition else forced_selected)
-    auxiliary_loss = torch.tensor(0.0, dtype=x.dtype)
+    auxiliary_loss = torch.tensor(0.0, dtype=x.dtype, device=x.device)
     infor_aux: Dict[str, torch.Tensor] = {}
     debug = {"gate_selected": gate_sel, "gate_weights": gate_weights, "gate_softmax": gate_softmax,
              "gate_logits": gate_logits}

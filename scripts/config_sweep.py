@@ -42,8 +42,9 @@ def mm_args():
 
 
 class Case:
-    def __init__(self, name, kind, T, D, hidden, E, K, d_out=None, autocast=True, note="", moe_name="competesmoe"):
+    def __init__(self, name, kind, T, D, hidden, E, K, d_out=None, autocast=True, note="", moe_name="competesmoe", key=None):
         self.name, self.kind, self.T, self.D, self.hidden, self.E, self.K = name, kind, T, D, hidden, E, K
+        self.key = key or name.split()[0]
         self.moe_name = moe_name
         self.d_out = d_out or D
         self.autocast, self.note = autocast, note
@@ -126,8 +127,11 @@ def build(case: Case, dev, ep):
     return layer, set_branch, step, x_dtype
 
 
-def time_case(case: Case, dev, ep, steps, warmup, dist_on):
+def time_case(case: Case, dev, ep, steps, warmup, dist_on, graphs=None):
     import torch.distributed as dist
+    global GRAPHS
+    if graphs is not None:
+        GRAPHS = graphs
     layer, set_branch, step, x_dtype = build(case, dev, ep)
     params = list(layer.parameters())
     rank = ep.rank if ep is not None else 0
@@ -148,6 +152,8 @@ def time_case(case: Case, dev, ep, steps, warmup, dist_on):
         if dist_on:
             dist.barrier()
         torch.cuda.synchronize()
+        from competesmoe_b200 import ops as _ops
+        n0 = _ops.launch_count
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         for _ in range(steps):
@@ -158,6 +164,10 @@ def time_case(case: Case, dev, ep, steps, warmup, dist_on):
         if dist_on:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         res[comp] = float(ms)
+        # libcsmoe launches issued from Python per step (0 when the step is replayed from captured CUDA graphs)
+        if not hasattr(case, "launches"):
+            case.launches = {}
+        case.launches[comp] = (_ops.launch_count - n0) // max(steps, 1)
     del layer, params, x, dy
     torch.cuda.empty_cache()
     return res
@@ -254,18 +264,21 @@ def cpu_baseline_rows():
 
 
 def cases(world):
-    cs = [Case("C1 pretrain layer d=512 E=8 K=2 H=128 T=8x512 (fp32 in, bf16 autocast)", "pretrain", 4096, 512, 128, 8, 2)]
+    cs = [Case("C1 pretrain layer d=512 E=8 K=2 H=128 T=8x512 (fp32 in, bf16 autocast)", "pretrain", 4096, 512, 128, 8, 2,
+               key="C1")]
     for E, K in ((8, 2), (16, 2), (32, 2), (64, 2), (64, 8)):
-        cs.append(Case(f"C3 competition sweep d=1024 H=128 E={E} K={K} T=16384", "pretrain", 16384, 1024, 128, E, K))
+        cs.append(Case(f"C3 competition sweep d=1024 H=128 E={E} K={K} T=16384", "pretrain", 16384, 1024, 128, E, K,
+                       key=f"C3_E{E}_K{K}"))
     cs.append(Case(f"C4 pretrain LM layer d=1024 E=64 K=8 H=128, {65536 // max(world, 1) if world > 1 else 8192} tokens/GPU",
-                   "pretrain", 65536 // world if world > 1 else 8192, 1024, 128, 64, 8))
-    cs.append(Case("C5/C2' SigLIP MoE MLP d=1152 F=4304 E=4 K=2 gelu-tanh+bias, 12800 tokens/GPU", "siglip", 12800, 1152, 4304, 4, 2))
+                   "pretrain", 65536 // world if world > 1 else 8192, 1024, 128, 64, 8, key="C4"))
+    cs.append(Case("C5/C2' SigLIP MoE MLP d=1152 F=4304 E=4 K=2 gelu-tanh+bias, 12800 tokens/GPU", "siglip", 12800, 1152, 4304, 4, 2,
+                   key="C5_siglip"))
     cs.append(Case("C5/C2' projector MoE 2304->3072->3072 E=4 K=2 gelu+bias, 1280 tokens/GPU", "projector", 1280, 2304, 3072, 4, 2,
-                   d_out=3072))
+                   d_out=3072, key="C5_projector"))
     for nm, E, K in (("smoe", 4, 2), ("smoe_sigmoidgating", 4, 2), ("xmoe", 4, 2), ("smoe_perturbed", 4, 2),
                      ("smoe_share", 5, 3), ("deepseekv3", 5, 3)):
         cs.append(Case(f"S sibling router {nm}: SigLIP MoE MLP d=1152 F=4304 E={E} K={K}, 12800 tokens", "siglip", 12800, 1152,
-                       4304, E, K, moe_name=nm))
+                       4304, E, K, moe_name=nm, key=f"S_{nm}"))
     return cs
 
 

@@ -468,3 +468,115 @@ def test_act_bwd_bias_matches_separate_kernels(ops, act, dense):
         for e in range(E):
             assert torch.equal(dz[po[e]:po[e + 1]], dz_ref[po[e]:po[e + 1]])
     assert torch.equal(db, db_ref)
+
+
+# ------------------------------------------------------------------------------------------------ loss kernels (losses.cu)
+def _torch_comp_losses(p, aff, aff_idx, gate_idx, B):
+    """Plain PyTorch fp32 restatement of the five scalars csmoe_losses_fwd produces (reference lines in include/csmoe.h)."""
+    import math
+    T, E = p.shape
+    N = T // B
+    q = F.softmax(aff, dim=-1)
+    qd = q.detach()
+    li, gi = aff_idx.long(), gate_idx.long()
+    l0 = F.mse_loss(p, qd)
+    l1 = F.mse_loss(torch.gather(p, -1, li), torch.gather(qd, -1, li))
+    l2 = F.mse_loss(torch.gather(p, -1, gi), torch.gather(qd, -1, gi))
+    q3 = q.view(B, N, E)
+    top1 = F.one_hot(li.view(B, N, -1)[..., 0], E).float()
+    l3 = (q3.mean(-2) * top1.mean(-2)).mean() * float(E * E)
+    ls = F.log_softmax(q3, dim=-1)
+    lm = ls.logsumexp(-2) - math.log(N)
+    l4 = (lm * lm.exp()).sum(-1).mean()
+    return q, torch.stack([l0, l1, l2, l3, l4])
+
+
+@pytest.mark.parametrize("B,N,E,K", [(1, 4096, 4, 2), (3, 200, 8, 2), (4, 1024, 64, 8), (2, 77, 33, 5)])
+def test_compete_losses_kernels_match_torch(B, N, E, K):
+    from competesmoe_b200.functional import CompeteLossesFn
+    g = torch.Generator().manual_seed(B * 1000 + E)
+    T = B * N
+    p = F.softmax(torch.randn(T, E, generator=g), -1).to(DEV).requires_grad_(True)
+    aff = (0.7 + 0.1 * torch.randn(T, E, generator=g)).to(DEV).requires_grad_(True)
+    aff_idx = torch.stack([torch.randperm(E, generator=g)[:K] for _ in range(T)]).int().to(DEV)
+    gate_idx = torch.stack([torch.randperm(E, generator=g)[:K] for _ in range(T)]).int().to(DEV)
+    coef = torch.tensor([1.0, 0.7, -0.3, 0.5, 2.0], device=DEV)
+    q, losses = CompeteLossesFn.apply(p, aff, aff_idx, gate_idx, B)
+    (losses * coef).sum().backward()
+    pr, ar = p.detach().clone().requires_grad_(True), aff.detach().clone().requires_grad_(True)
+    q_ref, l_ref = _torch_comp_losses(pr, ar, aff_idx, gate_idx, B)
+    (l_ref * coef).sum().backward()
+    torch.testing.assert_close(q, q_ref, rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(losses, l_ref, rtol=2e-5, atol=1e-8)
+    torch.testing.assert_close(p.grad, pr.grad, rtol=1e-4, atol=1e-10)
+    torch.testing.assert_close(aff.grad, ar.grad, rtol=1e-3, atol=1e-9)
+    # deterministic: bit-identical on a second run
+    q2, losses2 = CompeteLossesFn.apply(p.detach(), aff.detach(), aff_idx, gate_idx, B)
+    assert torch.equal(losses2, losses.detach()) and torch.equal(q2, q)
+    # gate_idx = None: term [2] is zero and nothing else changes
+    _, l3 = CompeteLossesFn.apply(p.detach(), aff.detach(), aff_idx, None, B)
+    assert float(l3[2]) == 0.0 and torch.equal(l3[[0, 1, 3, 4]], losses.detach()[[0, 1, 3, 4]])
+
+
+@pytest.mark.parametrize("B,N,E", [(1, 512, 4), (8, 512, 8), (4, 1024, 64)])
+def test_entropy_balance_kernel_matches_pretrain_formula(B, N, E):
+    """moe_pretrain_model/layers/moe/moe.py:323-332 on logits == the kernel on softmax(logits)."""
+    import math
+    from competesmoe_b200.functional import EntropyBalanceFn
+    g = torch.Generator().manual_seed(E)
+    logits = torch.randn(B, N, E, generator=g).to(DEV).requires_grad_(True)
+    ls = F.log_softmax(logits.float(), dim=-1)
+    lm = ls.logsumexp(-2) - math.log(N)
+    ref = (lm * lm.exp()).sum(-1).mean()
+    ref.backward()
+    lg = logits.detach().clone().requires_grad_(True)
+    got = EntropyBalanceFn.apply(F.softmax(lg, dim=-1).view(B * N, E), B)
+    got.backward()
+    torch.testing.assert_close(got, ref, rtol=2e-5, atol=1e-8)
+    torch.testing.assert_close(lg.grad, logits.grad, rtol=1e-3, atol=1e-9)
+
+
+@pytest.mark.parametrize("sigmoid", [False, True])
+def test_topk_renorm_bwd_and_dense_rows(sigmoid, ops):
+    g = torch.Generator().manual_seed(5)
+    T, E, K, t_pad = 300, 16, 4, 512
+    scores = (0.7 + 0.2 * torch.randn(T, E, generator=g)).to(DEV)
+    w, idx = ops.topk_renorm(scores, K, sigmoid=sigmoid)
+    dw = torch.randn(T, K, generator=g).to(DEV)
+    s = scores.clone().requires_grad_(True)
+    v = torch.gather(torch.sigmoid(s) if sigmoid else s, 1, idx.long())
+    (v / v.sum(-1, keepdim=True) * dw).sum().backward()
+    got = ops.topk_renorm_bwd(scores, w, idx, dw, sigmoid)
+    torch.testing.assert_close(got, s.grad, rtol=1e-4, atol=1e-7)
+    base = torch.randn(T, E, generator=g).to(DEV)
+    acc = ops.topk_renorm_bwd(scores, w, idx, dw, sigmoid, out=base.clone())
+    torch.testing.assert_close(acc, base + s.grad, rtol=1e-4, atol=1e-6)
+    rows = ops.dense_rows(idx, t_pad)
+    want = (idx.long() * t_pad + torch.arange(T, device=DEV).unsqueeze(1)).reshape(-1).int()
+    assert torch.equal(rows, want)
+
+
+def test_topk_is_total_on_non_finite_scores(ops):
+    """NaN / Inf scores must still give K distinct in-range expert ids (NaN sorts as the largest value, like
+    torch.topk), and the routing maps built from them must stay in bounds."""
+    T, E, K = 64, 8, 2
+    scores = torch.randn(T, E, device=DEV)
+    scores[3] = float("nan")
+    scores[5, 2] = float("nan")
+    scores[7, 1] = float("inf")
+    scores[9] = float("-inf")
+    w, idx = ops.topk_renorm(scores, K)
+    assert int(idx.min()) >= 0 and int(idx.max()) < E
+    assert bool((idx[:, 0] != idx[:, 1]).all())
+    assert idx[3].tolist() == [0, 1] and idx[5, 0].item() == 2 and idx[7, 0].item() == 1
+    x = torch.randn(T, 64, device=DEV, dtype=torch.bfloat16)
+    x[11] = float("nan")
+    wg = torch.randn(E, 64, device=DEV, dtype=torch.bfloat16)
+    _, _, _, ti = ops.router_fwd(x, wg, K)
+    assert int(ti.min()) >= 0 and int(ti.max()) < E and ti[11].tolist() == [0, 1]
+    route = ops.route_build(ti, E)
+    assert int(route.counts.sum()) == T * K
+    # out-of-range ids handed to the public op are clamped instead of corrupting memory
+    bad = torch.tensor([[0, 99], [-5, 1]], dtype=torch.int32, device=DEV)
+    r2 = ops.route_build(bad, E)
+    assert r2.counts.tolist() == [2, 1, 0, 0, 0, 0, 0, 1]

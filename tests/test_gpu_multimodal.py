@@ -215,3 +215,26 @@ def test_layer_cuda_graph_mode_matches_eager(name):
     with torch.no_grad():
         out, aux, _, _ = graphed(fx["x"].to(DEV, dtype))
     assert out.shape == fx["out"].shape
+
+
+def test_layer_cuda_graph_mode_under_autocast_matches_eager():
+    """fp32 module called under torch.autocast(bf16): graph mode keys on the autocast state and replays what the eager
+    call computes, bit for bit."""
+    fx = load_golden("mm_siglip_router_f32")
+    eager = build_multimodal_layer(fx, DEV, torch.float32)
+    graphed = build_multimodal_layer(fx, DEV, torch.float32).enable_cuda_graphs()
+    g = torch.Generator().manual_seed(13)
+    for trial in range(2):
+        x_cpu = fx["x"] if trial == 0 else torch.randn(fx["x"].shape, generator=g)
+        dy = fx["dy"].to(DEV)
+        res = []
+        for layer in (eager, graphed):
+            for p in layer.parameters():
+                p.grad = None
+            x = x_cpu.to(DEV).requires_grad_(True)
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                out, aux, _, _ = layer(x)
+            torch.autograd.backward((out, aux), (dy.to(out.dtype), torch.ones_like(aux)))
+            res.append((out.clone(), aux.clone(), x.grad.clone()))
+        assert all(torch.equal(a, b) for a, b in zip(*res))
+    assert len(graphed._graphs) == 1
