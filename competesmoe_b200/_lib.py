@@ -34,7 +34,7 @@ class GemmArgs(C.Structure):
         ("aux", vp), ("ldaux", i64),
         ("row_tile", i32), ("sum_experts", i32),
         ("c_rows", vp),
-        ("rowsum", vp), ("rowsum_round", i32), ("reserved2", i32),
+        ("rowsum", vp), ("rowsum_round", i32), ("bias_after_round", i32),
     ]
 
 
@@ -69,6 +69,10 @@ _SIGNATURES = {
     "csmoe_affinity_bwd": (i32, [vp, vp, i32, i32, i64, i64, i32, i32, vp, vp]),
     "csmoe_diversity_fwd": (i32, [vp, i32, i64, i64, i32, i32, vp, vp, vp, vp, vp, vp]),
     "csmoe_compete_bwd": (i32, [vp, i32, i32, i64, i64, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "csmoe_sigma_ffn_supported": (i32, [i64, i32, i64]),
+    "csmoe_sigma_ffn_fwd": (i32, [vp, i64, i32, i32, i32, vp, vp, vp, i32, vp, vp, i64, i32, vp, vp, vp, vp]),
+    "csmoe_sigma_ffn_bwd": (i32, [vp, i64, i32, i32, i32, vp, vp, vp, vp, i64, i32, vp, i64, vp, vp, vp, vp, vp, vp, vp]),
+    "csmoe_sigma_wgrad": (i32, [vp, vp, i64, i32, i32, vp, vp, i64, i32, i32, vp, i32, vp]),
     "csmoe_losses_workspace_bytes": (i64, [i64, i64, i32]),
     "csmoe_losses_fwd": (i32, [vp, vp, vp, vp, i64, i64, i32, i32, vp, vp, vp, vp, vp, vp, vp]),
     "csmoe_losses_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, i64, i64, i32, i32, vp, vp, vp]),

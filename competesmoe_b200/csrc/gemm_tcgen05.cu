@@ -40,6 +40,7 @@ struct KParams {
   int act;
   int c_fp32;
   int bias_fp32;
+  int bias_after_round;  // 1: C = bf16(acc) + bias (an fp32 bias added to a bf16 op result: the pretrain plugin, moe.py:400-401)
   int accumulate;
   int glu_f;          // GLU epilogues: F (forward: n == 2F and tiles interleave gate|up; backward: n == F)
   int epi;            // kEpiPlain / kEpiGluFwd / kEpiActBwd / kEpiGluBwd
@@ -154,7 +155,7 @@ __device__ __forceinline__ void epilogue_store8(const KParams& p, const float (&
     else
       load8(reinterpret_cast<const __nv_bfloat16*>(bias_row) + col, b);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) z[i] += b[i];
+    for (int i = 0; i < 8; ++i) z[i] = (p.bias_after_round ? bf16_round(z[i]) : z[i]) + b[i];
   }
   if (p.accumulate) {
     float old[8];
@@ -477,7 +478,7 @@ __device__ __forceinline__ void epilogue_tile_staged(const KParams& p, const Til
             else
               load8(reinterpret_cast<const __nv_bfloat16*>(p.bias) + boff + col0 + c * 8, b);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) f[c * 8 + i] += b[i];
+            for (int i = 0; i < 8; ++i) f[c * 8 + i] = (p.bias_after_round ? bf16_round(f[c * 8 + i]) : f[c * 8 + i]) + b[i];
           }
         }
       }
@@ -625,7 +626,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const KParams& p, const Tile& 
             else
               load8(reinterpret_cast<const __nv_bfloat16*>(p.bias) + boff + col0 + c * 8, b);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) f[c * 8 + i] += b[i];
+            for (int i = 0; i < 8; ++i) f[c * 8 + i] = (p.bias_after_round ? bf16_round(f[c * 8 + i]) : f[c * 8 + i]) + b[i];
           }
         }
       }
@@ -1871,6 +1872,7 @@ extern "C" int csmoe_grouped_gemm(const csmoe_gemm_args* a, void* stream_) {
   kp.act = a->act;
   kp.c_fp32 = a->c_dtype == CSMOE_F32;
   kp.bias_fp32 = a->bias_dtype == CSMOE_F32;
+  kp.bias_after_round = a->bias_after_round != 0;
   kp.accumulate = a->accumulate;
   kp.tile_expert = a->tile_expert;
   kp.pad_offsets = a->pad_offsets;

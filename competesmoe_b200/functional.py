@@ -40,6 +40,7 @@ _FUSE_ACT_BIAS = os.environ.get("CSMOE_FUSE_ACT_BIAS", "1") != "0"
 #   "0" never (stand-alone csmoe_affinity_fwd re-reads y), "auto" = only where that GEMM's main loop is long enough to
 #   hide the extra epilogue math (contraction >= 1024; the sigma-MoE shapes with H = 128 are epilogue bound).
 _SCORE_EPILOGUE = os.environ.get("CSMOE_SCORE_EPILOGUE", "auto")
+_SIGMA_FUSED = os.environ.get("CSMOE_SIGMA_FUSED", "1") != "0"
 
 
 @dataclass(frozen=True)
@@ -49,6 +50,7 @@ class FFNSpec:
     kn_layout: bool = False  # False: w1 [E,F,D], w2 [E,Dout,F] (nn.Linear);  True: w1 [E,D,H], w2 [E,H,Dout] (sigma-MoE)
     round_each: bool = True  # combine: round the running sum to the activation dtype after every expert (moe.py:204)
     round_w: bool = False    # combine: round the routing weight to the activation dtype first (cvmm.py:483)
+    bias_after_round: bool = False  # first projection: bf16(x . W) + b (pretrain: fp32 bias added to the bf16 cvmm result)
     return_hidden: bool = False  # SparseFFNFn also returns (h = act(z) [row_cap, H], row_to_slot) for the relu_pass_rate log
 
     @property
@@ -74,13 +76,14 @@ def _ffn_first(xp, w1, b1, spec: FFNSpec, **where):
     if spec.glu and not spec.kn_layout and b1 is None and _FUSE_FWD:
         h, z = ops.gemm_rows(xp, w1, w_is_kn=False, act=ops.ACT_SILU_GLU, **where)   # GLU fused in the epilogue
         return z, h
+    bar = spec.bias_after_round and b1 is not None
     if spec.glu:
-        z = ops.gemm_rows(xp, w1, w_is_kn=spec.kn_layout, bias=b1, **where)
+        z = ops.gemm_rows(xp, w1, w_is_kn=spec.kn_layout, bias=b1, bias_after_round=bar, **where)
         return z, ops.act_fwd(z, spec.act, where.get("route"))
     if spec.act == ops.ACT_NONE:
-        z = ops.gemm_rows(xp, w1, w_is_kn=spec.kn_layout, bias=b1, **where)
+        z = ops.gemm_rows(xp, w1, w_is_kn=spec.kn_layout, bias=b1, bias_after_round=bar, **where)
         return z, z
-    h, z = ops.gemm_rows(xp, w1, w_is_kn=spec.kn_layout, bias=b1, act=spec.act, want_preact=True, **where)
+    h, z = ops.gemm_rows(xp, w1, w_is_kn=spec.kn_layout, bias=b1, act=spec.act, want_preact=True, bias_after_round=bar, **where)
     return z, h
 
 
@@ -185,6 +188,55 @@ class SparseFFNFn(Function):
             dxp = ops.gemm_rows(dz, w1b, w_is_kn=not spec.kn_layout, route=route)
             dx = ops.scatter_reduce(dxp, route.slot_to_row, T, K).to(ctx.x_dtype)
         return dx, dw, None, dw1, db1, dw2, db2, None
+
+
+class SigmaFFNFn(Function):
+    """SparseFFNFn for the sigma-MoE layout with expert size 128 and ReLU (the pretrain plugin's compute_moe_main,
+    competesmoe.py:510-522) on the fused kernels of csrc/sigma_ffn.cu: one kernel gathers the token rows, runs both
+    projections with the hidden activations kept on chip and writes y; backward is one fused dgrad kernel (dh, relu',
+    d routing weight, dx rows) plus two gathered weight-gradient GEMMs.  Saved for backward: x (bf16) and h only."""
+
+    @staticmethod
+    def forward(ctx, x, w, sel, keys, bias, values, spec: FFNSpec):
+        T, K = sel.shape
+        E = keys.shape[0]
+        xb, kb, vb = _bf16(x).contiguous(), _bf16(keys), _bf16(values)
+        route = ops.route_build(sel, E, row_tile=ROW_TILE)
+        y, h = ops.sigma_ffn_fwd(xb, kb, vb, bias, route)
+        out = ops.combine_fwd(y, route.slot_to_row, route.sel, w, T, K, round_each=spec.round_each, round_w=spec.round_w)
+        ctx.route, ctx.spec, ctx.x_dtype = route, spec, x.dtype
+        ctx.save_for_backward(xb, h, w, keys, values, bias)
+        ctx.wb = (kb if kb is not keys else None, vb if vb is not values else None)
+        if spec.return_hidden:
+            hd = h.detach()
+            ctx.mark_non_differentiable(hd, route.row_to_slot)
+            return out, hd, route.row_to_slot
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout, _dh=None, _dmap=None):
+        xb, h, w, keys, values, bias = ctx.saved_tensors
+        route, spec = ctx.route, ctx.spec
+        T, K, E = route.n_slots // route.top_k, route.top_k, route.num_experts
+        kb = ctx.wb[0] if ctx.wb[0] is not None else _bf16(keys)
+        vb = ctx.wb[1] if ctx.wb[1] is not None else _bf16(values)
+        dout = _bf16(dout.contiguous())
+        wu = w.to(torch.bfloat16).float() if spec.round_w else w
+        dz, hw, dxr, dw_part = ops.sigma_ffn_bwd(dout, kb, vb, route, wu, h)
+        dw = dw_part.sum(0).view(T, K) if ctx.needs_input_grad[1] else None
+        dvalues = ops.sigma_wgrad(hw, dout, E, route, transpose=False, out_dtype=values.dtype)   # [E, H, Dout]
+        dkeys = ops.sigma_wgrad(dz, xb, E, route, transpose=True, out_dtype=keys.dtype)          # [E, D, H]
+        dbias = ops.bias_grad(dz, E, route=route, out_dtype=bias.dtype) if bias is not None else None
+        dx = ops.scatter_reduce(dxr, route.slot_to_row, T, K).to(ctx.x_dtype) if ctx.needs_input_grad[0] else None
+        return dx, dw, None, dkeys, dbias, dvalues, None
+
+
+def sigma_fused_ok(x: torch.Tensor, keys: torch.Tensor, values: torch.Tensor, spec: FFNSpec, cdt: torch.dtype) -> bool:
+    """The fused path covers the shapes the reference's pretraining sweeps use: expert size 128, ReLU, bf16 compute,
+    model dims that are multiples of 128.  Everything else takes SparseFFNFn.  CSMOE_SIGMA_FUSED=0 switches it off."""
+    return (_SIGMA_FUSED and spec.kn_layout and spec.act == ops.ACT_RELU and cdt == torch.bfloat16
+            and keys.shape[1] % 128 == 0 and ops.sigma_ffn_supported(keys.shape[1], keys.shape[2], values.shape[2]))
 
 
 # ------------------------------------------------------------------------------------------------ dense experts

@@ -280,7 +280,7 @@ def gemm_rows(a: torch.Tensor, w: torch.Tensor, *, w_is_kn: bool, route: Optiona
               dense_rows: int = 0, a_expert_rows: int = 0, bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
               want_preact: bool = False, out_dtype: Optional[torch.dtype] = None, act_bwd: int = ACT_NONE,
               aux: Optional[torch.Tensor] = None, c_rows: Optional[torch.Tensor] = None, sum_experts: bool = False,
-              rowsum_softplus: Optional[bool] = None):
+              rowsum_softplus: Optional[bool] = None, bias_after_round: bool = False):
     """C[row] = A[row] . W[expert(row)] with a fused epilogue.
 
     a: [rows, k] bf16.  w: [E, n, k] (w_is_kn=False, nn.Linear layout) or [E, k, n] (w_is_kn=True).
@@ -339,6 +339,7 @@ def gemm_rows(a: torch.Tensor, w: torch.Tensor, *, w_is_kn: bool, route: Optiona
         bias = bias.contiguous()
         assert bias.shape == (E, n)
         g.bias, g.bias_dtype = _p(bias), _dt(bias)
+        g.bias_after_round = 1 if bias_after_round else 0   # bf16(acc) + bias instead of bf16(acc + bias)
     if act_bwd != ACT_NONE:
         assert aux is not None and aux.dtype == torch.bfloat16 and aux.stride(1) == 1 and aux.shape[0] == m
         assert aux.shape[1] == (2 * n if glu_bwd else n)
@@ -605,3 +606,61 @@ def dense_rows(idx: torch.Tensor, t_pad: int) -> torch.Tensor:
     rows = torch.empty(T * K, dtype=torch.int32, device=idx.device)
     _call("csmoe_dense_rows", _p(idx.contiguous()), T, K, t_pad, _p(rows), _stream())
     return rows
+
+
+# ----------------------------------------------------------------------------------------------- fused sigma-MoE FFN
+def sigma_ffn_supported(D: int, H: int, Dout: int) -> bool:
+    return bool(_lib.load().csmoe_sigma_ffn_supported(D, H, Dout))
+
+
+def sigma_ffn_fwd(x: torch.Tensor, keys: torch.Tensor, values: torch.Tensor, bias: Optional[torch.Tensor], route: Route,
+                  slots_per_row: Optional[int] = None, xp: Optional[torch.Tensor] = None):
+    """x [T, D] bf16 token-major, keys [E, D, H], values [E, H, Dout] bf16 -> (y [row_cap, Dout], h [row_cap, H]) bf16 in
+    the padded expert-major row space; h = relu(x . keys + bias) is zero on padding rows."""
+    _cuda(x, keys, values, bias, xp)
+    assert x.dtype == keys.dtype == values.dtype == torch.bfloat16 and x.is_contiguous() and keys.is_contiguous() and values.is_contiguous()
+    T, D = x.shape
+    E, _, H = keys.shape
+    Dout = values.shape[2]
+    k = route.top_k if slots_per_row is None else slots_per_row
+    h = torch.empty(route.row_cap, H, dtype=torch.bfloat16, device=x.device)
+    y = torch.empty(route.row_cap, Dout, dtype=torch.bfloat16, device=x.device)
+    if bias is not None:
+        bias = bias.contiguous()
+    _call("csmoe_sigma_ffn_fwd", _p(x), T, D, Dout, E, _p(keys), _p(values), _p(bias), _dt(bias) if bias is not None else F32,
+          _p(route.row_to_slot), _p(route.tile_expert), route.row_cap, k, _p(xp), _p(h), _p(y), _stream())
+    return y, h
+
+
+def sigma_ffn_bwd(dout: torch.Tensor, keys: torch.Tensor, values: torch.Tensor, route: Route, slot_w: torch.Tensor,
+                  h: torch.Tensor, slots_per_row: Optional[int] = None, dyp: Optional[torch.Tensor] = None):
+    """-> (dz [row_cap, H], hw [row_cap, H], dxr [row_cap, D] bf16, dw_part [2, n_slots] f32)."""
+    _cuda(dout, keys, values, slot_w, h, dyp)
+    assert dout.dtype == torch.bfloat16 and dout.is_contiguous() and slot_w.dtype == torch.float32
+    T, Dout = dout.shape
+    E, D, H = keys.shape
+    k = route.top_k if slots_per_row is None else slots_per_row
+    dev = dout.device
+    dz = torch.empty(route.row_cap, H, dtype=torch.bfloat16, device=dev)
+    hw = torch.empty(route.row_cap, H, dtype=torch.bfloat16, device=dev)
+    dxr = torch.empty(route.row_cap, D, dtype=torch.bfloat16, device=dev)
+    dw_part = torch.empty(2, route.n_slots, dtype=torch.float32, device=dev)
+    slot_w = slot_w.reshape(-1).contiguous()
+    _call("csmoe_sigma_ffn_bwd", _p(dout), T, D, Dout, E, _p(keys), _p(values), _p(route.row_to_slot), _p(route.tile_expert),
+          route.row_cap, k, _p(slot_w), route.n_slots, _p(h), _p(dyp), _p(dz), _p(hw), _p(dxr), _p(dw_part), _stream())
+    return dz, hw, dxr, dw_part
+
+
+def sigma_wgrad(a: torch.Tensor, g: torch.Tensor, num_experts: int, route: Route, transpose: bool,
+                out_dtype: torch.dtype = torch.float32, slots_per_row: Optional[int] = None) -> torch.Tensor:
+    """c[e] = a[rows of e]^T . gather(g)[rows of e]; a [row_cap, 128], g [T, N] token-major.
+    transpose=False -> [E, 128, N]; True -> [E, N, 128]."""
+    _cuda(a, g)
+    assert a.dtype == g.dtype == torch.bfloat16 and a.is_contiguous() and g.is_contiguous() and a.shape[0] == route.row_cap
+    T, N = g.shape
+    H = a.shape[1]
+    k = route.top_k if slots_per_row is None else slots_per_row
+    c = torch.empty((num_experts, N, H) if transpose else (num_experts, H, N), dtype=out_dtype, device=a.device)
+    _call("csmoe_sigma_wgrad", _p(a), _p(g), T, N, num_experts, _p(route.row_to_slot), _p(route.pad_offsets), route.row_cap, k,
+          1 if transpose else 0, _p(c), _dt(c), _stream())
+    return c

@@ -17,7 +17,8 @@ import torch
 import torch.nn.functional as F
 
 from . import ops
-from .functional import CompeteLossesFn, CompeteTailFn, DenseFFNFn, EntropyBalanceFn, FFNSpec, GateFn, SparseFFNFn
+from .functional import (CompeteLossesFn, CompeteTailFn, DenseFFNFn, EntropyBalanceFn, FFNSpec, GateFn, SigmaFFNFn,
+                         SparseFFNFn, sigma_fused_ok)
 from .graphs import capture_guard
 from .multimodal import TopkRenormFn
 from .schedule import make_layer_schedule
@@ -361,7 +362,8 @@ class MoE(LoggingLayer, RegularizedLayer, OncePerIterLayer, torch.nn.Module):
     def _spec(self, cdt: torch.dtype) -> FFNSpec:
         # CVMM.forward reduces with `reduction_weight.type_as(res) @ res` (cvmm.py:481-483): weight rounded to the op
         # dtype, fp32 accumulation, one rounding at the end.
-        return FFNSpec(act=self._act_code, kn_layout=True, round_each=False, round_w=cdt == torch.bfloat16)
+        return FFNSpec(act=self._act_code, kn_layout=True, round_each=False, round_w=cdt == torch.bfloat16,
+                       bias_after_round=True)
 
     def compute_gate(self, x2: torch.Tensor, cdt: torch.dtype):
         return GateFn.apply(self._cast(x2, cdt), self.w_gate, self.num_selected, 1, False)[:4]
@@ -385,13 +387,20 @@ class MoE(LoggingLayer, RegularizedLayer, OncePerIterLayer, torch.nn.Module):
             from .ep import EPSparseFFNFn
             return EPSparseFFNFn.apply(self._cast(x2, cdt), weights, selected, self.keys, self.bias, self.values, None,
                                        self._spec(cdt), self._ep)
+        spec = self._spec(cdt)
+        xc = self._cast(x2, cdt)
+        fused = sigma_fused_ok(xc, self.keys, self.values, spec, cdt)      # expert size 128 + ReLU: csrc/sigma_ffn.cu
         if self._plot_training():
-            spec = dataclasses.replace(self._spec(cdt), return_hidden=True)
-            out, h, row_to_slot = SparseFFNFn.apply(self._cast(x2, cdt), weights, selected, self.keys, self.bias, self.values,
-                                                    None, spec)
+            spec = dataclasses.replace(spec, return_hidden=True)
+            if fused:
+                out, h, row_to_slot = SigmaFFNFn.apply(xc, weights, selected, self.keys, self.bias, self.values, spec)
+            else:
+                out, h, row_to_slot = SparseFFNFn.apply(xc, weights, selected, self.keys, self.bias, self.values, None, spec)
             self._log_relu_pass_rate(h, row_to_slot, selected.numel())
             return out
-        return SparseFFNFn.apply(self._cast(x2, cdt), weights, selected, self.keys, self.bias, self.values, None, self._spec(cdt))
+        if fused:
+            return SigmaFFNFn.apply(xc, weights, selected, self.keys, self.bias, self.values, spec)
+        return SparseFFNFn.apply(xc, weights, selected, self.keys, self.bias, self.values, None, spec)
 
     def forward(self, x, return_id_experts=False, return_full=True, *args, **kwargs):
         """Plain sigma-MoE forward (moe.py:418-449)."""

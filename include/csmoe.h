@@ -190,7 +190,9 @@ typedef struct csmoe_gemm_args {
                               (moe_model/.../competesmoe.py:243: mean(softplus(out_i), -1)); csmoe_affinity_from_rowsum
                               finishes the mean.  Rows of skipped tiles are not written. */
   int32_t rowsum_round;    /* 1: round every softplus to bf16 before summing (eager bf16 reference arithmetic) */
-  int32_t reserved2;
+  int32_t bias_after_round; /* 1: the accumulator is rounded to bf16 BEFORE the bias is added -- the pretrain plugin's
+                              `scores = cvmm(...)` (bf16) `+ self.bias[...]` (fp32), moe.py:397-401; 0: bias added to the fp32
+                              accumulator, one rounding (nn.Linear with bias, the multimodal experts) */
 } csmoe_gemm_args;
 
 int csmoe_grouped_gemm(const csmoe_gemm_args* args, void* stream);
@@ -251,6 +253,34 @@ int csmoe_diversity_fwd(const void* y, int32_t dtype, int64_t T, int64_t t_pad, 
 int csmoe_compete_bwd(const void* y, int32_t dtype, int32_t E, int64_t T, int64_t t_pad, int32_t D, int32_t K,
                       const float* daff, const int32_t* sel, const float* w, const void* dout, const float* inv_norm,
                       const float* sim, const float* g_div, void* dy, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ fused sigma-MoE FFN
+ * The pretrain plugin's expert path -- cvmm(x, sel, keys) -> (+bias) -> relu -> cvmm(., sel, values), moe_pretrain_model/
+ * layers/moe/competesmoe.py:510-522 with layers/moe/moe.py:397-416 -- as one kernel per direction for expert size
+ * H = 128 (every sweep of the reference; transformer_lm_mixin.py:33).  Rows live in the padded expert-major row space
+ * of csmoe_route_build (row_to_slot / tile_expert / pad_offsets); the token rows are read straight from the
+ * token-major tensor with TMA gather4 loads (row of slot j = j / slots_per_row), so the K-fold expanded copy of the
+ * tokens is never written and the [rows, H] hidden activations stay on chip between the two MMAs.  All tensors bf16.
+ *   csmoe_sigma_ffn_supported(D, H, Dout): 1 if this path handles the shape (H == 128, D % 64 == 0, Dout % 128 == 0).
+ *   fwd:  h [row_cap, H] = relu(gather(x) . keys[e] + bias[e]) (saved for backward, zero on padding rows);
+ *         y [row_cap, Dout] = h . values[e].   xp (may be NULL) = a pre-gathered [row_cap, D] copy to load instead.
+ *   bwd:  dh = gather(dout) . values[e]^T;  dw_part[half][slot] = partial <h, dh> (sum the two halves: d routing weight);
+ *         dz [row_cap, H] = slot_w * dh * [h > 0];  hw [row_cap, H] = slot_w * h;  dxr [row_cap, D] = dz . keys[e]^T.
+ *         dyp (may be NULL) = pre-gathered UNWEIGHTED dout rows.  Needs D % 128 == 0 as well.
+ *   wgrad: c[e] = a[rows of e]^T . gather(g)[rows of e] with a [row_cap, H], g token-major [T, N], N % 128 == 0:
+ *         transpose = 0 -> c [E, H, N] (dvalues = hw^T . gather(dout));  1 -> c [E, N, H] (dkeys = (dz^T . gather(x))^T).
+ *         fp32 accumulation over the expert's rows inside one CTA: deterministic (cvmm.py:194-345 uses fp32 atomics). */
+int csmoe_sigma_ffn_supported(int64_t D, int32_t H, int64_t Dout);
+int csmoe_sigma_ffn_fwd(const void* x, int64_t T, int32_t D, int32_t Dout, int32_t E, const void* keys, const void* values,
+                        const void* bias, int32_t bias_dtype, const int32_t* row_to_slot, const int32_t* tile_expert,
+                        int64_t row_cap, int32_t slots_per_row, const void* xp, void* h, void* y, void* stream);
+int csmoe_sigma_ffn_bwd(const void* dout, int64_t T, int32_t D, int32_t Dout, int32_t E, const void* keys,
+                        const void* values, const int32_t* row_to_slot, const int32_t* tile_expert, int64_t row_cap,
+                        int32_t slots_per_row, const float* slot_w, int64_t n_slots, const void* h, const void* dyp,
+                        void* dz, void* hw, void* dxr, float* dw_part, void* stream);
+int csmoe_sigma_wgrad(const void* a, const void* g, int64_t T, int32_t N, int32_t E, const int32_t* row_to_slot,
+                      const int32_t* pad_offsets, int64_t row_cap, int32_t slots_per_row, int32_t transpose, void* c,
+                      int32_t c_dtype, void* stream);
 
 /* ------------------------------------------------------------------------------------------------ losses
  * Competition-step losses in one pass over [T, E] (T = B * N tokens, batch-major) + a fixed-order reduction.  Replaces

@@ -221,12 +221,14 @@ def test_c3_mid_sweep_layer_matches_oracle(competition):
     _pt_compare(f"C3(E=16) {'competition' if competition else 'router'} step", 2, competition, *res)
 
 
+@pytest.mark.parametrize("H", [64, 128], ids=["H64-grouped-gemm", "H128-fused"])
 @pytest.mark.parametrize("competition", [False, True], ids=["router", "competition"])
-def test_pretrain_bias_path_matches_oracle(competition):
-    """`-moe.bias 1` (moe.py:129-134, :400-401, competesmoe.py:613-614): hidden bias[E,H] inside the selected experts,
-    o_bias[D] on the layer output; the competition's dense scoring pass runs WITHOUT the bias (:381-414)."""
-    res = _pt_case(256, 64, 8, 2, 2, 192, competition, seed=1240, bias=True)
-    _pt_compare(f"bias=True {'competition' if competition else 'router'} step", 2, competition, *res)
+def test_pretrain_bias_path_matches_oracle(competition, H):
+    """`-moe.bias 1` (moe.py:129-134, :400-401, competesmoe.py:613-614): hidden bias[E,H] inside the selected experts
+    (added in fp32 to the bf16 cvmm result, then ReLU), o_bias[D] on the layer output; the competition's dense scoring
+    pass runs WITHOUT the bias (:381-414).  Expert size 128 takes the fused kernels, 64 the grouped-GEMM path."""
+    res = _pt_case(256, H, 8, 2, 2, 192, competition, seed=1240, bias=True)
+    _pt_compare(f"bias=True H={H} {'competition' if competition else 'router'} step", 2, competition, *res)
 
 
 def test_base_moe_forward_uses_raw_topk_probabilities():
