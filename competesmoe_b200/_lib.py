@@ -70,6 +70,7 @@ _SIGNATURES = {
     "csmoe_diversity_fwd": (i32, [vp, i32, i64, i64, i32, i32, vp, vp, vp, vp, vp, vp]),
     "csmoe_compete_bwd": (i32, [vp, i32, i32, i64, i64, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "csmoe_sigma_ffn_supported": (i32, [i64, i32, i64]),
+    "csmoe_sigma_set_stats": (i32, [vp]),
     "csmoe_sigma_ffn_fwd": (i32, [vp, i64, i32, i32, i32, vp, vp, vp, i32, vp, vp, i64, i32, vp, vp, vp, vp]),
     "csmoe_sigma_ffn_bwd": (i32, [vp, i64, i32, i32, i32, vp, vp, vp, vp, i64, i32, vp, i64, vp, vp, vp, vp, vp, vp, vp]),
     "csmoe_sigma_wgrad": (i32, [vp, vp, i64, i32, i32, vp, vp, i64, i32, i32, vp, i32, vp]),

@@ -73,16 +73,28 @@ route_scan_kernel(int32_t* __restrict__ chunk_counts, int n_chunks, int E, int r
   __shared__ int32_t s_cnt[kMaxExperts];
   __shared__ int32_t s_off[kMaxExperts + 1];
   __shared__ int32_t s_pad[kMaxExperts + 1];
-  for (int e = threadIdx.x; e < E; e += blockDim.x) {
+  // one warp per expert: the chunks are scanned 32 at a time with a warp prefix sum (a thread per expert walking the
+  // chunks one by one was a chain of dependent global loads: 16.7 us at 64 experts x 32 chunks)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
+  for (int e = warp; e < E; e += n_warps) {
     int run = 0;
-    for (int c = 0; c < n_chunks; ++c) {
+    for (int c0 = 0; c0 < n_chunks; c0 += 32) {
+      const int c = c0 + lane;
       const long long i = static_cast<long long>(c) * E + e;
-      const int v = chunk_counts[i];
-      chunk_counts[i] = run;
-      run += v;
+      const int v = c < n_chunks ? chunk_counts[i] : 0;
+      int x = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+      }
+      if (c < n_chunks) chunk_counts[i] = run + x - v;
+      run += __shfl_sync(0xffffffffu, x, 31);
     }
-    s_cnt[e] = run;
-    counts[e] = run;
+    if (lane == 0) {
+      s_cnt[e] = run;
+      counts[e] = run;
+    }
   }
   __syncthreads();
   if (threadIdx.x == 0) {

@@ -61,6 +61,8 @@ struct Params {
   const __nv_bfloat16* h;       // [row_cap, H] saved hidden activations
   float* dw_part;               // [2, n_slots] partial <h, dh> of the two column halves
   long long n_slots;
+  int dbg;                      // tuning experiments (CSMOE_SIGMA_DBG bit mask): 1 = no gather copies, 2 = no output-tile stores,
+                                // 4 = no saved-tile (h / dz / hw) stores
 };
 
 __device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int r0, int r1, int r2,
@@ -150,7 +152,7 @@ sigma_ffn_kernel(const __grid_constant__ CUtensorMap map_a,    // gathered opera
   }
   if (warp == kMmaWarp && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
-      ptx::mbar_init(bar.full(s), 1 + kProdThreads);   // thread 0's expect_tx arrive + one arrival per producer thread
+      ptx::mbar_init(bar.full(s), 1 + 32);   // the owning producer warp: lane 0's expect_tx arrive + one arrival per lane
       ptx::mbar_init(bar.empty(s), 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -175,36 +177,47 @@ sigma_ffn_kernel(const __grid_constant__ CUtensorMap map_a,    // gathered opera
   const int nch = p.Dout / 128;        // GEMM-2 column chunks
 
   if (warp < kProdWarps) {
-    // ===================================================== producers (128 threads, thread gt owns tile row gt)
-    const int gt = threadIdx.x;
-    uint32_t stage = 0, phase = 0;
-    auto advance = [&]() {
-      if (++stage == kStages) {
-        stage = 0;
-        phase ^= 1u;
-      }
-    };
+    // ===================================================== producers: pipeline iteration `it` (one operand stage) is
+    // filled entirely by warp it % 4 -- so a stage's "full" barrier sees 33 arrivals from one warp, and only that warp
+    // polls the stage's "empty" barrier.  (All 128 producer threads arriving on / polling one barrier word serialised to
+    // profiles/r02k_sigma_bisect.md.)  In pass j lane l copies 16-byte chunk (l & 7) of tile row 32 (l >> 3) + j: eight
+    // consecutive lanes cover one contiguous 128-byte slice of a token row, and a lane's 32 rows are consecutive, so their
+    // slots come in eight 16-byte loads issued back to back (sixteen dependent scalar loads per k-block cost 3.6 k cycles
+    // in the first version of the weight-gradient kernel).
+    uint32_t it = 0;
+    const int lrow = lane >> 3, lchunk = lane & 7;
+    const uint32_t dst0 = lrow * 32 * 128;
     auto load_g1 = [&](int t, int e) {
-      const char* src_row = nullptr;
+      int tok[32];
       int r0 = 0, r1 = 0, r2 = 0, r3 = 0;
       const int k = p.slots_per_row;
       if (p.gather == 1) {
-        const int sl = __ldg(p.row_to_slot + static_cast<long long>(t) * kBM + gt);
-        // padding rows read token 0 (finite data): their results are masked in the epilogue
-        src_row = reinterpret_cast<const char*>(p.a_src) + static_cast<long long>(sl >= 0 ? sl / k : 0) * p.D * 2;
-      } else if (p.gather == 2 && gt < 32) {
-        const int4 s4 = __ldg(reinterpret_cast<const int4*>(p.row_to_slot + static_cast<long long>(t) * kBM) + gt);
+        const int4* sp = reinterpret_cast<const int4*>(p.row_to_slot + static_cast<long long>(t) * kBM + lrow * 32);
+        int4 s4[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s4[j] = __ldg(sp + j);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {   // padding rows (slot -1) read token 0 (finite data): masked in the epilogue
+          tok[4 * j] = max(s4[j].x, 0) / k;
+          tok[4 * j + 1] = max(s4[j].y, 0) / k;
+          tok[4 * j + 2] = max(s4[j].z, 0) / k;
+          tok[4 * j + 3] = max(s4[j].w, 0) / k;
+        }
+      } else if (p.gather == 2) {
+        const int4 s4 = __ldg(reinterpret_cast<const int4*>(p.row_to_slot + static_cast<long long>(t) * kBM) + lane);
         r0 = s4.x >= 0 ? s4.x / k : 0;
         r1 = s4.y >= 0 ? s4.y / k : 0;
         r2 = s4.z >= 0 ? s4.z / k : 0;
         r3 = s4.w >= 0 ? s4.w / k : 0;
       }
-      const uint32_t row_off = gt * 128, swz = gt & 7;
-      for (int kb = 0; kb < nkb1; ++kb) {
-        ptx::mbar_wait(bar.empty(stage), phase ^ 1u);
+      for (int kb = 0; kb < nkb1; ++kb, ++it) {
+        if ((it & (kProdWarps - 1)) != static_cast<uint32_t>(warp)) continue;
+        const uint32_t stage = it % kStages;
+        if (lane == 0) ptx::mbar_wait(bar.empty(stage), ((it / kStages) & 1u) ^ 1u);
+        __syncwarp();
         const uint32_t fb = bar.full(stage);
         const uint32_t sa = smem_base + stage * kStageBytes, sb = sa + 16384;
-        if (gt == 0) {
+        if (lane == 0) {
           ptx::mbar_arrive_expect_tx(fb, p.gather == 1 ? 16384 : kStageBytes);
           if (!BWD) {   // keys[e]: [D, H], MN-major B: two 64(n) x 64(k) boxes
             ptx::tma_load_3d(sb, &map_b1, fb, 0, kb * kBK, e);
@@ -215,22 +228,28 @@ sigma_ffn_kernel(const __grid_constant__ CUtensorMap map_a,    // gathered opera
           if (p.gather == 0) ptx::tma_load_2d(sa, &map_a, fb, kb * kBK, t * kBM);
         }
         if (p.gather == 1) {
-          const char* src = src_row + kb * 128;
+          if (!(p.dbg & 1)) {
+            const char* base = reinterpret_cast<const char*>(p.a_src) + kb * 128 + lchunk * 16;
+            const long long pitch = static_cast<long long>(p.D) * 2;
 #pragma unroll
-          for (int c = 0; c < 8; ++c) cp_async16(sa + row_off + ((c ^ swz) << 4), src + c * 16);
+            for (int j = 0; j < 32; ++j)   // row 32 lrow + j: (row & 7) == (j & 7)
+              cp_async16(sa + dst0 + j * 128 + ((lchunk ^ (j & 7)) << 4), base + tok[j] * pitch);
+          }
           cp_async_arrive_noinc(fb);
         } else {
-          if (p.gather == 2 && gt < 32) tma_gather4(sa + gt * 512, &map_a, fb, kb * kBK, r0, r1, r2, r3);
+          if (p.gather == 2) tma_gather4(sa + lane * 512, &map_a, fb, kb * kBK, r0, r1, r2, r3);
           ptx::mbar_arrive(fb);
         }
-        advance();
       }
     };
     auto load_g2 = [&](int e) {
-      for (int nc = 0; nc < nch; ++nc) {
-        ptx::mbar_wait(bar.empty(stage), phase ^ 1u);
+      for (int nc = 0; nc < nch; ++nc, ++it) {
+        if ((it & (kProdWarps - 1)) != static_cast<uint32_t>(warp)) continue;
+        const uint32_t stage = it % kStages;
+        if (lane == 0) ptx::mbar_wait(bar.empty(stage), ((it / kStages) & 1u) ^ 1u);
+        __syncwarp();
         const uint32_t fb = bar.full(stage);
-        if (gt == 0) {
+        if (lane == 0) {
           const uint32_t st = smem_base + stage * kStageBytes;
           ptx::mbar_arrive_expect_tx(fb, kStageBytes);
           if (!BWD) {   // values[e][k = 0..128, n = nc*128 ..]: MN-major, per 64-k block two 64(n) x 64(k) boxes
@@ -245,7 +264,6 @@ sigma_ffn_kernel(const __grid_constant__ CUtensorMap map_a,    // gathered opera
           }
         }
         ptx::mbar_arrive(fb);
-        advance();
       }
     };
     int n_done = 0, prev_e = -1;
@@ -413,6 +431,8 @@ sigma_ffn_kernel(const __grid_constant__ CUtensorMap map_a,    // gathered opera
       if (lane == 0) {
         ptx::mbar_arrive(bar.s_empty(sb));
         ptx::mbar_arrive(bar.a2_full(ab));
+      }
+      if (lane == 0 && !(p.dbg & 4)) {
         if (BWD) {   // first, so that the wait_group.read<1> of the next staged store covers it
           tma_store_2d(&map_t2, stg, half * 64, t * kBM + q * 32);
           ptx::bulk_commit_group();
@@ -436,6 +456,7 @@ sigma_ffn_kernel(const __grid_constant__ CUtensorMap map_a,    // gathered opera
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(bar.y_empty(yb));     // the accumulator is in registers: hand the buffer back early
         ++ycount;
+        if (p.dbg & 2) continue;
         uint32_t w[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) w[i] = pack_bf16(__uint_as_float(v0[2 * i]), __uint_as_float(v0[2 * i + 1]));
@@ -486,6 +507,9 @@ struct WParams {
   int gather;           // 1 = cp.async row gather, 2 = TMA gather4
   const __nv_bfloat16* g_src;   // token-major [T, N]
   int N;
+  int dbg;              // tuning experiments (CSMOE_SIGMA_DBG bit mask): 1 = no gather copies, 8 = no epilogue stores
+  unsigned long long* stats;   // debug (csmoe_sigma_set_stats): per CTA {producer wait empty, mma wait full, mma wait tempty,
+                               // epilogue wait tfull, total, k-blocks}
   int c_fp32;
   void* c;
   long long ldc;
@@ -510,7 +534,7 @@ sigma_wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   }
   if (warp == kMmaWarp && lane == 0) {
     for (int s = 0; s < kWStages; ++s) {
-      ptx::mbar_init(full_bar(s), 1 + kProdThreads);
+      ptx::mbar_init(full_bar(s), 1 + 32);
       ptx::mbar_init(empty_bar(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -528,45 +552,88 @@ sigma_wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   const long long total = static_cast<long long>(p.num_experts) * p.n_nblocks;
+  const bool st_on = p.stats != nullptr;
+  const long long t_begin = clock64();
+  unsigned long long w_acc = 0, w_acc2 = 0, w_acc3 = 0, w_acc4 = 0, n_kb = 0;
+  auto timed_wait = [&](uint32_t b, uint32_t par, unsigned long long& acc) {
+    if (!st_on) {
+      ptx::mbar_wait(b, par);
+      return;
+    }
+    const long long t0 = clock64();
+    ptx::mbar_wait(b, par);
+    acc += static_cast<unsigned long long>(clock64() - t0);
+  };
 
   if (warp < kProdWarps) {
-    // producers: thread gt owns k-row (gt & 63) of sub-tile (gt >> 6) of the gathered operand
-    const int gt = threadIdx.x;
-    const int j = gt >> 6, kr = gt & 63;
-    uint32_t stage = 0, phase = 0;
+    // producers: pipeline iteration `it` (one 64-row k-block) is filled entirely by warp it % 4 (see sigma_ffn_kernel).
+    // In pass j lane l copies 16-byte chunk (l & 7) of k-row 16 (l >> 3) + j of both 64-column sub-tiles.
+    uint32_t it = 0;
+    const int lrow = lane >> 3, lchunk = lane & 7;
+    const uint32_t dst0 = lrow * 16 * 128;
+    const int k = p.slots_per_row;
     for (long long t = blockIdx.x; t < total; t += gridDim.x) {
       const int e = static_cast<int>(t / p.n_nblocks), nb = static_cast<int>(t % p.n_nblocks);
       const int r0 = __ldg(p.pad_offsets + e), r1 = __ldg(p.pad_offsets + e + 1);
-      const int k = p.slots_per_row;
-      for (int r = r0; r < r1; r += kBK) {
-        ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+      for (int r = r0; r < r1; r += kBK, ++it) {
+        if ((it & (kProdWarps - 1)) != static_cast<uint32_t>(warp)) continue;
+        const long long ta = st_on ? clock64() : 0;
+        int tok[16];
+        if (p.gather == 1) {
+          const int4* sp = reinterpret_cast<const int4*>(p.row_to_slot + r + lrow * 16);
+          int4 s4[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) s4[j] = __ldg(sp + j);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            tok[4 * j] = max(s4[j].x, 0) / k;
+            tok[4 * j + 1] = max(s4[j].y, 0) / k;
+            tok[4 * j + 2] = max(s4[j].z, 0) / k;
+            tok[4 * j + 3] = max(s4[j].w, 0) / k;
+          }
+        }
+        const uint32_t stage = it % kWStages;
+        if (st_on) {
+          int chk = 0;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) chk += tok[j];
+          if (chk == -12345) n_kb += 100;            // forces the index loads to have completed here
+          w_acc3 += static_cast<unsigned long long>(clock64() - ta);
+        }
+        if (lane == 0) timed_wait(empty_bar(stage), ((it / kWStages) & 1u) ^ 1u, w_acc);
+        __syncwarp();
+        const long long tb = st_on ? clock64() : 0;
+        ++n_kb;
         const uint32_t fb = full_bar(stage);
         const uint32_t sa = smem_base + stage * kStageBytes, sb = sa + 16384;
-        if (gt == 0) {
+        if (lane == 0) {
           ptx::mbar_arrive_expect_tx(fb, p.gather == 1 ? 16384 : kStageBytes);
           ptx::tma_load_2d(sa, &map_a, fb, 0, r);
           ptx::tma_load_2d(sa + kSub, &map_a, fb, 64, r);
         }
         if (p.gather == 1) {
-          const int sl = __ldg(p.row_to_slot + r + kr);
-          const char* src = reinterpret_cast<const char*>(p.g_src + static_cast<long long>(sl >= 0 ? sl / k : 0) * p.N + nb * 128 + j * 64);
-          const uint32_t dst = sb + j * kSub + kr * 128;
+          if (!(p.dbg & 1)) {
+            const char* base = reinterpret_cast<const char*>(p.g_src + nb * 128) + lchunk * 16;
+            const long long pitch = static_cast<long long>(p.N) * 2;
 #pragma unroll
-          for (int c = 0; c < 8; ++c) cp_async16(dst + ((c ^ (kr & 7)) << 4), src + c * 16);
+            for (int j = 0; j < 16; ++j) {
+              const char* src = base + tok[j] * pitch;
+              const uint32_t dst = sb + dst0 + j * 128 + ((lchunk ^ (j & 7)) << 4);   // k-row 16 lrow + j
+              cp_async16(dst, src);                  // sub-tile 0: columns [nb*128, +64)
+              cp_async16(dst + kSub, src + 128);     // sub-tile 1: columns [nb*128 + 64, +64)
+            }
+          }
           cp_async_arrive_noinc(fb);
         } else {
-          if (gt < 32) {
-            const int4 s4 = __ldg(reinterpret_cast<const int4*>(p.row_to_slot + r + (gt & 15) * 4));
+          if (lane < 32) {
+            const int4 s4 = __ldg(reinterpret_cast<const int4*>(p.row_to_slot + r + (lane & 15) * 4));
             const int t0 = s4.x >= 0 ? s4.x / k : 0, t1 = s4.y >= 0 ? s4.y / k : 0;
             const int t2 = s4.z >= 0 ? s4.z / k : 0, t3 = s4.w >= 0 ? s4.w / k : 0;
-            tma_gather4(sb + (gt >> 4) * kSub + (gt & 15) * 512, &map_g, fb, nb * 128 + (gt >> 4) * 64, t0, t1, t2, t3);
+            tma_gather4(sb + (lane >> 4) * kSub + (lane & 15) * 512, &map_g, fb, nb * 128 + (lane >> 4) * 64, t0, t1, t2, t3);
           }
           ptx::mbar_arrive(fb);
         }
-        if (++stage == kWStages) {
-          stage = 0;
-          phase ^= 1u;
-        }
+        if (st_on) w_acc4 += static_cast<unsigned long long>(clock64() - tb);
       }
     }
   } else if (warp == kMmaWarp) {
@@ -577,11 +644,11 @@ sigma_wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         const int e = static_cast<int>(t / p.n_nblocks);
         const int nkb = (__ldg(p.pad_offsets + e + 1) - __ldg(p.pad_offsets + e)) / kBK;
         if (nkb == 0) continue;
-        ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        timed_wait(tempty_bar(acc), acc_phase ^ 1u, w_acc2);
         ptx::tc_fence_after();
         const uint32_t d = tmem_base + acc * 128;
         for (int kb = 0; kb < nkb; ++kb) {
-          ptx::mbar_wait(full_bar(stage), phase);
+          timed_wait(full_bar(stage), phase, w_acc);
           ptx::tc_fence_after();
           const uint32_t sa = smem_base + stage * kStageBytes, sb = sa + 16384;
 #pragma unroll
@@ -610,7 +677,7 @@ sigma_wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       const bool has_acc = __ldg(p.pad_offsets + e + 1) > __ldg(p.pad_offsets + e);
       uint32_t v0[32], v1[32];
       if (has_acc) {
-        ptx::mbar_wait(tfull_bar(acc), acc_phase);
+        timed_wait(tfull_bar(acc), acc_phase, w_acc);
         ptx::tc_fence_after();
         const uint32_t taddr = tmem_base + acc * 128 + half * 64 + (static_cast<uint32_t>(q * 32) << 16);
         ptx::tmem_ld_32x32b_x32(taddr, v0);
@@ -628,6 +695,7 @@ sigma_wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         for (int i = 0; i < 32; ++i) v0[i] = v1[i] = 0u;
       }
       const int n0 = nb * 128 + half * 64;
+      if (p.dbg & 8) continue;
       if (p.transpose) {
         // C[e][n][m]: for a fixed column the 32 lanes write 32 consecutive elements
         if (p.c_fp32) {
@@ -666,6 +734,12 @@ sigma_wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         }
       }
     }
+  }
+  if (st_on && lane == 0) {
+    unsigned long long* o = p.stats + static_cast<long long>(blockIdx.x) * 8;
+    if (warp == 0) { o[0] = w_acc; o[5] = n_kb; o[6] = w_acc3; o[7] = w_acc4; }
+    if (warp == kMmaWarp) { o[1] = w_acc; o[2] = w_acc2; o[4] = static_cast<unsigned long long>(clock64() - t_begin); }
+    if (warp == kEpiWarp0) o[3] = w_acc;
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -721,6 +795,13 @@ int gather_mode() {   // 1 = cp.async row gather (default), 2 = TMA gather4 (CSM
   return v;
 }
 
+unsigned long long* g_stats = nullptr;
+
+int dbg_mask() {
+  const char* d = getenv("CSMOE_SIGMA_DBG");
+  return d != nullptr ? atoi(d) : 0;
+}
+
 int gather_box_rows() {
   static int v = []() {
     const char* s = getenv("CSMOE_GATHER4_BOX_ROWS");
@@ -759,6 +840,12 @@ int set_smem(K kern, int bytes) {
 
 using namespace csmoe;
 
+/* debug: per-CTA wait-cycle counters of csmoe_sigma_wgrad land in `buf` (8 x uint64 per CTA, >= 148 CTAs); NULL = off */
+extern "C" int csmoe_sigma_set_stats(void* buf) {
+  g_stats = static_cast<unsigned long long*>(buf);
+  return CSMOE_OK;
+}
+
 extern "C" int csmoe_sigma_ffn_supported(int64_t D, int32_t H, int64_t Dout) {
   return (H == kH && D > 0 && D % kBK == 0 && Dout > 0 && Dout % 128 == 0) ? 1 : 0;
 }
@@ -790,6 +877,7 @@ extern "C" int csmoe_sigma_ffn_fwd(const void* x, int64_t T, int32_t D, int32_t 
   p.bias_fp32 = bias_dtype == CSMOE_F32;
   p.gather = xp == nullptr ? gather_mode() : 0;
   p.a_src = static_cast<const __nv_bfloat16*>(x);
+  p.dbg = dbg_mask();
   static bool configured = false;
   if (!configured) {
     CSMOE_TRY(set_smem(sigma_ffn_kernel<false>, kSmemBytes));
@@ -831,6 +919,7 @@ extern "C" int csmoe_sigma_ffn_bwd(const void* dout, int64_t T, int32_t D, int32
   p.Dout = D;        // GEMM-2 produces the d x rows
   p.gather = dyp == nullptr ? gather_mode() : 0;
   p.a_src = static_cast<const __nv_bfloat16*>(dout);
+  p.dbg = dbg_mask();
   p.slot_w = slot_w;
   p.h = static_cast<const __nv_bfloat16*>(h);
   p.dw_part = dw_part;
@@ -867,6 +956,8 @@ extern "C" int csmoe_sigma_wgrad(const void* a, const void* g, int64_t T, int32_
   p.gather = gather_mode();
   p.g_src = static_cast<const __nv_bfloat16*>(g);
   p.N = N;
+  p.dbg = dbg_mask();
+  p.stats = g_stats;
   p.c_fp32 = c_dtype == CSMOE_F32;
   p.c = c;
   p.ldc = transpose ? kH : N;

@@ -271,6 +271,8 @@ int csmoe_compete_bwd(const void* y, int32_t dtype, int32_t E, int64_t T, int64_
  *         transpose = 0 -> c [E, H, N] (dvalues = hw^T . gather(dout));  1 -> c [E, N, H] (dkeys = (dz^T . gather(x))^T).
  *         fp32 accumulation over the expert's rows inside one CTA: deterministic (cvmm.py:194-345 uses fp32 atomics). */
 int csmoe_sigma_ffn_supported(int64_t D, int32_t H, int64_t Dout);
+/* tuning aid: per-CTA wait-cycle counters of csmoe_sigma_wgrad are written to buf (8 x uint64 per CTA); NULL switches it off */
+int csmoe_sigma_set_stats(void* buf);
 int csmoe_sigma_ffn_fwd(const void* x, int64_t T, int32_t D, int32_t Dout, int32_t E, const void* keys, const void* values,
                         const void* bias, int32_t bias_dtype, const int32_t* row_to_slot, const int32_t* tile_expert,
                         int64_t row_cap, int32_t slots_per_row, const void* xp, void* h, void* y, void* stream);

@@ -56,9 +56,10 @@ def check_grad(got, ref, what, rtol=RTOL, tail=3e-5):
     err = (g - r).abs() / (r.abs() + rms + 1e-30)
     n_out = int((err > rtol).sum())
     fro = float((g - r).norm() / (r.norm() + 1e-30))
+    allowed = max(int(tail * err.numel()), 4 if err.numel() >= 65536 else 0)   # small tensors: at most 4 stragglers
     print(f"    {what:34s} band error {float(err.max()):.3e} (limit {rtol:.0e}; {n_out}/{err.numel()} elements outside, "
-          f"allowed {int(tail * err.numel())}), Frobenius {fro:.2e}")
-    assert n_out <= tail * err.numel(), f"{what}: {n_out}/{err.numel()} elements outside the {rtol} band"
+          f"allowed {allowed}), Frobenius {fro:.2e}")
+    assert n_out <= allowed, f"{what}: {n_out}/{err.numel()} elements outside the {rtol} band"
     assert float(err.max()) <= 2 * rtol, f"{what}: worst element {float(err.max()):.3e} outside 2x the band"
     assert fro <= rtol / 4, f"{what}: Frobenius relative error {fro:.3e}"
 
