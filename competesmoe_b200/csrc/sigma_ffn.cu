@@ -62,7 +62,8 @@ struct Params {
   float* dw_part;               // [2, n_slots] partial <h, dh> of the two column halves
   long long n_slots;
   int dbg;                      // tuning experiments (CSMOE_SIGMA_DBG bit mask): 1 = no gather copies, 2 = no output-tile stores,
-                                // 4 = no saved-tile (h / dz / hw) stores
+                                // 4 = no saved-tile (h / dz / hw) stores, 16 = output tile by register-direct stores instead of staged TMA stores
+  __nv_bfloat16* out;           // [row_cap, Dout] output rows (y / dx rows), row pitch Dout
 };
 
 __device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int r0, int r1, int r2,
@@ -443,6 +444,7 @@ sigma_ffn_kernel(const __grid_constant__ CUtensorMap map_a,    // gathered opera
       }
     };
     auto epi2 = [&](int t) {
+      const bool row_valid = __ldg(p.row_to_slot + static_cast<long long>(t) * kBM + row) >= 0;
       for (int nc = 0; nc < nch; ++nc) {
         const int yb = ycount & 1;
         ptx::mbar_wait(bar.y_full(yb), (ycount >> 1) & 1);
@@ -457,13 +459,30 @@ sigma_ffn_kernel(const __grid_constant__ CUtensorMap map_a,    // gathered opera
         if (lane == 0) ptx::mbar_arrive(bar.y_empty(yb));     // the accumulator is in registers: hand the buffer back early
         ++ycount;
         if (p.dbg & 2) continue;
-        uint32_t w[16];
+        if (!(p.dbg & 16)) {   // 32 x 32 groups through the warp's staging tile and TMA stores
+          uint32_t w[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) w[i] = pack_bf16(__uint_as_float(v0[2 * i]), __uint_as_float(v0[2 * i + 1]));
-        store_group_bf16(stg, lane, w, &map_o, nc * 128 + half * 64, t * kBM + q * 32, slot);
+          for (int i = 0; i < 16; ++i) w[i] = pack_bf16(__uint_as_float(v0[2 * i]), __uint_as_float(v0[2 * i + 1]));
+          store_group_bf16(stg, lane, w, &map_o, nc * 128 + half * 64, t * kBM + q * 32, slot);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) w[i] = pack_bf16(__uint_as_float(v1[2 * i]), __uint_as_float(v1[2 * i + 1]));
-        store_group_bf16(stg, lane, w, &map_o, nc * 128 + half * 64 + 32, t * kBM + q * 32, slot);
+          for (int i = 0; i < 16; ++i) w[i] = pack_bf16(__uint_as_float(v1[2 * i]), __uint_as_float(v1[2 * i + 1]));
+          store_group_bf16(stg, lane, w, &map_o, nc * 128 + half * 64 + 32, t * kBM + q * 32, slot);
+        } else if (row_valid) {
+          // (CSMOE_SIGMA_DBG=16) register-direct: this thread owns 64 consecutive columns (128 bytes) of its row.  Measured
+          // slower at the C4 shape (forward 113 vs 79 us): 32 rows x 16 bytes per warp store instruction
+          uint4* dst = reinterpret_cast<uint4*>(p.out + (static_cast<long long>(t) * kBM + row) * p.Dout + nc * 128 + half * 64);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            dst[c] = make_uint4(pack_bf16(__uint_as_float(v0[8 * c]), __uint_as_float(v0[8 * c + 1])),
+                                pack_bf16(__uint_as_float(v0[8 * c + 2]), __uint_as_float(v0[8 * c + 3])),
+                                pack_bf16(__uint_as_float(v0[8 * c + 4]), __uint_as_float(v0[8 * c + 5])),
+                                pack_bf16(__uint_as_float(v0[8 * c + 6]), __uint_as_float(v0[8 * c + 7])));
+            dst[4 + c] = make_uint4(pack_bf16(__uint_as_float(v1[8 * c]), __uint_as_float(v1[8 * c + 1])),
+                                    pack_bf16(__uint_as_float(v1[8 * c + 2]), __uint_as_float(v1[8 * c + 3])),
+                                    pack_bf16(__uint_as_float(v1[8 * c + 4]), __uint_as_float(v1[8 * c + 5])),
+                                    pack_bf16(__uint_as_float(v1[8 * c + 6]), __uint_as_float(v1[8 * c + 7])));
+          }
+        }
       }
     };
     int n_done = 0, prev_t = -1;
@@ -572,18 +591,36 @@ sigma_wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     const int lrow = lane >> 3, lchunk = lane & 7;
     const uint32_t dst0 = lrow * 16 * 128;
     const int k = p.slots_per_row;
+    int4 s4_next[4];
+    bool have_next = false;
+    int next_r = -1;
     for (long long t = blockIdx.x; t < total; t += gridDim.x) {
       const int e = static_cast<int>(t / p.n_nblocks), nb = static_cast<int>(t % p.n_nblocks);
       const int r0 = __ldg(p.pad_offsets + e), r1 = __ldg(p.pad_offsets + e + 1);
+      have_next = false;
       for (int r = r0; r < r1; r += kBK, ++it) {
         if ((it & (kProdWarps - 1)) != static_cast<uint32_t>(warp)) continue;
         const long long ta = st_on ? clock64() : 0;
         int tok[16];
         if (p.gather == 1) {
-          const int4* sp = reinterpret_cast<const int4*>(p.row_to_slot + r + lrow * 16);
           int4 s4[4];
+          if (have_next && next_r == r) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) s4[j] = __ldg(sp + j);
+            for (int j = 0; j < 4; ++j) s4[j] = s4_next[j];
+          } else {
+            const int4* sp = reinterpret_cast<const int4*>(p.row_to_slot + r + lrow * 16);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) s4[j] = __ldg(sp + j);
+          }
+          // this warp's next k-block of the same tile is kProdWarps blocks further on: fetch its slots now, they arrive
+          // while this block's copies are issued and the stage wait is served
+          next_r = r + kProdWarps * kBK;
+          have_next = next_r < r1;
+          if (have_next) {
+            const int4* sp = reinterpret_cast<const int4*>(p.row_to_slot + next_r + lrow * 16);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) s4_next[j] = __ldg(sp + j);
+          }
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             tok[4 * j] = max(s4[j].x, 0) / k;
@@ -877,6 +914,7 @@ extern "C" int csmoe_sigma_ffn_fwd(const void* x, int64_t T, int32_t D, int32_t 
   p.bias_fp32 = bias_dtype == CSMOE_F32;
   p.gather = xp == nullptr ? gather_mode() : 0;
   p.a_src = static_cast<const __nv_bfloat16*>(x);
+  p.out = static_cast<__nv_bfloat16*>(y);
   p.dbg = dbg_mask();
   static bool configured = false;
   if (!configured) {
@@ -919,6 +957,7 @@ extern "C" int csmoe_sigma_ffn_bwd(const void* dout, int64_t T, int32_t D, int32
   p.Dout = D;        // GEMM-2 produces the d x rows
   p.gather = dyp == nullptr ? gather_mode() : 0;
   p.a_src = static_cast<const __nv_bfloat16*>(dout);
+  p.out = static_cast<__nv_bfloat16*>(dxr);
   p.dbg = dbg_mask();
   p.slot_w = slot_w;
   p.h = static_cast<const __nv_bfloat16*>(h);
