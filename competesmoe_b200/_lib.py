@@ -64,6 +64,7 @@ _SIGNATURES = {
     "csmoe_bias_grad": (i32, [vp, i32, i64, i32, i32, vp, i32, i64, vp, i32, vp, vp]),
     "csmoe_act_bwd_bias": (i32, [vp, vp, i32, i64, i64, i32, i32, vp, i32, i64, i32, vp, vp, i32, vp, vp]),
     "csmoe_cast_f32_bf16": (i32, [vp, vp, i64, vp]),
+    "csmoe_split_f32_bf16x3": (i32, [vp, vp, vp, vp, i64, vp]),
     "csmoe_affinity_fwd": (i32, [vp, i32, i32, i64, i64, i32, i32, vp, vp]),
     "csmoe_affinity_from_rowsum": (i32, [vp, i32, i32, i64, i64, i32, i32, vp, vp]),
     "csmoe_affinity_bwd": (i32, [vp, vp, i32, i32, i64, i64, i32, i32, vp, vp]),

@@ -173,6 +173,25 @@ cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ 
   }
 }
 
+// fp32 -> three bf16 terms with hi + mid + lo == x to 24 bits: the operands of the fp32-accurate GEMM path (six bf16
+// tensor-core products accumulated in fp32 reproduce an IEEE fp32 matmul to ~2^-22 relative, where a single bf16 product
+// has 2^-9).  The reference's fp32 cvmm forbids TF32 (layers/cvmm.py:395 allow_tf32=False).
+__global__ void __launch_bounds__(kThreads)
+split_bf16x3_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ mid,
+                    __nv_bfloat16* __restrict__ lo, long long n) {
+  for (long long i = static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * kThreads) {
+    const float x = src[i];
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    const float r1 = x - __bfloat162float(h);
+    const __nv_bfloat16 m = __float2bfloat16_rn(r1);
+    const float r2 = r1 - __bfloat162float(m);
+    hi[i] = h;
+    mid[i] = m;
+    lo[i] = __float2bfloat16_rn(r2);
+  }
+}
+
 inline unsigned flat_grid(long long work_items) {
   const long long blocks = (work_items + kThreads - 1) / kThreads;
   const long long cap = static_cast<long long>(num_sms() > 0 ? num_sms() : 148) * 8;
@@ -304,6 +323,15 @@ extern "C" int csmoe_cast_f32_bf16(const float* src, void* dst, int64_t n, void*
   if (n == 0) return CSMOE_OK;
   cast_f32_bf16_kernel<<<flat_grid(n / 8 + 1), kThreads, 0, as_stream(stream_)>>>(
       src, static_cast<__nv_bfloat16*>(dst), n);
+  CSMOE_CHECK_LAUNCH();
+  return CSMOE_OK;
+}
+
+extern "C" int csmoe_split_f32_bf16x3(const float* src, void* hi, void* mid, void* lo, int64_t n, void* stream_) {
+  CSMOE_CHECK_ARG(src && hi && mid && lo && n >= 0, "csmoe_split_f32_bf16x3: bad arguments");
+  if (n == 0) return CSMOE_OK;
+  split_bf16x3_kernel<<<flat_grid(n), kThreads, 0, as_stream(stream_)>>>(
+      src, static_cast<__nv_bfloat16*>(hi), static_cast<__nv_bfloat16*>(mid), static_cast<__nv_bfloat16*>(lo), n);
   CSMOE_CHECK_LAUNCH();
   return CSMOE_OK;
 }

@@ -1920,6 +1920,7 @@ extern "C" int csmoe_grouped_gemm(const csmoe_gemm_args* a, void* stream_) {
                    (a->mode == CSMOE_GEMM_ROWS && (a->preact != nullptr || a->act != CSMOE_ACT_NONE || act_bwd || a->k < 2048)))
                       ? 0 : 1;
   if (a->rowsum != nullptr) kp.direct_epi = 1;
+  if (a->accumulate) kp.direct_epi = 1;   // only the register-direct epilogue reads the old C (fp32-accurate path)
   if (epilogue_override() != 0 && !a->accumulate && a->rowsum == nullptr) kp.direct_epi = epilogue_override() == 1 ? 1 : 0;
   // TMA-store epilogue (the staged groups leave through cp.async.bulk.tensor instead of ld.shared + st.global): every
   // launch whose outputs are plain row-major matrices.  CSMOE_GEMM_EPI=tma forces it where legal, =staged / =direct

@@ -192,3 +192,59 @@ def cvmm(x: torch.Tensor, sel: Union[torch.Tensor, CVMMSel], keys: torch.Tensor)
     if sel.reduction_weight is None:
         return out.view(*sel.raw_sel.shape, keys.shape[-1])
     return out.view(*sel.reduction_weight.shape[:-1], keys.shape[-1])
+
+
+# ------------------------------------------------------------------------------------------------ torch.library op
+# The reference also exposes the forward kernel launcher as a dispatcher op so that torch.compile can trace through it
+# (cvmm.py:348-416):  mylib::cvmm_triton(Tensor x, Tensor sel_index, Tensor sel, Tensor keys, ScalarType out_dtype,
+# Tensor out_index) -> Tensor, with   out[out_index[i]] = x[sel_index[i]] @ keys[sel[i]]   for the SORTED expert ids
+# `sel` (out_index = tensor(-1): row i of the output is sorted row i).  This entry point takes the index tensors as
+# they are -- any sel_index / out_index, not only the two layouts `cvmm()` recognises -- because the rows are first
+# brought into sorted order with the caller's own indices and only then handed to the grouped GEMM.
+CVMM_TRITON_SCHEMA = "(Tensor x, Tensor sel_index, Tensor sel, Tensor keys, ScalarType out_dtype, Tensor out_index) -> Tensor"
+
+
+def cvmm_triton(x: torch.Tensor, sel_index: torch.Tensor, sel: torch.Tensor, keys: torch.Tensor, out_dtype: torch.dtype,
+                out_index: torch.Tensor) -> torch.Tensor:
+    x2 = x.flatten(end_dim=-2)
+    assert x2.shape[-1] == keys.shape[1]
+    sel_shape = sel.shape
+    fsel = sel.flatten()
+    M, (E, _, N) = fsel.shape[0], keys.shape
+    xs = x2.index_select(0, sel_index.flatten().long())                       # sorted row i <- x[sel_index[i]]
+    xb = ops.cast_bf16(xs) if xs.dtype != torch.bfloat16 else xs.contiguous()
+    kb = ops.cast_bf16(keys) if keys.dtype != torch.bfloat16 else keys
+    route = ops.route_build(fsel.to(torch.int32).view(-1, 1), E)              # already sorted: slot i is sorted row i
+    xp = ops.gather_rows(xb, route, slots_per_src_row=1)
+    yp = ops.gemm_rows(xp, kb, w_is_kn=True, route=route, out_dtype=out_dtype if out_dtype in (torch.bfloat16, torch.float32) else torch.float32)
+    ys = ops.scatter_reduce(yp, route.slot_to_row, M, 1)
+    if ys.dtype != out_dtype:
+        ys = ys.to(out_dtype)
+    # out_index "is None" is spelled tensor(-1) (cvmm.py:385-387); a 1-element index with M > 1 can only be that marker
+    if out_index.numel() == 1 and (M != 1 or int(out_index) == -1):
+        out = ys
+    else:
+        out = torch.empty_like(ys).index_copy_(0, out_index.flatten().long(), ys)
+    return out.view(*sel_shape, N)
+
+
+def _cvmm_triton_fake(x, sel_index, sel, keys, out_dtype, out_index):
+    return torch.empty((*sel.shape, keys.shape[-1]), device=x.device, dtype=out_dtype)
+
+
+def _register_library_op():
+    """Define mylib::cvmm_triton unless the reference's own module already did (both in one process: the reference's
+    definition stays, ours is reachable as csmoe::cvmm_triton and through `cvmm_triton_call`)."""
+    lib = torch.library
+    for ns in ("mylib", "csmoe"):
+        try:
+            lib.define(f"{ns}::cvmm_triton", CVMM_TRITON_SCHEMA)
+        except RuntimeError:
+            continue                                   # already defined in this process
+        lib.impl(f"{ns}::cvmm_triton", "CUDA")(cvmm_triton)
+        (getattr(lib, "register_fake", None) or lib.impl_abstract)(f"{ns}::cvmm_triton")(_cvmm_triton_fake)
+        return getattr(getattr(torch.ops, ns), "cvmm_triton")
+    return cvmm_triton
+
+
+cvmm_triton_call = _register_library_op()

@@ -50,6 +50,7 @@ class FFNSpec:
     kn_layout: bool = False  # False: w1 [E,F,D], w2 [E,Dout,F] (nn.Linear);  True: w1 [E,D,H], w2 [E,H,Dout] (sigma-MoE)
     round_each: bool = True  # combine: round the running sum to the activation dtype after every expert (moe.py:204)
     round_w: bool = False    # combine: round the routing weight to the activation dtype first (cvmm.py:483)
+    fp32: bool = False       # fp32 operands outside autocast: fp32-accurate products (six split-bf16 MMAs, ops.gemm_rows_f32)
     bias_after_round: bool = False  # first projection: bf16(x . W) + b (pretrain: fp32 bias added to the bf16 cvmm result)
     return_hidden: bool = False  # SparseFFNFn also returns (h = act(z) [row_cap, H], row_to_slot) for the relu_pass_rate log
 
@@ -64,6 +65,31 @@ def _bf16(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
     return ops.cast_bf16(t)
 
 
+def _op(t: Optional[torch.Tensor], spec: "FFNSpec") -> Optional[torch.Tensor]:
+    """GEMM operand in the arithmetic the spec asks for: bf16 (cast when needed) or, in fp32 mode, the fp32 tensor itself."""
+    if t is None:
+        return None
+    if spec.fp32:
+        return t if t.dtype == torch.float32 else t.float()
+    return _bf16(t)
+
+
+def _mm_rows(a, w, spec: "FFNSpec", **kw):
+    if not spec.fp32:
+        return ops.gemm_rows(a, w, **kw)
+    for k in ("rowsum_softplus", "act_bwd", "aux", "c_rows"):
+        assert kw.pop(k, None) in (None, ops.ACT_NONE), f"fp32-accurate path has no fused '{k}' epilogue"
+    kw.pop("out_dtype", None)
+    return ops.gemm_rows_f32(a, w, **kw)
+
+
+def _mm_reduce(a, b, num_experts, spec: "FFNSpec", **kw):
+    if not spec.fp32:
+        return ops.gemm_reduce(a, b, num_experts, **kw)
+    out_dtype = kw.pop("out_dtype", torch.float32)
+    return ops.gemm_reduce_f32(a, b, num_experts, **kw).to(out_dtype)
+
+
 def _pad_rows(x: torch.Tensor, rows: int) -> torch.Tensor:
     if x.shape[0] == rows:
         return x
@@ -73,17 +99,17 @@ def _pad_rows(x: torch.Tensor, rows: int) -> torch.Tensor:
 
 def _ffn_first(xp, w1, b1, spec: FFNSpec, **where):
     """z (pre-activation, with bias) and h = act(z) for the first projection."""
-    if spec.glu and not spec.kn_layout and b1 is None and _FUSE_FWD:
+    if spec.glu and not spec.kn_layout and b1 is None and _FUSE_FWD and not spec.fp32:
         h, z = ops.gemm_rows(xp, w1, w_is_kn=False, act=ops.ACT_SILU_GLU, **where)   # GLU fused in the epilogue
         return z, h
-    bar = spec.bias_after_round and b1 is not None
+    bar = spec.bias_after_round and b1 is not None and not spec.fp32
     if spec.glu:
-        z = ops.gemm_rows(xp, w1, w_is_kn=spec.kn_layout, bias=b1, bias_after_round=bar, **where)
+        z = _mm_rows(xp, w1, spec, w_is_kn=spec.kn_layout, bias=b1, bias_after_round=bar, **where)
         return z, ops.act_fwd(z, spec.act, where.get("route"))
     if spec.act == ops.ACT_NONE:
-        z = ops.gemm_rows(xp, w1, w_is_kn=spec.kn_layout, bias=b1, bias_after_round=bar, **where)
+        z = _mm_rows(xp, w1, spec, w_is_kn=spec.kn_layout, bias=b1, bias_after_round=bar, **where)
         return z, z
-    h, z = ops.gemm_rows(xp, w1, w_is_kn=spec.kn_layout, bias=b1, act=spec.act, want_preact=True, bias_after_round=bar, **where)
+    h, z = _mm_rows(xp, w1, spec, w_is_kn=spec.kn_layout, bias=b1, act=spec.act, want_preact=True, bias_after_round=bar, **where)
     return z, h
 
 
@@ -128,19 +154,19 @@ class SparseFFNFn(Function):
     def forward(ctx, x, w, sel, w1, b1, w2, b2, spec: FFNSpec):
         T, K = sel.shape
         E = w1.shape[0]
-        xb = _bf16(x)
-        w1b, w2b = _bf16(w1), _bf16(w2)
+        xb = _op(x, spec)
+        w1b, w2b = _op(w1, spec), _op(w2, spec)
         route = ops.route_build(sel, E)
         xp = ops.gather_rows(xb, route)
         z, h = _ffn_first(xp, w1b, b1, spec, route=route)
-        y = ops.gemm_rows(h, w2b, w_is_kn=spec.kn_layout, bias=b2, route=route)
+        y = _mm_rows(h, w2b, spec, w_is_kn=spec.kn_layout, bias=b2, route=route)
         out = ops.combine_fwd(y, route.slot_to_row, route.sel, w, T, K, round_each=spec.round_each, round_w=spec.round_w)
         ctx.route, ctx.spec = route, spec
         ctx.x_dtype = x.dtype
         ctx.has_b = (b1 is not None, b2 is not None)
         ctx.save_for_backward(xp, z, h, y, w, w1, w2)
         # fp32 master weights (pretrain under autocast): keep the bf16 copies of this step for the backward pass
-        ctx.wb = (w1b if w1b is not w1 else None, w2b if w2b is not w2 else None)
+        ctx.wb = (w1b if (w1b is not w1 and not spec.fp32) else None, w2b if (w2b is not w2 and not spec.fp32) else None)
         if spec.return_hidden:
             hd = h.detach()
             ctx.mark_non_differentiable(hd, route.row_to_slot)
@@ -153,24 +179,24 @@ class SparseFFNFn(Function):
         xp, z, h, y, w, w1, w2 = ctx.saved_tensors
         route, spec = ctx.route, ctx.spec
         T, K, E = route.n_slots // route.top_k, route.top_k, route.num_experts
-        w1b = ctx.wb[0] if ctx.wb[0] is not None else _bf16(w1)
-        w2b = ctx.wb[1] if ctx.wb[1] is not None else _bf16(w2)
-        dout = _bf16(dout.contiguous())
+        w1b = ctx.wb[0] if ctx.wb[0] is not None else _op(w1, spec)
+        w2b = ctx.wb[1] if ctx.wb[1] is not None else _op(w2, spec)
+        dout = _op(dout.contiguous(), spec)
         need = ctx.needs_input_grad
         dw = ops.combine_bwd_w(y, dout, route.slot_to_row, T, K) if need[1] else None
         wu = w.to(torch.bfloat16).float() if spec.round_w else w
         dyp = ops.gather_rows(dout, route, slot_w=wu)                          # w * dout in expert-major order
         db2 = ops.bias_grad(dyp, E, route=route, out_dtype=w2.dtype) if ctx.has_b[1] else None
         if spec.kn_layout:
-            dw2 = ops.gemm_reduce(h, dyp, E, route=route, out_dtype=w2.dtype)  # [E, H, Dout]
+            dw2 = _mm_reduce(h, dyp, E, spec, route=route, out_dtype=w2.dtype)  # [E, H, Dout]
         else:
-            dw2 = ops.gemm_reduce(dyp, h, E, route=route, out_dtype=w2.dtype)  # [E, Dout, F]
+            dw2 = _mm_reduce(dyp, h, E, spec, route=route, out_dtype=w2.dtype)  # [E, Dout, F]
         # dgrad of the second projection with the activation backward fused into its epilogue: dz = (dy W2) * act'(z)
         fused_db1 = False
-        if _FUSE_BWD:
+        if _FUSE_BWD and not spec.fp32:
             dz = ops.gemm_rows(dyp, w2b, w_is_kn=not spec.kn_layout, route=route, act_bwd=spec.act, aux=z)
         else:
-            dh = ops.gemm_rows(dyp, w2b, w_is_kn=not spec.kn_layout, route=route)
+            dh = _mm_rows(dyp, w2b, spec, w_is_kn=not spec.kn_layout, route=route)
             if ctx.has_b[0] and _FUSE_ACT_BIAS and spec.act not in (ops.ACT_NONE, ops.ACT_SILU_GLU):
                 # activation backward + bias gradient in one pass over dh / z
                 dz, db1 = ops.act_bwd_bias(z, dh, spec.act, E, route=route, out_dtype=w1.dtype)
@@ -180,12 +206,12 @@ class SparseFFNFn(Function):
         if not fused_db1:
             db1 = ops.bias_grad(dz, E, route=route, out_dtype=w1.dtype) if ctx.has_b[0] else None
         if spec.kn_layout:
-            dw1 = ops.gemm_reduce(xp, dz, E, route=route, out_dtype=w1.dtype)  # [E, D, H]
+            dw1 = _mm_reduce(xp, dz, E, spec, route=route, out_dtype=w1.dtype)  # [E, D, H]
         else:
-            dw1 = ops.gemm_reduce(dz, xp, E, route=route, out_dtype=w1.dtype)  # [E, F, D]
+            dw1 = _mm_reduce(dz, xp, E, spec, route=route, out_dtype=w1.dtype)  # [E, F, D]
         dx = None
         if need[0]:
-            dxp = ops.gemm_rows(dz, w1b, w_is_kn=not spec.kn_layout, route=route)
+            dxp = _mm_rows(dz, w1b, spec, w_is_kn=not spec.kn_layout, route=route)
             dx = ops.scatter_reduce(dxp, route.slot_to_row, T, K).to(ctx.x_dtype)
         return dx, dw, None, dw1, db1, dw2, db2, None
 
@@ -252,12 +278,13 @@ class DenseFFNFn(Function):
     def forward(ctx, x, w1, b1, w2, b2, spec: FFNSpec, score_round: Optional[bool] = None):
         T = x.shape[0]
         t_pad = (T + 2 * ROW_TILE - 1) // (2 * ROW_TILE) * (2 * ROW_TILE)   # 256: CTA-pair GEMM tiles
-        xb = _pad_rows(_bf16(x), t_pad)
-        w1b, w2b = _bf16(w1), _bf16(w2)
+        xb = _pad_rows(_op(x, spec), t_pad)
+        w1b, w2b = _op(w1, spec), _op(w2, spec)
         z, h = _ffn_first(xb, w1b, b1, spec, dense_rows=t_pad, a_expert_rows=0)
-        fuse_score = score_round is not None and (_SCORE_EPILOGUE == "1" or (_SCORE_EPILOGUE == "auto" and h.shape[1] >= 1024))
-        y = ops.gemm_rows(h, w2b, w_is_kn=spec.kn_layout, bias=b2, dense_rows=t_pad, a_expert_rows=t_pad,
-                          rowsum_softplus=score_round if fuse_score else None)
+        fuse_score = score_round is not None and not spec.fp32 and \
+            (_SCORE_EPILOGUE == "1" or (_SCORE_EPILOGUE == "auto" and h.shape[1] >= 1024))
+        y = _mm_rows(h, w2b, spec, w_is_kn=spec.kn_layout, bias=b2, dense_rows=t_pad, a_expert_rows=t_pad,
+                     rowsum_softplus=score_round if fuse_score else None)
         ctx.spec, ctx.T, ctx.t_pad, ctx.x_dtype = spec, T, t_pad, x.dtype
         ctx.has_b = (b1 is not None, b2 is not None)
         ctx.save_for_backward(xb, z, h, w1, w2)
@@ -275,19 +302,19 @@ class DenseFFNFn(Function):
         xb, z, h, w1, w2 = ctx.saved_tensors
         spec, T, t_pad = ctx.spec, ctx.T, ctx.t_pad
         E = w1.shape[0]
-        w1b, w2b = _bf16(w1), _bf16(w2)
-        dy = _bf16(dy.contiguous())
+        w1b, w2b = _op(w1, spec), _op(w2, spec)
+        dy = _op(dy.contiguous(), spec)
         db2 = ops.bias_grad(dy, E, dense_rows=t_pad, out_dtype=w2.dtype) if ctx.has_b[1] else None
         if spec.kn_layout:
-            dw2 = ops.gemm_reduce(h, dy, E, dense_rows=t_pad, a_expert_rows=t_pad, b_expert_rows=t_pad, out_dtype=w2.dtype)
+            dw2 = _mm_reduce(h, dy, E, spec, dense_rows=t_pad, a_expert_rows=t_pad, b_expert_rows=t_pad, out_dtype=w2.dtype)
         else:
-            dw2 = ops.gemm_reduce(dy, h, E, dense_rows=t_pad, a_expert_rows=t_pad, b_expert_rows=t_pad, out_dtype=w2.dtype)
+            dw2 = _mm_reduce(dy, h, E, spec, dense_rows=t_pad, a_expert_rows=t_pad, b_expert_rows=t_pad, out_dtype=w2.dtype)
         fused_db1 = False
-        if _FUSE_BWD:
+        if _FUSE_BWD and not spec.fp32:
             dz = ops.gemm_rows(dy, w2b, w_is_kn=not spec.kn_layout, dense_rows=t_pad, a_expert_rows=t_pad,
                                act_bwd=spec.act, aux=z)
         else:
-            dh = ops.gemm_rows(dy, w2b, w_is_kn=not spec.kn_layout, dense_rows=t_pad, a_expert_rows=t_pad)
+            dh = _mm_rows(dy, w2b, spec, w_is_kn=not spec.kn_layout, dense_rows=t_pad, a_expert_rows=t_pad)
             if ctx.has_b[0] and _FUSE_ACT_BIAS and spec.act not in (ops.ACT_NONE, ops.ACT_SILU_GLU):
                 dz, db1 = ops.act_bwd_bias(z, dh, spec.act, E, dense_rows=t_pad, out_dtype=w1.dtype)
                 fused_db1 = True
@@ -296,17 +323,17 @@ class DenseFFNFn(Function):
         if not fused_db1:
             db1 = ops.bias_grad(dz, E, dense_rows=t_pad, out_dtype=w1.dtype) if ctx.has_b[0] else None
         if spec.kn_layout:
-            dw1 = ops.gemm_reduce(xb, dz, E, dense_rows=t_pad, a_expert_rows=0, b_expert_rows=t_pad, out_dtype=w1.dtype)
+            dw1 = _mm_reduce(xb, dz, E, spec, dense_rows=t_pad, a_expert_rows=0, b_expert_rows=t_pad, out_dtype=w1.dtype)
         else:
-            dw1 = ops.gemm_reduce(dz, xb, E, dense_rows=t_pad, a_expert_rows=t_pad, b_expert_rows=0, out_dtype=w1.dtype)
+            dw1 = _mm_reduce(dz, xb, E, spec, dense_rows=t_pad, a_expert_rows=t_pad, b_expert_rows=0, out_dtype=w1.dtype)
         dx = None
         if ctx.needs_input_grad[0]:
             # dx[t] = sum_e dz[e, t] . W1[e]: one GEMM whose k loop runs over (expert, hidden) -- no [E, T, D] intermediate
             if dz.shape[1] % 64 == 0:
-                dx = ops.gemm_rows(dz, w1b, w_is_kn=not spec.kn_layout, dense_rows=t_pad, a_expert_rows=t_pad,
-                                   sum_experts=True)[:T].to(ctx.x_dtype)
+                dx = _mm_rows(dz, w1b, spec, w_is_kn=not spec.kn_layout, dense_rows=t_pad, a_expert_rows=t_pad,
+                              sum_experts=True)[:T].to(ctx.x_dtype)
             else:
-                dxe = ops.gemm_rows(dz, w1b, w_is_kn=not spec.kn_layout, dense_rows=t_pad, a_expert_rows=t_pad)
+                dxe = _mm_rows(dz, w1b, spec, w_is_kn=not spec.kn_layout, dense_rows=t_pad, a_expert_rows=t_pad)
                 dx = dxe.view(E, t_pad, -1)[:, :T].float().sum(0).to(ctx.x_dtype)
         return dx, dw1, db1, dw2, db2, None, None
 

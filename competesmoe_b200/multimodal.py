@@ -287,8 +287,11 @@ class MoeLayer(nn.Module):
         sim = sim * (1 - torch.eye(K, device=eo.device))
         return sim.mean()
 
-    def _spec(self, lay: X.ExpertLayout) -> FFNSpec:
-        return FFNSpec(act=lay.act, kn_layout=False, round_each=True, round_w=False)
+    def _spec(self, lay: X.ExpertLayout, x: Optional[torch.Tensor] = None) -> FFNSpec:
+        # fp32 activations outside autocast (an fp32 module called as is): fp32-accurate expert products, what the eager
+        # reference computes; everything else runs the bf16 tensor-core path
+        fp32 = x is not None and x.dtype == torch.float32 and not torch.is_autocast_enabled()
+        return FFNSpec(act=lay.act, kn_layout=False, round_each=True, round_w=False, fp32=fp32)
 
     def forward(self, x, return_id_experts=False):
         """Plain sparse MoE (moe.py:228-246)."""
@@ -296,7 +299,7 @@ class MoeLayer(nn.Module):
         x2 = x.reshape(B * N, D)
         lay, w1, b1, w2, b2 = self._stacked_weights()
         logits, probs, gw, gidx, losses = GateFn.apply(x2, self.gate.weight, self.num_selected, B, True)
-        out = self._sparse_ffn(x2, gw, gidx, w1, b1, w2, b2, self._spec(lay)).view(B, N, self.out_embed_dim)
+        out = self._sparse_ffn(x2, gw, gidx, w1, b1, w2, b2, self._spec(lay, x2)).view(B, N, self.out_embed_dim)
         balance_loss, router_z_loss = losses[0], losses[1]
         aux = balance_loss * self.args.balance_loss_coef + router_z_loss * self.args.router_z_loss_coef
         infor_aux = {"balance_loss": balance_loss.detach().clone(), "router_z_loss": router_z_loss.detach().clone()}
@@ -372,7 +375,7 @@ class CompeteSMoE(MoeLayer):
         T, E, K = B * N, self.num_of_experts, self.num_selected
         x2 = x.reshape(T, D)
         lay, w1, b1, w2, b2 = self._stacked_weights()
-        spec = self._spec(lay)
+        spec = self._spec(lay, x2)
         compete = self._is_competition_step(x)
         want_aux = (not compete) and (x.requires_grad or return_id_experts)
         gate_logits, gate_softmax, gate_w, gate_idx, gate_losses = self.router_policy(x2, B, want_aux)

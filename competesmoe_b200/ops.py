@@ -293,7 +293,8 @@ def gemm_rows(a: torch.Tensor, w: torch.Tensor, *, w_is_kn: bool, route: Optiona
               dense_rows: int = 0, a_expert_rows: int = 0, bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
               want_preact: bool = False, out_dtype: Optional[torch.dtype] = None, act_bwd: int = ACT_NONE,
               aux: Optional[torch.Tensor] = None, c_rows: Optional[torch.Tensor] = None, sum_experts: bool = False,
-              rowsum_softplus: Optional[bool] = None, bias_after_round: bool = False):
+              rowsum_softplus: Optional[bool] = None, bias_after_round: bool = False,
+              accumulate_into: Optional[torch.Tensor] = None):
     """C[row] = A[row] . W[expert(row)] with a fused epilogue.
 
     a: [rows, k] bf16.  w: [E, n, k] (w_is_kn=False, nn.Linear layout) or [E, k, n] (w_is_kn=True).
@@ -340,6 +341,11 @@ def gemm_rows(a: torch.Tensor, w: torch.Tensor, *, w_is_kn: bool, route: Optiona
         assert not want_preact and out_dtype in (torch.bfloat16, torch.float32)
         c = None
         g.c, g.ldc, g.c_dtype, g.c_rows = None, c_cols, BF16 if out_dtype == torch.bfloat16 else F32, _p(c_rows)
+    elif accumulate_into is not None:    # C += A . W (fp32 C; the fp32-accurate path sums six bf16 products this way)
+        c = accumulate_into
+        assert c.dtype == torch.float32 and c.shape == (m, c_cols) and c.is_contiguous() and not glu_fwd and not glu_bwd
+        g.c, g.ldc, g.c_dtype, g.accumulate = _p(c), c_cols, F32, 1
+        out_dtype = torch.float32
     else:
         c = torch.empty(m, c_cols, dtype=out_dtype, device=a.device)
         g.c, g.ldc, g.c_dtype = _p(c), c_cols, _dt(c)
@@ -371,7 +377,7 @@ def gemm_rows(a: torch.Tensor, w: torch.Tensor, *, w_is_kn: bool, route: Optiona
 
 def gemm_reduce(a: torch.Tensor, b: torch.Tensor, num_experts: int, *, route: Optional[Route] = None,
                 dense_rows: int = 0, a_expert_rows: int = 0, b_expert_rows: int = 0,
-                out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
+                out_dtype: torch.dtype = torch.float32, accumulate_into: Optional[torch.Tensor] = None) -> torch.Tensor:
     """C[e] = A[rows of e]^T . B[rows of e]  -> [E, a.shape[1], b.shape[1]] (wgrad)."""
     _cuda(a, b)
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
@@ -390,7 +396,12 @@ def gemm_reduce(a: torch.Tensor, b: torch.Tensor, num_experts: int, *, route: Op
     g.m, g.n = m, n
     g.a, g.lda = _p(a), a.stride(0)
     g.b, g.ldb = _p(b), b.stride(0)
-    c = torch.empty(num_experts, m, n, dtype=out_dtype, device=a.device)
+    if accumulate_into is not None:
+        c = accumulate_into
+        assert c.dtype == torch.float32 and c.shape == (num_experts, m, n) and c.is_contiguous()
+        g.accumulate = 1
+    else:
+        c = torch.empty(num_experts, m, n, dtype=out_dtype, device=a.device)
     g.c, g.ldc, g.c_expert_stride, g.c_dtype = _p(c), n, m * n, _dt(c)
     algo_rows = num_experts * dense_rows if dense_rows else route.n_slots
     _gemm(g, 2.0 * algo_rows * m * n, "reduce")
@@ -457,6 +468,54 @@ def act_bwd_bias(z: torch.Tensor, dh: torch.Tensor, act: int, num_experts: int, 
     _call("csmoe_act_bwd_bias", _p(z), _p(dh), _dt(z), z.stride(0), dh.stride(0), n, num_experts, po,
           1 if dense_rows else 0, dense_rows, act, _p(dz), _p(db), _dt(db), _p(ws), _stream(), kernels=2)
     return dz, db
+
+
+def split_bf16x3(src: torch.Tensor):
+    """fp32 tensor -> (hi, mid, lo) bf16 tensors of the same shape with hi + mid + lo == src to 24 bits."""
+    _cuda(src)
+    assert src.dtype == torch.float32
+    src = src.contiguous()
+    hi, mid, lo = (torch.empty(src.shape, dtype=torch.bfloat16, device=src.device) for _ in range(3))
+    _call("csmoe_split_f32_bf16x3", _p(src), _p(hi), _p(mid), _p(lo), src.numel(), _stream())
+    return hi, mid, lo
+
+
+# hi.hi, hi.mid, mid.hi, mid.mid, hi.lo, lo.hi: every product term above 2^-24 of the result
+_X3_PAIRS = ((0, 0), (0, 1), (1, 0), (1, 1), (0, 2), (2, 0))
+
+
+def gemm_rows_f32(a: torch.Tensor, w: torch.Tensor, *, bias=None, act: int = ACT_NONE, want_preact: bool = False,
+                  bias_after_round: bool = False, **where):
+    """gemm_rows for fp32 operands with fp32-accurate results (six split-bf16 tensor-core products, fp32 accumulation).
+    Same arguments as gemm_rows (layout / row-space keywords in **where); bias, activation and the saved pre-activation
+    are applied by the last product's epilogue."""
+    A = a if isinstance(a, tuple) else split_bf16x3(a)
+    W = w if isinstance(w, tuple) else split_bf16x3(w)
+    c = None
+    for n, (i, j) in enumerate(_X3_PAIRS):
+        last = n == len(_X3_PAIRS) - 1
+        kw = dict(where)
+        if last:
+            kw.update(bias=bias, act=act, want_preact=want_preact)
+        if c is None:
+            c = gemm_rows(A[i], W[j], out_dtype=torch.float32, **kw)
+        else:
+            r = gemm_rows(A[i], W[j], accumulate_into=c, **kw)
+            if last and want_preact:
+                return r
+    return c
+
+
+def gemm_reduce_f32(a: torch.Tensor, b: torch.Tensor, num_experts: int, **where) -> torch.Tensor:
+    """gemm_reduce for fp32 operands, fp32-accurate (see gemm_rows_f32)."""
+    A = a if isinstance(a, tuple) else split_bf16x3(a)
+    B = b if isinstance(b, tuple) else split_bf16x3(b)
+    where.pop("out_dtype", None)
+    c = None
+    for i, j in _X3_PAIRS:
+        c = gemm_reduce(A[i], B[j], num_experts, out_dtype=torch.float32, **where) if c is None else \
+            gemm_reduce(A[i], B[j], num_experts, accumulate_into=c, **where)
+    return c
 
 
 def cast_bf16(src: torch.Tensor) -> torch.Tensor:

@@ -363,7 +363,7 @@ class MoE(LoggingLayer, RegularizedLayer, OncePerIterLayer, torch.nn.Module):
         # CVMM.forward reduces with `reduction_weight.type_as(res) @ res` (cvmm.py:481-483): weight rounded to the op
         # dtype, fp32 accumulation, one rounding at the end.
         return FFNSpec(act=self._act_code, kn_layout=True, round_each=False, round_w=cdt == torch.bfloat16,
-                       bias_after_round=True)
+                       bias_after_round=True, fp32=cdt == torch.float32)
 
     def compute_gate(self, x2: torch.Tensor, cdt: torch.dtype):
         return GateFn.apply(self._cast(x2, cdt), self.w_gate, self.num_selected, 1, False)[:4]

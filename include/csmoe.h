@@ -222,6 +222,11 @@ int csmoe_act_bwd_bias(const void* z, const void* dh, int32_t dtype, int64_t ldz
                        void* dz, void* dbias, int32_t out_dtype, void* workspace, void* stream);
 /* dst = (bf16) src, n elements. */
 int csmoe_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream);
+/* hi + mid + lo == src to 24 bits, each term bf16: operands of the fp32-accurate path, in which one fp32 GEMM is six bf16
+ * tensor-core products (hi.hi, hi.mid, mid.hi, mid.mid, hi.lo, lo.hi) accumulated into an fp32 C with
+ * csmoe_gemm_args.accumulate -- fp32 callers outside autocast get fp32 results (the reference's fp32 cvmm is IEEE FMA,
+ * layers/cvmm.py:395 allow_tf32=False; BASELINE north_star: fp32 rtol 1e-4). */
+int csmoe_split_f32_bf16x3(const float* src, void* hi, void* mid, void* lo, int64_t n, void* stream);
 
 /* ------------------------------------------------------------------------------------------------ competition
  * Neural-response score (moe_model/.../competesmoe.py:240-243; moe_pretrain_model/.../competesmoe.py:399-403):

@@ -226,3 +226,43 @@ def test_pretrain_layer_cuda_graph_mode_matches_eager(name):
     graphed.eval()
     with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
         assert graphed(fx["x"].to(DEV), id_layer=0).shape == fx["out"].shape
+
+
+def test_cvmm_triton_library_op_honours_arbitrary_index_tensors():
+    """torch.ops.mylib.cvmm_triton (cvmm.py:348-416): out[out_index[i]] = x[sel_index[i]] @ keys[sel[i]] for sorted
+    expert ids `sel`, with index tensors that are NOT the stable-sort maps (a shuffled gather and scatter), and with the
+    out_index = tensor(-1) marker.  Reference = the same formula in plain torch."""
+    import competesmoe_b200.cvmm as C
+    g = torch.Generator().manual_seed(3)
+    M, R, E, D, N = 300, 120, 6, 64, 96
+    sel = torch.sort(torch.randint(0, E, (M,), generator=g)).values.int()
+    sel_index = torch.randint(0, R, (M,), generator=g)
+    out_index = torch.randperm(M, generator=g)
+    x = torch.randn(R, D, generator=g)
+    keys = torch.randn(E, D, N, generator=g) / D ** 0.5
+    want_sorted = torch.einsum("md,mdn->mn", x.bfloat16().float()[sel_index], keys.bfloat16().float()[sel.long()])
+    want = torch.empty(M, N).index_copy_(0, out_index, want_sorted)
+    op = torch.ops.mylib.cvmm_triton if C.cvmm_triton_call is torch.ops.mylib.cvmm_triton else C.cvmm_triton_call
+    got = op(x.to(DEV), sel_index.to(DEV), sel.to(DEV), keys.to(DEV), torch.float32, out_index.to(DEV))
+    assert got.shape == (M, N) and got.dtype == torch.float32
+    assert_close_rms(got, want, 1e-2, "cvmm_triton with shuffled indices")
+    got2 = op(x.to(DEV), sel_index.to(DEV), sel.to(DEV).view(M // 2, 2), keys.to(DEV), torch.bfloat16, torch.tensor(-1, device=DEV))
+    assert got2.shape == (M // 2, 2, N) and got2.dtype == torch.bfloat16
+    assert_close_rms(got2.view(M, N), want_sorted, 2e-2, "cvmm_triton, out_index = -1")
+
+
+def test_cvmm_rejects_index_tensors_it_cannot_express():
+    """cvmm() uses the route built from raw_sel; a CVMMSel whose sel_index was edited to anything but the recognised
+    layouts must raise instead of silently computing other rows."""
+    from competesmoe_b200.cvmm import cvmm, cvmm_prepare_sel2
+    g = torch.Generator().manual_seed(4)
+    T, K, E, D = 64, 2, 4, 32
+    sel = torch.stack([torch.randperm(E, generator=g)[:K] for _ in range(T)]).int().to(DEV)
+    x = torch.randn(T, D, generator=g).to(DEV)
+    keys = torch.randn(E, D, 16, generator=g).to(DEV)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        s = cvmm_prepare_sel2(sel, n_experts=E)
+        cvmm(x, s, keys)                                   # the maps it built itself are fine
+        s.sel_index = torch.flip(s.sel_index, dims=[0])    # not `pos // K` any more
+        with pytest.raises(NotImplementedError):
+            cvmm(x, s, keys)
