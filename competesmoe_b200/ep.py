@@ -27,7 +27,7 @@ from torch.autograd.function import once_differentiable
 
 from . import _lib, ops
 from ._lib import ROW_TILE, check
-from .functional import FFNSpec, _bf16, _ffn_first, _FUSE_ACT_BIAS, _FUSE_BWD
+from .functional import FFNSpec, _bf16, _ffn_first, _FUSE_ACT_BIAS, _FUSE_BWD, sigma_fused_ok
 
 MAX_EXPERTS = 1024
 _CTRL_BYTES = 4096 + 16 * MAX_EXPERTS * 4   # flags, epoch, counts_all[P<=16][E<=1024]
@@ -226,6 +226,15 @@ class EPPlan:
         return ops.Route(self.experts_per_rank, 1, n_slots_hint, self.row_cap, None, self.recv_counts, None,
                          self.recv_pad_offsets, None, None, None, None, self.tile_expert, self.row_tile)
 
+    def fused_route(self, c_rows: torch.Tensor) -> ops.Route:
+        """The received rows as the fused sigma-MoE kernels see them: one "slot" per received row (row r is slot r when
+        it holds a routed row, -1 on padding), so the kernels' validity masks and row gathers work on the receive buffer
+        directly.  c_rows (the return addresses) is 0 exactly on padding rows."""
+        rows = torch.arange(self.row_cap, dtype=torch.int32, device=c_rows.device)
+        rmap = torch.where(c_rows != 0, rows, torch.full_like(rows, -1))
+        return ops.Route(self.experts_per_rank, 1, self.row_cap, self.row_cap, None, self.recv_counts, None,
+                         self.recv_pad_offsets, None, None, None, rmap, self.tile_expert, self.row_tile)
+
 
 class EPLayerState:
     """Per-layer exchange buffers that must live from forward to backward (the received tokens are the activations
@@ -361,13 +370,24 @@ class EPSparseFFNFn(Function):
         tags = st.tags.tensor(0, (st.row_cap,), torch.int64)
         c_rows = g.row_ptrs(tags, plan, st.ret_y.peers(), st.Dout, torch.bfloat16, xp)
         lr = plan.local_route(T * K)
-        z, h = _ffn_first(xp, w1b, b1, spec, route=lr)
-        ops.gemm_rows(h, w2b, w_is_kn=spec.kn_layout, bias=b2, route=lr, c_rows=c_rows)   # output rows land on their source ranks
+        fused = b2 is None and sigma_fused_ok(xb, w1, w2, spec, torch.bfloat16)
+        if fused:
+            # expert size 128 + ReLU: both projections in one kernel on the received rows (tiled loads: the rows are
+            # already expert-major here), then the output rows are pushed to their source ranks
+            fr = plan.fused_route(c_rows)
+            y_loc, h = ops.sigma_ffn_fwd(xp, w1b, w2b, b1, fr, slots_per_row=1, xp=xp)
+            ops._call("csmoe_ep_push_rows", y_loc.data_ptr(), ops.BF16, y_loc.shape[1], y_loc.shape[1], y_loc.shape[0],
+                      c_rows.data_ptr(), ops._stream())
+            z = h
+        else:
+            z, h = _ffn_first(xp, w1b, b1, spec, route=lr)
+            ops.gemm_rows(h, w2b, w_is_kn=spec.kn_layout, bias=b2, route=lr, c_rows=c_rows)   # output rows land on their source ranks
         g.barrier()
         y = st.ret_y.tensor(0, (T * K, st.Dout), torch.bfloat16)
         ident = g.identity(T * K)
         out = ops.combine_fwd(y, ident, route.sel, w, T, K, round_each=spec.round_each, round_w=spec.round_w)
         ctx.st, ctx.spec, ctx.route, ctx.plan = st, spec, route, plan
+        ctx.fused = fused
         ctx.x_dtype, ctx.has_b = x.dtype, (b1 is not None, b2 is not None)
         ctx.save_for_backward(z, h, w, w1, w2)
         return out
@@ -394,6 +414,23 @@ class EPSparseFFNFn(Function):
         dyp = recv_dy.tensor(0, (st.row_cap, st.Dout), torch.bfloat16)
         c_rows = g.row_ptrs(tags, plan, ret_dx.peers(), st.D, torch.bfloat16, dyp)
         lr = plan.local_route(T * K)
+        if ctx.fused:
+            # fused dgrad on the received (already weighted) upstream rows, d x rows pushed back to their source ranks,
+            # weight gradients straight from the receive buffers (identity row map)
+            fr = plan.fused_route(c_rows)
+            ones = torch.ones(st.row_cap, dtype=torch.float32, device=dyp.device)
+            dz, _hw, dxr, _ = ops.sigma_ffn_bwd(dyp, w1b, w2b, fr, ones, h, slots_per_row=1, dyp=dyp)
+            dw2 = ops.sigma_wgrad(h, dyp, El, fr, transpose=False, out_dtype=w2.dtype, slots_per_row=1)
+            dw1 = ops.sigma_wgrad(dz, xp, El, fr, transpose=True, out_dtype=w1.dtype, slots_per_row=1)
+            db1 = ops.bias_grad(dz, El, route=lr, out_dtype=w1.dtype) if ctx.has_b[0] else None
+            ops._call("csmoe_ep_push_rows", dxr.data_ptr(), ops.BF16, dxr.shape[1], dxr.shape[1], dxr.shape[0],
+                      c_rows.data_ptr(), ops._stream())
+            g.barrier()
+            dx = None
+            if ctx.needs_input_grad[0]:
+                dxs = ret_dx.tensor(0, (T * K, st.D), torch.bfloat16)
+                dx = ops.scatter_reduce(dxs, ident, T, K).to(ctx.x_dtype)
+            return dx, dw, None, dw1, db1, dw2, None, None, None
         db2 = ops.bias_grad(dyp, El, route=lr, out_dtype=w2.dtype) if ctx.has_b[1] else None
         if spec.kn_layout:
             dw2 = ops.gemm_reduce(h, dyp, El, route=lr, out_dtype=w2.dtype)

@@ -117,7 +117,7 @@ class MoeLayer(nn.Module):
     _inplace_params = ()     # parameters a forward call rescales in place (xmoe / smoe_perturbed: expert_embeddings)
 
     def _wrapped_graph_forward(self, x, return_id_experts=False, is_vision=False):
-        if not self._graph_eligible(x, return_id_experts):
+        if not self._graph_eligible(x, return_id_experts) or self._ep is not None:
             return self._eager_forward(x, return_id_experts, is_vision)
         self._stacked_weights()
         params = tuple(p for p in self.parameters() if p.requires_grad)
@@ -149,7 +149,7 @@ class MoeLayer(nn.Module):
         return res[0], res[1], None, dict(zip(names, res[2:]))
 
     def _graph_eligible(self, x, return_id_experts) -> bool:
-        return (self._graphs is not None and self._ep is None and self.training and x.is_cuda and x.requires_grad
+        return (self._graphs is not None and self.training and x.is_cuda and x.requires_grad
                 and torch.is_grad_enabled() and not return_id_experts
                 and not torch.cuda.is_current_stream_capturing())
 
@@ -367,7 +367,11 @@ class CompeteSMoE(MoeLayer):
 
     def forward(self, x, return_id_experts=False, is_vision=False):
         if self._graph_eligible(x, return_id_experts):
-            return self._graphed_call(x, self._is_competition_step(x))
+            branch = self._is_competition_step(x)
+            # under expert parallelism only the router step is captured (kernels + device-side barriers); the competition
+            # step gathers the expert weights with NCCL and stays eager
+            if self._ep is None or not branch:
+                return self._graphed_call(x, branch)
         return self._forward_impl(x, return_id_experts)
 
     def _forward_impl(self, x, return_id_experts=False):

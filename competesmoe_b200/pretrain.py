@@ -239,7 +239,8 @@ class MoE(LoggingLayer, RegularizedLayer, OncePerIterLayer, torch.nn.Module):
         forward + one backward graph per (step kind, shape, dtype, autocast state); torch.cuda.make_graphed_callables
         behind the unchanged `layer(x, id_layer=...)` call).  At the sigma-MoE shapes (H = 128) the ~80 launches of a step
         take longer to issue from Python than to run, so this is worth 1.5-4x there.  Regularisers still arrive through
-        `add_reg` under their usual names.  Eval / no-grad / expert-parallel / test_only calls take the normal path."""
+        `add_reg` under their usual names.  Eval / no-grad / test_only calls, and the competition step under expert
+        parallelism (NCCL weight gather), take the normal path."""
         if enabled and self._graphs is None:
             self._graphs = {}
             self._eager_forward = self.forward
@@ -258,7 +259,7 @@ class MoE(LoggingLayer, RegularizedLayer, OncePerIterLayer, torch.nn.Module):
         return state
 
     def _graph_forward(self, x, *args, **kwargs):
-        eligible = (self._graphable and self._ep is None and self.training and torch.is_tensor(x) and x.is_cuda
+        eligible = (self._graphable and self.training and torch.is_tensor(x) and x.is_cuda
                     and x.requires_grad and torch.is_grad_enabled() and not getattr(self.args, "test_only", False)
                     and not torch.cuda.is_current_stream_capturing() and not args
                     and set(kwargs) <= {"id_layer"})
@@ -269,6 +270,11 @@ class MoE(LoggingLayer, RegularizedLayer, OncePerIterLayer, torch.nn.Module):
         id_layer = kwargs.get("id_layer")
         probe = getattr(self, "_is_competition_step", None)
         branch = bool(probe(x, id_layer)) if probe is not None else False
+        # expert parallelism: the router step is kernels + device-side barriers over peer memory, which capture like any
+        # other launch (every rank replays the same sequence); the competition step gathers the expert weights with NCCL
+        # and stays eager
+        if self._ep is not None and branch:
+            return self._eager_forward(x, *args, **kwargs)
         params = tuple(p for p in self.parameters() if p.requires_grad)
         reg_on = self.reg_enabled
         key = (branch, id_layer, tuple(x.shape), x.dtype, autocast, adt, reg_on,

@@ -78,8 +78,8 @@ def build(case: Case, dev, ep):
         layer.step_warm = 0
         if ep is not None:
             layer.enable_expert_parallel(ep, max_tokens=case.T)
-        elif GRAPHS:
-            layer.enable_cuda_graphs()
+        if GRAPHS:
+            layer.enable_cuda_graphs()     # under expert parallelism the router step only (the layer decides)
 
         def set_branch(comp):
             layer.prob_flips_final = {0: torch.full((8,), bool(comp), device=dev)}
@@ -112,7 +112,7 @@ def build(case: Case, dev, ep):
         layer.train()
         if ep is not None:
             layer.enable_expert_parallel(ep, max_tokens=case.T)
-        elif GRAPHS and hasattr(layer, "enable_cuda_graphs"):
+        if GRAPHS and hasattr(layer, "enable_cuda_graphs"):
             layer.enable_cuda_graphs()
 
         def set_branch(comp):

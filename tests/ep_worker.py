@@ -155,6 +155,26 @@ def run_pretrain(group, dev, E, K, D, H, B, N, competition):
         want = all_reduce_(getattr(lr, n).grad.float().clone(), world)[lo:lo + El]
         close(getattr(le, n).grad, want, 3e-2, f"EP d {n}")
     close(le.w_gate.grad, lr.w_gate.grad, 3e-2, "EP d w_gate")
+    if not competition:
+        # the same expert-parallel call replayed from CUDA graphs (device-side barriers are captured like any launch):
+        # bit-identical to the eager expert-parallel step, on fresh inputs too
+        le.enable_cuda_graphs()
+        for rep in range(3):
+            gx = torch.Generator().manual_seed(300 + rank + rep)
+            xn = torch.randn(B, N, D, generator=gx).to(dev)
+            outs = []
+            for use_graph in (False, True):
+                le.forward = le._graph_forward if use_graph else le._eager_forward
+                for p in le.parameters():
+                    p.grad = None
+                x = xn.clone().requires_grad_(True)
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    out = le(x, id_layer=0)
+                regs = le.get_reg_loss()
+                ((out.float() * dy).sum() + sum(regs.values())).backward()
+                outs.append((out.detach().clone(), x.grad.clone(), le.keys.grad.clone()))
+            assert all(torch.equal(a, b) for a, b in zip(*outs)), "EP graph replay differs from the eager EP step"
+        le.forward = le._graph_forward
     if rank == 0:
         print(f"ep pretrain E={E} K={K} D={D} H={H} T={B * N} world={world} "
               f"{'competition' if competition else 'router'}: ok", flush=True)
