@@ -157,24 +157,26 @@ def run_pretrain(group, dev, E, K, D, H, B, N, competition):
     close(le.w_gate.grad, lr.w_gate.grad, 3e-2, "EP d w_gate")
     if not competition:
         # the same expert-parallel call replayed from CUDA graphs (device-side barriers are captured like any launch):
-        # bit-identical to the eager expert-parallel step, on fresh inputs too
-        le.enable_cuda_graphs()
+        # bit-identical to the eager expert-parallel step, on fresh inputs too.  A fresh layer: gradient accumulators
+        # created by earlier eager backward passes live on the default stream and would be waited on during capture.
+        epg = build()
+        epg.enable_expert_parallel(group, max_tokens=B * N)
+        epg.enable_cuda_graphs()
         for rep in range(3):
             gx = torch.Generator().manual_seed(300 + rank + rep)
             xn = torch.randn(B, N, D, generator=gx).to(dev)
             outs = []
-            for use_graph in (False, True):
-                le.forward = le._graph_forward if use_graph else le._eager_forward
-                for p in le.parameters():
+            for layer in (le, epg):
+                for p in layer.parameters():
                     p.grad = None
                 x = xn.clone().requires_grad_(True)
                 with torch.autocast("cuda", dtype=torch.bfloat16):
-                    out = le(x, id_layer=0)
-                regs = le.get_reg_loss()
+                    out = layer(x, id_layer=0)
+                regs = layer.get_reg_loss()
                 ((out.float() * dy).sum() + sum(regs.values())).backward()
-                outs.append((out.detach().clone(), x.grad.clone(), le.keys.grad.clone()))
+                outs.append((out.detach().clone(), x.grad.clone(), layer.keys.grad.clone(), layer.w_gate.grad.clone()))
             assert all(torch.equal(a, b) for a, b in zip(*outs)), "EP graph replay differs from the eager EP step"
-        le.forward = le._graph_forward
+        assert len(epg._graphs) == 1
     if rank == 0:
         print(f"ep pretrain E={E} K={K} D={D} H={H} T={B * N} world={world} "
               f"{'competition' if competition else 'router'}: ok", flush=True)
