@@ -18,6 +18,7 @@ GEMM_ROWS, GEMM_REDUCE = 0, 1
 ROW_TILE = 128
 
 vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
+f32c, u64 = C.c_float, C.c_uint64
 
 
 class GemmArgs(C.Structure):
@@ -82,6 +83,12 @@ _SIGNATURES = {
     "csmoe_entropy_balance_bwd": (i32, [vp, vp, i64, i64, i32, vp, vp]),
     "csmoe_topk_renorm_bwd": (i32, [vp, vp, vp, vp, i64, i32, i32, i32, i32, vp, vp]),
     "csmoe_dense_rows": (i32, [vp, i64, i32, i64, vp, vp]),
+    "csmoe_layernorm_fwd": (i32, [vp, i32, i64, i32, vp, vp, f32c, vp, i32, vp, vp, vp]),
+    "csmoe_layernorm_bwd_workspace_bytes": (i64, [i64, i32]),
+    "csmoe_layernorm_bwd": (i32, [vp, i32, vp, i32, vp, vp, vp, i64, i32, vp, vp, vp, vp, vp]),
+    "csmoe_combine_residual_fwd": (i32, [vp, i32, i64, i32, i32, vp, vp, vp, i32, vp, i32, f32c, u64, vp, vp]),
+    "csmoe_residual_dropout_fwd": (i32, [vp, i32, vp, i32, i64, i32, f32c, u64, vp, vp]),
+    "csmoe_dropout_bwd": (i32, [vp, i32, i64, f32c, u64, vp, i32, vp]),
     "csmoe_ep_ipc_handle_bytes": (i32, []),
     "csmoe_ep_alloc": (i32, [i64, C.POINTER(vp), vp]),
     "csmoe_ep_open": (i32, [vp, C.POINTER(vp)]),

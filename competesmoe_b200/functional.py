@@ -223,13 +223,20 @@ class SigmaFFNFn(Function):
     d routing weight, dx rows) plus two gathered weight-gradient GEMMs.  Saved for backward: x (bf16) and h only."""
 
     @staticmethod
-    def forward(ctx, x, w, sel, keys, bias, values, spec: FFNSpec):
+    def forward(ctx, x, w, sel, keys, bias, values, spec: FFNSpec, residual=None, drop_p: float = 0.0, drop_seed: int = 0):
+        """residual [T, Dout] given: returns residual + dropout(layer output) (the block tail of
+        relative_moe_transformer.py:157) from the combine kernel's epilogue, in the residual's dtype."""
         T, K = sel.shape
         E = keys.shape[0]
         xb, kb, vb = _bf16(x).contiguous(), _bf16(keys), _bf16(values)
         route = ops.route_build(sel, E, row_tile=ROW_TILE)
         y, h = ops.sigma_ffn_fwd(xb, kb, vb, bias, route)
-        out = ops.combine_fwd(y, route.slot_to_row, route.sel, w, T, K, round_each=spec.round_each, round_w=spec.round_w)
+        if residual is None:
+            out = ops.combine_fwd(y, route.slot_to_row, route.sel, w, T, K, round_each=spec.round_each, round_w=spec.round_w)
+        else:
+            out = ops.combine_residual_fwd(y, route.slot_to_row, route.sel, w, T, K, residual, drop_p, drop_seed,
+                                           round_each=spec.round_each, round_w=spec.round_w)
+        ctx.tail = None if residual is None else (drop_p, drop_seed)
         ctx.route, ctx.spec, ctx.x_dtype = route, spec, x.dtype
         ctx.save_for_backward(xb, h, w, keys, values, bias)
         ctx.wb = (kb if kb is not keys else None, vb if vb is not values else None)
@@ -247,6 +254,10 @@ class SigmaFFNFn(Function):
         T, K, E = route.n_slots // route.top_k, route.top_k, route.num_experts
         kb = ctx.wb[0] if ctx.wb[0] is not None else _bf16(keys)
         vb = ctx.wb[1] if ctx.wb[1] is not None else _bf16(values)
+        dres = None
+        if ctx.tail is not None:      # d(block output): identity into the residual, dropout mask regenerated for the layer
+            dres = dout
+            dout = ops.dropout_bwd(dout.reshape(-1, dout.shape[-1]), ctx.tail[0], ctx.tail[1], torch.bfloat16)
         dout = _bf16(dout.contiguous())
         wu = w.to(torch.bfloat16).float() if spec.round_w else w
         dz, hw, dxr, dw_part = ops.sigma_ffn_bwd(dout, kb, vb, route, wu, h)
@@ -255,7 +266,7 @@ class SigmaFFNFn(Function):
         dkeys = ops.sigma_wgrad(dz, xb, E, route, transpose=True, out_dtype=keys.dtype)          # [E, D, H]
         dbias = ops.bias_grad(dz, E, route=route, out_dtype=bias.dtype) if bias is not None else None
         dx = ops.scatter_reduce(dxr, route.slot_to_row, T, K).to(ctx.x_dtype) if ctx.needs_input_grad[0] else None
-        return dx, dw, None, dkeys, dbias, dvalues, None
+        return dx, dw, None, dkeys, dbias, dvalues, None, dres, None, None
 
 
 def sigma_fused_ok(x: torch.Tensor, keys: torch.Tensor, values: torch.Tensor, spec: FFNSpec, cdt: torch.dtype) -> bool:
@@ -493,3 +504,41 @@ class EntropyBalanceFn(Function):
     def backward(ctx, g):
         (colr,) = ctx.saved_tensors
         return ops.entropy_balance_bwd(colr, g, *ctx.dims), None
+
+
+# ------------------------------------------------------------------------------------------------ block tail
+class LayerNormCastFn(Function):
+    """y = LayerNorm(x) written in `out_dtype` (fp32 statistics): norm2 of the pre-LN block plus the autocast cast that
+    follows it, one pass (relative_moe_transformer.py:150-153)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps: float, out_dtype: torch.dtype):
+        x2 = x.reshape(-1, x.shape[-1])
+        y, mean, rstd = ops.layernorm_fwd(x2, gamma, beta, eps, out_dtype)
+        ctx.save_for_backward(x2, mean, rstd, gamma)
+        ctx.shape = x.shape
+        return y.view(*x.shape)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        x2, mean, rstd, gamma = ctx.saved_tensors
+        dx, dgamma, dbeta = ops.layernorm_bwd(dy.reshape(x2.shape), x2, mean, rstd, gamma)
+        return dx.view(ctx.shape), dgamma.to(gamma.dtype), dbeta.to(gamma.dtype), None, None
+
+
+class ResidualDropoutFn(Function):
+    """out = residual + dropout_p(v) in one pass (`src = src + self.dropout(src3)`, relative_moe_transformer.py:157); the
+    mask comes from a counter-based Philox stream and is regenerated in backward."""
+
+    @staticmethod
+    def forward(ctx, v, residual, p: float, seed: int):
+        out = ops.residual_dropout_fwd(v.reshape(-1, v.shape[-1]), residual, p, seed)
+        ctx.tail, ctx.v_dtype = (p, seed), v.dtype
+        return out.view(*residual.shape)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        dv = ops.dropout_bwd(g.reshape(-1, g.shape[-1]), ctx.tail[0], ctx.tail[1], ctx.v_dtype)
+        return dv.view(*g.shape), g, None, None

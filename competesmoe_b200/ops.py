@@ -736,3 +736,63 @@ def sigma_wgrad(a: torch.Tensor, g: torch.Tensor, num_experts: int, route: Route
     _call("csmoe_sigma_wgrad", _p(a), _p(g), T, N, num_experts, _p(route.row_to_slot), _p(route.pad_offsets), route.row_cap, k,
           1 if transpose else 0, _p(c), _dt(c), _stream())
     return c
+
+
+# ----------------------------------------------------------------------------------------------- block tail
+def layernorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, out_dtype: torch.dtype):
+    """x [T, D] (fp32 / bf16) -> (y [T, D] out_dtype, mean [T], rstd [T]); fp32 statistics."""
+    _cuda(x, gamma, beta)
+    x = x.contiguous()
+    T, D = x.shape
+    y = torch.empty(T, D, dtype=out_dtype, device=x.device)
+    mean = torch.empty(T, dtype=torch.float32, device=x.device)
+    rstd = torch.empty(T, dtype=torch.float32, device=x.device)
+    _call("csmoe_layernorm_fwd", _p(x), _dt(x), T, D, _p(gamma.float().contiguous()), _p(beta.float().contiguous()), float(eps),
+          _p(y), _dt(y), _p(mean), _p(rstd), _stream())
+    return y, mean, rstd
+
+
+def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, mean: torch.Tensor, rstd: torch.Tensor, gamma: torch.Tensor):
+    """-> (dx [T, D] x.dtype, dgamma [D] f32, dbeta [D] f32)."""
+    _cuda(dy, x, mean, rstd, gamma)
+    dy, x = dy.contiguous(), x.contiguous()
+    T, D = x.shape
+    dx = torch.empty_like(x)
+    dgamma = torch.empty(D, dtype=torch.float32, device=x.device)
+    dbeta = torch.empty(D, dtype=torch.float32, device=x.device)
+    ws = torch.empty(int(_lib.load().csmoe_layernorm_bwd_workspace_bytes(T, D)) // 4, dtype=torch.float32, device=x.device)
+    _call("csmoe_layernorm_bwd", _p(dy), _dt(dy), _p(x), _dt(x), _p(mean), _p(rstd), _p(gamma.float().contiguous()), T, D, _p(dx),
+          _p(dgamma), _p(dbeta), _p(ws), _stream(), kernels=2)
+    return dx, dgamma, dbeta
+
+
+def combine_residual_fwd(y, slot_to_row, sel, w, T: int, top_k: int, residual: torch.Tensor, p: float, seed: int,
+                         round_each: bool = False, round_w: bool = False) -> torch.Tensor:
+    """out [T, D] (residual's dtype) = residual + dropout_p(sum_k w[t,k] * y[row(t,k)])."""
+    _cuda(y, slot_to_row, sel, w, residual)
+    D = y.shape[-1]
+    residual = residual.reshape(T, D).contiguous()
+    out = torch.empty_like(residual)
+    w = w.reshape(-1).contiguous()
+    flags = (1 if round_each else 0) | (2 if round_w else 0)
+    _call("csmoe_combine_residual_fwd", _p(y), _dt(y), T, D, top_k, _p(slot_to_row), _p(sel), _p(w), flags, _p(residual),
+          _dt(residual), float(p), int(seed), _p(out), _stream())
+    return out
+
+
+def residual_dropout_fwd(v: torch.Tensor, residual: torch.Tensor, p: float, seed: int) -> torch.Tensor:
+    _cuda(v, residual)
+    v = v.contiguous()
+    T, D = v.shape
+    residual = residual.reshape(T, D).contiguous()
+    out = torch.empty_like(residual)
+    _call("csmoe_residual_dropout_fwd", _p(v), _dt(v), _p(residual), _dt(residual), T, D, float(p), int(seed), _p(out), _stream())
+    return out
+
+
+def dropout_bwd(g: torch.Tensor, p: float, seed: int, out_dtype: torch.dtype) -> torch.Tensor:
+    _cuda(g)
+    g = g.contiguous()
+    dv = torch.empty(g.shape, dtype=out_dtype, device=g.device)
+    _call("csmoe_dropout_bwd", _p(g), _dt(g), g.numel(), float(p), int(seed), _p(dv), _dt(dv), _stream())
+    return dv

@@ -229,6 +229,11 @@ class MoE(LoggingLayer, RegularizedLayer, OncePerIterLayer, torch.nn.Module):
         g = self._ep.group
         return gather_experts(self.keys, g), gather_experts(self.bias, g), gather_experts(self.values, g)
 
+    # ---- block tail (pretrain_block.FusedPreLNMoEBlock): (residual, dropout p, seed) for the combine epilogue
+    _tail = None
+    _tail_done = False
+    _x_dtype = None     # dtype of the block's LayerNorm output when the fused pre-LN already cast the input
+
     # ---- CUDA graphs (no counterpart in the reference, whose cvmm path re-tunes and syncs on the host)
     _graphs = None
     _graphable = True
@@ -396,6 +401,13 @@ class MoE(LoggingLayer, RegularizedLayer, OncePerIterLayer, torch.nn.Module):
         spec = self._spec(cdt)
         xc = self._cast(x2, cdt)
         fused = sigma_fused_ok(xc, self.keys, self.values, spec, cdt)      # expert size 128 + ReLU: csrc/sigma_ffn.cu
+        tail = self._tail
+        if tail is not None and fused and self.o_bias is None and not self._plot_training():
+            # called from pretrain_block.FusedPreLNMoEBlock: `src + dropout(layer output)` leaves the combine epilogue
+            residual, p, seed = tail
+            self._tail_done = True
+            return SigmaFFNFn.apply(xc, weights, selected, self.keys, self.bias, self.values, spec,
+                                    residual.reshape(-1, residual.shape[-1]), p, seed)
         if self._plot_training():
             spec = dataclasses.replace(spec, return_hidden=True)
             if fused:
@@ -539,7 +551,10 @@ class CompeteSMoE(MoE):
         x2 = x.reshape(-1, x.shape[-1])
         T, E, K = x2.shape[0], self.n_experts, self.num_selected
         is_comp = self._is_competition_step(x, id_layer)
-        gate_w, gate_idx, gate_softmax, gate_logits = self.router_policy(x2, cdt, x.dtype)
+        # dtype the reference layer would see: a fused pre-LN hands the input over already cast (pretrain_block.py), but
+        # the `.to(x.dtype)` roundings of the reference refer to the LayerNorm's output dtype
+        xdt = self._x_dtype or x.dtype
+        gate_w, gate_idx, gate_softmax, gate_logits = self.router_policy(x2, cdt, xdt)
         if is_comp:
             spec = self._spec(cdt)
             keys, bias, values = self._all_expert_weights()
@@ -547,9 +562,9 @@ class CompeteSMoE(MoE):
             # recomputes the selected experts with it (moe.py:400-401).  Without a bias the two coincide and the selected
             # outputs are reused from the dense pass; with one the sparse path runs on the competition's selection.
             y_all, score_sums = DenseFFNFn.apply(self._cast(x2, cdt), keys, None, values, None, spec,
-                                                 x.dtype == torch.bfloat16)          # [E * t_pad, Dv]
+                                                 xdt == torch.bfloat16)              # [E * t_pad, Dv]
             t_pad = y_all.shape[0] // E
-            aff, aff_w, aff_idx, out, diver = CompeteTailFn.apply(y_all, E, T, t_pad, K, False, x.dtype, spec, score_sums)
+            aff, aff_w, aff_idx, out, diver = CompeteTailFn.apply(y_all, E, T, t_pad, K, False, xdt, spec, score_sums)
             self.nb_diver += K * (K - 1) * T
             if self.bias is not None:
                 out = self.compute_moe_main(x2, aff_idx, aff_w, cdt)

@@ -328,6 +328,32 @@ int csmoe_topk_renorm_bwd(const float* scores, const float* w, const int32_t* id
 /* rows[t*K + k] = idx[t,k] * t_pad + t: where the selected experts' rows sit in the dense outputs y[E, t_pad, D]. */
 int csmoe_dense_rows(const int32_t* idx, int64_t T, int32_t K, int64_t t_pad, int32_t* rows, void* stream);
 
+/* ------------------------------------------------------------------------------------------------ block tail
+ * The steps either side of the layer in the reference's pre-LN transformer block
+ * (moe_pretrain_model/layers/transformer/relative_moe_transformer.py:150-159):
+ *     src2 = norm2(src);  src3 = pkm(src2, id_layer);  src = src + dropout(src3)
+ * csmoe_layernorm_fwd: y = LayerNorm(x) with fp32 statistics, written in y_dtype (fp32 -> bf16: the autocast cast that
+ *   follows the LayerNorm is folded in); mean / rstd [T] are saved for backward.
+ * csmoe_layernorm_bwd: dx (x's dtype), dgamma / dbeta [D] fp32 (two-stage, fixed order); workspace from the query.
+ * csmoe_combine_residual_fwd: csmoe_combine_fwd whose epilogue computes out = residual + dropout(combined rows), the
+ *   combined value rounded to the row dtype first (it is the layer's bf16 output in the reference), out in res_dtype.
+ * csmoe_residual_dropout_fwd: the same tail on a finished layer output v [T, D].
+ * csmoe_dropout_bwd: dv = keep ? g * 1/(1-p) : 0 -- the mask is regenerated from (seed, element index): Philox4x32-10,
+ *   counter = element index / 4.  p = 0 switches dropout off (seed ignored). */
+int csmoe_layernorm_fwd(const void* x, int32_t x_dtype, int64_t T, int32_t D, const float* gamma, const float* beta, float eps,
+                        void* y, int32_t y_dtype, float* mean, float* rstd, void* stream);
+int64_t csmoe_layernorm_bwd_workspace_bytes(int64_t T, int32_t D);
+int csmoe_layernorm_bwd(const void* dy, int32_t dy_dtype, const void* x, int32_t x_dtype, const float* mean, const float* rstd,
+                        const float* gamma, int64_t T, int32_t D, void* dx, float* dgamma, float* dbeta, void* workspace,
+                        void* stream);
+int csmoe_combine_residual_fwd(const void* y, int32_t dtype, int64_t T, int32_t D, int32_t K, const int32_t* slot_to_row,
+                               const int32_t* sel, const float* w, int32_t flags, const void* residual, int32_t res_dtype,
+                               float p, uint64_t seed, void* out, void* stream);
+int csmoe_residual_dropout_fwd(const void* v, int32_t v_dtype, const void* residual, int32_t res_dtype, int64_t T, int32_t D,
+                               float p, uint64_t seed, void* out, void* stream);
+int csmoe_dropout_bwd(const void* g, int32_t g_dtype, int64_t n, float p, uint64_t seed, void* dv, int32_t v_dtype,
+                      void* stream);
+
 /* ------------------------------------------------------------------------------------------------ expert parallelism
  * One process per GPU; rank r of P owns experts [r*E/P, (r+1)*E/P).  Exchange buffers are allocated by the library
  * (cudaMalloc, so that they can be exported with CUDA IPC) and mapped into every peer once; after that dispatch and
