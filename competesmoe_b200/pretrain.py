@@ -9,6 +9,7 @@ Same constructor keywords, `forward(x, *, id_layer)`, schedule hooks, regularise
 """
 from __future__ import annotations
 
+import collections
 import dataclasses
 import math
 from typing import Any, Callable, Dict, Optional
@@ -121,6 +122,9 @@ def _activation_code(fn: Callable) -> int:
     raise NotImplementedError("expert activation is not one of relu / gelu / gelu-tanh / silu / identity")
 
 
+Selection = collections.namedtuple("Selection", ["raw_sel", "sel_val", "raw_sel_index", "sel_index"])   # moe.py:33
+
+
 # ------------------------------------------------------------------------------------------------ base layer
 class MoE(LoggingLayer, RegularizedLayer, OncePerIterLayer, torch.nn.Module):
     """sigma-MoE layout MoE MLP (reference: layers/moe/moe.py:35-138,323-332,373-440)."""
@@ -137,9 +141,7 @@ class MoE(LoggingLayer, RegularizedLayer, OncePerIterLayer, torch.nn.Module):
         torch.nn.Module.__init__(self)
         LoggingLayer.__init__(self)
         RegularizedLayer.__init__(self)
-        if is_att:
-            raise NotImplementedError("the attention-projection variant (is_att) is outside the MoE-MLP hot path")
-        self.is_att = False
+        self.is_att = bool(is_att)
         self.iter = 0
         self.k_dim = self.k_vec_dim = dmodel
         self.v_dim = v_dim if v_dim is not None else dmodel
@@ -164,12 +166,24 @@ class MoE(LoggingLayer, RegularizedLayer, OncePerIterLayer, torch.nn.Module):
         self.name_moe = "mlp"
         self.args = args
         self.training = False
-        self.w_gate = torch.nn.Parameter(torch.empty(n_experts, dmodel))
-        torch.nn.init.normal_(self.w_gate, std=dmodel ** -0.5 * weight_scale)
-        self.register_parameter("values", torch.nn.Parameter(torch.empty(n_experts, expert_size, self.v_dim)))
-        self.register_parameter("keys", torch.nn.Parameter(torch.empty(n_experts, dmodel, expert_size)))
-        torch.nn.init.normal_(self.keys, std=dmodel ** -0.5 * weight_scale)
-        torch.nn.init.normal_(self.values, std=self.size ** -0.5 * weight_scale)
+        if self.is_att:
+            # expert projections of SwitchHead-style MoE attention (moe.py:111-117; created by
+            # full_moe_relative_attention.py:267-296 with n_experts = experts x heads): a gate over all (head, expert)
+            # pairs and one [inp_expert, out_expert] matrix per pair; top-k is the `topk` argument here (moe.py:105)
+            self.num_selected = topk
+            self.w_gate = torch.nn.Parameter(torch.randn(n_experts, dmodel) * std_gate)
+            self.renorm_rows(self.w_gate)
+            self.div = 10
+            self.real_n_experts = n_heads
+            self.register_parameter("experts", torch.nn.Parameter(torch.randn(n_experts, inp_expert, out_expert) * std_expert))
+            self.keys = self.values = None
+        else:
+            self.w_gate = torch.nn.Parameter(torch.empty(n_experts, dmodel))
+            torch.nn.init.normal_(self.w_gate, std=dmodel ** -0.5 * weight_scale)
+            self.register_parameter("values", torch.nn.Parameter(torch.empty(n_experts, expert_size, self.v_dim)))
+            self.register_parameter("keys", torch.nn.Parameter(torch.empty(n_experts, dmodel, expert_size)))
+            torch.nn.init.normal_(self.keys, std=dmodel ** -0.5 * weight_scale)
+            torch.nn.init.normal_(self.values, std=self.size ** -0.5 * weight_scale)
         if bias:
             self.bias = torch.nn.Parameter(torch.zeros(n_experts, expert_size))
             self.o_bias = torch.nn.Parameter(torch.zeros(self.v_dim))
@@ -182,6 +196,42 @@ class MoE(LoggingLayer, RegularizedLayer, OncePerIterLayer, torch.nn.Module):
         self.pre_train_forward()
 
     gate = property(lambda self: (lambda x: F.linear(x, self.w_gate, None)))
+
+    def renorm_rows(self, x: torch.Tensor):
+        """moe.py:140-144."""
+        with torch.no_grad():
+            std_t = x.std(dim=-1, keepdim=True)
+            x.div_(x.norm(dim=-1, keepdim=True))
+            x.mul_(std_t / x.std())
+
+    # ---- MoE-attention projections (is_att): layers/transformer/full_moe_relative_attention.py:351-389,453-458
+    def att_forward(self, x, n_experts, n_copies, return_full=True, *args, **kwargs):
+        """Per-head expert selection for one attention projection (moe.py:456-486, the sigmoid-gated SwitchHead form the
+        attention module calls at full_moe_relative_attention.py:374): gate logits [.., heads, experts], top-k per head,
+        sigmoid of the selected logits as weights, and the CVMM selection over the shifted (head, expert) indices."""
+        from .cvmm import cvmm_prepare_sel2
+        assert self.is_att, "att_forward needs a layer built with is_att=True"
+        if self.selection_dropout > 0 and self.training:
+            x = F.dropout(x, self.selection_dropout)
+        sel = F.linear(x, self.w_gate.to(x.dtype) if not torch.is_autocast_enabled() else self.w_gate, None)
+        sel = sel.view(*sel.shape[:-1], n_copies, -1)
+        with torch.no_grad():
+            if self.expert_dropout > 0 and self.training:
+                sel2 = sel.masked_fill(torch.rand_like(sel) < self.expert_dropout, float("-inf"))
+            else:
+                sel2 = sel
+            _, sel_index = sel2.topk(self.num_selected, dim=-1, sorted=False)
+        sel_val = torch.gather(sel, -1, sel_index).sigmoid()
+        if self.training is False:
+            self.add_dist_experts(selection=sel_index)
+        shift = (torch.arange(n_copies, device=sel_index.device, dtype=sel_index.dtype) * n_experts).unsqueeze(-1)
+        sel_pp = cvmm_prepare_sel2((shift + sel_index).flatten(-2, -1).int(), sel_val, n_experts=self.n_experts)
+        return Selection(sel, sel_val, sel_index, sel_pp)
+
+    def compute_moe(self, x: torch.Tensor, sel: "Selection") -> torch.Tensor:
+        """moe.py:488-489: the projection itself, one grouped GEMM over the (head, expert) pairs."""
+        from .cvmm import cvmm
+        return cvmm(x, sel.sel_index, self.experts)
 
     # ---- expert parallelism (no counterpart in the reference, which is data-parallel only; SURVEY.md 8e)
     _ep = None

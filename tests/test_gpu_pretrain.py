@@ -266,3 +266,39 @@ def test_cvmm_rejects_index_tensors_it_cannot_express():
         s.sel_index = torch.flip(s.sel_index, dims=[0])    # not `pos // K` any more
         with pytest.raises(NotImplementedError):
             cvmm(x, s, keys)
+
+
+def test_moe_attention_projection_layer_is_att():
+    """`get_moe(name)(..., is_att=True, inp_expert, out_expert)` -- the expert projections FullMoeRopeAttention builds
+    (full_moe_relative_attention.py:267-296) and drives through att_forward / compute_moe (:351-389, moe.py:456-489):
+    per-head top-k over sigmoid gates, one [in, out] matrix per (head, expert), weighted sum over the k selections."""
+    from competesmoe_b200.pretrain import CompeteSMoE
+    torch.manual_seed(0)
+    D, heads, E, k, dh, B, N = 128, 4, 5, 2, 32, 2, 96
+    layer = CompeteSMoE(D, E * heads, 1, n_heads=heads, topk=k, args=op.default_args(), is_att=True, inp_expert=D,
+                        out_expert=dh, std_gate=D ** -0.5, std_expert=D ** -0.5).to(DEV).train()
+    assert set(layer.state_dict()) == {"w_gate", "experts"} and layer.experts.shape == (E * heads, D, dh)
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(B, N, D, generator=g).to(DEV).requires_grad_(True)
+    dy = torch.randn(B, N, heads, dh, generator=g).to(DEV)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        sel = layer.att_forward(x, n_copies=heads, n_experts=E)
+        out = layer.compute_moe(x, sel)
+    assert out.shape == (B, N, heads, dh) and sel.raw_sel_index.shape == (B, N, heads, k)
+    (out.float() * dy).sum().backward()
+    # plain-torch restatement
+    xr = x.detach().clone().requires_grad_(True)
+    wg = layer.w_gate.detach().clone().requires_grad_(True)
+    ex = layer.experts.detach().clone().requires_grad_(True)
+    logits = F.linear(xr.bfloat16(), wg.bfloat16()).view(B, N, heads, E)
+    idx = sel.raw_sel_index
+    val = torch.gather(logits, -1, idx).sigmoid()
+    flat = (torch.arange(heads, device=DEV).view(1, 1, heads, 1) * E + idx)
+    w_sel = ex.bfloat16()[flat]                                              # [B, N, heads, k, D, dh]
+    proj = torch.einsum("bnd,bnhkde->bnhke", xr.bfloat16().float(), w_sel.float())
+    ref = (val.float().unsqueeze(-1) * proj.bfloat16().float()).sum(-2)
+    (ref * dy).sum().backward()
+    assert_close_rms(out, ref.detach(), 2e-2, "is_att projection")
+    assert_close_rms(x.grad, xr.grad, 3e-2, "dx")
+    assert_close_rms(layer.experts.grad, ex.grad, 3e-2, "d experts")
+    assert_close_rms(layer.w_gate.grad, wg.grad, 4e-2, "d w_gate")
