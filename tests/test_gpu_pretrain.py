@@ -294,8 +294,8 @@ def test_moe_attention_projection_layer_is_att():
     idx = sel.raw_sel_index
     val = torch.gather(logits, -1, idx).sigmoid()
     flat = (torch.arange(heads, device=DEV).view(1, 1, heads, 1) * E + idx)
-    w_sel = ex.bfloat16()[flat]                                              # [B, N, heads, k, D, dh]
-    proj = torch.einsum("bnd,bnhkde->bnhke", xr.bfloat16().float(), w_sel.float())
+    w_sel = ex.bfloat16().float()[flat]              # [B, N, heads, k, D, dh]; fp32 after the rounding: fp32 grad accumulation
+    proj = torch.einsum("bnd,bnhkde->bnhke", xr.bfloat16().float(), w_sel)
     ref = (val.float().unsqueeze(-1) * proj.bfloat16().float()).sum(-2)
     (ref * dy).sum().backward()
     assert_close_rms(out, ref.detach(), 2e-2, "is_att projection")
