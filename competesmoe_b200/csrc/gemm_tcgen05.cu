@@ -14,6 +14,12 @@
 #include "common.h"
 #include "ptx.cuh"
 
+// The quad-cluster variant (clusters of two CTA pairs with the A tile multicast; measured slower, profiles/r01n_quad_cluster.md)
+// is kept in the source for the record but compiled only with -DCSMOE_BUILD_QUAD=1: three fewer cubins in the default build.
+#ifndef CSMOE_BUILD_QUAD
+#define CSMOE_BUILD_QUAD 0
+#endif
+
 namespace csmoe {
 namespace {
 
@@ -1856,7 +1862,7 @@ extern "C" int csmoe_grouped_gemm(const csmoe_gemm_args* a, void* stream_) {
   }
 
   // clusters of two pairs (A multicast): plain pair launches only (no per-row destinations; the n-blocks come in twos)
-  const bool quad = pair && (quad_mask() & (a->mode == CSMOE_GEMM_ROWS ? 1 : 2)) != 0 && a->c_rows == nullptr;
+  const bool quad = CSMOE_BUILD_QUAD != 0 && pair && (quad_mask() & (a->mode == CSMOE_GEMM_ROWS ? 1 : 2)) != 0 && a->c_rows == nullptr;
 
   KParams kp{};
   kp.n = static_cast<int>(a->n);
@@ -2032,6 +2038,7 @@ extern "C" int csmoe_grouped_gemm(const csmoe_gemm_args* a, void* stream_) {
     const bool wide = n_grid >= 512 && (n_grid % 512 == 0 || n_grid >= 2048) && long_k && kp.tma_epi != 2 &&
                       (wm & (a->mode == CSMOE_GEMM_ROWS ? 1 : 2)) != 0;
     if (wide) kp.num_n_blocks = glu_fwd ? static_cast<int>((n_grid + 255) / 256) : static_cast<int>((a->n + 511) / 512);
+#if CSMOE_BUILD_QUAD
     if (quad && !wide) {
       // two pairs per cluster on neighbouring n-blocks: the cluster iterates over ceil(n-blocks / 2) groups
       const long long per_q = static_cast<long long>(kp.num_m_pairs) * ((kp.num_n_blocks + 1) / 2);
@@ -2062,6 +2069,7 @@ extern "C" int csmoe_grouped_gemm(const csmoe_gemm_args* a, void* stream_) {
       }
       return rcq;
     }
+#endif
     const long long per = static_cast<long long>(kp.num_m_pairs) * kp.num_n_blocks;
     kp.total_tiles = a->mode == CSMOE_GEMM_ROWS ? per : per * E;
     int clusters = num_sms() / 2;

@@ -394,7 +394,7 @@ def test_diversity_and_fused_competition_backward(ops, dtype, E, K, T, t_pad, D)
     {"CSMOE_GEMM_EPI": "staged", "CSMOE_GEMM_WIDE": "15"},   # staged epilogue everywhere, 256x512 tiles wherever legal
     {"CSMOE_GEMM_EPI": "direct", "CSMOE_GEMM_WIDE": "0"},    # register-direct epilogue, 256x256 CTA-pair tiles only
     {"CSMOE_GEMM_PAIR": "0"},                                 # single-CTA kernels only
-    {"CSMOE_GEMM_QUAD": "3", "CSMOE_GEMM_WIDE": "0"},        # clusters of two CTA pairs with the A operand multicast
+    {"CSMOE_GEMM_EPI": "tma", "CSMOE_GEMM_WIDE": "0"},       # TMA-store epilogue forced wherever legal, pair tiles only
 ])
 def test_gemm_kernel_variants_in_subprocess(env):
     """The kernel / epilogue variant is picked per launch by shape; the switches that force one variant are read once
