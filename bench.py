@@ -469,8 +469,12 @@ def ep_parity_section(device, world, rank, bench_layer, x, dy, params):
                 ew.run_multimodal(group, device, kind="mlp", E=4 if world <= 4 else 8, K=2, D=256, Fh=520, B=2, N=200, competition=comp)
                 ew.run_multimodal(group, device, kind="glu", E=8, K=2, D=512, Fh=1024, B=1, N=1000, competition=comp)
                 ew.run_pretrain(group, device, E=16, K=4, D=256, H=128, B=2, N=300, competition=comp)
+                ew.run_pretrain(group, device, E=16, K=4, D=256, H=128, B=2, N=300, competition=comp, exchange="weights")
+                ew.run_pretrain(group, device, E=16, K=2, D=256, H=128, B=1, N=500, competition=comp, exchange="weights", bias=True)
                 res["cases"] += [f"multimodal mlp {'comp' if comp else 'router'}", f"multimodal glu {'comp' if comp else 'router'}",
-                                 f"pretrain E=16 K=4 {'comp' if comp else 'router'}"]
+                                 f"pretrain E=16 K=4 {'comp' if comp else 'router'} (tokens exchanged)",
+                                 f"pretrain E=16 K=4 {'comp' if comp else 'router'} (weights exchanged)",
+                                 f"pretrain E=16 K=2 bias {'comp' if comp else 'router'} (weights exchanged)"]
             ew.run_multimodal(group, device, kind="mlp", E=8, K=1, D=128, Fh=256, B=1, N=3 + 5 * group.rank, competition=False,
                               max_tokens=3 + 5 * (group.world - 1))
             res["cases"].append("ragged top-1")
@@ -512,35 +516,49 @@ def c4_ep_section(device, world, rank, steps):
     """BASELINE.json configs[3] (d=1024, H=128, 64 experts, top-8, bf16 autocast): 8192 tokens per GPU (N = 8 gives the
     yaml's global batch of 64 x 1024), expert-parallel over all N ranks, next to the UNSHARDED layer running the same
     per-GPU batch on every GPU at the same time (the 1-GPU program under the same power conditions).
-    efficiency = local_ms / ep_ms = tokens/s(N) / (N * tokens/s(1))."""
+    efficiency = local_ms / ep_ms = tokens/s(N) / (N * tokens/s(1)).  Both exchange modes of the pretrain layer are
+    timed: "weights" (owners publish bf16 expert copies, gradients reduced onto the owners; what "auto" picks at this
+    shape) and "tokens" (every (token, expert) row travels to the expert's owner and back)."""
     import torch.distributed as dist
     sys.path.insert(0, str(ROOT / "scripts"))
     import config_sweep as cs
     from competesmoe_b200.ep import EPGroup
     case = cs.Case("C4 pretrain LM layer d=1024 E=64 K=8 H=128, 8192 tokens/GPU", "pretrain", 8192, 1024, 128, 64, 8, key="C4")
-    out = {"what": case.name, "tokens_per_gpu": case.T, "world": world}
+    out = {"what": case.name, "tokens_per_gpu": case.T, "world": world, "exchange_auto": None}
     try:
         local_eager = cs.time_case(case, device, None, steps, 3, True, graphs=False)
         local_graph = cs.time_case(case, device, None, steps, 3, True, graphs=True)
         group = EPGroup(None, device)
+        modes = {}
         try:
-            ep = cs.time_case(case, device, group, steps, 3, True, graphs=False)
-            try:
-                ep_graph = cs.time_case(case, device, group, steps, 3, True, graphs=True)   # router step replayed from graphs
-            except Exception as exc:
-                ep_graph = {False: float("nan"), True: float("nan")}
-                out["ep_graph_error"] = repr(exc)[:300]
+            for mode in ("weights", "tokens"):
+                ep = cs.time_case(case, device, group, steps, 3, True, graphs=False, exchange=mode)
+                try:
+                    ep_graph = cs.time_case(case, device, group, steps, 3, True, graphs=True, exchange=mode)
+                except Exception as exc:
+                    ep_graph = {False: float("nan"), True: float("nan")}
+                    out[f"ep_graph_error_{mode}"] = repr(exc)[:300]
+                modes[mode] = (ep, ep_graph)
         finally:
+            cs.EXCHANGE = "auto"
             group.close()
+        from competesmoe_b200.ep import WeightExchange
+        out["exchange_auto"] = "weights" if WeightExchange.prefer_weights(case.E, 2 * case.D * case.hidden, case.T, case.K,
+                                                                          case.D, case.D) else "tokens"
         for comp, nm in ((False, "router"), (True, "competition")):
             best_local = min(local_eager[comp], local_graph[comp])
-            best_ep = min(v for v in (ep[comp], ep_graph[comp]) if v == v)
-            out[nm] = {"ep_ms": round(best_ep, 4), "ep_eager_ms": round(ep[comp], 4),
-                       "ep_graphed_ms": None if ep_graph[comp] != ep_graph[comp] else round(ep_graph[comp], 4),
-                       "local_eager_ms": round(local_eager[comp], 4), "local_graphed_ms": round(local_graph[comp], 4),
-                       "tokens_per_s": round(case.T * world / (best_ep * 1e-3), 1),
-                       "efficiency_vs_local_best": round(best_local / best_ep, 4),
-                       "efficiency_vs_local_eager": round(local_eager[comp] / ep[comp], 4)}
+            row = {"local_eager_ms": round(local_eager[comp], 4), "local_graphed_ms": round(local_graph[comp], 4)}
+            for mode, (ep, ep_graph) in modes.items():
+                best_ep = min(v for v in (ep[comp], ep_graph[comp]) if v == v)
+                row[mode] = {"ep_ms": round(best_ep, 4), "ep_eager_ms": round(ep[comp], 4),
+                             "ep_graphed_ms": None if ep_graph[comp] != ep_graph[comp] else round(ep_graph[comp], 4),
+                             "tokens_per_s": round(case.T * world / (best_ep * 1e-3), 1),
+                             "efficiency_vs_local_best": round(best_local / best_ep, 4),
+                             "efficiency_vs_local_eager": round(local_eager[comp] / ep[comp], 4)}
+            auto = row[out["exchange_auto"]]
+            row.update({"ep_ms": auto["ep_ms"], "tokens_per_s": auto["tokens_per_s"],
+                        "efficiency_vs_local_best": auto["efficiency_vs_local_best"]})
+            out[nm] = row
     except Exception as exc:
         out["error"] = repr(exc)[:500]
     return out

@@ -99,6 +99,8 @@ _SIGNATURES = {
     "csmoe_ep_dispatch": (i32, [vp, i32, i32, i32, i64, vp, vp, vp, vp, i32, vp, vp, vp, i32, i32, vp]),
     "csmoe_ep_row_ptrs": (i32, [vp, vp, vp, vp, i32, i64, vp, i64, i32, i32, vp, vp, i32, vp]),
     "csmoe_ep_push_rows": (i32, [vp, i32, i64, i32, i64, vp, vp]),
+    "csmoe_ep_gather_push": (i32, [vp, i32, i64, vp, i32, i64, i32, i32, vp]),
+    "csmoe_ep_reduce_pull": (i32, [vp, i64, i64, vp, i32, i32, vp]),
 }
 
 _lock = threading.Lock()

@@ -45,7 +45,9 @@ def _digest(paths: list[Path]) -> str:
     for p in paths:
         h.update(p.name.encode())
         h.update(p.read_bytes())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    # the flags without the checkout's absolute path: the tree is copied to another directory on the GPU box, and a
+    # digest that changed there would rebuild the library on every run (and race between the ranks of one job)
+    h.update(" ".join(f.replace(str(ROOT), "<root>") for f in NVCC_FLAGS).encode())
     return h.hexdigest()
 
 
@@ -58,6 +60,16 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         return LIB
     OBJDIR.mkdir(exist_ok=True)
     LIBDIR.mkdir(exist_ok=True)
+    # one builder at a time (the ranks of a multi-GPU job import the package concurrently); whoever waited re-checks
+    import fcntl
+    with open(LIBDIR / ".build.lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and LIB.exists() and stamp.exists() and stamp.read_text() == digest:
+            return LIB
+        return _build_locked(srcs, deps, stamp, digest, force, verbose)
+
+
+def _build_locked(srcs, deps, stamp, digest, force, verbose) -> Path:
     nvcc = _nvcc()
 
     headers = [p for p in deps if p not in srcs]
@@ -81,10 +93,12 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
     with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
         objs = list(ex.map(compile_one, srcs))
-    cmd = [nvcc, "-shared", "-o", str(LIB), *map(str, objs), "-gencode", "arch=compute_100a,code=sm_100a"]
+    tmp = LIB.with_suffix(f".so.tmp{os.getpid()}")
+    cmd = [nvcc, "-shared", "-o", str(tmp), *map(str, objs), "-gencode", "arch=compute_100a,code=sm_100a"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    os.replace(tmp, LIB)     # a process that is loading the library never sees a half-written file
     stamp.write_text(digest)
     return LIB
 

@@ -17,6 +17,7 @@
 //
 // The reference has no counterpart (it is data-parallel only: moe_pretrain_model/framework/task/simple_task.py:403-413,
 // DeepSpeed ZeRO in moe_model/train/train.py:1474-1480).
+#include <algorithm>
 #include <cstring>
 
 #include "common.h"
@@ -218,6 +219,52 @@ ep_push_rows_kernel(const T* __restrict__ src, long long ld, int D, long long ro
   }
 }
 
+// ---- weight exchange (sigma-MoE shapes: the experts are small, the K-fold expanded token rows are not)
+// Every rank keeps its E / P experts' parameters and optimizer state; for compute, every rank holds a bf16 copy of ALL
+// experts in a symmetric buffer.  gather_push = cast + all-gather in one pass (each 16-byte vector of the local shard is
+// converted once and stored into every rank's copy, peers staggered by rank so that the P writers do not converge on
+// one destination); reduce_pull = reduce-scatter: the owner sums its slice of every rank's full-size gradient buffer
+// in ascending rank order (deterministic), all P loads of a vector in flight together.
+template <typename S, typename T>
+__global__ void __launch_bounds__(256)
+ep_gather_push_kernel(const S* __restrict__ src, long long n, Peers dst, long long dst_off, int rank, int P) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x * 8;
+  for (long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 8; i < n; i += stride) {
+    float v[8];
+    load8(src + i, v);
+    for (int q = 0; q < P; ++q) {
+      int p = rank + 1 + q;
+      if (p >= P) p -= P;
+      store8(reinterpret_cast<T*>(dst.p[p]) + dst_off + i, v);
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+ep_reduce_pull_kernel(Peers src, long long src_off, long long n, T* __restrict__ out, int P) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x * 4;
+  for (long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+    float4 v[kMaxRanks];
+#pragma unroll
+    for (int p = 0; p < kMaxRanks; ++p)
+      if (p < P) v[p] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src.p[p]) + src_off + i);
+    float4 a = v[0];
+#pragma unroll
+    for (int p = 1; p < kMaxRanks; ++p)
+      if (p < P) { a.x += v[p].x; a.y += v[p].y; a.z += v[p].z; a.w += v[p].w; }
+    if constexpr (sizeof(T) == 4) {
+      *reinterpret_cast<float4*>(out + i) = a;
+    } else {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(a.x, a.y), hi = __floats2bfloat162_rn(a.z, a.w);
+      uint2 u;
+      u.x = *reinterpret_cast<uint32_t*>(&lo);
+      u.y = *reinterpret_cast<uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(out + i) = u;
+    }
+  }
+}
+
 int fill_peers(Peers& out, const void* const* ptrs, int P, bool allow_null, const char* what) {
   for (int i = 0; i < kMaxRanks; ++i) out.p[i] = nullptr;
   if (ptrs == nullptr) {
@@ -376,6 +423,56 @@ extern "C" int csmoe_ep_push_rows(const void* src, int32_t dtype, int64_t ld, in
   EP_DISPATCH_DTYPE(dtype, (ep_push_rows_kernel<T><<<warp_grid(rows), 256, 0, stream>>>(
                                static_cast<const T*>(src), ld, D, rows,
                                reinterpret_cast<const unsigned long long*>(dst_rows))));
+  CSMOE_CHECK_LAUNCH();
+  return CSMOE_OK;
+}
+
+extern "C" int csmoe_ep_gather_push(const void* src, int32_t src_dtype, int64_t n, const void* const* dst, int32_t dst_dtype,
+                                    int64_t dst_offset, int32_t rank, int32_t P, void* stream_) {
+  CSMOE_CHECK_ARG(src != nullptr && n >= 0 && n % 8 == 0 && dst_offset >= 0 && dst_offset % 8 == 0,
+                  "csmoe_ep_gather_push: n and dst_offset must be multiples of 8");
+  CSMOE_CHECK_ARG(P >= 1 && P <= kMaxRanks && rank >= 0 && rank < P, "csmoe_ep_gather_push: bad rank / P");
+  if (n == 0) return CSMOE_OK;
+  Peers d;
+  int rc = fill_peers(d, dst, P, false, "csmoe_ep_gather_push");
+  if (rc != CSMOE_OK) return rc;
+  cudaStream_t stream = as_stream(stream_);
+  const long long vecs = n / 8;
+  const long long cap = static_cast<long long>(num_sms() > 0 ? num_sms() : 148) * 8;
+  const unsigned grid = static_cast<unsigned>(std::min<long long>((vecs + 255) / 256, cap));
+  if (src_dtype == CSMOE_F32 && dst_dtype == CSMOE_BF16) {
+    ep_gather_push_kernel<float, __nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<const float*>(src), n, d, dst_offset, rank, P);
+  } else if (src_dtype == CSMOE_BF16 && dst_dtype == CSMOE_BF16) {
+    ep_gather_push_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(src), n, d, dst_offset, rank, P);
+  } else if (src_dtype == CSMOE_F32 && dst_dtype == CSMOE_F32) {
+    ep_gather_push_kernel<float, float><<<grid, 256, 0, stream>>>(static_cast<const float*>(src), n, d, dst_offset, rank, P);
+  } else {
+    CSMOE_CHECK_ARG(false, "csmoe_ep_gather_push: unsupported dtype pair %d -> %d", src_dtype, dst_dtype);
+  }
+  CSMOE_CHECK_LAUNCH();
+  return CSMOE_OK;
+}
+
+extern "C" int csmoe_ep_reduce_pull(const void* const* src, int64_t src_offset, int64_t n, void* out, int32_t out_dtype,
+                                    int32_t P, void* stream_) {
+  CSMOE_CHECK_ARG(out != nullptr && n >= 0 && n % 4 == 0 && src_offset >= 0 && src_offset % 4 == 0,
+                  "csmoe_ep_reduce_pull: n and src_offset must be multiples of 4");
+  CSMOE_CHECK_ARG(P >= 1 && P <= kMaxRanks, "csmoe_ep_reduce_pull: bad P");
+  if (n == 0) return CSMOE_OK;
+  Peers s;
+  int rc = fill_peers(s, src, P, false, "csmoe_ep_reduce_pull");
+  if (rc != CSMOE_OK) return rc;
+  cudaStream_t stream = as_stream(stream_);
+  const long long vecs = n / 4;
+  const long long cap = static_cast<long long>(num_sms() > 0 ? num_sms() : 148) * 8;
+  const unsigned grid = static_cast<unsigned>(std::min<long long>((vecs + 255) / 256, cap));
+  if (out_dtype == CSMOE_F32) {
+    ep_reduce_pull_kernel<float><<<grid, 256, 0, stream>>>(s, src_offset, n, static_cast<float*>(out), P);
+  } else if (out_dtype == CSMOE_BF16) {
+    ep_reduce_pull_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(s, src_offset, n, static_cast<__nv_bfloat16*>(out), P);
+  } else {
+    CSMOE_CHECK_ARG(false, "csmoe_ep_reduce_pull: unsupported output dtype %d", out_dtype);
+  }
   CSMOE_CHECK_LAUNCH();
   return CSMOE_OK;
 }

@@ -16,7 +16,9 @@ only).
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import List, Optional
 
@@ -30,6 +32,8 @@ from ._lib import ROW_TILE, check
 from .functional import FFNSpec, _bf16, _ffn_first, _FUSE_ACT_BIAS, _FUSE_BWD, sigma_fused_ok
 
 MAX_EXPERTS = 1024
+# WeightExchange: run the gather under the router kernels and the gradient reduction under the dx reduction (side stream)
+_WX_OVERLAP = os.environ.get("CSMOE_WX_OVERLAP", "1") != "0"
 _CTRL_BYTES = 4096 + 16 * MAX_EXPERTS * 4   # flags, epoch, counts_all[P<=16][E<=1024]
 
 
@@ -255,6 +259,164 @@ class EPLayerState:
         # backward-only scratch is shared by every layer of the group (consumed inside one backward call)
         group.scratch("recv_dy", self.row_cap * d_out * 2)
         group.scratch("ret_dx", self.max_slots * d_in * 2)
+
+
+
+# ------------------------------------------------------------------------------------------------ weights move, tokens stay
+class WeightExchange:
+    """Expert parallelism for SMALL experts (the sigma-MoE shapes of the pretraining plugin): parameters, gradients and
+    optimizer state stay sharded (rank r owns experts [r*E/P, (r+1)*E/P)), but for compute every rank holds a full-size
+    operand copy of all experts and runs the ordinary single-GPU kernels on its own tokens.  Per layer step and rank
+    this moves (2 + 4) * |experts| * (P-1)/P bytes (bf16 operands out, fp32 gradients in) instead of the
+    4 * T*K*D*2 * (P-1)/P bytes of dispatching the K-fold expanded token rows and their gradients: at BASELINE
+    configs[3] (d=1024, H=128, E=64, K=8, 8192 tokens per GPU) 88 MB against 470 MB.  `prefer_weights()` is the rule.
+
+        forward    gather_push: cast + all-gather in one kernel, each rank stores its shard into every rank's copy
+                   -> barrier -> local fused expert kernels on the full copy
+        backward   weight-gradient GEMMs write full-size fp32 buffers -> barrier -> reduce_pull: the owner sums its
+                   slice of every rank's buffer in ascending rank order (deterministic)
+
+    Everything is kernels over IPC-mapped peer memory plus the device-side flag barrier (csrc/ep.cu), so both the router
+    and the competition step stay CUDA-graph capturable.  Hazards: the operand copy of a layer is rewritten by the next
+    forward of that layer -- a peer can only get there after the barrier of this layer's backward, i.e. after every
+    rank's last read; without a backward in between (evaluation, activation recomputation) the parameters have not
+    changed and the rewrite stores identical bytes.  The gradient buffers are per layer and rewritten one step later,
+    with that step's forward barrier in between.  No counterpart in the reference (data-parallel all-reduce of every
+    gradient, simple_task.py:403-413; ZeRO in moe_model/train/train.py:1474-1480)."""
+
+    def __init__(self, group: EPGroup, shards: dict):
+        """shards: role ('w1', 'b1', 'w2', 'b2') -> this rank's parameter shard [E/P, ...] (or None).  Collective."""
+        self.group = group
+        self._op = {}       # (role, dtype) -> (SymmetricBuffer, full shape)
+        self._grad = {}     # role -> (SymmetricBuffer, full shape)
+        self._have = {}     # role -> full operand tensor gathered in the current layer step
+        self.consumers = 0
+        self._prefetched = None
+        self._side = None
+        for role in ("w1", "b1", "w2", "b2"):
+            t = shards.get(role)
+            if t is None:
+                continue
+            assert t.numel() % 8 == 0, "weight exchange moves 8-element vectors: the shard size must be a multiple of 8"
+            full = (group.world * t.shape[0], *t.shape[1:])
+            n = group.world * t.numel()
+            odt = torch.bfloat16 if role in ("w1", "w2") else t.dtype
+            self._op[(role, odt)] = (group.alloc(n * (2 if odt == torch.bfloat16 else 4)), full)
+            self._grad[role] = (group.alloc(n * 4), full)
+
+    @staticmethod
+    def prefer_weights(num_experts: int, expert_params: int, max_tokens: int, top_k: int, d_in: int, d_out: int) -> bool:
+        """True when exchanging the expert weights moves fewer bytes per layer step than dispatching the token rows."""
+        weights = (2 + 4) * num_experts * expert_params
+        tokens = 2 * max_tokens * top_k * (d_in + d_out) * 2
+        return weights < tokens
+
+    def begin_step(self):
+        self._have = {}
+        self.consumers = 0
+        self._prefetched = None
+
+    def _operand_buffer(self, role: str, shard: torch.Tensor, dtype: torch.dtype):
+        key = (role, dtype)
+        if key not in self._op:       # fp32-accurate mode outside autocast: allocated on first use (collective)
+            full = (self.group.world * shard.shape[0], *shard.shape[1:])
+            self._op[key] = (self.group.alloc(self.group.world * shard.numel() * (2 if dtype == torch.bfloat16 else 4)), full)
+        return self._op[key]
+
+    def _side_stream(self) -> torch.cuda.Stream:
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.group.device)
+        return self._side
+
+    def _push(self, shards: dict, op_dtype: torch.dtype) -> bool:
+        g = self.group
+        pushed = False
+        for role, t in shards.items():
+            if t is None:
+                continue
+            dt = op_dtype if role in ("w1", "w2") else t.dtype
+            have = self._have.get(role)
+            if have is not None and have.dtype == dt:
+                continue
+            buf, full = self._operand_buffer(role, t, dt)
+            src = t.detach().contiguous()
+            ops._call("csmoe_ep_gather_push", src.data_ptr(), ops._dt(src), src.numel(), buf.peers(),
+                      _lib.BF16 if dt == torch.bfloat16 else _lib.F32, g.rank * src.numel(), g.rank, g.world, ops._stream())
+            self._have[role] = buf.tensor(0, full, dt)
+            pushed = True
+        return pushed
+
+    def prefetch(self, shards: dict, op_dtype: torch.dtype):
+        """Start a layer step: publish this rank's shards from a side stream, so that the transfer runs under the
+        router GEMM / top-k / routing-map kernels the layer issues next.  operands() joins and runs the barrier."""
+        self.begin_step()
+        if self.group.world == 1 or not _WX_OVERLAP:
+            return
+        main, side = torch.cuda.current_stream(self.group.device), self._side_stream()
+        side.wait_stream(main)            # the optimizer's update of the shards is ordered on the main stream
+        with torch.cuda.stream(side):
+            self._prefetched = self._push(shards, op_dtype)
+
+    def operands(self, shards: dict, op_dtype: torch.dtype) -> dict:
+        g = self.group
+        self.consumers += 1
+        pushed = False
+        if self._prefetched is not None:
+            torch.cuda.current_stream(g.device).wait_stream(self._side_stream())
+            pushed, self._prefetched = self._prefetched, None
+        pushed = self._push(shards, op_dtype) or pushed
+        if pushed:
+            g.barrier()
+        return {role: (None if t is None else self._have[role]) for role, t in shards.items()}
+
+    def grad_out(self, role: str, shape) -> torch.Tensor:
+        buf, full = self._grad[role]
+        assert tuple(shape) == tuple(full), f"gradient of {role}: {tuple(shape)} != {tuple(full)}"
+        return buf.tensor(0, full, torch.float32)
+
+    def reduce_begin(self, grads: dict):
+        """grads: role -> (full-size gradient or None, parameter shard or None for 'dtype of the gradient').  Gradients
+        that were not written into grad_out() already (bias gradients) are copied there.  Barrier, then the owner's
+        slices are summed on a side stream: what the caller issues before reduce_end() (the dx reduction) overlaps."""
+        g = self.group
+        todo = []
+        for role, (full, param) in grads.items():
+            if full is None:
+                todo.append(None)
+                continue
+            buf, shape = self._grad[role]
+            dst = buf.tensor(0, shape, torch.float32)
+            if full.data_ptr() != dst.data_ptr():
+                dst.copy_(full)
+            dt = param.dtype if param is not None else full.dtype
+            todo.append((buf, torch.empty((shape[0] // g.world, *shape[1:]), dtype=dt, device=g.device)))
+        g.barrier()
+        overlap = g.world > 1 and _WX_OVERLAP
+        main = torch.cuda.current_stream(g.device)
+        if overlap:
+            side = self._side_stream()
+            side.wait_stream(main)
+        with torch.cuda.stream(side) if overlap else contextlib.nullcontext():
+            for item in todo:
+                if item is None:
+                    continue
+                buf, local = item
+                n = local.numel()
+                ops._call("csmoe_ep_reduce_pull", buf.peers(), g.rank * n, n, local.data_ptr(), ops._dt(local), g.world, ops._stream())
+        return todo, overlap
+
+    def reduce_end(self, pending):
+        """-> the local gradient slices in role order (None where no gradient was given)."""
+        todo, overlap = pending
+        g = self.group
+        if overlap:
+            torch.cuda.current_stream(g.device).wait_stream(self._side_stream())
+        if self.consumers > 1:
+            g.barrier()     # another function of this layer step writes the same gradient buffers next
+        return [None if item is None else item[1] for item in todo]
+
+    def reduce(self, grads: dict):
+        return self.reduce_end(self.reduce_begin(grads))
 
 
 # ------------------------------------------------------------------------------------------------ weights for the dense step

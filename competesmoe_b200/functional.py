@@ -87,7 +87,25 @@ def _mm_reduce(a, b, num_experts, spec: "FFNSpec", **kw):
     if not spec.fp32:
         return ops.gemm_reduce(a, b, num_experts, **kw)
     out_dtype = kw.pop("out_dtype", torch.float32)
-    return ops.gemm_reduce_f32(a, b, num_experts, **kw).to(out_dtype)
+    out = kw.pop("out", None)
+    c = ops.gemm_reduce_f32(a, b, num_experts, **kw)
+    return c.to(out_dtype) if out is None else out.copy_(c)
+
+
+def _wx_operands(wx, spec: "FFNSpec", w1, b1, w2, b2=None):
+    """Expert parameters as GEMM operands.  wx = None: this rank holds every expert (cast when needed).  wx =
+    ep.WeightExchange: w1 / b1 / w2 are this rank's SHARDS; the exchange returns the full-size operand copies (cast +
+    all-gather over peer memory, once per layer step)."""
+    if wx is None:
+        return _op(w1, spec), b1, _op(w2, spec), b2
+    full = wx.operands({"w1": w1, "b1": b1, "w2": w2, "b2": b2}, torch.float32 if spec.fp32 else torch.bfloat16)
+    return full["w1"], full["b1"], full["w2"], full["b2"]
+
+
+def _wx_grad_out(wx, name: str, like: torch.Tensor):
+    """Where a weight-gradient GEMM writes: a fresh tensor, or (expert parallel, weights exchanged) the full-size fp32
+    gradient buffer the owners will reduce their slices from."""
+    return None if wx is None else wx.grad_out(name, like.shape)
 
 
 def _pad_rows(x: torch.Tensor, rows: int) -> torch.Tensor:
@@ -151,11 +169,11 @@ class SparseFFNFn(Function):
     """out[t] = sum_k w[t,k] * FFN_{sel[t,k]}(x[t])   with x [T,D] bf16, w [T,K] f32, sel [T,K] i32."""
 
     @staticmethod
-    def forward(ctx, x, w, sel, w1, b1, w2, b2, spec: FFNSpec):
+    def forward(ctx, x, w, sel, w1, b1, w2, b2, spec: FFNSpec, wx=None):
         T, K = sel.shape
-        E = w1.shape[0]
         xb = _op(x, spec)
-        w1b, w2b = _op(w1, spec), _op(w2, spec)
+        w1b, b1, w2b, b2 = _wx_operands(wx, spec, w1, b1, w2, b2)
+        E = w1b.shape[0]
         route = ops.route_build(sel, E)
         xp = ops.gather_rows(xb, route)
         z, h = _ffn_first(xp, w1b, b1, spec, route=route)
@@ -166,7 +184,9 @@ class SparseFFNFn(Function):
         ctx.has_b = (b1 is not None, b2 is not None)
         ctx.save_for_backward(xp, z, h, y, w, w1, w2)
         # fp32 master weights (pretrain under autocast): keep the bf16 copies of this step for the backward pass
-        ctx.wb = (w1b if (w1b is not w1 and not spec.fp32) else None, w2b if (w2b is not w2 and not spec.fp32) else None)
+        ctx.wb = (w1b if (w1b is not w1 and (wx is not None or not spec.fp32)) else None,
+                  w2b if (w2b is not w2 and (wx is not None or not spec.fp32)) else None)
+        ctx.wx = wx
         if spec.return_hidden:
             hd = h.detach()
             ctx.mark_non_differentiable(hd, route.row_to_slot)
@@ -177,7 +197,7 @@ class SparseFFNFn(Function):
     @once_differentiable
     def backward(ctx, dout, _dh=None, _dmap=None):
         xp, z, h, y, w, w1, w2 = ctx.saved_tensors
-        route, spec = ctx.route, ctx.spec
+        route, spec, wx = ctx.route, ctx.spec, ctx.wx
         T, K, E = route.n_slots // route.top_k, route.top_k, route.num_experts
         w1b = ctx.wb[0] if ctx.wb[0] is not None else _op(w1, spec)
         w2b = ctx.wb[1] if ctx.wb[1] is not None else _op(w2, spec)
@@ -188,9 +208,9 @@ class SparseFFNFn(Function):
         dyp = ops.gather_rows(dout, route, slot_w=wu)                          # w * dout in expert-major order
         db2 = ops.bias_grad(dyp, E, route=route, out_dtype=w2.dtype) if ctx.has_b[1] else None
         if spec.kn_layout:
-            dw2 = _mm_reduce(h, dyp, E, spec, route=route, out_dtype=w2.dtype)  # [E, H, Dout]
+            dw2 = _mm_reduce(h, dyp, E, spec, route=route, out_dtype=w2.dtype, out=_wx_grad_out(wx, "w2", w2b))  # [E, H, Dout]
         else:
-            dw2 = _mm_reduce(dyp, h, E, spec, route=route, out_dtype=w2.dtype)  # [E, Dout, F]
+            dw2 = _mm_reduce(dyp, h, E, spec, route=route, out_dtype=w2.dtype, out=_wx_grad_out(wx, "w2", w2b))  # [E, Dout, F]
         # dgrad of the second projection with the activation backward fused into its epilogue: dz = (dy W2) * act'(z)
         fused_db1 = False
         if _FUSE_BWD and not spec.fp32:
@@ -206,14 +226,16 @@ class SparseFFNFn(Function):
         if not fused_db1:
             db1 = ops.bias_grad(dz, E, route=route, out_dtype=w1.dtype) if ctx.has_b[0] else None
         if spec.kn_layout:
-            dw1 = _mm_reduce(xp, dz, E, spec, route=route, out_dtype=w1.dtype)  # [E, D, H]
+            dw1 = _mm_reduce(xp, dz, E, spec, route=route, out_dtype=w1.dtype, out=_wx_grad_out(wx, "w1", w1b))  # [E, D, H]
         else:
-            dw1 = _mm_reduce(dz, xp, E, spec, route=route, out_dtype=w1.dtype)  # [E, F, D]
+            dw1 = _mm_reduce(dz, xp, E, spec, route=route, out_dtype=w1.dtype, out=_wx_grad_out(wx, "w1", w1b))  # [E, F, D]
         dx = None
         if need[0]:
             dxp = _mm_rows(dz, w1b, spec, w_is_kn=not spec.kn_layout, route=route)
             dx = ops.scatter_reduce(dxp, route.slot_to_row, T, K).to(ctx.x_dtype)
-        return dx, dw, None, dw1, db1, dw2, db2, None
+        if wx is not None:     # every rank's full-size gradients are complete: the owners sum their slices
+            dw1, db1, dw2, db2 = wx.reduce({"w1": (dw1, w1), "b1": (db1, None), "w2": (dw2, w2), "b2": (db2, None)})
+        return dx, dw, None, dw1, db1, dw2, db2, None, None
 
 
 class SigmaFFNFn(Function):
@@ -223,14 +245,16 @@ class SigmaFFNFn(Function):
     d routing weight, dx rows) plus two gathered weight-gradient GEMMs.  Saved for backward: x (bf16) and h only."""
 
     @staticmethod
-    def forward(ctx, x, w, sel, keys, bias, values, spec: FFNSpec, residual=None, drop_p: float = 0.0, drop_seed: int = 0):
+    def forward(ctx, x, w, sel, keys, bias, values, spec: FFNSpec, residual=None, drop_p: float = 0.0, drop_seed: int = 0,
+                wx=None):
         """residual [T, Dout] given: returns residual + dropout(layer output) (the block tail of
         relative_moe_transformer.py:157) from the combine kernel's epilogue, in the residual's dtype."""
         T, K = sel.shape
-        E = keys.shape[0]
-        xb, kb, vb = _bf16(x).contiguous(), _bf16(keys), _bf16(values)
+        xb = _bf16(x).contiguous()
+        kb, bias_full, vb, _ = _wx_operands(wx, spec, keys, bias, values)
+        E = kb.shape[0]
         route = ops.route_build(sel, E, row_tile=ROW_TILE)
-        y, h = ops.sigma_ffn_fwd(xb, kb, vb, bias, route)
+        y, h = ops.sigma_ffn_fwd(xb, kb, vb, bias_full, route)
         if residual is None:
             out = ops.combine_fwd(y, route.slot_to_row, route.sel, w, T, K, round_each=spec.round_each, round_w=spec.round_w)
         else:
@@ -240,6 +264,7 @@ class SigmaFFNFn(Function):
         ctx.route, ctx.spec, ctx.x_dtype = route, spec, x.dtype
         ctx.save_for_backward(xb, h, w, keys, values, bias)
         ctx.wb = (kb if kb is not keys else None, vb if vb is not values else None)
+        ctx.wx = wx
         if spec.return_hidden:
             hd = h.detach()
             ctx.mark_non_differentiable(hd, route.row_to_slot)
@@ -250,7 +275,7 @@ class SigmaFFNFn(Function):
     @once_differentiable
     def backward(ctx, dout, _dh=None, _dmap=None):
         xb, h, w, keys, values, bias = ctx.saved_tensors
-        route, spec = ctx.route, ctx.spec
+        route, spec, wx = ctx.route, ctx.spec, ctx.wx
         T, K, E = route.n_slots // route.top_k, route.top_k, route.num_experts
         kb = ctx.wb[0] if ctx.wb[0] is not None else _bf16(keys)
         vb = ctx.wb[1] if ctx.wb[1] is not None else _bf16(values)
@@ -262,11 +287,17 @@ class SigmaFFNFn(Function):
         wu = w.to(torch.bfloat16).float() if spec.round_w else w
         dz, hw, dxr, dw_part = ops.sigma_ffn_bwd(dout, kb, vb, route, wu, h)
         dw = dw_part.sum(0).view(T, K) if ctx.needs_input_grad[1] else None
-        dvalues = ops.sigma_wgrad(hw, dout, E, route, transpose=False, out_dtype=values.dtype)   # [E, H, Dout]
-        dkeys = ops.sigma_wgrad(dz, xb, E, route, transpose=True, out_dtype=keys.dtype)          # [E, D, H]
+        dvalues = ops.sigma_wgrad(hw, dout, E, route, transpose=False, out_dtype=values.dtype,
+                                  out=_wx_grad_out(wx, "w2", vb))                                 # [E, H, Dout]
+        dkeys = ops.sigma_wgrad(dz, xb, E, route, transpose=True, out_dtype=keys.dtype,
+                                out=_wx_grad_out(wx, "w1", kb))                                   # [E, D, H]
         dbias = ops.bias_grad(dz, E, route=route, out_dtype=bias.dtype) if bias is not None else None
+        if wx is not None:      # the owners sum their slices of every rank's gradients while dx is reduced over k
+            pending = wx.reduce_begin({"w1": (dkeys, keys), "b1": (dbias, None), "w2": (dvalues, values), "b2": (None, None)})
         dx = ops.scatter_reduce(dxr, route.slot_to_row, T, K).to(ctx.x_dtype) if ctx.needs_input_grad[0] else None
-        return dx, dw, None, dkeys, dbias, dvalues, None, dres, None, None
+        if wx is not None:
+            dkeys, dbias, dvalues, _ = wx.reduce_end(pending)
+        return dx, dw, None, dkeys, dbias, dvalues, None, dres, None, None, None
 
 
 def sigma_fused_ok(x: torch.Tensor, keys: torch.Tensor, values: torch.Tensor, spec: FFNSpec, cdt: torch.dtype) -> bool:
@@ -286,11 +317,11 @@ class DenseFFNFn(Function):
     differentiates the score through y."""
 
     @staticmethod
-    def forward(ctx, x, w1, b1, w2, b2, spec: FFNSpec, score_round: Optional[bool] = None):
+    def forward(ctx, x, w1, b1, w2, b2, spec: FFNSpec, score_round: Optional[bool] = None, wx=None):
         T = x.shape[0]
         t_pad = (T + 2 * ROW_TILE - 1) // (2 * ROW_TILE) * (2 * ROW_TILE)   # 256: CTA-pair GEMM tiles
         xb = _pad_rows(_op(x, spec), t_pad)
-        w1b, w2b = _op(w1, spec), _op(w2, spec)
+        w1b, b1, w2b, b2 = _wx_operands(wx, spec, w1, b1, w2, b2)
         z, h = _ffn_first(xb, w1b, b1, spec, dense_rows=t_pad, a_expert_rows=0)
         fuse_score = score_round is not None and not spec.fp32 and \
             (_SCORE_EPILOGUE == "1" or (_SCORE_EPILOGUE == "auto" and h.shape[1] >= 1024))
@@ -299,6 +330,7 @@ class DenseFFNFn(Function):
         ctx.spec, ctx.T, ctx.t_pad, ctx.x_dtype = spec, T, t_pad, x.dtype
         ctx.has_b = (b1 is not None, b2 is not None)
         ctx.save_for_backward(xb, z, h, w1, w2)
+        ctx.wx, ctx.wb = wx, ((w1b, w2b) if wx is not None else None)
         if score_round is None:
             return y
         if not fuse_score:
@@ -311,15 +343,16 @@ class DenseFFNFn(Function):
     @once_differentiable
     def backward(ctx, dy, _drowsum=None):
         xb, z, h, w1, w2 = ctx.saved_tensors
-        spec, T, t_pad = ctx.spec, ctx.T, ctx.t_pad
-        E = w1.shape[0]
-        w1b, w2b = _op(w1, spec), _op(w2, spec)
+        spec, T, t_pad, wx = ctx.spec, ctx.T, ctx.t_pad, ctx.wx
+        w1b, w2b = ctx.wb if wx is not None else (_op(w1, spec), _op(w2, spec))
+        E = w1b.shape[0]
         dy = _op(dy.contiguous(), spec)
         db2 = ops.bias_grad(dy, E, dense_rows=t_pad, out_dtype=w2.dtype) if ctx.has_b[1] else None
+        o2 = _wx_grad_out(wx, "w2", w2b)
         if spec.kn_layout:
-            dw2 = _mm_reduce(h, dy, E, spec, dense_rows=t_pad, a_expert_rows=t_pad, b_expert_rows=t_pad, out_dtype=w2.dtype)
+            dw2 = _mm_reduce(h, dy, E, spec, dense_rows=t_pad, a_expert_rows=t_pad, b_expert_rows=t_pad, out_dtype=w2.dtype, out=o2)
         else:
-            dw2 = _mm_reduce(dy, h, E, spec, dense_rows=t_pad, a_expert_rows=t_pad, b_expert_rows=t_pad, out_dtype=w2.dtype)
+            dw2 = _mm_reduce(dy, h, E, spec, dense_rows=t_pad, a_expert_rows=t_pad, b_expert_rows=t_pad, out_dtype=w2.dtype, out=o2)
         fused_db1 = False
         if _FUSE_BWD and not spec.fp32:
             dz = ops.gemm_rows(dy, w2b, w_is_kn=not spec.kn_layout, dense_rows=t_pad, a_expert_rows=t_pad,
@@ -333,10 +366,11 @@ class DenseFFNFn(Function):
                 dz = dh if spec.act == ops.ACT_NONE else ops.act_bwd(z, dh, spec.act)
         if not fused_db1:
             db1 = ops.bias_grad(dz, E, dense_rows=t_pad, out_dtype=w1.dtype) if ctx.has_b[0] else None
+        o1 = _wx_grad_out(wx, "w1", w1b)
         if spec.kn_layout:
-            dw1 = _mm_reduce(xb, dz, E, spec, dense_rows=t_pad, a_expert_rows=0, b_expert_rows=t_pad, out_dtype=w1.dtype)
+            dw1 = _mm_reduce(xb, dz, E, spec, dense_rows=t_pad, a_expert_rows=0, b_expert_rows=t_pad, out_dtype=w1.dtype, out=o1)
         else:
-            dw1 = _mm_reduce(dz, xb, E, spec, dense_rows=t_pad, a_expert_rows=t_pad, b_expert_rows=0, out_dtype=w1.dtype)
+            dw1 = _mm_reduce(dz, xb, E, spec, dense_rows=t_pad, a_expert_rows=t_pad, b_expert_rows=0, out_dtype=w1.dtype, out=o1)
         dx = None
         if ctx.needs_input_grad[0]:
             # dx[t] = sum_e dz[e, t] . W1[e]: one GEMM whose k loop runs over (expert, hidden) -- no [E, T, D] intermediate
@@ -346,7 +380,9 @@ class DenseFFNFn(Function):
             else:
                 dxe = _mm_rows(dz, w1b, spec, w_is_kn=not spec.kn_layout, dense_rows=t_pad, a_expert_rows=t_pad)
                 dx = dxe.view(E, t_pad, -1)[:, :T].float().sum(0).to(ctx.x_dtype)
-        return dx, dw1, db1, dw2, db2, None, None
+        if wx is not None:
+            dw1, db1, dw2, db2 = wx.reduce({"w1": (dw1, w1), "b1": (db1, None), "w2": (dw2, w2), "b2": (db2, None)})
+        return dx, dw1, db1, dw2, db2, None, None, None
 
 
 class AffinityFn(Function):

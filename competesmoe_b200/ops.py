@@ -377,8 +377,10 @@ def gemm_rows(a: torch.Tensor, w: torch.Tensor, *, w_is_kn: bool, route: Optiona
 
 def gemm_reduce(a: torch.Tensor, b: torch.Tensor, num_experts: int, *, route: Optional[Route] = None,
                 dense_rows: int = 0, a_expert_rows: int = 0, b_expert_rows: int = 0,
-                out_dtype: torch.dtype = torch.float32, accumulate_into: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """C[e] = A[rows of e]^T . B[rows of e]  -> [E, a.shape[1], b.shape[1]] (wgrad)."""
+                out_dtype: torch.dtype = torch.float32, accumulate_into: Optional[torch.Tensor] = None,
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """C[e] = A[rows of e]^T . B[rows of e]  -> [E, a.shape[1], b.shape[1]] (wgrad).  `out`: write into this contiguous
+    [E, m, n] tensor (e.g. a symmetric gradient buffer of ep.WeightExchange) instead of allocating."""
     _cuda(a, b)
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
     assert a.dim() == 2 and b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1
@@ -400,6 +402,9 @@ def gemm_reduce(a: torch.Tensor, b: torch.Tensor, num_experts: int, *, route: Op
         c = accumulate_into
         assert c.dtype == torch.float32 and c.shape == (num_experts, m, n) and c.is_contiguous()
         g.accumulate = 1
+    elif out is not None:
+        c = out
+        assert c.shape == (num_experts, m, n) and c.is_contiguous() and c.dtype in (torch.float32, torch.bfloat16)
     else:
         c = torch.empty(num_experts, m, n, dtype=out_dtype, device=a.device)
     g.c, g.ldc, g.c_expert_stride, g.c_dtype = _p(c), n, m * n, _dt(c)
@@ -724,15 +729,21 @@ def sigma_ffn_bwd(dout: torch.Tensor, keys: torch.Tensor, values: torch.Tensor, 
 
 
 def sigma_wgrad(a: torch.Tensor, g: torch.Tensor, num_experts: int, route: Route, transpose: bool,
-                out_dtype: torch.dtype = torch.float32, slots_per_row: Optional[int] = None) -> torch.Tensor:
+                out_dtype: torch.dtype = torch.float32, slots_per_row: Optional[int] = None,
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """c[e] = a[rows of e]^T . gather(g)[rows of e]; a [row_cap, 128], g [T, N] token-major.
-    transpose=False -> [E, 128, N]; True -> [E, N, 128]."""
+    transpose=False -> [E, 128, N]; True -> [E, N, 128].  `out`: write into this contiguous tensor of that shape."""
     _cuda(a, g)
     assert a.dtype == g.dtype == torch.bfloat16 and a.is_contiguous() and g.is_contiguous() and a.shape[0] == route.row_cap
     T, N = g.shape
     H = a.shape[1]
     k = route.top_k if slots_per_row is None else slots_per_row
-    c = torch.empty((num_experts, N, H) if transpose else (num_experts, H, N), dtype=out_dtype, device=a.device)
+    shape = (num_experts, N, H) if transpose else (num_experts, H, N)
+    if out is not None:
+        assert tuple(out.shape) == shape and out.is_contiguous()
+        c = out
+    else:
+        c = torch.empty(shape, dtype=out_dtype, device=a.device)
     _call("csmoe_sigma_wgrad", _p(a), _p(g), T, N, num_experts, _p(route.row_to_slot), _p(route.pad_offsets), route.row_cap, k,
           1 if transpose else 0, _p(c), _dt(c), _stream())
     return c

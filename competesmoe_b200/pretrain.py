@@ -236,17 +236,37 @@ class MoE(LoggingLayer, RegularizedLayer, OncePerIterLayer, torch.nn.Module):
     # ---- expert parallelism (no counterpart in the reference, which is data-parallel only)
     _ep = None
 
-    def enable_expert_parallel(self, group, max_tokens: int, row_tile: int = 128):
+    def enable_expert_parallel(self, group, max_tokens: int, row_tile: int = 128, exchange: str = "auto"):
         """Shard keys / values (/ bias) over `group` (competesmoe_b200.ep.EPGroup): this rank keeps the slices
         [rank*E/P, (rank+1)*E/P) along dim 0; w_gate (and o_bias) stay replicated.  `max_tokens` = the largest number of
         tokens this rank passes to forward.  Call after loading a full checkpoint and BEFORE the optimizer is built: the
         sharded tensors are new Parameters, an optimizer created earlier would keep updating the old full-size ones.
         Afterwards `state_dict()` holds this rank's shard only; use `full_state_dict()` / `load_full_state_dict()` for
-        checkpoints in the reference layout."""
-        from .ep import EPLayerState
+        checkpoints in the reference layout.
+
+        `exchange`: what crosses NVLink in a layer step.  "tokens": every (token, expert) row travels to the expert's
+        owner and back (ep.EPSparseFFNFn).  "weights": the owners publish bf16 copies of their experts, every rank
+        computes on its own tokens and the weight gradients are reduced onto the owners (ep.WeightExchange) -- fewer
+        bytes whenever the experts are small next to the K-fold expanded batch, which is the case for every sigma-MoE
+        configuration of the reference's sweeps.  "auto" compares the two byte counts."""
+        from .ep import EPLayerState, WeightExchange
+        if exchange not in ("auto", "tokens", "weights"):
+            raise ValueError(f"exchange must be 'auto', 'tokens' or 'weights', got {exchange!r}")
+        if exchange == "auto":
+            per_expert = self.k_vec_dim * self.expert_size + self.expert_size * self.v_dim
+            exchange = "weights" if WeightExchange.prefer_weights(self.n_experts, per_expert, max_tokens, self.num_selected,
+                                                                  self.k_vec_dim, self.v_dim) else "tokens"
         self._shard_experts(group.rank, group.world)
-        self._ep = EPLayerState(group, self.n_experts, self.num_selected, self.k_vec_dim, self.v_dim, max_tokens, row_tile)
+        if exchange == "weights":
+            self._ep = _WeightsEP(group, WeightExchange(group, {"w1": self.keys, "b1": self.bias, "w2": self.values}))
+        else:
+            self._ep = EPLayerState(group, self.n_experts, self.num_selected, self.k_vec_dim, self.v_dim, max_tokens, row_tile)
         return self
+
+    @property
+    def _wx(self):
+        """The layer's ep.WeightExchange when its experts are sharded with exchange="weights", else None."""
+        return getattr(self._ep, "wx", None)
 
     def _shard_experts(self, rank: int, world: int):
         E = self.n_experts
@@ -273,7 +293,7 @@ class MoE(LoggingLayer, RegularizedLayer, OncePerIterLayer, torch.nn.Module):
         return load_full_state_dict(self, state_dict, group, strict)
 
     def _all_expert_weights(self):
-        if self._ep is None or self._ep.group.world == 1:
+        if self._ep is None or self._ep.group.world == 1 or self._wx is not None:
             return self.keys, self.bias, self.values
         from .ep import gather_experts
         g = self._ep.group
@@ -328,7 +348,7 @@ class MoE(LoggingLayer, RegularizedLayer, OncePerIterLayer, torch.nn.Module):
         # expert parallelism: the router step is kernels + device-side barriers over peer memory, which capture like any
         # other launch (every rank replays the same sequence); the competition step gathers the expert weights with NCCL
         # and stays eager
-        if self._ep is not None and branch:
+        if self._ep is not None and branch and self._wx is None:
             return self._eager_forward(x, *args, **kwargs)
         params = tuple(p for p in self.parameters() if p.requires_grad)
         reg_on = self.reg_enabled
@@ -443,8 +463,23 @@ class MoE(LoggingLayer, RegularizedLayer, OncePerIterLayer, torch.nn.Module):
             routed = (row_to_slot >= 0).unsqueeze(1)
             self.log("relu_pass_rate", ((h > 0) & routed).sum().float() / float(n_slots * h.shape[1]))
 
-    def compute_moe_main(self, x2, selected, weights, cdt):
-        if self._ep is not None:
+    def _wx_prefetch(self, cdt: torch.dtype):
+        """Expert parallelism with exchanged weights: publish this rank's expert shards now, from a side stream, so
+        that the transfer runs under the router kernels of this forward call (ep.WeightExchange.prefetch)."""
+        wx = self._wx
+        if wx is not None:
+            wx.prefetch({"w1": self.keys, "b1": self.bias, "w2": self.values},
+                        torch.bfloat16 if cdt == torch.bfloat16 else torch.float32)
+            self._wx_open = True
+
+    _wx_open = False
+
+    def compute_moe_main(self, x2, selected, weights, cdt, same_step: bool = False):
+        wx = self._wx
+        if wx is not None and not same_step and not self._wx_open:   # callers that did not prefetch (sibling routers)
+            wx.begin_step()
+        self._wx_open = False
+        if self._ep is not None and wx is None:
             from .ep import EPSparseFFNFn
             return EPSparseFFNFn.apply(self._cast(x2, cdt), weights, selected, self.keys, self.bias, self.values, None,
                                        self._spec(cdt), self._ep)
@@ -457,23 +492,25 @@ class MoE(LoggingLayer, RegularizedLayer, OncePerIterLayer, torch.nn.Module):
             residual, p, seed = tail
             self._tail_done = True
             return SigmaFFNFn.apply(xc, weights, selected, self.keys, self.bias, self.values, spec,
-                                    residual.reshape(-1, residual.shape[-1]), p, seed)
+                                    residual.reshape(-1, residual.shape[-1]), p, seed, wx)
         if self._plot_training():
             spec = dataclasses.replace(spec, return_hidden=True)
             if fused:
-                out, h, row_to_slot = SigmaFFNFn.apply(xc, weights, selected, self.keys, self.bias, self.values, spec)
+                out, h, row_to_slot = SigmaFFNFn.apply(xc, weights, selected, self.keys, self.bias, self.values, spec,
+                                                       None, 0.0, 0, wx)
             else:
-                out, h, row_to_slot = SparseFFNFn.apply(xc, weights, selected, self.keys, self.bias, self.values, None, spec)
+                out, h, row_to_slot = SparseFFNFn.apply(xc, weights, selected, self.keys, self.bias, self.values, None, spec, wx)
             self._log_relu_pass_rate(h, row_to_slot, selected.numel())
             return out
         if fused:
-            return SigmaFFNFn.apply(xc, weights, selected, self.keys, self.bias, self.values, spec)
-        return SparseFFNFn.apply(xc, weights, selected, self.keys, self.bias, self.values, None, spec)
+            return SigmaFFNFn.apply(xc, weights, selected, self.keys, self.bias, self.values, spec, None, 0.0, 0, wx)
+        return SparseFFNFn.apply(xc, weights, selected, self.keys, self.bias, self.values, None, spec, wx)
 
     def forward(self, x, return_id_experts=False, return_full=True, *args, **kwargs):
         """Plain sigma-MoE forward (moe.py:418-449)."""
         B = x.shape[:-1]
         cdt = self._compute_dtype(x)
+        self._wx_prefetch(cdt)
         x2 = x.reshape(-1, x.shape[-1])
         logits, probs, _, gidx = self.compute_gate(x2, cdt)
         gw = torch.gather(probs, 1, gidx.long())     # moe.py:373-393 topk_expert: the raw top-k probabilities, no renormalisation
@@ -488,6 +525,13 @@ class MoE(LoggingLayer, RegularizedLayer, OncePerIterLayer, torch.nn.Module):
         lg = logits.view(*B, -1)
         self.add_reg(lambda: self.entropy_balance(lg) * (self.args.balance_loss_coef / self.div), f"{self.name_moe}_ebalance")
         return res
+
+
+class _WeightsEP:
+    """`layer._ep` of a layer whose experts are sharded with exchange="weights": the group and the exchange, no token buffers."""
+
+    def __init__(self, group, wx):
+        self.group, self.wx = group, wx
 
 
 # ------------------------------------------------------------------------------------------------ CompeteSMoE
@@ -598,6 +642,7 @@ class CompeteSMoE(MoE):
         a = self.args
         lead = x.shape[:-1]
         cdt = self._compute_dtype(x)
+        self._wx_prefetch(cdt)
         x2 = x.reshape(-1, x.shape[-1])
         T, E, K = x2.shape[0], self.n_experts, self.num_selected
         is_comp = self._is_competition_step(x, id_layer)
@@ -607,17 +652,18 @@ class CompeteSMoE(MoE):
         gate_w, gate_idx, gate_softmax, gate_logits = self.router_policy(x2, cdt, xdt)
         if is_comp:
             spec = self._spec(cdt)
+            self._wx_open = False
             keys, bias, values = self._all_expert_weights()
             # competition_policy_mlp_faster (:381-414) scores every expert WITHOUT the hidden bias; compute_moe_main then
             # recomputes the selected experts with it (moe.py:400-401).  Without a bias the two coincide and the selected
             # outputs are reused from the dense pass; with one the sparse path runs on the competition's selection.
             y_all, score_sums = DenseFFNFn.apply(self._cast(x2, cdt), keys, None, values, None, spec,
-                                                 xdt == torch.bfloat16)              # [E * t_pad, Dv]
+                                                 xdt == torch.bfloat16, self._wx)    # [E * t_pad, Dv]
             t_pad = y_all.shape[0] // E
             aff, aff_w, aff_idx, out, diver = CompeteTailFn.apply(y_all, E, T, t_pad, K, False, xdt, spec, score_sums)
             self.nb_diver += K * (K - 1) * T
             if self.bias is not None:
-                out = self.compute_moe_main(x2, aff_idx, aff_w, cdt)
+                out = self.compute_moe_main(x2, aff_idx, aff_w, cdt, same_step=True)
             # softmax(affinity), every router-loss variant and the entropy balance on the affinity from one kernel pair
             # (competesmoe.py:541-593): losses = (MSE, MSE at the competition's top-k, MSE at the router's top-k, -, ebalance)
             _, cl = CompeteLossesFn.apply(gate_softmax, aff, aff_idx, gate_idx if a.tribrid and not (a.in_topk or a.hybrid) else None,

@@ -398,6 +398,19 @@ int csmoe_ep_row_ptrs(const int64_t* tags, const int32_t* tile_expert, const int
 int csmoe_ep_push_rows(const void* src, int32_t dtype, int64_t ld, int32_t D, int64_t rows, const uint64_t* dst_rows,
                        void* stream);
 
+/* Weight exchange for small experts (sigma-MoE: E*D*H*2 bytes of parameters << T*K*D of expanded token rows): the
+ * parameters and their optimizer state stay sharded, every rank computes on a full operand copy.
+ * gather_push: dst[r][dst_offset + i] = convert(src[i]) for every rank r (cast + all-gather in one pass; dst = peer
+ * array of the full-size operand copies, dst_offset = rank * n).  f32->bf16, bf16->bf16, f32->f32.  n % 8 == 0.
+ * reduce_pull: out[i] = sum over r ascending of src[r][src_offset + i] (src = peer array of full-size FP32 gradient
+ * buffers, src_offset = rank * n): a deterministic reduce-scatter; out f32 or bf16.  n % 4 == 0.
+ * Both need a csmoe_ep_barrier between the writers and the readers; no counterpart in the reference (data-parallel
+ * all-reduce of every gradient, simple_task.py:403-413). */
+int csmoe_ep_gather_push(const void* src, int32_t src_dtype, int64_t n, const void* const* dst, int32_t dst_dtype,
+                         int64_t dst_offset, int32_t rank, int32_t P, void* stream);
+int csmoe_ep_reduce_pull(const void* const* src, int64_t src_offset, int64_t n, void* out, int32_t out_dtype, int32_t P,
+                         void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -24,6 +24,7 @@ sys.path.insert(0, str(ROOT / "tests"))
 from helpers import MLPExpert  # noqa: E402
 
 PEAK_TF, PEAK_GBS = 1607.8, 6554.9   # MEASURED_PEAKS.json (burst bf16, HBM copy)
+EXCHANGE = "auto"                     # pretrain layers under expert parallelism: "auto" / "tokens" / "weights"
 GRAPHS = False                        # --graphs: the layers' opt-in CUDA-graph mode (single GPU)
 
 
@@ -77,7 +78,7 @@ def build(case: Case, dev, ep):
         layer.regularization_present = True
         layer.step_warm = 0
         if ep is not None:
-            layer.enable_expert_parallel(ep, max_tokens=case.T)
+            layer.enable_expert_parallel(ep, max_tokens=case.T, exchange=EXCHANGE)
         if GRAPHS:
             layer.enable_cuda_graphs()     # under expert parallelism the router step only (the layer decides)
 
@@ -127,11 +128,13 @@ def build(case: Case, dev, ep):
     return layer, set_branch, step, x_dtype
 
 
-def time_case(case: Case, dev, ep, steps, warmup, dist_on, graphs=None):
+def time_case(case: Case, dev, ep, steps, warmup, dist_on, graphs=None, exchange=None):
     import torch.distributed as dist
-    global GRAPHS
+    global GRAPHS, EXCHANGE
     if graphs is not None:
         GRAPHS = graphs
+    if exchange is not None:
+        EXCHANGE = exchange
     layer, set_branch, step, x_dtype = build(case, dev, ep)
     params = list(layer.parameters())
     rank = ep.rank if ep is not None else 0

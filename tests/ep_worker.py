@@ -108,14 +108,18 @@ def run_multimodal(group, dev, kind, E, K, D, Fh, B, N, competition, max_tokens=
               f"{'competition' if competition else 'router'}: ok", flush=True)
 
 
-def run_pretrain(group, dev, E, K, D, H, B, N, competition):
+def run_pretrain(group, dev, E, K, D, H, B, N, competition, exchange="tokens", bias=False):
     from competesmoe_b200.pretrain import CompeteSMoE
     rank, world = group.rank, group.world
 
     def build():
         torch.manual_seed(11)
         layer = CompeteSMoE(D, E, H, n_heads=K, args=pt_args(), activation=F.relu, selection_mode="gate",
-                            log_interval=None).to(dev)
+                            log_interval=None, bias=bias).to(dev)
+        if bias:
+            with torch.no_grad():
+                layer.bias.normal_(0, 0.1)
+                layer.o_bias.normal_(0, 0.1)
         layer.train()
         layer.regularization_present = True
         layer.set_total_steps(id_layer=0)
@@ -124,7 +128,8 @@ def run_pretrain(group, dev, E, K, D, H, B, N, competition):
         return layer
 
     ref, epl = build(), build()
-    epl.enable_expert_parallel(group, max_tokens=B * N)
+    epl.enable_expert_parallel(group, max_tokens=B * N, exchange=exchange)
+    assert (epl._wx is not None) == (exchange == "weights")
     g = torch.Generator().manual_seed(200 + rank)
     x0 = torch.randn(B, N, D, generator=g).to(dev)
     dy = torch.randn(B, N, D, generator=g).to(dev)
@@ -142,7 +147,11 @@ def run_pretrain(group, dev, E, K, D, H, B, N, competition):
         res.append((out.detach(), x.grad.clone(), layer))
     (o_r, dx_r, lr), (o_e, dx_e, le) = res
     assert torch.equal(lr.last_routing[0], le.last_routing[0])
-    if competition:
+    if exchange == "weights":
+        # the same kernels on the same operands (the gathered bf16 copies are the casts of the same fp32 parameters)
+        assert torch.equal(o_e, o_r), f"EP(weights) output differs bitwise: max {float((o_e.float() - o_r.float()).abs().max())}"
+        assert torch.equal(dx_e, dx_r), f"EP(weights) dx differs bitwise: max {float((dx_e.float() - dx_r.float()).abs().max())}"
+    elif competition:
         close(o_e, o_r, 2e-2, "EP pretrain output"); close(dx_e, dx_r, 3e-2, "EP pretrain dx")
     else:
         # the local layer runs the fused sigma-MoE kernels (expert size 128), the expert-parallel one the grouped-GEMM
@@ -151,16 +160,17 @@ def run_pretrain(group, dev, E, K, D, H, B, N, competition):
         close(o_e, o_r, 2e-2, "EP pretrain output")
         close(dx_e, dx_r, 2e-2, "EP pretrain dx")
     lo, El = le.ep_expert_offset, E // world
-    for n in ("keys", "values"):
+    for n in ("keys", "values") + (("bias",) if bias else ()):
         want = all_reduce_(getattr(lr, n).grad.float().clone(), world)[lo:lo + El]
-        close(getattr(le, n).grad, want, 3e-2, f"EP d {n}")
+        # weights exchanged: the owner adds the ranks' fp32 gradients in rank order, NCCL in its own order -> 1e-5
+        close(getattr(le, n).grad, want, 1e-5 if exchange == "weights" else 3e-2, f"EP d {n}")
     close(le.w_gate.grad, lr.w_gate.grad, 3e-2, "EP d w_gate")
-    if not competition:
+    if not competition or exchange == "weights":
         # the same expert-parallel call replayed from CUDA graphs (device-side barriers are captured like any launch):
         # bit-identical to the eager expert-parallel step, on fresh inputs too.  A fresh layer: gradient accumulators
         # created by earlier eager backward passes live on the default stream and would be waited on during capture.
         epg = build()
-        epg.enable_expert_parallel(group, max_tokens=B * N)
+        epg.enable_expert_parallel(group, max_tokens=B * N, exchange=exchange)
         epg.enable_cuda_graphs()
         for rep in range(3):
             gx = torch.Generator().manual_seed(300 + rank + rep)
@@ -178,7 +188,7 @@ def run_pretrain(group, dev, E, K, D, H, B, N, competition):
             assert all(torch.equal(a, b) for a, b in zip(*outs)), "EP graph replay differs from the eager EP step"
         assert len(epg._graphs) == 1
     if rank == 0:
-        print(f"ep pretrain E={E} K={K} D={D} H={H} T={B * N} world={world} "
+        print(f"ep pretrain E={E} K={K} D={D} H={H} T={B * N} world={world} exchange={exchange}{' bias' if bias else ''} "
               f"{'competition' if competition else 'router'}: ok", flush=True)
 
 
@@ -197,6 +207,9 @@ def main():
             run_multimodal(group, dev, kind="mlp", E=4 if world <= 4 else 8, K=2, D=256, Fh=520, B=2, N=200, competition=comp)
             run_multimodal(group, dev, kind="glu", E=8, K=2, D=512, Fh=1024, B=1, N=1000, competition=comp)
             run_pretrain(group, dev, E=16, K=4, D=256, H=128, B=2, N=300, competition=comp)
+            run_pretrain(group, dev, E=16, K=4, D=256, H=128, B=2, N=300, competition=comp, exchange="weights")
+            run_pretrain(group, dev, E=16, K=2, D=256, H=128, B=1, N=500, competition=comp, exchange="weights", bias=True)
+            run_pretrain(group, dev, E=8, K=2, D=128, H=64, B=1, N=200, competition=comp, exchange="weights")   # grouped-GEMM path
         # ragged: a rank with very few tokens, top-1, more experts than tokens
         run_multimodal(group, dev, kind="mlp", E=8, K=1, D=128, Fh=256, B=1, N=3 + 5 * group.rank, competition=False,
                        max_tokens=3 + 5 * (group.world - 1))
