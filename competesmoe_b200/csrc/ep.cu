@@ -240,29 +240,53 @@ ep_gather_push_kernel(const S* __restrict__ src, long long n, Peers dst, long lo
   }
 }
 
-template <typename T>
+// PMAX = compile-time bound on P, U = vectors per thread and iteration: U * (P - 1) remote 16-byte loads are in flight
+// per thread (small groups need U > 1 to cover the NVLink latency: one vector per thread measured 410 GB/s at P = 2).
+template <typename T, int PMAX, int U>
 __global__ void __launch_bounds__(256)
 ep_reduce_pull_kernel(Peers src, long long src_off, long long n, T* __restrict__ out, int P) {
-  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x * 4;
-  for (long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
-    float4 v[kMaxRanks];
+  const long long tile = static_cast<long long>(blockDim.x) * 4 * U;
+  for (long long base = static_cast<long long>(blockIdx.x) * tile; base < n; base += static_cast<long long>(gridDim.x) * tile) {
+    float4 v[U][PMAX];
 #pragma unroll
-    for (int p = 0; p < kMaxRanks; ++p)
-      if (p < P) v[p] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src.p[p]) + src_off + i);
-    float4 a = v[0];
+    for (int u = 0; u < U; ++u) {
+      const long long i = base + (static_cast<long long>(u) * blockDim.x + threadIdx.x) * 4;
 #pragma unroll
-    for (int p = 1; p < kMaxRanks; ++p)
-      if (p < P) { a.x += v[p].x; a.y += v[p].y; a.z += v[p].z; a.w += v[p].w; }
-    if constexpr (sizeof(T) == 4) {
-      *reinterpret_cast<float4*>(out + i) = a;
-    } else {
-      __nv_bfloat162 lo = __floats2bfloat162_rn(a.x, a.y), hi = __floats2bfloat162_rn(a.z, a.w);
-      uint2 u;
-      u.x = *reinterpret_cast<uint32_t*>(&lo);
-      u.y = *reinterpret_cast<uint32_t*>(&hi);
-      *reinterpret_cast<uint2*>(out + i) = u;
+      for (int p = 0; p < PMAX; ++p)
+        if (p < P && i < n) v[u][p] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src.p[p]) + src_off + i);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = base + (static_cast<long long>(u) * blockDim.x + threadIdx.x) * 4;
+      if (i >= n) continue;
+      float4 a = v[u][0];
+#pragma unroll
+      for (int p = 1; p < PMAX; ++p)
+        if (p < P) { a.x += v[u][p].x; a.y += v[u][p].y; a.z += v[u][p].z; a.w += v[u][p].w; }
+      if constexpr (sizeof(T) == 4) {
+        *reinterpret_cast<float4*>(out + i) = a;
+      } else {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(a.x, a.y), hi = __floats2bfloat162_rn(a.z, a.w);
+        uint2 w;
+        w.x = *reinterpret_cast<uint32_t*>(&lo);
+        w.y = *reinterpret_cast<uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(out + i) = w;
+      }
     }
   }
+}
+
+template <typename T>
+void launch_reduce_pull(const Peers& s, long long src_off, long long n, T* out, int P, cudaStream_t stream) {
+  const long long cap = static_cast<long long>(num_sms() > 0 ? num_sms() : 148) * 4;
+  auto grid = [&](int U) {
+    const long long tile = 256ll * 4 * U;
+    return static_cast<unsigned>(std::min<long long>((n + tile - 1) / tile, cap));
+  };
+  if (P <= 2) ep_reduce_pull_kernel<T, 2, 4><<<grid(4), 256, 0, stream>>>(s, src_off, n, out, P);
+  else if (P <= 4) ep_reduce_pull_kernel<T, 4, 2><<<grid(2), 256, 0, stream>>>(s, src_off, n, out, P);
+  else if (P <= 8) ep_reduce_pull_kernel<T, 8, 1><<<grid(1), 256, 0, stream>>>(s, src_off, n, out, P);
+  else ep_reduce_pull_kernel<T, kMaxRanks, 1><<<grid(1), 256, 0, stream>>>(s, src_off, n, out, P);
 }
 
 int fill_peers(Peers& out, const void* const* ptrs, int P, bool allow_null, const char* what) {
@@ -463,13 +487,10 @@ extern "C" int csmoe_ep_reduce_pull(const void* const* src, int64_t src_offset, 
   int rc = fill_peers(s, src, P, false, "csmoe_ep_reduce_pull");
   if (rc != CSMOE_OK) return rc;
   cudaStream_t stream = as_stream(stream_);
-  const long long vecs = n / 4;
-  const long long cap = static_cast<long long>(num_sms() > 0 ? num_sms() : 148) * 8;
-  const unsigned grid = static_cast<unsigned>(std::min<long long>((vecs + 255) / 256, cap));
   if (out_dtype == CSMOE_F32) {
-    ep_reduce_pull_kernel<float><<<grid, 256, 0, stream>>>(s, src_offset, n, static_cast<float*>(out), P);
+    launch_reduce_pull<float>(s, src_offset, n, static_cast<float*>(out), P, stream);
   } else if (out_dtype == CSMOE_BF16) {
-    ep_reduce_pull_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(s, src_offset, n, static_cast<__nv_bfloat16*>(out), P);
+    launch_reduce_pull<__nv_bfloat16>(s, src_offset, n, static_cast<__nv_bfloat16*>(out), P, stream);
   } else {
     CSMOE_CHECK_ARG(false, "csmoe_ep_reduce_pull: unsupported output dtype %d", out_dtype);
   }

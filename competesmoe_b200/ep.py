@@ -119,6 +119,7 @@ class EPGroup:
         self._epoch_ptr = self.ctrl.local_ptr + 2048
         self._scratch = {}
         self._identity = {}
+        self._flags_ch = {}
 
     # ---- memory
     def alloc(self, nbytes: int) -> SymmetricBuffer:
@@ -177,8 +178,17 @@ class EPGroup:
         self._owned.clear()
 
     # ---- kernels
-    def barrier(self):
-        ops._call("csmoe_ep_barrier", self._flags, self._epoch_ptr, self.rank, self.world, ops._stream())
+    def barrier(self, channel: int = 0):
+        """Device-side barrier on the current stream.  Channels have their own flag vectors and epoch counters: two
+        streams of one rank may each run a barrier sequence as long as every rank issues the same sequence per channel."""
+        assert 0 <= channel < 8
+        if channel == 0:
+            flags = self._flags
+        else:
+            flags = self._flags_ch.get(channel)
+            if flags is None:
+                flags = self._flags_ch[channel] = self.ctrl.peers(128 * channel)
+        ops._call("csmoe_ep_barrier", flags, self._epoch_ptr + 64 * channel, self.rank, self.world, ops._stream())
 
     def exchange_plan(self, counts: torch.Tensor, num_experts: int, row_tile: int, row_cap: int) -> "EPPlan":
         assert num_experts % self.world == 0 and num_experts <= MAX_EXPERTS
@@ -374,10 +384,12 @@ class WeightExchange:
         assert tuple(shape) == tuple(full), f"gradient of {role}: {tuple(shape)} != {tuple(full)}"
         return buf.tensor(0, full, torch.float32)
 
-    def reduce_begin(self, grads: dict):
+    def reduce_begin(self, grads: dict, early: bool = False):
         """grads: role -> (full-size gradient or None, parameter shard or None for 'dtype of the gradient').  Gradients
         that were not written into grad_out() already (bias gradients) are copied there.  Barrier, then the owner's
-        slices are summed on a side stream: what the caller issues before reduce_end() (the dx reduction) overlaps."""
+        slices are summed on a side stream: what the caller issues before reduce_end() (the dx reduction) overlaps.
+        early=True: the barrier itself runs on the side stream too (its own barrier channel), so the caller's next
+        kernels -- the other weight-gradient GEMM -- overlap the wait and the transfer."""
         g = self.group
         todo = []
         for role, (full, param) in grads.items():
@@ -390,13 +402,17 @@ class WeightExchange:
                 dst.copy_(full)
             dt = param.dtype if param is not None else full.dtype
             todo.append((buf, torch.empty((shape[0] // g.world, *shape[1:]), dtype=dt, device=g.device)))
-        g.barrier()
         overlap = g.world > 1 and _WX_OVERLAP
+        early = early and overlap
         main = torch.cuda.current_stream(g.device)
+        if not early:
+            g.barrier()
         if overlap:
             side = self._side_stream()
             side.wait_stream(main)
         with torch.cuda.stream(side) if overlap else contextlib.nullcontext():
+            if early:
+                g.barrier(channel=1)
             for item in todo:
                 if item is None:
                     continue
@@ -405,15 +421,14 @@ class WeightExchange:
                 ops._call("csmoe_ep_reduce_pull", buf.peers(), g.rank * n, n, local.data_ptr(), ops._dt(local), g.world, ops._stream())
         return todo, overlap
 
-    def reduce_end(self, pending):
-        """-> the local gradient slices in role order (None where no gradient was given)."""
-        todo, overlap = pending
+    def reduce_end(self, *pending):
+        """-> the local gradient slices of every reduce_begin() handed in, in order (None where no gradient was given)."""
         g = self.group
-        if overlap:
+        if any(ov for _, ov in pending):
             torch.cuda.current_stream(g.device).wait_stream(self._side_stream())
         if self.consumers > 1:
             g.barrier()     # another function of this layer step writes the same gradient buffers next
-        return [None if item is None else item[1] for item in todo]
+        return [None if item is None else item[1] for todo, _ in pending for item in todo]
 
     def reduce(self, grads: dict):
         return self.reduce_end(self.reduce_begin(grads))

@@ -289,14 +289,16 @@ class SigmaFFNFn(Function):
         dw = dw_part.sum(0).view(T, K) if ctx.needs_input_grad[1] else None
         dvalues = ops.sigma_wgrad(hw, dout, E, route, transpose=False, out_dtype=values.dtype,
                                   out=_wx_grad_out(wx, "w2", vb))                                 # [E, H, Dout]
+        if wx is not None:      # the owners start summing d values while d keys is still being computed
+            pend_v = wx.reduce_begin({"w2": (dvalues, values)}, early=True)
         dkeys = ops.sigma_wgrad(dz, xb, E, route, transpose=True, out_dtype=keys.dtype,
                                 out=_wx_grad_out(wx, "w1", kb))                                   # [E, D, H]
         dbias = ops.bias_grad(dz, E, route=route, out_dtype=bias.dtype) if bias is not None else None
-        if wx is not None:      # the owners sum their slices of every rank's gradients while dx is reduced over k
-            pending = wx.reduce_begin({"w1": (dkeys, keys), "b1": (dbias, None), "w2": (dvalues, values), "b2": (None, None)})
+        if wx is not None:      # ... and d keys / d bias while dx is reduced over k
+            pend_k = wx.reduce_begin({"w1": (dkeys, keys), "b1": (dbias, None)})
         dx = ops.scatter_reduce(dxr, route.slot_to_row, T, K).to(ctx.x_dtype) if ctx.needs_input_grad[0] else None
         if wx is not None:
-            dkeys, dbias, dvalues, _ = wx.reduce_end(pending)
+            dvalues, dkeys, dbias = wx.reduce_end(pend_v, pend_k)
         return dx, dw, None, dkeys, dbias, dvalues, None, dres, None, None, None
 
 
