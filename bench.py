@@ -468,9 +468,9 @@ def ep_parity_section(device, world, rank, bench_layer, x, dy, params):
             for comp in (False, True):
                 ew.run_multimodal(group, device, kind="mlp", E=4 if world <= 4 else 8, K=2, D=256, Fh=520, B=2, N=200, competition=comp)
                 ew.run_multimodal(group, device, kind="glu", E=8, K=2, D=512, Fh=1024, B=1, N=1000, competition=comp)
-                ew.run_pretrain(group, device, E=16, K=4, D=256, H=128, B=2, N=300, competition=comp)
                 ew.run_pretrain(group, device, E=16, K=4, D=256, H=128, B=2, N=300, competition=comp, exchange="weights")
                 ew.run_pretrain(group, device, E=16, K=2, D=256, H=128, B=1, N=500, competition=comp, exchange="weights", bias=True)
+                ew.run_pretrain(group, device, E=16, K=4, D=256, H=128, B=2, N=300, competition=comp)
                 res["cases"] += [f"multimodal mlp {'comp' if comp else 'router'}", f"multimodal glu {'comp' if comp else 'router'}",
                                  f"pretrain E=16 K=4 {'comp' if comp else 'router'} (tokens exchanged)",
                                  f"pretrain E=16 K=4 {'comp' if comp else 'router'} (weights exchanged)",
@@ -505,6 +505,7 @@ def ep_parity_section(device, world, rank, bench_layer, x, dy, params):
     except Exception as exc:
         res["ok"] = False
         res["error"] = repr(exc)[:500]
+        print(f"bench: rank {rank}: EP parity section failed: {res['error']}", file=sys.stderr, flush=True)
     if rank == 0:
         print(f"EP parity {'ok' if res['ok'] else 'FAILED'} world={world}: {len(res['cases'])} ep_worker cases"
               f"{', bench layer bitwise equal to its unsharded copy' if res.get('bench_layer_bitwise') else ''}"
@@ -512,53 +513,50 @@ def ep_parity_section(device, world, rank, bench_layer, x, dy, params):
     return res
 
 
-def c4_ep_section(device, world, rank, steps):
+def c4_ep_section(device, world, rank, steps, out):
     """BASELINE.json configs[3] (d=1024, H=128, 64 experts, top-8, bf16 autocast): 8192 tokens per GPU (N = 8 gives the
     yaml's global batch of 64 x 1024), expert-parallel over all N ranks, next to the UNSHARDED layer running the same
     per-GPU batch on every GPU at the same time (the 1-GPU program under the same power conditions).
     efficiency = local_ms / ep_ms = tokens/s(N) / (N * tokens/s(1)).  Both exchange modes of the pretrain layer are
     timed: "weights" (owners publish bf16 expert copies, gradients reduced onto the owners; what "auto" picks at this
-    shape) and "tokens" (every (token, expert) row travels to the expert's owner and back)."""
-    import torch.distributed as dist
+    shape) and then "tokens" (every (token, expert) row travels to the expert's owner and back).  `out` is filled as the
+    parts complete, so that a hang in a later part leaves the earlier numbers in the line."""
     sys.path.insert(0, str(ROOT / "scripts"))
     import config_sweep as cs
-    from competesmoe_b200.ep import EPGroup
+    from competesmoe_b200.ep import EPGroup, WeightExchange
     case = cs.Case("C4 pretrain LM layer d=1024 E=64 K=8 H=128, 8192 tokens/GPU", "pretrain", 8192, 1024, 128, 64, 8, key="C4")
-    out = {"what": case.name, "tokens_per_gpu": case.T, "world": world, "exchange_auto": None}
+    auto = "weights" if WeightExchange.prefer_weights(case.E, 2 * case.D * case.hidden, case.T, case.K, case.D, case.D) else "tokens"
+    out.update({"what": case.name, "tokens_per_gpu": case.T, "world": world, "exchange_auto": auto})
+    names = ((False, "router"), (True, "competition"))
     try:
         local_eager = cs.time_case(case, device, None, steps, 3, True, graphs=False)
         local_graph = cs.time_case(case, device, None, steps, 3, True, graphs=True)
+        for comp, nm in names:
+            out[nm] = {"local_eager_ms": round(local_eager[comp], 4), "local_graphed_ms": round(local_graph[comp], 4)}
         group = EPGroup(None, device)
-        modes = {}
         try:
-            for mode in ("weights", "tokens"):
+            for mode in ((auto,) + tuple(m for m in ("weights", "tokens") if m != auto)):
                 ep = cs.time_case(case, device, group, steps, 3, True, graphs=False, exchange=mode)
                 try:
                     ep_graph = cs.time_case(case, device, group, steps, 3, True, graphs=True, exchange=mode)
                 except Exception as exc:
                     ep_graph = {False: float("nan"), True: float("nan")}
                     out[f"ep_graph_error_{mode}"] = repr(exc)[:300]
-                modes[mode] = (ep, ep_graph)
+                for comp, nm in names:
+                    best_local = min(local_eager[comp], local_graph[comp])
+                    best_ep = min(v for v in (ep[comp], ep_graph[comp]) if v == v)
+                    row = {"ep_ms": round(best_ep, 4), "ep_eager_ms": round(ep[comp], 4),
+                           "ep_graphed_ms": None if ep_graph[comp] != ep_graph[comp] else round(ep_graph[comp], 4),
+                           "tokens_per_s": round(case.T * world / (best_ep * 1e-3), 1),
+                           "efficiency_vs_local_best": round(best_local / best_ep, 4),
+                           "efficiency_vs_local_eager": round(local_eager[comp] / ep[comp], 4)}
+                    out[nm][mode] = row
+                    if mode == auto:
+                        out[nm].update({"ep_ms": row["ep_ms"], "tokens_per_s": row["tokens_per_s"],
+                                        "efficiency_vs_local_best": row["efficiency_vs_local_best"]})
         finally:
             cs.EXCHANGE = "auto"
             group.close()
-        from competesmoe_b200.ep import WeightExchange
-        out["exchange_auto"] = "weights" if WeightExchange.prefer_weights(case.E, 2 * case.D * case.hidden, case.T, case.K,
-                                                                          case.D, case.D) else "tokens"
-        for comp, nm in ((False, "router"), (True, "competition")):
-            best_local = min(local_eager[comp], local_graph[comp])
-            row = {"local_eager_ms": round(local_eager[comp], 4), "local_graphed_ms": round(local_graph[comp], 4)}
-            for mode, (ep, ep_graph) in modes.items():
-                best_ep = min(v for v in (ep[comp], ep_graph[comp]) if v == v)
-                row[mode] = {"ep_ms": round(best_ep, 4), "ep_eager_ms": round(ep[comp], 4),
-                             "ep_graphed_ms": None if ep_graph[comp] != ep_graph[comp] else round(ep_graph[comp], 4),
-                             "tokens_per_s": round(case.T * world / (best_ep * 1e-3), 1),
-                             "efficiency_vs_local_best": round(best_local / best_ep, 4),
-                             "efficiency_vs_local_eager": round(local_eager[comp] / ep[comp], 4)}
-            auto = row[out["exchange_auto"]]
-            row.update({"ep_ms": auto["ep_ms"], "tokens_per_s": auto["tokens_per_s"],
-                        "efficiency_vs_local_best": auto["efficiency_vs_local_best"]})
-            out[nm] = row
     except Exception as exc:
         out["error"] = repr(exc)[:500]
     return out
@@ -657,16 +655,6 @@ def run_ours(a):
     ms_e2e, h2d, d2h = e2e_region(layer, x_host, dy_host, params, a.steps, a.warmup, dist_on, device)
     clocks = sampler.stop() if sampler else None
 
-    # ---- outside the headline regions: the stage-3/5 kernels alone, the other named shapes, expert-parallel parity
-    hbm_stage = hbm_stage_gbs(device, peak_gbs) if a.sections else None
-    ep_parity = c4_ep = configs = None
-    if a.sections and ep_group is not None:
-        ep_parity = ep_parity_section(device, world, rank, layer, x, dy, params)
-    if a.sections and dist_on and 64 % world == 0:
-        c4_ep = c4_ep_section(device, world, rank, max(5, a.steps // 2))
-    if a.sections and world == 1:
-        configs = named_configs(device, max(6, a.steps // 2), peak_tf, peak_gbs)
-
     if rank == 0:
         tok = TOKENS * world
         value = tok / (ms_router * 1e-3)
@@ -708,15 +696,49 @@ def run_ours(a):
                          "peak_source": peak_src, "launches_per_step": len(timed) // max(a.steps, 1),
                          "share_of_step": gemm_share, "per_launch": gemm_detail},
             "cpu_baseline": cpu, "gpu_launches": launches, "clocks": clocks,
-            "hbm_stage": hbm_stage, "configs": configs, "ep_parity": ep_parity, "c4_ep": c4_ep,
+            "hbm_stage": None, "configs": None, "ep_parity": None, "c4_ep": None,
         }
         if traffic is not None:
             line["roofline"]["traffic_source"] = "profiles/gemm_traffic.json (ncu --set full of the same launches, committed; not re-measured in this run)"
-        print(json.dumps(line), flush=True)
-    if ep_group is not None:
-        ep_group.close()
-    if dist_on:
-        dist.destroy_process_group()
+    else:
+        line = {}
+
+    # ---- outside the headline regions: the stage-3/5 kernels alone, the other named shapes, expert-parallel parity and
+    # the C4 expert-parallel step.  The headline numbers above are complete at this point; a watchdog makes sure that a
+    # hang in one of these sections (a peer that left the barrier sequence) costs that section, not the JSON line.
+    done = threading.Event()
+
+    def emit():
+        if rank == 0:
+            print(json.dumps(line), flush=True)
+
+    def watchdog():
+        if not done.wait(a.sections_timeout):
+            line["sections_timeout"] = f"optional sections did not finish within {a.sections_timeout} s; the line carries what was complete"
+            print(f"bench: rank {rank}: optional sections timed out", file=sys.stderr, flush=True)
+            emit()
+            os._exit(0)
+
+    if a.sections:
+        threading.Thread(target=watchdog, daemon=True).start()
+        line["hbm_stage"] = hbm_stage_gbs(device, peak_gbs)
+        if ep_group is not None:
+            line["ep_parity"] = ep_parity_section(device, world, rank, layer, x, dy, params)
+        if dist_on and 64 % world == 0 and (line["ep_parity"] or {}).get("ok", True):
+            line["c4_ep"] = {}
+            c4_ep_section(device, world, rank, max(5, a.steps // 2), line["c4_ep"])
+        if world == 1:
+            line["configs"] = named_configs(device, max(6, a.steps // 2), peak_tf, peak_gbs)
+    done.set()
+    emit()
+    try:
+        if ep_group is not None:
+            ep_group.close()
+        if dist_on:
+            dist.destroy_process_group()
+    except Exception as exc:      # a section left the CUDA context in an error state: the line is out, leave quietly
+        print(f"bench: rank {rank}: teardown failed: {exc!r}"[:400], file=sys.stderr, flush=True)
+        os._exit(0)
 
 
 def main():
@@ -728,6 +750,8 @@ def main():
     ap.add_argument("--graphs", type=int, default=1, help="1: use the layer's CUDA-graph mode where available (single GPU / replicas)")
     ap.add_argument("--sections", type=int, default=1,
                     help="1: also report hbm_stage, the other named configs (N=1), EP parity and C4 expert-parallel (N>1)")
+    ap.add_argument("--sections-timeout", type=float, default=240.0,
+                    help="seconds the optional sections may take before the line is printed without them")
     ap.add_argument("--parallel", default="ep", choices=["ep", "replicas"],
                     help="N > 1: expert-parallel groups (default) or N independent replicas of the layer")
     a = ap.parse_args()

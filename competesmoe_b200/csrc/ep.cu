@@ -27,6 +27,7 @@ namespace {
 
 constexpr int kMaxRanks = CSMOE_EP_MAX_RANKS;
 constexpr int kMaxExperts = 1024;
+constexpr unsigned long long kBarrierTimeoutNs = 60ull * 1000ull * 1000ull * 1000ull;
 
 struct Peers {
   void* p[kMaxRanks];
@@ -55,9 +56,16 @@ __device__ __forceinline__ void flag_barrier(const Peers& flags, int* epoch, int
   if (threadIdx.x < P) {
     st_release_sys(reinterpret_cast<int*>(flags.p[threadIdx.x]) + rank, ep);
     const int* mine = reinterpret_cast<const int*>(flags.p[rank]) + threadIdx.x;
-    unsigned long long spins = 0;
+    // a peer died or the ranks disagree on the call sequence: trap after kBarrierTimeoutNs of wall clock (an error on
+    // this rank within a minute instead of a job that hangs until someone kills it)
+    unsigned long long spins = 0, t0 = 0;
     while (ld_acquire_sys(mine) - ep < 0) {
-      if (++spins > (1ull << 31)) __trap();   // a peer died or the ranks disagree on the call sequence
+      if ((++spins & 1023ull) == 0) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > kBarrierTimeoutNs) __trap();
+      }
     }
   }
   __syncthreads();
