@@ -472,9 +472,9 @@ def ep_parity_section(device, world, rank, bench_layer, x, dy, params):
                 ew.run_pretrain(group, device, E=16, K=2, D=256, H=128, B=1, N=500, competition=comp, exchange="weights", bias=True)
                 ew.run_pretrain(group, device, E=16, K=4, D=256, H=128, B=2, N=300, competition=comp)
                 res["cases"] += [f"multimodal mlp {'comp' if comp else 'router'}", f"multimodal glu {'comp' if comp else 'router'}",
-                                 f"pretrain E=16 K=4 {'comp' if comp else 'router'} (tokens exchanged)",
                                  f"pretrain E=16 K=4 {'comp' if comp else 'router'} (weights exchanged)",
-                                 f"pretrain E=16 K=2 bias {'comp' if comp else 'router'} (weights exchanged)"]
+                                 f"pretrain E=16 K=2 bias {'comp' if comp else 'router'} (weights exchanged)",
+                                 f"pretrain E=16 K=4 {'comp' if comp else 'router'} (tokens exchanged)"]
             ew.run_multimodal(group, device, kind="mlp", E=8, K=1, D=128, Fh=256, B=1, N=3 + 5 * group.rank, competition=False,
                               max_tokens=3 + 5 * (group.world - 1))
             res["cases"].append("ragged top-1")
