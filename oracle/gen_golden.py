@@ -300,7 +300,7 @@ def pt_args(**kw):
     return SimpleNamespace(**base)
 
 
-def gen_pretrain(pm, name, D, E, H, K, B, N, competition, seed=0, **argkw):
+def gen_pretrain(pm, name, D, E, H, K, B, N, competition, seed=0, bias=False, **argkw):
     """Reference layer with its `cvmm` name bound to the oracle's per-expert restatement (the Triton op needs a GPU);
     the restatement itself is pinned by gen_cvmm_interpreter below."""
     from oracle import pretrain as op
@@ -320,7 +320,11 @@ def gen_pretrain(pm, name, D, E, H, K, B, N, competition, seed=0, **argkw):
     try:
         with quiet():
             layer = pm["get_moe"]("competesmoe")(D, E, H, n_heads=K, args=args, activation=F.relu, selection_mode="gate",
-                                                 log_interval=None)
+                                                 log_interval=None, bias=bias)
+            if bias:    # `-moe.bias 1` (moe.py:129-134): both biases start at zero in the reference; make them matter
+                with torch.no_grad():
+                    layer.bias.normal_(0, 0.3)
+                    layer.o_bias.normal_(0, 0.3)
             layer.train()
             layer.regularization_present = True
             layer.set_total_steps(id_layer=0)
@@ -343,9 +347,13 @@ def gen_pretrain(pm, name, D, E, H, K, B, N, competition, seed=0, **argkw):
         "dx": x.grad.clone(), "dw_gate": layer.w_gate.grad.clone(), "dkeys": layer.keys.grad.clone(),
         "dvalues": layer.values.grad.clone(),
     }
+    if bias:
+        fx.update({"bias": layer.bias.detach().clone(), "o_bias": layer.o_bias.detach().clone(),
+                   "dbias": layer.bias.grad.clone(), "do_bias": layer.o_bias.grad.clone()})
     x2 = fx["x"].clone().requires_grad_(True)
     wg, ks, vs = (fx[n].clone().requires_grad_(True) for n in ("w_gate", "keys", "values"))
-    o_out, o_regs, dbg = op.competesmoe_forward(x2, wg, ks, vs, K, args, competition)
+    bs, obs = ((fx[n].clone().requires_grad_(True) for n in ("bias", "o_bias")) if bias else (None, None))
+    o_out, o_regs, dbg = op.competesmoe_forward(x2, wg, ks, vs, K, args, competition, bias=bs, o_bias=obs)
     ((o_out * dy).sum() + sum(o_regs.values())).backward()
     tol = dict(rtol=1e-4, atol=1e-6)
     torch.testing.assert_close(o_out, fx["out"], **tol)
@@ -356,6 +364,9 @@ def gen_pretrain(pm, name, D, E, H, K, B, N, competition, seed=0, **argkw):
     torch.testing.assert_close(wg.grad, fx["dw_gate"], **tol)
     torch.testing.assert_close(ks.grad, fx["dkeys"], **tol)
     torch.testing.assert_close(vs.grad, fx["dvalues"], **tol)
+    if bias:
+        torch.testing.assert_close(bs.grad, fx["dbias"], **tol)
+        torch.testing.assert_close(obs.grad, fx["do_bias"], **tol)
     fx["selected"] = dbg["selected"].clone()
     torch.save(fx, OUT / f"{name}.pt")
     print(f"  wrote {name}.pt  (oracle == reference)  regs={ {k: round(float(v), 6) for k, v in regs.items()} }")
@@ -541,6 +552,13 @@ def gen_gate_variants(mm, pm):
     gen_multimodal(mm, "mm_siglip_comp_normsigmoid_f32", "siglip", 64, 64, 128, 4, 2, 2, 16, True, seed=34, norm_sigmoid=True)
 
 
+def gen_bias(pm):
+    """`-moe.bias 1`: hidden bias [E, H] inside the selected experts, o_bias [D] on the layer output (moe.py:129-134,
+    :400-401; competesmoe.py:613-614); the competition's dense scoring pass ignores the hidden bias (:381-414)."""
+    gen_pretrain(pm, "pt_router_bias_f32", 64, 8, 32, 2, 2, 24, False, seed=40, bias=True)
+    gen_pretrain(pm, "pt_comp_bias_f32", 64, 8, 32, 2, 2, 24, True, seed=41, bias=True)
+
+
 def main():
     OUT.mkdir(parents=True, exist_ok=True)
     if "--gate-variants-only" in sys.argv:
@@ -548,6 +566,9 @@ def main():
         return
     if "--siblings-only" in sys.argv:
         gen_all_siblings(load_multimodal_reference())
+        return
+    if "--bias-only" in sys.argv:
+        gen_bias(load_pretrain_reference())
         return
     if "--pretrain-siblings-only" in sys.argv:
         gen_all_pretrain_siblings(load_pretrain_reference())
@@ -578,6 +599,7 @@ def main():
     gen_pretrain(pm, "pt_comp_tribrid_f32", 64, 8, 32, 2, 2, 16, True, seed=4, tribrid=True)
     gen_all_pretrain_siblings(pm)
     gen_gate_variants(mm, pm)
+    gen_bias(pm)
     print("done; now run:  TRITON_INTERPRET=1 python -m oracle.gen_golden")
 
 

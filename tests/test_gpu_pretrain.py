@@ -16,7 +16,8 @@ from helpers import assert_close_rms
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
 PT = ["pt_router_f32", "pt_comp_f32", "pt_comp_hybrid_bal_f32", "pt_comp_intopk_f32", "pt_comp_tribrid_f32",
-      "pt_router_cosine_f32", "pt_router_normweight_f32", "pt_router_normsigmoid_f32", "pt_comp_cosine_f32"]
+      "pt_router_cosine_f32", "pt_router_normweight_f32", "pt_router_normsigmoid_f32", "pt_comp_cosine_f32",
+      "pt_router_bias_f32", "pt_comp_bias_f32"]
 
 
 def build_layer(fx):
@@ -24,9 +25,11 @@ def build_layer(fx):
     m = fx["meta"]
     args = SimpleNamespace(**m["args"])
     layer = CompeteSMoE(m["D"], m["E"], m["H"], n_heads=m["K"], args=args, activation=F.relu, selection_mode="gate",
-                        log_interval=None)
+                        log_interval=None, bias="bias" in fx)
     with torch.no_grad():
         layer.w_gate.copy_(fx["w_gate"]); layer.keys.copy_(fx["keys"]); layer.values.copy_(fx["values"])
+        if "bias" in fx:     # `-moe.bias 1` fixtures (moe.py:129-134)
+            layer.bias.copy_(fx["bias"]); layer.o_bias.copy_(fx["o_bias"])
     layer = layer.to(DEV)
     layer.train()
     layer.regularization_present = True
@@ -41,12 +44,14 @@ def test_pretrain_layer_matches_reference_golden(name):
     fx = load_golden(name)
     m = fx["meta"]
     layer, args = build_layer(fx)
-    assert set(layer.state_dict().keys()) == {"w_gate", "keys", "values"}
+    has_bias = "bias" in fx
+    assert set(layer.state_dict().keys()) == {"w_gate", "keys", "values"} | ({"bias", "o_bias"} if has_bias else set())
     x = fx["x"].to(DEV).requires_grad_(True)
     with torch.autocast("cuda", dtype=torch.bfloat16):
         out = layer(x, id_layer=0)
         regs = layer.get_reg_loss()
-    assert out.dtype == torch.bfloat16 and out.shape == fx["out"].shape
+    # `res + self.o_bias` (competesmoe.py:613-614) promotes the bf16 result to the fp32 parameter's dtype, here as there
+    assert out.dtype == (torch.float32 if has_bias else torch.bfloat16) and out.shape == fx["out"].shape
     assert set(regs) == set(fx["regs"])
     ((out.float() * fx["dy"].to(DEV)).sum() + sum(regs.values())).backward()
     # The oracle (pinned to the reference by these same fp32 fixtures, tests/test_oracle_golden.py) evaluated with the
@@ -54,7 +59,9 @@ def test_pretrain_layer_matches_reference_golden(name):
     # conditioned on tokens whose two selected experts have nearly equal dw (differences of O(1) numbers), where fp32
     # and bf16 legitimately differ by tens of percent -- the CPU bf16 oracle shows the same deviation from the fixture.
     xr, wg, ks, vs = (fx[n].clone().requires_grad_(True) for n in ("x", "w_gate", "keys", "values"))
-    o_out, o_regs, dbg = op.competesmoe_forward(xr, wg, ks, vs, m["K"], args, m["competition"], op_dtype=torch.bfloat16)
+    bs, obs = ((fx[n].clone().requires_grad_(True) for n in ("bias", "o_bias")) if has_bias else (None, None))
+    o_out, o_regs, dbg = op.competesmoe_forward(xr, wg, ks, vs, m["K"], args, m["competition"], op_dtype=torch.bfloat16,
+                                                bias=bs, o_bias=obs)
     ((o_out.float() * fx["dy"]).sum() + sum(o_regs.values())).backward()
     sel, w = layer.last_routing
     margin = om.topk_margin(dbg["affinity"] if m["competition"] else dbg["gate_softmax"], m["K"])
@@ -77,6 +84,9 @@ def test_pretrain_layer_matches_reference_golden(name):
         assert_close_rms(layer.keys.grad, ks.grad, 3e-2, "dkeys")
         assert_close_rms(layer.values.grad, vs.grad, 3e-2, "dvalues")
         assert_close_rms(layer.w_gate.grad, wg.grad, 3e-2, "dw_gate")
+        if has_bias:
+            assert_close_rms(layer.bias.grad, bs.grad, 3e-2, "dbias")
+            assert_close_rms(layer.o_bias.grad, obs.grad, 3e-2, "do_bias")
     assert layer.keys.grad.dtype == torch.float32        # fp32 master parameters keep fp32 gradients
 
 

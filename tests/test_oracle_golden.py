@@ -15,7 +15,8 @@ MM = ["mm_siglip_router_f32", "mm_projector_router_f32", "mm_glu_router_f32", "m
       "mm_projector_comp_f32", "mm_glu_comp_f32", "mm_siglip_comp_hybrid_f32", "mm_siglip_router_bf16",
       "mm_siglip_comp_bf16", "mm_siglip_comp_upcycled_f32", "mm_siglip_comp_normsigmoid_f32"]
 PT = ["pt_router_f32", "pt_comp_f32", "pt_comp_hybrid_bal_f32", "pt_comp_intopk_f32", "pt_comp_tribrid_f32",
-      "pt_router_cosine_f32", "pt_router_normweight_f32", "pt_router_normsigmoid_f32", "pt_comp_cosine_f32"]
+      "pt_router_cosine_f32", "pt_router_normweight_f32", "pt_router_normsigmoid_f32", "pt_comp_cosine_f32",
+      "pt_router_bias_f32", "pt_comp_bias_f32"]
 
 
 def _req(t):
@@ -67,7 +68,8 @@ def test_pretrain_oracle_matches_reference(name):
     m = fx["meta"]
     args = SimpleNamespace(**m["args"])
     x, wg, ks, vs = (_req(fx[n]) for n in ("x", "w_gate", "keys", "values"))
-    out, regs, dbg = op.competesmoe_forward(x, wg, ks, vs, m["K"], args, m["competition"])
+    bs, obs = (_req(fx["bias"]), _req(fx["o_bias"])) if "bias" in fx else (None, None)     # `-moe.bias 1` fixtures
+    out, regs, dbg = op.competesmoe_forward(x, wg, ks, vs, m["K"], args, m["competition"], bias=bs, o_bias=obs)
     ((out * fx["dy"]).sum() + sum(regs.values())).backward()
     tol = dict(rtol=1e-4, atol=1e-6)
     torch.testing.assert_close(out, fx["out"], **tol)
@@ -76,6 +78,9 @@ def test_pretrain_oracle_matches_reference(name):
         torch.testing.assert_close(regs[k], fx["regs"][k], **tol)
     for got, ref in ((x.grad, "dx"), (wg.grad, "dw_gate"), (ks.grad, "dkeys"), (vs.grad, "dvalues")):
         torch.testing.assert_close(got, fx[ref], **tol)
+    if bs is not None:
+        torch.testing.assert_close(bs.grad, fx["dbias"], **tol)
+        torch.testing.assert_close(obs.grad, fx["do_bias"], **tol)
 
 
 def test_cvmm_restatement_matches_triton_interpreter_run():
