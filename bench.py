@@ -203,10 +203,13 @@ def cpu_reference_step_time(steps: int, warmup: int, tokens: int = TOKENS, devic
     dy = torch.randn(1, tokens, D_MODEL, generator=g).to(device, dt)
     ref_cls, root = _reference_layer() if device == "cpu" else (None, None)
     if ref_cls is not None:
+        import contextlib
+        import io
         torch.manual_seed(0)
         experts = nn.ModuleList([_GLUForward(D_MODEL, FFN) for _ in range(N_EXPERTS)])
-        layer = ref_cls(in_embed_dim=D_MODEL, out_embed_dim=D_MODEL, num_of_experts=N_EXPERTS, num_selected=TOP_K,
-                        expert=experts, args=layer_args())
+        with contextlib.redirect_stdout(io.StringIO()):     # the reference's constructor prints; stdout is the JSON line's
+            layer = ref_cls(in_embed_dim=D_MODEL, out_embed_dim=D_MODEL, num_of_experts=N_EXPERTS, num_selected=TOP_K,
+                            expert=experts, args=layer_args())
         layer.total_steps, layer.step_warm, layer.current_steps = 2, 0, 0
         layer.prob_flips = torch.zeros(2)
         layer.train()
