@@ -51,7 +51,9 @@ struct KParams {
   int glu_f;          // GLU epilogues: F (forward: n == 2F and tiles interleave gate|up; backward: n == F)
   int epi;            // kEpiPlain / kEpiGluFwd / kEpiActBwd / kEpiGluBwd
   int band;           // n-blocks per rasterisation band
-  int raster_m;       // pair / wide ROWS launches: 1 = bands of m-blocks with m fastest (see decode_tile_pair)
+  int raster_m;       // pair / wide ROWS launches: 1 = bands of m-blocks with m fastest (see decode_tile_pair);
+                      // 2 = the same with the bands aligned to the experts' row ranges (needs pad_offsets)
+  int band_cap;       // raster_m == 2: largest band (m-blocks) an expert's row range is swept in
   int num_m_pairs;    // CTA-pair kernel: number of 256-row blocks
   const void* aux;    // backward epilogues: the saved pre-activation z
   long long ldaux;
@@ -1001,7 +1003,34 @@ __device__ __forceinline__ Tile decode_tile_pair(const KParams& p, long long t, 
   const int num_m2 = p.num_m_pairs;
   if (num_n < 0) num_n = p.num_n_blocks;
   if (MODE == CSMOE_GEMM_ROWS) {
-    if (p.raster_m) {
+    if (p.raster_m == 2) {
+      // Bands aligned to the experts: the m-blocks of expert e are swept as ceil(w_e / band_cap) equal bands, m fastest
+      // inside a band, so an expert's weights are fetched from DRAM once per band of ITS rows.  Fixed bands of 8
+      // straddle the expert boundaries (4 experts x ~8.1 blocks at the bench shape) and re-read a whole expert for one
+      // stray m-block: 0.96 GB of DRAM reads for 0.45 GB of operands in the fc1 launch (profiles/r02B_gemm_ncu_full.md).
+      const int q = static_cast<int>(t / num_n);
+      const int e = __ldg(p.tile_expert + 2 * q);
+      if (e < 0) {              // past the last routed row
+        ti.e = -1;
+        ti.mb = q;
+        ti.nb = 0;
+        ti.a_row = q * 256 + rank * kBM;
+        ti.b_row = 0;
+        ti.nkb = p.num_kb;
+        ti.valid = false;
+        return ti;
+      }
+      const int m0 = __ldg(p.pad_offsets + e) >> 8, w_e = (__ldg(p.pad_offsets + e + 1) >> 8) - m0;
+      const int r = static_cast<int>(t - static_cast<long long>(m0) * num_n);
+      const int nbands = (w_e + p.band_cap - 1) / p.band_cap;
+      const int bs = (w_e + nbands - 1) / nbands;
+      const int band_tiles = bs * num_n;
+      const int b = r / band_tiles, rr = r % band_tiles;
+      const int mb0 = b * bs;
+      const int w = min(bs, w_e - mb0);
+      ti.nb = rr / w;
+      ti.mb = m0 + mb0 + rr % w;
+    } else if (p.raster_m) {
       // bands of `band` m-blocks, m fastest inside a band: neighbouring clusters ask for the same B tile at the same time
       const long long band_tiles = static_cast<long long>(p.band) * num_n;
       const int b = static_cast<int>(t / band_tiles);
@@ -1894,10 +1923,16 @@ extern "C" int csmoe_grouped_gemm(const csmoe_gemm_args* a, void* stream_) {
     kp.band = band > 0 ? band : 8;
     // m-fastest raster (neighbouring clusters share the B tile, one expert's weights stay hot in L2 while its row
     // band is swept): DRAM reads of the fc1 launch 1.45 -> 0.75 GB, +7 % (profiles/r01k_gemm_epilogue.md).
-    static const int rm = []() { const char* v = getenv("CSMOE_GEMM_RASTER"); return v ? atoi(v) : 1; }();
+    static const int rm = []() { const char* v = getenv("CSMOE_GEMM_RASTER"); return v ? atoi(v) : 2; }();
     // ... only where the expert changes along m: with one local expert (expert-parallel ranks of the bench shape) every
     // tile shares the same weights and the n-fastest bands are 5 % faster (EP4 step 3.88 vs 3.70 ms).
     kp.raster_m = E >= 2 ? rm : 0;
+    // expert-aligned bands (CSMOE_GEMM_RASTER=2, the default): routed launches whose segments are 256-row aligned
+    static const int cap = []() { const char* v = getenv("CSMOE_GEMM_BAND_CAP"); return v ? atoi(v) : 12; }();
+    kp.band_cap = cap > 0 ? cap : 12;
+    if (kp.raster_m == 2 && !(a->mode == CSMOE_GEMM_ROWS && !a->dense && a->pad_offsets != nullptr && a->tile_expert != nullptr &&
+                              a->row_tile >= 256))
+      kp.raster_m = 1;
   }
   kp.aux = a->aux;
   kp.ldaux = a->ldaux;

@@ -331,6 +331,7 @@ def gemm_rows(a: torch.Tensor, w: torch.Tensor, *, w_is_kn: bool, route: Optiona
         assert route is not None and a.shape[0] == route.row_cap
         m = route.row_cap
         g.tile_expert = _p(route.tile_expert)
+        g.pad_offsets = _p(route.pad_offsets)      # expert-aligned tile raster of the pair kernels
         g.row_tile = route.row_tile
     g.m, g.n, g.k = m, n, k
     g.a, g.lda = _p(a), a.stride(0)

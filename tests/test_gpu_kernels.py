@@ -395,6 +395,8 @@ def test_diversity_and_fused_competition_backward(ops, dtype, E, K, T, t_pad, D)
     {"CSMOE_GEMM_EPI": "direct", "CSMOE_GEMM_WIDE": "0"},    # register-direct epilogue, 256x256 CTA-pair tiles only
     {"CSMOE_GEMM_PAIR": "0"},                                 # single-CTA kernels only
     {"CSMOE_GEMM_EPI": "tma", "CSMOE_GEMM_WIDE": "0"},       # TMA-store epilogue forced wherever legal, pair tiles only
+    {"CSMOE_GEMM_RASTER": "1"},                               # fixed bands of 8 m-blocks instead of expert-aligned bands
+    {"CSMOE_GEMM_BAND_CAP": "2"},                             # expert-aligned bands split into several bands per expert
 ])
 def test_gemm_kernel_variants_in_subprocess(env):
     """The kernel / epilogue variant is picked per launch by shape; the switches that force one variant are read once
