@@ -3,7 +3,7 @@ import sys
 from pathlib import Path
 import torch
 import torch.nn.functional as F
-ROOT = Path(__file__).resolve().parent.parent
+ROOT = Path(__file__).resolve().parent.parent.parent
 sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
 from oracle import pretrain as op
 import test_gpu_full_configs as tf

@@ -2,7 +2,7 @@
 import sys
 from pathlib import Path
 import torch
-sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent.parent))
 from competesmoe_b200 import ops
 from competesmoe_b200.ep import EPGroup, EPLayerState
 

@@ -2,7 +2,7 @@
 import os, sys
 from pathlib import Path
 import torch
-sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent.parent))
 from competesmoe_b200 import ops  # noqa: E402
 dev = torch.device("cuda")
 T, D, E, K, H = 8192, 1024, 64, 8, 128
