@@ -11,7 +11,7 @@ in a second region and reported under "competition"; "mix" is the schedule-weigh
 
 Prints ONE JSON line (rank 0).  `value` = tokens/s with inputs resident in HBM, CUDA-event timed, max over ranks;
 `e2e` = the same through the public nn.Module call with HOST buffers (pinned H2D of tokens and upstream gradient and a
-D2H read of the loss inside the timed region); `roofline` = the grouped GEMM's achieved TFLOP/s from per-launch CUDA
+D2H read of the loss, awaited by the host, inside the timed region); `roofline` = the grouped GEMM's achieved TFLOP/s from per-launch CUDA
 events inside the timed region; `cpu_baseline` = the reference's CPU path timed on this box's host cores on a bounded sample
 (the reference's own modules when /root/reference is importable, else the oracle port -- `kind` says which).
 `configs` = the other BASELINE.json shapes (C1, the C3 sweep, C4, C5) at one GPU, router and competition step each;
@@ -339,7 +339,9 @@ def e2e_region(layer, x_host, dy_host, params, steps, warmup, dist_on, device):
             for _ in range(2)]
     ready = [torch.cuda.Event() for _ in range(2)]
     consumed = [torch.cuda.Event() for _ in range(2)]
-    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+    loss_host = [torch.empty((), dtype=torch.float32).pin_memory() for _ in range(2)]
+    landed = [torch.cuda.Event() for _ in range(2)]
+    seen = []
 
     def prefetch(i):
         x_dev, dy_dev = bufs[i % 2]
@@ -348,6 +350,12 @@ def e2e_region(layer, x_host, dy_host, params, steps, warmup, dist_on, device):
             x_dev.copy_(x_host, non_blocking=True)
             dy_dev.copy_(dy_host, non_blocking=True)
             ready[i % 2].record(copy)
+
+    def read_loss(i):
+        # the host WAITS for step i's loss to land in pinned memory and reads it, one step behind the step it has just
+        # issued (a training loop's logger): every step's result reaches the host inside the timed region
+        landed[i % 2].synchronize()
+        seen.append(float(loss_host[i % 2]))
 
     def run(n):
         for e in consumed:
@@ -360,7 +368,12 @@ def e2e_region(layer, x_host, dy_host, params, steps, warmup, dist_on, device):
             main.wait_event(ready[i % 2])
             aux = one_step(layer, x_dev, dy_dev, params)
             consumed[i % 2].record(main)
-            loss_host.copy_(aux.detach().float(), non_blocking=True)
+            loss_host[i % 2].copy_(aux.detach().float(), non_blocking=True)
+            landed[i % 2].record(main)
+            if i >= 1:
+                read_loss(i - 1)
+        if n >= 1:
+            read_loss(n - 1)
 
     run(warmup)
     if dist_on:
@@ -375,7 +388,10 @@ def e2e_region(layer, x_host, dy_host, params, steps, warmup, dist_on, device):
     if dist_on:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     h2d = x_host.numel() * x_host.element_size() + dy_host.numel() * dy_host.element_size()
-    return float(ms) / steps, h2d, loss_host.numel() * loss_host.element_size()
+    finite = [v == v and abs(v) != float("inf") for v in seen]
+    reads = {"losses_read_on_host": len(seen) - warmup, "last_loss": seen[-1] if seen and finite[-1] else None,
+             "all_finite": all(finite)}
+    return float(ms) / steps, h2d, loss_host[0].numel() * loss_host[0].element_size(), reads
 
 
 # ------------------------------------------------------------------------------------------------ extra sections
@@ -660,7 +676,7 @@ def run_ours(a):
     ms_comp = timed_region(layer, x, dy, params, max(2, a.steps // 2), a.warmup, dist_on)
     # ---- timed region 3: end to end through the module with host buffers (router step)
     set_branch(layer, False)
-    ms_e2e, h2d, d2h = e2e_region(layer, x_host, dy_host, params, a.steps, a.warmup, dist_on, device)
+    ms_e2e, h2d, d2h, e2e_reads = e2e_region(layer, x_host, dy_host, params, a.steps, a.warmup, dist_on, device)
     clocks = sampler.stop() if sampler else None
 
     if rank == 0:
@@ -698,7 +714,10 @@ def run_ours(a):
                                                       "note": "layer.enable_cuda_graphs(): same call replayed from captured graphs"},
             "mix": {"rate_flip": RATE_FLIP, "ms_per_step": mix_ms, "tokens_per_s": tok / (mix_ms * 1e-3)},
             "e2e": {"value": tok / (ms_e2e * 1e-3), "unit": "tokens/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},
+                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e, **e2e_reads,
+                    "note": "H2D of the tokens and the upstream gradient from pinned memory every step (next step's copy "
+                            "overlapped on a second stream); the host waits for and reads every step's loss, one step behind "
+                            "the step it has just issued"},
             "roofline": {"bound": "tensor", "achieved": gemm_tflops, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": gemm_tflops / peak_tf, "achieved_median": gemm_tflops_median,
                          "frac_median": gemm_tflops_median / peak_tf, "traffic": traffic, "kernel": "grouped_gemm_kernel (tcgen05)",
@@ -743,6 +762,14 @@ def run_ours(a):
             line["configs"] = named_configs(device, max(6, a.steps // 2), peak_tf, peak_gbs)
     done.set()
     emit()
+
+    def teardown_watchdog():       # the line is out: a peer that died in a section must not keep this rank in a collective
+        time.sleep(60.0)
+        print(f"bench: rank {rank}: teardown did not return within 60 s, leaving", file=sys.stderr, flush=True)
+        os._exit(0)
+
+    if dist_on:
+        threading.Thread(target=teardown_watchdog, daemon=True).start()
     try:
         if ep_group is not None:
             ep_group.close()
