@@ -467,6 +467,10 @@ def named_configs(device, steps, peak_tf, peak_gbs):
                 gbs = case.bytes_per_token_router() * case.T / (ms * 1e-3) / 1e9
                 e.update(unfused_algorithmic_gbs=round(gbs, 1), frac_of_hbm_peak=round(gbs / peak_gbs, 4))
             entry[nm] = e
+        # schedule-weighted blend: rate_flip 0.07 in the pretraining sweeps' yaml, 0.05 the multimodal default
+        flip = 0.07 if case.kind == "pretrain" else 0.05
+        mix = (1 - flip) * entry["router"]["ms_per_step"] + flip * entry["competition"]["ms_per_step"]
+        entry["mix"] = {"rate_flip": flip, "ms_per_step": round(mix, 4), "tokens_per_s": round(case.T / (mix * 1e-3), 1)}
         out[case.key] = entry
     return out
 
@@ -749,17 +753,25 @@ def run_ours(a):
 
     if a.sections:
         threading.Thread(target=watchdog, daemon=True).start()
-        line["hbm_stage"] = hbm_stage_gbs(device, peak_gbs)
+
+        def guarded(name, fn):       # an exception in an optional section is recorded in the line, it does not cost the line
+            try:
+                line[name] = fn()
+            except Exception as exc:
+                line[name] = {"error": repr(exc)[:500]}
+                print(f"bench: rank {rank}: section {name} failed: {exc!r}"[:600], file=sys.stderr, flush=True)
+
+        guarded("hbm_stage", lambda: hbm_stage_gbs(device, peak_gbs))
         if ep_group is not None:
             line["ep_parity"] = ep_parity_section(device, world, rank, layer, x, dy, params)
         # a failed comparison is raised by every rank together (finish_case) and leaves the ranks aligned: the timing
         # section still runs; any other exception (a CUDA error after a trapped barrier) means the context is gone
-        par = line["ep_parity"] or {}
+        par = line.get("ep_parity") or {}
         if dist_on and 64 % world == 0 and (par.get("ok", True) or par.get("error", "").startswith("AssertionError")):
             line["c4_ep"] = {}
             c4_ep_section(device, world, rank, max(5, a.steps // 2), line["c4_ep"])
         if world == 1:
-            line["configs"] = named_configs(device, max(6, a.steps // 2), peak_tf, peak_gbs)
+            guarded("configs", lambda: named_configs(device, max(6, a.steps // 2), peak_tf, peak_gbs))
     done.set()
     emit()
 
