@@ -731,7 +731,8 @@ def run_ours(a):
             "hbm_stage": None, "configs": None, "ep_parity": None, "c4_ep": None,
         }
         if traffic is not None:
-            line["roofline"]["traffic_source"] = "profiles/gemm_traffic.json (ncu --set full of the same launches, committed; not re-measured in this run)"
+            line["roofline"]["traffic_source"] = ("profiles/gemm_traffic.json (ncu --set full of the same six launches, mean per launch, committed; not re-measured "
+                                                  "in this run; captured before the expert-aligned tile raster, which lowers the fc1 / fc2 / dgrad reads)")
     else:
         line = {}
 
