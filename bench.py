@@ -656,9 +656,10 @@ def run_ours(a):
     gemm_tflops_median = sum(timed[i][2] for i in range(per_step)) / (med_ms * 1e-3) / 1e12 if med_ms > 0 else 0.0
 
     # ---- timed region 1b: the same call with the layer's CUDA-graph mode on (layer.enable_cuda_graphs(): forward and
-    # backward replayed from captured graphs behind the unchanged nn.Module call).  Not available under expert
-    # parallelism (router step; kernels + device-side barriers capture like any launch).  When it works it is the headline
-    # `value`; the eager number stays in the line as "eager".
+    # backward replayed from captured graphs behind the unchanged nn.Module call).  Under expert parallelism the router
+    # step is captured too (the exchange kernels and the device-side barriers capture like any launch); the competition
+    # step of the multimodal layer stays eager there (NCCL all-gather of the expert weights).  When the graphed call is
+    # faster it is the headline `value`; the eager number stays in the line as "eager".
     ms_graph = None
     if a.graphs:
         try:
@@ -799,7 +800,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--graphs", type=int, default=1, help="1: use the layer's CUDA-graph mode where available (single GPU / replicas)")
+    ap.add_argument("--graphs", type=int, default=1, help="1: use the layer's CUDA-graph mode where available")
     ap.add_argument("--sections", type=int, default=1,
                     help="1: also report hbm_stage, the other named configs (N=1), EP parity and C4 expert-parallel (N>1)")
     ap.add_argument("--sections-timeout", type=float, default=240.0,
