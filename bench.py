@@ -18,7 +18,8 @@ events inside the timed region; `cpu_baseline` = the reference's CPU path timed 
 `hbm_stage` = achieved HBM GB/s of the permute / combine kernels; at N > 1 `ep_parity` (tests/ep_worker.py run on the
 job's ranks + a bitwise check of the bench layer against its unsharded copy) and `c4_ep` (configs[3] expert-parallel
 over all N ranks next to the unsharded layer on every GPU).  `--impl reference` times only the CPU path, at the
-requested --steps / --warmup, on all 4096 tokens of the workload.
+requested --steps / --warmup, on all 4096 tokens of the workload; both arms also time the CPU path of the
+pretrain-layer shapes (C1 = BASELINE configs[0], the reference's own CPU-runnable case, and C4) -- `configs.C1/C4.cpu_baseline`.
 """
 from __future__ import annotations
 
@@ -246,6 +247,73 @@ def cpu_reference_step_time(steps: int, warmup: int, tokens: int = TOKENS, devic
     return statistics.median(times), cores, tokens, kind, source
 
 
+# the language-pretraining layer shapes among BASELINE.json's configs
+PRETRAIN_SHAPES = {
+    "C1": dict(what="configs[0]: pretrain layer d=512, 8 experts top-2, expert size 128, batch 8 x seq 512", B=8, N=512, D=512, E=8, K=2, H=128),
+    "C4": dict(what="configs[3]: pretrain LM layer d=1024, 64 experts top-8, expert size 128, 8 x 1024 tokens per GPU", B=8, N=1024, D=1024, E=64, K=8,
+               H=128),
+}
+
+
+def pretrain_port_step_time(key: str, steps: int, warmup: int, device: str = "cpu"):
+    """One router step (fwd + bwd, regularisers included) of the language-pretraining CompeteSMoE layer
+    (moe_pretrain_model/layers/moe/competesmoe.py:524) at a named shape.  The reference computes this layer through its
+    Triton CVMM kernels, which have no CPU path; its CPU-runnable statement is the per-expert-loop form of the same
+    algebra, i.e. oracle/pretrain.py -- `kind` is always "port" here.  fp32 on the CPU; device="cuda" runs
+    the same eager code on the GPU under the reference's bf16 autocast convention (informational).
+    Returns (median s/step, tokens, cores)."""
+    from oracle import pretrain as opr
+    sh = PRETRAIN_SHAPES[key]
+    B, N, D, E, K, H = (sh[k] for k in ("B", "N", "D", "E", "K", "H"))
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    g = torch.Generator().manual_seed(1234)
+    mk = lambda *shape, std=1.0: (torch.randn(*shape, generator=g) * std).to(device).requires_grad_(True)  # noqa: E731
+    w_gate, keys, values = mk(E, D, std=D ** -0.5), mk(E, D, H, std=D ** -0.5), mk(E, H, D, std=(E * H) ** -0.5)
+    x = mk(B, N, D)
+    dy = torch.randn(B, N, D, generator=g).to(device)
+    args = opr.default_args()
+    op_dtype = torch.float32 if device == "cpu" else torch.bfloat16
+    times = []
+    for i in range(warmup + steps):
+        for t in (x, w_gate, keys, values):
+            t.grad = None
+        if device != "cpu":
+            torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out, regs, _ = opr.competesmoe_forward(x, w_gate, keys, values, K, args, False, op_dtype=op_dtype)
+        ((out.float() * dy).sum() + sum(r.float() for r in regs.values())).backward()
+        if device != "cpu":
+            torch.cuda.synchronize()
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    return statistics.median(times), B * N, cores
+
+
+def pretrain_port_entries(steps: int = 3, warmup: int = 1, gpu: bool = False) -> dict:
+    """`cpu_baseline` (and, with gpu=True, `gpu_eager_loop`) of the pretrain-layer shapes, keyed like `configs`."""
+    out = {}
+    for key, sh in PRETRAIN_SHAPES.items():
+        entry = {"what": sh["what"]}
+        try:
+            dt, tokens, cores = pretrain_port_step_time(key, steps, warmup)
+            entry["cpu_baseline"] = {"value": tokens / dt, "unit": "tokens/s", "ms_per_step": dt * 1e3, "cores": cores, "kind": "port",
+                                     "sample": f"{steps} router steps (after {warmup} warm-up) over all {tokens} tokens, fp32, "
+                                               "oracle/pretrain.py (per-expert-loop CVMM: the reference's Triton CVMM has no CPU path)"}
+        except Exception as exc:
+            entry["cpu_baseline"] = {"unavailable": repr(exc)[:300]}
+        if gpu:
+            try:
+                gdt, tokens, _ = pretrain_port_step_time(key, max(steps, 5), 2, device="cuda")
+                entry["gpu_eager_loop"] = {"value": tokens / gdt, "unit": "tokens/s", "ms_per_step": gdt * 1e3, "dtype": "bf16",
+                                           "what": "oracle/pretrain.py run on cuda:0 (eager PyTorch, one matmul per expert, none of "
+                                                   "this repo's kernels)"}
+            except Exception as exc:
+                entry["gpu_eager_loop"] = {"unavailable": repr(exc)[:300]}
+        out[key] = entry
+    return out
+
+
 def run_reference_arm(a):
     """The reference's CPU implementation of the path on this box's host cores: every one of the requested --steps
     (after --warmup) is one fwd + bwd router step over ALL 4096 tokens of the workload (about 2-3 s each on 16 cores)."""
@@ -273,6 +341,8 @@ def run_reference_arm(a):
                                       "what": f"{gsrc} run on cuda:0 (eager PyTorch / cuBLAS, none of this repo's kernels)"}
         except Exception as exc:
             line["gpu_eager_loop"] = {"unavailable": repr(exc)}
+    # the pretrain-layer shapes of BASELINE.json (configs[0] is the reference's own CPU-runnable case) beside the headline
+    line["configs"] = pretrain_port_entries(steps=3, warmup=1, gpu=torch.cuda.is_available())
     print(json.dumps(line), flush=True)
 
 
@@ -774,6 +844,13 @@ def run_ours(a):
             c4_ep_section(device, world, rank, max(5, a.steps // 2), line["c4_ep"])
         if world == 1:
             guarded("configs", lambda: named_configs(device, max(6, a.steps // 2), peak_tf, peak_gbs))
+
+            try:       # the CPU path timed beside the GPU numbers of the pretrain shapes (C1 is required)
+                for key, entry in pretrain_port_entries(steps=3, warmup=1).items():
+                    if isinstance(line.get("configs"), dict) and isinstance(line["configs"].get(key), dict):
+                        line["configs"][key]["cpu_baseline"] = entry["cpu_baseline"]
+            except Exception as exc:
+                line["configs_cpu_error"] = repr(exc)[:300]
     done.set()
     emit()
 

@@ -60,14 +60,14 @@ def cvmm(x: torch.Tensor, sel: Sel, keys: torch.Tensor, op_dtype: torch.dtype = 
     M = ssel.shape[0]
     E, _, N = keys.shape
     dest = sel.sel_index if sel.out_index is None else sel.out_index
-    bounds = torch.searchsorted(ssel.contiguous(), torch.arange(E + 1, dtype=ssel.dtype))
+    bounds = torch.searchsorted(ssel.contiguous(), torch.arange(E + 1, dtype=ssel.dtype, device=ssel.device))
     pieces = []
     for e in range(E):
         lo, hi = int(bounds[e]), int(bounds[e + 1])
         a = x2[sel.sel_index[lo:hi]].to(op_dtype)
         pieces.append(a @ keys[e].to(op_dtype))
     stacked = torch.cat(pieces, dim=0)
-    out = torch.zeros(M, N, dtype=op_dtype).index_copy(0, dest, stacked)
+    out = torch.zeros(M, N, dtype=op_dtype, device=stacked.device).index_copy(0, dest, stacked)
     out = out.view(*sel.sel.shape, N)
     if sel.reduction_weight is not None:
         rw = sel.reduction_weight
@@ -89,7 +89,7 @@ def experts_diversity_loss(topk_outputs: torch.Tensor) -> torch.Tensor:
     """competesmoe.py:330-372."""
     B, N, K, D = topk_outputs.shape
     nrm = F.normalize(topk_outputs.float(), p=2, dim=-1).view(B * N, K, D)
-    sim = torch.bmm(nrm, nrm.transpose(1, 2)) * (1 - torch.eye(K))
+    sim = torch.bmm(nrm, nrm.transpose(1, 2)) * (1 - torch.eye(K, device=nrm.device))
     return sim.mean()
 
 

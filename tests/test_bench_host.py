@@ -116,3 +116,18 @@ def test_e2e_loop_reads_every_loss_on_the_host(monkeypatch):
     want = float((x * layer.w).detach().mean()) + steps + warmup      # the LAST step's loss was the last one read
     assert abs(reads["last_loss"] - want) < 1e-5
     json.dumps(reads)
+
+
+def test_pretrain_shapes_have_a_cpu_baseline(monkeypatch):
+    # the shapes are BASELINE.json configs[0] / configs[3]; shrink the token count so that the check stays cheap
+    assert bench.PRETRAIN_SHAPES["C1"] | {"what": ""} == dict(what="", B=8, N=512, D=512, E=8, K=2, H=128)
+    assert {k: bench.PRETRAIN_SHAPES["C4"][k] for k in ("D", "E", "K", "H")} == dict(D=1024, E=64, K=8, H=128)
+    small = {k: dict(v, B=2, N=64) for k, v in bench.PRETRAIN_SHAPES.items()}
+    monkeypatch.setattr(bench, "PRETRAIN_SHAPES", small)
+    out = bench.pretrain_port_entries(steps=1, warmup=1)
+    assert set(out) == {"C1", "C4"}
+    for entry in out.values():
+        cb = entry["cpu_baseline"]
+        assert cb["kind"] == "port" and cb["unit"] == "tokens/s" and cb["value"] > 0 and cb["cores"] >= 1
+        assert "gpu_eager_loop" not in entry
+    json.dumps(out)
