@@ -10,13 +10,12 @@ row map names, and nothing else may be produced.  A raster that skips or repeats
 this catches it without one.  (The GPU tests run the same launches under every raster and compare results bit for bit.)
 """
 import ctypes as C
-import re
-import shutil
-import subprocess
 from pathlib import Path
 
 import numpy as np
 import pytest
+
+from host_extract import block, compile_host
 
 ROOT = Path(__file__).resolve().parent.parent
 SRC = ROOT / "competesmoe_b200" / "csrc" / "gemm_tcgen05.cu"
@@ -109,42 +108,13 @@ extern "C" long long raster_walk(int mode, int pair, int raster_m, int band, int
 """
 
 
-def _block(text: str, start_pat: str) -> str:
-    """The source from the match of start_pat to the brace that closes the first '{' after it (plus a trailing ';')."""
-    m = re.search(start_pat, text)
-    assert m, f"{start_pat!r} not found in {SRC.name}: the raster test needs updating"
-    i = text.index("{", m.start())
-    depth = 0
-    for j in range(i, len(text)):
-        if text[j] == "{":
-            depth += 1
-        elif text[j] == "}":
-            depth -= 1
-            if depth == 0:
-                end = j + 1
-                if text[end:end + 1] == ";":
-                    end += 1
-                return text[m.start():end]
-    raise AssertionError("unbalanced braces")
-
-
 @pytest.fixture(scope="module")
 def raster(tmp_path_factory):
-    gxx = shutil.which("g++")
-    if gxx is None:
-        pytest.skip("g++ not available")
     text = SRC.read_text()
-    parts = [_block(text, r"struct KParams\s*\{"), _block(text, r"struct Tile\s*\{"),
-             _block(text, r"template <int MODE>\s*__device__ __forceinline__ Tile decode_tile\("),
-             _block(text, r"template <int MODE>\s*__device__ __forceinline__ Tile decode_tile_pair\(")]
-    d = tmp_path_factory.mktemp("raster")
-    src = d / "raster_host.cpp"
-    src.write_text(PRELUDE + "\n".join(parts) + HARNESS)
-    so = d / "raster_host.so"
-    r = subprocess.run([gxx, "-O1", "-std=c++17", "-shared", "-fPIC", "-I", str(ROOT / "include"), str(src), "-o", str(so)],
-                       capture_output=True, text=True)
-    assert r.returncode == 0, f"the tile-decode source no longer compiles for the host:\n{r.stderr[-3000:]}"
-    lib = C.CDLL(str(so))
+    parts = [block(text, r"struct KParams\s*\{", SRC.name), block(text, r"struct Tile\s*\{", SRC.name),
+             block(text, r"template <int MODE>\s*__device__ __forceinline__ Tile decode_tile\(", SRC.name),
+             block(text, r"template <int MODE>\s*__device__ __forceinline__ Tile decode_tile_pair\(", SRC.name)]
+    lib = compile_host(PRELUDE + "\n".join(parts) + HARNESS, tmp_path_factory.mktemp("raster"), "raster_host")
     lib.raster_walk.restype = C.c_longlong
     lib.raster_walk.argtypes = [C.c_int] * 12 + [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     return lib
