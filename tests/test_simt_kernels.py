@@ -14,6 +14,7 @@ import torch
 import torch.nn.functional as F
 
 import simt_host
+import test_gpu_block as gb
 import test_gpu_kernels as gk
 
 from oracle import multimodal as om
@@ -33,6 +34,7 @@ def ops(tmp_path_factory):
     mp.setattr(_ops, "_stream", lambda: None)
     mp.setattr(_ops, "_ROUTER_GEMM", False)           # the tensor-core gate GEMM is not part of the emulated library
     mp.setattr(gk, "DEV", "cpu")
+    mp.setattr(gb, "DEV", "cpu")
     yield _ops
     mp.undo()
 
@@ -94,3 +96,69 @@ def test_activation_fwd_bwd(ops, act, fn, dtype):
 
 def test_glu_fwd_bwd(ops):
     gk.test_glu_fwd_bwd(ops)
+
+
+def test_bias_grad_and_cast(ops):
+    gk.test_bias_grad_and_cast(ops)
+
+
+@pytest.mark.parametrize("act,dense", [("relu", False), ("gelu_tanh", True), ("gelu", False), ("silu", True)])
+def test_act_bwd_bias_matches_separate_kernels(ops, act, dense):
+    gk.test_act_bwd_bias_matches_separate_kernels(ops, act, dense)
+
+
+def test_split_bf16x3_is_exact_to_24_bits(ops):
+    """csmoe_split_f32_bf16x3 (the operands of the fp32-accurate products): hi + mid + lo == x to fp32 precision, each
+    term a bf16 number, hi the round-to-nearest of x."""
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(4099, generator=g) * torch.logspace(-6, 6, 4099)
+    hi, mid, lo = ops.split_bf16x3(x)
+    assert hi.dtype == mid.dtype == lo.dtype == torch.bfloat16
+    assert torch.equal(hi, x.bfloat16())
+    total = hi.double() + mid.double() + lo.double()
+    assert float(((total - x.double()).abs() / x.double().abs().clamp_min(1e-30)).max()) <= 2.0 ** -22
+
+
+# ------------------------------------------------------------------------------------------------ stage 2: competition tail
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_affinity_fwd_bwd(ops, dtype):
+    gk.test_affinity_fwd_bwd(ops, dtype)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("E,K,T,t_pad,D", [(4, 2, 70, 256, 1152), (8, 1, 5, 256, 64), (64, 8, 20, 256, 1024), (6, 3, 40, 256, 264)])
+def test_diversity_and_fused_competition_backward(ops, dtype, E, K, T, t_pad, D):
+    gk.test_diversity_and_fused_competition_backward(ops, dtype, E, K, T, t_pad, D)
+
+
+@pytest.mark.parametrize("sigmoid", [False, True])
+def test_topk_renorm_bwd_and_dense_rows(sigmoid, ops):
+    gk.test_topk_renorm_bwd_and_dense_rows(sigmoid, ops)
+
+
+def test_topk_is_total_on_non_finite_scores(ops):
+    gk.test_topk_is_total_on_non_finite_scores(ops)
+
+
+# ------------------------------------------------------------------------------------------------ losses
+@pytest.mark.parametrize("B,N,E,K", [(1, 300, 4, 2), (3, 200, 8, 2), (2, 130, 64, 8), (2, 77, 33, 5)])
+def test_compete_losses_kernels_match_torch(ops, B, N, E, K):
+    gk.test_compete_losses_kernels_match_torch(B, N, E, K)
+
+
+@pytest.mark.parametrize("B,N,E", [(1, 512, 4), (3, 100, 8), (2, 96, 64)])
+def test_entropy_balance_kernel_matches_pretrain_formula(ops, B, N, E):
+    gk.test_entropy_balance_kernel_matches_pretrain_formula(B, N, E)
+
+
+# ------------------------------------------------------------------------------------------------ block tail
+def test_layernorm_cast_kernel_matches_torch(ops):
+    gb.test_layernorm_cast_kernel_matches_torch()
+
+
+def test_residual_dropout_mask_is_consistent_between_forward_and_backward(ops):
+    gb.test_residual_dropout_mask_is_consistent_between_forward_and_backward()
+
+
+def test_fused_combine_tail_applies_dropout_like_the_stand_alone_kernel(ops):
+    gb.test_fused_combine_tail_applies_dropout_like_the_stand_alone_kernel()
