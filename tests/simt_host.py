@@ -104,7 +104,9 @@ def rewrite(text: str) -> tuple[str, dict]:
     return text, dict(launches=n_launch, dynamic_smem=n_dyn, lanemask=n_lm, tanh_approx=n_th)
 
 
-def build(workdir: Path) -> tuple[C.CDLL, dict]:
+def build(workdir: Path, ref_gemm: bool = False) -> tuple[C.CDLL, dict]:
+    """ref_gemm: also link tests/simt/ref_gemm.cpp, a plain-loop statement of csmoe_grouped_gemm's contract (NOT the
+    tensor-core kernel), so that whole layers can run on the emulator."""
     gxx = shutil.which("g++")
     if gxx is None or not Path("/usr/local/cuda/include/cuda_runtime.h").exists():
         pytest.skip("g++ or the CUDA headers are not available")
@@ -127,9 +129,10 @@ def build(workdir: Path) -> tuple[C.CDLL, dict]:
         obj = src.with_suffix(".o")
         jobs.append((obj, subprocess.Popen([gxx, *flags, "-c", str(src), "-o", str(obj)], stdout=subprocess.PIPE,
                                            stderr=subprocess.STDOUT, text=True)))
-    rt = workdir / "simt_rt.o"
-    jobs.append((rt, subprocess.Popen([gxx, *flags, "-c", str(SIMT / "simt_rt.cpp"), "-o", str(rt)], stdout=subprocess.PIPE,
-                                      stderr=subprocess.STDOUT, text=True)))
+    for extra in ["simt_rt.cpp"] + (["ref_gemm.cpp"] if ref_gemm else []):
+        obj = workdir / (Path(extra).stem + ".o")
+        jobs.append((obj, subprocess.Popen([gxx, *flags, "-c", str(SIMT / extra), "-o", str(obj)], stdout=subprocess.PIPE,
+                                           stderr=subprocess.STDOUT, text=True)))
     for obj, p in jobs:
         out, _ = p.communicate()
         assert p.returncode == 0, f"{obj.name}: the source no longer builds against the SIMT emulator:\n{out[-4000:]}"

@@ -1,0 +1,129 @@
+"""Whole layers on the CPU: the plugins' host code (competesmoe_b200/{multimodal,pretrain,siblings,pretrain_siblings,
+functional,cvmm}.py) driving the shipped non-GEMM kernels on the SIMT emulator (tests/simt/), checked against the golden
+fixtures of the UNMODIFIED reference with the GPU tests' own assertions (the `-m gpu` test functions are called with
+DEV = "cpu").
+
+Two stand-ins, both test infrastructure and both stated here so that nobody reads more into a green run than it says:
+  * csmoe_grouped_gemm is tests/simt/ref_gemm.cpp, a plain-loop statement of the entry point's contract with the
+    kernel's rounding points -- NOT the tcgen05 kernel (which, like the fused sigma-MoE kernels, is tested on the GPU
+    only; the fused path is switched off here and the layers take the grouped-GEMM path);
+  * CUDA autocast does not exist on a CPU-only torch, so `torch.autocast / is_autocast_enabled / get_autocast_dtype` are
+    replaced by a flag for the duration of the module: the pretrain layer reads exactly these to pick its compute dtype.
+What IS verified without a GPU: routing decisions and maps, router / loss / competition-tail / combine kernels as shipped,
+every autograd.Function's wiring (saved tensors, gradient routing, regulariser names), the schedule, checkpoint layout --
+against reference outputs, losses and gradients.
+"""
+import contextlib
+
+import pytest
+import torch
+
+import simt_host
+import test_gpu_fp32 as gf
+import test_gpu_multimodal as gm
+import test_gpu_pretrain as gp
+import test_gpu_pretrain_siblings as gps
+import test_gpu_siblings as gs
+
+
+class _Fresh(dict):
+    """Fixture dict whose tensors come out as fresh copies: on the GPU `fx["x"].to("cuda")` is a copy, on the CPU it is
+    the fixture tensor itself, and `requires_grad_()` on it would leak into the next reader."""
+
+    def __getitem__(self, k):
+        v = dict.__getitem__(self, k)
+        return v.clone() if torch.is_tensor(v) else v
+
+
+@pytest.fixture(scope="module", autouse=True)
+def emulated(tmp_path_factory):
+    lib, stats = simt_host.build(tmp_path_factory.mktemp("simt_layers"), ref_gemm=True)
+    from competesmoe_b200 import _lib, functional, ops
+    mp = pytest.MonkeyPatch()
+    mp.setattr(_lib, "load", lambda: lib)
+    mp.setattr(ops, "_cuda", lambda *ts: None)
+    mp.setattr(ops, "_stream", lambda: None)
+    mp.setattr(ops, "_ROUTER_GEMM", False)
+    mp.setattr(functional, "_SIGMA_FUSED", False)
+    state = {"on": False, "dtype": torch.bfloat16}
+
+    @contextlib.contextmanager
+    def autocast(device_type, dtype=torch.bfloat16, enabled=True, cache_enabled=None):
+        old = dict(state)
+        state.update(on=bool(enabled), dtype=dtype)
+        try:
+            yield
+        finally:
+            state.update(old)
+
+    mp.setattr(torch, "autocast", autocast)
+    mp.setattr(torch, "is_autocast_enabled", lambda *a: state["on"])
+    mp.setattr(torch, "get_autocast_dtype", lambda dev: state["dtype"])
+    mp.setattr(torch.cuda, "is_current_stream_capturing", lambda: False)
+    for mod in (gm, gp, gs, gps, gf):
+        mp.setattr(mod, "DEV", "cpu")
+        if hasattr(mod, "load_golden"):
+            mp.setattr(mod, "load_golden", (lambda f: lambda name: _Fresh(f(name)))(mod.load_golden))
+    yield
+    mp.undo()
+
+
+# ------------------------------------------------------------------------------------------------ multimodal plugin
+@pytest.mark.parametrize("name", gm.CASES)
+def test_multimodal_layer_matches_reference_golden(name):
+    gm.test_layer_matches_reference_golden(name)
+
+
+def test_multimodal_upcycled_experts_analytic_kats():
+    gm.test_upcycled_experts_analytic_kats()
+
+
+def test_multimodal_checkpoint_layout_and_fused_storage():
+    gm.test_checkpoint_layout_and_fused_storage()
+
+
+def test_multimodal_inference_path_takes_router_branch_without_aux():
+    gm.test_inference_path_takes_router_branch_without_aux()
+
+
+@pytest.mark.parametrize("name", gs.SIB)
+def test_multimodal_sibling_matches_reference_golden(name):
+    gs.test_sibling_matches_reference_golden(name)
+
+
+# ------------------------------------------------------------------------------------------------ pretrain plugin
+@pytest.mark.parametrize("name", gp.PT)
+def test_pretrain_layer_matches_reference_golden(name):
+    gp.test_pretrain_layer_matches_reference_golden(name)
+
+
+def test_cvmm_op_both_call_patterns():
+    gp.test_cvmm_op_both_call_patterns()
+
+
+def test_cvmm_moe_attention_call_patterns():
+    gp.test_cvmm_moe_attention_call_patterns()
+
+
+def test_cvmm_rejects_index_tensors_it_cannot_express():
+    gp.test_cvmm_rejects_index_tensors_it_cannot_express()
+
+
+def test_moe_attention_projection_layer_is_att():
+    gp.test_moe_attention_projection_layer_is_att()
+
+
+@pytest.mark.parametrize("name", gps.PTSIB)
+def test_pretrain_sibling_matches_reference_golden(name):
+    gps.test_pretrain_sibling_matches_reference_golden(name)
+
+
+# ------------------------------------------------------------------------------------------------ fp32 callers (rtol 1e-4)
+@pytest.mark.parametrize("name", ["mm_siglip_router_f32", "mm_glu_router_f32", "mm_siglip_comp_f32", "mm_projector_comp_f32"])
+def test_multimodal_fp32_module_matches_reference_at_1e4(name):
+    gf.test_multimodal_fp32_module_matches_reference_at_1e4(name)
+
+
+@pytest.mark.parametrize("name", ["pt_router_f32", "pt_comp_tribrid_f32"])
+def test_pretrain_fp32_without_autocast_matches_reference_at_1e4(name):
+    gf.test_pretrain_fp32_without_autocast_matches_reference_at_1e4(name)
