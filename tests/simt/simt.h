@@ -98,6 +98,7 @@ Ctx& ctx();
 void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body);
 
 inline void* dyn_smem() { return g_dyn_smem.data(); }
+unsigned long long wall_ns();
 
 // every participating lane deposits 8 bytes and gets all 32 back
 inline void exchange(uint64_t mine, uint64_t (&all)[32]) {
@@ -130,8 +131,9 @@ inline T from_bits(uint64_t u) {
 
 inline void __syncthreads() { simt::g_block_bar.wait(); }
 inline void __syncwarp(unsigned = 0xffffffffu) { simt::ctx().warp->bar.wait(); }
-inline void __threadfence() {}
+inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 inline void __threadfence_block() {}
+inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 
 template <typename T>
 inline T __shfl_sync(unsigned, T v, int src, int width = 32) {

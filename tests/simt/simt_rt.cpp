@@ -2,6 +2,8 @@
 // functions of the emulated kernels call (see simt.h).
 #include "simt.h"
 
+#include <ctime>
+
 namespace simt {
 
 dim3 g_grid, g_block;
@@ -56,6 +58,12 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& bod
   for (auto& th : pool) th.join();
 }
 
+unsigned long long wall_ns() {
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return static_cast<unsigned long long>(ts.tv_sec) * 1000000000ull + static_cast<unsigned long long>(ts.tv_nsec);
+}
+
 }  // namespace simt
 
 static int sms() {
@@ -81,4 +89,8 @@ cudaError_t cudaDeviceSynchronize(void) { return cudaSuccess; }
 cudaError_t cudaMalloc(void** p, size_t n) { *p = malloc(n); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
 cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
 cudaError_t cudaFuncSetAttribute(const void*, cudaFuncAttribute, int) { return cudaSuccess; }
+// peer memory: the emulated "ranks" share anonymous mappings created by the test; CUDA IPC itself is not emulated
+cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t*, void*) { return cudaErrorNotSupported; }
+cudaError_t cudaIpcOpenMemHandle(void**, cudaIpcMemHandle_t, unsigned int) { return cudaErrorNotSupported; }
+cudaError_t cudaIpcCloseMemHandle(void*) { return cudaErrorNotSupported; }
 }

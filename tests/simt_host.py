@@ -5,7 +5,9 @@ The sources are used as they are, with three mechanical rewrites (no kernel code
   * `kernel<<<grid, block, smem, stream>>>(args);`  ->  `simt::launch(grid, block, smem, [&]() { kernel(args); });`
   * `extern __shared__ T name[];`                   ->  `T* name = reinterpret_cast<T*>(simt::dyn_smem());`
   * the three inline-PTX one-liners these files contain (`%lanemask_lt`, `tanh.approx.f32`) -> their C++ meaning.
-The tensor-core / TMA kernels (gemm_tcgen05.cu, sigma_ffn.cu) and the peer-memory kernels (ep.cu) are not built here.
+ep.cu (peer-memory kernels) is built on request: its release / acquire flag accesses become __atomic builtins, and the
+"ranks" of a test are forked processes that share anonymous mappings.  The tensor-core / TMA kernels (gemm_tcgen05.cu,
+sigma_ffn.cu) are not built here.
 """
 from __future__ import annotations
 
@@ -100,11 +102,17 @@ def rewrite(text: str) -> tuple[str, dict]:
     text, n_lm = re.subn(r'asm\("mov\.u32 %0, %%lanemask_lt;"\s*:\s*"=r"\((\w+)\)\);',
                          r"\1 = (1u << simt::ctx().lane) - 1u;", text)
     text, n_th = re.subn(r'asm\("tanh\.approx\.f32 %0, %1;"\s*:\s*"=f"\((\w+)\)\s*:\s*"f"\((.+?)\)\);', r"\1 = tanhf(\2);", text)
+    # ep.cu: system-scope release / acquire on the barrier flags, the wall clock of the bounded spin
+    text, n_st = re.subn(r'asm volatile\("st\.release\.sys\.global\.s32 \[%0\], %1;"\s*::\s*"l"\((\w+)\),\s*"r"\((\w+)\)\s*:\s*"memory"\);',
+                         r"__atomic_store_n(\1, \2, __ATOMIC_RELEASE);", text)
+    text, n_ld = re.subn(r'asm volatile\("ld\.acquire\.sys\.global\.s32 %0, \[%1\];"\s*:\s*"=r"\((\w+)\)\s*:\s*"l"\((\w+)\)\s*:\s*"memory"\);',
+                         r"\1 = __atomic_load_n(\2, __ATOMIC_ACQUIRE);", text)
+    text, n_gt = re.subn(r'asm volatile\("mov\.u64 %0, %globaltimer;"\s*:\s*"=l"\((\w+)\)\);', r"\1 = simt::wall_ns();", text)
     assert "asm(" not in text and "asm volatile" not in text, "inline PTX the emulator has no rewrite for"
-    return text, dict(launches=n_launch, dynamic_smem=n_dyn, lanemask=n_lm, tanh_approx=n_th)
+    return text, dict(launches=n_launch, dynamic_smem=n_dyn, lanemask=n_lm, tanh_approx=n_th, sys_flags=n_st + n_ld + n_gt)
 
 
-def build(workdir: Path, ref_gemm: bool = False) -> tuple[C.CDLL, dict]:
+def build(workdir: Path, ref_gemm: bool = False, ep: bool = False) -> tuple[C.CDLL, dict]:
     """ref_gemm: also link tests/simt/ref_gemm.cpp, a plain-loop statement of csmoe_grouped_gemm's contract (NOT the
     tensor-core kernel), so that whole layers can run on the emulator."""
     gxx = shutil.which("g++")
@@ -122,7 +130,7 @@ def build(workdir: Path, ref_gemm: bool = False) -> tuple[C.CDLL, dict]:
     flags = ["-O1", "-std=c++17", "-fPIC", "-pthread", "-w", "-I", str(inc), "-I", str(SIMT), "-I", str(ROOT / "include"),
              "-I", "/usr/local/cuda/include", "-include", "simt.h"]
     jobs = []
-    for name in SOURCES:
+    for name in SOURCES + (["ep.cu"] if ep else []):     # ep: the peer-memory kernels (ranks = forked processes, shared mappings)
         t, stats[name] = rewrite((CSRC / name).read_text())
         src = workdir / (Path(name).stem + "_simt.cpp")
         src.write_text(t)
