@@ -13,8 +13,8 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cmath>
-#include <condition_variable>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -43,40 +43,19 @@
 
 namespace simt {
 
-// Barrier whose participant count shrinks when a thread leaves the kernel early (`if (t >= T) return;`).
+// Barrier whose participant count shrinks when a thread leaves the kernel early (`if (t >= T) return;`).  Sleeping is a
+// futex wait on the generation counter (simt_rt.cpp, C++20 atomic wait): no mutex is re-acquired on wake-up, which is
+// what made a condition-variable barrier of 256 threads cost milliseconds.
 class Barrier {
  public:
-  void reset(int n) {
-    std::lock_guard<std::mutex> lk(m_);
-    expected_ = n;
-    waiting_ = 0;
-  }
-  void wait() {
-    std::unique_lock<std::mutex> lk(m_);
-    const unsigned long g = gen_;
-    if (++waiting_ >= expected_) {
-      waiting_ = 0;
-      ++gen_;
-      cv_.notify_all();
-    } else {
-      cv_.wait(lk, [&] { return gen_ != g; });
-    }
-  }
-  void drop() {
-    std::lock_guard<std::mutex> lk(m_);
-    --expected_;
-    if (expected_ > 0 && waiting_ >= expected_) {
-      waiting_ = 0;
-      ++gen_;
-      cv_.notify_all();
-    }
-  }
+  void reset(int n);
+  void wait();
+  void drop();
 
  private:
   std::mutex m_;
-  std::condition_variable cv_;
   int expected_ = 0, waiting_ = 0;
-  unsigned long gen_ = 0;
+  std::atomic<unsigned> gen_{0};
 };
 
 struct Warp {

@@ -139,14 +139,15 @@ def build(workdir: Path, ref_gemm: bool = False, ep: bool = False) -> tuple[C.CD
                                            stderr=subprocess.STDOUT, text=True)))
     for extra in ["simt_rt.cpp"] + (["ref_gemm.cpp"] if ref_gemm else []):
         obj = workdir / (Path(extra).stem + ".o")
-        jobs.append((obj, subprocess.Popen([gxx, *flags, "-c", str(SIMT / extra), "-o", str(obj)], stdout=subprocess.PIPE,
+        std = ["-std=c++20"] if extra == "simt_rt.cpp" else []      # C++20 atomic wait / notify in the barrier
+        jobs.append((obj, subprocess.Popen([gxx, *flags, *std, "-c", str(SIMT / extra), "-o", str(obj)], stdout=subprocess.PIPE,
                                            stderr=subprocess.STDOUT, text=True)))
     for obj, p in jobs:
         out, _ = p.communicate()
         assert p.returncode == 0, f"{obj.name}: the source no longer builds against the SIMT emulator:\n{out[-4000:]}"
         objs.append(str(obj))
     so = workdir / "libcsmoe_simt.so"
-    r = subprocess.run([gxx, "-shared", "-pthread", "-Wl,-Bsymbolic", "-o", str(so), *objs], capture_output=True, text=True)
+    r = subprocess.run([gxx, "-shared", "-pthread", "-Wl,-Bsymbolic", "-o", str(so), *objs, "-lrt"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
     lib = C.CDLL(str(so))
     from competesmoe_b200 import _lib

@@ -15,6 +15,7 @@ TEST INFRASTRUCTURE: no NVLink, no memory-model fidelity beyond acquire / releas
 import ctypes as C
 import mmap
 import multiprocessing as mp
+import os
 import traceback
 
 import numpy as np
@@ -47,12 +48,14 @@ def ptr(a):
     return None if a is None else a.ctypes.data
 
 
+# numpy only: these run inside forked children, where torch's OpenMP pool (threads of the parent) must not be touched
 def bf16_bits(x: np.ndarray) -> np.ndarray:
-    return torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).bfloat16().view(torch.int16).numpy().view(np.uint16)
+    u = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32)
+    return ((u + 0x7FFF + ((u >> 16) & 1)) >> 16).astype(np.uint16)          # round to nearest even (finite inputs)
 
 
 def bf16_vals(bits: np.ndarray) -> np.ndarray:
-    return torch.from_numpy(bits.view(np.int16).copy()).view(torch.bfloat16).float().numpy()
+    return (bits.astype(np.uint32) << 16).view(np.float32)
 
 
 @pytest.fixture(scope="module")
@@ -247,3 +250,35 @@ def test_gather_push_and_reduce_pull(lib, P):
             acc += grad(r)[rank * n:(rank + 1) * n]
         assert np.array_equal(out32, acc), f"rank {rank}: reduced slice"
         assert np.array_equal(out16, bf16_vals(bf16_bits(acc)))
+
+
+# ------------------------------------------------------------------------------------------------ whole layers, sharded
+@pytest.mark.parametrize("world", [8] + ([2, 4] if os.environ.get("CSMOE_SIMT_FULL", "0") == "1" else []))
+def test_sharded_layers_match_unsharded_layers_on_emulated_ranks(tmp_path_factory, world):
+    """tests/ep_worker.py's parity cases (what `bench.py --gpus N` reports as `ep_parity`) on `world` emulated ranks:
+    spawned processes, gloo, the peer-memory kernels on shared memory.  Both plugins, both steps, both exchange modes of
+    the pretrain layer, ragged token counts.  The builder's GPU budget ended before an 8-GPU run of this code.
+    CSMOE_SIMT_FULL=1 adds group sizes 2 and 4 and the pretrain competition step (about five more minutes)."""
+    import socket
+    import simt_ep_worker
+    workdir = tmp_path_factory.mktemp(f"simt_ep_layers{world}")
+    simt_host.build(workdir, ref_gemm=True, ep=True)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=simt_ep_worker.rank_main, args=(r, world, port, str(workdir / "libcsmoe_simt.so"), q))
+             for r in range(world)]
+    for p in procs:
+        p.start()
+    try:
+        for _ in range(world):
+            rank, ok, res = q.get(timeout=900)
+            assert ok, f"rank {rank} failed:\n{res}"
+            assert len(res) >= 5 and res[-1] == "ragged glu top-1", res
+    finally:
+        for p in procs:
+            p.join(timeout=10)
+            if p.is_alive():
+                p.kill()
