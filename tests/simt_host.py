@@ -112,9 +112,13 @@ def rewrite(text: str) -> tuple[str, dict]:
     return text, dict(launches=n_launch, dynamic_smem=n_dyn, lanemask=n_lm, tanh_approx=n_th, sys_flags=n_st + n_ld + n_gt)
 
 
-def build(workdir: Path, ref_gemm: bool = False, ep: bool = False) -> tuple[C.CDLL, dict]:
+def build(workdir: Path, ref_gemm: bool = False, ep: bool = False, tsan: bool = False, load: bool = True):
     """ref_gemm: also link tests/simt/ref_gemm.cpp, a plain-loop statement of csmoe_grouped_gemm's contract (NOT the
     tensor-core kernel), so that whole layers can run on the emulator."""
+    import os
+    prebuilt = os.environ.get("CSMOE_SIMT_PREBUILT")       # scripts/simt_racecheck.py: a ThreadSanitizer build of everything
+    if prebuilt and load:
+        return _bind(C.CDLL(prebuilt), {"prebuilt": prebuilt, "ep.cu": dict(sys_flags=3, launches=12)})
     gxx = shutil.which("g++")
     if gxx is None or not Path("/usr/local/cuda/include/cuda_runtime.h").exists():
         pytest.skip("g++ or the CUDA headers are not available")
@@ -127,7 +131,10 @@ def build(workdir: Path, ref_gemm: bool = False, ep: bool = False) -> tuple[C.CD
     for h in sorted(CSRC.glob("*.h")):
         t, stats[h.name] = rewrite(h.read_text())
         (inc / h.name).write_text(t)
-    flags = ["-O1", "-std=c++17", "-fPIC", "-pthread", "-w", "-I", str(inc), "-I", str(SIMT), "-I", str(ROOT / "include"),
+    # tsan: ThreadSanitizer build.  The barriers are std::mutex / std::atomic / sem_t, which TSAN models, so two emulated
+    # CUDA threads touching the same shared or global word without a __syncthreads / __syncwarp / collective in between
+    # are reported as a data race (scripts/simt_racecheck.py; needs LD_PRELOAD=libtsan.so, hence load=False)
+    flags = (["-fsanitize=thread", "-g"] if tsan else []) + ["-O1", "-std=c++17", "-fPIC", "-pthread", "-w", "-I", str(inc), "-I", str(SIMT), "-I", str(ROOT / "include"),
              "-I", "/usr/local/cuda/include", "-include", "simt.h"]
     jobs = []
     for name in SOURCES + (["ep.cu"] if ep else []):     # ep: the peer-memory kernels (ranks = forked processes, shared mappings)
@@ -147,9 +154,14 @@ def build(workdir: Path, ref_gemm: bool = False, ep: bool = False) -> tuple[C.CD
         assert p.returncode == 0, f"{obj.name}: the source no longer builds against the SIMT emulator:\n{out[-4000:]}"
         objs.append(str(obj))
     so = workdir / "libcsmoe_simt.so"
-    r = subprocess.run([gxx, "-shared", "-pthread", "-Wl,-Bsymbolic", "-o", str(so), *objs, "-lrt"], capture_output=True, text=True)
+    r = subprocess.run([gxx, "-shared", "-pthread", *(["-fsanitize=thread"] if tsan else []), "-Wl,-Bsymbolic", "-o", str(so), *objs, "-lrt"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
-    lib = C.CDLL(str(so))
+    if not load:
+        return so, stats
+    return _bind(C.CDLL(str(so)), stats)
+
+
+def _bind(lib: C.CDLL, stats: dict):
     from competesmoe_b200 import _lib
     bound = 0
     for name, (res, args) in _lib._SIGNATURES.items():
