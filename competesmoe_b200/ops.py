@@ -44,8 +44,22 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+_NO_STORAGE = {}
+
+
 def _p(t: Optional[torch.Tensor]):
-    return None if t is None else t.data_ptr()
+    """Device address of a tensor.  A tensor with zero elements has no storage (data_ptr() == 0), which the library
+    would reject as a NULL pointer although every entry point returns early on zero sizes: such a tensor gets a valid
+    address that is never dereferenced (a rank without tokens, an empty micro-batch)."""
+    if t is None:
+        return None
+    p = t.data_ptr()
+    if p == 0:
+        d = _NO_STORAGE.get(t.device)
+        if d is None:
+            d = _NO_STORAGE[t.device] = torch.zeros(64, dtype=torch.uint8, device=t.device)
+        return d.data_ptr()
+    return p
 
 
 def _call(name: str, *args, kernels: int = 1) -> None:

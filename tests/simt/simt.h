@@ -71,6 +71,7 @@ struct Ctx {
 };
 
 extern dim3 g_grid, g_block;
+extern cudaError_t g_last_error;
 extern Barrier g_block_bar;
 extern std::vector<uint8_t> g_dyn_smem;
 Ctx& ctx();

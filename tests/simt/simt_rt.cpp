@@ -116,9 +116,17 @@ void worker_loop(Worker* w, int t) {
 }
 }  // namespace
 
+cudaError_t g_last_error = cudaSuccess;
+
 void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body) {
   const int nthreads = static_cast<int>(block.x * block.y * block.z);
-  if (nthreads <= 0 || grid.x * grid.y * grid.z == 0) return;
+  // what the CUDA runtime rejects, the emulator rejects: an empty grid or block, more than 1024 threads per block, more
+  // dynamic shared memory than an sm_100 block can opt in to, grid.y / grid.z beyond 65535
+  if (nthreads <= 0 || nthreads > 1024 || grid.x == 0 || grid.y == 0 || grid.z == 0 || grid.y > 65535 || grid.z > 65535 ||
+      smem > 227 * 1024) {
+    g_last_error = cudaErrorInvalidConfiguration;
+    return;
+  }
   if (g_pool_pid != getpid()) {          // first launch, or a forked child: the parent's pool threads do not exist here
     g_pool.clear();
     sem_init(&g_done, 0, 0);
@@ -174,9 +182,15 @@ static int sms() {
 }
 
 extern "C" {
-cudaError_t cudaGetLastError(void) { return cudaSuccess; }
-cudaError_t cudaPeekAtLastError(void) { return cudaSuccess; }
-const char* cudaGetErrorString(cudaError_t) { return "simt: no error"; }
+cudaError_t cudaGetLastError(void) {
+  const cudaError_t e = simt::g_last_error;
+  simt::g_last_error = cudaSuccess;
+  return e;
+}
+cudaError_t cudaPeekAtLastError(void) { return simt::g_last_error; }
+const char* cudaGetErrorString(cudaError_t e) {
+  return e == cudaSuccess ? "no error" : (e == cudaErrorInvalidConfiguration ? "invalid configuration argument (simt)" : "error (simt)");
+}
 cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
 cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr a, int) {
   *v = a == cudaDevAttrMultiProcessorCount ? sms() : (a == cudaDevAttrComputeCapabilityMajor ? 10 : 0);

@@ -57,6 +57,27 @@ def test_route_build_empty_input(ops):
     assert bool((r.tile_expert == -1).all())
 
 
+def test_ops_accept_empty_inputs(ops):
+    """Zero tokens (an empty micro-batch, a rank without tokens): the op-level calls return empty / all-padding results
+    instead of failing on the NULL data pointer of a tensor without storage."""
+    T, D, E, K = 0, 64, 4, 2
+    x = torch.zeros(T, D, dtype=torch.bfloat16, device=DEV)
+    wg = torch.randn(E, D, device=DEV).bfloat16()
+    logits, probs, tw, ti = ops.router_fwd(x, wg, K)
+    assert logits.shape == (0, E) and probs.shape == (0, E) and tw.shape == (0, K) and ti.shape == (0, K)
+    route = ops.route_build(ti, E)
+    assert int(route.counts.sum()) == 0 and bool((route.row_to_slot == -1).all())
+    xp = ops.gather_rows(x, route)
+    assert xp.shape == (route.row_cap, D) and not bool(xp.any())
+    w = torch.zeros(T, K, device=DEV)
+    assert ops.combine_fwd(xp, route.slot_to_row, route.sel, w, T, K).shape == (0, D)
+    assert ops.scatter_reduce(xp, route.slot_to_row, T, K).shape == (0, D)
+    assert ops.combine_bwd_w(xp, x, route.slot_to_row, T, K).shape == (0, K)
+    assert ops.cast_bf16(torch.zeros(0, device=DEV)).numel() == 0
+    wts, idx = ops.topk_renorm(torch.zeros(0, E, device=DEV), K)
+    assert wts.shape == (0, K) and idx.shape == (0, K)
+
+
 # ------------------------------------------------------------------------------------------------ router
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
 @pytest.mark.parametrize("T,D,E,K", [(257, 64, 4, 2), (1024, 1152, 4, 2), (512, 1024, 64, 8), (300, 512, 8, 2), (64, 3072, 4, 2)])

@@ -50,6 +50,10 @@ def test_route_build_empty_input(ops):
     gk.test_route_build_empty_input(ops)
 
 
+def test_ops_accept_empty_inputs(ops):
+    gk.test_ops_accept_empty_inputs(ops)
+
+
 def test_route_build_clamps_out_of_range_ids(ops):
     sel = torch.tensor([[0, 9], [-3, 1], [2, 2]], dtype=torch.int32)
     r = ops.route_build(sel, 3)
