@@ -86,6 +86,11 @@ def test_multimodal_inference_path_takes_router_branch_without_aux():
     gm.test_inference_path_takes_router_branch_without_aux()
 
 
+@pytest.mark.parametrize("competition", [False, True])
+def test_multimodal_skewed_routing_hot_and_empty_experts(competition):
+    gm.check_skewed_routing_hot_and_empty_experts_against_oracle(competition)
+
+
 @pytest.mark.parametrize("name", gs.SIB)
 def test_multimodal_sibling_matches_reference_golden(name):
     gs.test_sibling_matches_reference_golden(name)
