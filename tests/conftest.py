@@ -14,10 +14,21 @@ GOLDEN = ROOT / "tests" / "golden"
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line(
+        "markers", "first_hw_run: a GPU test written after the round's GPU budget was spent -- green on the SIMT emulator "
+        "(tests/test_simt_*.py), never yet run on a B200.  On a CUDA box it runs LAST and as a non-strict xfail, so a "
+        "surprise on its first hardware run is reported (xfail / XPASS) without costing the tests already seen green "
+        "under `pytest -x`.  Drop the marker once the test has been seen on hardware.")
 
 
 def pytest_collection_modifyitems(config, items):
     if torch.cuda.is_available():
+        first = [it for it in items if "first_hw_run" in it.keywords]
+        if first:
+            seen = [it for it in items if "first_hw_run" not in it.keywords]
+            for it in first:
+                it.add_marker(pytest.mark.xfail(strict=False, reason="first hardware run of this test"))
+            items[:] = seen + first
         return
     skip = pytest.mark.skip(reason="no CUDA device")
     for item in items:

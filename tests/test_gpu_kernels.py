@@ -57,6 +57,7 @@ def test_route_build_empty_input(ops):
     assert bool((r.tile_expert == -1).all())
 
 
+@pytest.mark.first_hw_run
 def test_ops_accept_empty_inputs(ops):
     """Zero tokens (an empty micro-batch, a rank without tokens): the op-level calls return empty / all-padding results
     instead of failing on the NULL data pointer of a tensor without storage."""

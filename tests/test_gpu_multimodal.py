@@ -154,9 +154,11 @@ def test_siglip_shape_against_oracle(competition):
     assert_close_rms(xg.grad[agree.to(DEV)], xr.grad[agree], 4e-2, "dx")
 
 
-def check_skewed_routing_hot_and_empty_experts_against_oracle(competition):
-    """Not collected here: written after the round's GPU budget was spent, so it runs on the SIMT emulator only
-    (tests/test_simt_layers.py); rename to test_* once it has been seen green on a B200.
+@pytest.mark.first_hw_run
+@pytest.mark.parametrize("competition", [False, True])
+def test_skewed_routing_hot_and_empty_experts_against_oracle(competition):
+    """Written after the round's GPU budget was spent: green on the SIMT emulator (tests/test_simt_layers.py), first
+    hardware run pending (marker first_hw_run, tests/conftest.py).
     SURVEY.md 8(d) skewed-routing variant: +2.0 on the gate logit of expert 0 for every token (a hot expert) and two
     experts the router never picks (empty segments in the row space, zero weight gradients).  Layer vs oracle: routing,
     output, dx, gate gradient, every expert's weight gradients."""

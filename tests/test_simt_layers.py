@@ -88,7 +88,7 @@ def test_multimodal_inference_path_takes_router_branch_without_aux():
 
 @pytest.mark.parametrize("competition", [False, True])
 def test_multimodal_skewed_routing_hot_and_empty_experts(competition):
-    gm.check_skewed_routing_hot_and_empty_experts_against_oracle(competition)
+    gm.test_skewed_routing_hot_and_empty_experts_against_oracle(competition)
 
 
 @pytest.mark.parametrize("name", gs.SIB)
