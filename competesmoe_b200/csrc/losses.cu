@@ -272,6 +272,202 @@ __global__ void dense_rows_kernel(const int32_t* __restrict__ idx, long long T, 
   rows[i] = static_cast<int32_t>(static_cast<long long>(idx[i]) * t_pad + i / K);
 }
 
+// ------------------------------------------------------------------------------------------------ more than 64 experts
+// 64 < E <= 256 (the pretrain plugin's default -moe.n_experts is 128): the kernels above with C = 4 or 8 experts per lane
+// (lane l: experts l, l + 32, ...), partials [3 * 32 C + 4] per CTA.  Same formulas, same fixed-order reductions.
+constexpr int kMaxEWide = 256;
+__host__ __device__ constexpr int part_stride(int C) { return 3 * 32 * C + 4; }
+inline int wide_slots(int E) { return E <= 128 ? 4 : 8; }
+
+template <int C>
+__device__ __forceinline__ void warp_softmax_wide(const float (&a)[C], int lane, int E, float (&q)[C]) {
+  float m = -INFINITY;
+#pragma unroll
+  for (int c = 0; c < C; ++c)
+    if (lane + 32 * c < E) m = fmaxf(m, a[c]);
+  m = warp_max(m);
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    q[c] = lane + 32 * c < E ? expf(a[c] - m) : 0.f;
+    s += q[c];
+  }
+  const float d = warp_sum(s);
+#pragma unroll
+  for (int c = 0; c < C; ++c) q[c] = q[c] / d;
+}
+
+template <bool kEntropyOnly, int C>
+__global__ void __launch_bounds__(kWarps * 32)
+losses_stage1_wide(const float* __restrict__ p, const float* __restrict__ aff, const int32_t* __restrict__ aff_idx,
+                   const int32_t* __restrict__ gate_idx, long long N, int E, int K, float* __restrict__ q,
+                   float* __restrict__ part) {
+  constexpr int kP = part_stride(C), kME = 32 * C;
+  __shared__ float sh[kWarps][kP];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long b = blockIdx.y;
+  float cq[C], cn[C], cr[C], s0 = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int c = 0; c < C; ++c) cq[c] = cn[c] = cr[c] = 0.f;
+  for (int i = 0; i < kTokPerWarp; ++i) {
+    const long long n = static_cast<long long>(blockIdx.x) * kTokPerBlock + warp * kTokPerWarp + i;
+    if (n >= N) break;
+    const long long t = b * N + n;
+    if constexpr (kEntropyOnly) {
+#pragma unroll
+      for (int c = 0; c < C; ++c)
+        if (lane + 32 * c < E) cr[c] += p[t * E + lane + 32 * c];
+    } else {
+    float pv[C], av[C], qv[C], rv[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const bool h = lane + 32 * c < E;
+      pv[c] = h ? p[t * E + lane + 32 * c] : 0.f;
+      av[c] = h ? aff[t * E + lane + 32 * c] : 0.f;
+    }
+    warp_softmax_wide<C>(av, lane, E, qv);
+    warp_softmax_wide<C>(qv, lane, E, rv);      // entropy_balance applies log_softmax to the affinity SOFTMAX (:542-545)
+    const int32_t* ai = aff_idx + t * K;
+    const int32_t* gi = gate_idx != nullptr ? gate_idx + t * K : nullptr;
+    const int top1 = ai[0];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const int e = lane + 32 * c;
+      const bool h = e < E;
+      if (h) q[t * E + e] = qv[c];
+      const float d = pv[c] - qv[c];
+      const float sq = h ? d * d : 0.f;
+      s0 += sq;
+      s1 += in_list(ai, K, e) ? sq : 0.f;
+      if (gi != nullptr) s2 += in_list(gi, K, e) ? sq : 0.f;
+      cq[c] += qv[c];
+      cr[c] += rv[c];
+      cn[c] += (top1 == e) ? 1.f : 0.f;
+    }
+    }
+  }
+  s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2);
+  float* mine = sh[warp];
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    mine[lane + 32 * c] = cq[c];
+    mine[kME + lane + 32 * c] = cn[c];
+    mine[2 * kME + lane + 32 * c] = cr[c];
+  }
+  if (lane == 0) { mine[3 * kME] = s0; mine[3 * kME + 1] = s1; mine[3 * kME + 2] = s2; mine[3 * kME + 3] = 0.f; }
+  __syncthreads();
+  float* out = part + (b * gridDim.x + blockIdx.x) * kP;
+  for (int j = threadIdx.x; j < kP; j += kWarps * 32) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) s += sh[w][j];
+    out[j] = s;
+  }
+}
+
+// stage 2 with the partial stride as an argument (me = 32 C experts per section)
+template <bool kEntropyOnly>
+__global__ void __launch_bounds__(1024)
+losses_stage2_wide(const float* __restrict__ part, int me, int chunks, long long B, long long N, int E, int K,
+                   float* __restrict__ colq, float* __restrict__ cnt, float* __restrict__ colr, float* __restrict__ losses) {
+  __shared__ float red[33];
+  const int kP = 3 * me + 4;
+  float bal = 0.f, ent = 0.f, s0 = 0.f, s1 = 0.f, s2 = 0.f;
+  const float invN = 1.f / static_cast<float>(N);
+  for (long long i = threadIdx.x; i < B * E; i += blockDim.x) {
+    const long long b = i / E;
+    const int e = static_cast<int>(i % E);
+    float a = 0.f, c = 0.f, r = 0.f;
+    for (int ch = 0; ch < chunks; ++ch) {
+      const float* pp = part + (b * chunks + ch) * kP;
+      if (!kEntropyOnly) { a += pp[e]; c += pp[me + e]; }
+      r += pp[2 * me + e];
+    }
+    if (!kEntropyOnly) { colq[i] = a; cnt[i] = c; bal += (a * invN) * (c * invN); }
+    colr[i] = r;
+    const float m = r * invN;
+    ent += m > 0.f ? m * logf(m) : 0.f;
+  }
+  if (!kEntropyOnly) {
+    for (long long i = threadIdx.x; i < B * chunks; i += blockDim.x) {
+      const float* pp = part + i * kP + 3 * me;
+      s0 += pp[0]; s1 += pp[1]; s2 += pp[2];
+    }
+  }
+  bal = block_sum_1024(bal, red);
+  ent = block_sum_1024(ent, red);
+  if (!kEntropyOnly) {
+    s0 = block_sum_1024(s0, red);
+    s1 = block_sum_1024(s1, red);
+    s2 = block_sum_1024(s2, red);
+  }
+  if (threadIdx.x == 0) {
+    const float T = static_cast<float>(B) * static_cast<float>(N);
+    if (kEntropyOnly) {
+      losses[0] = ent / static_cast<float>(B);
+    } else {
+      losses[0] = s0 / (T * E);
+      losses[1] = s1 / (T * K);
+      losses[2] = s2 / (T * K);
+      losses[3] = bal / (static_cast<float>(B) * E) * static_cast<float>(E) * static_cast<float>(E);
+      losses[4] = ent / static_cast<float>(B);
+    }
+  }
+}
+
+template <int C>
+__global__ void __launch_bounds__(kWarps * 32)
+losses_bwd_wide_kernel(const float* __restrict__ p, const float* __restrict__ q, const int32_t* __restrict__ aff_idx,
+                       const int32_t* __restrict__ gate_idx, const float* __restrict__ cnt, const float* __restrict__ colr,
+                       const float* __restrict__ g, long long B, long long N, int E, int K, float* __restrict__ dp,
+                       float* __restrict__ daff) {
+  const int lane = threadIdx.x & 31;
+  const long long t = static_cast<long long>(blockIdx.x) * kWarps + (threadIdx.x >> 5);
+  const long long T = B * N;
+  if (t >= T) return;
+  const long long b = t / N;
+  const float g0 = g[0], g1 = g[1], g2 = g[2], g3 = g[3], g4 = g[4];
+  const float Tf = static_cast<float>(T), Nf = static_cast<float>(N), Bf = static_cast<float>(B);
+  const int32_t* ai = aff_idx + t * K;
+  const int32_t* gi = gate_idx != nullptr ? gate_idx + t * K : nullptr;
+  const float kb = g3 * static_cast<float>(E) / (Bf * Nf * Nf);
+  float qv[C], dq[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    const int e = lane + 32 * c;
+    const bool h = e < E;
+    const float pv = h ? p[t * E + e] : 0.f;
+    qv[c] = h ? q[t * E + e] : 0.f;
+    float cf = g0 / (Tf * E);
+    if (in_list(ai, K, e)) cf += g1 / (Tf * K);
+    if (gi != nullptr && in_list(gi, K, e)) cf += g2 / (Tf * K);
+    if (h) dp[t * E + e] = 2.f * (pv - qv[c]) * cf;
+    dq[c] = h ? kb * cnt[b * E + e] : 0.f;
+  }
+  if (g4 != 0.f) {
+    float rv[C], dr[C], dt = 0.f;
+    warp_softmax_wide<C>(qv, lane, E, rv);
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const int e = lane + 32 * c;
+      const bool h = e < E;
+      const float m = h ? colr[b * E + e] / Nf : 1.f;
+      dr[c] = h && m > 0.f ? g4 * (logf(m) + 1.f) / (Bf * Nf) : 0.f;
+      dt += rv[c] * dr[c];
+    }
+    const float dot = warp_sum(dt);
+#pragma unroll
+    for (int c = 0; c < C; ++c) dq[c] += rv[c] * (dr[c] - dot);
+  }
+  float dtq = 0.f;
+#pragma unroll
+  for (int c = 0; c < C; ++c) dtq += qv[c] * dq[c];
+  const float dotq = warp_sum(dtq);
+#pragma unroll
+  for (int c = 0; c < C; ++c)
+    if (lane + 32 * c < E) daff[t * E + lane + 32 * c] = qv[c] * (dq[c] - dotq);
+}
+
 inline int n_chunks(int64_t N) { return static_cast<int>((N + kTokPerBlock - 1) / kTokPerBlock); }
 
 }  // namespace
@@ -281,22 +477,34 @@ using namespace csmoe;
 
 extern "C" int64_t csmoe_losses_workspace_bytes(int64_t B, int64_t N, int32_t E) {
   if (B <= 0 || N <= 0 || E <= 0) return -1;
-  return B * n_chunks(N) * static_cast<int64_t>(kPart) * static_cast<int64_t>(sizeof(float));
+  if (E > kMaxEWide) return -1;
+  const int64_t stride = E > kMaxE ? part_stride(wide_slots(E)) : kPart;
+  return B * n_chunks(N) * stride * static_cast<int64_t>(sizeof(float));
 }
 
 extern "C" int csmoe_losses_fwd(const float* p, const float* aff, const int32_t* aff_idx, const int32_t* gate_idx, int64_t B,
                                 int64_t N, int32_t E, int32_t K, float* q, float* colq, float* cnt, float* colr,
                                 float* losses, void* workspace, void* stream_) {
   CSMOE_CHECK_ARG(p && aff && aff_idx && q && colq && cnt && colr && losses && workspace, "csmoe_losses_fwd: NULL argument");
-  CSMOE_CHECK_ARG(B >= 1 && N >= 1 && B <= 65535 && E >= 1 && E <= kMaxE && K >= 1 && K <= kMaxK && K <= E,
-                  "csmoe_losses_fwd: need 1 <= B <= 65535, N >= 1, E <= %d, K <= min(E, %d)", kMaxE, kMaxK);
+  CSMOE_CHECK_ARG(B >= 1 && N >= 1 && B <= 65535 && E >= 1 && E <= kMaxEWide && K >= 1 && K <= kMaxK && K <= E,
+                  "csmoe_losses_fwd: need 1 <= B <= 65535, N >= 1, E <= %d, K <= min(E, %d)", kMaxEWide, kMaxK);
   cudaStream_t stream = as_stream(stream_);
   const int chunks = n_chunks(N);
   float* part = reinterpret_cast<float*>(workspace);
-  losses_stage1<false><<<dim3(chunks, static_cast<unsigned>(B)), kWarps * 32, 0, stream>>>(p, aff, aff_idx, gate_idx, N, E,
-                                                                                           K, q, part);
-  CSMOE_CHECK_LAUNCH();
-  losses_stage2<false><<<1, 1024, 0, stream>>>(part, chunks, B, N, E, K, colq, cnt, colr, losses);
+  const dim3 grid(chunks, static_cast<unsigned>(B));
+  if (E > 128) {
+    losses_stage1_wide<false, 8><<<grid, kWarps * 32, 0, stream>>>(p, aff, aff_idx, gate_idx, N, E, K, q, part);
+    CSMOE_CHECK_LAUNCH();
+    losses_stage2_wide<false><<<1, 1024, 0, stream>>>(part, 256, chunks, B, N, E, K, colq, cnt, colr, losses);
+  } else if (E > kMaxE) {
+    losses_stage1_wide<false, 4><<<grid, kWarps * 32, 0, stream>>>(p, aff, aff_idx, gate_idx, N, E, K, q, part);
+    CSMOE_CHECK_LAUNCH();
+    losses_stage2_wide<false><<<1, 1024, 0, stream>>>(part, 128, chunks, B, N, E, K, colq, cnt, colr, losses);
+  } else {
+    losses_stage1<false><<<grid, kWarps * 32, 0, stream>>>(p, aff, aff_idx, gate_idx, N, E, K, q, part);
+    CSMOE_CHECK_LAUNCH();
+    losses_stage2<false><<<1, 1024, 0, stream>>>(part, chunks, B, N, E, K, colq, cnt, colr, losses);
+  }
   CSMOE_CHECK_LAUNCH();
   return CSMOE_OK;
 }
@@ -305,10 +513,15 @@ extern "C" int csmoe_losses_bwd(const float* p, const float* q, const int32_t* a
                                 const float* cnt, const float* colr, const float* g, int64_t B, int64_t N, int32_t E,
                                 int32_t K, float* dp, float* daff, void* stream_) {
   CSMOE_CHECK_ARG(p && q && aff_idx && cnt && colr && g && dp && daff, "csmoe_losses_bwd: NULL argument");
-  CSMOE_CHECK_ARG(B >= 1 && N >= 1 && E >= 1 && E <= kMaxE && K >= 1 && K <= kMaxK, "csmoe_losses_bwd: bad sizes");
+  CSMOE_CHECK_ARG(B >= 1 && N >= 1 && E >= 1 && E <= kMaxEWide && K >= 1 && K <= kMaxK, "csmoe_losses_bwd: bad sizes");
   const int64_t T = B * N;
-  losses_bwd_kernel<<<static_cast<unsigned>((T + kWarps - 1) / kWarps), kWarps * 32, 0, as_stream(stream_)>>>(
-      p, q, aff_idx, gate_idx, cnt, colr, g, B, N, E, K, dp, daff);
+  const unsigned grid = static_cast<unsigned>((T + kWarps - 1) / kWarps);
+  if (E > 128)
+    losses_bwd_wide_kernel<8><<<grid, kWarps * 32, 0, as_stream(stream_)>>>(p, q, aff_idx, gate_idx, cnt, colr, g, B, N, E, K, dp, daff);
+  else if (E > kMaxE)
+    losses_bwd_wide_kernel<4><<<grid, kWarps * 32, 0, as_stream(stream_)>>>(p, q, aff_idx, gate_idx, cnt, colr, g, B, N, E, K, dp, daff);
+  else
+    losses_bwd_kernel<<<grid, kWarps * 32, 0, as_stream(stream_)>>>(p, q, aff_idx, gate_idx, cnt, colr, g, B, N, E, K, dp, daff);
   CSMOE_CHECK_LAUNCH();
   return CSMOE_OK;
 }
@@ -316,14 +529,24 @@ extern "C" int csmoe_losses_bwd(const float* p, const float* q, const int32_t* a
 extern "C" int csmoe_entropy_balance_fwd(const float* probs, int64_t B, int64_t N, int32_t E, float* colr, float* loss,
                                          void* workspace, void* stream_) {
   CSMOE_CHECK_ARG(probs && colr && loss && workspace, "csmoe_entropy_balance_fwd: NULL argument");
-  CSMOE_CHECK_ARG(B >= 1 && N >= 1 && B <= 65535 && E >= 1 && E <= kMaxE, "csmoe_entropy_balance_fwd: bad sizes");
+  CSMOE_CHECK_ARG(B >= 1 && N >= 1 && B <= 65535 && E >= 1 && E <= kMaxEWide, "csmoe_entropy_balance_fwd: bad sizes");
   cudaStream_t stream = as_stream(stream_);
   const int chunks = n_chunks(N);
   float* part = reinterpret_cast<float*>(workspace);
-  losses_stage1<true><<<dim3(chunks, static_cast<unsigned>(B)), kWarps * 32, 0, stream>>>(probs, nullptr, nullptr, nullptr,
-                                                                                          N, E, 1, nullptr, part);
-  CSMOE_CHECK_LAUNCH();
-  losses_stage2<true><<<1, 1024, 0, stream>>>(part, chunks, B, N, E, 1, nullptr, nullptr, colr, loss);
+  const dim3 grid(chunks, static_cast<unsigned>(B));
+  if (E > 128) {
+    losses_stage1_wide<true, 8><<<grid, kWarps * 32, 0, stream>>>(probs, nullptr, nullptr, nullptr, N, E, 1, nullptr, part);
+    CSMOE_CHECK_LAUNCH();
+    losses_stage2_wide<true><<<1, 1024, 0, stream>>>(part, 256, chunks, B, N, E, 1, nullptr, nullptr, colr, loss);
+  } else if (E > kMaxE) {
+    losses_stage1_wide<true, 4><<<grid, kWarps * 32, 0, stream>>>(probs, nullptr, nullptr, nullptr, N, E, 1, nullptr, part);
+    CSMOE_CHECK_LAUNCH();
+    losses_stage2_wide<true><<<1, 1024, 0, stream>>>(part, 128, chunks, B, N, E, 1, nullptr, nullptr, colr, loss);
+  } else {
+    losses_stage1<true><<<grid, kWarps * 32, 0, stream>>>(probs, nullptr, nullptr, nullptr, N, E, 1, nullptr, part);
+    CSMOE_CHECK_LAUNCH();
+    losses_stage2<true><<<1, 1024, 0, stream>>>(part, chunks, B, N, E, 1, nullptr, nullptr, colr, loss);
+  }
   CSMOE_CHECK_LAUNCH();
   return CSMOE_OK;
 }

@@ -397,16 +397,20 @@ router_bwd_dx_kernel(const T* __restrict__ wg, const float* __restrict__ probs, 
   if (h0) dl_out[t * E + lane] = l0;
   if (h1) dl_out[t * E + lane + 32] = l1;
   if (dx == nullptr) return;
-  for (int d = lane * 8; d < D; d += 256) {
+  for (int d0 = 0; d0 < D; d0 += 256) {     // every lane runs every pass: the shuffle reads dl from lane e & 31, which
+    const int d = d0 + lane * 8;            // must be there also when that lane has no columns left (D % 256 != 0)
+    const bool on = d < D;
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     for (int e = 0; e < E; ++e) {
       const float g = __shfl_sync(0xffffffffu, e < 32 ? l0 : l1, e & 31);
-      float wv[8];
-      load8(wg + static_cast<long long>(e) * D + d, wv);
+      if (on) {
+        float wv[8];
+        load8(wg + static_cast<long long>(e) * D + d, wv);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = fmaf(g, wv[j], acc[j]);
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(g, wv[j], acc[j]);
+      }
     }
-    store8(dx + t * D + d, acc);
+    if (on) store8(dx + t * D + d, acc);
   }
 }
 
@@ -487,6 +491,371 @@ router_bwd_dw_stage2(const float* __restrict__ partial, int n_chunks, long long 
   }
 }
 
+// ------------------------------------------------------------------------------------------------ more than 64 experts
+// The kernels above keep two experts per lane (E <= 64: every shipped sweep, and the shapes that were measured).  The
+// pretrain plugin's own default is -moe.n_experts 128 (transformer_lm_mixin.py:32), so for 64 < E <= 256 the same
+// algorithms run with C = 4 or 8 experts per lane: lane l holds experts l, l + 32, ..., l + 32 (C - 1).  Rounding points,
+// the order of every reduction and the tie-break (highest value, then lowest expert index) are the ones stated above.
+constexpr int kMaxEWide = 256;
+
+template <int C>
+__device__ __forceinline__ float slot_of(const float (&v)[C], int c) {   // v[c] for a warp-uniform c, without local memory
+  float r = v[0];
+#pragma unroll
+  for (int i = 1; i < C; ++i)
+    if (c == i) r = v[i];
+  return r;
+}
+
+template <int C>
+__device__ __forceinline__ void warp_topk_wide(const float (&v)[C], int lane, int E, int K, float (&out_v)[kMaxK],
+                                               int (&out_i)[kMaxK]) {
+  bool taken[C];
+  unsigned key[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    taken[c] = lane + 32 * c >= E;
+    key[c] = order_key(v[c]);
+  }
+#pragma unroll
+  for (int k = 0; k < kMaxK; ++k) {
+    if (k >= K) break;
+    unsigned bk = 0u;            // below the key of every valid value
+    int bi = 0x7fffffff;
+#pragma unroll
+    for (int c = 0; c < C; ++c)  // slots in ascending expert order: a later one wins only when strictly larger
+      if (!taken[c] && (bi == 0x7fffffff || key[c] > bk)) {
+        bk = key[c];
+        bi = lane + 32 * c;
+      }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned ok = __shfl_xor_sync(0xffffffffu, bk, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ok > bk || (ok == bk && oi < bi)) {
+        bk = ok;
+        bi = oi;
+      }
+    }
+    if (bi == 0x7fffffff) bi = k < E ? k : 0;   // unreachable for K <= E
+    out_v[k] = __shfl_sync(0xffffffffu, slot_of<C>(v, bi >> 5), bi & 31);
+    out_i[k] = bi;
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+      if (bi == lane + 32 * c) taken[c] = true;
+  }
+}
+
+// softmax of the C values per lane (invalid slots excluded); returns the probabilities in place
+template <int C>
+__device__ __forceinline__ void warp_softmax_wide(float (&l)[C], int lane, int E) {
+  float m = -INFINITY;
+#pragma unroll
+  for (int c = 0; c < C; ++c)
+    if (lane + 32 * c < E) m = fmaxf(m, l[c]);
+  m = warp_max(m);
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    l[c] = lane + 32 * c < E ? expf(l[c] - m) : 0.f;
+    s += l[c];
+  }
+  const float denom = warp_sum(s);
+#pragma unroll
+  for (int c = 0; c < C; ++c) l[c] = l[c] / denom;
+}
+
+template <typename T>
+__device__ __forceinline__ void write_topk(const float (&tv)[kMaxK], const int (&ti)[kMaxK], int K, long long t,
+                                           float* __restrict__ topk_w, int32_t* __restrict__ topk_idx) {
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < kMaxK; ++k)
+    if (k < K) s += tv[k];
+  s = round_as(s, static_cast<const T*>(nullptr));
+#pragma unroll
+  for (int k = 0; k < kMaxK; ++k)
+    if (k < K) {
+      topk_w[t * K + k] = tv[k] / s;
+      topk_idx[t * K + k] = ti[k];
+    }
+}
+
+template <typename T, int C>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+router_fwd_wide_kernel(const T* __restrict__ x, const T* __restrict__ wg, long long Tn, int D, int E, int K,
+                       T* __restrict__ logits, float* __restrict__ probs, float* __restrict__ topk_w,
+                       int32_t* __restrict__ topk_idx) {
+  const int lane = threadIdx.x & 31;
+  const long long t = static_cast<long long>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (t >= Tn) return;
+  const T* xr = x + t * D;
+  float l[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) l[c] = 0.f;
+  constexpr int EC = 4;
+  for (int e0 = 0; e0 < E; e0 += EC) {
+    float acc[EC] = {0.f, 0.f, 0.f, 0.f};
+    for (int d = lane * 8; d < D; d += 256) {
+      float xv[8];
+      load8(xr + d, xv);
+#pragma unroll
+      for (int i = 0; i < EC; ++i) {
+        if (e0 + i < E) {
+          float wv[8];
+          load8(wg + static_cast<long long>(e0 + i) * D + d, wv);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[i] = fmaf(xv[j], wv[j], acc[i]);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < EC; ++i) {
+      const float s = round_as(warp_sum(acc[i]), static_cast<const T*>(nullptr));
+      const int e = e0 + i;
+#pragma unroll
+      for (int c = 0; c < C; ++c)
+        if (e < E && e == lane + 32 * c) l[c] = s;
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < C; ++c)
+    if (lane + 32 * c < E) logits[t * E + lane + 32 * c] = static_cast<T>(l[c]);
+  warp_softmax_wide<C>(l, lane, E);
+#pragma unroll
+  for (int c = 0; c < C; ++c)
+    if (lane + 32 * c < E) probs[t * E + lane + 32 * c] = l[c];
+  float tv[kMaxK];
+  int ti[kMaxK];
+  warp_topk_wide<C>(l, lane, E, K, tv, ti);
+  if (lane == 0) write_topk<T>(tv, ti, K, t, topk_w, topk_idx);
+}
+
+template <typename T, int C>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+router_from_logits_wide_kernel(const T* __restrict__ logits, long long Tn, int E, int K, float* __restrict__ probs,
+                               float* __restrict__ topk_w, int32_t* __restrict__ topk_idx) {
+  const int lane = threadIdx.x & 31;
+  const long long t = static_cast<long long>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (t >= Tn) return;
+  float l[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) l[c] = lane + 32 * c < E ? static_cast<float>(logits[t * E + lane + 32 * c]) : -INFINITY;
+  warp_softmax_wide<C>(l, lane, E);
+#pragma unroll
+  for (int c = 0; c < C; ++c)
+    if (lane + 32 * c < E) probs[t * E + lane + 32 * c] = l[c];
+  float tv[kMaxK];
+  int ti[kMaxK];
+  warp_topk_wide<C>(l, lane, E, K, tv, ti);
+  if (lane == 0) write_topk<T>(tv, ti, K, t, topk_w, topk_idx);
+}
+
+template <int C>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+topk_renorm_wide_kernel(const float* __restrict__ scores, long long Tn, int E, int K, int mode, int round_dtype,
+                        float* __restrict__ topk_w, int32_t* __restrict__ topk_idx) {
+  const int lane = threadIdx.x & 31;
+  const long long t = static_cast<long long>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (t >= Tn) return;
+  const bool sigmoid = (mode & 1) != 0, round_out = (mode & 2) != 0, bf = round_dtype == CSMOE_BF16;
+  float v[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    v[c] = lane + 32 * c < E ? scores[t * E + lane + 32 * c] : 0.f;
+    if (sigmoid) {
+      v[c] = 1.f / (1.f + expf(-v[c]));
+      if (bf) v[c] = bf16_round(v[c]);
+    }
+  }
+  float tv[kMaxK];
+  int ti[kMaxK];
+  warp_topk_wide<C>(v, lane, E, K, tv, ti);
+  if (lane == 0) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < kMaxK; ++k)
+      if (k < K) s += tv[k];
+    if (bf) s = bf16_round(s);
+#pragma unroll
+    for (int k = 0; k < kMaxK; ++k)
+      if (k < K) {
+        float w = tv[k] / s;
+        if (round_out && bf) w = bf16_round(w);
+        topk_w[t * K + k] = w;
+        topk_idx[t * K + k] = ti[k];
+      }
+  }
+}
+
+// stage 1 of the balance / z losses (same partial layout as router_aux_stage1: [chunk][2E + 1]); stage 2 is shared
+template <typename T, int C>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+router_aux_stage1_wide(const T* __restrict__ logits, const float* __restrict__ probs, const int32_t* __restrict__ topk_idx,
+                       int N, int E, int K, int chunks_per_b, float* __restrict__ partial, float* __restrict__ lse_out) {
+  extern __shared__ float sh[];  // [8 warps][2E + 1]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x / chunks_per_b, ch = blockIdx.x % chunks_per_b;
+  const int stride = 2 * E + 1;
+  float sp[C], sc[C], zz = 0.f;
+#pragma unroll
+  for (int c = 0; c < C; ++c) sp[c] = sc[c] = 0.f;
+  const int n0 = ch * kAuxChunk + warp * 32;
+  for (int i = 0; i < 32; ++i) {
+    const int n = n0 + i;
+    if (n >= N) break;
+    const long long t = static_cast<long long>(b) * N + n;
+    float m = -INFINITY, lg[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      lg[c] = lane + 32 * c < E ? static_cast<float>(logits[t * E + lane + 32 * c]) : -INFINITY;
+      m = fmaxf(m, lg[c]);
+    }
+    m = warp_max(m);
+    float se = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) se += lane + 32 * c < E ? expf(lg[c] - m) : 0.f;
+    se = warp_sum(se);
+    const float lse = m + logf(se);
+    if (lane == 0 && lse_out) lse_out[t] = lse;
+    zz += lse * lse;
+    const int top1 = topk_idx[t * K];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      if (lane + 32 * c < E) sp[c] += probs[t * E + lane + 32 * c];
+      if (top1 == lane + 32 * c) sc[c] += 1.f;
+    }
+  }
+  float* mine = sh + warp * stride;
+#pragma unroll
+  for (int c = 0; c < C; ++c)
+    if (lane + 32 * c < E) {
+      mine[lane + 32 * c] = sp[c];
+      mine[E + lane + 32 * c] = sc[c];
+    }
+  if (lane == 0) mine[2 * E] = zz;
+  __syncthreads();
+  for (int i = threadIdx.x; i < stride; i += blockDim.x) {
+    float a = 0.f;
+#pragma unroll
+    for (int w = 0; w < kWarpsPerBlock; ++w) a += sh[w * stride + i];
+    partial[static_cast<long long>(blockIdx.x) * stride + i] = a;
+  }
+}
+
+template <typename T, int C>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+router_bwd_dx_wide_kernel(const T* __restrict__ wg, const float* __restrict__ probs, const float* __restrict__ topk_w,
+                          const int32_t* __restrict__ topk_idx, const float* __restrict__ dtw,
+                          const float* __restrict__ dprobs_in, const float* __restrict__ dlogits_in,
+                          const float* __restrict__ lse, const float* __restrict__ cnt, const float* __restrict__ g_losses,
+                          long long Tn, int N, int B, int D, int E, int K, float* __restrict__ dl_out, T* __restrict__ dx) {
+  const int lane = threadIdx.x & 31;
+  const long long t = static_cast<long long>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (t >= Tn) return;
+  float p[C], d[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    const bool h = lane + 32 * c < E;
+    p[c] = h ? probs[t * E + lane + 32 * c] : 0.f;
+    d[c] = (h && dprobs_in) ? dprobs_in[t * E + lane + 32 * c] : 0.f;
+  }
+  if (g_losses != nullptr && cnt != nullptr) {
+    const int b = static_cast<int>(t / N);
+    const float coef = g_losses[0] * static_cast<float>(E) / (static_cast<float>(B) * N * N);
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+      if (lane + 32 * c < E) d[c] += coef * cnt[b * E + lane + 32 * c];
+  }
+  if (dtw != nullptr) {
+    float s = 0.f, dot = 0.f;
+    for (int k = 0; k < K; ++k) {
+      const int i = topk_idx[t * K + k];
+      s += probs[t * E + i];
+      dot += dtw[t * K + k] * topk_w[t * K + k];
+    }
+    for (int k = 0; k < K; ++k) {
+      const int i = topk_idx[t * K + k];
+      const float g = (dtw[t * K + k] - dot) / s;
+#pragma unroll
+      for (int c = 0; c < C; ++c)
+        if (i == lane + 32 * c) d[c] += g;
+    }
+  }
+  float in = 0.f;
+#pragma unroll
+  for (int c = 0; c < C; ++c) in += d[c] * p[c];
+  const float inner = warp_sum(in);
+  const float gz = (g_losses != nullptr && lse != nullptr) ? g_losses[1] * 2.f * lse[t] / static_cast<float>(Tn) : 0.f;
+  float l[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    const bool h = lane + 32 * c < E;
+    l[c] = p[c] * (d[c] - inner);
+    if (dlogits_in != nullptr && h) l[c] += dlogits_in[t * E + lane + 32 * c];
+    if (g_losses != nullptr && lse != nullptr) l[c] += gz * p[c];
+    l[c] = round_as(l[c], static_cast<const T*>(nullptr));
+    if (h) dl_out[t * E + lane + 32 * c] = l[c];
+  }
+  if (dx == nullptr) return;
+  for (int d0 = 0; d0 < D; d0 += 256) {     // every lane runs every pass (the shuffle needs the whole warp)
+    const int dd = d0 + lane * 8;
+    const bool on = dd < D;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int e = 0; e < E; ++e) {
+      const float g = __shfl_sync(0xffffffffu, slot_of<C>(l, e >> 5), e & 31);
+      if (on) {
+        float wv[8];
+        load8(wg + static_cast<long long>(e) * D + dd, wv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(g, wv[j], acc[j]);
+      }
+    }
+    if (on) store8(dx + t * D + dd, acc);
+  }
+}
+
+// host side: C = 4 up to 128 experts, 8 up to 256
+template <typename T>
+void launch_router_fwd_wide(unsigned grid, cudaStream_t stream, const T* x, const T* wg, long long Tn, int D, int E, int K,
+                            T* logits, float* probs, float* topk_w, int32_t* topk_idx) {
+  if (E <= 128)
+    router_fwd_wide_kernel<T, 4><<<grid, kWarpsPerBlock * 32, 0, stream>>>(x, wg, Tn, D, E, K, logits, probs, topk_w, topk_idx);
+  else
+    router_fwd_wide_kernel<T, 8><<<grid, kWarpsPerBlock * 32, 0, stream>>>(x, wg, Tn, D, E, K, logits, probs, topk_w, topk_idx);
+}
+
+template <typename T>
+void launch_router_from_logits_wide(unsigned grid, cudaStream_t stream, const T* logits, long long Tn, int E, int K,
+                                    float* probs, float* topk_w, int32_t* topk_idx) {
+  if (E <= 128)
+    router_from_logits_wide_kernel<T, 4><<<grid, kWarpsPerBlock * 32, 0, stream>>>(logits, Tn, E, K, probs, topk_w, topk_idx);
+  else
+    router_from_logits_wide_kernel<T, 8><<<grid, kWarpsPerBlock * 32, 0, stream>>>(logits, Tn, E, K, probs, topk_w, topk_idx);
+}
+
+template <typename T>
+void launch_router_aux_stage1_wide(unsigned grid, size_t smem, cudaStream_t stream, const T* logits, const float* probs,
+                                   const int32_t* topk_idx, int N, int E, int K, int chunks, float* partial, float* lse) {
+  if (E <= 128)
+    router_aux_stage1_wide<T, 4><<<grid, kWarpsPerBlock * 32, smem, stream>>>(logits, probs, topk_idx, N, E, K, chunks, partial, lse);
+  else
+    router_aux_stage1_wide<T, 8><<<grid, kWarpsPerBlock * 32, smem, stream>>>(logits, probs, topk_idx, N, E, K, chunks, partial, lse);
+}
+
+template <typename T>
+void launch_router_bwd_dx_wide(unsigned grid, cudaStream_t stream, const T* wg, const float* probs, const float* topk_w,
+                               const int32_t* topk_idx, const float* dtw, const float* dprobs, const float* dlogits,
+                               const float* lse, const float* cnt, const float* g_losses, long long Tn, int N, int B, int D,
+                               int E, int K, float* dl, T* dx) {
+  if (E <= 128)
+    router_bwd_dx_wide_kernel<T, 4><<<grid, kWarpsPerBlock * 32, 0, stream>>>(wg, probs, topk_w, topk_idx, dtw, dprobs, dlogits,
+                                                                               lse, cnt, g_losses, Tn, N, B, D, E, K, dl, dx);
+  else
+    router_bwd_dx_wide_kernel<T, 8><<<grid, kWarpsPerBlock * 32, 0, stream>>>(wg, probs, topk_w, topk_idx, dtw, dprobs, dlogits,
+                                                                               lse, cnt, g_losses, Tn, N, B, D, E, K, dl, dx);
+}
+
 }  // namespace
 }  // namespace csmoe
 
@@ -495,14 +864,24 @@ using namespace csmoe;
 extern "C" int csmoe_router_fwd(const void* x, const void* wg, int32_t x_dtype, int64_t T, int32_t D, int32_t E,
                                 int32_t K, void* logits, float* probs, float* topk_w, int32_t* topk_idx, void* stream_) {
   CSMOE_CHECK_ARG(x && wg && logits && probs && topk_w && topk_idx, "csmoe_router_fwd: NULL pointer");
-  CSMOE_CHECK_ARG(E >= 1 && E <= kMaxE, "csmoe_router_fwd: E must be in [1, %d], got %d", kMaxE, E);
+  CSMOE_CHECK_ARG(E >= 1 && E <= kMaxEWide, "csmoe_router_fwd: E must be in [1, %d], got %d", kMaxEWide, E);
   CSMOE_CHECK_ARG(K >= 1 && K <= kMaxK && K <= E, "csmoe_router_fwd: K must be in [1, min(E, %d)], got %d", kMaxK, K);
   CSMOE_CHECK_ARG(D > 0 && D % 8 == 0, "csmoe_router_fwd: D must be a positive multiple of 8");
   CSMOE_CHECK_ARG(T >= 0, "csmoe_router_fwd: T must be >= 0");
   if (T == 0) return CSMOE_OK;
   const unsigned grid = static_cast<unsigned>((T + kWarpsPerBlock - 1) / kWarpsPerBlock);
   cudaStream_t stream = as_stream(stream_);
-  if (x_dtype == CSMOE_BF16) {
+  if (E > kMaxE) {
+    if (x_dtype == CSMOE_BF16) {
+      launch_router_fwd_wide<__nv_bfloat16>(grid, stream, static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(wg),
+                                            T, D, E, K, static_cast<__nv_bfloat16*>(logits), probs, topk_w, topk_idx);
+    } else if (x_dtype == CSMOE_F32) {
+      launch_router_fwd_wide<float>(grid, stream, static_cast<const float*>(x), static_cast<const float*>(wg), T, D, E, K,
+                                    static_cast<float*>(logits), probs, topk_w, topk_idx);
+    } else {
+      CSMOE_CHECK_ARG(false, "csmoe_router_fwd: unsupported dtype %d", x_dtype);
+    }
+  } else if (x_dtype == CSMOE_BF16) {
     router_fwd_kernel<__nv_bfloat16><<<grid, kWarpsPerBlock * 32, 0, stream>>>(
         static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(wg), T, D, E, K,
         static_cast<__nv_bfloat16*>(logits), probs, topk_w, topk_idx);
@@ -520,11 +899,20 @@ extern "C" int csmoe_router_fwd(const void* x, const void* wg, int32_t x_dtype, 
 extern "C" int csmoe_router_from_logits(const void* logits, int32_t dtype, int64_t T, int32_t E, int32_t K, float* probs,
                                         float* topk_w, int32_t* topk_idx, void* stream_) {
   CSMOE_CHECK_ARG(logits && probs && topk_w && topk_idx, "csmoe_router_from_logits: NULL pointer");
-  CSMOE_CHECK_ARG(E >= 1 && E <= kMaxE && K >= 1 && K <= kMaxK && K <= E && T >= 0, "csmoe_router_from_logits: bad sizes");
+  CSMOE_CHECK_ARG(E >= 1 && E <= kMaxEWide && K >= 1 && K <= kMaxK && K <= E && T >= 0, "csmoe_router_from_logits: bad sizes");
   if (T == 0) return CSMOE_OK;
   const unsigned grid = static_cast<unsigned>((T + kWarpsPerBlock - 1) / kWarpsPerBlock);
   cudaStream_t stream = as_stream(stream_);
-  if (dtype == CSMOE_BF16) {
+  if (E > kMaxE) {
+    if (dtype == CSMOE_BF16) {
+      launch_router_from_logits_wide<__nv_bfloat16>(grid, stream, static_cast<const __nv_bfloat16*>(logits), T, E, K, probs,
+                                                    topk_w, topk_idx);
+    } else if (dtype == CSMOE_F32) {
+      launch_router_from_logits_wide<float>(grid, stream, static_cast<const float*>(logits), T, E, K, probs, topk_w, topk_idx);
+    } else {
+      CSMOE_CHECK_ARG(false, "csmoe_router_from_logits: unsupported dtype %d", dtype);
+    }
+  } else if (dtype == CSMOE_BF16) {
     router_from_logits_kernel<__nv_bfloat16><<<grid, kWarpsPerBlock * 32, 0, stream>>>(
         static_cast<const __nv_bfloat16*>(logits), T, E, K, probs, topk_w, topk_idx);
   } else if (dtype == CSMOE_F32) {
@@ -540,12 +928,16 @@ extern "C" int csmoe_router_from_logits(const void* logits, int32_t dtype, int64
 extern "C" int csmoe_topk_renorm(const float* scores, int64_t T, int32_t E, int32_t K, int32_t mode, int32_t round_dtype,
                                  float* topk_w, int32_t* topk_idx, void* stream_) {
   CSMOE_CHECK_ARG(scores && topk_w && topk_idx, "csmoe_topk_renorm: NULL pointer");
-  CSMOE_CHECK_ARG(E >= 1 && E <= kMaxE, "csmoe_topk_renorm: E must be in [1, %d]", kMaxE);
+  CSMOE_CHECK_ARG(E >= 1 && E <= kMaxEWide, "csmoe_topk_renorm: E must be in [1, %d]", kMaxEWide);
   CSMOE_CHECK_ARG(K >= 1 && K <= kMaxK && K <= E, "csmoe_topk_renorm: K must be in [1, min(E, %d)]", kMaxK);
   if (T == 0) return CSMOE_OK;
   const unsigned grid = static_cast<unsigned>((T + kWarpsPerBlock - 1) / kWarpsPerBlock);
-  topk_renorm_kernel<<<grid, kWarpsPerBlock * 32, 0, as_stream(stream_)>>>(scores, T, E, K, mode, round_dtype, topk_w,
-                                                                           topk_idx);
+  if (E > 128)
+    topk_renorm_wide_kernel<8><<<grid, kWarpsPerBlock * 32, 0, as_stream(stream_)>>>(scores, T, E, K, mode, round_dtype, topk_w, topk_idx);
+  else if (E > kMaxE)
+    topk_renorm_wide_kernel<4><<<grid, kWarpsPerBlock * 32, 0, as_stream(stream_)>>>(scores, T, E, K, mode, round_dtype, topk_w, topk_idx);
+  else
+    topk_renorm_kernel<<<grid, kWarpsPerBlock * 32, 0, as_stream(stream_)>>>(scores, T, E, K, mode, round_dtype, topk_w, topk_idx);
   CSMOE_CHECK_LAUNCH();
   return CSMOE_OK;
 }
@@ -560,13 +952,23 @@ extern "C" int csmoe_router_aux_fwd(const void* logits, int32_t dtype, const flo
                                     int64_t B, int64_t N, int32_t E, int32_t K, float* psum, float* cnt, float* lse,
                                     float* losses, void* workspace, void* stream_) {
   CSMOE_CHECK_ARG(logits && probs && topk_idx && psum && cnt && losses && workspace, "csmoe_router_aux_fwd: NULL pointer");
-  CSMOE_CHECK_ARG(E >= 1 && E <= kMaxE && K >= 1 && B >= 1 && N >= 1, "csmoe_router_aux_fwd: bad sizes");
+  CSMOE_CHECK_ARG(E >= 1 && E <= kMaxEWide && K >= 1 && B >= 1 && N >= 1, "csmoe_router_aux_fwd: bad sizes");
   cudaStream_t stream = as_stream(stream_);
   const int chunks = static_cast<int>((N + kAuxChunk - 1) / kAuxChunk);
   const unsigned grid = static_cast<unsigned>(B * chunks);
   const size_t smem = kWarpsPerBlock * (2 * E + 1) * sizeof(float);
   float* partial = static_cast<float*>(workspace);
-  if (dtype == CSMOE_BF16) {
+  if (E > kMaxE) {
+    if (dtype == CSMOE_BF16) {
+      launch_router_aux_stage1_wide<__nv_bfloat16>(grid, smem, stream, static_cast<const __nv_bfloat16*>(logits), probs, topk_idx,
+                                                   static_cast<int>(N), E, K, chunks, partial, lse);
+    } else if (dtype == CSMOE_F32) {
+      launch_router_aux_stage1_wide<float>(grid, smem, stream, static_cast<const float*>(logits), probs, topk_idx,
+                                           static_cast<int>(N), E, K, chunks, partial, lse);
+    } else {
+      CSMOE_CHECK_ARG(false, "csmoe_router_aux_fwd: unsupported dtype %d", dtype);
+    }
+  } else if (dtype == CSMOE_BF16) {
     router_aux_stage1<__nv_bfloat16><<<grid, kWarpsPerBlock * 32, smem, stream>>>(
         static_cast<const __nv_bfloat16*>(logits), probs, topk_idx, static_cast<int>(N), E, K, chunks, partial, lse);
   } else if (dtype == CSMOE_F32) {
@@ -594,7 +996,7 @@ extern "C" int csmoe_router_bwd(const void* x, const void* wg, int32_t x_dtype, 
                                 int32_t E, int32_t K, float* dl, void* dx, void* dwg, int32_t wg_dtype, void* workspace,
                                 void* stream_) {
   CSMOE_CHECK_ARG(x && wg && probs && topk_w && topk_idx && dl, "csmoe_router_bwd: NULL pointer");
-  CSMOE_CHECK_ARG(E >= 1 && E <= kMaxE && K >= 1 && K <= kMaxK && D > 0 && D % 8 == 0 && B >= 1 && N >= 1,
+  CSMOE_CHECK_ARG(E >= 1 && E <= kMaxEWide && K >= 1 && K <= kMaxK && D > 0 && D % 8 == 0 && B >= 1 && N >= 1,
                   "csmoe_router_bwd: bad sizes");
   CSMOE_CHECK_ARG(dwg == nullptr || workspace != nullptr, "csmoe_router_bwd: dwg needs a workspace");
   cudaStream_t stream = as_stream(stream_);
@@ -607,9 +1009,13 @@ extern "C" int csmoe_router_bwd(const void* x, const void* wg, int32_t x_dtype, 
   float* partial = static_cast<float*>(workspace);
   if (x_dtype == CSMOE_BF16) {
     using T_ = __nv_bfloat16;
-    router_bwd_dx_kernel<T_><<<grid, kWarpsPerBlock * 32, 0, stream>>>(
-        static_cast<const T_*>(wg), probs, topk_w, topk_idx, dtw, dprobs, dlogits, lse, cnt, g_losses, T,
-        static_cast<int>(N), static_cast<int>(B), D, E, K, dl, static_cast<T_*>(dx));
+    if (E > kMaxE)
+      launch_router_bwd_dx_wide<T_>(grid, stream, static_cast<const T_*>(wg), probs, topk_w, topk_idx, dtw, dprobs, dlogits, lse,
+                                    cnt, g_losses, T, static_cast<int>(N), static_cast<int>(B), D, E, K, dl, static_cast<T_*>(dx));
+    else
+      router_bwd_dx_kernel<T_><<<grid, kWarpsPerBlock * 32, 0, stream>>>(
+          static_cast<const T_*>(wg), probs, topk_w, topk_idx, dtw, dprobs, dlogits, lse, cnt, g_losses, T,
+          static_cast<int>(N), static_cast<int>(B), D, E, K, dl, static_cast<T_*>(dx));
     CSMOE_CHECK_LAUNCH();
     if (dwg != nullptr) {
       router_bwd_dw_stage1<T_><<<g1, 128, 0, stream>>>(static_cast<const T_*>(x), dl, T, D, E, partial);
@@ -621,9 +1027,14 @@ extern "C" int csmoe_router_bwd(const void* x, const void* wg, int32_t x_dtype, 
       CSMOE_CHECK_LAUNCH();
     }
   } else if (x_dtype == CSMOE_F32) {
-    router_bwd_dx_kernel<float><<<grid, kWarpsPerBlock * 32, 0, stream>>>(
-        static_cast<const float*>(wg), probs, topk_w, topk_idx, dtw, dprobs, dlogits, lse, cnt, g_losses, T,
-        static_cast<int>(N), static_cast<int>(B), D, E, K, dl, static_cast<float*>(dx));
+    if (E > kMaxE)
+      launch_router_bwd_dx_wide<float>(grid, stream, static_cast<const float*>(wg), probs, topk_w, topk_idx, dtw, dprobs, dlogits,
+                                       lse, cnt, g_losses, T, static_cast<int>(N), static_cast<int>(B), D, E, K, dl,
+                                       static_cast<float*>(dx));
+    else
+      router_bwd_dx_kernel<float><<<grid, kWarpsPerBlock * 32, 0, stream>>>(
+          static_cast<const float*>(wg), probs, topk_w, topk_idx, dtw, dprobs, dlogits, lse, cnt, g_losses, T,
+          static_cast<int>(N), static_cast<int>(B), D, E, K, dl, static_cast<float*>(dx));
     CSMOE_CHECK_LAUNCH();
     if (dwg != nullptr) {
       router_bwd_dw_stage1<float><<<g1, 128, 0, stream>>>(static_cast<const float*>(x), dl, T, D, E, partial);

@@ -17,7 +17,7 @@ from ._lib import (ACT_GELU, ACT_GELU_TANH, ACT_NONE, ACT_RELU, ACT_SILU, ACT_SI
                    GEMM_ROWS, ROW_TILE, GemmArgs, check)
 
 __all__ = [
-    "Route", "route_build", "router_fwd", "topk_renorm", "gather_rows", "combine_fwd", "combine_bwd_w",
+    "Route", "route_build", "router_fwd", "router_from_logits", "topk_renorm", "gather_rows", "combine_fwd", "combine_bwd_w",
     "scatter_reduce", "gemm_rows", "gemm_reduce", "act_fwd", "act_bwd", "act_bwd_bias", "bias_grad", "cast_bf16", "affinity_fwd",
     "affinity_bwd", "affinity_from_rowsum", "diversity_fwd", "compete_bwd", "ACT_NONE", "ACT_RELU", "ACT_GELU", "ACT_GELU_TANH", "ACT_SILU", "ACT_SILU_GLU",
 ]
@@ -150,11 +150,25 @@ def router_fwd(x: torch.Tensor, wg: torch.Tensor, top_k: int):
     if _router_gemm_ok(T, D, E, x.dtype):
         # many experts: logits = x . Wg^T as a one-"expert" dense grouped GEMM, then softmax / top-k from the logits
         logits = gemm_rows(x, wg.unsqueeze(0), w_is_kn=False, dense_rows=T, a_expert_rows=0)
-        _call("csmoe_router_from_logits", _p(logits), _dt(logits), T, E, top_k, _p(probs), _p(tw), _p(ti), _stream())
-        return logits, probs, tw, ti
+        return (logits,) + router_from_logits(logits, top_k, out=(probs, tw, ti))
     logits = torch.empty(T, E, dtype=x.dtype, device=x.device)
     _call("csmoe_router_fwd", _p(x), _p(wg), _dt(x), T, D, E, top_k, _p(logits), _p(probs), _p(tw), _p(ti), _stream())
     return logits, probs, tw, ti
+
+
+def router_from_logits(logits: torch.Tensor, top_k: int, out=None):
+    """logits [T, E] (activation dtype, already rounded) -> probs [T,E] f32, topk_w [T,K] f32, topk_idx [T,K] i32: the
+    softmax / top-k / renormalisation half of router_fwd, bit-identical to it on the same logits."""
+    _cuda(logits)
+    logits = logits.contiguous()
+    T, E = logits.shape
+    if out is None:
+        out = (torch.empty(T, E, dtype=torch.float32, device=logits.device),
+               torch.empty(T, top_k, dtype=torch.float32, device=logits.device),
+               torch.empty(T, top_k, dtype=torch.int32, device=logits.device))
+    probs, tw, ti = out
+    _call("csmoe_router_from_logits", _p(logits), _dt(logits), T, E, top_k, _p(probs), _p(tw), _p(ti), _stream())
+    return probs, tw, ti
 
 
 def router_aux_fwd(logits: torch.Tensor, probs: torch.Tensor, topk_idx: torch.Tensor, batch: int):

@@ -71,7 +71,7 @@ int csmoe_route_build(const int32_t* sel, int64_t n_slots, int32_t num_experts, 
  * moe_pretrain_model/layers/moe/competesmoe.py:465-490): logits = x @ Wg^T (fp32 accumulate, rounded to `x_dtype`),
  * p = softmax_fp32(logits), (w, idx) = topk(p, K) (descending, ties -> lowest index), w /= round_to_x_dtype(sum w).
  * x[T,D] and wg[E,D] share x_dtype (bf16 or fp32).  Outputs: logits[T,E] (x_dtype), probs[T,E] fp32, topk_w[T,K] fp32,
- * topk_idx[T,K] int32.  E <= 64, K <= 8. */
+ * topk_idx[T,K] int32.  E <= 256 (two experts per lane up to 64, four / eight per lane above), K <= 8. */
 int csmoe_router_fwd(const void* x, const void* wg, int32_t x_dtype, int64_t T, int32_t D, int32_t E, int32_t K,
                      void* logits, float* probs, float* topk_w, int32_t* topk_idx, void* stream);
 
@@ -303,7 +303,7 @@ int csmoe_sigma_wgrad(const void* a, const void* g, int64_t T, int32_t N, int32_
  *        [3] mean_{b,e}(mean_n q * mean_n onehot(aff_idx[..., 0])) * E^2      balanceloss on the affinity (multimodal)
  *        [4] mean_b sum_e m log m,  m = mean_n softmax(q)                      entropy_balance(aff_softmax) (pretrain)
  *        colq / cnt / colr [B,E]: per-batch column sums of q, top-1 counts and column sums of softmax(q) (for backward).
- * workspace: csmoe_losses_workspace_bytes(B, N, E) bytes.  E <= 64, K <= 8, B <= 65535. */
+ * workspace: csmoe_losses_workspace_bytes(B, N, E) bytes.  E <= 256, K <= 8, B <= 65535. */
 int64_t csmoe_losses_workspace_bytes(int64_t B, int64_t N, int32_t E);
 int csmoe_losses_fwd(const float* p, const float* aff, const int32_t* aff_idx, const int32_t* gate_idx, int64_t B,
                      int64_t N, int32_t E, int32_t K, float* q, float* colq, float* cnt, float* colr, float* losses,

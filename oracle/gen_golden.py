@@ -559,8 +559,19 @@ def gen_bias(pm):
     gen_pretrain(pm, "pt_comp_bias_f32", 64, 8, 32, 2, 2, 24, True, seed=41, bias=True)
 
 
+def gen_wide(pm):
+    """The reference's own default expert count, `-moe.n_experts 128` (transformer_lm_mixin.py:32): more experts than the
+    two-per-lane router / loss kernels hold, so the 4-per-lane variants run (router.cu / losses.cu "more than 64 experts")."""
+    gen_pretrain(pm, "pt_router_e128_f32", 32, 128, 16, 4, 2, 40, False, seed=50)
+    gen_pretrain(pm, "pt_comp_e128_f32", 32, 128, 16, 4, 2, 24, True, seed=51, hybrid=True, balance_affinity=True,
+                 router_theta=0.5)
+
+
 def main():
     OUT.mkdir(parents=True, exist_ok=True)
+    if "--wide-only" in sys.argv:
+        gen_wide(load_pretrain_reference())
+        return
     if "--gate-variants-only" in sys.argv:
         gen_gate_variants(load_multimodal_reference(), load_pretrain_reference())
         return
@@ -600,6 +611,7 @@ def main():
     gen_all_pretrain_siblings(pm)
     gen_gate_variants(mm, pm)
     gen_bias(pm)
+    gen_wide(pm)
     print("done; now run:  TRITON_INTERPRET=1 python -m oracle.gen_golden")
 
 

@@ -89,6 +89,7 @@ def test_multimodal_fp32_module_matches_reference_at_1e4(name):
 
 
 PT = ["pt_router_f32", "pt_comp_f32", "pt_comp_hybrid_bal_f32", "pt_comp_intopk_f32", "pt_comp_tribrid_f32"]
+PT_WIDE = ["pt_router_e128_f32", "pt_comp_e128_f32"]
 
 
 @pytest.mark.parametrize("name", PT)
@@ -112,3 +113,11 @@ def test_pretrain_fp32_without_autocast_matches_reference_at_1e4(name):
     assert_close_rms(layer.keys.grad, fx["dkeys"], RTOL, "dkeys")
     assert_close_rms(layer.values.grad, fx["dvalues"], RTOL, "dvalues")
     assert_close_rms(layer.w_gate.grad, fx["dw_gate"], RTOL, "dw_gate")
+
+
+@pytest.mark.first_hw_run
+@pytest.mark.parametrize("name", PT_WIDE)
+def test_pretrain_fp32_with_128_experts_matches_reference_at_1e4(name):
+    """`-moe.n_experts 128`, the reference's default: the four-experts-per-lane router / loss kernels in the fp32-accurate
+    mode.  Written after the round's GPU budget was spent (green on the SIMT emulator)."""
+    test_pretrain_fp32_without_autocast_matches_reference_at_1e4(name)

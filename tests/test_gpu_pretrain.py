@@ -40,7 +40,7 @@ def build_layer(fx):
 
 
 @pytest.mark.parametrize("name", PT)
-def test_pretrain_layer_matches_reference_golden(name):
+def test_pretrain_layer_matches_reference_golden(name, grad_outliers=0.0):
     fx = load_golden(name)
     m = fx["meta"]
     layer, args = build_layer(fx)
@@ -81,13 +81,27 @@ def test_pretrain_layer_matches_reference_golden(name):
             assert abs(got - ref) <= 3e-2 * abs(ref) + 2e-5, (k, got, ref)
             assert abs(got - float(fx["regs"][k])) <= 6e-2 * abs(float(fx["regs"][k])) + 5e-5, (k, got)
         assert_close_rms(x.grad, xr.grad, 3e-2, "dx")
-        assert_close_rms(layer.keys.grad, ks.grad, 3e-2, "dkeys")
-        assert_close_rms(layer.values.grad, vs.grad, 3e-2, "dvalues")
-        assert_close_rms(layer.w_gate.grad, wg.grad, 3e-2, "dw_gate")
+        assert_close_rms(layer.keys.grad, ks.grad, 3e-2, "dkeys", outliers=grad_outliers)
+        assert_close_rms(layer.values.grad, vs.grad, 3e-2, "dvalues", outliers=grad_outliers)
+        assert_close_rms(layer.w_gate.grad, wg.grad, 3e-2, "dw_gate", outliers=grad_outliers)
         if has_bias:
             assert_close_rms(layer.bias.grad, bs.grad, 3e-2, "dbias")
             assert_close_rms(layer.o_bias.grad, obs.grad, 3e-2, "do_bias")
     assert layer.keys.grad.dtype == torch.float32        # fp32 master parameters keep fp32 gradients
+
+
+PT_WIDE = ["pt_router_e128_f32", "pt_comp_e128_f32"]     # the reference's default -moe.n_experts 128 (transformer_lm_mixin.py:32)
+
+
+@pytest.mark.first_hw_run
+@pytest.mark.parametrize("name", PT_WIDE)
+def test_pretrain_layer_with_128_experts_matches_reference_golden(name):
+    """More experts than the two-per-lane router / loss kernels hold: the four-per-lane variants.  Written after the GPU
+    budget of the round was spent (green on the SIMT emulator, tests/test_simt_layers.py).
+    320 (token, expert) pairs over 128 experts: a weight-gradient element is the sum of two or three products, so one
+    bf16 rounding of d(scores) (the oracle rounds op by op, this path once) can decide it -- seen on the emulator: 1 of
+    65 536 elements of dkeys at 2.3x the 3e-2 band; allowed: 0.1 % of the elements, each within 5x the band."""
+    test_pretrain_layer_matches_reference_golden(name, grad_outliers=1e-3)
 
 
 def test_cvmm_op_both_call_patterns():

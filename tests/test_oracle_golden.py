@@ -16,7 +16,7 @@ MM = ["mm_siglip_router_f32", "mm_projector_router_f32", "mm_glu_router_f32", "m
       "mm_siglip_comp_bf16", "mm_siglip_comp_upcycled_f32", "mm_siglip_comp_normsigmoid_f32"]
 PT = ["pt_router_f32", "pt_comp_f32", "pt_comp_hybrid_bal_f32", "pt_comp_intopk_f32", "pt_comp_tribrid_f32",
       "pt_router_cosine_f32", "pt_router_normweight_f32", "pt_router_normsigmoid_f32", "pt_comp_cosine_f32",
-      "pt_router_bias_f32", "pt_comp_bias_f32"]
+      "pt_router_bias_f32", "pt_comp_bias_f32", "pt_router_e128_f32", "pt_comp_e128_f32"]
 
 
 def _req(t):

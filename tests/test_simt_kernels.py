@@ -80,6 +80,11 @@ def test_router_aux_and_backward_match_autograd(ops):
     gk.test_router_aux_and_backward_match_autograd(ops)
 
 
+@pytest.mark.parametrize("B,N,D,E,K", [(2, 60, 128, 64, 4), (1, 50, 64, 33, 2)])
+def test_router_backward_with_more_experts_than_column_lanes(ops, B, N, D, E, K):
+    gk.test_router_aux_and_backward_match_autograd(ops, B, N, D, E, K)
+
+
 # ------------------------------------------------------------------------------------------------ stages 3 / 5: permute, combine
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
 def test_gather_combine_scatter(ops, dtype):
@@ -152,6 +157,47 @@ def test_compete_losses_kernels_match_torch(ops, B, N, E, K):
 
 @pytest.mark.parametrize("B,N,E", [(1, 512, 4), (3, 100, 8), (2, 96, 64)])
 def test_entropy_balance_kernel_matches_pretrain_formula(ops, B, N, E):
+    gk.test_entropy_balance_kernel_matches_pretrain_formula(B, N, E)
+
+
+# ------------------------------------------------------------------------------------------------ more than 64 experts
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("T,D,E,K", [(40, 256, 128, 4), (24, 512, 128, 8), (33, 128, 200, 8), (20, 64, 256, 2), (30, 128, 65, 3)])
+def test_router_matches_oracle_wide(ops, dtype, T, D, E, K):
+    gk.test_router_matches_oracle(ops, dtype, T, D, E, K)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("T,D,E,K", [(77, 64, 8, 2), (50, 128, 64, 8), (40, 128, 128, 8), (21, 64, 256, 5), (33, 64, 97, 1)])
+def test_router_from_logits_equals_fused_router(ops, dtype, T, D, E, K):
+    gk.test_router_from_logits_equals_fused_router(ops, dtype, T, D, E, K)
+
+
+def test_router_tie_break_is_lowest_index_wide(ops):
+    gk.test_router_tie_break_is_lowest_index_wide(ops)
+
+
+@pytest.mark.parametrize("E,K", [(65, 3), (128, 8), (200, 5), (256, 8)])
+def test_topk_renorm_wide(ops, E, K):
+    gk.test_topk_renorm(ops, E, K)
+
+
+@pytest.mark.parametrize("B,N,D,E,K", [(3, 50, 128, 128, 4), (2, 70, 64, 200, 8), (1, 70, 64, 72, 2)])
+def test_router_aux_and_backward_match_autograd_wide(ops, B, N, D, E, K):
+    gk.test_router_aux_and_backward_match_autograd(ops, B, N, D, E, K)
+
+
+def test_topk_is_total_on_non_finite_scores_wide(ops):
+    gk.test_topk_is_total_on_non_finite_scores_wide(ops)
+
+
+@pytest.mark.parametrize("B,N,E,K", [(2, 130, 128, 8), (3, 77, 200, 5), (1, 150, 65, 2), (2, 64, 256, 8)])
+def test_compete_losses_kernels_match_torch_wide(ops, B, N, E, K):
+    gk.test_compete_losses_kernels_match_torch(B, N, E, K)
+
+
+@pytest.mark.parametrize("B,N,E", [(2, 200, 128), (3, 96, 256), (1, 130, 100)])
+def test_entropy_balance_kernel_matches_pretrain_formula_wide(ops, B, N, E):
     gk.test_entropy_balance_kernel_matches_pretrain_formula(B, N, E)
 
 

@@ -102,6 +102,11 @@ def test_pretrain_layer_matches_reference_golden(name):
     gp.test_pretrain_layer_matches_reference_golden(name)
 
 
+@pytest.mark.parametrize("name", gp.PT_WIDE)
+def test_pretrain_layer_with_128_experts_matches_reference_golden(name):
+    gp.test_pretrain_layer_with_128_experts_matches_reference_golden(name)
+
+
 def test_cvmm_op_both_call_patterns():
     gp.test_cvmm_op_both_call_patterns()
 
@@ -129,6 +134,6 @@ def test_multimodal_fp32_module_matches_reference_at_1e4(name):
     gf.test_multimodal_fp32_module_matches_reference_at_1e4(name)
 
 
-@pytest.mark.parametrize("name", ["pt_router_f32", "pt_comp_tribrid_f32"])
+@pytest.mark.parametrize("name", ["pt_router_f32", "pt_comp_tribrid_f32", "pt_router_e128_f32", "pt_comp_e128_f32"])
 def test_pretrain_fp32_without_autocast_matches_reference_at_1e4(name):
     gf.test_pretrain_fp32_without_autocast_matches_reference_at_1e4(name)
