@@ -11,6 +11,7 @@ from pathlib import Path
 
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "lib" / "libcsmoe.so"
+ABI_VERSION = 2      # include/csmoe.h CSMOE_ABI_VERSION: bumped whenever a signature or csmoe_gemm_args changes
 
 F32, BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_GELU, ACT_GELU_TANH, ACT_SILU, ACT_SILU_GLU = range(6)
@@ -47,12 +48,12 @@ _SIGNATURES = {
     "csmoe_route_row_cap": (i64, [i64, i32, i32]),
     "csmoe_route_workspace_bytes": (i64, [i64, i32]),
     "csmoe_route_build": (i32, [vp, i64, i32, i32, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
-    "csmoe_router_fwd": (i32, [vp, vp, i32, i64, i32, i32, i32, vp, vp, vp, vp, vp]),
+    "csmoe_router_fwd": (i32, [vp, vp, i32, i64, i32, i32, i32, i32, vp, vp, vp, vp, vp]),
     "csmoe_router_aux_workspace_bytes": (i64, [i64, i64, i32]),
     "csmoe_router_aux_fwd": (i32, [vp, i32, vp, vp, i64, i64, i32, i32, vp, vp, vp, vp, vp, vp]),
     "csmoe_router_bwd_workspace_bytes": (i64, [i64, i32, i32]),
-    "csmoe_router_bwd": (i32, [vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i32, i32, i32, vp, vp, vp, i32, vp, vp]),
-    "csmoe_router_from_logits": (i32, [vp, i32, i64, i32, i32, vp, vp, vp, vp]),
+    "csmoe_router_bwd": (i32, [vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i32, i32, i32, i32, vp, vp, vp, i32, vp, vp]),
+    "csmoe_router_from_logits": (i32, [vp, i32, i64, i32, i32, i32, vp, vp, vp, vp]),
     "csmoe_topk_renorm": (i32, [vp, i64, i32, i32, i32, i32, vp, vp, vp]),
     "csmoe_gather_rows": (i32, [vp, i32, i64, i32, i32, vp, i64, vp, vp, vp]),
     "csmoe_combine_fwd": (i32, [vp, i32, i64, i32, i32, vp, vp, vp, i32, vp, vp]),
@@ -133,7 +134,7 @@ def load() -> C.CDLL:
             fn = getattr(lib, name)  # AttributeError if the library is stale / incomplete
             fn.restype = res
             fn.argtypes = args
-        if lib.csmoe_abi_version() != 1:
+        if lib.csmoe_abi_version() != ABI_VERSION:
             raise RuntimeError("libcsmoe.so ABI version mismatch; rebuild with `python -m competesmoe_b200.build --force`")
         _lib = lib
     return _lib

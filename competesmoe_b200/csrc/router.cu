@@ -4,7 +4,8 @@
 //
 // Rounding points follow the reference: logits are accumulated in fp32 and rounded to the activation dtype (the
 // nn.Linear / F.linear output), softmax runs in fp32 on the rounded logits, the top-k weights stay fp32 and are divided
-// by their sum rounded to the activation dtype (`.to(x.dtype)` on the denominator only).
+// by their sum rounded to the dtype of the LAYER INPUT (`.to(x.dtype)` on the denominator only): `renorm_dtype`, which is
+// the activation dtype for a bf16 model (multimodal plugin) and fp32 for fp32 inputs under autocast (pretrain plugin).
 // Tie-break: highest value first, equal values -> lowest expert index (the reference's torch.topk is unspecified on
 // ties; see DESIGN.md "routing parity").
 #include "common.h"
@@ -79,7 +80,7 @@ __device__ __forceinline__ void warp_topk(float v0, float v1, int lane, int E, i
 
 template <typename T>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
-router_fwd_kernel(const T* __restrict__ x, const T* __restrict__ wg, long long Tn, int D, int E, int K,
+router_fwd_kernel(const T* __restrict__ x, const T* __restrict__ wg, long long Tn, int D, int E, int K, int renorm_bf16,
                   T* __restrict__ logits, float* __restrict__ probs, float* __restrict__ topk_w,
                   int32_t* __restrict__ topk_idx) {
   const int lane = threadIdx.x & 31;
@@ -142,7 +143,7 @@ router_fwd_kernel(const T* __restrict__ x, const T* __restrict__ wg, long long T
 #pragma unroll
     for (int k = 0; k < kMaxK; ++k)
       if (k < K) s += tv[k];
-    s = round_as(s, static_cast<const T*>(nullptr));
+    if (renorm_bf16) s = bf16_round(s);
 #pragma unroll
     for (int k = 0; k < kMaxK; ++k)
       if (k < K) {
@@ -157,7 +158,7 @@ router_fwd_kernel(const T* __restrict__ x, const T* __restrict__ wg, long long T
 // points as router_fwd_kernel; logits are read in the activation dtype.
 template <typename T>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
-router_from_logits_kernel(const T* __restrict__ logits, long long Tn, int E, int K, float* __restrict__ probs,
+router_from_logits_kernel(const T* __restrict__ logits, long long Tn, int E, int K, int renorm_bf16, float* __restrict__ probs,
                           float* __restrict__ topk_w, int32_t* __restrict__ topk_idx) {
   const int lane = threadIdx.x & 31;
   const long long t = static_cast<long long>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
@@ -179,7 +180,7 @@ router_from_logits_kernel(const T* __restrict__ logits, long long Tn, int E, int
 #pragma unroll
     for (int k = 0; k < kMaxK; ++k)
       if (k < K) s += tv[k];
-    s = round_as(s, static_cast<const T*>(nullptr));
+    if (renorm_bf16) s = bf16_round(s);
 #pragma unroll
     for (int k = 0; k < kMaxK; ++k)
       if (k < K) {
@@ -344,7 +345,10 @@ router_aux_stage2(const float* __restrict__ partial, int B, int N, int E, int ch
 
 // ------------------------------------------------------------------------------------------------ router backward
 // Stage A (one warp per token): total gradient w.r.t. the gate logits,
-//   dp  = dprobs_in + g_bal * E/(B N^2) * C[b,e] + scatter_k( (dtw_k - sum_j dtw_j w_j) / s )       s = sum_k p_{i_k}
+//   dp  = dprobs_in + g_bal * E/(B N^2) * C[b,e] + scatter_k( dtw_k / r + round(-sum_j dtw_j (w_j / r)) )
+//         r = round(sum_k p_{i_k}), round = to `renorm_dtype`: autograd's gradients of `w / sum(w).to(x.dtype)` -- the
+//         quotient's numerator gradient in fp32, the denominator's accumulated and then cast to the denominator's dtype
+//         (with an fp32 denominator this is (dtw_k - sum_j dtw_j w_j) / s)
 //   dl  = p * (dp - <dp, p>) + dlogits_in + g_z * (2 lse / T) * p
 // rounded to the activation dtype (the reference back-propagates through a bf16 nn.Linear), then dx[t,:] = dl . Wg.
 template <typename T>
@@ -352,7 +356,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 router_bwd_dx_kernel(const T* __restrict__ wg, const float* __restrict__ probs, const float* __restrict__ topk_w,
                      const int32_t* __restrict__ topk_idx, const float* __restrict__ dtw, const float* __restrict__ dprobs_in,
                      const float* __restrict__ dlogits_in, const float* __restrict__ lse, const float* __restrict__ cnt,
-                     const float* __restrict__ g_losses, long long Tn, int N, int B, int D, int E, int K,
+                     const float* __restrict__ g_losses, long long Tn, int N, int B, int D, int E, int K, int renorm_bf16,
                      float* __restrict__ dl_out, T* __restrict__ dx) {
   const int lane = threadIdx.x & 31;
   const long long t = static_cast<long long>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
@@ -368,15 +372,15 @@ router_bwd_dx_kernel(const T* __restrict__ wg, const float* __restrict__ probs, 
     if (h1) d1 += coef * cnt[b * E + lane + 32];
   }
   if (dtw != nullptr) {
-    float s = 0.f, dot = 0.f;
+    float s = 0.f;
+    for (int k = 0; k < K; ++k) s += probs[t * E + topk_idx[t * K + k]];
+    if (renorm_bf16) s = bf16_round(s);
+    float dden = 0.f;
+    for (int k = 0; k < K; ++k) dden -= dtw[t * K + k] * (topk_w[t * K + k] / s);
+    if (renorm_bf16) dden = bf16_round(dden);
     for (int k = 0; k < K; ++k) {
       const int i = topk_idx[t * K + k];
-      s += probs[t * E + i];
-      dot += dtw[t * K + k] * topk_w[t * K + k];
-    }
-    for (int k = 0; k < K; ++k) {
-      const int i = topk_idx[t * K + k];
-      const float g = (dtw[t * K + k] - dot) / s;
+      const float g = dtw[t * K + k] / s + dden;
       if (i == lane) d0 += g;
       if (i == lane + 32) d1 += g;
     }
@@ -565,14 +569,13 @@ __device__ __forceinline__ void warp_softmax_wide(float (&l)[C], int lane, int E
   for (int c = 0; c < C; ++c) l[c] = l[c] / denom;
 }
 
-template <typename T>
-__device__ __forceinline__ void write_topk(const float (&tv)[kMaxK], const int (&ti)[kMaxK], int K, long long t,
+__device__ __forceinline__ void write_topk(const float (&tv)[kMaxK], const int (&ti)[kMaxK], int K, int renorm_bf16, long long t,
                                            float* __restrict__ topk_w, int32_t* __restrict__ topk_idx) {
   float s = 0.f;
 #pragma unroll
   for (int k = 0; k < kMaxK; ++k)
     if (k < K) s += tv[k];
-  s = round_as(s, static_cast<const T*>(nullptr));
+  if (renorm_bf16) s = bf16_round(s);
 #pragma unroll
   for (int k = 0; k < kMaxK; ++k)
     if (k < K) {
@@ -583,7 +586,7 @@ __device__ __forceinline__ void write_topk(const float (&tv)[kMaxK], const int (
 
 template <typename T, int C>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
-router_fwd_wide_kernel(const T* __restrict__ x, const T* __restrict__ wg, long long Tn, int D, int E, int K,
+router_fwd_wide_kernel(const T* __restrict__ x, const T* __restrict__ wg, long long Tn, int D, int E, int K, int renorm_bf16,
                        T* __restrict__ logits, float* __restrict__ probs, float* __restrict__ topk_w,
                        int32_t* __restrict__ topk_idx) {
   const int lane = threadIdx.x & 31;
@@ -628,12 +631,12 @@ router_fwd_wide_kernel(const T* __restrict__ x, const T* __restrict__ wg, long l
   float tv[kMaxK];
   int ti[kMaxK];
   warp_topk_wide<C>(l, lane, E, K, tv, ti);
-  if (lane == 0) write_topk<T>(tv, ti, K, t, topk_w, topk_idx);
+  if (lane == 0) write_topk(tv, ti, K, renorm_bf16, t, topk_w, topk_idx);
 }
 
 template <typename T, int C>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
-router_from_logits_wide_kernel(const T* __restrict__ logits, long long Tn, int E, int K, float* __restrict__ probs,
+router_from_logits_wide_kernel(const T* __restrict__ logits, long long Tn, int E, int K, int renorm_bf16, float* __restrict__ probs,
                                float* __restrict__ topk_w, int32_t* __restrict__ topk_idx) {
   const int lane = threadIdx.x & 31;
   const long long t = static_cast<long long>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
@@ -648,7 +651,7 @@ router_from_logits_wide_kernel(const T* __restrict__ logits, long long Tn, int E
   float tv[kMaxK];
   int ti[kMaxK];
   warp_topk_wide<C>(l, lane, E, K, tv, ti);
-  if (lane == 0) write_topk<T>(tv, ti, K, t, topk_w, topk_idx);
+  if (lane == 0) write_topk(tv, ti, K, renorm_bf16, t, topk_w, topk_idx);
 }
 
 template <int C>
@@ -749,7 +752,8 @@ router_bwd_dx_wide_kernel(const T* __restrict__ wg, const float* __restrict__ pr
                           const int32_t* __restrict__ topk_idx, const float* __restrict__ dtw,
                           const float* __restrict__ dprobs_in, const float* __restrict__ dlogits_in,
                           const float* __restrict__ lse, const float* __restrict__ cnt, const float* __restrict__ g_losses,
-                          long long Tn, int N, int B, int D, int E, int K, float* __restrict__ dl_out, T* __restrict__ dx) {
+                          long long Tn, int N, int B, int D, int E, int K, int renorm_bf16, float* __restrict__ dl_out,
+                          T* __restrict__ dx) {
   const int lane = threadIdx.x & 31;
   const long long t = static_cast<long long>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
   if (t >= Tn) return;
@@ -768,15 +772,15 @@ router_bwd_dx_wide_kernel(const T* __restrict__ wg, const float* __restrict__ pr
       if (lane + 32 * c < E) d[c] += coef * cnt[b * E + lane + 32 * c];
   }
   if (dtw != nullptr) {
-    float s = 0.f, dot = 0.f;
+    float s = 0.f;
+    for (int k = 0; k < K; ++k) s += probs[t * E + topk_idx[t * K + k]];
+    if (renorm_bf16) s = bf16_round(s);
+    float dden = 0.f;
+    for (int k = 0; k < K; ++k) dden -= dtw[t * K + k] * (topk_w[t * K + k] / s);
+    if (renorm_bf16) dden = bf16_round(dden);
     for (int k = 0; k < K; ++k) {
       const int i = topk_idx[t * K + k];
-      s += probs[t * E + i];
-      dot += dtw[t * K + k] * topk_w[t * K + k];
-    }
-    for (int k = 0; k < K; ++k) {
-      const int i = topk_idx[t * K + k];
-      const float g = (dtw[t * K + k] - dot) / s;
+      const float g = dtw[t * K + k] / s + dden;
 #pragma unroll
       for (int c = 0; c < C; ++c)
         if (i == lane + 32 * c) d[c] += g;
@@ -815,45 +819,54 @@ router_bwd_dx_wide_kernel(const T* __restrict__ wg, const float* __restrict__ pr
   }
 }
 
-// host side: C = 4 up to 128 experts, 8 up to 256
+// ---- host side: two experts per lane up to 64 experts, C = 4 up to 128, C = 8 up to 256
 template <typename T>
-void launch_router_fwd_wide(unsigned grid, cudaStream_t stream, const T* x, const T* wg, long long Tn, int D, int E, int K,
-                            T* logits, float* probs, float* topk_w, int32_t* topk_idx) {
-  if (E <= 128)
-    router_fwd_wide_kernel<T, 4><<<grid, kWarpsPerBlock * 32, 0, stream>>>(x, wg, Tn, D, E, K, logits, probs, topk_w, topk_idx);
+void launch_router_fwd(unsigned grid, cudaStream_t stream, const T* x, const T* wg, long long Tn, int D, int E, int K, int rbf,
+                       T* logits, float* probs, float* topk_w, int32_t* topk_idx) {
+  if (E <= kMaxE)
+    router_fwd_kernel<T><<<grid, kWarpsPerBlock * 32, 0, stream>>>(x, wg, Tn, D, E, K, rbf, logits, probs, topk_w, topk_idx);
+  else if (E <= 128)
+    router_fwd_wide_kernel<T, 4><<<grid, kWarpsPerBlock * 32, 0, stream>>>(x, wg, Tn, D, E, K, rbf, logits, probs, topk_w, topk_idx);
   else
-    router_fwd_wide_kernel<T, 8><<<grid, kWarpsPerBlock * 32, 0, stream>>>(x, wg, Tn, D, E, K, logits, probs, topk_w, topk_idx);
+    router_fwd_wide_kernel<T, 8><<<grid, kWarpsPerBlock * 32, 0, stream>>>(x, wg, Tn, D, E, K, rbf, logits, probs, topk_w, topk_idx);
 }
 
 template <typename T>
-void launch_router_from_logits_wide(unsigned grid, cudaStream_t stream, const T* logits, long long Tn, int E, int K,
-                                    float* probs, float* topk_w, int32_t* topk_idx) {
-  if (E <= 128)
-    router_from_logits_wide_kernel<T, 4><<<grid, kWarpsPerBlock * 32, 0, stream>>>(logits, Tn, E, K, probs, topk_w, topk_idx);
+void launch_router_from_logits(unsigned grid, cudaStream_t stream, const T* logits, long long Tn, int E, int K, int rbf,
+                               float* probs, float* topk_w, int32_t* topk_idx) {
+  if (E <= kMaxE)
+    router_from_logits_kernel<T><<<grid, kWarpsPerBlock * 32, 0, stream>>>(logits, Tn, E, K, rbf, probs, topk_w, topk_idx);
+  else if (E <= 128)
+    router_from_logits_wide_kernel<T, 4><<<grid, kWarpsPerBlock * 32, 0, stream>>>(logits, Tn, E, K, rbf, probs, topk_w, topk_idx);
   else
-    router_from_logits_wide_kernel<T, 8><<<grid, kWarpsPerBlock * 32, 0, stream>>>(logits, Tn, E, K, probs, topk_w, topk_idx);
+    router_from_logits_wide_kernel<T, 8><<<grid, kWarpsPerBlock * 32, 0, stream>>>(logits, Tn, E, K, rbf, probs, topk_w, topk_idx);
 }
 
 template <typename T>
-void launch_router_aux_stage1_wide(unsigned grid, size_t smem, cudaStream_t stream, const T* logits, const float* probs,
-                                   const int32_t* topk_idx, int N, int E, int K, int chunks, float* partial, float* lse) {
-  if (E <= 128)
+void launch_router_aux_stage1(unsigned grid, size_t smem, cudaStream_t stream, const T* logits, const float* probs,
+                              const int32_t* topk_idx, int N, int E, int K, int chunks, float* partial, float* lse) {
+  if (E <= kMaxE)
+    router_aux_stage1<T><<<grid, kWarpsPerBlock * 32, smem, stream>>>(logits, probs, topk_idx, N, E, K, chunks, partial, lse);
+  else if (E <= 128)
     router_aux_stage1_wide<T, 4><<<grid, kWarpsPerBlock * 32, smem, stream>>>(logits, probs, topk_idx, N, E, K, chunks, partial, lse);
   else
     router_aux_stage1_wide<T, 8><<<grid, kWarpsPerBlock * 32, smem, stream>>>(logits, probs, topk_idx, N, E, K, chunks, partial, lse);
 }
 
 template <typename T>
-void launch_router_bwd_dx_wide(unsigned grid, cudaStream_t stream, const T* wg, const float* probs, const float* topk_w,
-                               const int32_t* topk_idx, const float* dtw, const float* dprobs, const float* dlogits,
-                               const float* lse, const float* cnt, const float* g_losses, long long Tn, int N, int B, int D,
-                               int E, int K, float* dl, T* dx) {
-  if (E <= 128)
+void launch_router_bwd_dx(unsigned grid, cudaStream_t stream, const T* wg, const float* probs, const float* topk_w,
+                          const int32_t* topk_idx, const float* dtw, const float* dprobs, const float* dlogits,
+                          const float* lse, const float* cnt, const float* g_losses, long long Tn, int N, int B, int D, int E,
+                          int K, int rbf, float* dl, T* dx) {
+  if (E <= kMaxE)
+    router_bwd_dx_kernel<T><<<grid, kWarpsPerBlock * 32, 0, stream>>>(wg, probs, topk_w, topk_idx, dtw, dprobs, dlogits, lse,
+                                                                       cnt, g_losses, Tn, N, B, D, E, K, rbf, dl, dx);
+  else if (E <= 128)
     router_bwd_dx_wide_kernel<T, 4><<<grid, kWarpsPerBlock * 32, 0, stream>>>(wg, probs, topk_w, topk_idx, dtw, dprobs, dlogits,
-                                                                               lse, cnt, g_losses, Tn, N, B, D, E, K, dl, dx);
+                                                                               lse, cnt, g_losses, Tn, N, B, D, E, K, rbf, dl, dx);
   else
     router_bwd_dx_wide_kernel<T, 8><<<grid, kWarpsPerBlock * 32, 0, stream>>>(wg, probs, topk_w, topk_idx, dtw, dprobs, dlogits,
-                                                                               lse, cnt, g_losses, Tn, N, B, D, E, K, dl, dx);
+                                                                               lse, cnt, g_losses, Tn, N, B, D, E, K, rbf, dl, dx);
 }
 
 }  // namespace
@@ -862,33 +875,25 @@ void launch_router_bwd_dx_wide(unsigned grid, cudaStream_t stream, const T* wg, 
 using namespace csmoe;
 
 extern "C" int csmoe_router_fwd(const void* x, const void* wg, int32_t x_dtype, int64_t T, int32_t D, int32_t E,
-                                int32_t K, void* logits, float* probs, float* topk_w, int32_t* topk_idx, void* stream_) {
+                                int32_t K, int32_t renorm_dtype, void* logits, float* probs, float* topk_w,
+                                int32_t* topk_idx, void* stream_) {
   CSMOE_CHECK_ARG(x && wg && logits && probs && topk_w && topk_idx, "csmoe_router_fwd: NULL pointer");
   CSMOE_CHECK_ARG(E >= 1 && E <= kMaxEWide, "csmoe_router_fwd: E must be in [1, %d], got %d", kMaxEWide, E);
   CSMOE_CHECK_ARG(K >= 1 && K <= kMaxK && K <= E, "csmoe_router_fwd: K must be in [1, min(E, %d)], got %d", kMaxK, K);
   CSMOE_CHECK_ARG(D > 0 && D % 8 == 0, "csmoe_router_fwd: D must be a positive multiple of 8");
   CSMOE_CHECK_ARG(T >= 0, "csmoe_router_fwd: T must be >= 0");
+  CSMOE_CHECK_ARG(renorm_dtype == CSMOE_BF16 || renorm_dtype == CSMOE_F32, "csmoe_router_fwd: bad renorm_dtype %d", renorm_dtype);
   if (T == 0) return CSMOE_OK;
   const unsigned grid = static_cast<unsigned>((T + kWarpsPerBlock - 1) / kWarpsPerBlock);
   cudaStream_t stream = as_stream(stream_);
-  if (E > kMaxE) {
-    if (x_dtype == CSMOE_BF16) {
-      launch_router_fwd_wide<__nv_bfloat16>(grid, stream, static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(wg),
-                                            T, D, E, K, static_cast<__nv_bfloat16*>(logits), probs, topk_w, topk_idx);
-    } else if (x_dtype == CSMOE_F32) {
-      launch_router_fwd_wide<float>(grid, stream, static_cast<const float*>(x), static_cast<const float*>(wg), T, D, E, K,
-                                    static_cast<float*>(logits), probs, topk_w, topk_idx);
-    } else {
-      CSMOE_CHECK_ARG(false, "csmoe_router_fwd: unsupported dtype %d", x_dtype);
-    }
-  } else if (x_dtype == CSMOE_BF16) {
-    router_fwd_kernel<__nv_bfloat16><<<grid, kWarpsPerBlock * 32, 0, stream>>>(
-        static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(wg), T, D, E, K,
-        static_cast<__nv_bfloat16*>(logits), probs, topk_w, topk_idx);
+  const int rbf = renorm_dtype == CSMOE_BF16;
+  if (x_dtype == CSMOE_BF16) {
+    using T_ = __nv_bfloat16;
+    launch_router_fwd<T_>(grid, stream, static_cast<const T_*>(x), static_cast<const T_*>(wg), T, D, E, K, rbf,
+                          static_cast<T_*>(logits), probs, topk_w, topk_idx);
   } else if (x_dtype == CSMOE_F32) {
-    router_fwd_kernel<float><<<grid, kWarpsPerBlock * 32, 0, stream>>>(static_cast<const float*>(x),
-                                                                       static_cast<const float*>(wg), T, D, E, K,
-                                                                       static_cast<float*>(logits), probs, topk_w, topk_idx);
+    launch_router_fwd<float>(grid, stream, static_cast<const float*>(x), static_cast<const float*>(wg), T, D, E, K, rbf,
+                             static_cast<float*>(logits), probs, topk_w, topk_idx);
   } else {
     CSMOE_CHECK_ARG(false, "csmoe_router_fwd: unsupported dtype %d", x_dtype);
   }
@@ -896,28 +901,21 @@ extern "C" int csmoe_router_fwd(const void* x, const void* wg, int32_t x_dtype, 
   return CSMOE_OK;
 }
 
-extern "C" int csmoe_router_from_logits(const void* logits, int32_t dtype, int64_t T, int32_t E, int32_t K, float* probs,
-                                        float* topk_w, int32_t* topk_idx, void* stream_) {
+extern "C" int csmoe_router_from_logits(const void* logits, int32_t dtype, int64_t T, int32_t E, int32_t K,
+                                        int32_t renorm_dtype, float* probs, float* topk_w, int32_t* topk_idx, void* stream_) {
   CSMOE_CHECK_ARG(logits && probs && topk_w && topk_idx, "csmoe_router_from_logits: NULL pointer");
   CSMOE_CHECK_ARG(E >= 1 && E <= kMaxEWide && K >= 1 && K <= kMaxK && K <= E && T >= 0, "csmoe_router_from_logits: bad sizes");
+  CSMOE_CHECK_ARG(renorm_dtype == CSMOE_BF16 || renorm_dtype == CSMOE_F32, "csmoe_router_from_logits: bad renorm_dtype %d",
+                  renorm_dtype);
   if (T == 0) return CSMOE_OK;
   const unsigned grid = static_cast<unsigned>((T + kWarpsPerBlock - 1) / kWarpsPerBlock);
   cudaStream_t stream = as_stream(stream_);
-  if (E > kMaxE) {
-    if (dtype == CSMOE_BF16) {
-      launch_router_from_logits_wide<__nv_bfloat16>(grid, stream, static_cast<const __nv_bfloat16*>(logits), T, E, K, probs,
-                                                    topk_w, topk_idx);
-    } else if (dtype == CSMOE_F32) {
-      launch_router_from_logits_wide<float>(grid, stream, static_cast<const float*>(logits), T, E, K, probs, topk_w, topk_idx);
-    } else {
-      CSMOE_CHECK_ARG(false, "csmoe_router_from_logits: unsupported dtype %d", dtype);
-    }
-  } else if (dtype == CSMOE_BF16) {
-    router_from_logits_kernel<__nv_bfloat16><<<grid, kWarpsPerBlock * 32, 0, stream>>>(
-        static_cast<const __nv_bfloat16*>(logits), T, E, K, probs, topk_w, topk_idx);
+  const int rbf = renorm_dtype == CSMOE_BF16;
+  if (dtype == CSMOE_BF16) {
+    launch_router_from_logits<__nv_bfloat16>(grid, stream, static_cast<const __nv_bfloat16*>(logits), T, E, K, rbf, probs, topk_w,
+                                             topk_idx);
   } else if (dtype == CSMOE_F32) {
-    router_from_logits_kernel<float><<<grid, kWarpsPerBlock * 32, 0, stream>>>(static_cast<const float*>(logits), T, E, K,
-                                                                               probs, topk_w, topk_idx);
+    launch_router_from_logits<float>(grid, stream, static_cast<const float*>(logits), T, E, K, rbf, probs, topk_w, topk_idx);
   } else {
     CSMOE_CHECK_ARG(false, "csmoe_router_from_logits: unsupported dtype %d", dtype);
   }
@@ -958,23 +956,12 @@ extern "C" int csmoe_router_aux_fwd(const void* logits, int32_t dtype, const flo
   const unsigned grid = static_cast<unsigned>(B * chunks);
   const size_t smem = kWarpsPerBlock * (2 * E + 1) * sizeof(float);
   float* partial = static_cast<float*>(workspace);
-  if (E > kMaxE) {
-    if (dtype == CSMOE_BF16) {
-      launch_router_aux_stage1_wide<__nv_bfloat16>(grid, smem, stream, static_cast<const __nv_bfloat16*>(logits), probs, topk_idx,
-                                                   static_cast<int>(N), E, K, chunks, partial, lse);
-    } else if (dtype == CSMOE_F32) {
-      launch_router_aux_stage1_wide<float>(grid, smem, stream, static_cast<const float*>(logits), probs, topk_idx,
-                                           static_cast<int>(N), E, K, chunks, partial, lse);
-    } else {
-      CSMOE_CHECK_ARG(false, "csmoe_router_aux_fwd: unsupported dtype %d", dtype);
-    }
-  } else if (dtype == CSMOE_BF16) {
-    router_aux_stage1<__nv_bfloat16><<<grid, kWarpsPerBlock * 32, smem, stream>>>(
-        static_cast<const __nv_bfloat16*>(logits), probs, topk_idx, static_cast<int>(N), E, K, chunks, partial, lse);
+  if (dtype == CSMOE_BF16) {
+    launch_router_aux_stage1<__nv_bfloat16>(grid, smem, stream, static_cast<const __nv_bfloat16*>(logits), probs, topk_idx,
+                                            static_cast<int>(N), E, K, chunks, partial, lse);
   } else if (dtype == CSMOE_F32) {
-    router_aux_stage1<float><<<grid, kWarpsPerBlock * 32, smem, stream>>>(static_cast<const float*>(logits), probs,
-                                                                          topk_idx, static_cast<int>(N), E, K, chunks,
-                                                                          partial, lse);
+    launch_router_aux_stage1<float>(grid, smem, stream, static_cast<const float*>(logits), probs, topk_idx, static_cast<int>(N),
+                                    E, K, chunks, partial, lse);
   } else {
     CSMOE_CHECK_ARG(false, "csmoe_router_aux_fwd: unsupported dtype %d", dtype);
   }
@@ -993,11 +980,12 @@ extern "C" int64_t csmoe_router_bwd_workspace_bytes(int64_t T, int32_t D, int32_
 extern "C" int csmoe_router_bwd(const void* x, const void* wg, int32_t x_dtype, const float* probs, const float* topk_w,
                                 const int32_t* topk_idx, const float* dtw, const float* dprobs, const float* dlogits,
                                 const float* lse, const float* cnt, const float* g_losses, int64_t B, int64_t N, int32_t D,
-                                int32_t E, int32_t K, float* dl, void* dx, void* dwg, int32_t wg_dtype, void* workspace,
-                                void* stream_) {
+                                int32_t E, int32_t K, int32_t renorm_dtype, float* dl, void* dx, void* dwg, int32_t wg_dtype,
+                                void* workspace, void* stream_) {
   CSMOE_CHECK_ARG(x && wg && probs && topk_w && topk_idx && dl, "csmoe_router_bwd: NULL pointer");
   CSMOE_CHECK_ARG(E >= 1 && E <= kMaxEWide && K >= 1 && K <= kMaxK && D > 0 && D % 8 == 0 && B >= 1 && N >= 1,
                   "csmoe_router_bwd: bad sizes");
+  CSMOE_CHECK_ARG(renorm_dtype == CSMOE_BF16 || renorm_dtype == CSMOE_F32, "csmoe_router_bwd: bad renorm_dtype %d", renorm_dtype);
   CSMOE_CHECK_ARG(dwg == nullptr || workspace != nullptr, "csmoe_router_bwd: dwg needs a workspace");
   cudaStream_t stream = as_stream(stream_);
   const long long T = B * N;
@@ -1007,15 +995,11 @@ extern "C" int csmoe_router_bwd(const void* x, const void* wg, int32_t x_dtype, 
   const long long ED = static_cast<long long>(E) * D;
   const unsigned g2 = static_cast<unsigned>((ED / 8 + 7) / 8);
   float* partial = static_cast<float*>(workspace);
+  const int rbf = renorm_dtype == CSMOE_BF16;
   if (x_dtype == CSMOE_BF16) {
     using T_ = __nv_bfloat16;
-    if (E > kMaxE)
-      launch_router_bwd_dx_wide<T_>(grid, stream, static_cast<const T_*>(wg), probs, topk_w, topk_idx, dtw, dprobs, dlogits, lse,
-                                    cnt, g_losses, T, static_cast<int>(N), static_cast<int>(B), D, E, K, dl, static_cast<T_*>(dx));
-    else
-      router_bwd_dx_kernel<T_><<<grid, kWarpsPerBlock * 32, 0, stream>>>(
-          static_cast<const T_*>(wg), probs, topk_w, topk_idx, dtw, dprobs, dlogits, lse, cnt, g_losses, T,
-          static_cast<int>(N), static_cast<int>(B), D, E, K, dl, static_cast<T_*>(dx));
+    launch_router_bwd_dx<T_>(grid, stream, static_cast<const T_*>(wg), probs, topk_w, topk_idx, dtw, dprobs, dlogits, lse, cnt,
+                             g_losses, T, static_cast<int>(N), static_cast<int>(B), D, E, K, rbf, dl, static_cast<T_*>(dx));
     CSMOE_CHECK_LAUNCH();
     if (dwg != nullptr) {
       router_bwd_dw_stage1<T_><<<g1, 128, 0, stream>>>(static_cast<const T_*>(x), dl, T, D, E, partial);
@@ -1027,14 +1011,9 @@ extern "C" int csmoe_router_bwd(const void* x, const void* wg, int32_t x_dtype, 
       CSMOE_CHECK_LAUNCH();
     }
   } else if (x_dtype == CSMOE_F32) {
-    if (E > kMaxE)
-      launch_router_bwd_dx_wide<float>(grid, stream, static_cast<const float*>(wg), probs, topk_w, topk_idx, dtw, dprobs, dlogits,
-                                       lse, cnt, g_losses, T, static_cast<int>(N), static_cast<int>(B), D, E, K, dl,
-                                       static_cast<float*>(dx));
-    else
-      router_bwd_dx_kernel<float><<<grid, kWarpsPerBlock * 32, 0, stream>>>(
-          static_cast<const float*>(wg), probs, topk_w, topk_idx, dtw, dprobs, dlogits, lse, cnt, g_losses, T,
-          static_cast<int>(N), static_cast<int>(B), D, E, K, dl, static_cast<float*>(dx));
+    launch_router_bwd_dx<float>(grid, stream, static_cast<const float*>(wg), probs, topk_w, topk_idx, dtw, dprobs, dlogits, lse,
+                                cnt, g_losses, T, static_cast<int>(N), static_cast<int>(B), D, E, K, rbf, dl,
+                                static_cast<float*>(dx));
     CSMOE_CHECK_LAUNCH();
     if (dwg != nullptr) {
       router_bwd_dw_stage1<float><<<g1, 128, 0, stream>>>(static_cast<const float*>(x), dl, T, D, E, partial);

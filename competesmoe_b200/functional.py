@@ -135,21 +135,22 @@ def _ffn_first(xp, w1, b1, spec: FFNSpec, **where):
 class GateFn(Function):
     """(x [T,D], wg [E,D]) -> logits [T,E] (x dtype), probs [T,E] f32, topk_w [T,K] f32, topk_idx [T,K] i32,
     losses [2] f32 = (balance loss, z-loss) of the router step (zeros unless want_aux).
+    renorm_dtype: dtype of the LAYER's input, to which the reference rounds the top-k sum (`.to(x.dtype)`); None = x's.
 
     Forward: csmoe_router_fwd (+ csmoe_router_aux_fwd).  Backward: one fused csmoe_router_bwd call folds the routing
     weight gradient, any incoming d probs / d logits and the two aux-loss gradients into d logits, then dx and dWg."""
 
     @staticmethod
-    def forward(ctx, x, wg, top_k: int, batch: int, want_aux: bool):
+    def forward(ctx, x, wg, top_k: int, batch: int, want_aux: bool, renorm_dtype=None):
         wgx = wg if wg.dtype == x.dtype else wg.to(x.dtype)
-        logits, probs, tw, ti = ops.router_fwd(x, wgx, top_k)
+        logits, probs, tw, ti = ops.router_fwd(x, wgx, top_k, renorm_dtype)
         cnt = lse = None
         if want_aux:
             losses, cnt, lse = ops.router_aux_fwd(logits, probs, ti, batch)
         else:
             losses = torch.zeros(2, dtype=torch.float32, device=x.device)
         ctx.save_for_backward(x, wgx, probs, tw, ti, cnt, lse)
-        ctx.batch, ctx.wg_dtype, ctx.want_aux = batch, wg.dtype, want_aux
+        ctx.batch, ctx.wg_dtype, ctx.want_aux, ctx.renorm_dtype = batch, wg.dtype, want_aux, renorm_dtype
         ctx.mark_non_differentiable(ti)
         return logits, probs, tw, ti, losses
 
@@ -160,8 +161,8 @@ class GateFn(Function):
         dx, dwg = ops.router_bwd(x, wgx, probs, tw, ti, ctx.batch, dtw=dtw, dprobs=dprobs, dlogits=dlogits,
                                  lse=lse if ctx.want_aux else None, cnt=cnt if ctx.want_aux else None,
                                  g_losses=dlosses if ctx.want_aux else None, need_dx=ctx.needs_input_grad[0],
-                                 need_dwg=ctx.needs_input_grad[1], wg_dtype=ctx.wg_dtype)
-        return dx, dwg, None, None, None
+                                 need_dwg=ctx.needs_input_grad[1], wg_dtype=ctx.wg_dtype, renorm_dtype=ctx.renorm_dtype)
+        return dx, dwg, None, None, None, None
 
 
 # ------------------------------------------------------------------------------------------------ sparse experts

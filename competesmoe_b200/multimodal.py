@@ -149,7 +149,7 @@ class MoeLayer(nn.Module):
         return res[0], res[1], None, dict(zip(names, res[2:]))
 
     def _graph_eligible(self, x, return_id_experts) -> bool:
-        return (self._graphs is not None and self.training and x.is_cuda and x.requires_grad
+        return (self._graphs is not None and self.training and x.is_cuda and x.requires_grad and x.numel() > 0
                 and torch.is_grad_enabled() and not return_id_experts
                 and not torch.cuda.is_current_stream_capturing())
 
@@ -374,9 +374,26 @@ class CompeteSMoE(MoeLayer):
                 return self._graphed_call(x, branch)
         return self._forward_impl(x, return_id_experts)
 
+    def _forward_empty(self, x, return_id_experts):
+        """No tokens (an empty micro-batch): nothing to launch.  The reference runs its ops on the empty tensors: an empty
+        output, and every loss it computes on this branch is a mean over zero tokens, i.e. NaN -- reproduced as is."""
+        B, N, _ = x.shape
+        compete = self._is_competition_step(x)
+        out = x.new_zeros(B, N, self.out_embed_dim) + x.sum() * 0          # keeps the output attached to x's graph
+        nan = x.new_full((), float("nan"))
+        self.last_routing = (torch.zeros(B, N, self.num_selected, dtype=torch.int32, device=x.device),
+                             torch.zeros(B, N, self.num_selected, dtype=torch.float32, device=x.device))
+        if compete:
+            return out, nan, None, {"balance_loss": nan.clone(), "diversity_loss": nan.clone(), "routerloss": nan.clone()}
+        if x.requires_grad or return_id_experts:
+            return out, nan, None, {"balance_loss": nan.clone(), "router_z_loss": nan.clone()}
+        return out, x.new_zeros(()), None, {}
+
     def _forward_impl(self, x, return_id_experts=False):
         B, N, D = x.shape
         T, E, K = B * N, self.num_of_experts, self.num_selected
+        if T == 0 and self._ep is None:      # under expert parallelism a rank without tokens still takes part in the exchange
+            return self._forward_empty(x, return_id_experts)
         x2 = x.reshape(T, D)
         lay, w1, b1, w2, b2 = self._stacked_weights()
         spec = self._spec(lay, x2)

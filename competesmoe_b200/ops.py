@@ -137,8 +137,16 @@ def _router_gemm_ok(T: int, D: int, E: int, dtype: torch.dtype) -> bool:
     return _ROUTER_GEMM and dtype == torch.bfloat16 and E >= 16 and E % 8 == 0 and T >= 256 and T % ROW_TILE == 0 and D % 64 == 0
 
 
-def router_fwd(x: torch.Tensor, wg: torch.Tensor, top_k: int):
-    """x [T, D], wg [E, D] (same dtype) -> logits [T,E] (x dtype), probs [T,E] f32, topk_w [T,K] f32, topk_idx [T,K] i32."""
+def _renorm_dt(renorm_dtype: Optional[torch.dtype], default: torch.dtype) -> int:
+    """dtype the reference rounds the routing-weight denominator to (`.to(x.dtype)`, x = the layer's input)."""
+    rd = default if renorm_dtype is None else renorm_dtype
+    return BF16 if rd == torch.bfloat16 else F32
+
+
+def router_fwd(x: torch.Tensor, wg: torch.Tensor, top_k: int, renorm_dtype: Optional[torch.dtype] = None):
+    """x [T, D], wg [E, D] (same dtype) -> logits [T,E] (x dtype), probs [T,E] f32, topk_w [T,K] f32, topk_idx [T,K] i32.
+    renorm_dtype: dtype of the layer input whose `.to(x.dtype)` rounds the top-k sum (default: x's own dtype; fp32 for
+    fp32 inputs that were cast to bf16 under autocast)."""
     _cuda(x, wg)
     assert x.dim() == 2 and wg.dim() == 2 and x.shape[1] == wg.shape[1] and x.dtype == wg.dtype
     x, wg = x.contiguous(), wg.contiguous()
@@ -150,13 +158,14 @@ def router_fwd(x: torch.Tensor, wg: torch.Tensor, top_k: int):
     if _router_gemm_ok(T, D, E, x.dtype):
         # many experts: logits = x . Wg^T as a one-"expert" dense grouped GEMM, then softmax / top-k from the logits
         logits = gemm_rows(x, wg.unsqueeze(0), w_is_kn=False, dense_rows=T, a_expert_rows=0)
-        return (logits,) + router_from_logits(logits, top_k, out=(probs, tw, ti))
+        return (logits,) + router_from_logits(logits, top_k, out=(probs, tw, ti), renorm_dtype=renorm_dtype)
     logits = torch.empty(T, E, dtype=x.dtype, device=x.device)
-    _call("csmoe_router_fwd", _p(x), _p(wg), _dt(x), T, D, E, top_k, _p(logits), _p(probs), _p(tw), _p(ti), _stream())
+    _call("csmoe_router_fwd", _p(x), _p(wg), _dt(x), T, D, E, top_k, _renorm_dt(renorm_dtype, x.dtype), _p(logits), _p(probs),
+          _p(tw), _p(ti), _stream())
     return logits, probs, tw, ti
 
 
-def router_from_logits(logits: torch.Tensor, top_k: int, out=None):
+def router_from_logits(logits: torch.Tensor, top_k: int, out=None, renorm_dtype: Optional[torch.dtype] = None):
     """logits [T, E] (activation dtype, already rounded) -> probs [T,E] f32, topk_w [T,K] f32, topk_idx [T,K] i32: the
     softmax / top-k / renormalisation half of router_fwd, bit-identical to it on the same logits."""
     _cuda(logits)
@@ -167,7 +176,8 @@ def router_from_logits(logits: torch.Tensor, top_k: int, out=None):
                torch.empty(T, top_k, dtype=torch.float32, device=logits.device),
                torch.empty(T, top_k, dtype=torch.int32, device=logits.device))
     probs, tw, ti = out
-    _call("csmoe_router_from_logits", _p(logits), _dt(logits), T, E, top_k, _p(probs), _p(tw), _p(ti), _stream())
+    _call("csmoe_router_from_logits", _p(logits), _dt(logits), T, E, top_k, _renorm_dt(renorm_dtype, logits.dtype), _p(probs),
+          _p(tw), _p(ti), _stream())
     return probs, tw, ti
 
 
@@ -192,7 +202,8 @@ def router_aux_fwd(logits: torch.Tensor, probs: torch.Tensor, topk_idx: torch.Te
 
 def router_bwd(x: torch.Tensor, wg: torch.Tensor, probs: torch.Tensor, topk_w: torch.Tensor, topk_idx: torch.Tensor,
                batch: int, *, dtw=None, dprobs=None, dlogits=None, lse=None, cnt=None, g_losses=None,
-               need_dx: bool = True, need_dwg: bool = True, wg_dtype: Optional[torch.dtype] = None):
+               need_dx: bool = True, need_dwg: bool = True, wg_dtype: Optional[torch.dtype] = None,
+               renorm_dtype: Optional[torch.dtype] = None):
     """Fused router backward -> (dx [T,D] x.dtype or None, dwg [E,D] or None)."""
     _cuda(x, wg, probs, topk_w, topk_idx, dtw, dprobs, dlogits, lse, cnt, g_losses)
     T, D = x.shape
@@ -203,12 +214,13 @@ def router_bwd(x: torch.Tensor, wg: torch.Tensor, probs: torch.Tensor, topk_w: t
     f32 = lambda t: None if t is None else t.contiguous().float()  # noqa: E731
     dtw, dprobs, dlogits, g_losses = f32(dtw), f32(dprobs), f32(dlogits), f32(g_losses)
     wg_dtype = wg_dtype or wg.dtype
+    rdt = _renorm_dt(renorm_dtype, x.dtype)
     dl = torch.empty(T, E, dtype=torch.float32, device=dev)
     if _router_gemm_ok(T, D, E, x.dtype) and wg_dtype in (torch.bfloat16, torch.float32):
         # many experts: only d logits comes from the fused kernel; dx = dl . Wg and dWg = dl^T . x run on the tensor
         # cores with dl rounded to the activation dtype (what autograd hands the reference's bf16 gate Linear)
         _call("csmoe_router_bwd", _p(x), _p(wg), _dt(x), _p(probs), _p(topk_w), _p(topk_idx), _p(dtw), _p(dprobs),
-              _p(dlogits), _p(lse), _p(cnt), _p(g_losses), batch, N, D, E, K, _p(dl), None, None, F32, None, _stream())
+              _p(dlogits), _p(lse), _p(cnt), _p(g_losses), batch, N, D, E, K, rdt, _p(dl), None, None, F32, None, _stream())
         dlb = dl.to(x.dtype)
         dx = gemm_rows(dlb, wg.unsqueeze(0), w_is_kn=True, dense_rows=T, a_expert_rows=0) if need_dx else None
         dwg = None
@@ -232,7 +244,7 @@ def router_bwd(x: torch.Tensor, wg: torch.Tensor, probs: torch.Tensor, topk_w: t
     if need_dwg:
         ws = torch.empty(int(_lib.load().csmoe_router_bwd_workspace_bytes(T, D, E)) // 4, dtype=torch.float32, device=dev)
     _call("csmoe_router_bwd", _p(x), _p(wg), _dt(x), _p(probs), _p(topk_w), _p(topk_idx), _p(dtw), _p(dprobs),
-          _p(dlogits), _p(lse), _p(cnt), _p(g_losses), batch, N, D, E, K, _p(dl), _p(dx), _p(dwg),
+          _p(dlogits), _p(lse), _p(cnt), _p(g_losses), batch, N, D, E, K, rdt, _p(dl), _p(dx), _p(dwg),
           _dt(dwg) if dwg is not None else F32, _p(ws), _stream(), kernels=3 if need_dwg else 1)
     return dx, dwg
 

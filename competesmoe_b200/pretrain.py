@@ -446,8 +446,9 @@ class MoE(LoggingLayer, RegularizedLayer, OncePerIterLayer, torch.nn.Module):
         return FFNSpec(act=self._act_code, kn_layout=True, round_each=False, round_w=cdt == torch.bfloat16,
                        bias_after_round=True, fp32=cdt == torch.float32)
 
-    def compute_gate(self, x2: torch.Tensor, cdt: torch.dtype):
-        return GateFn.apply(self._cast(x2, cdt), self.w_gate, self.num_selected, 1, False)[:4]
+    def compute_gate(self, x2: torch.Tensor, cdt: torch.dtype, x_dtype: Optional[torch.dtype] = None):
+        """x_dtype: the layer input's dtype, to which the reference rounds the sum of the top-k weights (`.to(x.dtype)`)."""
+        return GateFn.apply(self._cast(x2, cdt), self.w_gate, self.num_selected, 1, False, x_dtype)[:4]
 
     def _plot_training(self) -> bool:
         """moe.py:405: `self.train and log_interval is not None and iter % log_interval == 0` (`self.train` is the bound
@@ -603,22 +604,24 @@ class CompeteSMoE(MoE):
             self.iter += 1
 
     # ---- policies
-    def compute_gate(self, x2: torch.Tensor, cdt: torch.dtype):
-        """competesmoe.py:456-464: plain, cosine, or weight-normalised gate."""
+    def compute_gate(self, x2: torch.Tensor, cdt: torch.dtype, x_dtype: Optional[torch.dtype] = None):
+        """competesmoe.py:456-464: plain, cosine, or weight-normalised gate.  x_dtype: dtype of the layer input, which the
+        reference rounds the top-k sum to (`.to(x.dtype)`, :489): fp32 for fp32 inputs under autocast, so no rounding."""
         a = self.args
         if getattr(a, "is_cosine", False) and not getattr(a, "is_norm_weight", False):
             return GateFn.apply(F.normalize(x2.float(), p=2.0, dim=-1).to(cdt), F.normalize(self.w_gate, p=2.0, dim=-1),
-                                self.num_selected, 1, False)[:4]
+                                self.num_selected, 1, False, x_dtype)[:4]
         if getattr(a, "is_norm_weight", False):
-            return GateFn.apply(self._cast(x2, cdt), F.normalize(self.w_gate, p=2.0, dim=-1), self.num_selected, 1, False)[:4]
-        return GateFn.apply(self._cast(x2, cdt), self.w_gate, self.num_selected, 1, False)[:4]
+            return GateFn.apply(self._cast(x2, cdt), F.normalize(self.w_gate, p=2.0, dim=-1), self.num_selected, 1, False,
+                                x_dtype)[:4]
+        return GateFn.apply(self._cast(x2, cdt), self.w_gate, self.num_selected, 1, False, x_dtype)[:4]
 
     def router_policy(self, x2, cdt, x_dtype):
         """competesmoe.py:465-490."""
         a = self.args
         assert not (getattr(a, "is_cosine", False) and getattr(a, "is_norm_weight", False)), \
             "Can not active  both  Cosine and Norm Weigh. Just use one method - Cosine or Norm Weigh to Normalization"
-        logits, probs, gw, gidx = self.compute_gate(x2, cdt)
+        logits, probs, gw, gidx = self.compute_gate(x2, cdt, x_dtype)
         if getattr(a, "norm_sigmoid", False):
             scale = float(getattr(a, "scale_weight", 1.0))
             gw, gidx = TopkRenormFn.apply(logits.float() / scale, self.num_selected, True, x_dtype)
@@ -646,6 +649,15 @@ class CompeteSMoE(MoE):
         x2 = x.reshape(-1, x.shape[-1])
         T, E, K = x2.shape[0], self.n_experts, self.num_selected
         is_comp = self._is_competition_step(x, id_layer)
+        if T == 0 and self._ep is None:      # (under expert parallelism a rank without tokens still takes part in the exchange)
+            # The reference cannot train on an empty batch: entropy_balance takes math.log(0) (moe.py:323-332 -> ValueError)
+            # and the competition's `.view(B, N, -1)` is ambiguous (competesmoe.py:399 -> RuntimeError).  Without
+            # regularisers its router branch returns an empty result, and so does this.
+            if is_comp or self.reg_enabled:
+                raise ValueError("CompeteSMoE.forward: no tokens in the batch (math domain error in the reference's "
+                                 "entropy_balance / ambiguous view in its competition step)")
+            res = x.new_zeros(*lead, self.v_dim) + x.sum() * 0
+            return res + self.o_bias if self.o_bias is not None else res
         # dtype the reference layer would see: a fused pre-LN hands the input over already cast (pretrain_block.py), but
         # the `.to(x.dtype)` roundings of the reference refer to the LayerNorm's output dtype
         xdt = self._x_dtype or x.dtype

@@ -45,7 +45,7 @@ class SMoeLayer(_SiblingBase):
     def forward(self, x, return_id_experts=False, return_full=True, *args, **kwargs):
         cdt = self._compute_dtype(x)
         x2 = x.reshape(-1, x.shape[-1])
-        logits, probs, gw, gidx = self.compute_gate(x2, cdt)
+        logits, probs, gw, gidx = self.compute_gate(x2, cdt, self._x_dtype or x.dtype)     # smoe.py:238 `.to(x.dtype)`
         out = self.compute_moe_main(x2, gidx, gw, cdt)
         return self._finish(x, out, logits, gidx, gw, probs)
 

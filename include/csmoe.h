@@ -17,7 +17,7 @@
 extern "C" {
 #endif
 
-#define CSMOE_ABI_VERSION 1
+#define CSMOE_ABI_VERSION 2
 
 typedef enum csmoe_status {
   CSMOE_OK = 0,
@@ -69,16 +69,18 @@ int csmoe_route_build(const int32_t* sel, int64_t n_slots, int32_t num_experts, 
 /* ------------------------------------------------------------------------------------------------ router
  * Replaces router_policy + topk_expert (moe_model/model/moe/competesmoe.py:301-320, moe.py:113-132;
  * moe_pretrain_model/layers/moe/competesmoe.py:465-490): logits = x @ Wg^T (fp32 accumulate, rounded to `x_dtype`),
- * p = softmax_fp32(logits), (w, idx) = topk(p, K) (descending, ties -> lowest index), w /= round_to_x_dtype(sum w).
+ * p = softmax_fp32(logits), (w, idx) = topk(p, K) (descending, ties -> lowest index), w /= round_to(renorm_dtype)(sum w):
+ * the reference's `.to(x.dtype)` on the denominator refers to the LAYER INPUT, which is the activation dtype for a bf16
+ * model and fp32 for fp32 inputs run under autocast (then x_dtype = bf16, renorm_dtype = fp32).
  * x[T,D] and wg[E,D] share x_dtype (bf16 or fp32).  Outputs: logits[T,E] (x_dtype), probs[T,E] fp32, topk_w[T,K] fp32,
  * topk_idx[T,K] int32.  E <= 256 (two experts per lane up to 64, four / eight per lane above), K <= 8. */
 int csmoe_router_fwd(const void* x, const void* wg, int32_t x_dtype, int64_t T, int32_t D, int32_t E, int32_t K,
-                     void* logits, float* probs, float* topk_w, int32_t* topk_idx, void* stream);
+                     int32_t renorm_dtype, void* logits, float* probs, float* topk_w, int32_t* topk_idx, void* stream);
 
 /* The softmax / top-k / renormalisation half of csmoe_router_fwd for logits [T, E] that were produced elsewhere (the
  * gate GEMM on the tensor cores when E is large: csmoe_grouped_gemm with one "expert" = the gate matrix). */
-int csmoe_router_from_logits(const void* logits, int32_t dtype, int64_t T, int32_t E, int32_t K, float* probs,
-                             float* topk_w, int32_t* topk_idx, void* stream);
+int csmoe_router_from_logits(const void* logits, int32_t dtype, int64_t T, int32_t E, int32_t K, int32_t renorm_dtype,
+                             float* probs, float* topk_w, int32_t* topk_idx, void* stream);
 /* Top-k over given fp32 scores[T,E] (competition step: affinity scores; moe_model/.../competesmoe.py:249-254).
  * mode 0: w = topk values; mode 1: w = sigmoid(topk values) (norm_sigmoid).  Then w /= round_to(dtype)(sum w). */
 int csmoe_topk_renorm(const float* scores, int64_t T, int32_t E, int32_t K, int32_t mode, int32_t round_dtype,
@@ -98,12 +100,15 @@ int csmoe_router_aux_fwd(const void* logits, int32_t dtype, const float* probs, 
  * dtw[T,K], an incoming dprobs[T,E] (e.g. router-distillation MSE), an incoming dlogits[T,E], and the balance / z
  * losses (g_losses[2] = d loss / d balance, d loss / d z on the device; cnt and lse from csmoe_router_aux_fwd);
  * then dx[T,D] = dl . Wg (may be NULL) and dWg[E,D] = dl^T . x (may be NULL; deterministic two-stage reduction).
+ * The routing-weight term follows autograd through `w / sum(w).to(dtype)`: numerator gradient dtw / r in fp32, denominator
+ * gradient -sum_k dtw_k (w_k / r) rounded to renorm_dtype (r = the rounded denominator of the forward pass).
  * dl[T,E] (fp32 storage, values rounded to x_dtype) is an output.  workspace: csmoe_router_bwd_workspace_bytes. */
 int64_t csmoe_router_bwd_workspace_bytes(int64_t T, int32_t D, int32_t E);
 int csmoe_router_bwd(const void* x, const void* wg, int32_t x_dtype, const float* probs, const float* topk_w,
                      const int32_t* topk_idx, const float* dtw, const float* dprobs, const float* dlogits,
                      const float* lse, const float* cnt, const float* g_losses, int64_t B, int64_t N, int32_t D, int32_t E,
-                     int32_t K, float* dl, void* dx, void* dwg, int32_t wg_dtype, void* workspace, void* stream);
+                     int32_t K, int32_t renorm_dtype, float* dl, void* dx, void* dwg, int32_t wg_dtype, void* workspace,
+                     void* stream);
 
 /* ------------------------------------------------------------------------------------------------ permutation
  * Gather rows of src[T, D] into the padded expert-major space: dst[row] = scale(row) * src[row_to_slot[row] / K],

@@ -633,6 +633,53 @@ def test_router_from_logits_equals_fused_router(ops, dtype, T, D, E, K):
 
 
 @WIDE
+@pytest.mark.parametrize("B,N,D,E,K", [(1, 131, 128, 8, 1), (2, 90, 64, 8, 2), (1, 70, 128, 128, 1), (1, 64, 64, 4, 4)])
+def test_router_backward_reproduces_autograd_through_the_rounded_denominator(ops, B, N, D, E, K):
+    """bf16 model: w = topk(p) / sum(topk(p)).to(bf16) (moe.py:131).  Autograd hands the numerator dtw / r in fp32 and the
+    denominator -sum_k dtw_k (w_k / r) rounded to bf16; for top-1 the two cancel to the last bf16 digit and what is left
+    is that rounding.  Fed with the same dtw the kernel gives autograd's dx and d gate: all but a few elements bit for bit
+    (torch's softmax differs from the kernel's in the last fp32 digit), every element within the bf16 band."""
+    g = torch.Generator().manual_seed(3 + K)
+    x = torch.randn(B * N, D, generator=g).bfloat16()
+    wg = (torch.randn(E, D, generator=g) * 0.3).bfloat16()
+    dtw = torch.randn(B * N, K, generator=g) * 8
+    xr, wr = x.clone().requires_grad_(True), wg.clone().requires_grad_(True)
+    w_ref, idx_ref, p_ref, _ = om.router_policy(xr.view(B, N, D), wr, K)
+    (w_ref * dtw.view(B, N, K)).sum().backward()
+    logits, probs, tw, ti = ops.router_fwd(x.to(DEV), wg.to(DEV), K)
+    margin = om.topk_margin(p_ref[0], K) if K < E else torch.ones(N)
+    if not torch.equal(ti.cpu().long().view(B, N, K), idx_ref):
+        assert bool((margin.min() < 1e-3)), "routing differs on a clear margin"
+        pytest.skip("a low-margin token routes differently: the gradients are not comparable element by element")
+    dx, dwg = ops.router_bwd(x.to(DEV), wg.to(DEV), probs, tw, ti, B, dtw=dtw.to(DEV))
+    for got, ref, nm in ((dx, xr.grad, "dx"), (dwg, wr.grad, "d gate")):
+        same = float((got.cpu() == ref).float().mean())
+        assert same >= 0.9, f"{nm}: only {same:.3f} of the elements are bit-identical to autograd's"
+        assert_close_rms(got, ref, 2e-2, nm)
+
+
+@WIDE
+def test_router_renorm_dtype_is_the_layer_inputs(ops):
+    """fp32 inputs under autocast (pretrain plugin): bf16 activations, but the reference's `.to(x.dtype)` is fp32 -- the
+    top-k weights sum to one in fp32, a top-1 weight is exactly 1 and carries (up to fp32 rounding) no gradient."""
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(200, 64, generator=g).bfloat16().to(DEV)
+    wg = (torch.randn(8, 64, generator=g) * 0.3).bfloat16().to(DEV)
+    _, probs, w_bf, idx_bf = ops.router_fwd(x, wg, 2)
+    _, probs2, w_f, idx_f = ops.router_fwd(x, wg, 2, renorm_dtype=torch.float32)
+    assert torch.equal(idx_bf, idx_f) and torch.equal(probs, probs2)
+    top = torch.gather(probs, 1, idx_f.long())
+    assert torch.equal(w_f, top / top.sum(-1, keepdim=True))
+    assert torch.equal(w_bf, top / top.sum(-1, keepdim=True).bfloat16().float()) and not torch.equal(w_bf, w_f)
+    _, probs1, w1, i1 = ops.router_fwd(x, wg, 1, renorm_dtype=torch.float32)
+    assert bool((w1 == 1).all())
+    dtw = torch.randn(200, 1, generator=g).to(DEV)
+    dx, dwg = ops.router_bwd(x, wg, probs1, w1, i1, 1, dtw=dtw, renorm_dtype=torch.float32)
+    # dtw / p - dtw * (1 / p): zero up to the last fp32 digit of the two quotients (autograd's own expression)
+    assert float(dx.float().abs().max()) < 1e-6 and float(dwg.float().abs().max()) < 1e-5
+
+
+@WIDE
 def test_router_tie_break_is_lowest_index_wide(ops):
     x = torch.zeros(8, 64, device=DEV, dtype=torch.bfloat16)
     wg = torch.randn(160, 64, device=DEV, dtype=torch.bfloat16)

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.load()
     for name in declared_symbols():
         assert hasattr(lib, name), name
-    assert lib.csmoe_abi_version() == 1
+    assert lib.csmoe_abi_version() == _lib.ABI_VERSION == 2
 
 
 def test_row_cap_and_workspace_queries():
@@ -43,7 +43,7 @@ def test_argument_errors_are_status_codes():
     # NULL args struct -> CSMOE_ERR_ARG, with a message; must not crash even without a GPU
     assert lib.csmoe_grouped_gemm(None, None) == -1
     assert b"NULL" in lib.csmoe_last_error()
-    assert lib.csmoe_router_fwd(None, None, 1, 4, 64, 4, 2, None, None, None, None, None) == -1
+    assert lib.csmoe_router_fwd(None, None, 1, 4, 64, 4, 2, 1, None, None, None, None, None) == -1
     g = _lib.GemmArgs()
     g.a = g.b = g.c = 16
     g.mode, g.num_experts, g.m, g.n, g.k = 0, 1, 128, 12, 64   # n not a multiple of 8

@@ -19,6 +19,7 @@ import pytest
 import torch
 
 import simt_host
+import test_gpu_edge_cases as ge
 import test_gpu_fp32 as gf
 import test_gpu_multimodal as gm
 import test_gpu_pretrain as gp
@@ -60,7 +61,7 @@ def emulated(tmp_path_factory):
     mp.setattr(torch, "is_autocast_enabled", lambda *a: state["on"])
     mp.setattr(torch, "get_autocast_dtype", lambda dev: state["dtype"])
     mp.setattr(torch.cuda, "is_current_stream_capturing", lambda: False)
-    for mod in (gm, gp, gs, gps, gf):
+    for mod in (gm, gp, gs, gps, gf, ge):
         mp.setattr(mod, "DEV", "cpu")
         if hasattr(mod, "load_golden"):
             mp.setattr(mod, "load_golden", (lambda f: lambda name: _Fresh(f(name)))(mod.load_golden))
@@ -137,3 +138,29 @@ def test_multimodal_fp32_module_matches_reference_at_1e4(name):
 @pytest.mark.parametrize("name", ["pt_router_f32", "pt_comp_tribrid_f32", "pt_router_e128_f32", "pt_comp_e128_f32"])
 def test_pretrain_fp32_without_autocast_matches_reference_at_1e4(name):
     gf.test_pretrain_fp32_without_autocast_matches_reference_at_1e4(name)
+
+
+# ------------------------------------------------------------------------------------------------ edge shapes, both plugins
+@pytest.mark.parametrize("competition", [False, True])
+@pytest.mark.parametrize("case", list(ge.MM_EDGE))
+def test_multimodal_edge_shape_matches_oracle(case, competition):
+    ge.test_multimodal_edge_shape_matches_oracle(case, competition)
+
+
+@pytest.mark.parametrize("competition", [False, True])
+def test_multimodal_non_contiguous_input_without_gradient_and_zero_tokens(competition):
+    ge.test_multimodal_non_contiguous_input(competition)
+    ge.test_multimodal_input_without_gradient(competition)
+    ge.test_multimodal_zero_tokens(competition)
+
+
+@pytest.mark.parametrize("competition", [False, True])
+@pytest.mark.parametrize("case", list(ge.PT_EDGE))
+def test_pretrain_edge_shape_matches_oracle(case, competition):
+    ge.test_pretrain_edge_shape_matches_oracle(case, competition)
+
+
+@pytest.mark.parametrize("competition", [False, True])
+def test_pretrain_non_contiguous_input_and_zero_tokens(competition):
+    ge.test_pretrain_non_contiguous_input(competition)
+    ge.test_pretrain_zero_tokens(competition)
