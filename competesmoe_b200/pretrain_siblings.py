@@ -60,7 +60,7 @@ class SMoEUTNorm(_SiblingBase):
         cdt = self._compute_dtype(x)
         x2 = x.reshape(-1, x.shape[-1])
         logits, probs, _, _ = self.compute_gate(x2, cdt)
-        gw, gidx = TopkRenormFn.apply(logits.float(), self.num_selected, True, x.dtype)
+        gw, gidx = TopkRenormFn.apply(logits.float(), self.num_selected, True, self._x_dtype or x.dtype)
         out = self.compute_moe_main(x2, gidx, gw, cdt)
         return self._finish(x, out, logits, gidx, gw, torch.sigmoid(logits.float()).softmax(dim=-1))
 
@@ -101,7 +101,7 @@ class _CosineGate(_SiblingBase):
         gate_logits = self._cosine(reduced, self.expert_embeddings)
         ok = gate_logits.isfinite()
         gate_logits = torch.where(ok, gate_logits, gate_logits.masked_fill(~ok, float("inf")).min())
-        gate_softmax = F.softmax(gate_logits / self.temperature, dim=-1, dtype=torch.float).to(x.dtype)
+        gate_softmax = F.softmax(gate_logits / self.temperature, dim=-1, dtype=torch.float).to(self._x_dtype or x.dtype)
         _, gidx = ops.topk_renorm(gate_softmax.detach().float(), K)
         kept = torch.gather(gate_softmax, 1, gidx.long())
         gw = torch.softmax(kept, dim=-1).float()
@@ -156,7 +156,7 @@ class DeepSeekV2(_SharedExpert):
         x2 = x.reshape(-1, x.shape[-1])
         logits, probs, _, _ = self.compute_gate(x2, cdt)
         _, gidx = ops.topk_renorm(logits.detach().float(), self.num_selected)
-        gw = F.softmax(torch.gather(logits, 1, gidx.long()), dim=-1).to(x.dtype).float()
+        gw = F.softmax(torch.gather(logits, 1, gidx.long()), dim=-1).to(self._x_dtype or x.dtype).float()
         out = self.compute_moe_main(x2, gidx, gw, cdt) + self._shared_out(x2, cdt)
         return self._finish(x, out, logits, gidx, gw, probs)
 
