@@ -199,7 +199,7 @@ PT_EDGE = {
     "top-1": dict(B=1, N=77, D=64, H=32, E=8, K=1),
     "single expert": dict(B=2, N=9, D=64, H=32, E=1, K=1),
     "odd sizes": dict(B=3, N=43, D=72, H=24, E=5, K=3),
-    "expert size 128": dict(B=2, N=65, D=64, H=128, E=8, K=2),        # the fused sigma-MoE kernels on the GPU
+    "expert size 128": dict(B=2, N=65, D=128, H=128, E=8, K=2),       # the fused sigma-MoE kernels on the GPU
 }
 
 

@@ -164,3 +164,32 @@ def test_pretrain_edge_shape_matches_oracle(case, competition):
 def test_pretrain_non_contiguous_input_and_zero_tokens(competition):
     ge.test_pretrain_non_contiguous_input(competition)
     ge.test_pretrain_zero_tokens(competition)
+
+
+# ------------------------------------------------------------------------------------------------ gate GEMM branch of the router ops
+@pytest.mark.parametrize("T,D,E,K", [(256, 64, 16, 2), (512, 128, 128, 8)])
+@pytest.mark.parametrize("renorm", [None, torch.float32])
+def test_router_ops_gate_gemm_branch_matches_the_fused_kernels(T, D, E, K, renorm, monkeypatch):
+    """ops.router_fwd / router_bwd take the tensor-core gate GEMM for E >= 16 on full row tiles (csmoe_router_from_logits,
+    dx / dWg as grouped GEMMs).  The host wiring of that branch -- here over the plain-loop GEMM stand-in -- against the
+    fused CUDA-core kernels on the same inputs: same routing, same weights, gradients to bf16 rounding."""
+    from competesmoe_b200 import ops
+    g = torch.Generator().manual_seed(T + E)
+    x = torch.randn(T, D, generator=g).bfloat16()
+    wg = (torch.randn(E, D, generator=g) * 0.1).bfloat16()
+    dtw = torch.randn(T, K, generator=g)
+    res = {}
+    for flag in (False, True):
+        monkeypatch.setattr(ops, "_ROUTER_GEMM", flag)
+        assert ops._router_gemm_ok(T, D, E, x.dtype) == flag
+        logits, probs, tw, ti = ops.router_fwd(x, wg, K, renorm_dtype=renorm)
+        dx, dwg = ops.router_bwd(x, wg, probs, tw, ti, 1, dtw=dtw, renorm_dtype=renorm)
+        res[flag] = (logits, probs, tw, ti, dx, dwg)
+    a, b = res[False], res[True]
+    gf.assert_close_rms(b[0], a[0], 1e-2, "logits")
+    same = (a[3] == b[3]).all(-1)
+    assert float(same.float().mean()) > 0.98                      # a bf16 ulp on a logit may swap a near-tie
+    torch.testing.assert_close(b[2][same], a[2][same], rtol=2e-2, atol=1e-4)
+    if bool(same.all()):
+        gf.assert_close_rms(b[4], a[4], 2e-2, "dx")
+        gf.assert_close_rms(b[5], a[5], 2e-2, "d gate")
