@@ -121,10 +121,18 @@ class CVMM(Function):
     @staticmethod
     def forward(ctx, x, keys, route: ops.Route, slots_per_row: int, reduction_weight, out_dtype):
         x2 = x.flatten(end_dim=-2)
-        xb = ops.cast_bf16(x2) if x2.dtype != torch.bfloat16 else x2
-        kb = ops.cast_bf16(keys) if keys.dtype != torch.bfloat16 else keys
-        xp = ops.gather_rows(xb, route, slots_per_src_row=slots_per_row)
-        yp = ops.gemm_rows(xp, kb, w_is_kn=True, route=route, out_dtype=out_dtype)
+        # Outside autocast the reference computes in fp32 (get_dtype(), cvmm.py:29-32; allow_tf32=False, :395): fp32
+        # operands then take the fp32-accurate products (six split-bf16 tensor-core GEMMs, fp32 accumulation) instead of
+        # one bf16 product -- rtol 1e-4 against the reference instead of 1e-2.
+        ctx.fp32 = fp32 = out_dtype == torch.float32 and (x2.dtype == torch.float32 or keys.dtype == torch.float32)
+        if fp32:
+            xp = ops.gather_rows(x2.float(), route, slots_per_src_row=slots_per_row)
+            yp = ops.gemm_rows_f32(xp, keys.float(), w_is_kn=True, route=route)
+        else:
+            xb = ops.cast_bf16(x2) if x2.dtype != torch.bfloat16 else x2
+            kb = ops.cast_bf16(keys) if keys.dtype != torch.bfloat16 else keys
+            xp = ops.gather_rows(xb, route, slots_per_src_row=slots_per_row)
+            yp = ops.gemm_rows(xp, kb, w_is_kn=True, route=route, out_dtype=out_dtype)
         n_slots = route.n_slots
         if reduction_weight is None:
             out = ops.scatter_reduce(yp, route.slot_to_row, n_slots, 1)           # back to slot order, no reduction
@@ -145,8 +153,11 @@ class CVMM(Function):
         n_slots, E = route.n_slots, route.num_experts
         K = rw.shape[-1] if rw is not None else 1
         g2 = g.reshape(-1, g.shape[-1]).contiguous()
-        gb = ops.cast_bf16(g2) if g2.dtype != torch.bfloat16 else g2
-        kb = ops.cast_bf16(keys) if keys.dtype != torch.bfloat16 else keys
+        if ctx.fp32:
+            gb, kb = g2.float(), keys.float()
+        else:
+            gb = ops.cast_bf16(g2) if g2.dtype != torch.bfloat16 else g2
+            kb = ops.cast_bf16(keys) if keys.dtype != torch.bfloat16 else keys
         drw = None
         if rw is None:
             gp = ops.gather_rows(gb, route, slots_per_src_row=1)
@@ -157,10 +168,14 @@ class CVMM(Function):
             if ctx.out_dtype == torch.bfloat16:
                 wv = wv.bfloat16().float()
             gp = ops.gather_rows(gb, route, slot_w=wv, slots_per_src_row=K)
-        dkeys = ops.gemm_reduce(xp, gp, E, route=route, out_dtype=keys.dtype)        # [E, k_in, n]
+        if ctx.fp32:
+            dkeys = ops.gemm_reduce_f32(xp, gp, E, route=route).to(keys.dtype)
+        else:
+            dkeys = ops.gemm_reduce(xp, gp, E, route=route, out_dtype=keys.dtype)    # [E, k_in, n]
         dx = None
         if ctx.needs_input_grad[0]:
-            dxp = ops.gemm_rows(gp, kb, w_is_kn=False, route=route)                 # gp @ keys^T
+            dxp = ops.gemm_rows_f32(gp, kb, w_is_kn=False, route=route) if ctx.fp32 else \
+                ops.gemm_rows(gp, kb, w_is_kn=False, route=route)                   # gp @ keys^T
             rows_in = n_slots // ctx.slots_per_row
             dx = ops.scatter_reduce(dxp, route.slot_to_row, rows_in, ctx.slots_per_row).view(ctx.x_shape).to(ctx.x_dtype)
         return dx, dkeys, None, None, drw, None
@@ -212,11 +227,17 @@ def cvmm_triton(x: torch.Tensor, sel_index: torch.Tensor, sel: torch.Tensor, key
     fsel = sel.flatten()
     M, (E, _, N) = fsel.shape[0], keys.shape
     xs = x2.index_select(0, sel_index.flatten().long())                       # sorted row i <- x[sel_index[i]]
-    xb = ops.cast_bf16(xs) if xs.dtype != torch.bfloat16 else xs.contiguous()
-    kb = ops.cast_bf16(keys) if keys.dtype != torch.bfloat16 else keys
     route = ops.route_build(fsel.to(torch.int32).view(-1, 1), E)              # already sorted: slot i is sorted row i
-    xp = ops.gather_rows(xb, route, slots_per_src_row=1)
-    yp = ops.gemm_rows(xp, kb, w_is_kn=True, route=route, out_dtype=out_dtype if out_dtype in (torch.bfloat16, torch.float32) else torch.float32)
+    if out_dtype == torch.float32 and (xs.dtype == torch.float32 or keys.dtype == torch.float32):
+        # the reference's kernel converts the operands to out_dtype (cvmm.py:389-395): fp32 in, fp32 arithmetic
+        yp = ops.gemm_rows_f32(ops.gather_rows(xs.float().contiguous(), route, slots_per_src_row=1), keys.float(),
+                               w_is_kn=True, route=route)
+    else:
+        xb = ops.cast_bf16(xs) if xs.dtype != torch.bfloat16 else xs.contiguous()
+        kb = ops.cast_bf16(keys) if keys.dtype != torch.bfloat16 else keys
+        xp = ops.gather_rows(xb, route, slots_per_src_row=1)
+        yp = ops.gemm_rows(xp, kb, w_is_kn=True, route=route,
+                           out_dtype=out_dtype if out_dtype in (torch.bfloat16, torch.float32) else torch.float32)
     ys = ops.scatter_reduce(yp, route.slot_to_row, M, 1)
     if ys.dtype != out_dtype:
         ys = ys.to(out_dtype)

@@ -88,10 +88,9 @@ class _CosineGate(_SiblingBase):
             m1 = F.normalize(mat1.float(), p=2.0, dim=-1, eps=eps)
         return torch.matmul(m1, mat2.float().transpose(0, 1)).type_as(mat1)
 
-    def forward(self, x, return_id_experts=False, return_full=True, *args, **kwargs):
-        cdt = self._compute_dtype(x)
-        K = self.num_selected
-        x2 = x.reshape(-1, x.shape[-1])
+    def _cosine_gate_logits(self, x2, cdt):
+        """compute_gate of xmoe.py / smoe_perturbed.py:149-160: cosine of the reduced input with the (rescaled in place)
+        expert embeddings, non-finite scores replaced by the smallest finite one."""
         reduced = GateFn.apply(self._cast(x2, cdt), self.expert_sel, 1, 1, False)[0]          # D -> E/2 projection in the router kernel
         if self.sel_bias is not None:
             reduced = reduced + self.sel_bias.to(reduced.dtype)
@@ -100,7 +99,35 @@ class _CosineGate(_SiblingBase):
             self.expert_embeddings.mul_(1.5 / (norm + self.theta) if self.theta else 1.5 / norm)
         gate_logits = self._cosine(reduced, self.expert_embeddings)
         ok = gate_logits.isfinite()
-        gate_logits = torch.where(ok, gate_logits, gate_logits.masked_fill(~ok, float("inf")).min())
+        return torch.where(ok, gate_logits, gate_logits.masked_fill(~ok, float("inf")).min())
+
+    def att_forward(self, x, n_experts, n_copies, return_full=True, *args, **kwargs):
+        """smoe_perturbed.py:199-223 -- the one att_forward the reference ships live (the base class's is commented out,
+        moe.py:456-486): per-head softmax(cosine gate / temperature) in the layer input's dtype, top-k per head, softmax
+        of the kept probabilities as weights, CVMM selection over the shifted (head, expert) indices.  The reference also
+        appends the gate tensors to three lists that `before_loss` empties unread (moe.py:259-267, :341-358): dropped."""
+        from .cvmm import cvmm_prepare_sel2
+        from .pretrain import Selection
+        assert self.is_att, "att_forward needs a layer built with is_att=True"
+        if self.selection_dropout > 0 and self.training:
+            x = F.dropout(x, self.selection_dropout)
+        cdt = self._compute_dtype(x)
+        lead = x.shape[:-1]
+        gate_logits = self._cosine_gate_logits(x.reshape(-1, x.shape[-1]), cdt).view(*lead, n_copies, -1)
+        gate_softmax = F.softmax(gate_logits / self.temperature, dim=-1, dtype=torch.float).to(self._x_dtype or x.dtype)
+        with torch.no_grad():      # torch.topk(sorted=False) leaves ties open; here: highest first, lowest index on ties
+            _, idx = ops.topk_renorm(gate_softmax.detach().float().reshape(-1, gate_softmax.shape[-1]), self.num_selected)
+            idx = idx.view(*lead, n_copies, self.num_selected).long()
+        val = torch.softmax(torch.gather(gate_softmax, -1, idx), dim=-1)
+        shift = (torch.arange(n_copies, device=idx.device, dtype=idx.dtype) * n_experts).unsqueeze(-1)
+        sel_pp = cvmm_prepare_sel2((shift + idx).flatten(-2, -1).int(), val, n_experts=self.n_experts)
+        return Selection(gate_logits, val, idx, sel_pp)
+
+    def forward(self, x, return_id_experts=False, return_full=True, *args, **kwargs):
+        cdt = self._compute_dtype(x)
+        K = self.num_selected
+        x2 = x.reshape(-1, x.shape[-1])
+        gate_logits = self._cosine_gate_logits(x2, cdt)
         gate_softmax = F.softmax(gate_logits / self.temperature, dim=-1, dtype=torch.float).to(self._x_dtype or x.dtype)
         _, gidx = ops.topk_renorm(gate_softmax.detach().float(), K)
         kept = torch.gather(gate_softmax, 1, gidx.long())

@@ -559,6 +559,62 @@ def gen_bias(pm):
     gen_pretrain(pm, "pt_comp_bias_f32", 64, 8, 32, 2, 2, 24, True, seed=41, bias=True)
 
 
+def gen_att_projection(pm, fixture="ptatt_perturbed_f32", D=64, heads=4, E=6, k=2, dh=16, B=2, N=24, seed=60):
+    """Expert projection of MoE attention: the one `att_forward` the reference ships live (smoe_perturbed.py:199-226; the
+    base class's is commented out), on a layer built the way full_moe_relative_attention.py:267-296 builds it."""
+    from oracle import pretrain as op
+    from oracle import pretrain_siblings as ops_
+
+    def cvmm_standin(x, sel, keys):
+        if not isinstance(sel, pm["cvmm"].CVMMSel):
+            sel = pm["cvmm"].cvmm_prepare_sel(sel, keys.shape[0])
+        s = op.Sel(sel.raw_sel, sel.sel, sel.sel_index, sel.out_index, sel.reduction_weight)
+        return op.cvmm(x, s, keys, torch.float32)
+
+    with quiet():
+        mod = importlib.import_module("layers.moe.smoe_perturbed")
+    pm["base"].cvmm = cvmm_standin
+    mod.cvmm = cvmm_standin
+    args = pt_args()
+    torch.manual_seed(seed)
+    with quiet():
+        layer = pm["get_moe"]("smoe_perturbed")(dmodel=D, n_experts=E * heads, expert_size=1, n_heads=heads, topk=k, args=args,
+                                                is_att=True, inp_expert=D, out_expert=dh, std_gate=D ** -0.5,
+                                                std_expert=D ** -0.5, out_dmodel=heads * dh, log_interval=None)
+    with torch.no_grad():      # the reference leaves this parameter as torch.empty (smoe_perturbed.py:99-103)
+        layer.expert_embeddings.normal_(0, 0.3)
+    layer.train()
+    names = ("expert_sel", "expert_embeddings", "experts", "w_gate")
+    before = {n: getattr(layer, n).detach().clone() for n in names}
+    g = torch.Generator().manual_seed(1234 + seed)
+    x = torch.randn(B, N, D, generator=g).requires_grad_(True)
+    dy = torch.randn(B, N, heads, dh, generator=g)
+    sel = layer.att_forward(x, n_experts=E, n_copies=heads)
+    out = layer.compute_moe(x, sel)
+    (out * dy).sum().backward()
+    fx = {"meta": dict(name=fixture, D=D, heads=heads, E=E, K=k, dh=dh, B=B, N=N, args=vars(args)),
+          "x": x.detach().clone(), "dy": dy, "params": before, "out": out.detach().clone(),
+          "selected": sel.raw_sel_index.clone(), "weights": sel.sel_val.detach().clone(), "raw_sel": sel.raw_sel.detach().clone(),
+          "dx": x.grad.clone(), "expert_embeddings_after": layer.expert_embeddings.detach().clone(),
+          "grads": {n: (getattr(layer, n).grad.clone() if getattr(layer, n).grad is not None else None) for n in names}}
+    x2 = fx["x"].clone().requires_grad_(True)
+    p2 = {n: v.clone().requires_grad_(True) for n, v in before.items()}
+    o_out, dbg = ops_.att_projection(x2, p2, E, heads, k)
+    (o_out * dy).sum().backward()
+    tol = dict(rtol=1e-4, atol=1e-6)
+    assert torch.equal(dbg["selected"].sort(-1).values, fx["selected"].sort(-1).values)
+    torch.testing.assert_close(o_out, fx["out"], **tol)
+    torch.testing.assert_close(x2.grad, fx["dx"], **tol)
+    for n in names:
+        if fx["grads"][n] is None:
+            assert p2[n].grad is None or float(p2[n].grad.abs().max()) == 0.0, n
+        else:
+            torch.testing.assert_close(p2[n].grad, fx["grads"][n], **tol)
+    torch.testing.assert_close(p2["expert_embeddings"].detach(), fx["expert_embeddings_after"], **tol)
+    torch.save(fx, OUT / f"{fixture}.pt")
+    print(f"  wrote {fixture}.pt  (oracle == reference)")
+
+
 def gen_wide(pm):
     """The reference's own default expert count, `-moe.n_experts 128` (transformer_lm_mixin.py:32): more experts than the
     two-per-lane router / loss kernels hold, so the 4-per-lane variants run (router.cu / losses.cu "more than 64 experts")."""
@@ -569,6 +625,9 @@ def gen_wide(pm):
 
 def main():
     OUT.mkdir(parents=True, exist_ok=True)
+    if "--att-only" in sys.argv:
+        gen_att_projection(load_pretrain_reference())
+        return
     if "--wide-only" in sys.argv:
         gen_wide(load_pretrain_reference())
         return
@@ -612,6 +671,7 @@ def main():
     gen_gate_variants(mm, pm)
     gen_bias(pm)
     gen_wide(pm)
+    gen_att_projection(pm)
     print("done; now run:  TRITON_INTERPRET=1 python -m oracle.gen_golden")
 
 

@@ -84,3 +84,24 @@ def sibling_forward(name: str, x: torch.Tensor, params: Dict[str, torch.Tensor],
     res = out.view(*x.shape[:-1], values.shape[-1])
     regs = {REG_NAME.get(name, "mlp_ebalance"): entropy_balance(logits) * (args.balance_loss_coef / 1)}
     return res, regs, {"selected": selected, "weights": weights, "scores": scores_for_margin, "gate_logits": logits}
+
+
+def att_projection(x: torch.Tensor, params: Dict[str, torch.Tensor], n_experts: int, n_copies: int, k: int,
+                   op_dtype: torch.dtype = torch.float32, theta: float = 0.1):
+    """smoe_perturbed.py:199-226 (`att_forward` + `compute_moe` of a layer built with is_att=True, the expert projections
+    of FullMoeRopeAttention, full_moe_relative_attention.py:267-296,351-389): per head, softmax(cosine gate / 0.3) over that
+    head's experts in x's dtype, top-k, softmax of the kept values as weights; the projection is x @ experts[head * E + e]
+    ([D, d_head] each) summed over the k selections with those weights (CVMM with reduction_weight, cvmm.py:481-483:
+    weight rounded to the op dtype, fp32 accumulate, one rounding).
+    params: expert_sel [E_total / 2, D], expert_embeddings [E_total, E_total / 2], experts [E_total, D, d_head].
+    Returns (out [..., n_copies, d_head], debug)."""
+    logits = cosine_logits(x, params["expert_sel"], params["expert_embeddings"], theta, op_dtype)
+    logits = logits.view(*logits.shape[:-1], n_copies, -1)
+    softmax = F.softmax(logits / 0.3, dim=-1, dtype=torch.float).to(x.dtype)
+    _, idx = stable_topk(softmax.detach(), k)
+    val = torch.softmax(torch.gather(softmax, -1, idx), dim=-1)
+    flat = torch.arange(n_copies, device=idx.device).view(*([1] * (idx.dim() - 2)), n_copies, 1) * n_experts + idx
+    w = params["experts"].to(op_dtype)[flat]                                   # [..., heads, k, D, d_head]
+    proj = torch.einsum("...d,...hkde->...hke", x.to(op_dtype), w)
+    out = (val.to(op_dtype).unsqueeze(-2).float() @ proj.float()).squeeze(-2).to(op_dtype)
+    return out, {"selected": idx, "weights": val, "scores": softmax, "gate_logits": logits}

@@ -121,3 +121,27 @@ def test_pretrain_fp32_with_128_experts_matches_reference_at_1e4(name):
     """`-moe.n_experts 128`, the reference's default: the four-experts-per-lane router / loss kernels in the fp32-accurate
     mode.  Written after the round's GPU budget was spent (green on the SIMT emulator)."""
     test_pretrain_fp32_without_autocast_matches_reference_at_1e4(name)
+
+
+@pytest.mark.first_hw_run
+def test_cvmm_op_fp32_without_autocast_matches_the_reference_kernels_at_1e4():
+    """The public `cvmm` op on fp32 tensors outside autocast computes in fp32 in the reference (get_dtype(),
+    cvmm.py:29-32; tl.dot(..., allow_tf32=False), :395): both call patterns of compute_moe_main against the golden run of
+    the reference's own Triton kernels (TRITON_INTERPRET=1) at rtol 1e-4, forward and every gradient."""
+    import torch.nn.functional as F
+    from competesmoe_b200.cvmm import cvmm, cvmm_prepare_sel2
+    fx = load_golden("cvmm_triton_interp")
+    x, keys, values, w = (fx[n].to(DEV).requires_grad_(True) for n in ("x", "keys", "values", "w"))
+    s = cvmm_prepare_sel2(fx["sel"].to(DEV), n_experts=keys.shape[0])
+    scores = cvmm(x, s, keys)
+    assert scores.dtype == torch.float32 and scores.shape == fx["scores"].shape
+    s2 = s.clone()
+    s2.reduction_weight = w
+    s2.sel_index = s2.out_index
+    s2.out_index = None
+    out = cvmm(F.relu(scores), s2, values)
+    assert_close_rms(scores, fx["scores"], RTOL, "scores")
+    assert_close_rms(out, fx["out"], RTOL, "out")
+    (out * fx["dy"].to(DEV)).sum().backward()
+    for got, name in ((x.grad, "dx"), (keys.grad, "dkeys"), (values.grad, "dvalues"), (w.grad, "dw")):
+        assert_close_rms(got, fx[name], RTOL, name)

@@ -275,6 +275,27 @@ def test_cvmm_triton_library_op_honours_arbitrary_index_tensors():
     assert_close_rms(got2.view(M, N), want_sorted, 2e-2, "cvmm_triton, out_index = -1")
 
 
+@pytest.mark.first_hw_run
+def test_cvmm_triton_library_op_is_fp32_accurate_for_fp32_operands(direct=False):
+    """out_dtype = fp32 with fp32 operands: the reference's kernel runs tl.dot(..., allow_tf32=False) on fp32 values
+    (cvmm.py:389-395), so the result is the fp32 product, not a bf16 one -- rtol 1e-4 against plain fp32 torch.
+    direct: call the Python implementation instead of the dispatcher op (the CPU tier has no CUDA dispatch key)."""
+    import competesmoe_b200.cvmm as C
+    g = torch.Generator().manual_seed(5)
+    M, R, E, D, N = 260, 90, 5, 72, 40
+    sel = torch.sort(torch.randint(0, E, (M,), generator=g)).values.int()
+    sel_index = torch.randint(0, R, (M,), generator=g)
+    out_index = torch.randperm(M, generator=g)
+    x = torch.randn(R, D, generator=g)
+    keys = torch.randn(E, D, N, generator=g) / D ** 0.5
+    want = torch.empty(M, N).index_copy_(0, out_index, torch.einsum("md,mdn->mn", x[sel_index], keys[sel.long()]))
+    op = C.cvmm_triton if direct else (torch.ops.mylib.cvmm_triton if C.cvmm_triton_call is torch.ops.mylib.cvmm_triton
+                                       else C.cvmm_triton_call)
+    got = op(x.to(DEV), sel_index.to(DEV), sel.to(DEV), keys.to(DEV), torch.float32, out_index.to(DEV))
+    assert got.shape == (M, N) and got.dtype == torch.float32
+    assert_close_rms(got, want, 1e-4, "cvmm_triton fp32")
+
+
 def test_cvmm_rejects_index_tensors_it_cannot_express():
     """cvmm() uses the route built from raw_sel; a CVMMSel whose sel_index was edited to anything but the recognised
     layouts must raise instead of silently computing other rows."""

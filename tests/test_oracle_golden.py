@@ -264,3 +264,24 @@ def test_forced_selection_reproduces_own_selection():
         b = op.competesmoe_forward(x, wg, ks, vs, K, op.default_args(), comp, forced_selected=a[2]["selected"])
         assert torch.equal(a[0], b[0]) and torch.equal(a[2]["own_selected"], a[2]["selected"])
         assert all(torch.equal(a[1][k], b[1][k]) for k in a[1])
+
+
+def test_moe_attention_projection_oracle_matches_reference_golden():
+    """oracle/pretrain_siblings.att_projection against the unmodified reference's smoe_perturbed layer built with
+    is_att=True (att_forward + compute_moe; full_moe_relative_attention.py:267-296 builds it this way)."""
+    from oracle import pretrain_siblings as ops_
+    fx = load_golden("ptatt_perturbed_f32")
+    m = fx["meta"]
+    x = fx["x"].clone().requires_grad_(True)
+    p = {k: v.clone().requires_grad_(True) for k, v in fx["params"].items()}
+    out, dbg = ops_.att_projection(x, p, m["E"], m["heads"], m["K"])
+    (out * fx["dy"]).sum().backward()
+    assert torch.equal(dbg["selected"].sort(-1).values, fx["selected"].sort(-1).values)
+    tol = dict(rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(out, fx["out"], **tol)
+    torch.testing.assert_close(x.grad, fx["dx"], **tol)
+    for k, g in fx["grads"].items():
+        if g is None:
+            assert p[k].grad is None or float(p[k].grad.abs().max()) == 0.0
+        else:
+            torch.testing.assert_close(p[k].grad, g, **tol)

@@ -120,6 +120,10 @@ def test_cvmm_rejects_index_tensors_it_cannot_express():
     gp.test_cvmm_rejects_index_tensors_it_cannot_express()
 
 
+def test_cvmm_triton_library_op_is_fp32_accurate_for_fp32_operands():
+    gp.test_cvmm_triton_library_op_is_fp32_accurate_for_fp32_operands(direct=True)
+
+
 def test_moe_attention_projection_layer_is_att():
     gp.test_moe_attention_projection_layer_is_att()
 
@@ -129,10 +133,19 @@ def test_pretrain_sibling_matches_reference_golden(name):
     gps.test_pretrain_sibling_matches_reference_golden(name)
 
 
+@pytest.mark.parametrize("autocast", [True, False])
+def test_moe_attention_projection_matches_reference_golden(autocast):
+    gps.test_moe_attention_projection_matches_reference_golden(autocast)
+
+
 # ------------------------------------------------------------------------------------------------ fp32 callers (rtol 1e-4)
 @pytest.mark.parametrize("name", ["mm_siglip_router_f32", "mm_glu_router_f32", "mm_siglip_comp_f32", "mm_projector_comp_f32"])
 def test_multimodal_fp32_module_matches_reference_at_1e4(name):
     gf.test_multimodal_fp32_module_matches_reference_at_1e4(name)
+
+
+def test_cvmm_op_fp32_without_autocast_matches_the_reference_kernels_at_1e4():
+    gf.test_cvmm_op_fp32_without_autocast_matches_the_reference_kernels_at_1e4()
 
 
 @pytest.mark.parametrize("name", ["pt_router_f32", "pt_comp_tribrid_f32", "pt_router_e128_f32", "pt_comp_e128_f32"])
