@@ -107,9 +107,9 @@ def test_router_tie_break_is_lowest_index(ops):
 
 
 @pytest.mark.parametrize("E,K", [(4, 2), (64, 8), (33, 5)])
-def test_topk_renorm(ops, E, K):
+def test_topk_renorm(ops, E, K, T=500):
     g = torch.Generator().manual_seed(E)
-    s = torch.rand(500, E, generator=g)
+    s = torch.rand(T, E, generator=g)
     w, idx = ops.topk_renorm(s.to(DEV), K)
     wr, ir = om.stable_topk(s, K)
     assert torch.equal(idx.cpu().long(), ir)

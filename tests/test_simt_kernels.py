@@ -177,7 +177,7 @@ def test_router_tie_break_is_lowest_index_wide(ops):
     gk.test_router_tie_break_is_lowest_index_wide(ops)
 
 
-@pytest.mark.parametrize("B,N,D,E,K", [(1, 131, 128, 8, 1), (2, 90, 64, 8, 2), (1, 70, 128, 128, 1), (1, 64, 64, 4, 4)])
+@pytest.mark.parametrize("B,N,D,E,K", [(1, 131, 128, 8, 1), (2, 90, 64, 8, 2), (1, 24, 128, 128, 1), (1, 64, 64, 4, 4)])
 def test_router_backward_reproduces_autograd_through_the_rounded_denominator(ops, B, N, D, E, K):
     gk.test_router_backward_reproduces_autograd_through_the_rounded_denominator(ops, B, N, D, E, K)
 
@@ -188,10 +188,10 @@ def test_router_renorm_dtype_is_the_layer_inputs(ops):
 
 @pytest.mark.parametrize("E,K", [(65, 3), (128, 8), (200, 5), (256, 8)])
 def test_topk_renorm_wide(ops, E, K):
-    gk.test_topk_renorm(ops, E, K)
+    gk.test_topk_renorm(ops, E, K, T=60)
 
 
-@pytest.mark.parametrize("B,N,D,E,K", [(3, 50, 128, 128, 4), (2, 70, 64, 200, 8), (1, 70, 64, 72, 2)])
+@pytest.mark.parametrize("B,N,D,E,K", [(2, 20, 128, 128, 4), (1, 24, 64, 200, 8), (1, 40, 64, 72, 2)])
 def test_router_aux_and_backward_match_autograd_wide(ops, B, N, D, E, K):
     gk.test_router_aux_and_backward_match_autograd(ops, B, N, D, E, K)
 

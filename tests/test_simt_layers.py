@@ -180,8 +180,7 @@ def test_pretrain_non_contiguous_input_and_zero_tokens(competition):
 
 
 # ------------------------------------------------------------------------------------------------ gate GEMM branch of the router ops
-@pytest.mark.parametrize("T,D,E,K", [(256, 64, 16, 2), (512, 128, 128, 8)])
-@pytest.mark.parametrize("renorm", [None, torch.float32])
+@pytest.mark.parametrize("T,D,E,K,renorm", [(256, 64, 16, 2, None), (256, 64, 16, 2, torch.float32), (256, 64, 72, 4, None)])
 def test_router_ops_gate_gemm_branch_matches_the_fused_kernels(T, D, E, K, renorm, monkeypatch):
     """ops.router_fwd / router_bwd take the tensor-core gate GEMM for E >= 16 on full row tiles (csmoe_router_from_logits,
     dx / dWg as grouped GEMMs).  The host wiring of that branch -- here over the plain-loop GEMM stand-in -- against the
