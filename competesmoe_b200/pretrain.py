@@ -400,17 +400,27 @@ class MoE(LoggingLayer, RegularizedLayer, OncePerIterLayer, torch.nn.Module):
         if self.training:
             self.iter += 1
 
+    # ---- expert-usage statistics of `args.test_only` runs (moe.py:145-183; read by the evaluation harness)
+    def entropy(self, prob_dist):
+        return -torch.sum(prob_dist * torch.log(prob_dist + 1e-18), dim=-1)
+
     def add_dist_experts(self, selection=None):
+        assert selection is not None, "Selection must to not None"
+        n = self.num_of_experts // self.real_n_experts          # per-head expert count for MoE-attention projections
         sel = selection.reshape(-1, selection.shape[-1]).long()
-        hist = F.one_hot(sel, num_classes=self.num_of_experts).reshape(-1, self.num_of_experts).sum(-2)
+        hist = F.one_hot(sel, num_classes=n).reshape(-1, n).sum(-2)
         self.dist_experts = hist if self.dist_experts is None else self.dist_experts + hist
 
     def get_dist_experts(self):
         return self.dist_experts
 
     def add_dist_weight(self, weight, is_all=False):
-        ent = (-(weight * torch.log(weight + 1e-18)).sum(-1)).mean()
+        ent = self.entropy(weight).mean()
         (self.entropy_expert_all if is_all else self.entropy_expert_selected).append(ent)
+
+    def get_weight_dist(self):
+        return {"entropy_all": torch.stack(self.entropy_expert_all).mean().item(),
+                "entropy_topk": torch.stack(self.entropy_expert_selected).mean().item()}
 
     # ---- losses
     def entropy_balance(self, sel: torch.Tensor) -> torch.Tensor:

@@ -205,3 +205,60 @@ def test_router_ops_gate_gemm_branch_matches_the_fused_kernels(T, D, E, K, renor
     if bool(same.all()):
         gf.assert_close_rms(b[4], a[4], 2e-2, "dx")
         gf.assert_close_rms(b[5], a[5], 2e-2, "d gate")
+
+
+# ------------------------------------------------------------------------------------------------ `args.test_only` statistics
+@pytest.mark.parametrize("name", ["competesmoe", "smoe"])
+def test_pretrain_test_only_statistics_match_the_reference(name):
+    """Expert-usage histogram and routing entropies the evaluation harness reads after a `-test_only` run
+    (layers/moe/moe.py:145-183, competesmoe.py:607-611): the unmodified reference class and this layer on the same weights
+    and two eval batches.  Needs the reference tree (present in the build container, where this tier runs)."""
+    import importlib
+    import os
+    from pathlib import Path
+    import torch.nn.functional as F
+    if not Path("/root/reference/moe_pretrain_model").exists():
+        pytest.skip("the reference tree is not on this machine")
+    from oracle import gen_golden as gg
+    from oracle import pretrain as op
+    import competesmoe_b200.pretrain_siblings  # noqa: F401
+    from competesmoe_b200.pretrain import get_moe
+    pm = gg.load_pretrain_reference()
+
+    def cvmm_standin(x, sel, keys):
+        if not isinstance(sel, pm["cvmm"].CVMMSel):
+            sel = pm["cvmm"].cvmm_prepare_sel(sel, keys.shape[0])
+        return op.cvmm(x, op.Sel(sel.raw_sel, sel.sel, sel.sel_index, sel.out_index, sel.reduction_weight), keys, torch.float32)
+
+    pm["base"].cvmm = pm["comp"].cvmm = cvmm_standin
+    if name != "competesmoe":
+        with gg.quiet():
+            importlib.import_module("layers.moe." + gg.PT_SIBLING_MODULES[name]).cvmm = cvmm_standin
+    args = gg.pt_args(test_only=True)
+    D, E, H, K = 64, 8, 32, 2
+    torch.manual_seed(3)
+    cwd = os.getcwd()
+    os.chdir("/tmp")
+    try:
+        with gg.quiet():
+            ref = pm["get_moe"](name)(D, E, H, n_heads=K, args=args, activation=F.relu, selection_mode="gate", log_interval=None)
+            if name == "competesmoe":
+                ref.set_total_steps(id_layer=0)
+    finally:
+        os.chdir(cwd)
+    ours = get_moe(name)(D, E, H, n_heads=K, args=args, activation=F.relu, selection_mode="gate", log_interval=None)
+    ours.load_state_dict(ref.state_dict(), strict=True)
+    ref.eval(), ours.eval()
+    g = torch.Generator().manual_seed(9)
+    with torch.no_grad():
+        for _ in range(2):
+            x = torch.randn(2, 40, D, generator=g)
+            a = ref(x, id_layer=0) if name == "competesmoe" else ref(x)
+            b = ours(x, id_layer=0) if name == "competesmoe" else ours(x)
+            gf.assert_close_rms(b, a, 1e-4, "output")
+    assert torch.equal(ours.get_dist_experts().cpu(), ref.get_dist_experts())
+    assert int(ours.get_dist_experts().sum()) == 2 * 2 * 40 * K
+    wr, wo = ref.get_weight_dist(), ours.get_weight_dist()
+    assert set(wr) == set(wo)
+    for k in wr:
+        assert abs(wo[k] - wr[k]) <= 1e-5 * abs(wr[k]) + 1e-7, (k, wo[k], wr[k])
