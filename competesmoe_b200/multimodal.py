@@ -18,7 +18,8 @@ from torch.autograd.function import once_differentiable
 
 from . import experts as X
 from . import ops
-from .functional import CompeteLossesFn, CompeteTailFn, DenseFFNFn, FFNSpec, GateFn, SparseFFNFn
+from .functional import (AffinityFn, CompeteLossesFn, CompeteTailFn, DenseFFNFn, FFNSpec, GatherRowsFn, GateFn,
+                         SelectCombineFn, SparseFFNFn)
 from .graphs import capture_guard
 from .schedule import make_layer_schedule
 
@@ -61,6 +62,30 @@ class TopkRenormFn(Function):
     def backward(ctx, dw, _):
         scores, w, idx = ctx.saved_tensors
         return ops.topk_renorm_bwd(scores, w, idx, dw, ctx.sigmoid), None, None, None
+
+
+class _CombineRowsFn(Function):
+    """out[t] = sum_k w[t, k] * y[rows[t * K + k]] in ascending-expert order (compute_moe with the per-slot outputs given)."""
+
+    @staticmethod
+    def forward(ctx, y, w, sel, rows, spec: FFNSpec):
+        T, K = sel.shape
+        out = ops.combine_fwd(y.contiguous(), rows, sel.reshape(-1).contiguous(), w, T, K, round_each=spec.round_each,
+                              round_w=spec.round_w)
+        ctx.save_for_backward(y, w, rows)
+        ctx.dims = (T, K, spec)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        y, w, rows = ctx.saved_tensors
+        T, K, spec = ctx.dims
+        dout = dout.contiguous().to(y.dtype)
+        dw = ops.combine_bwd_w(y.contiguous(), dout, rows, T, K)
+        wu = w.to(torch.bfloat16).float() if spec.round_w else w
+        dy = (wu.reshape(T * K, 1) * dout.float().repeat_interleave(K, dim=0)).to(y.dtype)       # rows = identity here
+        return dy, dw, None, None, None
 
 
 class MoeLayer(nn.Module):
@@ -293,6 +318,56 @@ class MoeLayer(nn.Module):
         fp32 = x is not None and x.dtype == torch.float32 and not torch.is_autocast_enabled()
         return FFNSpec(act=lay.act, kn_layout=False, round_each=True, round_w=False, fp32=fp32)
 
+    # ---- the reference's policy-level methods, same names and signatures, on the kernels.  The layers' own forward does
+    # not go through them (it uses the fused forms of the same steps); they are here for callers and subclasses that do.
+    def topk_expert(self, gate_logits):
+        """moe.py:113-132: (top-k softmax probabilities -- not renormalised --, their indices, the full softmax).
+        Ties: lowest expert index first (torch.topk leaves them open)."""
+        gate_softmax = F.softmax(gate_logits, dim=-1, dtype=torch.float32)
+        _, idx = ops.topk_renorm(gate_softmax.detach().reshape(-1, gate_softmax.shape[-1]).contiguous(), self.num_selected)
+        selected_experts = idx.long().view(*gate_softmax.shape[:-1], self.num_selected)
+        return torch.gather(gate_softmax, -1, selected_experts), selected_experts, gate_softmax
+
+    def compute_moe(self, selected_experts, weights, results, x, expert_outputs=None, return_topk_outputs=False):
+        """moe.py:172-213: results += sum_k weights[..., k] * expert_{selected[..., k]}(x), experts visited in ascending
+        order with the running sum rounded to x's dtype (one fused dispatch / grouped GEMM / combine pass here).
+        expert_outputs: per-expert outputs on all tokens ([E][B, N, D_out]) to combine instead of running the experts.
+        return_topk_outputs: also the diversity loss of the selected experts' outputs, returned as (results, loss) when x
+        requires grad and logged to `log_metrics['diver_loss']` otherwise, like the reference."""
+        B, N, D = x.shape
+        T, K = B * N, selected_experts.shape[-1]
+        sel = selected_experts.reshape(T, K).to(torch.int32).contiguous()
+        w = weights.reshape(T, K).float()
+        x2 = x.reshape(T, D)
+        lay, w1, b1, w2, b2 = self._stacked_weights()
+        spec = self._spec(lay, x2)
+        topk_out = None
+        if expert_outputs is not None:
+            y = (torch.stack(list(expert_outputs), 0) if not torch.is_tensor(expert_outputs) else expert_outputs)
+            y = y.reshape(self.num_of_experts * T, -1).contiguous()
+            out = SelectCombineFn.apply(y, w, sel, T, spec)
+            if return_topk_outputs:
+                topk_out = GatherRowsFn.apply(y, sel, T)
+        elif return_topk_outputs:
+            # the selected experts' outputs themselves are needed: one sparse pass per selection rank with weight 1
+            one = torch.ones(T, 1, dtype=torch.float32, device=x.device)
+            cols = [self._sparse_ffn(x2, one, sel[:, k:k + 1].contiguous(), w1, b1, w2, b2, spec) for k in range(K)]
+            topk_out = torch.stack(cols, 1)                                         # [T, K, D_out]
+            rows = torch.arange(T * K, dtype=torch.int32, device=x.device)
+            out = _CombineRowsFn.apply(topk_out.reshape(T * K, -1), w, sel, rows, spec)
+        else:
+            out = self._sparse_ffn(x2, w, sel, w1, b1, w2, b2, spec)
+        results += out.view(B, N, -1).to(results.dtype)
+        if topk_out is not None:
+            diver_loss = self.experts_diversity_loss(topk_out.view(B, N, K, -1))
+            if not x.requires_grad:
+                if not hasattr(self, "log_metrics"):
+                    self.log_metrics = {}
+                self.log_metrics["diver_loss"] = diver_loss.item()
+            else:
+                return results, diver_loss
+        return results
+
     def forward(self, x, return_id_experts=False):
         """Plain sparse MoE (moe.py:228-246)."""
         B, N, D = x.shape
@@ -359,8 +434,51 @@ class CompeteSMoE(MoeLayer):
         return bool(self._flips_host[self.current_steps - self.step_warm])
 
     # ---- policies
-    def router_policy(self, x2, batch, want_aux):
+    def _gate(self, x2, batch, want_aux):
         return GateFn.apply(x2, self.gate.weight, self.num_selected, batch, want_aux)
+
+    def router_policy(self, x):
+        """competesmoe.py:301-320, the reference's signature: x [B, N, D] -> (renormalised top-k weights [B, N, K] fp32,
+        selected experts [B, N, K] int64, gate softmax [B, N, E] fp32, gate logits [B, N, E] in x's dtype)."""
+        B, N, D = x.shape
+        logits, probs, gw, gidx, _ = self._gate(x.reshape(B * N, D), B, False)
+        K, E = self.num_selected, self.num_of_experts
+        return gw.view(B, N, K), gidx.long().view(B, N, K), probs.view(B, N, E), logits.view(B, N, E)
+
+    def competition_policy(self, x):
+        """competesmoe.py:219-259, the reference's signature: every expert on every token, affinity = mean softplus(output)
+        held in x's dtype, top-k of it (of its sigmoid under args.norm_sigmoid) renormalised.  Returns (weights [B, N, K],
+        selected experts [B, N, K] int64, softmax(affinity) [B, N, E] fp32, affinity [B, N, E] in x's dtype, the selected
+        experts' outputs [B, N, K, D_out])."""
+        B, N, D = x.shape
+        T, E, K = B * N, self.num_of_experts, self.num_selected
+        x2 = x.reshape(T, D)
+        lay, w1, b1, w2, b2 = self._stacked_weights()
+        w1, b1, w2, b2 = self._all_expert_weights(w1, b1, w2, b2)
+        spec = self._spec(lay, x2)
+        y_all = DenseFFNFn.apply(x2, w1, b1, w2, b2, spec)                          # [E * t_pad, D_out]
+        t_pad = y_all.shape[0] // E
+        aff = AffinityFn.apply(y_all, E, T, t_pad, x.dtype == torch.bfloat16)       # fp32 tensor of values in x's dtype
+        w, idx = TopkRenormFn.apply(aff, K, bool(getattr(self.args, "norm_sigmoid", False)), x.dtype)
+        topk_out = GatherRowsFn.apply(y_all, idx, t_pad)
+        aff3 = aff.view(B, N, E)
+        return (w.to(x.dtype).view(B, N, K), idx.long().view(B, N, K), F.softmax(aff3, dim=-1, dtype=torch.float32),
+                aff3.to(x.dtype), topk_out.view(B, N, K, -1))
+
+    def topk_expert_softmax(self, gate_logits):
+        """competesmoe.py:262-278: top-k of the logits, softmax over the kept ones."""
+        gate_softmax = F.softmax(gate_logits, dim=-1, dtype=torch.float32)
+        _, idx = ops.topk_renorm(gate_logits.detach().float().reshape(-1, gate_logits.shape[-1]).contiguous(), self.num_selected)
+        selected_experts = idx.long().view(*gate_logits.shape[:-1], self.num_selected)
+        return F.softmax(torch.gather(gate_logits, -1, selected_experts), dim=-1, dtype=torch.float), selected_experts, gate_softmax
+
+    def topk_expert_sigmoid(self, gate_logits):
+        """competesmoe.py:279-295: top-k of sigmoid(logits), not renormalised."""
+        gate_softmax = F.softmax(gate_logits, dim=-1, dtype=torch.float32)
+        gate_sigmoid = torch.sigmoid(gate_logits)
+        _, idx = ops.topk_renorm(gate_sigmoid.detach().float().reshape(-1, gate_logits.shape[-1]).contiguous(), self.num_selected)
+        selected_experts = idx.long().view(*gate_logits.shape[:-1], self.num_selected)
+        return torch.gather(gate_sigmoid, -1, selected_experts), selected_experts, gate_softmax
 
     def router_loss(self, gate_softmax, affinity_softmax):
         return F.mse_loss(gate_softmax, affinity_softmax)
@@ -399,7 +517,7 @@ class CompeteSMoE(MoeLayer):
         spec = self._spec(lay, x2)
         compete = self._is_competition_step(x)
         want_aux = (not compete) and (x.requires_grad or return_id_experts)
-        gate_logits, gate_softmax, gate_w, gate_idx, gate_losses = self.router_policy(x2, B, want_aux)
+        gate_logits, gate_softmax, gate_w, gate_idx, gate_losses = self._gate(x2, B, want_aux)
         auxiliary_loss = x.new_zeros(())
         infor_aux = {}
         if compete:

@@ -296,3 +296,76 @@ def test_layer_cuda_graph_mode_under_autocast_matches_eager():
             res.append((out.clone(), aux.clone(), x.grad.clone()))
         assert all(torch.equal(a, b) for a, b in zip(*res))
     assert len(graphed._graphs) == 1
+
+
+@pytest.mark.first_hw_run
+@pytest.mark.parametrize("kind", ["mlp", "glu"])
+def test_policy_level_methods_match_the_oracle(kind):
+    """The reference's policy-level methods under their own names and signatures -- router_policy(x), topk_expert(logits),
+    compute_moe(selected, weights, results, x[, expert_outputs][, return_topk_outputs]), competition_policy(x)
+    (competesmoe.py:219-259,301-320; moe.py:113-132,172-213) -- against the oracle's restatement of each, values and
+    gradients.  Written after the round's GPU budget was spent (green on the SIMT emulator)."""
+    import torch.nn.functional as F
+    from test_gpu_edge_cases import _mm_case
+    B, N, D, Fh, E, K = 2, 45, 64, 136, 4, 2
+    exps, x, gate_w, dy = _mm_case(B, N, D, Fh, E, K, kind, seed=77)
+    args = om.default_args()
+    layer = build_multimodal_layer({"meta": dict(d_in=D, d_out=D, E=E, K=K, competition=False, args=vars(args)),
+                                    "experts": exps, "gate_w": gate_w, "x": x}, DEV, torch.bfloat16)
+    ex = [{k: (v.clone().requires_grad_(True) if torch.is_tensor(v) else v) for k, v in e.items()} for e in exps]
+    fresh = lambda: x.detach().clone()       # (on the CPU tier `.to(DEV)` is the tensor itself)
+    xr = fresh().requires_grad_(True)
+    xg = fresh().to(DEV).requires_grad_(True)
+    # ---- router_policy / topk_expert
+    ow, osel, oprobs, ologits = om.router_policy(xr, gate_w, K)
+    w, sel, probs, logits = layer.router_policy(xg)
+    assert sel.dtype == torch.int64 and sel.shape == (B, N, K) and probs.shape == (B, N, E) and logits.dtype == torch.bfloat16
+    agree = (sel.cpu() == osel).all(-1)
+    assert bool((om.topk_margin(oprobs, K)[~agree] < 1e-3).all())
+    assert_close_rms(logits, ologits.detach(), 2e-2, "gate logits")
+    assert_close_rms(probs, oprobs.detach(), 2e-2, "gate softmax")
+    assert_close_rms(w.cpu()[agree], ow.detach()[agree], 2e-2, "routing weights")
+    tw, tsel, tprobs = layer.topk_expert(logits.detach())
+    ref_p = F.softmax(logits.detach().cpu(), dim=-1, dtype=torch.float32)
+    rv, ri = om.stable_topk(ref_p, K)
+    assert torch.equal(tsel.cpu(), ri)
+    torch.testing.assert_close(tprobs.cpu(), ref_p, rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(tw.cpu(), rv, rtol=1e-5, atol=1e-7)
+    # ---- compute_moe under the oracle's routing: values, dx, return_topk_outputs, expert_outputs
+    o_out = om.compute_moe(xr, ex, osel, ow.detach(), D)
+    (o_out.float() * dy.float()).sum().backward()
+    res = torch.zeros(B, N, D, dtype=torch.bfloat16, device=DEV)
+    out = layer.compute_moe(osel.to(DEV), ow.detach().to(DEV), res, xg)
+    assert out is res
+    assert_close_rms(out, o_out.detach(), 2e-2, "compute_moe")
+    (out.float() * dy.to(DEV).float()).sum().backward()
+    assert_close_rms(xg.grad, xr.grad, 3e-2, "compute_moe dx")
+    with torch.no_grad():
+        dense = [om.expert_forward(e, fresh()) for e in exps]                                  # [E][B, N, D]
+        idx = osel.unsqueeze(-1).expand(B, N, K, D)
+        div_ref = om.experts_diversity_loss(torch.gather(torch.stack(dense, 2), 2, idx))
+    xg2 = fresh().to(DEV).requires_grad_(True)
+    out2, diver = layer.compute_moe(osel.to(DEV), ow.detach().to(DEV), torch.zeros_like(res), xg2, return_topk_outputs=True)
+    assert_close_rms(out2, o_out.detach(), 2e-2, "compute_moe (return_topk_outputs)")
+    assert abs(float(diver) - float(div_ref)) <= 2e-2 * abs(float(div_ref)) + 2e-3
+    (out2.float().sum() + diver).backward()
+    assert xg2.grad is not None and bool(torch.isfinite(xg2.grad).all())
+    out3 = layer.compute_moe(osel.to(DEV), ow.detach().to(DEV), torch.zeros_like(res), fresh().to(DEV),
+                             expert_outputs=[d.to(DEV) for d in dense])
+    assert_close_rms(out3, o_out.detach(), 2e-2, "compute_moe (expert_outputs)")
+    # ---- competition_policy
+    xr2 = fresh().requires_grad_(True)
+    cw, csel, csoft, caff, ctop = om.competition_policy(xr2, ex, K)
+    xg3 = fresh().to(DEV).requires_grad_(True)
+    w2, sel2, soft2, aff2, top2 = layer.competition_policy(xg3)
+    assert sel2.dtype == torch.int64 and aff2.dtype == torch.bfloat16 and top2.shape == (B, N, K, D)
+    agree2 = (sel2.cpu() == csel).all(-1)
+    assert bool((om.topk_margin(caff, K)[~agree2] < 1e-3).all())
+    assert_close_rms(aff2, caff.detach(), 2e-2, "affinity")
+    assert_close_rms(soft2, csoft.detach(), 2e-2, "softmax(affinity)")
+    assert_close_rms(w2.cpu()[agree2], cw.detach()[agree2], 2e-2, "competition weights")
+    assert_close_rms(top2.cpu()[agree2], ctop.detach()[agree2], 2e-2, "selected experts' outputs")
+    if bool(agree2.all()):
+        ((ctop.float() * dy.float().unsqueeze(2)).sum() + (cw.float() * 3).sum()).backward()
+        ((top2.float() * dy.to(DEV).float().unsqueeze(2)).sum() + (w2.float() * 3).sum()).backward()
+        assert_close_rms(xg3.grad, xr2.grad, 3e-2, "competition_policy dx")

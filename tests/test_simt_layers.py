@@ -92,6 +92,11 @@ def test_multimodal_skewed_routing_hot_and_empty_experts(competition):
     gm.test_skewed_routing_hot_and_empty_experts_against_oracle(competition)
 
 
+@pytest.mark.parametrize("kind", ["mlp", "glu"])
+def test_multimodal_policy_level_methods_match_the_oracle(kind):
+    gm.test_policy_level_methods_match_the_oracle(kind)
+
+
 @pytest.mark.parametrize("name", gs.SIB)
 def test_multimodal_sibling_matches_reference_golden(name):
     gs.test_sibling_matches_reference_golden(name)
