@@ -456,9 +456,54 @@ class MoE(LoggingLayer, RegularizedLayer, OncePerIterLayer, torch.nn.Module):
         return FFNSpec(act=self._act_code, kn_layout=True, round_each=False, round_w=cdt == torch.bfloat16,
                        bias_after_round=True, fp32=cdt == torch.float32)
 
-    def compute_gate(self, x2: torch.Tensor, cdt: torch.dtype, x_dtype: Optional[torch.dtype] = None):
-        """x_dtype: the layer input's dtype, to which the reference rounds the sum of the top-k weights (`.to(x.dtype)`)."""
+    def compute_gate(self, x2: torch.Tensor, cdt: Optional[torch.dtype] = None, x_dtype: Optional[torch.dtype] = None):
+        """x_dtype: the layer input's dtype, to which the reference rounds the sum of the top-k weights (`.to(x.dtype)`).
+        Called as the reference calls it -- compute_gate(x), moe.py:395-396 -- it returns the gate logits [..., E]."""
+        if cdt is None:
+            return self._reference_style_logits(x2)
         return GateFn.apply(self._cast(x2, cdt), self.w_gate, self.num_selected, 1, False, x_dtype)[:4]
+
+    # ---- the reference's policy-level methods under their own names and signatures (moe.py:273-322,373-416;
+    # competesmoe.py:381-455,465-490,510-522), on the kernels.  The layers' forward uses the fused forms of the same steps;
+    # these are for callers and subclasses that go through the reference's method names.
+    def _reference_style_logits(self, x):
+        cdt = self._compute_dtype(x)
+        return self.compute_gate(x.reshape(-1, x.shape[-1]), cdt, self._x_dtype or x.dtype)[0].view(*x.shape[:-1], -1)
+
+    def topk_expert(self, gate_logits):
+        """moe.py:373-393: (top-k softmax probabilities, not renormalised; their indices; the full softmax).  Ties: lowest
+        expert index first."""
+        gate_softmax = F.softmax(gate_logits, dim=-1, dtype=torch.float32)
+        _, idx = ops.topk_renorm(gate_softmax.detach().reshape(-1, gate_softmax.shape[-1]).contiguous(), self.num_selected)
+        selected_experts = idx.long().view(*gate_softmax.shape[:-1], self.num_selected)
+        return torch.gather(gate_softmax, -1, selected_experts), selected_experts, gate_softmax
+
+    def zloss(self, gate_logits, gate_softmax=None):
+        """moe.py:273-290."""
+        return torch.square(torch.logsumexp(gate_logits, dim=-1)).mean()
+
+    def balanceloss(self, selected_experts, gate_softmax):
+        """moe.py:292-321 (top-1 density x mean probability; per head for MoE-attention projections)."""
+        if self.is_att:
+            k = gate_softmax.shape[-1]
+            proxy = gate_softmax.mean(dim=1)                                                  # b n h k -> b h k
+            density = F.one_hot(selected_experts, num_classes=k).float()[:, :, :, 0, :].mean(dim=1)
+            return (proxy * density).mean() * float(k ** 2)
+        proxy = gate_softmax.mean(dim=-2)
+        density = F.one_hot(selected_experts[..., 0], self.num_of_experts // self.real_n_experts).float().mean(dim=-2)
+        return (proxy * density).mean() * float(self.num_of_experts ** 2)
+
+    def compute_scores(self, input: torch.Tensor, index) -> torch.Tensor:
+        """moe.py:397-416: activation(cvmm(input, index, keys) + bias[index.raw_sel]) through the public op."""
+        from .cvmm import cvmm
+        scores = cvmm(input, index, self.keys)
+        if self.bias is not None:
+            scores = scores + self.bias[index.raw_sel.long()]
+        scores = self.activation(scores)
+        if self._plot_training():
+            with torch.no_grad():
+                self.log("relu_pass_rate", (scores > 0).float().sum() / scores.numel())
+        return scores
 
     def _plot_training(self) -> bool:
         """moe.py:405: `self.train and log_interval is not None and iter % log_interval == 0` (`self.train` is the bound
@@ -485,7 +530,13 @@ class MoE(LoggingLayer, RegularizedLayer, OncePerIterLayer, torch.nn.Module):
 
     _wx_open = False
 
-    def compute_moe_main(self, x2, selected, weights, cdt, same_step: bool = False):
+    def compute_moe_main(self, x2, selected, weights, cdt: Optional[torch.dtype] = None, same_step: bool = False):
+        if cdt is None:
+            # the reference's signature (competesmoe.py:510-522): x [..., D], selected_experts / weights [..., K]
+            lead, K = x2.shape[:-1], selected.shape[-1]
+            out = self.compute_moe_main(x2.reshape(-1, x2.shape[-1]), selected.reshape(-1, K).to(torch.int32).contiguous(),
+                                        weights.reshape(-1, K).float(), self._compute_dtype(x2))
+            return out.view(*lead, self.v_dim)
         wx = self._wx
         if wx is not None and not same_step and not self._wx_open:   # callers that did not prefetch (sibling routers)
             wx.begin_step()
@@ -614,9 +665,12 @@ class CompeteSMoE(MoE):
             self.iter += 1
 
     # ---- policies
-    def compute_gate(self, x2: torch.Tensor, cdt: torch.dtype, x_dtype: Optional[torch.dtype] = None):
+    def compute_gate(self, x2: torch.Tensor, cdt: Optional[torch.dtype] = None, x_dtype: Optional[torch.dtype] = None):
         """competesmoe.py:456-464: plain, cosine, or weight-normalised gate.  x_dtype: dtype of the layer input, which the
-        reference rounds the top-k sum to (`.to(x.dtype)`, :489): fp32 for fp32 inputs under autocast, so no rounding."""
+        reference rounds the top-k sum to (`.to(x.dtype)`, :489): fp32 for fp32 inputs under autocast, so no rounding.
+        Called as compute_gate(x) it returns the gate logits [..., E] like the reference's."""
+        if cdt is None:
+            return self._reference_style_logits(x2)
         a = self.args
         if getattr(a, "is_cosine", False) and not getattr(a, "is_norm_weight", False):
             return GateFn.apply(F.normalize(x2.float(), p=2.0, dim=-1).to(cdt), F.normalize(self.w_gate, p=2.0, dim=-1),
@@ -626,8 +680,15 @@ class CompeteSMoE(MoE):
                                 x_dtype)[:4]
         return GateFn.apply(self._cast(x2, cdt), self.w_gate, self.num_selected, 1, False, x_dtype)[:4]
 
-    def router_policy(self, x2, cdt, x_dtype):
-        """competesmoe.py:465-490."""
+    def router_policy(self, x2, cdt: Optional[torch.dtype] = None, x_dtype: Optional[torch.dtype] = None,
+                      is_normal_mode: bool = False):
+        """competesmoe.py:465-490.  Called as the reference calls it -- router_policy(x, is_normal_mode=...) with
+        x [B, N, D] -- it returns (weights [B, N, K], selected experts [B, N, K] int64, gate softmax [B, N, E], gate logits)."""
+        if cdt is None:
+            lead, K = x2.shape[:-1], self.num_selected
+            gw, gidx, probs, logits = self.router_policy(x2.reshape(-1, x2.shape[-1]), self._compute_dtype(x2),
+                                                         self._x_dtype or x2.dtype)
+            return gw.view(*lead, K), gidx.long().view(*lead, K), probs.view(*lead, -1), logits.view(*lead, -1)
         a = self.args
         assert not (getattr(a, "is_cosine", False) and getattr(a, "is_norm_weight", False)), \
             "Can not active  both  Cosine and Norm Weigh. Just use one method - Cosine or Norm Weigh to Normalization"
@@ -639,6 +700,28 @@ class CompeteSMoE(MoE):
 
     def router_loss(self, gate_softmax, affinity_softmax):
         return F.mse_loss(gate_softmax, affinity_softmax)
+
+    def competition_policy_mlp_faster(self, x):
+        """competesmoe.py:381-414, the reference's signature: every expert on every token (without the hidden bias),
+        affinity = mean softplus(output) in fp32, top-k renormalised in x's dtype.  Returns (weights [B, N, K], selected
+        experts [B, N, K] int64, softmax(affinity) [B, N, E], affinity [B, N, E], selected outputs [B, N, K, D_v])."""
+        from .functional import AffinityFn, GatherRowsFn
+        lead = x.shape[:-1]
+        cdt = self._compute_dtype(x)
+        xdt = self._x_dtype or x.dtype
+        x2 = x.reshape(-1, x.shape[-1])
+        T, E, K = x2.shape[0], self.n_experts, self.num_selected
+        self._wx_prefetch(cdt)
+        self._wx_open = False
+        keys, _, values = self._all_expert_weights()
+        y_all = DenseFFNFn.apply(self._cast(x2, cdt), keys, None, values, None, self._spec(cdt), None, self._wx)
+        t_pad = y_all.shape[0] // E
+        aff = AffinityFn.apply(y_all, E, T, t_pad, xdt == torch.bfloat16)
+        w, idx = TopkRenormFn.apply(aff, K, False, xdt)
+        topk_out = GatherRowsFn.apply(y_all, idx, t_pad)
+        aff3 = aff.view(*lead, E)
+        return (w.view(*lead, K), idx.long().view(*lead, K), F.softmax(aff3, dim=-1, dtype=torch.float32), aff3,
+                topk_out.view(*lead, K, -1))
 
     def experts_diversity_loss(self, expert_outputs):
         """competesmoe.py:330-372 on [T, K, D]."""

@@ -347,3 +347,85 @@ def test_moe_attention_projection_layer_is_att():
     assert_close_rms(x.grad, xr.grad, 3e-2, "dx")
     assert_close_rms(layer.experts.grad, ex.grad, 3e-2, "d experts")
     assert_close_rms(layer.w_gate.grad, wg.grad, 4e-2, "d w_gate")
+
+
+@pytest.mark.first_hw_run
+@pytest.mark.parametrize("autocast,variant", [(True, {}), (True, {"norm_sigmoid": True, "scale_weight": 2.0}), (False, {}),
+                                              (True, {"is_cosine": True})])
+def test_policy_level_methods_match_the_oracle(autocast, variant):
+    """The reference's policy-level methods under their own names and signatures -- compute_gate(x), topk_expert(logits),
+    router_policy(x), compute_scores(x, sel), compute_moe_main(x, selected, weights), competition_policy_mlp_faster(x),
+    zloss, balanceloss (moe.py:273-322,373-416; competesmoe.py:381-414,456-490,510-522) -- against the oracle, values and
+    gradients; autocast=False: the fp32-accurate path at rtol 1e-4.  Written after the round's GPU budget was spent."""
+    from competesmoe_b200.cvmm import cvmm_prepare_sel2
+    from competesmoe_b200.pretrain import CompeteSMoE
+    D, E, H, K, B, N = 64, 8, 32, 2, 2, 37
+    args = op.default_args(**variant)
+    torch.manual_seed(5)
+    layer = CompeteSMoE(D, E, H, n_heads=K, args=args, activation=F.relu, selection_mode="gate", log_interval=None)
+    g = torch.Generator().manual_seed(6)
+    with torch.no_grad():
+        layer.w_gate.copy_(torch.randn(E, D, generator=g) * 0.3)
+    w_gate, keys, values = (p.detach().clone() for p in (layer.w_gate, layer.keys, layer.values))
+    layer = layer.to(DEV).train()
+    x = torch.randn(B, N, D, generator=g)
+    dy = torch.randn(B, N, D, generator=g)
+    odt = torch.bfloat16 if autocast else torch.float32
+    rt = 2e-2 if autocast else 1e-4
+    fresh = lambda: x.detach().clone()
+    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+        # ---- gate, top-k, router policy
+        xr, wg = fresh().requires_grad_(True), w_gate.clone().requires_grad_(True)
+        ow, osel, oprobs, ologits = op.router_policy(xr, wg, K, args, odt)
+        xg = fresh().to(DEV).requires_grad_(True)
+        logits = layer.compute_gate(xg)
+        assert logits.shape == (B, N, E)
+        assert_close_rms(logits, ologits.detach(), rt, "compute_gate")
+        w, sel, probs, logits2 = layer.router_policy(xg, is_normal_mode=True)
+        assert sel.dtype == torch.int64 and sel.shape == (B, N, K) and probs.shape == (B, N, E)
+        scores = ologits if variant.get("norm_sigmoid") else oprobs
+        agree = (sel.cpu() == osel).all(-1)
+        assert bool((om.topk_margin(scores.float(), K)[~agree] < 1e-3).all())
+        assert_close_rms(probs, oprobs.detach(), rt, "gate softmax")
+        assert_close_rms(w.cpu()[agree], ow.detach()[agree], rt, "routing weights")
+        tw, tsel, tprobs = layer.topk_expert(logits.detach())
+        ref_p = F.softmax(logits.detach().cpu(), dim=-1, dtype=torch.float32)
+        rv, ri = om.stable_topk(ref_p, K)
+        assert torch.equal(tsel.cpu(), ri)
+        torch.testing.assert_close(tw.cpu(), rv, rtol=1e-5, atol=1e-7)
+        torch.testing.assert_close(layer.zloss(logits.detach().float()).cpu(),
+                                   torch.square(torch.logsumexp(logits.detach().float().cpu(), -1)).mean(), rtol=1e-5, atol=1e-7)
+        top1 = F.one_hot(ri[..., 0], E).float().mean(-2)
+        torch.testing.assert_close(layer.balanceloss(tsel, tprobs).cpu(), (ref_p.mean(-2) * top1).mean() * E * E, rtol=1e-5, atol=1e-7)
+        # ---- compute_scores / compute_moe_main under the oracle's routing
+        ks, vs = keys.clone().requires_grad_(True), values.clone().requires_grad_(True)
+        o_out = op.compute_moe_main(xr, osel, ow.detach(), ks, vs, F.relu, odt)
+        (o_out.float() * dy).sum().backward()
+        out = layer.compute_moe_main(xg, osel.to(DEV), ow.detach().to(DEV))
+        assert out.shape == (B, N, D)
+        assert_close_rms(out, o_out.detach(), rt, "compute_moe_main")
+        (out.float() * dy.to(DEV)).sum().backward()
+        assert_close_rms(xg.grad, xr.grad, 3e-2 if autocast else rt, "compute_moe_main dx")
+        assert_close_rms(layer.keys.grad, ks.grad, 3e-2 if autocast else rt, "dkeys", outliers=1e-3 if autocast else 0.0)
+        assert_close_rms(layer.values.grad, vs.grad, 3e-2 if autocast else rt, "dvalues", outliers=1e-3 if autocast else 0.0)
+        sel_pp = cvmm_prepare_sel2(osel.to(DEV).int(), n_experts=E)
+        sc = layer.compute_scores(fresh().to(DEV), sel_pp)
+        o_sc = F.relu(op.cvmm(fresh(), op.prepare_sel2(osel.int()), keys, odt))
+        assert sc.shape == (B, N, K, H)
+        assert_close_rms(sc, o_sc, rt, "compute_scores")
+        # ---- competition policy
+        xr2 = fresh().requires_grad_(True)
+        cw, csel, csoft, caff, ctop = op.competition_policy(xr2, keys, values, K, F.relu, odt)
+        xg2 = fresh().to(DEV).requires_grad_(True)
+        w2, sel2, soft2, aff2, top2 = layer.competition_policy_mlp_faster(xg2)
+        assert sel2.dtype == torch.int64 and top2.shape == (B, N, K, D) and aff2.shape == (B, N, E)
+        agree2 = (sel2.cpu() == csel).all(-1)
+        assert bool((om.topk_margin(caff, K)[~agree2] < 1e-3).all())
+        assert_close_rms(aff2, caff.detach(), rt, "affinity")
+        assert_close_rms(soft2, csoft.detach(), rt, "softmax(affinity)")
+        assert_close_rms(w2.cpu()[agree2], cw.detach()[agree2], rt, "competition weights")
+        assert_close_rms(top2.cpu()[agree2], ctop.detach()[agree2], rt, "selected outputs")
+        if bool(agree2.all()):
+            ((ctop.float() * dy.unsqueeze(2)).sum() + (cw.float() * 3).sum()).backward()
+            ((top2.float() * dy.to(DEV).unsqueeze(2)).sum() + (w2.float() * 3).sum()).backward()
+            assert_close_rms(xg2.grad, xr2.grad, 3e-2 if autocast else rt, "competition_policy dx")

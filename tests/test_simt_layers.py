@@ -113,6 +113,12 @@ def test_pretrain_layer_with_128_experts_matches_reference_golden(name):
     gp.test_pretrain_layer_with_128_experts_matches_reference_golden(name)
 
 
+@pytest.mark.parametrize("autocast,variant", [(True, {}), (True, {"norm_sigmoid": True, "scale_weight": 2.0}), (False, {}),
+                                              (True, {"is_cosine": True})])
+def test_pretrain_policy_level_methods_match_the_oracle(autocast, variant):
+    gp.test_policy_level_methods_match_the_oracle(autocast, variant)
+
+
 def test_cvmm_op_both_call_patterns():
     gp.test_cvmm_op_both_call_patterns()
 
@@ -224,21 +230,31 @@ def test_pretrain_test_only_statistics_match_the_reference(name):
     import torch.nn.functional as F
     if not Path("/root/reference/moe_pretrain_model").exists():
         pytest.skip("the reference tree is not on this machine")
+    import sys
+    import types
     from oracle import gen_golden as gg
     from oracle import pretrain as op
     import competesmoe_b200.pretrain_siblings  # noqa: F401
     from competesmoe_b200.pretrain import get_moe
+    # The reference's layers/cvmm.py defines the torch.library op mylib::cvmm_triton at import: once per process, and this
+    # process may hold the package's definition already.  Its Triton kernels need a GPU anyway, so `layers.cvmm` is the
+    # oracle's restatement of the op here (pinned on the reference's kernels by cvmm_triton_interp); the LAYER classes --
+    # what this test is about -- are the unmodified reference's.
+    cv = types.ModuleType("layers.cvmm")
+    cv.CVMMSel, cv.cvmm_prepare_sel2 = op.Sel, op.prepare_sel2
+    cv.cvmm = lambda x, sel, keys: op.cvmm(x, sel, keys, torch.float32)
+
+    def _no_sel(*a, **k):
+        raise NotImplementedError("cvmm_prepare_sel is not used by the layers under test")
+
+    cv.cvmm_prepare_sel = _no_sel
+    for k in [k for k in sys.modules if k == "layers" or k == "framework" or k.startswith(("layers.", "framework."))]:
+        sys.modules.pop(k)
+    sys.modules["layers.cvmm"] = cv
     pm = gg.load_pretrain_reference()
-
-    def cvmm_standin(x, sel, keys):
-        if not isinstance(sel, pm["cvmm"].CVMMSel):
-            sel = pm["cvmm"].cvmm_prepare_sel(sel, keys.shape[0])
-        return op.cvmm(x, op.Sel(sel.raw_sel, sel.sel, sel.sel_index, sel.out_index, sel.reduction_weight), keys, torch.float32)
-
-    pm["base"].cvmm = pm["comp"].cvmm = cvmm_standin
     if name != "competesmoe":
         with gg.quiet():
-            importlib.import_module("layers.moe." + gg.PT_SIBLING_MODULES[name]).cvmm = cvmm_standin
+            importlib.import_module("layers.moe." + gg.PT_SIBLING_MODULES[name])
     args = gg.pt_args(test_only=True)
     D, E, H, K = 64, 8, 32, 2
     torch.manual_seed(3)
@@ -267,3 +283,5 @@ def test_pretrain_test_only_statistics_match_the_reference(name):
     assert set(wr) == set(wo)
     for k in wr:
         assert abs(wo[k] - wr[k]) <= 1e-5 * abs(wr[k]) + 1e-7, (k, wo[k], wr[k])
+    for k in [k for k in sys.modules if k == "layers" or k == "framework" or k.startswith(("layers.", "framework."))]:
+        sys.modules.pop(k)
