@@ -478,6 +478,19 @@ class MoE(LoggingLayer, RegularizedLayer, OncePerIterLayer, torch.nn.Module):
         selected_experts = idx.long().view(*gate_softmax.shape[:-1], self.num_selected)
         return torch.gather(gate_softmax, -1, selected_experts), selected_experts, gate_softmax
 
+    def topk_expert_softmax(self, gate_logits):
+        """competesmoe.py:415-434: top-k of the logits, softmax over the kept ones."""
+        gate_softmax = F.softmax(gate_logits, dim=-1, dtype=torch.float32)
+        _, idx = ops.topk_renorm(gate_logits.detach().float().reshape(-1, gate_logits.shape[-1]).contiguous(), self.num_selected)
+        selected_experts = idx.long().view(*gate_logits.shape[:-1], self.num_selected)
+        return F.softmax(torch.gather(gate_logits, -1, selected_experts), dim=-1, dtype=torch.float), selected_experts, gate_softmax
+
+    def update_aux_statistics(self, gate_logits, gate_softmax, selected_experts):
+        """moe.py:259-267: kept for callers; the three lists are emptied unread by `before_loss` (moe.py:341-358)."""
+        self.total_selections.append(selected_experts)
+        self.total_gate_logits.append(gate_logits)
+        self.total_gate_softmax.append(gate_softmax)
+
     def zloss(self, gate_logits, gate_softmax=None):
         """moe.py:273-290."""
         return torch.square(torch.logsumexp(gate_logits, dim=-1)).mean()
