@@ -506,6 +506,32 @@ class MoE(LoggingLayer, RegularizedLayer, OncePerIterLayer, torch.nn.Module):
         density = F.one_hot(selected_experts[..., 0], self.num_of_experts // self.real_n_experts).float().mean(dim=-2)
         return (proxy * density).mean() * float(self.num_of_experts ** 2)
 
+    def add_perplexity_reg(self):
+        """moe.py:341-358: everything but the reset of the per-iteration lists is commented out in the reference."""
+        self.pre_train_forward()
+
+    def competition_policy_mlp_faster(self, x):
+        """competesmoe.py:381-414, the reference's signature: every expert on every token (without the hidden bias),
+        affinity = mean softplus(output) in fp32, top-k renormalised in x's dtype.  Returns (weights [B, N, K], selected
+        experts [B, N, K] int64, softmax(affinity) [B, N, E], affinity [B, N, E], selected outputs [B, N, K, D_v])."""
+        from .functional import AffinityFn, GatherRowsFn
+        lead = x.shape[:-1]
+        cdt = self._compute_dtype(x)
+        xdt = self._x_dtype or x.dtype
+        x2 = x.reshape(-1, x.shape[-1])
+        T, E, K = x2.shape[0], self.n_experts, self.num_selected
+        self._wx_prefetch(cdt)
+        self._wx_open = False
+        keys, _, values = self._all_expert_weights()
+        y_all = DenseFFNFn.apply(self._cast(x2, cdt), keys, None, values, None, self._spec(cdt), None, self._wx)
+        t_pad = y_all.shape[0] // E
+        aff = AffinityFn.apply(y_all, E, T, t_pad, xdt == torch.bfloat16)
+        w, idx = TopkRenormFn.apply(aff, K, False, xdt)
+        topk_out = GatherRowsFn.apply(y_all, idx, t_pad)
+        aff3 = aff.view(*lead, E)
+        return (w.view(*lead, K), idx.long().view(*lead, K), F.softmax(aff3, dim=-1, dtype=torch.float32), aff3,
+                topk_out.view(*lead, K, -1))
+
     def compute_scores(self, input: torch.Tensor, index) -> torch.Tensor:
         """moe.py:397-416: activation(cvmm(input, index, keys) + bias[index.raw_sel]) through the public op."""
         from .cvmm import cvmm
@@ -713,28 +739,6 @@ class CompeteSMoE(MoE):
 
     def router_loss(self, gate_softmax, affinity_softmax):
         return F.mse_loss(gate_softmax, affinity_softmax)
-
-    def competition_policy_mlp_faster(self, x):
-        """competesmoe.py:381-414, the reference's signature: every expert on every token (without the hidden bias),
-        affinity = mean softplus(output) in fp32, top-k renormalised in x's dtype.  Returns (weights [B, N, K], selected
-        experts [B, N, K] int64, softmax(affinity) [B, N, E], affinity [B, N, E], selected outputs [B, N, K, D_v])."""
-        from .functional import AffinityFn, GatherRowsFn
-        lead = x.shape[:-1]
-        cdt = self._compute_dtype(x)
-        xdt = self._x_dtype or x.dtype
-        x2 = x.reshape(-1, x.shape[-1])
-        T, E, K = x2.shape[0], self.n_experts, self.num_selected
-        self._wx_prefetch(cdt)
-        self._wx_open = False
-        keys, _, values = self._all_expert_weights()
-        y_all = DenseFFNFn.apply(self._cast(x2, cdt), keys, None, values, None, self._spec(cdt), None, self._wx)
-        t_pad = y_all.shape[0] // E
-        aff = AffinityFn.apply(y_all, E, T, t_pad, xdt == torch.bfloat16)
-        w, idx = TopkRenormFn.apply(aff, K, False, xdt)
-        topk_out = GatherRowsFn.apply(y_all, idx, t_pad)
-        aff3 = aff.view(*lead, E)
-        return (w.view(*lead, K), idx.long().view(*lead, K), F.softmax(aff3, dim=-1, dtype=torch.float32), aff3,
-                topk_out.view(*lead, K, -1))
 
     def experts_diversity_loss(self, expert_outputs):
         """competesmoe.py:330-372 on [T, K, D]."""
